@@ -1,0 +1,130 @@
+/* rat_b200.h -- C ABI of librat_b200.so: the B200 (sm_100a) hot path of RAT (WWW'24) retrieval-augmented CTR.
+ *
+ * Boundary contract:
+ *   - plain C, raw DEVICE pointers + explicit sizes; no torch types.  All float tensors are fp32, contiguous,
+ *     row-major; ids are int32; every pointer must be 16-byte aligned (torch CUDA allocations are).
+ *   - the library never allocates or frees user-visible memory; scratch comes from caller-provided workspaces
+ *     whose size is returned by the matching *_workspace_bytes() query.
+ *   - every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*); no hidden synchronisation.
+ *   - return value: 0 = RAT_OK, negative = error (RAT_EINVAL -1, RAT_ECUDA -2, RAT_ESMEM -3); the message is
+ *     available from rat_last_error().  No exceptions, no exit().
+ *   - there is NO CPU fallback: on a machine without an sm_100 device every entry point fails with RAT_ECUDA.
+ *
+ * Each entry point cites the reference code it replaces (paths relative to the reference repository root;
+ * all of it is eager-PyTorch Python -- the reference has no native code, so this ABI is what a ctypes binding
+ * inside the reference's fuxictr/pytorch/models/base_model.py would bind).
+ */
+#ifndef RAT_B200_H
+#define RAT_B200_H
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RAT_ABI_VERSION 1
+
+const char* rat_last_error(void);
+int rat_abi_version(void);
+/* 0 if an sm_100 device is current, else RAT_ECUDA (the product path refuses to run anywhere else) */
+int rat_device_check(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K0: batch assembly
+ * ------------------------------------------------------------------------------------------------------- */
+/* Wire-format conversion.  Replaces BaseModel.inputs_to_device (fuxictr/pytorch/models/base_model.py:125-133)
+ * + the `.long()` casts of EmbeddingDictLayer.forward (fuxictr/pytorch/layers/embedding.py:166,169) and the
+ * token=2 construction (fuxictr/pytorch/models/RAT_m2.py:115-123).
+ * X [B,T,L] f64 ids, y [B,T] f64 labels (row 0 = target) -> ids [B,T,L] i32, labels [B,T] i32 (labels[:,0]=2),
+ * y_true [B] f32. */
+int rat_convert_wire_f64(const double* X, const double* y, int* ids, int* labels, float* y_true, int B, int T, int L,
+                         void* stream);
+
+/* Device-resident retrieval-set assembly.  Replaces Dataset.__getitem__ + default collate
+ * (fuxictr/pytorch/data_generator.py:66-78): ids[b,0,:] = q_ids[rows[b]], ids[b,1+k,:] = pool_ids[nbr[rows[b],k]]
+ * with numpy negative-index wraparound (-1 -> last pool row).  rows == NULL means rows[b] = row0 + b.
+ * err_flag (device int, caller-zeroed) gets bit 1 set on an out-of-range neighbour index. */
+int rat_assemble_ids(const int* q_ids, const unsigned char* q_labels, const long long* rows, long long row0,
+                     const int* pool_ids, const unsigned char* pool_labels, const long long* nbr, long long n_pool,
+                     int* ids, int* labels, float* y_true, int B, int T, int L, int* err_flag, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K1: fused FeatureEmbedding gather
+ * ------------------------------------------------------------------------------------------------------- */
+/* Replaces EmbeddingLayer/EmbeddingDictLayer.forward + dict2tensor (fuxictr/pytorch/layers/embedding.py:40-43,
+ * 138-178), MaskedSumPooling (layers/sequence.py:36-38), the label embedding + 3 concats (models/RAT_m2.py:
+ * 117-126), nn.Dropout(emb_dropout) (RAT_m2.py:135) and LR_Layer.forward (layers/shallow.py:36-45).
+ * emb_W [V_total,D] / lr_W [V_total] are the per-field tables concatenated in field order; col_off[l] is the first
+ * row of column l's table, col_vocab[l] its vocab size; field f spans columns [field_col0[f], +field_width[f]).
+ * Outputs: block [B,T,F+1,D] (dropout applied iff drop_p>0), x_emb [B,F*D] (target row, never dropped; may be
+ * NULL), lr_out [B] (may be NULL together with lr_W).  err_flag bit 0: id out of vocabulary, bit 2: bad label. */
+int rat_gather_fwd(const float* emb_W, const float* lr_W, const float* label_W, const int* ids, const int* labels,
+                   const int* col_off, const int* col_vocab, const int* field_col0, const int* field_width,
+                   float* block, float* x_emb, float* lr_out, int B, int T, int L, int F, int D, float drop_p,
+                   unsigned long long seed, unsigned int rng_stream, int* err_flag, void* stream);
+/* backward of the embedding dropout: grad *= mask/(1-p), same philox mask as rat_gather_fwd */
+int rat_dropout_bwd(float* grad, long long n, float p, unsigned long long seed, unsigned int rng_stream,
+                    void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K2: fused RAT block (forward)
+ * ------------------------------------------------------------------------------------------------------- */
+/* out = res + alpha * (MHA(LayerNorm(x)) Wo^T + bo) on a [B,T,N,D] tensor.  mode 0 ("intra"): sequences are the
+ * B*T rows of N tokens; mode 1 ("cross"): sequences are the B*N columns of T tokens (the reference's
+ * reshape/transpose/flatten, RAT_m2.py:221-235, becomes index arithmetic).  Replaces PreNorm (RAT_m2.py:155-161)
+ * + Attention (RAT_m2.py:176-202; RAT_m3.py:164-196 when Wq/Wk/Wv are separate tensors) + the residual add.
+ * Wq/Wk/Wv [heads*dim_head, D], Wo [D, heads*dim_head], bo [D].  res may be NULL (RAT_m3), alpha scales the
+ * attention branch (0.5 for RAT_m3's mean of the two branches). x, res and out may alias each other only if
+ * res == x == out is NOT used (out must not alias x). */
+int rat_attn_fwd(const float* x, const float* res, float* out, const float* ln_w, const float* ln_b,
+                 const float* Wq, const float* Wk, const float* Wv, const float* Wo, const float* bo, int B, int T,
+                 int N, int D, int heads, int dim_head, float scale, float alpha, int mode, void* stream);
+/* out = res + W2 gelu_erf(W1 LNopt(x) + b1) + b2 over `rows` tokens.  Replaces FeedForward (RAT_m2.py:163-174);
+ * ln_w/ln_b non-NULL adds the PreNorm of RAT_m0.py:197-201.  W1 [M,D], W2 [D,M]. */
+int rat_ff_fwd(const float* x, const float* res, float* out, const float* ln_w, const float* ln_b, const float* W1,
+               const float* b1, const float* W2, const float* b2, long long rows, int D, int M, void* stream);
+/* out = LayerNorm(x) (eps 1e-5).  Final norm of the RAT_m0/m1 Transformer (RAT_m0.py:202,208). */
+int rat_layernorm_fwd(const float* x, float* out, const float* w, const float* b, long long rows, int D,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K3/K4: DNN head, BatchNorm, loss
+ * ------------------------------------------------------------------------------------------------------- */
+/* C[M,N] = opA(A) opB(B) (+bias[n]).  trans_a=0: A[m*lda+k], 1: A[k*lda+m]; trans_b=0: B[n*ldb+k] (torch Linear
+ * weight), 1: B[k*ldb+n].  Replaces the nn.Linear calls of MLP_Layer (layers/deep.py:126,137) and their
+ * autograd backward.  Deterministic split-K when a workspace of rat_sgemm_workspace_bytes() is supplied. */
+size_t rat_sgemm_workspace_bytes(int M, int N, int K);
+int rat_sgemm(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda, int ldb,
+              int ldc, int trans_a, int trans_b, float* workspace, size_t workspace_bytes, void* stream);
+/* BatchNorm1d (layers/deep.py:128-129), train mode: raw per-column sums (double, [2C]: sum, sum of squares) so a
+ * data-parallel caller can all-reduce them, then mean/rstd + running-stat update (momentum 0.1, unbiased var). */
+int rat_bn_sums(const float* z, int rows, int C, double* sums, void* stream);
+int rat_bn_finalize(const double* sums, double count, int C, float* mean, float* rstd, float* running_mean,
+                    float* running_var, float momentum, float eps, void* stream);
+int rat_bn_eval_stats(const float* running_mean, const float* running_var, int C, float* mean, float* rstd,
+                      float eps, void* stream);
+/* out = dropout(relu(bn(z))) ; mean==NULL skips the normalisation (batch_norm: false). */
+int rat_bn_act_fwd(const float* z, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                   float* out, int rows, int C, float drop_p, unsigned long long seed, unsigned int rng_stream,
+                   void* stream);
+int rat_bn_act_bwd_sums(const float* dout, const float* out, const float* z, const float* mean, const float* rstd,
+                        int rows, int C, float drop_p, unsigned long long seed, unsigned int rng_stream, double* sums,
+                        void* stream);
+int rat_bn_act_bwd_apply(const float* dout, const float* out, const float* z, const float* mean, const float* rstd,
+                         const float* gamma, const double* sums, double count, float* dz, float* dgamma,
+                         float* dbeta, int rows, int C, float drop_p, unsigned long long seed,
+                         unsigned int rng_stream, void* stream);
+int rat_colsum(const float* A, int rows, int C, int lda, float* out, void* stream);
+/* logit = fc(enc[b,0,0,:]) + dnn_out[b] + lr_out[b]; y_pred = sigmoid; BCE(mean, log clamp -100) and, when dlogit
+ * is non-NULL, dlogit[b] = dBCE/dlogit * inv_count and denc[b,0,0,:] = dlogit[b]*fc_w (denc pre-zeroed by the
+ * caller).  Replaces RAT_m2.py:138-150 + BaseModel.add_loss (base_model.py:74-77).  loss_part: double
+ * [rat_head_blocks(B)] scratch. */
+int rat_head_blocks(int B);
+int rat_head(const float* enc, long long enc_stride, const float* fc_w, const float* fc_b, const float* dnn_out,
+             const float* lr_out, const float* y_true, int B, int D, float* y_pred, float* dlogit, float* denc,
+             float inv_count, double* loss_part, float* loss_sum, float* loss_mean, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAT_B200_H */

@@ -1,0 +1,57 @@
+"""Helpers for the -m gpu parity tests (CUDA path called through the C ABI, oracle as checker)."""
+import numpy as np
+import torch
+
+from oracle import rat_oracle as O
+from rat_native.engine import EngineSpec, FeatureSpec, RatEngine
+
+
+def to_engine_spec(spec: O.ModelSpec, **over) -> EngineSpec:
+    feats = [FeatureSpec(f.name, f.type, f.vocab_size, f.max_len, f.padding_idx) for f in spec.features]
+    kw = dict(features=feats, model=spec.model, embedding_dim=spec.embedding_dim, num_heads=spec.num_heads,
+              dim_head=spec.dim_head, scale_dim=spec.scale_dim, depth=spec.depth,
+              dnn_hidden_units=tuple(spec.dnn_hidden_units), batch_norm=spec.batch_norm, use_wide=spec.use_wide,
+              emb_dropout=spec.emb_dropout, net_dropout=spec.net_dropout,
+              embedding_regularizer=spec.embedding_regularizer, net_regularizer=spec.net_regularizer,
+              learning_rate=spec.learning_rate, max_gradient_norm=spec.max_gradient_norm)
+    kw.update(over)
+    return EngineSpec(**kw)
+
+
+def make_engine(spec: O.ModelSpec, params, bufs=None, **over) -> RatEngine:
+    eng = RatEngine(to_engine_spec(spec, **over), "cuda:0")
+    sd = dict(params)
+    if bufs:
+        sd.update(bufs)
+    eng.load_params(sd)
+    return eng
+
+
+def assert_close(name, got, want, rtol, atol):
+    got = got.detach().float().cpu().numpy() if torch.is_tensor(got) else np.asarray(got)
+    want = want.detach().float().cpu().numpy() if torch.is_tensor(want) else np.asarray(want)
+    assert got.shape == want.shape, f"{name}: shape {got.shape} vs {want.shape}"
+    err = np.abs(got - want)
+    tol = atol + rtol * np.abs(want)
+    bad = err > tol
+    if bad.any() or not np.isfinite(got).all():
+        i = np.unravel_index(np.argmax(err - tol), err.shape)
+        raise AssertionError(f"{name}: {int(bad.sum())}/{bad.size} mismatches, max abs err {err.max():.3e} "
+                             f"(at {i}: got {got[i]:.6e} want {want[i]:.6e}), max |want| {np.abs(want).max():.3e}, "
+                             f"finite={np.isfinite(got).all()}")
+
+
+def rand_params_nontrivial(spec: O.ModelSpec, seed=0):
+    """oracle params with non-degenerate embeddings / biases / LayerNorm affine (init values are ~0 / 1)."""
+    p = O.init_params(spec, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    for k, v in p.items():
+        if k.startswith("query_proj"):
+            continue
+        if "embedding_layer.embedding_layer" in k:
+            pad_zero = (v.abs().sum(1) == 0)
+            v.mul_(3000.0 if v.shape[1] > 1 else 1000.0)
+            v[pad_zero] = 0
+        elif k.endswith(".bias") or "norm.weight" in k or (".dnn." in k and v.ndim == 1):
+            v.add_(0.1 * torch.randn(v.shape, generator=g))
+    return p

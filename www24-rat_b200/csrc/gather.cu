@@ -1,0 +1,212 @@
+// K0/K1: retrieval-set assembly + fused FeatureEmbedding gather.
+//
+// Replaces (reference, /root/reference): Dataset.__getitem__ fuxictr/pytorch/data_generator.py:66-78,
+// BaseModel.inputs_to_device base_model.py:125-133, EmbeddingDictLayer.forward embedding.py:158-178,
+// MaskedSumPooling sequence.py:36-38, the label-token concat RAT_m2.py:115-126, nn.Dropout RAT_m2.py:135
+// and LR_Layer.forward shallow.py:36-45 -- in ONE pass over the output block.
+#include "common.cuh"
+#include "../../include/rat_b200.h"
+
+namespace rat {
+
+// ---- K0a: wire format (float64 ids/labels from the reference DataLoader) -> int32 ------------------------
+__global__ void k_convert_wire(const double* __restrict__ X, const double* __restrict__ y, int* __restrict__ ids,
+                               int* __restrict__ labels, float* __restrict__ y_true, int B, int T, int L) {
+    long long n_ids = (long long)B * T * L;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_ids; i += stride)
+        ids[i] = (int)X[i];                                   // .long() truncation, embedding.py:166
+    long long n_lab = (long long)B * T;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_lab; i += stride) {
+        int t = (int)(i % T);
+        double v = y[i];
+        labels[i] = (t == 0) ? 2 : (int)v;                    // token=2 for the target row, RAT_m2.py:115-123
+        if (t == 0) y_true[i / T] = (float)v;                 // y.float(), base_model.py:128
+    }
+}
+
+// ---- K0b: device-resident assembly: pool[retr_indices[i]] with numpy negative-index wraparound ----------
+__global__ void k_assemble(const int* __restrict__ q_ids, const unsigned char* __restrict__ q_labels,
+                           const long long* __restrict__ rows, long long row0, const int* __restrict__ pool_ids,
+                           const unsigned char* __restrict__ pool_labels, const long long* __restrict__ nbr,
+                           long long n_pool, int* __restrict__ ids, int* __restrict__ labels,
+                           float* __restrict__ y_true, int B, int T, int L, int* __restrict__ err) {
+    long long total = (long long)B * T * (L + 1);
+    long long stride = (long long)gridDim.x * blockDim.x;
+    const int K = T - 1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        int l = (int)(i % (L + 1));
+        long long bt = i / (L + 1);
+        int t = (int)(bt % T);
+        long long b = bt / T;
+        long long r = rows ? rows[b] : row0 + b;
+        if (t == 0) {
+            if (l < L) ids[bt * L + l] = q_ids[r * L + l];
+            else { labels[bt] = 2; y_true[b] = (float)q_labels[r]; }
+        } else {
+            long long j = nbr[r * K + (t - 1)];
+            if (j < 0) j += n_pool;                           // numpy fancy-index wrap: -1 -> last pool row
+            if (j < 0 || j >= n_pool) { atomicOr(err, 2); j = 0; }
+            if (l < L) ids[bt * L + l] = pool_ids[j * L + l];
+            else labels[bt] = (int)pool_labels[j];
+        }
+    }
+}
+
+// ---- K1: fused gather -> block [B,T,N,D], x_emb [B,F*D], lr_out [B] -------------------------------------
+template <int VW> struct Vec;
+template <> struct Vec<4> { typedef float4 T; };
+template <> struct Vec<2> { typedef float2 T; };
+template <> struct Vec<1> { typedef float T; };
+
+template <int VW>
+__device__ __forceinline__ void vload(const float* p, float (&v)[VW]) {
+    typename Vec<VW>::T t = __ldg(reinterpret_cast<const typename Vec<VW>::T*>(p));
+    const float* f = reinterpret_cast<const float*>(&t);
+#pragma unroll
+    for (int i = 0; i < VW; ++i) v[i] = f[i];
+}
+template <int VW>
+__device__ __forceinline__ void vstore(float* p, const float (&v)[VW]) {
+    typename Vec<VW>::T t;
+    float* f = reinterpret_cast<float*>(&t);
+#pragma unroll
+    for (int i = 0; i < VW; ++i) f[i] = v[i];
+    *reinterpret_cast<typename Vec<VW>::T*>(p) = t;
+}
+
+struct GatherArgs {
+    const float* emb_W; const float* lr_W; const float* label_W;
+    const int* ids; const int* labels;
+    const int* col_off; const int* col_vocab; const int* field_col0; const int* field_width;
+    float* block; float* x_emb; float* lr_out;
+    int B, T, L, F, D;
+    float drop_p; unsigned long long seed; unsigned int stream;
+    int* err;
+};
+
+template <int VW>
+__global__ void __launch_bounds__(256) k_gather(GatherArgs a) {
+    const int N = a.F + 1, DV = a.D / VW;
+    const long long total = (long long)a.B * a.T * N * DV;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const float inv_keep = a.drop_p > 0.f ? 1.0f / (1.0f - a.drop_p) : 1.0f;
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += stride) {
+        const int dv = (int)(v % DV);
+        const int n = (int)((v / DV) % N);
+        const long long bt = v / ((long long)DV * N);
+        const int t = (int)(bt % a.T);
+        const long long b = bt / a.T;
+        float val[VW];
+        if (n == 0) {
+            int lab = a.labels[bt];
+            if (lab < 0 || lab > 2) { atomicOr(a.err, 4); lab = 0; }
+            vload<VW>(a.label_W + (long long)lab * a.D + dv * VW, val);
+            if (t == 0 && dv == 0 && a.lr_out) {
+                // LR_Layer: per field (sequence: sum of its columns) then sum over fields, shallow.py:37-38
+                float tot = 0.f;
+                for (int f = 0; f < a.F; ++f) {
+                    int c0 = a.field_col0[f], w = a.field_width[f];
+                    float s = 0.f;
+                    for (int j = 0; j < w; ++j) {
+                        int id = a.ids[bt * a.L + c0 + j];
+                        if (id < 0 || id >= a.col_vocab[c0 + j]) id = 0;
+                        s += __ldg(a.lr_W + a.col_off[c0 + j] + id);
+                    }
+                    tot += s;
+                }
+                a.lr_out[b] = tot;
+            }
+        } else {
+            const int f = n - 1;
+            const int c0 = a.field_col0[f], w = a.field_width[f];
+#pragma unroll
+            for (int i = 0; i < VW; ++i) val[i] = 0.f;
+            for (int j = 0; j < w; ++j) {
+                int id = a.ids[bt * a.L + c0 + j];
+                if (id < 0 || id >= a.col_vocab[c0 + j]) { atomicOr(a.err, 1); id = 0; }
+                float r[VW];
+                vload<VW>(a.emb_W + ((long long)a.col_off[c0 + j] + id) * a.D + dv * VW, r);
+#pragma unroll
+                for (int i = 0; i < VW; ++i) val[i] = (j == 0) ? r[i] : val[i] + r[i];   // left-to-right sum-pool
+            }
+            if (t == 0 && a.x_emb)                           // X_emb: target row, never dropped out (RAT_m2.py:120)
+                vstore<VW>(a.x_emb + (b * a.F + f) * a.D + dv * VW, val);
+        }
+        if (a.drop_p > 0.f) {
+            const unsigned long long e0 = (unsigned long long)v * VW;
+#pragma unroll
+            for (int i = 0; i < VW; ++i) val[i] *= dropout_scale(a.seed, a.stream, e0 + i, a.drop_p, inv_keep);
+        }
+        vstore<VW>(a.block + v * VW, val);
+    }
+}
+
+// in-place dropout backward on the block gradient (same mask as k_gather)
+__global__ void k_dropout_bwd(float* __restrict__ g, long long n, float p, unsigned long long seed,
+                              unsigned int stream) {
+    const float inv_keep = 1.0f / (1.0f - p);
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride)
+        g[e] *= dropout_scale(seed, stream, (unsigned long long)e, p, inv_keep);
+}
+
+static int grid_for(long long total, int block) {
+    long long g = (total + block - 1) / block;
+    long long cap = (long long)num_sms() * 32;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace rat
+
+using namespace rat;
+
+extern "C" int rat_convert_wire_f64(const double* X, const double* y, int* ids, int* labels, float* y_true, int B,
+                                    int T, int L, void* stream) {
+    RAT_REQUIRE(B > 0 && T > 0 && L > 0, "rat_convert_wire_f64: bad shape B=%d T=%d L=%d", B, T, L);
+    k_convert_wire<<<grid_for((long long)B * T * L, 256), 256, 0, (cudaStream_t)stream>>>(X, y, ids, labels, y_true,
+                                                                                          B, T, L);
+    RAT_CHECK_LAUNCH("k_convert_wire");
+    return RAT_OK;
+}
+
+extern "C" int rat_assemble_ids(const int* q_ids, const unsigned char* q_labels, const long long* rows,
+                                long long row0, const int* pool_ids, const unsigned char* pool_labels,
+                                const long long* nbr, long long n_pool, int* ids, int* labels, float* y_true, int B,
+                                int T, int L, int* err_flag, void* stream) {
+    RAT_REQUIRE(B > 0 && T > 0 && L > 0 && n_pool > 0, "rat_assemble_ids: bad shape");
+    k_assemble<<<grid_for((long long)B * T * (L + 1), 256), 256, 0, (cudaStream_t)stream>>>(
+        q_ids, q_labels, rows, row0, pool_ids, pool_labels, nbr, n_pool, ids, labels, y_true, B, T, L, err_flag);
+    RAT_CHECK_LAUNCH("k_assemble");
+    return RAT_OK;
+}
+
+extern "C" int rat_gather_fwd(const float* emb_W, const float* lr_W, const float* label_W, const int* ids,
+                              const int* labels, const int* col_off, const int* col_vocab, const int* field_col0,
+                              const int* field_width, float* block, float* x_emb, float* lr_out, int B, int T, int L,
+                              int F, int D, float drop_p, unsigned long long seed, unsigned int rng_stream,
+                              int* err_flag, void* stream) {
+    RAT_REQUIRE(B > 0 && T > 0 && L > 0 && F > 0 && D > 0, "rat_gather_fwd: bad shape");
+    RAT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "rat_gather_fwd: dropout p=%f", drop_p);
+    GatherArgs a{emb_W, lr_W, label_W, ids, labels, col_off, col_vocab, field_col0, field_width,
+                 block, x_emb, lr_out, B, T, L, F, D, drop_p, seed, rng_stream, err_flag};
+    const int vw = (D % 4 == 0) ? 4 : (D % 2 == 0) ? 2 : 1;
+    long long total = (long long)B * T * (F + 1) * (D / vw);
+    int grid = grid_for(total, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (vw == 4) k_gather<4><<<grid, 256, 0, st>>>(a);
+    else if (vw == 2) k_gather<2><<<grid, 256, 0, st>>>(a);
+    else k_gather<1><<<grid, 256, 0, st>>>(a);
+    RAT_CHECK_LAUNCH("k_gather");
+    return RAT_OK;
+}
+
+extern "C" int rat_dropout_bwd(float* grad, long long n, float p, unsigned long long seed, unsigned int rng_stream,
+                               void* stream) {
+    if (p <= 0.f) return RAT_OK;
+    k_dropout_bwd<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(grad, n, p, seed, rng_stream);
+    RAT_CHECK_LAUNCH("k_dropout_bwd");
+    return RAT_OK;
+}

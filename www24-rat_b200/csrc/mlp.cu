@@ -1,0 +1,375 @@
+// K3/K4: DNN head (MLP_Layer fuxictr/pytorch/layers/deep.py:108-141), BatchNorm1d, ReLU, dropout,
+// fc + LR + sigmoid + BCE (RAT_m2.py:144-150, base_model.py:74-77) and their backward.
+//
+// Round-1 implementation: fp32 SIMT shared-memory-tiled GEMM (exact fp32 parity anchor).  The tcgen05/TMEM
+// bf16 variant of the same entry point is planned on top of this (see DESIGN.md "K3").
+#include "common.cuh"
+#include "../../include/rat_b200.h"
+
+namespace rat {
+
+// C[m][n] = sum_k opA(m,k) * opB(k,n) (+ bias[n]) ; opA = TA ? A[k*lda+m] : A[m*lda+k] ; opB = TB ? B[k*ldb+n] : B[n*ldb+k]
+// grid.z = split-K slices (each slice writes its own [M][N] partial at C + z*M*N when gridDim.z > 1).
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) k_sgemm(const float* __restrict__ A, const float* __restrict__ B,
+                                               float* __restrict__ C, const float* __restrict__ bias, int M, int N,
+                                               int K, int lda, int ldb, int ldc, int kchunk) {
+    constexpr int BM = 64, BN = 64, BK = 16;
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN + 4];
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int kbeg = blockIdx.z * kchunk, kend = min(K, kbeg + kchunk);
+    const int tid = threadIdx.x;
+    const int tm = (tid / 16) * 4, tn = (tid % 16) * 4;
+    float acc[4][4] = {};
+    for (int k0 = kbeg; k0 < kend; k0 += BK) {
+        // ---- load tiles (bounds-checked scalar loads; coalesced along the contiguous axis of each operand)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int e = tid + i * 256;                       // 0..1023
+            if (!TA) { int k = e % BK, m = e / BK; int gm = m0 + m, gk = k0 + k;
+                       As[k][m] = (gm < M && gk < kend) ? A[(size_t)gm * lda + gk] : 0.f; }
+            else     { int m = e % BM, k = e / BM; int gm = m0 + m, gk = k0 + k;
+                       As[k][m] = (gm < M && gk < kend) ? A[(size_t)gk * lda + gm] : 0.f; }
+            if (!TB) { int k = e % BK, n = e / BK; int gn = n0 + n, gk = k0 + k;
+                       Bs[k][n] = (gn < N && gk < kend) ? B[(size_t)gn * ldb + gk] : 0.f; }
+            else     { int n = e % BN, k = e / BN; int gn = n0 + n, gk = k0 + k;
+                       Bs[k][n] = (gn < N && gk < kend) ? B[(size_t)gk * ldb + gn] : 0.f; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[k][tm]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tn]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float* Cz = C + (gridDim.z > 1 ? (size_t)blockIdx.z * M * ldc : 0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gm = m0 + tm + i;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gn = n0 + tn + j;
+            if (gn < N) Cz[(size_t)gm * ldc + gn] = acc[i][j] + ((bias && gridDim.z == 1) ? bias[gn] : 0.f);
+        }
+    }
+}
+
+__global__ void k_splitk_reduce(const float* __restrict__ part, float* __restrict__ C, const float* __restrict__ bias,
+                                int M, int N, int ldc, int splits) {
+    const long long total = (long long)M * N;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int m = (int)(i / N), n = (int)(i % N);
+        float s = 0.f;
+        for (int z = 0; z < splits; ++z) s += part[((size_t)z * M + m) * N + n];   // fixed order: deterministic
+        C[(size_t)m * ldc + n] = s + (bias ? bias[n] : 0.f);
+    }
+}
+
+// ---- BatchNorm1d -----------------------------------------------------------------------------------------
+// per-column sums in double: sums[c] = sum_b z[b][c], sums[C + c] = sum_b z[b][c]^2 (raw sums so that the
+// data-parallel path can all-reduce them = SyncBN-equivalent to the single-device reference at global batch)
+__global__ void __launch_bounds__(256) k_bn_sums(const float* __restrict__ z, int Bn, int C, double* __restrict__ sums) {
+    __shared__ double s1[8][32], s2[8][32];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int rg = threadIdx.x >> 5;
+    double a = 0.0, b = 0.0;
+    if (c < C)
+        for (int r = rg; r < Bn; r += 8) { const double v = z[(size_t)r * C + c]; a += v; b += v * v; }
+    s1[rg][threadIdx.x & 31] = a; s2[rg][threadIdx.x & 31] = b;
+    __syncthreads();
+    if (rg == 0 && c < C) {
+        for (int i = 1; i < 8; ++i) { a += s1[i][threadIdx.x]; b += s2[i][threadIdx.x]; }
+        sums[c] = a; sums[C + c] = b;
+    }
+}
+// mean / rstd from (all-reduced) sums; running stats update (momentum 0.1, unbiased var), deep.py:128-129
+__global__ void k_bn_finalize(const double* __restrict__ sums, double count, int C, float* __restrict__ mean,
+                              float* __restrict__ rstd, float* __restrict__ running_mean,
+                              float* __restrict__ running_var, float momentum, float eps) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double m = sums[c] / count;
+    double var = sums[C + c] / count - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[c] = (float)m;
+    rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) {
+        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+}
+__global__ void k_bn_eval_stats(const float* __restrict__ running_mean, const float* __restrict__ running_var, int C,
+                                float* __restrict__ mean, float* __restrict__ rstd, float eps) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    mean[c] = running_mean[c];
+    rstd[c] = 1.0f / sqrtf(running_var[c] + eps);
+}
+// out = dropout(relu(bn(z)))  (bn optional: mean == nullptr -> out = dropout(relu(z)))
+__global__ void k_bn_act_fwd(const float* __restrict__ z, const float* __restrict__ mean,
+                             const float* __restrict__ rstd, const float* __restrict__ gamma,
+                             const float* __restrict__ beta, float* __restrict__ out, long long total, int C,
+                             float drop_p, unsigned long long seed, unsigned int stream) {
+    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        float v = z[i];
+        if (mean) v = (v - mean[c]) * rstd[c] * gamma[c] + beta[c];
+        v = fmaxf(v, 0.f);
+        if (drop_p > 0.f) v *= dropout_scale(seed, stream, (unsigned long long)i, drop_p, inv_keep);
+        out[i] = v;
+    }
+}
+// backward pass 1: dy = dout * 1[out>0] * dropscale ; sums[c] = sum dy ; sums[C+c] = sum dy * xhat
+__global__ void __launch_bounds__(256) k_bn_act_bwd_sums(const float* __restrict__ dout, const float* __restrict__ out,
+                                                         const float* __restrict__ z, const float* __restrict__ mean,
+                                                         const float* __restrict__ rstd, int Bn, int C, float drop_p,
+                                                         unsigned long long seed, unsigned int stream,
+                                                         double* __restrict__ sums) {
+    __shared__ double s1[8][32], s2[8][32];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int rg = threadIdx.x >> 5;
+    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    double a = 0.0, b = 0.0;
+    if (c < C) {
+        const float mu = mean[c], rs = rstd[c];
+        for (int r = rg; r < Bn; r += 8) {
+            const size_t i = (size_t)r * C + c;
+            float dy = out[i] > 0.f ? dout[i] : 0.f;
+            if (drop_p > 0.f) dy *= dropout_scale(seed, stream, (unsigned long long)i, drop_p, inv_keep);
+            a += dy;
+            b += (double)dy * (double)((z[i] - mu) * rs);
+        }
+    }
+    s1[rg][threadIdx.x & 31] = a; s2[rg][threadIdx.x & 31] = b;
+    __syncthreads();
+    if (rg == 0 && c < C) {
+        for (int i = 1; i < 8; ++i) { a += s1[i][threadIdx.x]; b += s2[i][threadIdx.x]; }
+        sums[c] = a; sums[C + c] = b;
+    }
+}
+// backward pass 2: dz = gamma*rstd*(dy - dbeta/count - xhat*dgamma/count)   (or dz = dy without bn);
+// also emits dgamma/dbeta as floats.
+__global__ void k_bn_act_bwd_apply(const float* __restrict__ dout, const float* __restrict__ out,
+                                   const float* __restrict__ z, const float* __restrict__ mean,
+                                   const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                   const double* __restrict__ sums, double count, float* __restrict__ dz,
+                                   float* __restrict__ dgamma, float* __restrict__ dbeta, long long total, int C,
+                                   float drop_p, unsigned long long seed, unsigned int stream) {
+    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        float dy = out[i] > 0.f ? dout[i] : 0.f;
+        if (drop_p > 0.f) dy *= dropout_scale(seed, stream, (unsigned long long)i, drop_p, inv_keep);
+        if (mean) {
+            const float xh = (z[i] - mean[c]) * rstd[c];
+            const float db = (float)(sums[c] / count), dg = (float)(sums[C + c] / count);
+            dz[i] = gamma[c] * rstd[c] * (dy - db - xh * dg);
+            if (i < C) { dgamma[c] = (float)sums[C + c]; dbeta[c] = (float)sums[c]; }
+        } else {
+            dz[i] = dy;
+        }
+    }
+}
+// out[c] = sum_r A[r][c]   (bias gradients), deterministic
+__global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ A, int R, int C, int lda,
+                                                float* __restrict__ out) {
+    __shared__ float s[8][32];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int rg = threadIdx.x >> 5;
+    float a = 0.f;
+    if (c < C) for (int r = rg; r < R; r += 8) a += A[(size_t)r * lda + c];
+    s[rg][threadIdx.x & 31] = a;
+    __syncthreads();
+    if (rg == 0 && c < C) {
+        for (int i = 1; i < 8; ++i) a += s[i][threadIdx.x];
+        out[c] = a;
+    }
+}
+
+// ---- head: logit = fc(enc[b,0,0,:]) + dnn_out + lr ; sigmoid ; BCE ; dlogit ---------------------------------
+// F.binary_cross_entropy clamps log() at -100 and its backward divides by max(y(1-y),1e-12); sigmoid' = y(1-y).
+__global__ void __launch_bounds__(256) k_head(const float* __restrict__ enc, long long enc_stride,
+                                              const float* __restrict__ fc_w, const float* __restrict__ fc_b,
+                                              const float* __restrict__ dnn_out, const float* __restrict__ lr_out,
+                                              const float* __restrict__ y_true, int Bn, int D,
+                                              float* __restrict__ y_pred, float* __restrict__ dlogit,
+                                              float* __restrict__ denc, float inv_count,
+                                              double* __restrict__ loss_part) {
+    __shared__ double red[8];
+    double lsum = 0.0;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < Bn; b += gridDim.x * blockDim.x) {
+        const float* e = enc + (size_t)b * enc_stride;
+        float logit = fc_b[0];
+        for (int d = 0; d < D; ++d) logit = fmaf(e[d], fc_w[d], logit);
+        if (dnn_out) logit += dnn_out[b];
+        if (lr_out) logit += lr_out[b];
+        const float y = 1.0f / (1.0f + expf(-logit));
+        y_pred[b] = y;
+        if (y_true) {
+            const float t = y_true[b];
+            const float l1 = fmaxf(logf(y), -100.f), l0 = fmaxf(logf(1.0f - y), -100.f);
+            lsum += -(double)(t * l1 + (1.0f - t) * l0);
+            if (dlogit) {
+                const float yy = y * (1.0f - y);
+                const float g = (y - t) / fmaxf(yy, 1e-12f) * yy * inv_count;
+                dlogit[b] = g;
+                if (denc) {
+                    float* de = denc + (size_t)b * enc_stride;
+                    for (int d = 0; d < D; ++d) de[d] = g * fc_w[d];
+                }
+            }
+        }
+    }
+    lsum = warp_sum_d(lsum);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lsum;
+    __syncthreads();
+    if (threadIdx.x == 0 && loss_part) {
+        double s = 0.0;
+        for (int i = 0; i < 8; ++i) s += red[i];
+        loss_part[blockIdx.x] = s;
+    }
+}
+__global__ void k_loss_finalize(const double* __restrict__ part, int n, float inv_count, float* __restrict__ loss_sum,
+                                float* __restrict__ loss_mean) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s += part[i];
+        if (loss_sum) loss_sum[0] = (float)s;
+        if (loss_mean) loss_mean[0] = (float)(s * (double)inv_count);
+    }
+}
+
+static int ew_grid(long long total) {
+    long long g = (total + 255) / 256;
+    long long cap = (long long)num_sms() * 16;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace rat
+
+using namespace rat;
+
+extern "C" size_t rat_sgemm_workspace_bytes(int M, int N, int K) {
+    // split-K only pays when the output grid under-fills the machine and K is long
+    int tiles = ceil_div(M, 64) * ceil_div(N, 64);
+    int splits = 1;
+    if (tiles < num_sms() && K >= 512) splits = min(16, max(1, (2 * num_sms()) / tiles));
+    while (splits > 1 && K / splits < 128) --splits;
+    return splits > 1 ? (size_t)splits * M * N * sizeof(float) : 0;
+}
+
+extern "C" int rat_sgemm(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda,
+                         int ldb, int ldc, int trans_a, int trans_b, float* workspace, size_t workspace_bytes,
+                         void* stream) {
+    RAT_REQUIRE(M > 0 && N > 0 && K > 0, "rat_sgemm: bad shape M=%d N=%d K=%d", M, N, K);
+    size_t need = rat_sgemm_workspace_bytes(M, N, K);
+    int splits = 1;
+    if (need > 0 && workspace && workspace_bytes >= need) splits = (int)(need / ((size_t)M * N * sizeof(float)));
+    const int kchunk = round_up(ceil_div(K, splits), 16);
+    splits = ceil_div(K, kchunk);
+    dim3 grid(ceil_div(N, 64), ceil_div(M, 64), splits);
+    cudaStream_t st = (cudaStream_t)stream;
+    float* out = splits > 1 ? workspace : C;
+    const int ldo = splits > 1 ? N : ldc;
+    if (!trans_a && !trans_b) k_sgemm<false, false><<<grid, 256, 0, st>>>(A, B, out, bias, M, N, K, lda, ldb, ldo, kchunk);
+    else if (!trans_a && trans_b) k_sgemm<false, true><<<grid, 256, 0, st>>>(A, B, out, bias, M, N, K, lda, ldb, ldo, kchunk);
+    else if (trans_a && !trans_b) k_sgemm<true, false><<<grid, 256, 0, st>>>(A, B, out, bias, M, N, K, lda, ldb, ldo, kchunk);
+    else k_sgemm<true, true><<<grid, 256, 0, st>>>(A, B, out, bias, M, N, K, lda, ldb, ldo, kchunk);
+    RAT_CHECK_LAUNCH("k_sgemm");
+    if (splits > 1) {
+        k_splitk_reduce<<<ew_grid((long long)M * N), 256, 0, st>>>(workspace, C, bias, M, N, ldc, splits);
+        RAT_CHECK_LAUNCH("k_splitk_reduce");
+    }
+    return RAT_OK;
+}
+
+extern "C" int rat_bn_sums(const float* z, int rows, int C, double* sums, void* stream) {
+    RAT_REQUIRE(rows > 0 && C > 0, "rat_bn_sums: bad shape");
+    k_bn_sums<<<ceil_div(C, 32), 256, 0, (cudaStream_t)stream>>>(z, rows, C, sums);
+    RAT_CHECK_LAUNCH("k_bn_sums");
+    return RAT_OK;
+}
+
+extern "C" int rat_bn_finalize(const double* sums, double count, int C, float* mean, float* rstd,
+                               float* running_mean, float* running_var, float momentum, float eps, void* stream) {
+    k_bn_finalize<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, count, C, mean, rstd, running_mean,
+                                                                      running_var, momentum, eps);
+    RAT_CHECK_LAUNCH("k_bn_finalize");
+    return RAT_OK;
+}
+
+extern "C" int rat_bn_eval_stats(const float* running_mean, const float* running_var, int C, float* mean, float* rstd,
+                                 float eps, void* stream) {
+    k_bn_eval_stats<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(running_mean, running_var, C, mean, rstd, eps);
+    RAT_CHECK_LAUNCH("k_bn_eval_stats");
+    return RAT_OK;
+}
+
+extern "C" int rat_bn_act_fwd(const float* z, const float* mean, const float* rstd, const float* gamma,
+                              const float* beta, float* out, int rows, int C, float drop_p, unsigned long long seed,
+                              unsigned int rng_stream, void* stream) {
+    const long long total = (long long)rows * C;
+    k_bn_act_fwd<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(z, mean, rstd, gamma, beta, out, total, C, drop_p,
+                                                                   seed, rng_stream);
+    RAT_CHECK_LAUNCH("k_bn_act_fwd");
+    return RAT_OK;
+}
+
+extern "C" int rat_bn_act_bwd_sums(const float* dout, const float* out, const float* z, const float* mean,
+                                   const float* rstd, int rows, int C, float drop_p, unsigned long long seed,
+                                   unsigned int rng_stream, double* sums, void* stream) {
+    k_bn_act_bwd_sums<<<ceil_div(C, 32), 256, 0, (cudaStream_t)stream>>>(dout, out, z, mean, rstd, rows, C, drop_p,
+                                                                         seed, rng_stream, sums);
+    RAT_CHECK_LAUNCH("k_bn_act_bwd_sums");
+    return RAT_OK;
+}
+
+extern "C" int rat_bn_act_bwd_apply(const float* dout, const float* out, const float* z, const float* mean,
+                                    const float* rstd, const float* gamma, const double* sums, double count,
+                                    float* dz, float* dgamma, float* dbeta, int rows, int C, float drop_p,
+                                    unsigned long long seed, unsigned int rng_stream, void* stream) {
+    const long long total = (long long)rows * C;
+    k_bn_act_bwd_apply<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(dout, out, z, mean, rstd, gamma, sums, count,
+                                                                         dz, dgamma, dbeta, total, C, drop_p, seed,
+                                                                         rng_stream);
+    RAT_CHECK_LAUNCH("k_bn_act_bwd_apply");
+    return RAT_OK;
+}
+
+extern "C" int rat_colsum(const float* A, int rows, int C, int lda, float* out, void* stream) {
+    k_colsum<<<ceil_div(C, 32), 256, 0, (cudaStream_t)stream>>>(A, rows, C, lda, out);
+    RAT_CHECK_LAUNCH("k_colsum");
+    return RAT_OK;
+}
+
+extern "C" int rat_head_blocks(int B) { return min(ceil_div(B, 256), 1024); }
+
+extern "C" int rat_head(const float* enc, long long enc_stride, const float* fc_w, const float* fc_b,
+                        const float* dnn_out, const float* lr_out, const float* y_true, int B, int D, float* y_pred,
+                        float* dlogit, float* denc, float inv_count, double* loss_part, float* loss_sum,
+                        float* loss_mean, void* stream) {
+    RAT_REQUIRE(B > 0 && D > 0, "rat_head: bad shape");
+    const int grid = rat_head_blocks(B);
+    cudaStream_t st = (cudaStream_t)stream;
+    k_head<<<grid, 256, 0, st>>>(enc, enc_stride, fc_w, fc_b, dnn_out, lr_out, y_true, B, D, y_pred, dlogit, denc,
+                                 inv_count, loss_part);
+    RAT_CHECK_LAUNCH("k_head");
+    if (loss_part && (loss_sum || loss_mean)) {
+        k_loss_finalize<<<1, 32, 0, st>>>(loss_part, grid, 1.0f / (float)B, loss_sum, loss_mean);
+        RAT_CHECK_LAUNCH("k_loss_finalize");
+    }
+    return RAT_OK;
+}

@@ -1,0 +1,149 @@
+// Shared-memory tile primitives used by the fused RAT-block kernels (encoder_fwd.cu / encoder_bwd.cu).
+//
+// All tiles are fp32, row-major, with leading dimensions that are multiples of 4 floats so that every row
+// start is 16-byte aligned for LDS.128.  The per-thread register tile is TM rows x 4 columns; a thread's rows
+// are STRIDED by nrt (= ceil(R/TM)) so that neighbouring threads touch neighbouring rows (no 8*lda bank
+// aliasing, see DESIGN.md "tile_gemm").
+#pragma once
+#include "common.cuh"
+
+namespace rat {
+
+struct EpiNone {
+    __device__ __forceinline__ void operator()(int, int, float4&) const {}
+};
+
+// C[r][c] (+)= sum_k A[r*lda + k] * Bt[k*ldb + c]      r < R, c < Cc (Cc % 4 == 0, padded), k < K
+template <int TM, class Epi>
+__device__ __forceinline__ void tile_gemm(const float* __restrict__ A, int lda, const float* __restrict__ Bt,
+                                          int ldb, float* __restrict__ C, int ldc, int R, int Cc, int K,
+                                          bool accum, Epi epi) {
+    const int nct = Cc >> 2;
+    const int nrt = (R + TM - 1) / TM;
+    const int ntiles = nct * nrt;
+    const int K4 = K & ~3;
+    for (int tile = threadIdx.x; tile < ntiles; tile += blockDim.x) {
+        const int ct = tile % nct, rt = tile / nct;
+        const int c0 = ct << 2;
+        float4 acc[TM];
+        const float* ap[TM];
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            int r = rt + i * nrt;
+            ap[i] = A + (size_t)(r < R ? r : R - 1) * lda;
+        }
+        const float* bp = Bt + c0;
+#pragma unroll 2
+        for (int k = 0; k < K4; k += 4) {
+            const float4 b0 = *reinterpret_cast<const float4*>(bp + (size_t)(k + 0) * ldb);
+            const float4 b1 = *reinterpret_cast<const float4*>(bp + (size_t)(k + 1) * ldb);
+            const float4 b2 = *reinterpret_cast<const float4*>(bp + (size_t)(k + 2) * ldb);
+            const float4 b3 = *reinterpret_cast<const float4*>(bp + (size_t)(k + 3) * ldb);
+#pragma unroll
+            for (int i = 0; i < TM; ++i) {
+                const float4 a = *reinterpret_cast<const float4*>(ap[i] + k);
+                acc[i].x = fmaf(a.x, b0.x, acc[i].x); acc[i].y = fmaf(a.x, b0.y, acc[i].y);
+                acc[i].z = fmaf(a.x, b0.z, acc[i].z); acc[i].w = fmaf(a.x, b0.w, acc[i].w);
+                acc[i].x = fmaf(a.y, b1.x, acc[i].x); acc[i].y = fmaf(a.y, b1.y, acc[i].y);
+                acc[i].z = fmaf(a.y, b1.z, acc[i].z); acc[i].w = fmaf(a.y, b1.w, acc[i].w);
+                acc[i].x = fmaf(a.z, b2.x, acc[i].x); acc[i].y = fmaf(a.z, b2.y, acc[i].y);
+                acc[i].z = fmaf(a.z, b2.z, acc[i].z); acc[i].w = fmaf(a.z, b2.w, acc[i].w);
+                acc[i].x = fmaf(a.w, b3.x, acc[i].x); acc[i].y = fmaf(a.w, b3.y, acc[i].y);
+                acc[i].z = fmaf(a.w, b3.z, acc[i].z); acc[i].w = fmaf(a.w, b3.w, acc[i].w);
+            }
+        }
+        for (int k = K4; k < K; ++k) {
+            const float4 b = *reinterpret_cast<const float4*>(bp + (size_t)k * ldb);
+#pragma unroll
+            for (int i = 0; i < TM; ++i) {
+                const float a = ap[i][k];
+                acc[i].x = fmaf(a, b.x, acc[i].x); acc[i].y = fmaf(a, b.y, acc[i].y);
+                acc[i].z = fmaf(a, b.z, acc[i].z); acc[i].w = fmaf(a, b.w, acc[i].w);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            const int r = rt + i * nrt;
+            if (r < R) {
+                float4* cp = reinterpret_cast<float4*>(C + (size_t)r * ldc + c0);
+                float4 v = acc[i];
+                if (accum) { const float4 o = *cp; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                epi(r, c0, v);
+                *cp = v;
+            }
+        }
+    }
+}
+
+// G[i][j] += sum_r A[r*lda + i] * B[r*ldb + j]     i < Ka (Ka%4==0 padded), j < Kb (Kb%4==0 padded), r < R
+// "TN" product used for weight gradients; the 4x4 register tile is accumulated into the CTA-private
+// shared-memory gradient accumulator G (each (i,j) is owned by exactly one thread: no atomics).
+__device__ __forceinline__ void tile_gemm_tn_acc(const float* __restrict__ A, int lda, const float* __restrict__ B,
+                                                 int ldb, float* __restrict__ G, int ldg, int R, int Ka, int Kb) {
+    const int na = Ka >> 2, nb = Kb >> 2;
+    const int ntiles = na * nb;
+    for (int tile = threadIdx.x; tile < ntiles; tile += blockDim.x) {
+        const int jb = tile % nb, ia = tile / nb;
+        const float* ap = A + (ia << 2);
+        const float* bp = B + (jb << 2);
+        float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0, acc2 = acc0, acc3 = acc0;
+#pragma unroll 4
+        for (int r = 0; r < R; ++r) {
+            const float4 a = *reinterpret_cast<const float4*>(ap + (size_t)r * lda);
+            const float4 b = *reinterpret_cast<const float4*>(bp + (size_t)r * ldb);
+            acc0.x = fmaf(a.x, b.x, acc0.x); acc0.y = fmaf(a.x, b.y, acc0.y);
+            acc0.z = fmaf(a.x, b.z, acc0.z); acc0.w = fmaf(a.x, b.w, acc0.w);
+            acc1.x = fmaf(a.y, b.x, acc1.x); acc1.y = fmaf(a.y, b.y, acc1.y);
+            acc1.z = fmaf(a.y, b.z, acc1.z); acc1.w = fmaf(a.y, b.w, acc1.w);
+            acc2.x = fmaf(a.z, b.x, acc2.x); acc2.y = fmaf(a.z, b.y, acc2.y);
+            acc2.z = fmaf(a.z, b.z, acc2.z); acc2.w = fmaf(a.z, b.w, acc2.w);
+            acc3.x = fmaf(a.w, b.x, acc3.x); acc3.y = fmaf(a.w, b.y, acc3.y);
+            acc3.z = fmaf(a.w, b.z, acc3.z); acc3.w = fmaf(a.w, b.w, acc3.w);
+        }
+        float4* g = reinterpret_cast<float4*>(G + (size_t)(ia << 2) * ldg + (jb << 2));
+        const int s = ldg >> 2;
+        float4 t;
+        t = g[0];     t.x += acc0.x; t.y += acc0.y; t.z += acc0.z; t.w += acc0.w; g[0] = t;
+        t = g[s];     t.x += acc1.x; t.y += acc1.y; t.z += acc1.z; t.w += acc1.w; g[s] = t;
+        t = g[2 * s]; t.x += acc2.x; t.y += acc2.y; t.z += acc2.z; t.w += acc2.w; g[2 * s] = t;
+        t = g[3 * s]; t.x += acc3.x; t.y += acc3.y; t.z += acc3.z; t.w += acc3.w; g[3 * s] = t;
+    }
+}
+
+// column sums: gsum[c] += sum_r A[r*lda + c]   (bias / LayerNorm-beta gradients)
+__device__ __forceinline__ void tile_colsum_acc(const float* __restrict__ A, int lda, float* __restrict__ gsum,
+                                                int R, int Cc) {
+    for (int c = threadIdx.x; c < Cc; c += blockDim.x) {
+        float s = 0.f;
+        for (int r = 0; r < R; ++r) s += A[(size_t)r * lda + c];
+        gsum[c] += s;
+    }
+}
+
+// sequence geometry: local row (ls, p) of a tile that starts at sequence s0
+struct SeqGeom {
+    int S;          // positions per sequence
+    int mode;       // 0: sequence = (b,t), rows contiguous ; 1: sequence = (b,n), rows strided by N
+    int T, N;
+    __device__ __forceinline__ long long grow(long long s, int p) const {
+        if (mode == 0) return s * S + p;
+        long long b = s / N;
+        int n = (int)(s - b * N);
+        return b * (long long)T * N + (long long)p * N + n;
+    }
+};
+
+__device__ __forceinline__ float group_sum(float v, int lg) {
+    for (int o = lg >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+    return cdf + x * pdf;
+}
+
+}  // namespace rat

@@ -1,0 +1,444 @@
+"""Host-side engine of the RAT hot path: owns the flat parameter / gradient / Adam-state buffers in HBM and
+sequences the C-ABI kernels of librat_b200.so for one forward, or one full training step.
+
+PyTorch is used for device memory, streams and (data-parallel) torch.distributed plumbing only; every
+arithmetic step of the path is a kernel of librat_b200.so.  There is no CPU / eager fallback.
+
+HBM layout (DESIGN.md "Data layout"): ONE fp32 buffer `W` holds every parameter, `G`, `M`, `V` mirror it
+(gradient, Adam moments).  [ net region | embedding-named region ]; the second region (label table, per-field
+tables concatenated to emb_W [V_total, D], LR tables concatenated to lr_W [V_total]) gets the embedding
+regulariser, exactly the `"embedding_layer" in name` rule of base_model.py:86.  state_dict tensors are views.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import call, current_stream, query, require_device
+
+EMB = "embedding_layer.embedding_layer.embedding_layer."
+LRP = "lr_layer.embedding_layer.embedding_layer.embedding_layer."
+
+
+@dataclass
+class FeatureSpec:
+    name: str
+    type: str                   # categorical | sequence
+    vocab_size: int
+    max_len: int = 1
+    padding_idx: Optional[int] = None
+
+    @property
+    def width(self):
+        return self.max_len if self.type == "sequence" else 1
+
+    @property
+    def pad(self):
+        return self.vocab_size - 1 if self.type == "sequence" else self.padding_idx
+
+
+@dataclass
+class EngineSpec:
+    features: List[FeatureSpec]
+    model: str = "RAT_m2"
+    embedding_dim: int = 10
+    num_heads: int = 1
+    dim_head: int = 10
+    scale_dim: int = 4
+    depth: int = 4
+    dnn_hidden_units: Sequence[int] = (64, 64, 64)
+    batch_norm: bool = False
+    use_wide: bool = False
+    emb_dropout: float = 0.0
+    net_dropout: float = 0.0
+    embedding_regularizer: float = 0.0
+    net_regularizer: float = 0.0
+    learning_rate: float = 1e-3
+    max_gradient_norm: float = 10.0
+    seed: int = 2021
+
+    @property
+    def F(self):
+        return len(self.features)
+
+    @property
+    def L(self):
+        return sum(f.width for f in self.features)
+
+    @property
+    def V(self):
+        return sum(f.vocab_size for f in self.features)
+
+
+def _align4(n):
+    return (n + 3) // 4 * 4
+
+
+def dnn_layout(spec) -> Tuple[List[Tuple[int, Optional[int]]], int]:
+    """indices inside the reference's nn.Sequential `dnn.dnn` (deep.py:126-137)."""
+    out, i = [], 0
+    for _ in spec.dnn_hidden_units:
+        lin, bn = i, None
+        i += 1
+        if spec.batch_norm:
+            bn = i
+            i += 1
+        i += 1                      # activation
+        if spec.net_dropout > 0:
+            i += 1
+        out.append((lin, bn))
+    return out, i
+
+
+def param_shapes(spec: EngineSpec) -> Tuple["OrderedDict[str, tuple]", "OrderedDict[str, tuple]"]:
+    """(net params, embedding-named params) with the reference's state_dict names and shapes."""
+    D, H, dh, F = spec.embedding_dim, spec.num_heads, spec.dim_head, spec.F
+    I, M = H * dh, D * spec.scale_dim
+    net: "OrderedDict[str, tuple]" = OrderedDict()
+    emb: "OrderedDict[str, tuple]" = OrderedDict()
+    emb["label_embedding_layer.weight"] = (3, D)
+    for f in spec.features:
+        emb[EMB + f.name + ".weight"] = (f.vocab_size, D)
+    if spec.use_wide:
+        for f in spec.features:
+            emb[LRP + f.name + ".weight"] = (f.vocab_size, 1)
+    net["query_proj.weight"] = (F * D, F * D)
+    net["query_proj.bias"] = (F * D,)
+
+    def attn(pre, qkv=True):
+        net[pre + "norm.weight"] = (D,)
+        net[pre + "norm.bias"] = (D,)
+        if qkv:
+            net[pre + "fn.to_qkv.weight"] = (3 * I, D)
+        net[pre + "fn.to_out.0.weight"] = (D, I)
+        net[pre + "fn.to_out.0.bias"] = (D,)
+
+    def ff(pre):
+        net[pre + "net.0.weight"] = (M, D)
+        net[pre + "net.0.bias"] = (M,)
+        net[pre + "net.3.weight"] = (D, M)
+        net[pre + "net.3.bias"] = (D,)
+
+    def transformer(pre):
+        for l in range(spec.depth):
+            attn(f"{pre}layers.{l}.0.")
+            net[f"{pre}layers.{l}.1.norm.weight"] = (D,)
+            net[f"{pre}layers.{l}.1.norm.bias"] = (D,)
+            ff(f"{pre}layers.{l}.1.fn.")
+        net[pre + "norm.weight"] = (D,)
+        net[pre + "norm.bias"] = (D,)
+
+    if spec.model == "RAT_m2":
+        for l in range(spec.depth):
+            attn(f"encoder.encoder.{l}.cross_attention.")
+            attn(f"encoder.encoder.{l}.intra_attention.")
+            ff(f"encoder.encoder.{l}.mlp.")
+    elif spec.model == "RAT_m0":
+        transformer("encoder.")
+    elif spec.model == "RAT_m1":
+        transformer("intra_transformer.")
+        transformer("cross_transformer.")
+    elif spec.model == "RAT_m3":
+        for l in range(spec.depth):
+            pre = f"encoder.encoder.{l}."
+            for nm in ("W_q", "W_k_s", "W_v_s", "W_k_t", "W_v_t"):
+                net[pre + nm + ".weight"] = (I, D)
+            attn(pre + "intra_attention.", qkv=False)
+            attn(pre + "cross_attention.", qkv=False)
+            ff(pre + "mlp.")
+    else:
+        raise NotImplementedError(f"model={spec.model}")
+    units = [F * D] + list(spec.dnn_hidden_units)
+    layers, final = dnn_layout(spec)
+    for (lin, bn), a, b in zip(layers, units[:-1], units[1:]):
+        net[f"dnn.dnn.{lin}.weight"] = (b, a)
+        net[f"dnn.dnn.{lin}.bias"] = (b,)
+        if bn is not None:
+            net[f"dnn.dnn.{bn}.weight"] = (b,)
+            net[f"dnn.dnn.{bn}.bias"] = (b,)
+    if len(spec.dnn_hidden_units) > 0:
+        net[f"dnn.dnn.{final}.weight"] = (1, units[-1])
+        net[f"dnn.dnn.{final}.bias"] = (1,)
+    net["fc.weight"] = (1, D)
+    net["fc.bias"] = (1,)
+    return net, emb
+
+
+class ParamStore:
+    """Flat fp32 parameter buffer + gradient + Adam moments, with named views."""
+
+    def __init__(self, spec: EngineSpec, device):
+        net, emb = param_shapes(spec)
+        self.offsets: "OrderedDict[str, Tuple[int, tuple]]" = OrderedDict()
+        off = 0
+        for k, shp in net.items():
+            self.offsets[k] = (off, shp)
+            off = _align4(off + math.prod(shp))
+        self.net_end = off
+        D, V = spec.embedding_dim, spec.V
+        k = "label_embedding_layer.weight"
+        self.offsets[k] = (off, emb[k])
+        off = _align4(off + 3 * D)
+        self.emb_off = off
+        for f in spec.features:                      # contiguous -> emb_W [V, D]
+            k = EMB + f.name + ".weight"
+            self.offsets[k] = (off, emb[k])
+            off += f.vocab_size * D
+        off = _align4(off)
+        self.lr_off = off
+        if spec.use_wide:
+            for f in spec.features:                  # contiguous -> lr_W [V]
+                k = LRP + f.name + ".weight"
+                self.offsets[k] = (off, emb[k])
+                off += f.vocab_size
+            off = _align4(off)
+        self.total = off
+        self.W = torch.zeros(off, dtype=torch.float32, device=device)
+        self.G = torch.zeros(off, dtype=torch.float32, device=device)
+        self.M = torch.zeros(off, dtype=torch.float32, device=device)
+        self.Vv = torch.zeros(off, dtype=torch.float32, device=device)
+        self.views = OrderedDict((k, self.W[o:o + math.prod(s)].view(s)) for k, (o, s) in self.offsets.items())
+        self.grad_views = OrderedDict((k, self.G[o:o + math.prod(s)].view(s)) for k, (o, s) in self.offsets.items())
+        self.emb_W = self.W[self.emb_off:self.emb_off + V * D].view(V, D)
+        self.lr_W = self.W[self.lr_off:self.lr_off + V] if spec.use_wide else None
+
+    def numel_params(self):
+        return sum(math.prod(s) for _, s in self.offsets.values())
+
+    def g(self, name):
+        return self.grad_views[name]
+
+    def p(self, name):
+        return self.views[name]
+
+
+class RatEngine:
+    def __init__(self, spec: EngineSpec, device="cuda:0"):
+        require_device()
+        self.spec = spec
+        self.device = torch.device(device)
+        self.store = ParamStore(spec, self.device)
+        self.p = self.store.views
+        D = spec.embedding_dim
+        # schema arrays
+        col_off, col_vocab, col_pad, f_col0, f_w = [], [], [], [], []
+        row = 0
+        col = 0
+        for f in spec.features:
+            f_col0.append(col)
+            f_w.append(f.width)
+            for _ in range(f.width):
+                col_off.append(row)
+                col_vocab.append(f.vocab_size)
+                col_pad.append(-1 if f.pad is None else f.pad)
+            row += f.vocab_size
+            col += f.width
+        mk = lambda v: torch.tensor(v, dtype=torch.int32, device=self.device)
+        self.col_off, self.col_vocab, self.col_pad = mk(col_off), mk(col_vocab), mk(col_pad)
+        self.field_col0, self.field_width = mk(f_col0), mk(f_w)
+        self.err_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        # BatchNorm buffers
+        self.buffers: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+        layers, _ = dnn_layout(spec)
+        for (lin, bn), w in zip(layers, spec.dnn_hidden_units):
+            if bn is not None:
+                self.buffers[f"dnn.dnn.{bn}.running_mean"] = torch.zeros(w, device=self.device)
+                self.buffers[f"dnn.dnn.{bn}.running_var"] = torch.ones(w, device=self.device)
+                self.buffers[f"dnn.dnn.{bn}.num_batches_tracked"] = torch.zeros((), dtype=torch.long, device=self.device)
+        self._ws: Dict[tuple, dict] = {}
+        self.step_count = 0
+        self.rng_step = 0
+
+    # ------------------------------------------------------------------ workspaces
+    def _workspace(self, B: int, T: int, training: bool) -> dict:
+        key = (B, T, training)
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        s, dev = self.spec, self.device
+        N, D, F, L = s.F + 1, s.embedding_dim, s.F, s.L
+        f32 = dict(dtype=torch.float32, device=dev)
+        ws = dict(
+            ids=torch.empty(B, T, L, dtype=torch.int32, device=dev),
+            labels=torch.empty(B, T, dtype=torch.int32, device=dev),
+            y_true=torch.empty(B, **f32),
+            x_emb=torch.empty(B, F * D, **f32),
+            lr_out=torch.empty(B, **f32) if s.use_wide else None,
+            y_pred=torch.empty(B, **f32),
+            loss_part=torch.empty(int(query("rat_head_blocks", B)), dtype=torch.float64, device=dev),
+            loss=torch.zeros(2, **f32),
+            dnn_out=torch.empty(B, **f32) if len(s.dnn_hidden_units) else None,
+        )
+        n_act = self._num_acts() if training else 3
+        ws["acts"] = [torch.empty(B, T, N, D, **f32) for _ in range(n_act)]
+        units = list(s.dnn_hidden_units)
+        ws["z"] = [torch.empty(B, u, **f32) for u in units]
+        ws["h"] = [torch.empty(B, u, **f32) for u in units]
+        ws["bn_mean"] = [torch.empty(u, **f32) for u in units]
+        ws["bn_rstd"] = [torch.empty(u, **f32) for u in units]
+        ws["bn_sums"] = [torch.empty(2 * u, dtype=torch.float64, device=dev) for u in units]
+        nbytes = 0
+        dims = [F * D] + units
+        for a, b in zip(dims[:-1], dims[1:]):
+            nbytes = max(nbytes, int(query("rat_sgemm_workspace_bytes", B, b, a)),
+                         int(query("rat_sgemm_workspace_bytes", b, a, B)), int(query("rat_sgemm_workspace_bytes", B, a, b)))
+        ws["gemm_ws"] = torch.empty(max(nbytes // 4, 4), **f32)
+        self._ws[key] = ws
+        return ws
+
+    def _num_acts(self) -> int:
+        s = self.spec
+        if s.model in ("RAT_m2", "RAT_m3"):
+            return 3 * s.depth + 1
+        raise NotImplementedError(s.model)
+
+    # ------------------------------------------------------------------ inputs
+    def load_wire(self, X: torch.Tensor, y: torch.Tensor, training: bool):
+        """X [B,T,L] float64 (device), y [B,T] float64 (device) -- the reference wire format."""
+        B, T, L = X.shape
+        assert L == self.spec.L, f"input_length {L} != schema {self.spec.L}"
+        ws = self._workspace(B, T, training)
+        call("rat_convert_wire_f64", X, y, ws["ids"], ws["labels"], ws["y_true"], B, T, L, current_stream())
+        return ws
+
+    # ------------------------------------------------------------------ forward
+    def _attn(self, x, res, out, pre, mode, B, T, N, alpha=1.0, heads=None, dh=None, wq=None, wk=None, wv=None):
+        s, p = self.spec, self.p
+        H = s.num_heads if heads is None else heads
+        d_h = s.dim_head if dh is None else dh
+        I = s.num_heads * s.dim_head
+        if wq is None:
+            w = p[pre + "fn.to_qkv.weight"]
+            wq, wk, wv = w[:I], w[I:2 * I], w[2 * I:]
+        call("rat_attn_fwd", x, res, out, p[pre + "norm.weight"], p[pre + "norm.bias"], wq, wk, wv,
+             p[pre + "fn.to_out.0.weight"], p[pre + "fn.to_out.0.bias"], B, T, N, s.embedding_dim, H, d_h,
+             float(s.dim_head ** -0.5), float(alpha), mode, current_stream())
+
+    def _ff(self, x, res, out, pre, rows, ln=None):
+        s, p = self.spec, self.p
+        D, M = s.embedding_dim, s.embedding_dim * s.scale_dim
+        lw = p[ln + "weight"] if ln else None
+        lb = p[ln + "bias"] if ln else None
+        call("rat_ff_fwd", x, res, out, lw, lb, p[pre + "net.0.weight"], p[pre + "net.0.bias"],
+             p[pre + "net.3.weight"], p[pre + "net.3.bias"], rows, D, M, current_stream())
+
+    def encode(self, ws, B, T, training):
+        """block acts[0] -> final activations; returns the tensor whose [b,0,0,:] is the pooled token."""
+        s = self.spec
+        N = s.F + 1
+        acts = ws["acts"]
+        rows = B * T * N
+        if s.model == "RAT_m2":
+            cur = 0
+            for l in range(s.depth):
+                pre = f"encoder.encoder.{l}."
+                if training:
+                    i0, i1, i2, i3 = 3 * l, 3 * l + 1, 3 * l + 2, 3 * l + 3
+                else:
+                    i0, i1, i2, i3 = cur, (cur + 1) % 3, (cur + 2) % 3, cur
+                self._attn(acts[i0], acts[i0], acts[i1], pre + "intra_attention.", 0, B, T, N)
+                self._attn(acts[i1], acts[i1], acts[i2], pre + "cross_attention.", 1, B, T, N)
+                self._ff(acts[i2], acts[i2], acts[i3], pre + "mlp.", rows)
+                cur = i3
+            return acts[cur]
+        if s.model == "RAT_m3":
+            cur = 0
+            h2 = max(1, int(s.num_heads / 2))
+            dh2 = (s.num_heads * s.dim_head) // h2
+            for l in range(s.depth):
+                pre = f"encoder.encoder.{l}."
+                if training:
+                    i0, i1, i2, i3 = 3 * l, 3 * l + 1, 3 * l + 2, 3 * l + 3
+                else:
+                    i0, i1, i2, i3 = cur, (cur + 1) % 3, (cur + 2) % 3, (cur + 1) % 3
+                p = self.p
+                self._attn(acts[i0], None, acts[i1], pre + "intra_attention.", 0, B, T, N, 0.5, h2, dh2,
+                           p[pre + "W_q.weight"], p[pre + "W_k_s.weight"], p[pre + "W_v_s.weight"])
+                self._attn(acts[i0], acts[i1], acts[i2], pre + "cross_attention.", 1, B, T, N, 0.5, h2, dh2,
+                           p[pre + "W_q.weight"], p[pre + "W_k_t.weight"], p[pre + "W_v_t.weight"])
+                self._ff(acts[i2], acts[i0], acts[i3], pre + "mlp.", rows)
+                cur = i3
+            return acts[cur]
+        raise NotImplementedError(s.model)
+
+    def _dnn_forward(self, ws, B, training):
+        s, p, st = self.spec, self.p, current_stream()
+        layers, final = dnn_layout(s)
+        h = ws["x_emb"]
+        K = s.F * s.embedding_dim
+        gw = ws["gemm_ws"]
+        for li, ((lin, bn), width) in enumerate(zip(layers, s.dnn_hidden_units)):
+            z, out = ws["z"][li], ws["h"][li]
+            call("rat_sgemm", h, p[f"dnn.dnn.{lin}.weight"], z, p[f"dnn.dnn.{lin}.bias"], B, width, K, K, K, width,
+                 0, 0, gw, gw.numel() * 4, st)
+            mean = rstd = gamma = beta = None
+            if bn is not None:
+                mean, rstd = ws["bn_mean"][li], ws["bn_rstd"][li]
+                gamma, beta = p[f"dnn.dnn.{bn}.weight"], p[f"dnn.dnn.{bn}.bias"]
+                rm, rv = self.buffers[f"dnn.dnn.{bn}.running_mean"], self.buffers[f"dnn.dnn.{bn}.running_var"]
+                if training:
+                    call("rat_bn_sums", z, B, width, ws["bn_sums"][li], st)
+                    count = float(B) * self._allreduce_sums(ws["bn_sums"][li])
+                    call("rat_bn_finalize", ws["bn_sums"][li], count, width, mean, rstd, rm, rv, 0.1, 1e-5, st)
+                    self.buffers[f"dnn.dnn.{bn}.num_batches_tracked"] += 1
+                else:
+                    call("rat_bn_eval_stats", rm, rv, width, mean, rstd, 1e-5, st)
+            drop = s.net_dropout if training else 0.0
+            call("rat_bn_act_fwd", z, mean, rstd, gamma, beta, out, B, width, float(drop), s.seed,
+                 self._rng_stream(16 + li), st)
+            h, K = out, width
+        call("rat_sgemm", h, p[f"dnn.dnn.{final}.weight"], ws["dnn_out"], p[f"dnn.dnn.{final}.bias"], B, 1, K, K, K, 1,
+             0, 0, gw, gw.numel() * 4, st)
+
+    def _allreduce_sums(self, t) -> int:
+        """data-parallel hook (SyncBN-equivalent): all-reduce raw BN sums; returns the world size."""
+        return 1
+
+    def _rng_stream(self, slot: int) -> int:
+        return (self.rng_step * 64 + slot) & 0xFFFFFFFF
+
+    def forward_ids(self, ws, B, T, training=False, with_loss=False, inv_count=None):
+        """ids/labels already in ws -> y_pred [B]; keeps activations in ws when training."""
+        s, st = self.spec, current_stream()
+        D, F, L = s.embedding_dim, s.F, s.L
+        drop = s.emb_dropout if training else 0.0
+        self.err_flag.zero_()
+        call("rat_gather_fwd", self.store.emb_W, self.store.lr_W, self.p["label_embedding_layer.weight"], ws["ids"],
+             ws["labels"], self.col_off, self.col_vocab, self.field_col0, self.field_width, ws["acts"][0],
+             ws["x_emb"], ws["lr_out"], B, T, L, F, D, float(drop), s.seed, self._rng_stream(0), self.err_flag, st)
+        enc = self.encode(ws, B, T, training)
+        ws["enc_out"] = enc
+        if len(s.dnn_hidden_units):
+            self._dnn_forward(ws, B, training)
+        N = F + 1
+        want_loss = with_loss or training
+        call("rat_head", enc, T * N * D, self.p["fc.weight"], self.p["fc.bias"], ws["dnn_out"], ws["lr_out"],
+             ws["y_true"] if want_loss else None, B, D, ws["y_pred"], ws.get("dlogit") if training else None,
+             ws.get("denc") if training else None, float(inv_count if inv_count else 1.0 / B),
+             ws["loss_part"] if want_loss else None, ws["loss"][0:1] if want_loss else None,
+             ws["loss"][1:2] if want_loss else None, st)
+        return ws["y_pred"]
+
+    def check_errors(self):
+        flag = int(self.err_flag.item())
+        if flag:
+            raise RuntimeError(f"RAT gather: invalid input (flag={flag}: 1=id out of vocabulary, "
+                               f"2=neighbour index out of range, 4=label not in {{0,1,2}})")
+
+    # ------------------------------------------------------------------ state
+    def load_params(self, sd: Dict[str, torch.Tensor], strict=True):
+        missing = []
+        for k, v in self.p.items():
+            if k in sd:
+                v.copy_(sd[k].to(device=self.device, dtype=torch.float32).view(v.shape))
+            elif not k.startswith("query_proj"):
+                missing.append(k)
+        for k, v in self.buffers.items():
+            if k in sd:
+                v.copy_(sd[k].to(self.device))
+        if strict and missing:
+            raise KeyError(f"missing parameters: {missing[:5]}...")
