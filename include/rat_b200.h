@@ -124,6 +124,65 @@ int rat_head(const float* enc, long long enc_stride, const float* fc_w, const fl
              const float* lr_out, const float* y_true, int B, int D, float* y_pred, float* dlogit, float* denc,
              float inv_count, double* loss_part, float* loss_sum, float* loss_mean, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * K5: fused RAT block (backward).  Replace autograd's reverse of RAT_m2.py:155-236 (loss.backward(),
+ * base_model.py:223).  Every kernel recomputes the sub-block's intermediates in shared memory from the saved
+ * sub-block INPUT x and writes  dx = (base ? base : 0) + d(sub-block)/dx ; weight gradients are summed
+ * deterministically (per-CTA partials in `workspace`, fixed-order reduction) and STORED to dW* (dWq is
+ * accumulated instead when accumulate_wq != 0: RAT_m3 shares W_q between its two attentions).
+ * dx may alias dout/base (in place).  Any dW* pointer may be NULL (gradient discarded).
+ * ------------------------------------------------------------------------------------------------------- */
+size_t rat_attn_bwd_workspace_bytes(int B, int T, int N, int D, int heads, int dim_head, int mode);
+int rat_attn_bwd(const float* x, const float* dout, const float* base, float* dx, const float* ln_w,
+                 const float* ln_b, const float* Wq, const float* Wk, const float* Wv, const float* Wo, float* dWq,
+                 float* dWk, float* dWv, float* dWo, float* dbo, float* dln_w, float* dln_b, int accumulate_wq, int B,
+                 int T, int N, int D, int heads, int dim_head, float scale, float alpha, int mode, float* workspace,
+                 size_t workspace_bytes, void* stream);
+size_t rat_ff_bwd_workspace_bytes(long long rows, int D, int M);
+int rat_ff_bwd(const float* x, const float* dout, const float* base, float* dx, const float* ln_w, const float* ln_b,
+               const float* W1, const float* b1, const float* W2, float* dW1, float* db1, float* dW2, float* db2,
+               float* dln_w, float* dln_b, long long rows, int D, int M, float* workspace, size_t workspace_bytes,
+               void* stream);
+size_t rat_layernorm_bwd_workspace_bytes(long long rows, int D);
+int rat_layernorm_bwd(const float* x, const float* dout, float* dx, const float* w, float* dw, float* db,
+                      long long rows, int D, float* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K6: embedding gradient = deterministic sorted segment-reduce.  Replaces ATen embedding_dense_backward for
+ * every nn.Embedding of EmbeddingDictLayer (layers/embedding.py:79-100), LR_Layer (layers/shallow.py:31) and the
+ * label table (RAT_m2.py:64).  Occurrence (b,t,l) contributes dblock[b,t,1+field(l),:] (+ dxemb[b,field(l),:] when
+ * t==0) to row col_off[l]+ids[b,t,l] of g_emb, and dlogit[b] (t==0 only) to the same row of g_lr; padding ids
+ * contribute nothing (torch padding_idx semantics).  g_label [3,D] = sum of dblock[b,t,0,:] by labels[b,t].
+ * Only touched rows of g_emb/g_lr are written (each exactly once); the caller keeps the rest zero.
+ * ------------------------------------------------------------------------------------------------------- */
+size_t rat_emb_scatter_workspace_bytes(long long n_occ, int D);
+int rat_emb_scatter_reduce(const int* ids, const int* labels, const float* dblock, const float* dxemb,
+                           const float* dlogit, const int* col_off, const int* col_pad, const int* col_vocab,
+                           const int* col_field, float* g_emb, float* g_lr, float* g_label, int B, int T, int L, int F,
+                           int D, long long V_total, void* workspace, size_t workspace_bytes, void* stream);
+/* the stable LSD radix sort used above, exposed for tests: sorts (keys, vals) by the low `bits` bits of keys.
+ * hist: scratch of 256*ceil(n/2048) uint32.  *result_in_tmp = 1 if the sorted data ended in the tmp buffers. */
+int rat_radix_sort_pairs(unsigned int* keys, unsigned int* vals, unsigned int* keys_tmp, unsigned int* vals_tmp,
+                         unsigned int* hist, long long n, int bits, int* result_in_tmp, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K7/K8: regulariser gradient + global-norm clip + dense-equivalent fused Adam over the flat buffers.
+ * Replace BaseModel.add_regularization (base_model.py:79-94), nn.utils.clip_grad_norm_ (base_model.py:224) and
+ * torch.optim.Adam.step (base_model.py:225; torch_utils.py:41-49).  Elements [0,reg_boundary) use lambda_net,
+ * the rest lambda_emb (the `"embedding_layer" in name` rule).  `partial`: double[2*rat_optim_blocks()].
+ * `state`: device float[8] = {grad_norm, clip_coef, lr/bc1, 1/sqrt(bc2), step, reg_loss, -, -}; `lr`: device
+ * float[1].  extra_sq (device double[2], may be NULL): {sum g^2, reg loss} contributed by other ranks' shards.
+ * ------------------------------------------------------------------------------------------------------- */
+int rat_optim_blocks(void);
+int rat_grad_sqnorm(const float* G, const float* W, long long n, long long reg_boundary, float lambda_net,
+                    float lambda_emb, double* partial, void* stream);
+int rat_optim_prepare(const double* partial, int nparts, const double* extra_sq, float max_norm, const float* lr,
+                      float beta1, float beta2, float* state, int advance_step, void* stream);
+int rat_adam_step(float* W, float* G, float* M, float* V, long long n, long long reg_boundary, float lambda_net,
+                  float lambda_emb, const float* state, float beta1, float beta2, float eps, void* stream);
+int rat_materialize_grad(const float* G, const float* W, long long n, long long reg_boundary, float lambda_net,
+                         float lambda_emb, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

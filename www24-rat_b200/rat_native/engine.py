@@ -225,21 +225,22 @@ class RatEngine:
         self.p = self.store.views
         D = spec.embedding_dim
         # schema arrays
-        col_off, col_vocab, col_pad, f_col0, f_w = [], [], [], [], []
+        col_off, col_vocab, col_pad, f_col0, f_w, col_field = [], [], [], [], [], []
         row = 0
         col = 0
-        for f in spec.features:
+        for fi, f in enumerate(spec.features):
             f_col0.append(col)
             f_w.append(f.width)
             for _ in range(f.width):
                 col_off.append(row)
                 col_vocab.append(f.vocab_size)
                 col_pad.append(-1 if f.pad is None else f.pad)
+                col_field.append(fi)
             row += f.vocab_size
             col += f.width
         mk = lambda v: torch.tensor(v, dtype=torch.int32, device=self.device)
         self.col_off, self.col_vocab, self.col_pad = mk(col_off), mk(col_vocab), mk(col_pad)
-        self.field_col0, self.field_width = mk(f_col0), mk(f_w)
+        self.field_col0, self.field_width, self.col_field = mk(f_col0), mk(f_w), mk(col_field)
         self.err_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
         # BatchNorm buffers
         self.buffers: "OrderedDict[str, torch.Tensor]" = OrderedDict()
@@ -250,8 +251,19 @@ class RatEngine:
                 self.buffers[f"dnn.dnn.{bn}.running_var"] = torch.ones(w, device=self.device)
                 self.buffers[f"dnn.dnn.{bn}.num_batches_tracked"] = torch.zeros((), dtype=torch.long, device=self.device)
         self._ws: Dict[tuple, dict] = {}
-        self.step_count = 0
         self.rng_step = 0
+        nb = int(query("rat_optim_blocks"))
+        self.opt_partial = torch.zeros(2 * nb, dtype=torch.float64, device=self.device)
+        self.opt_state = torch.zeros(8, dtype=torch.float32, device=self.device)
+        self.lr = torch.full((1,), float(spec.learning_rate), dtype=torch.float32, device=self.device)
+        self.world = 1
+        self.dist_group = None
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                self.world = dist.get_world_size()
+        except Exception:
+            pass
 
     # ------------------------------------------------------------------ workspaces
     def _workspace(self, B: int, T: int, training: bool) -> dict:
@@ -287,6 +299,24 @@ class RatEngine:
             nbytes = max(nbytes, int(query("rat_sgemm_workspace_bytes", B, b, a)),
                          int(query("rat_sgemm_workspace_bytes", b, a, B)), int(query("rat_sgemm_workspace_bytes", B, a, b)))
         ws["gemm_ws"] = torch.empty(max(nbytes // 4, 4), **f32)
+        if training:
+            H, dh, M = s.num_heads, s.dim_head, D * s.scale_dim
+            ws["dact"] = torch.empty(B, T, N, D, **f32)
+            ws["dact2"] = torch.empty(B, T, N, D, **f32) if s.model == "RAT_m3" else None
+            ws["dlogit"] = torch.empty(B, **f32)
+            ws["denc"] = ws["dact"]
+            ws["dxemb"] = torch.zeros(B, F * D, **f32)
+            ws["dh"] = [torch.empty(B, u, **f32) for u in units]
+            hh, dd = (max(1, int(H / 2)), (H * dh) // max(1, int(H / 2))) if s.model == "RAT_m3" else (H, dh)
+            nb = max(int(query("rat_attn_bwd_workspace_bytes", B, T, N, D, hh, dd, 0)),
+                     int(query("rat_attn_bwd_workspace_bytes", B, T, N, D, hh, dd, 1)),
+                     int(query("rat_ff_bwd_workspace_bytes", B * T * N, D, M)),
+                     int(query("rat_layernorm_bwd_workspace_bytes", B * T * N, D)))
+            if nb == 0:
+                raise RuntimeError("RAT backward kernels: tile does not fit in shared memory for this shape")
+            ws["bwd_ws"] = torch.empty(nb // 4 + 4, **f32)
+            sb = int(query("rat_emb_scatter_workspace_bytes", B * T * L, D))
+            ws["scatter_ws"] = torch.empty(sb // 4 + 4, dtype=torch.int32, device=dev)
         self._ws[key] = ws
         return ws
 
@@ -396,7 +426,10 @@ class RatEngine:
 
     def _allreduce_sums(self, t) -> int:
         """data-parallel hook (SyncBN-equivalent): all-reduce raw BN sums; returns the world size."""
-        return 1
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, group=self.dist_group)
+        return self.world
 
     def _rng_stream(self, slot: int) -> int:
         return (self.rng_step * 64 + slot) & 0xFFFFFFFF
@@ -428,6 +461,155 @@ class RatEngine:
         if flag:
             raise RuntimeError(f"RAT gather: invalid input (flag={flag}: 1=id out of vocabulary, "
                                f"2=neighbour index out of range, 4=label not in {{0,1,2}})")
+
+
+    # ------------------------------------------------------------------ backward
+    def _attn_bwd(self, ws, x, d_in, base, d_out, pre, mode, B, T, N, alpha=1.0, heads=None, dh=None,
+                  wq=None, wk=None, wv=None, names=None, acc_wq=0):
+        s, p, g = self.spec, self.p, self.store.grad_views
+        H = s.num_heads if heads is None else heads
+        d_h = s.dim_head if dh is None else dh
+        I = s.num_heads * s.dim_head
+        if wq is None:
+            w, gw = p[pre + "fn.to_qkv.weight"], g[pre + "fn.to_qkv.weight"]
+            wq, wk, wv = w[:I], w[I:2 * I], w[2 * I:]
+            gq, gk, gv = gw[:I], gw[I:2 * I], gw[2 * I:]
+        else:
+            gq, gk, gv = (g[n] for n in names)
+        bw = ws["bwd_ws"]
+        call("rat_attn_bwd", x, d_in, base, d_out, p[pre + "norm.weight"], p[pre + "norm.bias"], wq, wk, wv,
+             p[pre + "fn.to_out.0.weight"], gq, gk, gv, g[pre + "fn.to_out.0.weight"], g[pre + "fn.to_out.0.bias"],
+             g[pre + "norm.weight"], g[pre + "norm.bias"], acc_wq, B, T, N, s.embedding_dim, H, d_h,
+             float(s.dim_head ** -0.5), float(alpha), mode, bw, bw.numel() * 4, current_stream())
+
+    def _ff_bwd(self, ws, x, d_in, base, d_out, pre, rows, ln=None):
+        s, p, g = self.spec, self.p, self.store.grad_views
+        D, M = s.embedding_dim, s.embedding_dim * s.scale_dim
+        bw = ws["bwd_ws"]
+        call("rat_ff_bwd", x, d_in, base, d_out, p[ln + "weight"] if ln else None, p[ln + "bias"] if ln else None,
+             p[pre + "net.0.weight"], p[pre + "net.0.bias"], p[pre + "net.3.weight"], g[pre + "net.0.weight"],
+             g[pre + "net.0.bias"], g[pre + "net.3.weight"], g[pre + "net.3.bias"], g[ln + "weight"] if ln else None,
+             g[ln + "bias"] if ln else None, rows, D, M, bw, bw.numel() * 4, current_stream())
+
+    def encode_backward(self, ws, B, T):
+        """ws['dact'] holds d(loss)/d(encoder output); on return it holds d(loss)/d(block after dropout)."""
+        s = self.spec
+        N = s.F + 1
+        acts, d = ws["acts"], ws["dact"]
+        rows = B * T * N
+        if s.model == "RAT_m2":
+            for l in reversed(range(s.depth)):
+                pre = f"encoder.encoder.{l}."
+                self._ff_bwd(ws, acts[3 * l + 2], d, d, d, pre + "mlp.", rows)
+                self._attn_bwd(ws, acts[3 * l + 1], d, d, d, pre + "cross_attention.", 1, B, T, N)
+                self._attn_bwd(ws, acts[3 * l], d, d, d, pre + "intra_attention.", 0, B, T, N)
+            return d
+        if s.model == "RAT_m3":
+            d2 = ws["dact2"]
+            h2 = max(1, int(s.num_heads / 2))
+            dh2 = (s.num_heads * s.dim_head) // h2
+            for l in reversed(range(s.depth)):
+                pre = f"encoder.encoder.{l}."
+                # x_out = x + FF(u), u = .5 A_s(x) + .5 A_t(x):  du = FFbwd(d) ; dx = d + .5 dA_t(du) + .5 dA_s(du)
+                self._ff_bwd(ws, acts[3 * l + 2], d, None, d2, pre + "mlp.", rows)
+                self._attn_bwd(ws, acts[3 * l], d2, d, d, pre + "cross_attention.", 1, B, T, N, 0.5, h2, dh2,
+                               self.p[pre + "W_q.weight"], self.p[pre + "W_k_t.weight"], self.p[pre + "W_v_t.weight"],
+                               (pre + "W_q.weight", pre + "W_k_t.weight", pre + "W_v_t.weight"), 0)
+                self._attn_bwd(ws, acts[3 * l], d2, d, d, pre + "intra_attention.", 0, B, T, N, 0.5, h2, dh2,
+                               self.p[pre + "W_q.weight"], self.p[pre + "W_k_s.weight"], self.p[pre + "W_v_s.weight"],
+                               (pre + "W_q.weight", pre + "W_k_s.weight", pre + "W_v_s.weight"), 1)
+            return d
+        raise NotImplementedError(s.model)
+
+    def _dnn_backward(self, ws, B):
+        s, p, g, st = self.spec, self.p, self.store.grad_views, current_stream()
+        layers, final = dnn_layout(s)
+        units = list(s.dnn_hidden_units)
+        gw = ws["gemm_ws"]
+        gwb = gw.numel() * 4
+        dlogit = ws["dlogit"]
+        K = units[-1]
+        h_last = ws["h"][-1]
+        # final Linear(K -> 1)
+        call("rat_sgemm", dlogit, h_last, g[f"dnn.dnn.{final}.weight"], None, 1, K, B, 1, K, K, 1, 1, gw, gwb, st)
+        call("rat_colsum", dlogit, B, 1, 1, g[f"dnn.dnn.{final}.bias"], st)
+        call("rat_sgemm", dlogit, p[f"dnn.dnn.{final}.weight"], ws["dh"][-1], None, B, K, 1, 1, K, K, 0, 1, gw, gwb, st)
+        count = float(B * self.world)
+        for li in reversed(range(len(units))):
+            lin, bn = layers[li]
+            u = units[li]
+            dh, out, z = ws["dh"][li], ws["h"][li], ws["z"][li]
+            drop = float(s.net_dropout)
+            if bn is not None:
+                call("rat_bn_act_bwd_sums", dh, out, z, ws["bn_mean"][li], ws["bn_rstd"][li], B, u, drop, s.seed,
+                     self._rng_stream(16 + li), ws["bn_sums"][li], st)
+                self._allreduce_sums(ws["bn_sums"][li])
+                call("rat_bn_act_bwd_apply", dh, out, z, ws["bn_mean"][li], ws["bn_rstd"][li], p[f"dnn.dnn.{bn}.weight"],
+                     ws["bn_sums"][li], count, dh, g[f"dnn.dnn.{bn}.weight"], g[f"dnn.dnn.{bn}.bias"], B, u, drop,
+                     s.seed, self._rng_stream(16 + li), st)
+            else:
+                call("rat_bn_act_bwd_apply", dh, out, z, None, None, None, None, count, dh, None, None, B, u, drop,
+                     s.seed, self._rng_stream(16 + li), st)
+            h_prev = ws["h"][li - 1] if li > 0 else ws["x_emb"]
+            Kin = units[li - 1] if li > 0 else s.F * s.embedding_dim
+            d_prev = ws["dh"][li - 1] if li > 0 else ws["dxemb"]
+            call("rat_sgemm", dh, h_prev, g[f"dnn.dnn.{lin}.weight"], None, u, Kin, B, u, Kin, Kin, 1, 1, gw, gwb, st)
+            call("rat_colsum", dh, B, u, u, g[f"dnn.dnn.{lin}.bias"], st)
+            call("rat_sgemm", dh, p[f"dnn.dnn.{lin}.weight"], d_prev, None, B, Kin, u, u, Kin, Kin, 0, 1, gw, gwb, st)
+
+    def backward(self, ws, B, T):
+        """after forward_ids(training=True): fill self.store.G with the data gradient of the mean BCE."""
+        s, g, st = self.spec, self.store.grad_views, current_stream()
+        N, D, F, L = s.F + 1, s.embedding_dim, s.F, s.L
+        enc = ws["enc_out"]
+        # fc
+        call("rat_sgemm", ws["dlogit"], enc, g["fc.weight"], None, 1, D, B, 1, T * N * D, D, 1, 1, None, 0, st)
+        call("rat_colsum", ws["dlogit"], B, 1, 1, g["fc.bias"], st)
+        has_dnn = len(s.dnn_hidden_units) > 0
+        if has_dnn:
+            self._dnn_backward(ws, B)
+        d = self.encode_backward(ws, B, T)
+        if s.emb_dropout > 0:
+            call("rat_dropout_bwd", d, d.numel(), float(s.emb_dropout), s.seed, self._rng_stream(0), st)
+        sw = ws["scatter_ws"]
+        gs = self.store
+        g_emb = gs.G[gs.emb_off:gs.emb_off + s.V * D]
+        g_lr = gs.G[gs.lr_off:gs.lr_off + s.V] if s.use_wide else None
+        call("rat_emb_scatter_reduce", ws["ids"], ws["labels"], d, ws["dxemb"] if has_dnn else None,
+             ws["dlogit"] if s.use_wide else None, self.col_off, self.col_pad, self.col_vocab, self.col_field,
+             g_emb, g_lr, g["label_embedding_layer.weight"], B, T, L, F, D, s.V, sw, sw.numel() * 4, st)
+
+    def optimizer_step(self):
+        s, gs, st = self.spec, self.store, current_stream()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(gs.G, group=self.dist_group)
+        nb = int(query("rat_optim_blocks"))
+        lam_n, lam_e = float(s.net_regularizer or 0.0), float(s.embedding_regularizer or 0.0)
+        call("rat_grad_sqnorm", gs.G, gs.W, gs.total, gs.net_end, lam_n, lam_e, self.opt_partial, st)
+        call("rat_optim_prepare", self.opt_partial, nb, None, float(s.max_gradient_norm), self.lr, 0.9, 0.999,
+             self.opt_state, 1, st)
+        call("rat_adam_step", gs.W, gs.G, gs.M, gs.Vv, gs.total, gs.net_end, lam_n, lam_e, self.opt_state, 0.9, 0.999,
+             1e-8, st)
+
+    def train_step_ids(self, ws, B, T):
+        """one full training step on the ids/labels/y_true already in ws. Returns ws['loss'] (device):
+        [sum BCE, mean BCE of the local shard]; opt_state[5] holds the regularisation loss."""
+        self.rng_step += 1
+        ws["dact"].zero_()
+        self.forward_ids(ws, B, T, training=True, inv_count=1.0 / (B * self.world))
+        self.backward(ws, B, T)
+        self.optimizer_step()
+        return ws["loss"]
+
+    def materialize_grads(self) -> Dict[str, torch.Tensor]:
+        """dense gradients incl. the regulariser (what the reference's .grad holds before clipping). Tests only."""
+        s, gs = self.spec, self.store
+        out = torch.empty_like(gs.G)
+        call("rat_materialize_grad", gs.G, gs.W, gs.total, gs.net_end, float(s.net_regularizer or 0.0),
+             float(s.embedding_regularizer or 0.0), out, current_stream())
+        import math as _m
+        return OrderedDict((k, out[o:o + _m.prod(shp)].view(shp)) for k, (o, shp) in gs.offsets.items())
 
     # ------------------------------------------------------------------ state
     def load_params(self, sd: Dict[str, torch.Tensor], strict=True):
