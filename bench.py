@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- RAT_m2 training / inference throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--shape kkbox|ml|tmall] [--batch 4096] [--topk 5]
+    python bench.py --impl reference ...     # the reference algorithm on the host CPU cores (oracle port)
+
+One "step" = one full RAT_m2 training step (retrieval-set assembly + gather -> 4 RAT blocks -> DNN head -> loss ->
+backward -> sorted segment-reduce -> global-norm clip -> dense-equivalent Adam) on one batch of B=4096 samples PER GPU
+(weak scaling) of synthetic data with the kkbox_x1_10fold_retrieval shape (BASELINE.json configs[1]).
+
+Printed JSON line (rank 0):
+  value   whole-job train samples/s, inputs (id matrix, pool, neighbour index) resident in HBM
+  e2e     the same through the public FuxiCTR API (model.train_step(batch)) with HOST float64 wire-format batches in
+          pinned memory: H2D of every batch and a D2H read of the loss inside the timed region
+  infer   the same two numbers for model.forward (eval mode)
+  roofline / roofline_gather / roofline_adam / kernels   per-kernel CUDA-event timings vs measured peaks
+  cpu_baseline   the oracle (CPU restatement of the reference) on a bounded sample, N=1 only
+Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks; every step uses a
+different batch and the step's working set (>600 MB of activations) is larger than L2, so no L2 flush is needed.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "www24-rat_b200"))
+
+import numpy as np
+import torch
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--shape", default="kkbox", choices=["kkbox", "ml", "tmall"])
+    ap.add_argument("--batch", type=int, default=4096, help="per-GPU batch size")
+    ap.add_argument("--topk", type=int, default=5)
+    ap.add_argument("--pool-rows", type=int, default=2_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-batch", type=int, default=512)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d["hbm_gbs"]), tf_burst=float(d["bf16_tflops"]),
+                    tf_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+# ----------------------------------------------------------------------------------------- algorithmic work
+def gather_bytes_per_sample(K, L, F, D):
+    T, N = K + 1, F + 1            # nbr idx + ids + labels + table rows + LR scalars + block + x_emb
+    return K * 8 + T * L * 4 + T + T * L * D * 4 + L * 4 + T * N * D * 4 + F * D * 4
+
+
+def encoder_flops_per_sample(K, F, D, H, dh, scale_dim, depth=4):
+    T, N, I, M = K + 1, F + 1, H * dh, D * scale_dim
+    return depth * (T * N * (16 * D * I + 4 * D * M) + 4 * I * T * N * (N + T))
+
+
+def attn_flops_per_token(D, I, S):
+    return 2 * D * 3 * I + 2 * I * D + 4 * I * S
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower() == "active":
+                    reasons.add(name)
+        if sm:
+            busy = sorted(sm)[len(sm) // 2:]          # the upper half = samples taken under load
+            out = {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+def timed(fn_step, steps, warmup, dist):
+    """W untimed + exactly K timed steps, barrier+sync both sides, CUDA events, max over ranks. Returns seconds."""
+    for i in range(warmup):
+        fn_step(i)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn_step(warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item()) / 1e3
+
+
+# ----------------------------------------------------------------------------------------- our arm
+def run_ours(a):
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    dist = None
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist_
+        dist_.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_
+    assert world == a.gpus or world == 1, f"--gpus {a.gpus} but WORLD_SIZE={world}"
+    import rat_native as rn
+    from rat_native import shapes
+    from fuxictr.pytorch import models
+    from fuxictr.pytorch.data_generator import DeviceDataGenerator
+    from fuxictr.pytorch.torch_utils import seed_everything
+    rn.require_device()
+    seed_everything(2021)
+    B, K, S = a.batch, a.topk, a.shape
+    cfg = shapes.SHAPES[S]
+    fm = shapes.make_feature_map(S)
+    params = shapes.model_params(S, K=K, gpu=local)
+    os.makedirs(os.path.join(params["model_root"], fm.dataset_id), exist_ok=True)
+    model = models.RAT_m2(fm, **params)
+    if world > 1:                               # identical replicas: broadcast rank 0's initial weights
+        dist.broadcast(model._engine.store.W, 0)
+    n_params = model.count_parameters()
+    hp = cfg["hp"]
+    F, L, D, H = fm.num_fields, fm.input_length, hp["embedding_dim"], hp["num_heads"]
+    T, N = K + 1, F + 1
+
+    # ---- synthetic data (same seed on every rank; each rank takes its contiguous slice of every global batch)
+    pool = shapes.synthetic_array(fm.feature_specs, a.pool_rows, seed=2021, pos_ratio=cfg["pos_ratio"])
+    nbr = shapes.synthetic_neighbours(a.pool_rows, a.pool_rows, K, seed=2021)
+    gen = DeviceDataGenerator(pool, pool, nbr, batch_size=B * world, shuffle=True, device=f"cuda:{local}", seed=2021,
+                              rank=rank, world=world, drop_last=True)
+    n_steps_total = a.warmup + a.steps
+    it = iter(gen)
+    dev_batches = [next(it) for _ in range(n_steps_total)]
+    # host wire-format batches (pinned) for the e2e leg: disjoint rows per step and rank
+    rng = np.random.default_rng(1234 + rank)
+    host_batches = []
+    for i in range(n_steps_total):
+        rows = rng.integers(0, a.pool_rows, size=B)
+        X, y, v, l = shapes.host_wire_batch(pool, pool, nbr, rows)
+        host_batches.append(tuple(torch.from_numpy(t).pin_memory() for t in (X, y, v, l)))
+    h2d = host_batches[0][0].numel() * 8 + host_batches[0][1].numel() * 8
+
+    model.train()
+    model._max_gradient_norm = 10.0
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = rn.query("rat_launch_count")
+    t_train = timed(lambda i: model.train_step(dev_batches[i]), a.steps, a.warmup, dist)
+    launches = (rn.query("rat_launch_count") - launches0) * a.steps // n_steps_total
+    clocks = sampler.stop() if sampler else None
+    model._engine.check_errors()
+
+    def e2e_train(i):
+        loss = model.train_step(host_batches[i])
+        return float(loss.item())                 # device -> host read of the step's result
+    t_e2e = timed(e2e_train, a.steps, a.warmup, dist)
+
+    model.eval()
+    with torch.no_grad():
+        t_inf = timed(lambda i: model.forward(dev_batches[i]), a.steps, a.warmup, dist)
+        out_host = torch.empty(B, 1, dtype=torch.float32).pin_memory()
+
+        def e2e_inf(i):
+            rd = model.forward(host_batches[i])
+            out_host.copy_(rd["y_pred"], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        t_e2e_inf = timed(e2e_inf, a.steps, a.warmup, dist)
+
+    # ---- per-kernel timing pass (CUDA events around every C-ABI call; not part of the headline numbers)
+    model.train()
+    rn.profile_calls(True)
+    nprof = min(5, a.steps)
+    for i in range(nprof):
+        model.train_step(dev_batches[a.warmup + i])
+    torch.cuda.synchronize()
+    prof = rn.profile_results()
+    rn.profile_calls(False)
+    pk = peaks()
+    total_ms = sum(ms for _, ms in prof.values())
+    kernels = {k: {"calls_per_step": n // nprof, "ms_per_step": round(ms / nprof, 4), "share": round(ms / total_ms, 4)}
+               for k, (n, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    rows_tok = B * T * N
+    I = H * 10
+
+    def per_call_ms(name):
+        n, ms = prof[name]
+        return ms / n
+    # dominant kernel: fused attention backward (2 per block: intra S=N, cross S=T) -- FLOP-bound on the FP32 pipe
+    attn_bwd_flops = rows_tok * (attn_flops_per_token(D, I, N) + attn_flops_per_token(D, I, T)) / 2 * 2.75
+    ach_tf = attn_bwd_flops / (per_call_ms("rat_attn_bwd") * 1e-3) / 1e12
+    roofline = {"kernel": "k_attn_bwd (+k_reduce_partials)", "bound": "tensor", "achieved": round(ach_tf, 3),
+                "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": round(ach_tf / pk["tf_sustained"], 5),
+                "traffic": None, "peak_source": pk["src"] + " bf16 dense (sustained)",
+                "note": "round-1 kernel runs fp32 FFMA on the SIMT pipe (nominal ~75 TFLOP/s fp32), not tcgen05 yet; "
+                        "algorithmic FLOPs = 2.75x forward (recompute + dgrad + wgrad)"}
+    gb = B * gather_bytes_per_sample(K, L, F, D)
+    g_ms = per_call_ms("rat_gather_fwd")
+    roofline_gather = {"kernel": "k_gather", "bound": "hbm", "achieved": round(gb / (g_ms * 1e-3) / 1e9, 1),
+                       "peak": pk["hbm"], "unit": "GB/s", "frac": round(gb / (g_ms * 1e-3) / 1e9 / pk["hbm"], 4),
+                       "traffic": None, "bytes_per_launch": gb, "peak_source": pk["src"]}
+    P = model._engine.store.total
+    ad_ms = per_call_ms("rat_adam_step")
+    roofline_adam = {"kernel": "k_adam", "bound": "hbm", "achieved": round(P * 32 / (ad_ms * 1e-3) / 1e9, 1),
+                     "peak": pk["hbm"], "unit": "GB/s", "frac": round(P * 32 / (ad_ms * 1e-3) / 1e9 / pk["hbm"], 4),
+                     "traffic": None, "bytes_per_launch": P * 32, "peak_source": pk["src"]}
+
+    if rank != 0:
+        return
+    gB = B * world
+    line = {
+        "metric": "RAT_m2 train samples/sec", "value": round(a.steps * gB / t_train, 1), "unit": "samples/s",
+        "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(t_train / a.steps * 1e3, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"RAT_m2 {cfg['dataset_id']} shape, K={K}, B={B}/GPU, train step (fwd+bwd+clip+Adam)",
+                   "global_batch": gB, "topK": K, "fields": F, "input_length": L, "embedding_dim": D, "heads": H,
+                   "params": n_params, "pool_rows": a.pool_rows, "parallelism": f"dp{world}",
+                   "l2": "every step uses a new batch; per-step working set (~660 MB activations) exceeds the 126 MB L2"},
+        "e2e": {"value": round(a.steps * gB / t_e2e, 1), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4, "api": "fuxictr.pytorch.models.RAT_m2.train_step(host f64 wire batch)"},
+        "infer": {"value": round(a.steps * gB / t_inf, 1), "unit": "samples/s",
+                  "ms_per_step": round(t_inf / a.steps * 1e3, 4),
+                  "e2e": {"value": round(a.steps * gB / t_e2e_inf, 1), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                          "d2h_bytes_per_step": B * 4}},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline, "roofline_gather": roofline_gather, "roofline_adam": roofline_adam,
+        "kernels": kernels,
+        "reference_derived": {"note": "BASELINE.md derived (not published) reference-GPU numbers, unknown GPU, incl. dataloader",
+                              "train_samples_per_s": {"kkbox": 8800, "ml": 52000, "tmall": 3300}[S],
+                              "infer_samples_per_s": {"kkbox": 37500, "ml": 110000, "tmall": 22900}[S]},
+    }
+    if world == 1 and not a.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(a, S, K)
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------- CPU arms (oracle port)
+def _oracle_setup(S, K, Bc):
+    from oracle import rat_oracle as O
+    spec = O.shape_spec(S)
+    params = O.init_params(spec, 0)
+    bufs = O.init_buffers(spec)
+    pool = O.synthetic_pool(spec, 20000, seed=1)
+    nbr = O.synthetic_neighbours(Bc * 4, 20000, K, seed=1)
+    return O, spec, params, bufs, pool, nbr
+
+
+def cpu_baseline(a, S, K):
+    """bounded sample of the same workload on the host cores: 1 warm-up + 2 timed oracle training steps at B=cpu_batch."""
+    Bc = a.cpu_batch
+    O, spec, params, bufs, pool, nbr = _oracle_setup(S, K, Bc)
+    st = O.AdamState()
+    ts = []
+    for i in range(3):
+        X, y = O.assemble_batch(pool[i * Bc:(i + 1) * Bc], pool, nbr[i * Bc:(i + 1) * Bc], np.arange(Bc))
+        t0 = time.perf_counter()
+        O.train_step(params, bufs, spec, st, torch.from_numpy(X), torch.from_numpy(y))
+        ts.append(time.perf_counter() - t0)
+    t = min(ts[1:])
+    return {"value": round(Bc / t, 1), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"2 timed oracle (torch-CPU fp32 restatement of the reference) training steps at B={Bc}, "
+                      f"{torch.get_num_threads()} threads, host cpu_count={os.cpu_count()}"}
+
+
+def run_reference(a):
+    """--impl reference: the reference algorithm on the host cores (the Python reference cannot travel to the GPU box;
+    the oracle port is the same torch-CPU arithmetic, pinned against it by tests/golden)."""
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    S, K, Bc = a.shape, a.topk, a.cpu_batch
+    torch.set_num_threads(os.cpu_count() or 1)
+    O, spec, params, bufs, pool, nbr = _oracle_setup(S, K, Bc)
+    st = O.AdamState()
+    steps, warmup = min(a.steps, 6), min(a.warmup, 1)
+
+    def step(i):
+        j = i % 4
+        X, y = O.assemble_batch(pool[j * Bc:(j + 1) * Bc], pool, nbr[j * Bc:(j + 1) * Bc], np.arange(Bc))
+        O.train_step(params, bufs, spec, st, torch.from_numpy(X), torch.from_numpy(y))
+    for i in range(warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(warmup + i)
+    t = time.perf_counter() - t0
+    v = round(steps * Bc / t, 1)
+    from rat_native import shapes
+    cfg = shapes.SHAPES[S]
+    line = {"impl": "reference", "metric": "RAT_m2 train samples/sec", "value": v, "unit": "samples/s",
+            "n_gpus": a.gpus, "steps": steps, "warmup": warmup, "ms_per_step": round(t / steps * 1e3, 2),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"RAT_m2 {cfg['dataset_id']} shape, K={K}, train step; bounded sample B={Bc} per step on CPU"},
+            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"{steps} oracle training steps at B={Bc} on {torch.get_num_threads()} host threads"},
+            "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

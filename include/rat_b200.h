@@ -26,6 +26,8 @@ extern "C" {
 
 const char* rat_last_error(void);
 int rat_abi_version(void);
+/* number of CUDA kernels this library has launched so far in this process (bench.py's gpu_launches) */
+long long rat_launch_count(void);
 /* 0 if an sm_100 device is current, else RAT_ECUDA (the product path refuses to run anywhere else) */
 int rat_device_check(void);
 
@@ -65,6 +67,11 @@ int rat_gather_fwd(const float* emb_W, const float* lr_W, const float* label_W, 
 /* backward of the embedding dropout: grad *= mask/(1-p), same philox mask as rat_gather_fwd */
 int rat_dropout_bwd(float* grad, long long n, float p, unsigned long long seed, unsigned int rng_stream,
                     void* stream);
+
+/* dst[r*dst_stride + d] = src[r*src_stride + d] for d < D: the `x[:, 0]` token pooling between the two
+ * Transformers of RAT_m1 (models/RAT_m1.py:125-126) and, with the strides swapped, its backward scatter. */
+int rat_strided_copy(const float* src, float* dst, long long rows, int D, long long src_stride, long long dst_stride,
+                     void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * K2: fused RAT block (forward)

@@ -559,8 +559,10 @@ def shape_spec(name: str, model: str = "RAT_m2", vocab_scale: float = 1.0, **ove
                   use_wide=True, emb_dropout=0.1, net_dropout=0.08, embedding_regularizer=0.07)
     else:
         raise ValueError(name)
+    kw.setdefault("dim_head", 10)
+    kw.setdefault("depth", 4)
     kw.update(over)
-    return ModelSpec(features=feats, model=model, dim_head=10, depth=4, **kw)
+    return ModelSpec(features=feats, model=model, **kw)
 
 
 def synthetic_pool(spec: ModelSpec, n_rows: int, seed: int, pos_ratio: float = 0.5,

@@ -278,7 +278,7 @@ def test_bn_act_forward(rn):
 
 
 # ------------------------------------------------------------------------------------------ whole forward
-@pytest.mark.parametrize("name", CASES_M2 + ["rat_m3_small"])
+@pytest.mark.parametrize("name", CASES_M2 + ["rat_m3_small", "rat_m0_small", "rat_m1_small"])
 def test_eval_forward_matches_reference_golden(rn, name):
     """engine forward (eval) vs the y_pred the REFERENCE produced (fixture). fp32: rtol 1e-4 atol 1e-5."""
     from tests.gpu_util import assert_close, make_engine

@@ -18,8 +18,11 @@ namespace rat {
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 
+extern long long g_launches;     // kernels launched by this library (one RAT_CHECK_LAUNCH per launch)
+
 #define RAT_CHECK_LAUNCH(what)                                  \
     do {                                                        \
+        ++rat::g_launches;                                      \
         cudaError_t _e = cudaGetLastError();                    \
         if (_e != cudaSuccess) return rat::cuda_fail(_e, what); \
     } while (0)

@@ -7,6 +7,7 @@
 namespace rat {
 
 static thread_local char g_err[512] = "";
+long long g_launches = 0;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -36,6 +37,7 @@ int max_smem_optin() { if (!g_smem) query(); return g_smem; }
 
 extern "C" const char* rat_last_error(void) { return rat::g_err; }
 extern "C" int rat_abi_version(void) { return RAT_ABI_VERSION; }
+extern "C" long long rat_launch_count(void) { return rat::g_launches; }
 
 extern "C" int rat_device_check(void) {
     int dev = 0;

@@ -151,6 +151,17 @@ __global__ void k_dropout_bwd(float* __restrict__ g, long long n, float p, unsig
         g[e] *= dropout_scale(seed, stream, (unsigned long long)e, p, inv_keep);
 }
 
+// dst[r*dst_stride + d] = src[r*src_stride + d], d < D  (token-0 pooling of RAT_m1 and its backward scatter)
+__global__ void k_strided_copy(const float* __restrict__ src, float* __restrict__ dst, long long rows, int D,
+                               long long src_stride, long long dst_stride) {
+    const long long total = rows * D;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / D;
+        const int d = (int)(i % D);
+        dst[r * dst_stride + d] = src[r * src_stride + d];
+    }
+}
+
 static int grid_for(long long total, int block) {
     long long g = (total + block - 1) / block;
     long long cap = (long long)num_sms() * 32;
@@ -208,5 +219,13 @@ extern "C" int rat_dropout_bwd(float* grad, long long n, float p, unsigned long 
     if (p <= 0.f) return RAT_OK;
     k_dropout_bwd<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(grad, n, p, seed, rng_stream);
     RAT_CHECK_LAUNCH("k_dropout_bwd");
+    return RAT_OK;
+}
+
+extern "C" int rat_strided_copy(const float* src, float* dst, long long rows, int D, long long src_stride,
+                                long long dst_stride, void* stream) {
+    RAT_REQUIRE(rows > 0 && D > 0, "rat_strided_copy: bad shape");
+    k_strided_copy<<<grid_for(rows * D, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, rows, D, src_stride, dst_stride);
+    RAT_CHECK_LAUNCH("k_strided_copy");
     return RAT_OK;
 }

@@ -19,7 +19,8 @@ _SCALARS = {
     "int": ctypes.c_int, "long long": ctypes.c_longlong, "float": ctypes.c_float, "double": ctypes.c_double,
     "unsigned long long": ctypes.c_ulonglong, "unsigned int": ctypes.c_uint, "size_t": ctypes.c_size_t,
 }
-_RET = {"int": ctypes.c_int, "size_t": ctypes.c_size_t, "const char*": ctypes.c_char_p}
+_RET = {"int": ctypes.c_int, "size_t": ctypes.c_size_t, "const char*": ctypes.c_char_p,
+        "long long": ctypes.c_longlong}
 
 
 class RatError(RuntimeError):
@@ -32,7 +33,7 @@ def parse_header(path: str = HEADER) -> Dict[str, Tuple[str, List[Tuple[str, str
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     src = re.sub(r"//[^\n]*", "", src)
     protos = {}
-    for m in re.finditer(r"(const char\*|int|size_t)\s+(rat_\w+)\s*\(([^)]*)\)\s*;", src):
+    for m in re.finditer(r"(const char\*|int|size_t|long long)\s+(rat_\w+)\s*\(([^)]*)\)\s*;", src):
         ret, name, args = m.group(1), m.group(2), m.group(3).strip()
         parsed = []
         if args and args != "void":
@@ -89,11 +90,36 @@ def _ptr(x):
     return x
 
 
+_profile = None      # {name: [(start_event, end_event), ...]} while profiling
+
+
+def profile_calls(enable: bool):
+    """Record a CUDA-event pair around every entry-point call (bench.py's per-kernel timing pass)."""
+    global _profile
+    _profile = {} if enable else None
+
+
+def profile_results():
+    """{name: (n_calls, total_ms)}; call after torch.cuda.synchronize()."""
+    out = {}
+    for name, pairs in (_profile or {}).items():
+        out[name] = (len(pairs), sum(a.elapsed_time(b) for a, b in pairs))
+    return out
+
+
 def call(name: str, *args):
     """Call an int-returning entry point with torch tensors / scalars; raise RatError on failure."""
     L = lib()
     f = L.fn[name]
-    rc = f(*[_ptr(a) for a in args])
+    if _profile is not None:
+        import torch
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = f(*[_ptr(x) for x in args])
+        b.record()
+        _profile.setdefault(name, []).append((a, b))
+    else:
+        rc = f(*[_ptr(a) for a in args])
     if L.protos[name][0] == "int" and rc != 0 and not name.endswith(("_blocks", "_version")):
         raise RatError(f"{name} failed (rc={rc}): {L.last_error()}")
     return rc

@@ -285,8 +285,10 @@ class RatEngine:
             loss=torch.zeros(2, **f32),
             dnn_out=torch.empty(B, **f32) if len(s.dnn_hidden_units) else None,
         )
-        n_act = self._num_acts() if training else 3
+        n_act = self._num_acts() if (training or s.model in ("RAT_m0", "RAT_m1")) else 3
         ws["acts"] = [torch.empty(B, T, N, D, **f32) for _ in range(n_act)]
+        ws["acts_c"] = [torch.empty(B, T, D, **f32) for _ in range(n_act)] if s.model == "RAT_m1" else None
+        ws["enc_stride"] = T * D if s.model == "RAT_m1" else T * N * D
         units = list(s.dnn_hidden_units)
         ws["z"] = [torch.empty(B, u, **f32) for u in units]
         ws["h"] = [torch.empty(B, u, **f32) for u in units]
@@ -304,12 +306,17 @@ class RatEngine:
             ws["dact"] = torch.empty(B, T, N, D, **f32)
             ws["dact2"] = torch.empty(B, T, N, D, **f32) if s.model == "RAT_m3" else None
             ws["dlogit"] = torch.empty(B, **f32)
-            ws["denc"] = ws["dact"]
+            ws["dact_c"] = torch.empty(B, T, D, **f32) if s.model == "RAT_m1" else None
+            ws["denc"] = ws["dact_c"] if s.model == "RAT_m1" else ws["dact"]
             ws["dxemb"] = torch.zeros(B, F * D, **f32)
             ws["dh"] = [torch.empty(B, u, **f32) for u in units]
             hh, dd = (max(1, int(H / 2)), (H * dh) // max(1, int(H / 2))) if s.model == "RAT_m3" else (H, dh)
-            nb = max(int(query("rat_attn_bwd_workspace_bytes", B, T, N, D, hh, dd, 0)),
-                     int(query("rat_attn_bwd_workspace_bytes", B, T, N, D, hh, dd, 1)),
+            shapes = {"RAT_m0": [(B, 1, T * N, 0)], "RAT_m1": [(B, T, N, 0), (B, 1, T, 0)]}.get(
+                s.model, [(B, T, N, 0), (B, T, N, 1)])
+            sizes = [int(query("rat_attn_bwd_workspace_bytes", b_, t_, n_, D, hh, dd, m_)) for b_, t_, n_, m_ in shapes]
+            if min(sizes) == 0:
+                raise RuntimeError("RAT attention backward: a sequence tile does not fit in shared memory")
+            nb = max(max(sizes),
                      int(query("rat_ff_bwd_workspace_bytes", B * T * N, D, M)),
                      int(query("rat_layernorm_bwd_workspace_bytes", B * T * N, D)))
             if nb == 0:
@@ -324,7 +331,7 @@ class RatEngine:
         s = self.spec
         if s.model in ("RAT_m2", "RAT_m3"):
             return 3 * s.depth + 1
-        raise NotImplementedError(s.model)
+        return 2 * s.depth + 2          # RAT_m0 / RAT_m1 Transformer: (attn, ff) per layer + final LayerNorm
 
     # ------------------------------------------------------------------ inputs
     def load_wire(self, X: torch.Tensor, y: torch.Tensor, training: bool):
@@ -393,7 +400,38 @@ class RatEngine:
                 self._ff(acts[i2], acts[i0], acts[i3], pre + "mlp.", rows)
                 cur = i3
             return acts[cur]
+        if s.model == "RAT_m0":         # one flat sequence of T*N tokens per sample (RAT_m0.py:123-127)
+            return self._transformer_fwd(acts, "encoder.", B, 1, T * N)
+        if s.model == "RAT_m1":         # intra Transformer -> token 0 of every row -> cross Transformer
+            z = self._transformer_fwd(acts, "intra_transformer.", B, T, N)
+            c = ws["acts_c"]
+            call("rat_strided_copy", z, c[0], B * T, s.embedding_dim, N * s.embedding_dim, s.embedding_dim,
+                 current_stream())
+            return self._transformer_fwd(c, "cross_transformer.", B, 1, T)
         raise NotImplementedError(s.model)
+
+    def _transformer_fwd(self, a, prefix, B, T, N):
+        """vit-style pre-norm Transformer (RAT_m0.py:193-208) over [B,T,N,D] with sequences = rows of N tokens."""
+        s = self.spec
+        rows = B * T * N
+        for l in range(s.depth):
+            self._attn(a[2 * l], a[2 * l], a[2 * l + 1], f"{prefix}layers.{l}.0.", 0, B, T, N)
+            self._ff(a[2 * l + 1], a[2 * l + 1], a[2 * l + 2], f"{prefix}layers.{l}.1.fn.", rows,
+                     ln=f"{prefix}layers.{l}.1.norm.")
+        out = a[2 * s.depth + 1]
+        call("rat_layernorm_fwd", a[2 * s.depth], out, self.p[prefix + "norm.weight"], self.p[prefix + "norm.bias"],
+             rows, s.embedding_dim, current_stream())
+        return out
+
+    def _transformer_bwd(self, ws, a, d, prefix, B, T, N):
+        s, g = self.spec, self.store.grad_views
+        rows = B * T * N
+        bw = ws["bwd_ws"]
+        call("rat_layernorm_bwd", a[2 * s.depth], d, d, self.p[prefix + "norm.weight"], g[prefix + "norm.weight"],
+             g[prefix + "norm.bias"], rows, s.embedding_dim, bw, bw.numel() * 4, current_stream())
+        for l in reversed(range(s.depth)):
+            self._ff_bwd(ws, a[2 * l + 1], d, d, d, f"{prefix}layers.{l}.1.fn.", rows, ln=f"{prefix}layers.{l}.1.norm.")
+            self._attn_bwd(ws, a[2 * l], d, d, d, f"{prefix}layers.{l}.0.", 0, B, T, N)
 
     def _dnn_forward(self, ws, B, training):
         s, p, st = self.spec, self.p, current_stream()
@@ -449,7 +487,7 @@ class RatEngine:
             self._dnn_forward(ws, B, training)
         N = F + 1
         want_loss = with_loss or training
-        call("rat_head", enc, T * N * D, self.p["fc.weight"], self.p["fc.bias"], ws["dnn_out"], ws["lr_out"],
+        call("rat_head", enc, ws["enc_stride"], self.p["fc.weight"], self.p["fc.bias"], ws["dnn_out"], ws["lr_out"],
              ws["y_true"] if want_loss else None, B, D, ws["y_pred"], ws.get("dlogit") if training else None,
              ws.get("denc") if training else None, float(inv_count if inv_count else 1.0 / B),
              ws["loss_part"] if want_loss else None, ws["loss"][0:1] if want_loss else None,
@@ -519,6 +557,16 @@ class RatEngine:
                                self.p[pre + "W_q.weight"], self.p[pre + "W_k_s.weight"], self.p[pre + "W_v_s.weight"],
                                (pre + "W_q.weight", pre + "W_k_s.weight", pre + "W_v_s.weight"), 1)
             return d
+        if s.model == "RAT_m0":
+            self._transformer_bwd(ws, acts, d, "encoder.", B, 1, T * N)
+            return d
+        if s.model == "RAT_m1":
+            dc = ws["dact_c"]
+            self._transformer_bwd(ws, ws["acts_c"], dc, "cross_transformer.", B, 1, T)
+            call("rat_strided_copy", dc, d, B * T, s.embedding_dim, s.embedding_dim, N * s.embedding_dim,
+                 current_stream())          # d was zeroed by train_step_ids: only token 0 of each row gets gradient
+            self._transformer_bwd(ws, acts, d, "intra_transformer.", B, T, N)
+            return d
         raise NotImplementedError(s.model)
 
     def _dnn_backward(self, ws, B):
@@ -563,7 +611,7 @@ class RatEngine:
         N, D, F, L = s.F + 1, s.embedding_dim, s.F, s.L
         enc = ws["enc_out"]
         # fc
-        call("rat_sgemm", ws["dlogit"], enc, g["fc.weight"], None, 1, D, B, 1, T * N * D, D, 1, 1, None, 0, st)
+        call("rat_sgemm", ws["dlogit"], enc, g["fc.weight"], None, 1, D, B, 1, ws["enc_stride"], D, 1, 1, None, 0, st)
         call("rat_colsum", ws["dlogit"], B, 1, 1, g["fc.bias"], st)
         has_dnn = len(s.dnn_hidden_units) > 0
         if has_dnn:
@@ -597,6 +645,8 @@ class RatEngine:
         [sum BCE, mean BCE of the local shard]; opt_state[5] holds the regularisation loss."""
         self.rng_step += 1
         ws["dact"].zero_()
+        if ws.get("dact_c") is not None:
+            ws["dact_c"].zero_()
         self.forward_ids(ws, B, T, training=True, inv_count=1.0 / (B * self.world))
         self.backward(ws, B, T)
         self.optimizer_step()
