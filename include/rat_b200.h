@@ -31,6 +31,11 @@ long long rat_launch_count(void);
 /* 0 if an sm_100 device is current, else RAT_ECUDA (the product path refuses to run anywhere else) */
 int rat_device_check(void);
 
+/* Arithmetic of the RAT-block projections: 1 (default) = tensor cores, mma.sync TF32 operands with fp32
+ * accumulate (parity tolerance 3e-3 relative); 0 = exact fp32 on the SIMT pipe (parity anchor, ~1e-5). */
+int rat_set_precision(int tf32);
+int rat_get_precision(void);
+
 /* ---------------------------------------------------------------------------------------------------------
  * K0: batch assembly
  * ------------------------------------------------------------------------------------------------------- */

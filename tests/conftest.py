@@ -25,3 +25,16 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(params=["fp32", "tf32"])
+def precision(request):
+    """run a GPU test in both arithmetic modes of the RAT-block projections."""
+    import rat_native
+    from rat_native.engine import set_precision
+    from tests import gpu_util
+    set_precision(request.param)
+    gpu_util.PREC["mode"] = request.param
+    yield request.param
+    set_precision("tf32")
+    gpu_util.PREC["mode"] = "tf32"

@@ -6,6 +6,19 @@ from oracle import rat_oracle as O
 from rat_native.engine import EngineSpec, FeatureSpec, RatEngine
 
 
+PREC = {"mode": "fp32"}
+
+
+def tf32():
+    return PREC["mode"] == "tf32"
+
+
+def ptol(rtol, atol, rt=1e-2, at_scale=40.0):
+    """(rtol, atol) for the current precision mode: fp32 values as given; tf32 (10-bit mantissa operands,
+    fp32 accumulate): rtol 1e-2 and atol x40."""
+    return (max(rtol, rt), atol * at_scale) if tf32() else (rtol, atol)
+
+
 def to_engine_spec(spec: O.ModelSpec, **over) -> EngineSpec:
     feats = [FeatureSpec(f.name, f.type, f.vocab_size, f.max_len, f.padding_idx) for f in spec.features]
     kw = dict(features=feats, model=spec.model, embedding_dim=spec.embedding_dim, num_heads=spec.num_heads,

@@ -37,6 +37,8 @@ def _model_from_case(c, tmp_path, **over):
 def test_state_dict_keys_and_forward_match_reference(name, tmp_path):
     """state_dict key set/shapes == the reference's (checkpoint compatibility), and after load_state_dict of the
     reference weights, forward() returns the reference's y_pred (fixture), as [B,1] tensors like RAT_m2.py:151."""
+    from rat_native.engine import set_precision
+    set_precision("fp32")           # strict parity anchor; the default TF32 mode is covered in test_gpu_backward.py
     c = load_case(name)
     model, fm = _model_from_case(c, tmp_path)
     sd = model.state_dict()
@@ -68,6 +70,7 @@ def test_state_dict_keys_and_forward_match_reference(name, tmp_path):
     model.load_weights(model.checkpoint)
     for k, v in model.state_dict().items():
         assert torch.equal(v, before[k]), k
+    set_precision("tf32")
 
 
 def _write_dataset(tmp_path, fm, n_train=1500, n_valid=400, K=5, seed=0):

@@ -6,23 +6,20 @@
 //   k_ff_bwd   : same for the FeedForward sub-block.
 //   k_ln_bwd   : final-LayerNorm backward (RAT_m0/m1).
 //
-// These replace autograd's reverse of RAT_m2.py:155-236 (a11 in SURVEY.md 8a).  Weight gradients are accumulated
-// in shared memory over all tiles a CTA owns (static tile->CTA map), written once to a per-CTA partial buffer
-// and summed over CTAs in fixed order by k_reduce_partials  => bitwise run-to-run deterministic.
+// These replace autograd's reverse of RAT_m2.py:155-236 (a11 in SURVEY.md 8a).  One persistent CTA per SM keeps
+// the sub-block's weights resident in shared memory (natural layout: the same copy is the n-major operand of the
+// forward recompute and the k-major operand of the data-gradient product).  All seven products per head chunk run
+// on the tensor cores (mma.sync TF32) or on the exact SIMT twin (precision=fp32).  Weight-gradient products
+// (reduction over token rows) accumulate into a CTA-private record in global memory (L2 resident, every element
+// owned by one thread, static tile->CTA map), and k_reduce_* sums the records over CTAs in fixed order
+// => bitwise run-to-run deterministic.
 #include "tile.cuh"
+#include "encoder_common.cuh"
 #include "../../include/rat_b200.h"
 
 namespace rat {
 
-static inline int next_pow2_(int v) { int p = 1; while (p < v) p <<= 1; return p; }
-
-constexpr int BWD_THREADS = 512;
-
-struct AttnBwdPlan {
-    int SPT, hc, Dp, Cq, Cqp, C3p, lg, lpt, nchunks;
-    int psize;            // floats in one CTA's partial-gradient record
-    size_t smem_bytes;
-};
+int precision_mode();
 
 struct AttnBwdArgs {
     const float* x; const float* dout; const float* base; float* dx;
@@ -33,150 +30,8 @@ struct AttnBwdArgs {
     SeqGeom g;
     int D, H, I;
     float scale, alpha;
-    AttnBwdPlan p;
+    AttnPlan p;
 };
-
-// ---- attention pieces ---------------------------------------------------------------------------------------
-// forward recompute: o -> os, logsumexp -> lse   (q,k,v left intact)
-template <int DH>
-__device__ __forceinline__ void attn_fwd_recompute(const float* __restrict__ qkv, int ld, int Cq, float* __restrict__ os,
-                                                   int ldo, float* __restrict__ lse, int nseq_tile, int S, int hc,
-                                                   int lpt, float scale) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const int tpw = 32 / lpt, ntasks = nseq_tile * hc, sub = lane / lpt, li = lane % lpt;
-    for (int task0 = warp * tpw; task0 < ntasks; task0 += nwarps * tpw) {
-        const int task = task0 + sub;
-        if (task >= ntasks) continue;
-        const int ls = task / hc, hl = task % hc;
-        const float* base = qkv + (size_t)ls * S * ld + hl * DH;
-        for (int i = li; i < S; i += lpt) {
-            float q[DH], acc[DH];
-            const float* qrow = base + (size_t)i * ld;
-#pragma unroll
-            for (int d = 0; d < DH; ++d) { q[d] = qrow[d] * scale; acc[d] = 0.f; }
-            float m = -INFINITY, l = 0.f;
-            for (int j = 0; j < S; ++j) {
-                const float* krow = base + (size_t)j * ld + Cq;
-                const float* vrow = krow + Cq;
-                float sc = 0.f;
-#pragma unroll
-                for (int d = 0; d < DH; ++d) sc = fmaf(q[d], krow[d], sc);
-                const float mn = fmaxf(m, sc), corr = expf(m - mn), pj = expf(sc - mn);
-                l = fmaf(l, corr, pj);
-#pragma unroll
-                for (int d = 0; d < DH; ++d) acc[d] = fmaf(acc[d], corr, pj * vrow[d]);
-                m = mn;
-            }
-            const float inv = 1.0f / l;
-            float* orow = os + (size_t)(ls * S + i) * ldo + hl * DH;
-#pragma unroll
-            for (int d = 0; d < DH; ++d) orow[d] = acc[d] * inv;
-            lse[(ls * S + i) * hc + hl] = m + logf(l);
-        }
-    }
-}
-
-// softmax/attention backward.  Lane i as a query row -> dq_i ; lane j as a key row -> dk_j, dv_j.
-//   P_ij = exp(scale q_i.k_j - L_i) ; dP_ij = do_i.v_j ; dS_ij = P_ij (dP_ij - delta_i)
-template <int DH>
-__device__ __forceinline__ void attn_bwd_core(const float* __restrict__ qkv, float* __restrict__ dqkv, int ld, int Cq,
-                                              const float* __restrict__ dos, int ldo, const float* __restrict__ lse,
-                                              const float* __restrict__ delta, int nseq_tile, int S, int hc, int lpt,
-                                              float scale) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const int tpw = 32 / lpt, ntasks = nseq_tile * hc, sub = lane / lpt, li = lane % lpt;
-    for (int task0 = warp * tpw; task0 < ntasks; task0 += nwarps * tpw) {
-        const int task = task0 + sub;
-        if (task >= ntasks) continue;
-        const int ls = task / hc, hl = task % hc;
-        const size_t row0 = (size_t)ls * S;
-        const float* base = qkv + row0 * ld + hl * DH;
-        float* dbase = dqkv + row0 * ld + hl * DH;
-        const float* dobase = dos + row0 * ldo + hl * DH;
-        // ---- query role: dq_i
-        for (int i = li; i < S; i += lpt) {
-            float q[DH], dov[DH], dq[DH];
-            const float* qrow = base + (size_t)i * ld;
-            const float* dorow = dobase + (size_t)i * ldo;
-#pragma unroll
-            for (int d = 0; d < DH; ++d) { q[d] = qrow[d] * scale; dov[d] = dorow[d]; dq[d] = 0.f; }
-            const float Li = lse[(row0 + i) * hc + hl], di = delta[(row0 + i) * hc + hl];
-            for (int j = 0; j < S; ++j) {
-                const float* krow = base + (size_t)j * ld + Cq;
-                const float* vrow = krow + Cq;
-                float sc = 0.f, dp = 0.f;
-#pragma unroll
-                for (int d = 0; d < DH; ++d) { sc = fmaf(q[d], krow[d], sc); dp = fmaf(dov[d], vrow[d], dp); }
-                const float ds = expf(sc - Li) * (dp - di);
-#pragma unroll
-                for (int d = 0; d < DH; ++d) dq[d] = fmaf(ds, krow[d], dq[d]);
-            }
-            float* dqrow = dbase + (size_t)i * ld;
-#pragma unroll
-            for (int d = 0; d < DH; ++d) dqrow[d] = dq[d] * scale;
-        }
-        // ---- key role: dk_j, dv_j
-        for (int j = li; j < S; j += lpt) {
-            float k[DH], v[DH], dk[DH], dv[DH];
-            const float* krow = base + (size_t)j * ld + Cq;
-#pragma unroll
-            for (int d = 0; d < DH; ++d) { k[d] = krow[d]; v[d] = krow[Cq + d]; dk[d] = 0.f; dv[d] = 0.f; }
-            for (int i = 0; i < S; ++i) {
-                const float* qrow = base + (size_t)i * ld;
-                const float* dorow = dobase + (size_t)i * ldo;
-                float sc = 0.f, dp = 0.f;
-#pragma unroll
-                for (int d = 0; d < DH; ++d) { sc = fmaf(qrow[d], k[d], sc); dp = fmaf(dorow[d], v[d], dp); }
-                const float p = expf(sc * scale - lse[(row0 + i) * hc + hl]);
-                const float ds = p * (dp - delta[(row0 + i) * hc + hl]);
-#pragma unroll
-                for (int d = 0; d < DH; ++d) { dk[d] = fmaf(ds, qrow[d], dk[d]); dv[d] = fmaf(p, dorow[d], dv[d]); }
-            }
-            float* dkrow = dbase + (size_t)j * ld + Cq;
-#pragma unroll
-            for (int d = 0; d < DH; ++d) { dkrow[d] = dk[d] * scale; dkrow[Cq + d] = dv[d]; }
-        }
-    }
-}
-
-// stage W chunk in natural layout: Wn[c][d] (c in q|k|v chunk columns, zero padded to C3p x Dp)
-__device__ __forceinline__ void stage_qkv_natural(const float* __restrict__ Wq, const float* __restrict__ Wk,
-                                                  const float* __restrict__ Wv, int D, int Dp, int row0, int Cq,
-                                                  int C3p, float* __restrict__ Wn) {
-    const int total = C3p * Dp;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int d = i % Dp, c = i / Dp;
-        float v = 0.f;
-        if (d < D) {
-            if (c < Cq) v = __ldg(Wq + (size_t)(row0 + c) * D + d);
-            else if (c < 2 * Cq) v = __ldg(Wk + (size_t)(row0 + c - Cq) * D + d);
-            else if (c < 3 * Cq) v = __ldg(Wv + (size_t)(row0 + c - 2 * Cq) * D + d);
-        }
-        Wn[i] = v;
-    }
-}
-// WoN[d][c] = Wo[d][col0 + c]  (d < D rows, c < Cqp cols zero padded)
-__device__ __forceinline__ void stage_out_natural(const float* __restrict__ Wo, int D, int I, int col0, int Cq, int Cqp,
-                                                  float* __restrict__ WoN) {
-    const int total = D * Cqp;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int c = i % Cqp, d = i / Cqp;
-        WoN[i] = (c < Cq) ? __ldg(Wo + (size_t)d * I + col0 + c) : 0.f;
-    }
-}
-__device__ __forceinline__ void stage_qkv_T(const float* __restrict__ Wq, const float* __restrict__ Wk,
-                                            const float* __restrict__ Wv, int D, int row0, int Cq, int C3p,
-                                            float* __restrict__ Wt) {
-    const int total = C3p * D;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int k = i % D, c = i / D;
-        float v = 0.f;
-        if (c < Cq) v = __ldg(Wq + (size_t)(row0 + c) * D + k);
-        else if (c < 2 * Cq) v = __ldg(Wk + (size_t)(row0 + c - Cq) * D + k);
-        else if (c < 3 * Cq) v = __ldg(Wv + (size_t)(row0 + c - 2 * Cq) * D + k);
-        Wt[(size_t)k * C3p + c] = v;
-    }
-}
 
 // LayerNorm backward over the R rows of a tile + deterministic accumulation of per-column sums.
 //   g = grad wrt LN output (smem, ld) ; dx[gr] = base[gr] + rstd*(g*gamma - mean(g*gamma) - xhat*mean(g*gamma*xhat))
@@ -249,139 +104,137 @@ __device__ __forceinline__ void ln_bwd_rows(const float* __restrict__ x, const f
     }
 }
 
-template <int DH>
-__global__ void __launch_bounds__(BWD_THREADS, 1) k_attn_bwd(AttnBwdArgs a) {
+template <int DH, bool MMA>
+__global__ void __launch_bounds__(ENC_THREADS, 1) k_attn_bwd(AttnBwdArgs a) {
     extern __shared__ __align__(16) float smem[];
-    const AttnBwdPlan& p = a.p;
-    const int S = a.g.S, D = a.D, Dp = p.Dp, C3p = p.C3p, Cq = p.Cq, Cqp = p.Cqp;
-    const int Rmax = p.SPT * S;
-    float* as = smem;                                  // [Rmax][Dp] LN(x)
-    float* da = as + (size_t)Rmax * Dp;                // [Rmax][Dp] grad wrt LN output
-    float* dys = da + (size_t)Rmax * Dp;               // [Rmax][Dp] alpha*dout
-    float* qkv = dys + (size_t)Rmax * Dp;              // [Rmax][C3p]
-    float* dqkv = qkv + (size_t)Rmax * C3p;            // [Rmax][C3p]
-    float* os = dqkv + (size_t)Rmax * C3p;             // [Rmax][Cqp]
-    float* dos = os + (size_t)Rmax * Cqp;              // [Rmax][Cqp]
-    float* stats = dos + (size_t)Rmax * Cqp;           // [Rmax][2]  mean, rstd
-    float* lse = stats + (size_t)round_up(2 * Rmax, 4);        // [Rmax][hc]
-    float* delta = lse + (size_t)round_up(Rmax * p.hc, 4);     // [Rmax][hc]
-    float* Wt = delta + (size_t)round_up(Rmax * p.hc, 4);      // [D][C3p]
-    float* Wn = Wt + (size_t)D * C3p;                  // [C3p][Dp]
-    float* WoN = Wn + (size_t)C3p * Dp;                // [D][Cqp]
-    float* gW = WoN + (size_t)D * Cqp;                 // [nchunks][C3p][Dp]
-    float* gWo = gW + (size_t)p.nchunks * C3p * Dp;    // [nchunks][Dp][Cqp]
-    float* g3 = gWo + (size_t)p.nchunks * Dp * Cqp;    // [3][Dp] dgamma, dbeta, dbo
-    float* scratch = g3 + 3 * Dp;                      // [groups][3][Dp]
-    {
-        const int nacc = p.nchunks * C3p * Dp + p.nchunks * Dp * Cqp + 3 * Dp;
-        for (int i = threadIdx.x; i < nacc; i += blockDim.x) gW[i] = 0.f;
-    }
+    const AttnPlan& p = a.p;
+    const int S = a.g.S, D = a.D, Dl = p.Dl, C3l = p.C3l, Cql = p.Cql, Il = p.Il, Dp8 = p.Dp8;
+    const int Rmax = p.Rmax16;
+    float* Wc = smem;                                   // [nchunks][C3p8][Dl]
+    float* WoN = Wc + (size_t)p.nchunks * p.C3p8 * Dl;  // [Dp8][Il]
+    float* g3 = WoN + (size_t)Dp8 * Il;                 // [3][Dp8] dgamma, dbeta, dbo
+    float* scratch = g3 + 3 * Dp8;                      // [groups][3][Dp8]
+    float* stats = scratch + (size_t)(ENC_THREADS / p.lg) * 3 * Dp8;   // [Rmax][2]
+    float* lse = stats + 2 * Rmax;                      // [Rmax][hc]
+    float* delta = lse + (size_t)Rmax * p.hc;           // [Rmax][hc]
+    float* as = delta + (size_t)Rmax * p.hc;            // [Rmax][Dl] LN(x)
+    float* da = as + (size_t)Rmax * Dl;                 // [Rmax][Dl] grad wrt LN output
+    float* dys = da + (size_t)Rmax * Dl;                // [Rmax][Dl] alpha*dout
+    float* qkv = dys + (size_t)Rmax * Dl;               // [Rmax][C3l]
+    float* dqkv = qkv + (size_t)Rmax * C3l;             // [Rmax][C3l]
+    float* os = dqkv + (size_t)Rmax * C3l;              // [Rmax][Cql]
+    float* dos = os + (size_t)Rmax * Cql;               // [Rmax][Cql]
+    // CTA-private gradient record in global memory: [gW nchunks*C3p8*Dl | gWo Dp8*Il | small 3*Dp8]
+    float* rec = a.partials + (size_t)blockIdx.x * p.psize;
+    float* gW = rec;
+    float* gWo = gW + (size_t)p.nchunks * p.C3p8 * Dl;
+    stage_qkv_chunks(a.Wq, a.Wk, a.Wv, D, p, Wc);
+    stage_padded(a.Wo, D, a.I, Dp8, Il, WoN);
+    zero_floats(g3, 3 * Dp8);
+    zero_floats(as, (size_t)Rmax * (3 * Dl + 2 * C3l + 2 * Cql));
+    for (int i = threadIdx.x; i < p.psize; i += blockDim.x) rec[i] = 0.f;
     const long long ntiles = (a.nseq + p.SPT - 1) / p.SPT;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long s0 = tile * p.SPT;
         const int nseq_t = (int)min((long long)p.SPT, a.nseq - s0);
-        const int R = nseq_t * S;
+        const int R = nseq_t * S, R16 = pad16(R), R8 = pad8(R);
         __syncthreads();
-        {
-            // LayerNorm forward recompute (as + stats)
-            const int lg = p.lg, groups = blockDim.x / lg, gi = threadIdx.x / lg, li = threadIdx.x % lg;
-            const float invD = 1.0f / (float)D;
-            for (int r0 = 0; r0 < R; r0 += groups) {
-                const int r = r0 + gi;
-                const bool ok = r < R;
-                const float* src = a.x;
-                if (ok) src = a.x + a.g.grow(s0 + r / S, r % S) * D;
-                float sum = 0.f;
-                if (ok) for (int d = li; d < D; d += lg) sum += src[d];
-                const float mean = group_sum(sum, lg) * invD;
-                float sq = 0.f;
-                if (ok) for (int d = li; d < D; d += lg) { float t = src[d] - mean; sq = fmaf(t, t, sq); }
-                const float rstd = 1.0f / sqrtf(group_sum(sq, lg) * invD + 1e-5f);
-                if (ok) {
-                    for (int d = li; d < D; d += lg)
-                        as[(size_t)r * Dp + d] = (src[d] - mean) * rstd * a.ln_w[d] + a.ln_b[d];
-                    for (int d = D + li; d < Dp; d += lg) as[(size_t)r * Dp + d] = 0.f;
-                    if (li == 0) { stats[2 * r] = mean; stats[2 * r + 1] = rstd; }
-                }
-            }
-        }
-        for (int i = threadIdx.x; i < R * Dp; i += blockDim.x) {
-            const int r = i / Dp, d = i % Dp;
+        ln_rows_to_smem(a.x, a.g, s0, R, D, Dp8, a.ln_w, a.ln_b, as, Dl, p.lg, stats);
+        for (int i = threadIdx.x; i < R * Dl; i += blockDim.x) {
+            const int r = i / Dl, d = i - r * Dl;
             da[i] = 0.f;
             float v = 0.f;
             if (d < D) v = a.alpha * a.dout[a.g.grow(s0 + r / S, r % S) * D + d];
             dys[i] = v;
         }
+        zero_rows(as, Dl, R, R16);
+        zero_rows(da, Dl, R, R16);
+        zero_rows(dys, Dl, R, R16);
+        zero_rows(os, Cql, R, R16);
+        zero_rows(dqkv, C3l, R, R16);
         for (int ch = 0; ch < p.nchunks; ++ch) {
-            const int row0 = ch * Cq;
+            const float* W = Wc + (size_t)ch * p.C3p8 * Dl;
+            const int col0 = ch * p.Cq;
             __syncthreads();
-            stage_qkv_T(a.Wq, a.Wk, a.Wv, D, row0, Cq, C3p, Wt);
-            stage_qkv_natural(a.Wq, a.Wk, a.Wv, D, Dp, row0, Cq, C3p, Wn);
-            stage_out_natural(a.Wo, D, a.I, row0, Cq, Cqp, WoN);
+            // (1) qkv[r][c] = sum_d as[r][d] W[c][d] ; (3) dos[r][c] = sum_d dys[r][d] Wo[d][col0+c]
+            tc_gemm<MMA, 4>(as, Dl, 1, W, 1, Dl, qkv, C3l, R, p.C3p8, Dp8, false, EpiNone2());
+            tc_gemm<MMA, 3>(dys, Dl, 1, WoN + col0, Il, 1, dos, Cql, R, p.Cq8, Dp8, false, EpiNone2());
             __syncthreads();
-            // (1) qkv = as . Wt ; (3) dos = dys . WoN
-            tile_gemm<4>(as, Dp, Wt, C3p, qkv, C3p, R, C3p, D, false, EpiNone());
-            tile_gemm<4>(dys, Dp, WoN, Cqp, dos, Cqp, R, Cqp, D, false, EpiNone());
-            __syncthreads();
-            // (2) attention forward recompute
-            attn_fwd_recompute<DH>(qkv, C3p, Cq, os, Cqp, lse, nseq_t, S, p.hc, p.lpt, a.scale);
-            if (Cqp > Cq)
-                for (int i = threadIdx.x; i < R * (Cqp - Cq); i += blockDim.x)
-                    os[(size_t)(i / (Cqp - Cq)) * Cqp + Cq + i % (Cqp - Cq)] = 0.f;
+            // (2) attention forward recompute -> os, lse
+            attn_core<DH>(qkv, C3l, p.Cq, os, Cql, lse, nseq_t, S, p.hc, p.lpt, a.scale);
             __syncthreads();
             // delta[r][hl] = do . o
             for (int i = threadIdx.x; i < R * p.hc; i += blockDim.x) {
-                const int r = i / p.hc, hl = i % p.hc;
-                const float* o = os + (size_t)r * Cqp + hl * DH;
-                const float* dd = dos + (size_t)r * Cqp + hl * DH;
+                const int r = i / p.hc, hl = i - r * p.hc;
+                const float* o = os + (size_t)r * Cql + hl * DH;
+                const float* dd = dos + (size_t)r * Cql + hl * DH;
                 float s = 0.f;
 #pragma unroll
                 for (int d = 0; d < DH; ++d) s = fmaf(o[d], dd[d], s);
                 delta[i] = s;
             }
-            // (4) gWo[ch] += dys^T . os      [Dp][Cqp]
-            tile_gemm_tn_acc(dys, Dp, os, Cqp, gWo + (size_t)ch * Dp * Cqp, Cqp, R, Dp, Cqp);
+            // (4) gWo[d][col0+c] += sum_r dys[r][d] os[r][c]
+            tc_gemm<MMA, 3>(dys, 1, Dl, os, Cql, 1, gWo + col0, Il, Dp8, p.Cq8, R8, true, EpiNone2());
             __syncthreads();
-            // (5) attention backward -> dqkv (zero the pad columns first)
-            if (C3p > 3 * Cq)
-                for (int i = threadIdx.x; i < R * (C3p - 3 * Cq); i += blockDim.x)
-                    dqkv[(size_t)(i / (C3p - 3 * Cq)) * C3p + 3 * Cq + i % (C3p - 3 * Cq)] = 0.f;
-            attn_bwd_core<DH>(qkv, dqkv, C3p, Cq, dos, Cqp, lse, delta, nseq_t, S, p.hc, p.lpt, a.scale);
+            // (5) attention backward -> dqkv
+            attn_bwd_core<DH>(qkv, dqkv, C3l, p.Cq, dos, Cql, lse, delta, nseq_t, S, p.hc, p.lpt, a.scale);
             __syncthreads();
-            // (6) gW[ch] += dqkv^T . as      [C3p][Dp]   ; (7) da += dqkv . Wn
-            tile_gemm_tn_acc(dqkv, C3p, as, Dp, gW + (size_t)ch * C3p * Dp, Dp, R, C3p, Dp);
-            tile_gemm<4>(dqkv, C3p, Wn, Dp, da, Dp, R, Dp, C3p, true, EpiNone());
+            // (6) gW[ch][c][d] += sum_r dqkv[r][c] as[r][d] ; (7) da[r][d] += sum_c dqkv[r][c] W[c][d]
+            tc_gemm<MMA, 3>(dqkv, 1, C3l, as, Dl, 1, gW + (size_t)ch * p.C3p8 * Dl, Dl, p.C3p8, Dp8, R8, true, EpiNone2());
+            tc_gemm<MMA, 3>(dqkv, C3l, 1, W, Dl, 1, da, Dl, R, Dp8, p.C3p8, true, EpiNone2());
         }
         __syncthreads();
-        ln_bwd_rows(a.x, a.base, a.dx, a.g, s0, R, D, Dp, a.ln_w, da, Dp, stats, dys, Dp, p.lg, scratch, g3);
+        ln_bwd_rows(a.x, a.base, a.dx, a.g, s0, R, D, Dp8, a.ln_w, da, Dl, stats, dys, Dl, p.lg, scratch, g3);
     }
     __syncthreads();
-    // ---- flush the CTA-private partial sums in natural parameter layout:
-    //      [dWq I*D | dWk I*D | dWv I*D | dWo D*I | dbo D | dgamma D | dbeta D]
-    float* out = a.partials + (size_t)blockIdx.x * p.psize;
-    const int I = a.I;
-    for (int i = threadIdx.x; i < 3 * I * D; i += blockDim.x) {
-        const int which = i / (I * D), rem = i % (I * D);
-        const int row = rem / D, d = rem % D;
-        const int ch = row / Cq, c = row % Cq;
-        out[i] = gW[((size_t)ch * C3p + which * Cq + c) * Dp + d];
-    }
-    float* o2 = out + 3 * I * D;
-    for (int i = threadIdx.x; i < D * I; i += blockDim.x) {
-        const int d = i / I, col = i % I;
-        const int ch = col / Cq, c = col % Cq;
-        o2[i] = gWo[((size_t)ch * Dp + d) * Cqp + c];
-    }
-    float* o3 = o2 + D * I;
-    for (int i = threadIdx.x; i < D; i += blockDim.x) {
-        o3[i] = g3[2 * Dp + i];            // dbo  (sum of alpha*dout)
-        o3[D + i] = g3[0 * Dp + i];        // dgamma
-        o3[2 * D + i] = g3[1 * Dp + i];    // dbeta
+    float* small = gWo + (size_t)Dp8 * Il;
+    for (int i = threadIdx.x; i < 3 * Dp8; i += blockDim.x) small[i] = g3[i];     // dgamma | dbeta | dbo
+}
+
+// out[...] (+)= sum over CTA records, fixed order.  One thread per parameter-gradient element.
+struct AttnReduceArgs {
+    const float* partials; int nparts;
+    float* dWq; float* dWk; float* dWv; float* dWo; float* dbo; float* dln_w; float* dln_b;
+    int accumulate_wq, D, I;
+    AttnPlan p;
+};
+__global__ void k_reduce_attn(AttnReduceArgs a) {
+    const AttnPlan& p = a.p;
+    const int D = a.D, I = a.I;
+    const int total = 4 * I * D + 3 * D;
+    const size_t off_wo = (size_t)p.nchunks * p.C3p8 * p.Dl, off_small = off_wo + (size_t)p.Dp8 * p.Il;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        size_t src;
+        float* dst;
+        bool acc = false;
+        if (i < 3 * I * D) {
+            const int which = i / (I * D), rem = i - which * (I * D);
+            const int row = rem / D, d = rem - row * D;
+            const int ch = row / p.Cq, c = row - ch * p.Cq;
+            src = ((size_t)ch * p.C3p8 + which * p.Cq + c) * p.Dl + d;
+            dst = (which == 0 ? a.dWq : which == 1 ? a.dWk : a.dWv);
+            acc = which == 0 && a.accumulate_wq;
+            if (dst) dst += rem;
+        } else if (i < 4 * I * D) {
+            const int rem = i - 3 * I * D;
+            const int d = rem / I, col = rem - d * I;
+            src = off_wo + (size_t)d * p.Il + col;
+            dst = a.dWo ? a.dWo + rem : nullptr;
+        } else {
+            const int rem = i - 4 * I * D;
+            const int which = rem / D, d = rem - which * D;        // 0: dbo, 1: dgamma, 2: dbeta
+            src = off_small + (size_t)(which == 0 ? 2 : which == 1 ? 0 : 1) * p.Dp8 + d;
+            float* base = which == 0 ? a.dbo : which == 1 ? a.dln_w : a.dln_b;
+            dst = base ? base + d : nullptr;
+        }
+        if (!dst) continue;
+        float s = 0.f;
+        for (int c = 0; c < a.nparts; ++c) s += a.partials[(size_t)c * p.psize + src];
+        *dst = acc ? *dst + s : s;
     }
 }
 
 // ------------------------------------------------------------------------------------------------------------
-struct FFBwdPlan { int RPT, Dp, Mp, lg; int psize; size_t smem_bytes; };
 struct FFBwdArgs {
     const float* x; const float* dout; const float* base; float* dx;
     const float* ln_w; const float* ln_b;
@@ -389,117 +242,92 @@ struct FFBwdArgs {
     float* partials;
     long long rows;
     int D, M;
-    FFBwdPlan p;
+    FFPlan p;
 };
 
-struct EpiBias {
+struct EpiBias2 {
     const float* b;
-    __device__ __forceinline__ void operator()(int, int c0, float4& v) const {
-        v.x += b[c0]; v.y += b[c0 + 1]; v.z += b[c0 + 2]; v.w += b[c0 + 3];
-    }
+    __device__ __forceinline__ void operator()(int, int c, float& v0, float& v1) const { v0 += b[c]; v1 += b[c + 1]; }
 };
-// v = dh ; hs holds pre-activation: hs <- gelu(pre), v <- dh * gelu'(pre)
-struct EpiGeluBwd {
+// v = dh ; hs holds the pre-activation: hs <- gelu(pre), v <- dh * gelu'(pre)
+struct EpiGeluBwd2 {
     float* hs; int ld;
-    __device__ __forceinline__ void operator()(int r, int c0, float4& v) const {
-        float4* hp = reinterpret_cast<float4*>(hs + (size_t)r * ld + c0);
-        const float4 pre = *hp;
-        v.x *= gelu_erf_grad(pre.x); v.y *= gelu_erf_grad(pre.y); v.z *= gelu_erf_grad(pre.z); v.w *= gelu_erf_grad(pre.w);
-        *hp = make_float4(gelu_erf(pre.x), gelu_erf(pre.y), gelu_erf(pre.z), gelu_erf(pre.w));
+    __device__ __forceinline__ void operator()(int r, int c, float& v0, float& v1) const {
+        float2* hp = reinterpret_cast<float2*>(hs + (size_t)r * ld + c);
+        const float2 pre = *hp;
+        v0 *= gelu_erf_grad(pre.x);
+        v1 *= gelu_erf_grad(pre.y);
+        *hp = make_float2(gelu_erf(pre.x), gelu_erf(pre.y));
     }
 };
 
-__device__ __forceinline__ void stage_natural(const float* __restrict__ W, int Rw, int Cw, int Cp, float* __restrict__ dst) {
-    const int total = Rw * Cp;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int c = i % Cp, r = i / Cp;
-        dst[i] = (c < Cw) ? __ldg(W + (size_t)r * Cw + c) : 0.f;
-    }
-}
-__device__ __forceinline__ void stage_T(const float* __restrict__ W, int C, int K, int Cp, float* __restrict__ Wt) {
-    const int total = Cp * K;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int k = i % K, c = i / K;
-        Wt[(size_t)k * Cp + c] = (c < C) ? __ldg(W + (size_t)c * K + k) : 0.f;
-    }
-}
-
-__global__ void __launch_bounds__(BWD_THREADS, 1) k_ff_bwd(FFBwdArgs a) {
+template <bool MMA>
+__global__ void __launch_bounds__(ENC_THREADS, 1) k_ff_bwd(FFBwdArgs a) {
     extern __shared__ __align__(16) float smem[];
-    const FFBwdPlan& p = a.p;
-    const int D = a.D, M = a.M, Dp = p.Dp, Mp = p.Mp;
-    float* xs = smem;                                   // [RPT][Dp]  FF input (LN(x) or x)
-    float* dys = xs + (size_t)p.RPT * Dp;               // [RPT][Dp]  dout
-    float* ys = dys + (size_t)p.RPT * Dp;               // [RPT][Dp]  grad wrt FF input
-    float* hs = ys + (size_t)p.RPT * Dp;                // [RPT][Mp]  pre -> h
-    float* dhs = hs + (size_t)p.RPT * Mp;               // [RPT][Mp]  dh -> dpre
-    float* stats = dhs + (size_t)p.RPT * Mp;            // [RPT][2]
-    float* W1t = stats + (size_t)round_up(2 * p.RPT, 4);   // [D][Mp]   (k-major of W1 [M,D])
-    float* W2n = W1t + (size_t)D * Mp;                  // [D][Mp]   natural W2 [D,M]
-    float* W1n = W2n + (size_t)D * Mp;                  // [M][Dp]   natural W1 [M,D]
-    float* b1s = W1n + (size_t)M * Dp;                  // [Mp]
-    float* gW1 = b1s + Mp;                              // [Mp][Dp]
-    float* gW2 = gW1 + (size_t)Mp * Dp;                 // [Dp][Mp]
-    float* gb1 = gW2 + (size_t)Dp * Mp;                 // [Mp]
-    float* g3 = gb1 + Mp;                               // [3][Dp]  dgamma, dbeta, db2
-    float* scratch = g3 + 3 * Dp;                       // [groups][3][Dp]
-    stage_T(a.W1, M, D, Mp, W1t);
-    stage_natural(a.W2, D, M, Mp, W2n);
-    stage_natural(a.W1, M, D, Dp, W1n);
-    for (int i = threadIdx.x; i < Mp; i += blockDim.x) b1s[i] = i < M ? a.b1[i] : 0.f;
-    {
-        const int nacc = 2 * Mp * Dp + Mp + 3 * Dp;
-        for (int i = threadIdx.x; i < nacc; i += blockDim.x) gW1[i] = 0.f;
-    }
+    const FFPlan& p = a.p;
+    const int D = a.D, M = a.M, Dl = p.Dl, Ml = p.Ml, Dp8 = p.Dp8, Mp8 = p.Mp8;
+    float* W1n = smem;                                  // [Mp8][Dl]  natural W1 [M,D]
+    float* W2n = W1n + (size_t)Mp8 * Dl;                // [Dp8][Ml]  natural W2 [D,M]
+    float* b1s = W2n + (size_t)Dp8 * Ml;                // [Mp8]
+    float* gb1 = b1s + Mp8;                             // [Mp8]
+    float* g3 = gb1 + Mp8;                              // [3][Dp8]  dgamma, dbeta, db2
+    float* scratch = g3 + 3 * Dp8;                      // max(groups*3*Dp8, ENC_THREADS)
+    float* stats = scratch + max((ENC_THREADS / p.lg) * 3 * Dp8, ENC_THREADS);   // [RPT][2]
+    float* xs = stats + 2 * p.RPT;                      // [RPT][Dl]  FF input (LN(x) or x)
+    float* dys = xs + (size_t)p.RPT * Dl;               // [RPT][Dl]  dout
+    float* ys = dys + (size_t)p.RPT * Dl;               // [RPT][Dl]  grad wrt FF input
+    float* hs = ys + (size_t)p.RPT * Dl;                // [RPT][Ml]  pre -> h
+    float* dhs = hs + (size_t)p.RPT * Ml;               // [RPT][Ml]  dh -> dpre
+    // CTA-private gradient record: [gW1 Mp8*Dl | gW2 Dp8*Ml | gb1 Mp8 | small 3*Dp8]
+    float* rec = a.partials + (size_t)blockIdx.x * p.psize;
+    float* gW1 = rec;
+    float* gW2 = gW1 + (size_t)Mp8 * Dl;
+    stage_padded(a.W1, M, D, Mp8, Dl, W1n);
+    stage_padded(a.W2, D, M, Dp8, Ml, W2n);
+    for (int i = threadIdx.x; i < Mp8; i += blockDim.x) { b1s[i] = i < M ? a.b1[i] : 0.f; gb1[i] = 0.f; }
+    zero_floats(g3, 3 * Dp8);
+    zero_floats(xs, (size_t)p.RPT * (3 * Dl + 2 * Ml));
+    for (int i = threadIdx.x; i < p.psize; i += blockDim.x) rec[i] = 0.f;
     const long long ntiles = (a.rows + p.RPT - 1) / p.RPT;
     SeqGeom flat{1, 0, 1, 1};
     const int lg = p.lg, groups = blockDim.x / lg, gi = threadIdx.x / lg, li = threadIdx.x % lg;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long r0 = tile * p.RPT;
         const int R = (int)min((long long)p.RPT, a.rows - r0);
+        const int R16 = pad16(R), R8 = pad8(R);
         __syncthreads();
         if (a.ln_w) {
-            const float invD = 1.0f / (float)D;
-            for (int rr = 0; rr < R; rr += groups) {
-                const int r = rr + gi;
-                const bool ok = r < R;
-                const float* src = a.x + (ok ? (r0 + r) : 0) * D;
-                float sum = 0.f;
-                if (ok) for (int d = li; d < D; d += lg) sum += src[d];
-                const float mean = group_sum(sum, lg) * invD;
-                float sq = 0.f;
-                if (ok) for (int d = li; d < D; d += lg) { float t = src[d] - mean; sq = fmaf(t, t, sq); }
-                const float rstd = 1.0f / sqrtf(group_sum(sq, lg) * invD + 1e-5f);
-                if (ok) {
-                    for (int d = li; d < D; d += lg) xs[(size_t)r * Dp + d] = (src[d] - mean) * rstd * a.ln_w[d] + a.ln_b[d];
-                    for (int d = D + li; d < Dp; d += lg) xs[(size_t)r * Dp + d] = 0.f;
-                    if (li == 0) { stats[2 * r] = mean; stats[2 * r + 1] = rstd; }
-                }
-            }
+            ln_rows_to_smem(a.x, flat, r0, R, D, Dp8, a.ln_w, a.ln_b, xs, Dl, lg, stats);
         } else {
-            for (int i = threadIdx.x; i < R * Dp; i += blockDim.x) {
-                const int r = i / Dp, d = i % Dp;
-                xs[i] = d < D ? a.x[(r0 + r) * D + d] : 0.f;
+            for (int i = threadIdx.x; i < R * D; i += blockDim.x) {
+                const int r = i / D, d = i - r * D;
+                xs[(size_t)r * Dl + d] = a.x[(r0 + r) * D + d];
             }
         }
-        for (int i = threadIdx.x; i < R * Dp; i += blockDim.x) {
-            const int r = i / Dp, d = i % Dp;
-            dys[i] = d < D ? a.dout[(r0 + r) * D + d] : 0.f;
+        for (int i = threadIdx.x; i < R * D; i += blockDim.x) {
+            const int r = i / D, d = i - r * D;
+            dys[(size_t)r * Dl + d] = a.dout[(r0 + r) * D + d];
         }
+        zero_rows(xs, Dl, R, R16);
+        zero_rows(dys, Dl, R, R16);
         __syncthreads();
-        tile_gemm<4>(xs, Dp, W1t, Mp, hs, Mp, R, Mp, D, false, EpiBias{b1s});            // pre
+        // pre[r][m] = sum_d x[r][d] W1[m][d] + b1[m]
+        tc_gemm<MMA, 4>(xs, Dl, 1, W1n, 1, Dl, hs, Ml, R, Mp8, Dp8, false, EpiBias2{b1s});
         __syncthreads();
-        tile_gemm<4>(dys, Dp, W2n, Mp, dhs, Mp, R, Mp, D, false, EpiGeluBwd{hs, Mp});    // dpre ; hs <- h
+        // dpre[r][m] = (sum_d dy[r][d] W2[d][m]) * gelu'(pre) ; hs <- gelu(pre)
+        tc_gemm<MMA, 4>(dys, Dl, 1, W2n, Ml, 1, dhs, Ml, R, Mp8, Dp8, false, EpiGeluBwd2{hs, Ml});
+        zero_rows(hs, Ml, R, R16);          // pad rows were never touched by the epilogue; keep them zero
+        zero_rows(dhs, Ml, R, R16);
         __syncthreads();
-        tile_gemm_tn_acc(dys, Dp, hs, Mp, gW2, Mp, R, Dp, Mp);                           // dW2 [D][M]
-        tile_gemm_tn_acc(dhs, Mp, xs, Dp, gW1, Dp, R, Mp, Dp);                           // dW1 [M][D]
-        tile_colsum_acc(dhs, Mp, gb1, R, Mp);                                            // db1
-        tile_gemm<4>(dhs, Mp, W1n, Dp, ys, Dp, R, Dp, M, false, EpiNone());              // grad wrt FF input
-        __syncthreads();
+        // dW2[d][m] += sum_r dy[r][d] h[r][m] ; dW1[m][d] += sum_r dpre[r][m] x[r][d] ; dxa[r][d] = sum_m dpre[r][m] W1[m][d]
+        tc_gemm<MMA, 4>(dys, 1, Dl, hs, Ml, 1, gW2, Ml, Dp8, Mp8, R8, true, EpiNone2());
+        tc_gemm<MMA, 3>(dhs, 1, Ml, xs, Dl, 1, gW1, Dl, Mp8, Dp8, R8, true, EpiNone2());
+        tc_gemm<MMA, 3>(dhs, Ml, 1, W1n, Dl, 1, ys, Dl, R, Dp8, Mp8, false, EpiNone2());
+        tile_colsum_acc2(dhs, Ml, gb1, R, Mp8, scratch);              // db1 (two barriers inside)
         if (a.ln_w) {
-            ln_bwd_rows(a.x, a.base, a.dx, flat, r0, R, D, Dp, a.ln_w, ys, Dp, stats, dys, Dp, lg, scratch, g3);
+            ln_bwd_rows(a.x, a.base, a.dx, flat, r0, R, D, Dp8, a.ln_w, ys, Dl, stats, dys, Dl, lg, scratch, g3);
         } else {
-            // dx = base + ys ; db2 += colsum(dys)  (deterministic per-group partials as in ln_bwd_rows)
+            // dx = base + dxa ; db2 += colsum(dy)  (deterministic per-group partials)
             float pe[4] = {0.f, 0.f, 0.f, 0.f};
             for (int rr = 0; rr < R; rr += groups) {
                 const int r = rr + gi;
@@ -508,41 +336,64 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_ff_bwd(FFBwdArgs a) {
                     for (int k = 0; k < 4; ++k) {
                         const int d = li + k * lg;
                         if (d < D) {
-                            float v = ys[(size_t)r * Dp + d];
+                            float v = ys[(size_t)r * Dl + d];
                             if (a.base) v += a.base[(r0 + r) * D + d];
                             a.dx[(r0 + r) * D + d] = v;
-                            pe[k] += dys[(size_t)r * Dp + d];
+                            pe[k] += dys[(size_t)r * Dl + d];
                         }
                     }
                 }
             }
             __syncthreads();
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { const int d = li + k * lg; if (d < D) scratch[gi * Dp + d] = pe[k]; }
+            for (int k = 0; k < 4; ++k) { const int d = li + k * lg; if (d < D) scratch[gi * Dp8 + d] = pe[k]; }
             __syncthreads();
             for (int d = threadIdx.x; d < D; d += blockDim.x) {
                 float s = 0.f;
-                for (int q = 0; q < groups; ++q) s += scratch[q * Dp + d];
-                g3[2 * Dp + d] += s;
+                for (int q = 0; q < groups; ++q) s += scratch[q * Dp8 + d];
+                g3[2 * Dp8 + d] += s;
             }
         }
     }
     __syncthreads();
-    // flush: [dW1 M*D | db1 M | dW2 D*M | db2 D | dgamma D | dbeta D]
-    float* out = a.partials + (size_t)blockIdx.x * p.psize;
-    for (int i = threadIdx.x; i < M * D; i += blockDim.x) out[i] = gW1[(size_t)(i / D) * Dp + i % D];
-    for (int i = threadIdx.x; i < M; i += blockDim.x) out[M * D + i] = gb1[i];
-    float* o2 = out + M * D + M;
-    for (int i = threadIdx.x; i < D * M; i += blockDim.x) o2[i] = gW2[(size_t)(i / M) * Mp + i % M];
-    float* o3 = o2 + D * M;
-    for (int i = threadIdx.x; i < D; i += blockDim.x) {
-        o3[i] = g3[2 * Dp + i];
-        o3[D + i] = g3[0 * Dp + i];
-        o3[2 * D + i] = g3[1 * Dp + i];
+    float* sm_out = gW2 + (size_t)Dp8 * Ml;
+    for (int i = threadIdx.x; i < Mp8; i += blockDim.x) sm_out[i] = gb1[i];
+    for (int i = threadIdx.x; i < 3 * Dp8; i += blockDim.x) sm_out[Mp8 + i] = g3[i];
+}
+
+struct FFReduceArgs {
+    const float* partials; int nparts;
+    float* dW1; float* db1; float* dW2; float* db2; float* dln_w; float* dln_b;
+    int D, M;
+    FFPlan p;
+};
+__global__ void k_reduce_ff(FFReduceArgs a) {
+    const FFPlan& p = a.p;
+    const int D = a.D, M = a.M;
+    const int total = 2 * M * D + M + 3 * D;
+    const size_t off_w2 = (size_t)p.Mp8 * p.Dl, off_b1 = off_w2 + (size_t)p.Dp8 * p.Ml, off_small = off_b1 + p.Mp8;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        size_t src;
+        float* dst;
+        if (i < M * D) { const int m = i / D, d = i - m * D; src = (size_t)m * p.Dl + d; dst = a.dW1 ? a.dW1 + i : nullptr; }
+        else if (i < 2 * M * D) { const int rem = i - M * D; const int d = rem / M, m = rem - d * M;
+                                  src = off_w2 + (size_t)d * p.Ml + m; dst = a.dW2 ? a.dW2 + rem : nullptr; }
+        else if (i < 2 * M * D + M) { const int m = i - 2 * M * D; src = off_b1 + m; dst = a.db1 ? a.db1 + m : nullptr; }
+        else {
+            const int rem = i - 2 * M * D - M;
+            const int which = rem / D, d = rem - which * D;       // 0: db2, 1: dgamma, 2: dbeta
+            src = off_small + (size_t)(which == 0 ? 2 : which == 1 ? 0 : 1) * p.Dp8 + d;
+            float* base = which == 0 ? a.db2 : which == 1 ? a.dln_w : a.dln_b;
+            dst = base ? base + d : nullptr;
+        }
+        if (!dst) continue;
+        float s = 0.f;
+        for (int c = 0; c < a.nparts; ++c) s += a.partials[(size_t)c * p.psize + src];
+        *dst = s;
     }
 }
 
-// out[i] (+)= sum_c partials[c][off + i]   for up to 8 destination segments; fixed CTA order => deterministic
+// generic: out[i] = sum_c partials[c][off + i]  (final LayerNorm gradients)
 struct ReduceSeg { float* dst; int off; int len; int accumulate; };
 struct ReduceArgs { const float* partials; int nparts; int psize; int nseg; ReduceSeg seg[8]; };
 __global__ void k_reduce_partials(ReduceArgs a) {
@@ -609,65 +460,50 @@ __global__ void __launch_bounds__(256) k_ln_bwd(const float* __restrict__ x, con
 }
 
 // ---- planning ------------------------------------------------------------------------------------------------
-static size_t attn_bwd_floats(int R, int S, int D, int Dp, int hc, int dh, int H, int* psize_out, AttnBwdPlan* pl) {
-    const int Cq = hc * dh, Cqp = round_up(Cq, 4), C3p = round_up(3 * Cq, 4), nch = H / hc;
-    const int lg = min(32, next_pow2_(D));
-    const int groups = BWD_THREADS / lg;
-    size_t fl = (size_t)R * (3 * Dp + 2 * C3p + 2 * Cqp) + round_up(2 * R, 4) + 2 * (size_t)round_up(R * hc, 4);
-    fl += (size_t)D * C3p + (size_t)C3p * Dp + (size_t)D * Cqp;
-    fl += (size_t)nch * C3p * Dp + (size_t)nch * Dp * Cqp + 3 * Dp + (size_t)groups * 3 * Dp;
-    if (pl) { pl->hc = hc; pl->Dp = Dp; pl->Cq = Cq; pl->Cqp = Cqp; pl->C3p = C3p; pl->nchunks = nch; pl->lg = lg; }
-    (void)S; (void)psize_out;
-    return fl;
-}
-
-int plan_attn_bwd(int S, int D, int H, int dh, AttnBwdPlan* out) {
-    const int Dp = round_up(D, 4);
-    const size_t bud = (size_t)(max_smem_optin() - 1024) / 4;
-    const int cap_spt = max(1, 160 / S);
+int plan_attn_bwd(int S, int D, int H, int dh, AttnPlan* out) {
+    const size_t bud = (size_t)(max_smem_optin() - 2048) / 4;
+    const int cap_rows = 192;
+    AttnPlan best{};
     int bestR = 0;
-    AttnBwdPlan best{};
     for (int hc = H; hc >= 1; --hc) {
         if (H % hc) continue;
-        AttnBwdPlan cand{};
-        int spt = cap_spt;
-        for (; spt >= 1; --spt)
-            if (attn_bwd_floats(spt * S, S, D, Dp, hc, dh, H, nullptr, &cand) <= bud) break;
+        AttnPlan c{};
+        fill_attn_plan(S, D, H, dh, hc, &c);
+        const size_t fixed = (size_t)c.nchunks * c.C3p8 * c.Dl + (size_t)c.Dp8 * c.Il + 3 * c.Dp8 +
+                             (size_t)(ENC_THREADS / c.lg) * 3 * c.Dp8;
+        const size_t per_row = 3 * (size_t)c.Dl + 2 * c.C3l + 2 * c.Cql + 2 + 2 * hc;
+        if (fixed + per_row * pad16(S) > bud) continue;
+        int spt = (int)min((size_t)max(1, cap_rows / S), (bud - fixed) / (per_row * S));
+        while (spt > 1 && fixed + per_row * pad16(spt * S) > bud) --spt;
         if (spt < 1) continue;
         const int R = spt * S;
         if (R > bestR) {
-            bestR = R;
-            best = cand;
-            best.SPT = spt;
-            best.smem_bytes = attn_bwd_floats(R, S, D, Dp, hc, dh, H, nullptr, nullptr) * 4;
+            bestR = R; best = c; best.SPT = spt; best.Rmax16 = pad16(R);
+            best.smem_bytes = (fixed + per_row * pad16(R)) * 4;
         }
-        if (R >= min(96, cap_spt * S)) break;
+        if (R >= min(96, max(1, cap_rows / S) * S)) break;
     }
     if (!bestR) return RAT_ESMEM;
-    best.lpt = min(32, next_pow2_(S));
-    const int I = H * dh;
-    best.psize = round_up(3 * I * D + D * I + 3 * D, 4);
+    best.psize = (int)((size_t)best.nchunks * best.C3p8 * best.Dl + (size_t)best.Dp8 * best.Il + 3 * best.Dp8);
+    best.psize = (best.psize + 3) & ~3;
     *out = best;
     return RAT_OK;
 }
 
-int plan_ff_bwd(int D, int M, FFBwdPlan* out) {
-    FFBwdPlan p{};
-    p.Dp = round_up(D, 4); p.Mp = round_up(M, 4);
-    p.lg = min(32, next_pow2_(D));
-    const int groups = BWD_THREADS / p.lg;
-    const size_t bud = (size_t)(max_smem_optin() - 1024) / 4;
-    const size_t fixed = 2 * (size_t)D * p.Mp + (size_t)M * p.Dp + p.Mp + 2 * (size_t)p.Mp * p.Dp + p.Mp + 3 * p.Dp +
-                         (size_t)groups * 3 * p.Dp + 8;
-    int rpt = 160;
-    for (; rpt >= 8; rpt -= 8) {
-        size_t fl = (size_t)rpt * (3 * p.Dp + 2 * p.Mp) + round_up(2 * rpt, 4) + fixed;
-        if (fl <= bud) break;
-    }
-    if (rpt < 8) return RAT_ESMEM;
+int plan_ff_bwd(int D, int M, FFPlan* out) {
+    FFPlan p{};
+    fill_ff_plan(D, M, &p);
+    const size_t bud = (size_t)(max_smem_optin() - 2048) / 4;
+    const size_t fixed = (size_t)p.Mp8 * p.Dl + (size_t)p.Dp8 * p.Ml + 2 * p.Mp8 + 3 * p.Dp8 +
+                         (size_t)max((ENC_THREADS / p.lg) * 3 * p.Dp8, ENC_THREADS);
+    const size_t per_row = 3 * (size_t)p.Dl + 2 * p.Ml + 2;
+    int rpt = 192;
+    while (rpt >= 16 && fixed + per_row * rpt > bud) rpt -= 16;
+    if (rpt < 16) return RAT_ESMEM;
     p.RPT = rpt;
-    p.smem_bytes = ((size_t)rpt * (3 * p.Dp + 2 * p.Mp) + round_up(2 * rpt, 4) + fixed) * 4;
-    p.psize = round_up(2 * M * D + M + 3 * D, 4);
+    p.smem_bytes = (fixed + per_row * rpt) * 4;
+    p.psize = (int)((size_t)p.Mp8 * p.Dl + (size_t)p.Dp8 * p.Ml + p.Mp8 + 3 * p.Dp8);
+    p.psize = (p.psize + 3) & ~3;
     *out = p;
     return RAT_OK;
 }
@@ -678,18 +514,8 @@ static int bwd_grid(long long ntiles) { return (int)min(ntiles, (long long)num_s
 
 using namespace rat;
 
-static int run_reduce(const float* partials, int nparts, int psize, int nseg, const ReduceSeg* segs, cudaStream_t st) {
-    ReduceArgs r{};
-    r.partials = partials; r.nparts = nparts; r.psize = psize; r.nseg = nseg;
-    int total = 0;
-    for (int i = 0; i < nseg; ++i) { r.seg[i] = segs[i]; total += segs[i].len; }
-    k_reduce_partials<<<max(1, min(ceil_div(total, 256), 1024)), 256, 0, st>>>(r);
-    RAT_CHECK_LAUNCH("k_reduce_partials");
-    return RAT_OK;
-}
-
 extern "C" size_t rat_attn_bwd_workspace_bytes(int B, int T, int N, int D, int heads, int dim_head, int mode) {
-    AttnBwdPlan p{};
+    AttnPlan p{};
     const int S = mode == 0 ? N : T;
     if (plan_attn_bwd(S, D, heads, dim_head, &p) != RAT_OK) return 0;
     const long long nseq = mode == 0 ? (long long)B * T : (long long)B * N;
@@ -697,17 +523,21 @@ extern "C" size_t rat_attn_bwd_workspace_bytes(int B, int T, int N, int D, int h
     return (size_t)bwd_grid(ntiles) * p.psize * sizeof(float);
 }
 
-template <int DH>
+template <int DH, bool MMA>
 static int launch_attn_bwd(const AttnBwdArgs& a, int grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_attn_bwd<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin());
+        cudaError_t e = cudaFuncSetAttribute(k_attn_bwd<DH, MMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin());
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_attn_bwd)");
         attr_set = true;
     }
-    k_attn_bwd<DH><<<grid, BWD_THREADS, a.p.smem_bytes, st>>>(a);
+    k_attn_bwd<DH, MMA><<<grid, ENC_THREADS, a.p.smem_bytes, st>>>(a);
     RAT_CHECK_LAUNCH("k_attn_bwd");
     return RAT_OK;
+}
+template <int DH>
+static int launch_attn_bwd_p(const AttnBwdArgs& a, int grid, cudaStream_t st) {
+    return precision_mode() ? launch_attn_bwd<DH, true>(a, grid, st) : launch_attn_bwd<DH, false>(a, grid, st);
 }
 
 extern "C" int rat_attn_bwd(const float* x, const float* dout, const float* base, float* dx, const float* ln_w,
@@ -732,27 +562,40 @@ extern "C" int rat_attn_bwd(const float* x, const float* dout, const float* base
     a.partials = workspace;
     cudaStream_t st = (cudaStream_t)stream;
     switch (dim_head) {
-        case 4: rc = launch_attn_bwd<4>(a, grid, st); break;
-        case 8: rc = launch_attn_bwd<8>(a, grid, st); break;
-        case 10: rc = launch_attn_bwd<10>(a, grid, st); break;
-        case 16: rc = launch_attn_bwd<16>(a, grid, st); break;
-        case 20: rc = launch_attn_bwd<20>(a, grid, st); break;
-        case 32: rc = launch_attn_bwd<32>(a, grid, st); break;
+        case 4: rc = launch_attn_bwd_p<4>(a, grid, st); break;
+        case 8: rc = launch_attn_bwd_p<8>(a, grid, st); break;
+        case 10: rc = launch_attn_bwd_p<10>(a, grid, st); break;
+        case 16: rc = launch_attn_bwd_p<16>(a, grid, st); break;
+        case 20: rc = launch_attn_bwd_p<20>(a, grid, st); break;
+        case 32: rc = launch_attn_bwd_p<32>(a, grid, st); break;
         default: set_error("rat_attn_bwd: dim_head=%d not instantiated", dim_head); return RAT_EINVAL;
     }
     if (rc != RAT_OK) return rc;
-    const int I = a.I;
-    ReduceSeg segs[7] = {
-        {dWq, 0, I * D, accumulate_wq}, {dWk, I * D, I * D, 0}, {dWv, 2 * I * D, I * D, 0},
-        {dWo, 3 * I * D, D * I, 0}, {dbo, 4 * I * D, D, 0}, {dln_w, 4 * I * D + D, D, 0}, {dln_b, 4 * I * D + 2 * D, D, 0}};
-    return run_reduce(workspace, grid, a.p.psize, 7, segs, st);
+    AttnReduceArgs r{workspace, grid, dWq, dWk, dWv, dWo, dbo, dln_w, dln_b, accumulate_wq, D, a.I, a.p};
+    const int total = 4 * a.I * D + 3 * D;
+    k_reduce_attn<<<max(1, min(ceil_div(total, 256), 1024)), 256, 0, st>>>(r);
+    RAT_CHECK_LAUNCH("k_reduce_attn");
+    return RAT_OK;
 }
 
 extern "C" size_t rat_ff_bwd_workspace_bytes(long long rows, int D, int M) {
-    FFBwdPlan p{};
+    FFPlan p{};
     if (plan_ff_bwd(D, M, &p) != RAT_OK) return 0;
     const long long ntiles = (rows + p.RPT - 1) / p.RPT;
     return (size_t)bwd_grid(ntiles) * p.psize * sizeof(float);
+}
+
+template <bool MMA>
+static int launch_ff_bwd(const FFBwdArgs& a, int grid, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_ff_bwd<MMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin());
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_ff_bwd)");
+        attr_set = true;
+    }
+    k_ff_bwd<MMA><<<grid, ENC_THREADS, a.p.smem_bytes, st>>>(a);
+    RAT_CHECK_LAUNCH("k_ff_bwd");
+    return RAT_OK;
 }
 
 extern "C" int rat_ff_bwd(const float* x, const float* dout, const float* base, float* dx, const float* ln_w,
@@ -760,7 +603,7 @@ extern "C" int rat_ff_bwd(const float* x, const float* dout, const float* base, 
                           float* dW2, float* db2, float* dln_w, float* dln_b, long long rows, int D, int M,
                           float* workspace, size_t workspace_bytes, void* stream) {
     RAT_REQUIRE(rows > 0 && D > 0 && M > 0, "rat_ff_bwd: bad shape");
-    RAT_REQUIRE(D <= 128, "rat_ff_bwd: D=%d > 128 not supported", D);
+    RAT_REQUIRE(D <= 128 && pad8(M) <= ENC_THREADS, "rat_ff_bwd: D=%d (<=128) M=%d (<=%d) not supported", D, M, ENC_THREADS);
     FFBwdArgs a{};
     a.x = x; a.dout = dout; a.base = base; a.dx = dx; a.ln_w = ln_w; a.ln_b = ln_b; a.W1 = W1; a.b1 = b1; a.W2 = W2;
     a.rows = rows; a.D = D; a.M = M;
@@ -770,18 +613,14 @@ extern "C" int rat_ff_bwd(const float* x, const float* dout, const float* base, 
     const int grid = bwd_grid(ntiles);
     RAT_REQUIRE(workspace && workspace_bytes >= (size_t)grid * a.p.psize * sizeof(float), "rat_ff_bwd: workspace too small");
     a.partials = workspace;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_ff_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin());
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_ff_bwd)");
-        attr_set = true;
-    }
     cudaStream_t st = (cudaStream_t)stream;
-    k_ff_bwd<<<grid, BWD_THREADS, a.p.smem_bytes, st>>>(a);
-    RAT_CHECK_LAUNCH("k_ff_bwd");
-    ReduceSeg segs[6] = {{dW1, 0, M * D, 0}, {db1, M * D, M, 0}, {dW2, M * D + M, D * M, 0},
-                         {db2, 2 * M * D + M, D, 0}, {dln_w, 2 * M * D + M + D, D, 0}, {dln_b, 2 * M * D + M + 2 * D, D, 0}};
-    return run_reduce(workspace, grid, a.p.psize, 6, segs, st);
+    rc = precision_mode() ? launch_ff_bwd<true>(a, grid, st) : launch_ff_bwd<false>(a, grid, st);
+    if (rc != RAT_OK) return rc;
+    FFReduceArgs r{workspace, grid, dW1, db1, dW2, db2, dln_w, dln_b, D, M, a.p};
+    const int total = 2 * M * D + M + 3 * D;
+    k_reduce_ff<<<max(1, min(ceil_div(total, 256), 1024)), 256, 0, st>>>(r);
+    RAT_CHECK_LAUNCH("k_reduce_ff");
+    return RAT_OK;
 }
 
 extern "C" size_t rat_layernorm_bwd_workspace_bytes(long long rows, int D) {
@@ -792,13 +631,18 @@ extern "C" size_t rat_layernorm_bwd_workspace_bytes(long long rows, int D) {
 extern "C" int rat_layernorm_bwd(const float* x, const float* dout, float* dx, const float* w, float* dw, float* db,
                                  long long rows, int D, float* workspace, size_t workspace_bytes, void* stream) {
     RAT_REQUIRE(rows > 0 && D > 0 && D <= 128, "rat_layernorm_bwd: bad shape");
-    const int lg = min(32, next_pow2_(D));
+    const int lg = min(32, next_pow2(D));
     const int groups = 256 / lg;
     const int grid = (int)min((rows + groups - 1) / groups, (long long)num_sms() * 4);
     RAT_REQUIRE(workspace && workspace_bytes >= (size_t)grid * 2 * D * sizeof(float), "rat_layernorm_bwd: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     k_ln_bwd<<<grid, 256, (size_t)groups * 2 * D * sizeof(float), st>>>(x, dout, dx, w, rows, D, lg, workspace);
     RAT_CHECK_LAUNCH("k_ln_bwd");
-    ReduceSeg segs[2] = {{dw, 0, D, 0}, {db, D, D, 0}};
-    return run_reduce(workspace, grid, 2 * D, 2, segs, st);
+    ReduceArgs r{};
+    r.partials = workspace; r.nparts = grid; r.psize = 2 * D; r.nseg = 2;
+    r.seg[0] = ReduceSeg{dw, 0, D, 0};
+    r.seg[1] = ReduceSeg{db, D, D, 0};
+    k_reduce_partials<<<1, 256, 0, st>>>(r);
+    RAT_CHECK_LAUNCH("k_reduce_partials");
+    return RAT_OK;
 }

@@ -7,27 +7,19 @@
 //                (reference: FeedForward RAT_m2.py:163-174 ; PreNorm'd in RAT_m0.py:193-208)
 //   k_ln_fwd   : out = LayerNorm(x)                                         final norm of RAT_m0/m1 Transformer
 //
-// One CTA owns a tile of whole sequences (SPT sequences x S positions = R token rows).  LayerNorm output, the
-// per-head-chunk q|k|v, the attention output and the out-projection accumulator all stay in shared memory; the
-// weights of the current head chunk are staged (transposed, k-major) into shared memory.  "Intra" attention
-// (sequence = one sample row, positions = fields) and "cross" attention (sequence = one field over the 1+K
-// retrieved rows) differ only in the row-index map SeqGeom::grow, i.e. the reference's
+// One persistent CTA per SM (512 threads) keeps ALL weights of the sub-block resident in shared memory (natural
+// torch layout, zero padded) and walks tiles of whole sequences (SPT sequences x S positions = R token rows).
+// LayerNorm output, the per-head-chunk q|k|v, the attention output and the out-projection accumulator stay in
+// shared memory.  The projections run on the tensor cores (mma.sync m16n8k8 TF32, fp32 accumulate) or, with
+// precision=fp32, on an exact SIMT twin; softmax(QK^T)V runs on the SIMT pipe with all S scores in registers.
+// "Intra" attention (sequence = one sample row, positions = fields) and "cross" attention (sequence = one field
+// over the 1+K retrieved rows) differ only in the row-index map SeqGeom::grow, i.e. the reference's
 // reshape/transpose/flatten copies (RAT_m2.py:221-235) are pure indexing here.
 #include "tile.cuh"
+#include "encoder_common.cuh"
 #include "../../include/rat_b200.h"
 
 namespace rat {
-
-struct AttnPlan {
-    int SPT;      // sequences per tile
-    int hc;       // heads per chunk
-    int Dp;       // padded D
-    int Cq;       // hc*dh
-    int C3p;      // padded 3*Cq
-    int lg;       // lanes per LayerNorm row group
-    int lpt;      // lanes per attention task
-    size_t smem_bytes;
-};
 
 struct AttnArgs {
     const float* x; const float* res; float* out;
@@ -41,143 +33,48 @@ struct AttnArgs {
     AttnPlan p;
 };
 
-static inline int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
-
-// LayerNorm of R rows (global -> smem), eps=1e-5, biased variance (torch.nn.LayerNorm semantics).
-// If stats != nullptr the per-row (mean, rstd) are stored for the backward pass.
-__device__ __forceinline__ void ln_rows_to_smem(const float* __restrict__ x, const SeqGeom& g, long long s0, int R,
-                                                int D, const float* __restrict__ w, const float* __restrict__ b,
-                                                float* __restrict__ dst, int ld, int lg, float* __restrict__ stats,
-                                                float* __restrict__ raw, int ldraw) {
-    const int groups = blockDim.x / lg;
-    const int gi = threadIdx.x / lg, li = threadIdx.x % lg;
-    const float invD = 1.0f / (float)D;
-    for (int r0 = 0; r0 < R; r0 += groups) {
-        const int r = r0 + gi;
-        const bool ok = r < R;
-        const float* src = x;
-        if (ok) src = x + g.grow(s0 + r / g.S, r % g.S) * D;
-        float sum = 0.f;
-        if (ok) for (int d = li; d < D; d += lg) sum += src[d];
-        const float mean = group_sum(sum, lg) * invD;
-        float sq = 0.f;
-        if (ok) for (int d = li; d < D; d += lg) { float t = src[d] - mean; sq = fmaf(t, t, sq); }
-        const float var = group_sum(sq, lg) * invD;
-        const float rstd = 1.0f / sqrtf(var + 1e-5f);
-        if (ok) {
-            for (int d = li; d < D; d += lg) {
-                const float xv = src[d];
-                dst[(size_t)r * ld + d] = (xv - mean) * rstd * w[d] + b[d];
-                if (raw) raw[(size_t)r * ldraw + d] = xv;
-            }
-            if (stats && li == 0) { stats[2 * r] = mean; stats[2 * r + 1] = rstd; }
-        }
-    }
-}
-
-// stage the head-chunk weights transposed: Wt[k][c], c in [0,C3p): q cols | k cols | v cols | zero pad
-__device__ __forceinline__ void stage_qkv_weights(const float* __restrict__ Wq, const float* __restrict__ Wk,
-                                                  const float* __restrict__ Wv, int D, int row0, int Cq, int C3p,
-                                                  float* __restrict__ Wt) {
-    const int total = C3p * D;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int k = i % D, c = i / D;
-        float v = 0.f;
-        if (c < Cq) v = __ldg(Wq + (size_t)(row0 + c) * D + k);
-        else if (c < 2 * Cq) v = __ldg(Wk + (size_t)(row0 + c - Cq) * D + k);
-        else if (c < 3 * Cq) v = __ldg(Wv + (size_t)(row0 + c - 2 * Cq) * D + k);
-        Wt[(size_t)k * C3p + c] = v;
-    }
-}
-// WoT[c][d] = Wo[d][col0 + c]   (c < Cq, d < Dp, zero pad)
-__device__ __forceinline__ void stage_out_weights(const float* __restrict__ Wo, int D, int I, int col0, int Cq,
-                                                  int Dp, float* __restrict__ WoT) {
-    const int total = Cq * Dp;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int c = i % Cq, d = i / Cq;
-        WoT[(size_t)c * Dp + d] = (d < D) ? __ldg(Wo + (size_t)d * I + col0 + c) : 0.f;
-    }
-}
-
-// softmax(q k^T) v for every (sequence, head) task of the tile; o overwrites q. Optionally stores the
-// log-sum-exp of each row (for the backward pass).  q is pre-multiplied by `scale`.
-template <int DH>
-__device__ __forceinline__ void attn_core(float* __restrict__ qkv, int ld, int Cq, int nseq_tile, int S, int hc,
-                                          int lpt, float scale, float* __restrict__ lse) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const int tpw = 32 / lpt;
-    const int ntasks = nseq_tile * hc;
-    const int sub = lane / lpt, li = lane % lpt;
-    for (int task0 = warp * tpw; task0 < ntasks; task0 += nwarps * tpw) {
-        const int task = task0 + sub;
-        if (task >= ntasks) continue;
-        const int ls = task / hc, hl = task % hc;
-        float* base = qkv + (size_t)ls * S * ld + hl * DH;
-        for (int i = li; i < S; i += lpt) {
-            float q[DH], acc[DH];
-            float* qrow = base + (size_t)i * ld;
-#pragma unroll
-            for (int d = 0; d < DH; ++d) { q[d] = qrow[d] * scale; acc[d] = 0.f; }
-            float m = -INFINITY, l = 0.f;
-            for (int j = 0; j < S; ++j) {
-                const float* krow = base + (size_t)j * ld + Cq;
-                const float* vrow = krow + Cq;
-                float sc = 0.f;
-#pragma unroll
-                for (int d = 0; d < DH; ++d) sc = fmaf(q[d], krow[d], sc);
-                const float mn = fmaxf(m, sc);
-                const float corr = expf(m - mn);
-                const float pj = expf(sc - mn);
-                l = fmaf(l, corr, pj);
-#pragma unroll
-                for (int d = 0; d < DH; ++d) acc[d] = fmaf(acc[d], corr, pj * vrow[d]);
-                m = mn;
-            }
-            const float inv = 1.0f / l;
-#pragma unroll
-            for (int d = 0; d < DH; ++d) qrow[d] = acc[d] * inv;
-            if (lse) lse[(ls * S + i) * hc + hl] = m + logf(l);
-        }
-    }
-}
-
-template <int DH>
-__global__ void __launch_bounds__(256) k_attn_fwd(AttnArgs a) {
+template <int DH, bool MMA>
+__global__ void __launch_bounds__(ENC_THREADS, 1) k_attn_fwd(AttnArgs a) {
     extern __shared__ __align__(16) float smem[];
     const AttnPlan& p = a.p;
     const int S = a.g.S, D = a.D;
-    const int Rmax = p.SPT * S;
-    float* as = smem;                               // [Rmax][Dp]  LayerNorm(x)
-    float* ys = as + (size_t)Rmax * p.Dp;           // [Rmax][Dp]  out-projection accumulator
-    float* qkv = ys + (size_t)Rmax * p.Dp;          // [Rmax][C3p]
-    float* Wt = qkv + (size_t)Rmax * p.C3p;         // [D][C3p]
-    float* WoT = Wt + (size_t)D * p.C3p;            // [Cq][Dp]
+    const int Dl = p.Dl, C3l = p.C3l, Cql = p.Cql, Il = p.Il;
+    const int Rmax = p.Rmax16;
+    float* Wc = smem;                                   // [nchunks][C3p8][Dl]   q|k|v rows of each head chunk
+    float* WoN = Wc + (size_t)p.nchunks * p.C3p8 * Dl;  // [Dp8][Il]             natural Wo
+    float* as = WoN + (size_t)p.Dp8 * Il;               // [Rmax][Dl]  LayerNorm(x)
+    float* ys = as + (size_t)Rmax * Dl;                 // [Rmax][Dl]  out-projection accumulator
+    float* qkv = ys + (size_t)Rmax * Dl;                // [Rmax][C3l]
+    float* os = qkv + (size_t)Rmax * C3l;               // [Rmax][Cql]
+    stage_qkv_chunks(a.Wq, a.Wk, a.Wv, D, p, Wc);
+    stage_padded(a.Wo, D, a.I, p.Dp8, Il, WoN);
+    zero_floats(as, (size_t)Rmax * (2 * Dl + C3l + Cql));
     const long long ntiles = (a.nseq + p.SPT - 1) / p.SPT;
-    const int nchunks = a.H / p.hc;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long s0 = tile * p.SPT;
         const int nseq_t = (int)min((long long)p.SPT, a.nseq - s0);
         const int R = nseq_t * S;
-        __syncthreads();                            // previous tile fully consumed
-        ln_rows_to_smem(a.x, a.g, s0, R, D, a.ln_w, a.ln_b, as, p.Dp, p.lg, nullptr, nullptr, 0);
-        for (int i = threadIdx.x; i < R * p.Dp; i += blockDim.x) ys[i] = 0.f;
-        for (int ch = 0; ch < nchunks; ++ch) {
-            const int row0 = ch * p.Cq;             // first q/k/v feature of this head chunk
-            __syncthreads();                        // (a) previous chunk's GEMM2 done with qkv/WoT; LN visible
-            stage_qkv_weights(a.Wq, a.Wk, a.Wv, D, row0, p.Cq, p.C3p, Wt);
-            stage_out_weights(a.Wo, D, a.I, row0, p.Cq, p.Dp, WoT);
+        __syncthreads();                                // previous tile fully consumed (and staging visible)
+        ln_rows_to_smem(a.x, a.g, s0, R, D, p.Dp8, a.ln_w, a.ln_b, as, Dl, p.lg, nullptr);
+        zero_rows(as, Dl, R, pad16(R));
+        zero_rows(os, Cql, R, pad16(R));
+        zero_floats(ys, (size_t)pad16(R) * Dl);
+        for (int ch = 0; ch < p.nchunks; ++ch) {
+            const float* W = Wc + (size_t)ch * p.C3p8 * Dl;
+            __syncthreads();                            // LN / previous chunk's out-projection done
+            // q|k|v[r][c] = sum_d as[r][d] * W[c][d]
+            tc_gemm<MMA, 4>(as, Dl, 1, W, 1, Dl, qkv, C3l, R, p.C3p8, p.Dp8, false, EpiNone2());
             __syncthreads();
-            tile_gemm<8>(as, p.Dp, Wt, p.C3p, qkv, p.C3p, R, p.C3p, D, false, EpiNone());
+            attn_core<DH>(qkv, C3l, p.Cq, os, Cql, nullptr, nseq_t, S, p.hc, p.lpt, a.scale);
             __syncthreads();
-            attn_core<DH>(qkv, p.C3p, p.Cq, nseq_t, S, p.hc, p.lpt, a.scale, nullptr);
-            __syncthreads();
-            tile_gemm<8>(qkv, p.C3p, WoT, p.Dp, ys, p.Dp, R, p.Dp, p.Cq, true, EpiNone());
+            // ys[r][d] += sum_c os[r][c] * Wo[d][col0 + c]
+            tc_gemm<MMA, 3>(os, Cql, 1, WoN + ch * p.Cq, 1, Il, ys, Dl, R, p.Dp8, p.Cq8, true, EpiNone2());
         }
         __syncthreads();
         for (int i = threadIdx.x; i < R * D; i += blockDim.x) {
-            const int r = i / D, d = i % D;
+            const int r = i / D, d = i - r * D;
             const long long gr = a.g.grow(s0 + r / S, r % S);
-            float v = a.alpha * (ys[(size_t)r * p.Dp + d] + a.bo[d]);
+            float v = a.alpha * (ys[(size_t)r * Dl + d] + a.bo[d]);
             if (a.res) v += a.res[gr * D + d];
             a.out[gr * D + d] = v;
         }
@@ -185,7 +82,6 @@ __global__ void __launch_bounds__(256) k_attn_fwd(AttnArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------------
-struct FFPlan { int RPT; int Dp; int Mp; int lg; size_t smem_bytes; };
 struct FFArgs {
     const float* x; const float* res; float* out;
     const float* ln_w; const float* ln_b;               // nullptr => no pre-norm (RAT_m2/m3)
@@ -195,37 +91,29 @@ struct FFArgs {
     FFPlan p;
 };
 
-struct EpiBiasGelu {
+struct EpiBiasGelu2 {
     const float* b;
-    __device__ __forceinline__ void operator()(int, int c0, float4& v) const {
-        v.x = gelu_erf(v.x + b[c0]); v.y = gelu_erf(v.y + b[c0 + 1]);
-        v.z = gelu_erf(v.z + b[c0 + 2]); v.w = gelu_erf(v.w + b[c0 + 3]);
+    __device__ __forceinline__ void operator()(int, int c, float& v0, float& v1) const {
+        v0 = gelu_erf(v0 + b[c]);
+        v1 = gelu_erf(v1 + b[c + 1]);
     }
 };
 
-// stage Wt[k][c] = W[c][k] for a torch Linear weight W [C, K]; zero pad c >= C
-__device__ __forceinline__ void stage_linear_T(const float* __restrict__ W, int C, int K, int Cp,
-                                               float* __restrict__ Wt) {
-    const int total = Cp * K;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int k = i % K, c = i / K;
-        Wt[(size_t)k * Cp + c] = (c < C) ? __ldg(W + (size_t)c * K + k) : 0.f;
-    }
-}
-
-__global__ void __launch_bounds__(256) k_ff_fwd(FFArgs a) {
+template <bool MMA>
+__global__ void __launch_bounds__(ENC_THREADS, 1) k_ff_fwd(FFArgs a) {
     extern __shared__ __align__(16) float smem[];
     const FFPlan& p = a.p;
-    const int D = a.D, M = a.M;
-    float* xs = smem;                                   // [RPT][Dp]
-    float* hs = xs + (size_t)p.RPT * p.Dp;              // [RPT][Mp]
-    float* ys = hs + (size_t)p.RPT * p.Mp;              // [RPT][Dp]
-    float* W1t = ys + (size_t)p.RPT * p.Dp;             // [D][Mp]
-    float* W2t = W1t + (size_t)D * p.Mp;                // [M][Dp]
-    float* b1s = W2t + (size_t)M * p.Dp;                // [Mp]
-    stage_linear_T(a.W1, M, D, p.Mp, W1t);
-    stage_linear_T(a.W2, D, M, p.Dp, W2t);
-    for (int i = threadIdx.x; i < p.Mp; i += blockDim.x) b1s[i] = i < M ? a.b1[i] : 0.f;
+    const int D = a.D, M = a.M, Dl = p.Dl, Ml = p.Ml;
+    float* W1n = smem;                                  // [Mp8][Dl]  natural W1 [M,D]
+    float* W2n = W1n + (size_t)p.Mp8 * Dl;              // [Dp8][Ml]  natural W2 [D,M]
+    float* b1s = W2n + (size_t)p.Dp8 * Ml;              // [Mp8]
+    float* xs = b1s + p.Mp8;                            // [RPT][Dl]
+    float* hs = xs + (size_t)p.RPT * Dl;                // [RPT][Ml]
+    float* ys = hs + (size_t)p.RPT * Ml;                // [RPT][Dl]
+    stage_padded(a.W1, M, D, p.Mp8, Dl, W1n);
+    stage_padded(a.W2, D, M, p.Dp8, Ml, W2n);
+    for (int i = threadIdx.x; i < p.Mp8; i += blockDim.x) b1s[i] = i < M ? a.b1[i] : 0.f;
+    zero_floats(xs, (size_t)p.RPT * (2 * Dl + Ml));
     const long long ntiles = (a.rows + p.RPT - 1) / p.RPT;
     SeqGeom flat{1, 0, 1, 1};
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -233,21 +121,24 @@ __global__ void __launch_bounds__(256) k_ff_fwd(FFArgs a) {
         const int R = (int)min((long long)p.RPT, a.rows - r0);
         __syncthreads();
         if (a.ln_w) {
-            ln_rows_to_smem(a.x, flat, r0, R, D, a.ln_w, a.ln_b, xs, p.Dp, p.lg, nullptr, nullptr, 0);
+            ln_rows_to_smem(a.x, flat, r0, R, D, p.Dp8, a.ln_w, a.ln_b, xs, Dl, p.lg, nullptr);
         } else {
             for (int i = threadIdx.x; i < R * D; i += blockDim.x) {
-                const int r = i / D, d = i % D;
-                xs[(size_t)r * p.Dp + d] = a.x[(r0 + r) * D + d];
+                const int r = i / D, d = i - r * D;
+                xs[(size_t)r * Dl + d] = a.x[(r0 + r) * D + d];
             }
         }
+        zero_rows(xs, Dl, R, pad16(R));
         __syncthreads();
-        tile_gemm<8>(xs, p.Dp, W1t, p.Mp, hs, p.Mp, R, p.Mp, D, false, EpiBiasGelu{b1s});
+        // h[r][m] = gelu(sum_d x[r][d] W1[m][d] + b1[m])
+        tc_gemm<MMA, 4>(xs, Dl, 1, W1n, 1, Dl, hs, Ml, R, p.Mp8, p.Dp8, false, EpiBiasGelu2{b1s});
         __syncthreads();
-        tile_gemm<8>(hs, p.Mp, W2t, p.Dp, ys, p.Dp, R, p.Dp, M, false, EpiNone());
+        // y[r][d] = sum_m h[r][m] W2[d][m]
+        tc_gemm<MMA, 3>(hs, Ml, 1, W2n, 1, Ml, ys, Dl, R, p.Dp8, p.Mp8, false, EpiNone2());
         __syncthreads();
         for (int i = threadIdx.x; i < R * D; i += blockDim.x) {
-            const int r = i / D, d = i % D;
-            a.out[(r0 + r) * D + d] = a.res[(r0 + r) * D + d] + ys[(size_t)r * p.Dp + d] + a.b2[d];
+            const int r = i / D, d = i - r * D;
+            a.out[(r0 + r) * D + d] = a.res[(r0 + r) * D + d] + ys[(size_t)r * Dl + d] + a.b2[d];
         }
     }
 }
@@ -271,66 +162,80 @@ __global__ void k_ln_fwd(const float* __restrict__ x, float* __restrict__ out, c
 }
 
 // ---- host-side planning ---------------------------------------------------------------------------------
-// Choose (heads per chunk, sequences per tile): as many token rows per tile as fit (target 128..176), then the
-// widest head chunk.  per_row_extra / fixed_extra (floats) let the backward kernel reserve its extra buffers:
-// fixed_extra is counted per head-chunk column set by the caller through the callback-free formula below.
-int plan_attn_ex(int S, int D, int H, int dh, int row_mul_D, int row_mul_C3, int row_mul_Cq, int row_extra,
-                 int fix_mul_DC3, int fix_mul_CqD, int fix_extra, size_t budget, AttnPlan* out) {
-    const int Dp = round_up(D, 4);
-    const int cap_spt = max(1, 176 / S);
+// fixed: resident weights ; per row: as + ys (2 Dl) + qkv (C3l) + os (Cql).  Prefer >=128 rows, then wide chunks.
+int plan_attn(int S, int D, int H, int dh, AttnPlan* out) {
+    const size_t bud = (size_t)(max_smem_optin() - 2048) / 4;
+    const int cap_rows = 256;
     AttnPlan best{};
     int bestR = 0;
-    for (int pass = 0; pass < 2 && bestR == 0; ++pass) {
-        const size_t bud = (pass == 0 ? budget : (size_t)max_smem_optin()) / 4;
-        for (int hc = H; hc >= 1; --hc) {
-            if (H % hc) continue;
-            const int Cq = hc * dh, C3p = round_up(3 * Cq, 4), Cqp = round_up(Cq, 4);
-            const size_t per_row = (size_t)row_mul_D * Dp + (size_t)row_mul_C3 * C3p + (size_t)row_mul_Cq * Cqp + row_extra * hc;
-            const size_t fixed = (size_t)fix_mul_DC3 * D * C3p + (size_t)fix_mul_CqD * Cqp * Dp + fix_extra;
-            if (fixed + per_row * S > bud) continue;
-            int spt = (int)min((size_t)cap_spt, (bud - fixed) / (per_row * S));
-            if (spt < 1) continue;
-            const int R = spt * S;
-            if (R > bestR) {
-                bestR = R;
-                best.SPT = spt; best.hc = hc; best.Dp = Dp; best.Cq = Cq; best.C3p = C3p;
-                best.smem_bytes = (fixed + per_row * R) * 4;
-            }
-            if (R >= min(128, cap_spt * S)) break;
+    for (int hc = H; hc >= 1; --hc) {
+        if (H % hc) continue;
+        AttnPlan c{};
+        fill_attn_plan(S, D, H, dh, hc, &c);
+        const size_t fixed = (size_t)c.nchunks * c.C3p8 * c.Dl + (size_t)c.Dp8 * c.Il;
+        const size_t per_row = 2 * (size_t)c.Dl + c.C3l + c.Cql;
+        if (fixed + per_row * pad16(S) > bud) continue;
+        int spt = (int)min((size_t)max(1, cap_rows / S), (bud - fixed) / (per_row * S));
+        while (spt > 1 && fixed + per_row * pad16(spt * S) > bud) --spt;
+        if (spt < 1) continue;
+        const int R = spt * S;
+        if (R > bestR) {
+            bestR = R; best = c; best.SPT = spt; best.Rmax16 = pad16(R);
+            best.smem_bytes = (fixed + per_row * pad16(R)) * 4;
         }
+        if (R >= min(128, max(1, cap_rows / S) * S)) break;
     }
-    if (bestR == 0) return RAT_ESMEM;
-    best.lg = min(32, next_pow2(D));
-    best.lpt = min(32, next_pow2(S));
+    if (!bestR) return RAT_ESMEM;
     *out = best;
     return RAT_OK;
 }
 
-int plan_attn(int S, int D, int H, int dh, AttnPlan* out) {
-    // forward: as + ys (2 x Dp per row), qkv (C3p per row); Wt [D][C3p], WoT [Cq][Dp]
-    return plan_attn_ex(S, D, H, dh, 2, 1, 0, 0, 1, 1, 0, 100 * 1024, out);
+int plan_ff(int D, int M, FFPlan* out) {
+    FFPlan p{};
+    fill_ff_plan(D, M, &p);
+    const size_t bud = (size_t)(max_smem_optin() - 2048) / 4;
+    const size_t fixed = (size_t)p.Mp8 * p.Dl + (size_t)p.Dp8 * p.Ml + p.Mp8;
+    const size_t per_row = 2 * (size_t)p.Dl + p.Ml;
+    int rpt = 256;
+    while (rpt >= 16 && fixed + per_row * rpt > bud) rpt -= 16;
+    if (rpt < 16) return RAT_ESMEM;
+    p.RPT = rpt;
+    p.smem_bytes = (fixed + per_row * rpt) * 4;
+    *out = p;
+    return RAT_OK;
 }
+
+static int g_precision = 1;      // 1 = tf32 tensor-core projections (default), 0 = exact fp32 SIMT
+int precision_mode() { return g_precision; }
 
 }  // namespace rat
 
 using namespace rat;
 
-template <int DH>
+extern "C" int rat_set_precision(int tf32) {
+    g_precision = tf32 ? 1 : 0;
+    return RAT_OK;
+}
+extern "C" int rat_get_precision(void) { return g_precision; }
+
+template <int DH, bool MMA>
 static int launch_attn_fwd(const AttnArgs& a, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_attn_fwd<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(k_attn_fwd<DH, MMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              max_smem_optin());
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_attn_fwd)");
         attr_set = true;
     }
     const long long ntiles = (a.nseq + a.p.SPT - 1) / a.p.SPT;
-    int per_sm = max(1, (int)(220 * 1024 / (a.p.smem_bytes + 1024)));
-    if (per_sm > 4) per_sm = 4;
-    int grid = (int)min(ntiles, (long long)num_sms() * per_sm);
-    k_attn_fwd<DH><<<grid, 256, a.p.smem_bytes, st>>>(a);
+    const int grid = (int)min(ntiles, (long long)num_sms());
+    k_attn_fwd<DH, MMA><<<grid, ENC_THREADS, a.p.smem_bytes, st>>>(a);
     RAT_CHECK_LAUNCH("k_attn_fwd");
     return RAT_OK;
+}
+template <int DH>
+static int launch_attn_fwd_p(const AttnArgs& a, cudaStream_t st) {
+    return g_precision ? launch_attn_fwd<DH, true>(a, st) : launch_attn_fwd<DH, false>(a, st);
 }
 
 extern "C" int rat_attn_fwd(const float* x, const float* res, float* out, const float* ln_w, const float* ln_b,
@@ -349,39 +254,30 @@ extern "C" int rat_attn_fwd(const float* x, const float* res, float* out, const 
     if (rc != RAT_OK) { set_error("rat_attn_fwd: sequence length %d x dim %d does not fit in shared memory", a.g.S, D); return rc; }
     cudaStream_t st = (cudaStream_t)stream;
     switch (dim_head) {
-        case 4: return launch_attn_fwd<4>(a, st);
-        case 8: return launch_attn_fwd<8>(a, st);
-        case 10: return launch_attn_fwd<10>(a, st);
-        case 16: return launch_attn_fwd<16>(a, st);
-        case 20: return launch_attn_fwd<20>(a, st);
-        case 32: return launch_attn_fwd<32>(a, st);
+        case 4: return launch_attn_fwd_p<4>(a, st);
+        case 8: return launch_attn_fwd_p<8>(a, st);
+        case 10: return launch_attn_fwd_p<10>(a, st);
+        case 16: return launch_attn_fwd_p<16>(a, st);
+        case 20: return launch_attn_fwd_p<20>(a, st);
+        case 32: return launch_attn_fwd_p<32>(a, st);
         default: set_error("rat_attn_fwd: dim_head=%d not instantiated (4,8,10,16,20,32)", dim_head); return RAT_EINVAL;
     }
 }
 
-namespace rat {
-int plan_ff(int D, int M, FFPlan* out, int extra_row_floats) {
-    FFPlan p{};
-    p.Dp = round_up(D, 4); p.Mp = round_up(M, 4);
-    p.lg = min(32, next_pow2(D));
-    const size_t budget = 100 * 1024;
-    const size_t wfl = (size_t)D * p.Mp + (size_t)M * p.Dp + p.Mp;
-    int rpt = 192;
-    for (; rpt >= 8; rpt -= 8) {
-        size_t fl = (size_t)rpt * (2 * p.Dp + p.Mp + extra_row_floats) + wfl;
-        if (fl * 4 <= budget) break;
+template <bool MMA>
+static int launch_ff_fwd(const FFArgs& a, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_ff_fwd<MMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin());
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_ff_fwd)");
+        attr_set = true;
     }
-    if (rpt < 8) {
-        rpt = 8;
-        size_t fl = (size_t)rpt * (2 * p.Dp + p.Mp + extra_row_floats) + wfl;
-        if (fl * 4 > (size_t)max_smem_optin()) return RAT_ESMEM;
-    }
-    p.RPT = rpt;
-    p.smem_bytes = ((size_t)rpt * (2 * p.Dp + p.Mp + extra_row_floats) + wfl) * 4;
-    *out = p;
+    const long long ntiles = (a.rows + a.p.RPT - 1) / a.p.RPT;
+    const int grid = (int)min(ntiles, (long long)num_sms());
+    k_ff_fwd<MMA><<<grid, ENC_THREADS, a.p.smem_bytes, st>>>(a);
+    RAT_CHECK_LAUNCH("k_ff_fwd");
     return RAT_OK;
 }
-}  // namespace rat
 
 extern "C" int rat_ff_fwd(const float* x, const float* res, float* out, const float* ln_w, const float* ln_b,
                           const float* W1, const float* b1, const float* W2, const float* b2, long long rows, int D,
@@ -390,21 +286,9 @@ extern "C" int rat_ff_fwd(const float* x, const float* res, float* out, const fl
     FFArgs a{};
     a.x = x; a.res = res; a.out = out; a.ln_w = ln_w; a.ln_b = ln_b; a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2;
     a.rows = rows; a.D = D; a.M = M;
-    int rc = plan_ff(D, M, &a.p, 0);
+    int rc = plan_ff(D, M, &a.p);
     if (rc != RAT_OK) { set_error("rat_ff_fwd: D=%d M=%d does not fit in shared memory", D, M); return rc; }
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_ff_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin());
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_ff_fwd)");
-        attr_set = true;
-    }
-    const long long ntiles = (rows + a.p.RPT - 1) / a.p.RPT;
-    int per_sm = max(1, (int)(220 * 1024 / (a.p.smem_bytes + 1024)));
-    if (per_sm > 4) per_sm = 4;
-    int grid = (int)min(ntiles, (long long)num_sms() * per_sm);
-    k_ff_fwd<<<grid, 256, a.p.smem_bytes, (cudaStream_t)stream>>>(a);
-    RAT_CHECK_LAUNCH("k_ff_fwd");
-    return RAT_OK;
+    return g_precision ? launch_ff_fwd<true>(a, (cudaStream_t)stream) : launch_ff_fwd<false>(a, (cudaStream_t)stream);
 }
 
 extern "C" int rat_layernorm_fwd(const float* x, float* out, const float* w, const float* b, long long rows, int D,

@@ -121,6 +121,142 @@ __device__ __forceinline__ void tile_colsum_acc(const float* __restrict__ A, int
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Tensor-core tile GEMM on shared-memory operands: warp-level mma.sync.m16n8k8 TF32 (fp32 accumulate).
+//
+//   C[m][n] (+)= sum_k A(m,k) * B(k,n)      A(m,k) = A[m*sam + k*sak]   B(k,n) = B[k*sbk + n*sbn]
+//
+// Arbitrary element strides let ONE natural-layout copy of a weight matrix serve as the n-major operand of the
+// forward product and as the k-major operand of the data-gradient product, and let activations be read
+// transposed for the weight-gradient product (reduction over token rows) -- no transposed staging copies.
+// M is processed in 16-row tiles, N in 8-column tiles (NT of them per warp tile), K in steps of 8:
+//   * rows  [M, round_up(M,16)) and cols [N, round_up(N,8)) of the operands must be ALLOCATED and finite;
+//   * K8 = round_up(K,8) and the padding k-range must be zero in at least one operand (and finite in both).
+// Operands are rounded to TF32 with cvt.rna on fragment load (unbiased), accumulation is fp32.
+__device__ __forceinline__ unsigned f2tf32(float x) {
+    unsigned r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+struct EpiNone2 {
+    __device__ __forceinline__ void operator()(int, int, float&, float&) const {}
+};
+
+template <int NT, class Epi>
+__device__ __forceinline__ void mma_tile_gemm(const float* __restrict__ A, int sam, int sak,
+                                              const float* __restrict__ B, int sbk, int sbn, float* __restrict__ C,
+                                              int ldc, int M, int N, int K8, bool accum, Epi epi) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int mt = (M + 15) >> 4, n8 = (N + 7) >> 3, ng = (n8 + NT - 1) / NT;
+    for (int wt = warp; wt < mt * ng; wt += nwarps) {
+        const int m0 = (wt / ng) << 4, nb = (wt % ng) * NT;
+        const int nn = min(NT, n8 - nb);
+        float acc[NT][4];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+        const float* a_lo = A + (size_t)(m0 + g) * sam + (size_t)t * sak;
+        const float* a_hi = a_lo + (size_t)8 * sam;
+        const float* b_p = B + (size_t)t * sbk + (size_t)((nb << 3) + g) * sbn;
+        for (int k0 = 0; k0 < K8; k0 += 8) {
+            unsigned a[4];
+            a[0] = f2tf32(a_lo[(size_t)k0 * sak]);
+            a[1] = f2tf32(a_hi[(size_t)k0 * sak]);
+            a[2] = f2tf32(a_lo[(size_t)(k0 + 4) * sak]);
+            a[3] = f2tf32(a_hi[(size_t)(k0 + 4) * sak]);
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                if (j < nn) {
+                    const float* bp = b_p + (size_t)k0 * sbk + (size_t)(j << 3) * sbn;
+                    const unsigned b0 = f2tf32(bp[0]);
+                    const unsigned b1 = f2tf32(bp[(size_t)4 * sbk]);
+                    mma_tf32_16x8x8(acc[j], a, b0, b1);
+                }
+            }
+        }
+        const bool lo_ok = (m0 + g) < M, hi_ok = (m0 + g + 8) < M;     // rows >= M are computed but never stored
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            if (j < nn) {
+                const int col = ((nb + j) << 3) + 2 * t;
+                float2* plo = reinterpret_cast<float2*>(C + (size_t)(m0 + g) * ldc + col);
+                float2* phi = reinterpret_cast<float2*>(C + (size_t)(m0 + g + 8) * ldc + col);
+                if (lo_ok) {
+                    if (accum) { const float2 o = *plo; acc[j][0] += o.x; acc[j][1] += o.y; }
+                    epi(m0 + g, col, acc[j][0], acc[j][1]);
+                    *plo = make_float2(acc[j][0], acc[j][1]);
+                }
+                if (hi_ok) {
+                    if (accum) { const float2 o = *phi; acc[j][2] += o.x; acc[j][3] += o.y; }
+                    epi(m0 + g + 8, col, acc[j][2], acc[j][3]);
+                    *phi = make_float2(acc[j][2], acc[j][3]);
+                }
+            }
+        }
+    }
+}
+
+// exact-fp32 SIMT twin of mma_tile_gemm with the same operand contract (the parity anchor; `precision=fp32`)
+template <class Epi>
+__device__ __forceinline__ void simt_tile_gemm(const float* __restrict__ A, int sam, int sak,
+                                               const float* __restrict__ B, int sbk, int sbn, float* __restrict__ C,
+                                               int ldc, int M, int N, int K8, bool accum, Epi epi) {
+    const int n2 = (N + 1) >> 1;
+    for (int i = threadIdx.x; i < M * n2; i += blockDim.x) {
+        const int m = i / n2, n = (i % n2) << 1;
+        float c0 = 0.f, c1 = 0.f;
+        const float* ap = A + (size_t)m * sam;
+        const float* bp = B + (size_t)n * sbn;
+        for (int k = 0; k < K8; ++k) {
+            const float a = ap[(size_t)k * sak];
+            c0 = fmaf(a, bp[(size_t)k * sbk], c0);
+            c1 = fmaf(a, bp[(size_t)k * sbk + sbn], c1);
+        }
+        float* cp = C + (size_t)m * ldc + n;
+        if (accum) { c0 += cp[0]; c1 += cp[1]; }
+        epi(m, n, c0, c1);
+        cp[0] = c0; cp[1] = c1;
+    }
+}
+
+template <bool MMA, int NT, class Epi>
+__device__ __forceinline__ void tc_gemm(const float* A, int sam, int sak, const float* B, int sbk, int sbn, float* C,
+                                        int ldc, int M, int N, int K8, bool accum, Epi epi) {
+    if (MMA) mma_tile_gemm<NT>(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K8, accum, epi);
+    else simt_tile_gemm(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K8, accum, epi);
+}
+
+__host__ __device__ inline int pad_ld(int cols) { return ((cols + 7) & ~7) + 4; }   // conflict-free fragment loads
+__host__ __device__ inline int pad8(int v) { return (v + 7) & ~7; }
+__host__ __device__ inline int pad16(int v) { return (v + 15) & ~15; }
+
+// gsum[c] += sum_r A[r][c] with the rows split over thread groups and a fixed-order second stage (deterministic).
+// scratch: blockDim.x floats.  Contains two __syncthreads (call from uniform control flow).
+__device__ __forceinline__ void tile_colsum_acc2(const float* __restrict__ A, int lda, float* __restrict__ gsum,
+                                                 int R, int Cc, float* __restrict__ scratch) {
+    const int G = max(1, (int)blockDim.x / Cc);
+    const int c = threadIdx.x % Cc, rg = threadIdx.x / Cc;
+    if (rg < G) {
+        float s = 0.f;
+        for (int r = rg; r < R; r += G) s += A[(size_t)r * lda + c];
+        scratch[rg * Cc + c] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < Cc) {
+        float s = 0.f;
+        for (int q = 0; q < G; ++q) s += scratch[q * Cc + threadIdx.x];
+        gsum[threadIdx.x] += s;
+    }
+    __syncthreads();
+}
+
 // sequence geometry: local row (ls, p) of a tile that starts at sequence s0
 struct SeqGeom {
     int S;          // positions per sequence

@@ -74,6 +74,16 @@ class EngineSpec:
         return sum(f.vocab_size for f in self.features)
 
 
+def set_precision(mode: str):
+    """'tf32' (default): tensor-core projections (mma.sync TF32, fp32 accumulate); 'fp32': exact SIMT twin."""
+    assert mode in ("tf32", "fp32"), mode
+    call("rat_set_precision", 1 if mode == "tf32" else 0)
+
+
+def get_precision() -> str:
+    return "tf32" if query("rat_get_precision") else "fp32"
+
+
 def _align4(n):
     return (n + 3) // 4 * 4
 
