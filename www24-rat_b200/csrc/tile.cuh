@@ -162,8 +162,9 @@ __device__ __forceinline__ void mma_tile_gemm(const float* __restrict__ A, int s
         float acc[NT][4];
 #pragma unroll
         for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-        const float* a_lo = A + (size_t)(m0 + g) * sam + (size_t)t * sak;
-        const float* a_hi = a_lo + (size_t)8 * sam;
+        // rows >= M are clamped to the last valid row (their results are never stored): no out-of-tile reads
+        const float* a_lo = A + (size_t)min(m0 + g, M - 1) * sam + (size_t)t * sak;
+        const float* a_hi = A + (size_t)min(m0 + g + 8, M - 1) * sam + (size_t)t * sak;
         const float* b_p = B + (size_t)t * sbk + (size_t)((nb << 3) + g) * sbn;
         for (int k0 = 0; k0 < K8; k0 += 8) {
             unsigned a[4];
