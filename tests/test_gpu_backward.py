@@ -327,7 +327,7 @@ def _golden_train(rn, name):
     assert float(eng.opt_state[0]) == pytest.approx(float(c["z"]["train/norm2"]), rel=2e-3)
     ref_p, ref_b = split_state(c["sd2"])
     for k, w in ref_p.items():
-        atol = 2.5e-3 if noise_grad_param(k, spec) else 5e-5
+        atol = 4e-3 if noise_grad_param(k, spec) else 5e-5
         assert_close(f"param {k}", eng.p[k], w, 1e-4, atol)
     for k, w in ref_b.items():
         # running_mean tracks mean(z) where z includes the Linear bias that Adam moves by +-lr of pure rounding noise
@@ -370,7 +370,7 @@ def _full_width_train(rn, shape, B, K):
         if k.startswith("query_proj"):
             continue
         if noise_grad_param(k, spec):
-            assert_close(f"param {k}", eng.p[k], w, 2e-4, 3.5e-3)
+            assert_close(f"param {k}", eng.p[k], w, 2e-4, 5.5e-3)
         else:
             assert_close_adam(f"param {k}", eng.p[k], w, 2e-4, 1e-4, lr_steps=3.5e-3)
 
@@ -397,6 +397,6 @@ def test_two_train_steps_tf32_close_to_reference(rn, name):
     ref_p, _ = split_state(c["sd2"])
     for k, w in ref_p.items():
         if noise_grad_param(k, spec):
-            assert_close(f"param {k}", eng.p[k], w, 1e-3, 2.5e-3)
+            assert_close(f"param {k}", eng.p[k], w, 1e-3, 4e-3)
         else:
             assert_close_adam(f"param {k}", eng.p[k], w, 2e-3, 3e-4, lr_steps=2.5e-3, max_outlier_frac=0.03)

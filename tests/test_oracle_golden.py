@@ -61,7 +61,7 @@ def test_two_train_steps_match_reference(name):
         # Adam normalises the step to ~lr, so compare with an absolute tolerance of a few % of lr
         atol = 5e-5
         if noise_grad_param(k, spec):
-            atol = 2.5e-3      # true gradient is 0 (bias before BatchNorm): Adam turns rounding noise into +-lr steps
+            atol = 4e-3      # true gradient is 0 (bias before BatchNorm): Adam turns rounding noise into +-lr steps
         np.testing.assert_allclose(params[k].numpy(), w.numpy(), rtol=1e-4, atol=atol, err_msg=k)
     for k, w in ref_b.items():
         np.testing.assert_allclose(bufs[k].numpy(), w.numpy(), rtol=1e-4, atol=1e-6, err_msg=k)
