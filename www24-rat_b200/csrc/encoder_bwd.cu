@@ -15,6 +15,7 @@
 // => bitwise run-to-run deterministic.
 #include "tile.cuh"
 #include "encoder_common.cuh"
+#include "attn_mma.cuh"
 #include "../../include/rat_b200.h"
 
 namespace rat {
@@ -37,7 +38,7 @@ struct AttnBwdArgs {
 //   g = grad wrt LN output (smem, ld) ; dx[gr] = base[gr] + rstd*(g*gamma - mean(g*gamma) - xhat*mean(g*gamma*xhat))
 //   acc3[0][d] += sum_r g*xhat (dgamma), acc3[1][d] += sum_r g (dbeta), acc3[2][d] += sum_r extra[r][d] (optional)
 __device__ __forceinline__ void ln_bwd_rows(const float* __restrict__ x, const float* __restrict__ base,
-                                            float* __restrict__ dx, const SeqGeom& g, long long s0, int R, int D, int Dp,
+                                            float* __restrict__ dx, const long long* __restrict__ rowidx, int R, int D, int Dp,
                                             const float* __restrict__ gamma, const float* __restrict__ gsm, int ldg,
                                             const float* __restrict__ stats, const float* __restrict__ extra,
                                             int ldx, int lg, float* __restrict__ scratch, float* __restrict__ acc3) {
@@ -52,7 +53,7 @@ __device__ __forceinline__ void ln_bwd_rows(const float* __restrict__ x, const f
         const bool ok = r < R;
         long long gr = 0;
         float mean = 0.f, rstd = 0.f;
-        if (ok) { gr = g.grow(s0 + r / g.S, r % g.S); mean = stats[2 * r]; rstd = stats[2 * r + 1]; }
+        if (ok) { gr = rowidx[r]; mean = stats[2 * r]; rstd = stats[2 * r + 1]; }
         float s1 = 0.f, s2 = 0.f;
         float xh[MAXPER], gg[MAXPER];
 #pragma unroll
@@ -124,6 +125,8 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_attn_bwd(AttnBwdArgs a) {
     float* dqkv = qkv + (size_t)Rmax * C3l;             // [Rmax][C3l]
     float* os = dqkv + (size_t)Rmax * C3l;              // [Rmax][Cql]
     float* dos = os + (size_t)Rmax * Cql;               // [Rmax][Cql]
+    float* wscr = dos + (size_t)Rmax * Cql;             // [warps][32] per-warp softmax statistics (mma attention core)
+    long long* rowidx = reinterpret_cast<long long*>(wscr + (ENC_THREADS / 32) * 32);   // [Rmax]
     // CTA-private gradient record in global memory: [gW nchunks*C3p8*Dl | gWo Dp8*Il | small 3*Dp8]
     float* rec = a.partials + (size_t)blockIdx.x * p.psize;
     float* gW = rec;
@@ -139,13 +142,16 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_attn_bwd(AttnBwdArgs a) {
         const int nseq_t = (int)min((long long)p.SPT, a.nseq - s0);
         const int R = nseq_t * S, R16 = pad16(R), R8 = pad8(R);
         __syncthreads();
-        ln_rows_to_smem(a.x, a.g, s0, R, D, Dp8, a.ln_w, a.ln_b, as, Dl, p.lg, stats);
-        for (int i = threadIdx.x; i < R * Dl; i += blockDim.x) {
-            const int r = i / Dl, d = i - r * Dl;
-            da[i] = 0.f;
-            float v = 0.f;
-            if (d < D) v = a.alpha * a.dout[a.g.grow(s0 + r / S, r % S) * D + d];
-            dys[i] = v;
+        fill_rowidx(rowidx, a.g, s0, R);
+        __syncthreads();
+        ln_rows_to_smem(a.x, rowidx, R, D, Dp8, a.ln_w, a.ln_b, as, Dl, p.lg, stats);
+        zero_floats(da, (size_t)R * Dl);
+        {
+            const int lg = p.lg, groups = blockDim.x / lg, gi = threadIdx.x / lg, li = threadIdx.x % lg;
+            for (int r = gi; r < R; r += groups) {
+                const float* src = a.dout + rowidx[r] * D;
+                for (int d = li; d < Dp8; d += lg) dys[(size_t)r * Dl + d] = d < D ? a.alpha * src[d] : 0.f;
+            }
         }
         zero_rows(as, Dl, R, R16);
         zero_rows(da, Dl, R, R16);
@@ -160,11 +166,13 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_attn_bwd(AttnBwdArgs a) {
             tc_gemm<MMA, 4>(as, Dl, 1, W, 1, Dl, qkv, C3l, R, p.C3p8, Dp8, false, EpiNone2());
             tc_gemm<MMA, 3>(dys, Dl, 1, WoN + col0, Il, 1, dos, Cql, R, p.Cq8, Dp8, false, EpiNone2());
             __syncthreads();
-            // (2) attention forward recompute -> os, lse
-            attn_core<DH>(qkv, C3l, p.Cq, os, Cql, lse, nseq_t, S, p.hc, p.lpt, a.scale);
+            const bool tc_attn = MMA && S <= 16;
+            // (2) attention forward recompute -> os (+ lse for the SIMT backward core)
+            if (tc_attn) attn_fwd_mma<DH>(qkv, C3l, p.Cq, os, Cql, nullptr, nseq_t, S, p.hc, a.scale);
+            else attn_core<DH>(qkv, C3l, p.Cq, os, Cql, lse, nseq_t, S, p.hc, p.lpt, a.scale);
             __syncthreads();
-            // delta[r][hl] = do . o
-            for (int i = threadIdx.x; i < R * p.hc; i += blockDim.x) {
+            // delta[r][hl] = do . o   (SIMT core only; the tensor-core core derives it from P and dP)
+            if (!tc_attn) for (int i = threadIdx.x; i < R * p.hc; i += blockDim.x) {
                 const int r = i / p.hc, hl = i - r * p.hc;
                 const float* o = os + (size_t)r * Cql + hl * DH;
                 const float* dd = dos + (size_t)r * Cql + hl * DH;
@@ -177,14 +185,15 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_attn_bwd(AttnBwdArgs a) {
             tc_gemm<MMA, 3>(dys, 1, Dl, os, Cql, 1, gWo + col0, Il, Dp8, p.Cq8, R8, true, EpiNone2());
             __syncthreads();
             // (5) attention backward -> dqkv
-            attn_bwd_core<DH>(qkv, dqkv, C3l, p.Cq, dos, Cql, lse, delta, nseq_t, S, p.hc, p.lpt, a.scale);
+            if (tc_attn) attn_bwd_mma<DH>(qkv, dqkv, C3l, p.Cq, dos, Cql, nseq_t, S, p.hc, a.scale, wscr);
+            else attn_bwd_core<DH>(qkv, dqkv, C3l, p.Cq, dos, Cql, lse, delta, nseq_t, S, p.hc, p.lpt, a.scale);
             __syncthreads();
             // (6) gW[ch][c][d] += sum_r dqkv[r][c] as[r][d] ; (7) da[r][d] += sum_c dqkv[r][c] W[c][d]
             tc_gemm<MMA, 3>(dqkv, 1, C3l, as, Dl, 1, gW + (size_t)ch * p.C3p8 * Dl, Dl, p.C3p8, Dp8, R8, true, EpiNone2());
             tc_gemm<MMA, 3>(dqkv, C3l, 1, W, Dl, 1, da, Dl, R, Dp8, p.C3p8, true, EpiNone2());
         }
         __syncthreads();
-        ln_bwd_rows(a.x, a.base, a.dx, a.g, s0, R, D, Dp8, a.ln_w, da, Dl, stats, dys, Dl, p.lg, scratch, g3);
+        ln_bwd_rows(a.x, a.base, a.dx, rowidx, R, D, Dp8, a.ln_w, da, Dl, stats, dys, Dl, p.lg, scratch, g3);
     }
     __syncthreads();
     float* small = gWo + (size_t)Dp8 * Il;
@@ -278,6 +287,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_ff_bwd(FFBwdArgs a) {
     float* ys = dys + (size_t)p.RPT * Dl;               // [RPT][Dl]  grad wrt FF input
     float* hs = ys + (size_t)p.RPT * Dl;                // [RPT][Ml]  pre -> h
     float* dhs = hs + (size_t)p.RPT * Ml;               // [RPT][Ml]  dh -> dpre
+    long long* rowidx = reinterpret_cast<long long*>(dhs + (size_t)p.RPT * Ml);   // [RPT]
     // CTA-private gradient record: [gW1 Mp8*Dl | gW2 Dp8*Ml | gb1 Mp8 | small 3*Dp8]
     float* rec = a.partials + (size_t)blockIdx.x * p.psize;
     float* gW1 = rec;
@@ -296,8 +306,10 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_ff_bwd(FFBwdArgs a) {
         const int R = (int)min((long long)p.RPT, a.rows - r0);
         const int R16 = pad16(R), R8 = pad8(R);
         __syncthreads();
+        fill_rowidx(rowidx, flat, r0, R);
+        __syncthreads();
         if (a.ln_w) {
-            ln_rows_to_smem(a.x, flat, r0, R, D, Dp8, a.ln_w, a.ln_b, xs, Dl, lg, stats);
+            ln_rows_to_smem(a.x, rowidx, R, D, Dp8, a.ln_w, a.ln_b, xs, Dl, lg, stats);
         } else {
             for (int i = threadIdx.x; i < R * D; i += blockDim.x) {
                 const int r = i / D, d = i - r * D;
@@ -325,7 +337,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_ff_bwd(FFBwdArgs a) {
         tc_gemm<MMA, 3>(dhs, Ml, 1, W1n, Dl, 1, ys, Dl, R, Dp8, Mp8, false, EpiNone2());
         tile_colsum_acc2(dhs, Ml, gb1, R, Mp8, scratch);              // db1 (two barriers inside)
         if (a.ln_w) {
-            ln_bwd_rows(a.x, a.base, a.dx, flat, r0, R, D, Dp8, a.ln_w, ys, Dl, stats, dys, Dl, lg, scratch, g3);
+            ln_bwd_rows(a.x, a.base, a.dx, rowidx, R, D, Dp8, a.ln_w, ys, Dl, stats, dys, Dl, lg, scratch, g3);
         } else {
             // dx = base + dxa ; db2 += colsum(dy)  (deterministic per-group partials)
             float pe[4] = {0.f, 0.f, 0.f, 0.f};
@@ -470,8 +482,8 @@ int plan_attn_bwd(int S, int D, int H, int dh, AttnPlan* out) {
         AttnPlan c{};
         fill_attn_plan(S, D, H, dh, hc, &c);
         const size_t fixed = (size_t)c.nchunks * c.C3p8 * c.Dl + (size_t)c.Dp8 * c.Il + 3 * c.Dp8 +
-                             (size_t)(ENC_THREADS / c.lg) * 3 * c.Dp8;
-        const size_t per_row = 3 * (size_t)c.Dl + 2 * c.C3l + 2 * c.Cql + 2 + 2 * hc;
+                             (size_t)(ENC_THREADS / c.lg) * 3 * c.Dp8 + ENC_THREADS;
+        const size_t per_row = 3 * (size_t)c.Dl + 2 * c.C3l + 2 * c.Cql + 2 + 2 * hc + 2;
         if (fixed + per_row * pad16(S) > bud) continue;
         int spt = (int)min((size_t)max(1, cap_rows / S), (bud - fixed) / (per_row * S));
         while (spt > 1 && fixed + per_row * pad16(spt * S) > bud) --spt;
@@ -496,7 +508,7 @@ int plan_ff_bwd(int D, int M, FFPlan* out) {
     const size_t bud = (size_t)(max_smem_optin() - 2048) / 4;
     const size_t fixed = (size_t)p.Mp8 * p.Dl + (size_t)p.Dp8 * p.Ml + 2 * p.Mp8 + 3 * p.Dp8 +
                          (size_t)max((ENC_THREADS / p.lg) * 3 * p.Dp8, ENC_THREADS);
-    const size_t per_row = 3 * (size_t)p.Dl + 2 * p.Ml + 2;
+    const size_t per_row = 3 * (size_t)p.Dl + 2 * p.Ml + 2 + 2;
     int rpt = 192;
     while (rpt >= 16 && fixed + per_row * rpt > bud) rpt -= 16;
     if (rpt < 16) return RAT_ESMEM;

@@ -82,7 +82,12 @@ __device__ __forceinline__ void stage_qkv_chunks(const float* __restrict__ Wq, c
 
 // LayerNorm of R rows (global -> smem), eps=1e-5, biased variance (torch.nn.LayerNorm semantics); pad columns
 // [D, Dp8) are zeroed; stats (optional) receives per-row (mean, rstd) for the backward pass.
-__device__ __forceinline__ void ln_rows_to_smem(const float* __restrict__ x, const SeqGeom& g, long long s0, int R,
+// rowidx[r] = global token row of local row r (computed once per tile: no div/mod in the row loops)
+__device__ __forceinline__ void fill_rowidx(long long* __restrict__ rowidx, const SeqGeom& g, long long s0, int R) {
+    for (int r = threadIdx.x; r < R; r += blockDim.x) rowidx[r] = g.grow(s0 + r / g.S, r % g.S);
+}
+
+__device__ __forceinline__ void ln_rows_to_smem(const float* __restrict__ x, const long long* __restrict__ rowidx, int R,
                                                 int D, int Dp8, const float* __restrict__ w,
                                                 const float* __restrict__ b, float* __restrict__ dst, int ld, int lg,
                                                 float* __restrict__ stats) {
@@ -93,16 +98,20 @@ __device__ __forceinline__ void ln_rows_to_smem(const float* __restrict__ x, con
         const int r = r0 + gi;
         const bool ok = r < R;
         const float* src = x;
-        if (ok) src = x + g.grow(s0 + r / g.S, r % g.S) * D;
+        if (ok) src = x + rowidx[r] * D;
+        float xv[4] = {0.f, 0.f, 0.f, 0.f};          // D <= 4*lg (D <= 128)
         float sum = 0.f;
-        if (ok) for (int d = li; d < D; d += lg) sum += src[d];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const int d = li + k * lg; if (ok && d < D) { xv[k] = src[d]; sum += xv[k]; } }
         const float mean = group_sum(sum, lg) * invD;
         float sq = 0.f;
-        if (ok) for (int d = li; d < D; d += lg) { float t = src[d] - mean; sq = fmaf(t, t, sq); }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const int d = li + k * lg; if (ok && d < D) { float t = xv[k] - mean; sq = fmaf(t, t, sq); } }
         const float var = group_sum(sq, lg) * invD;
         const float rstd = 1.0f / sqrtf(var + 1e-5f);
         if (ok) {
-            for (int d = li; d < D; d += lg) dst[(size_t)r * ld + d] = (src[d] - mean) * rstd * w[d] + b[d];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const int d = li + k * lg; if (d < D) dst[(size_t)r * ld + d] = (xv[k] - mean) * rstd * w[d] + b[d]; }
             for (int d = D + li; d < Dp8; d += lg) dst[(size_t)r * ld + d] = 0.f;
             if (stats && li == 0) { stats[2 * r] = mean; stats[2 * r + 1] = rstd; }
         }

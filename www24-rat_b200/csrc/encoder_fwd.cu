@@ -17,6 +17,7 @@
 // reshape/transpose/flatten copies (RAT_m2.py:221-235) are pure indexing here.
 #include "tile.cuh"
 #include "encoder_common.cuh"
+#include "attn_mma.cuh"
 #include "../../include/rat_b200.h"
 
 namespace rat {
@@ -46,6 +47,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_attn_fwd(AttnArgs a) {
     float* ys = as + (size_t)Rmax * Dl;                 // [Rmax][Dl]  out-projection accumulator
     float* qkv = ys + (size_t)Rmax * Dl;                // [Rmax][C3l]
     float* os = qkv + (size_t)Rmax * C3l;               // [Rmax][Cql]
+    long long* rowidx = reinterpret_cast<long long*>(os + (size_t)Rmax * Cql);   // [Rmax]
     stage_qkv_chunks(a.Wq, a.Wk, a.Wv, D, p, Wc);
     stage_padded(a.Wo, D, a.I, p.Dp8, Il, WoN);
     zero_floats(as, (size_t)Rmax * (2 * Dl + C3l + Cql));
@@ -55,7 +57,9 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_attn_fwd(AttnArgs a) {
         const int nseq_t = (int)min((long long)p.SPT, a.nseq - s0);
         const int R = nseq_t * S;
         __syncthreads();                                // previous tile fully consumed (and staging visible)
-        ln_rows_to_smem(a.x, a.g, s0, R, D, p.Dp8, a.ln_w, a.ln_b, as, Dl, p.lg, nullptr);
+        fill_rowidx(rowidx, a.g, s0, R);
+        __syncthreads();
+        ln_rows_to_smem(a.x, rowidx, R, D, p.Dp8, a.ln_w, a.ln_b, as, Dl, p.lg, nullptr);
         zero_rows(as, Dl, R, pad16(R));
         zero_rows(os, Cql, R, pad16(R));
         zero_floats(ys, (size_t)pad16(R) * Dl);
@@ -65,18 +69,23 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_attn_fwd(AttnArgs a) {
             // q|k|v[r][c] = sum_d as[r][d] * W[c][d]
             tc_gemm<MMA, 4>(as, Dl, 1, W, 1, Dl, qkv, C3l, R, p.C3p8, p.Dp8, false, EpiNone2());
             __syncthreads();
-            attn_core<DH>(qkv, C3l, p.Cq, os, Cql, nullptr, nseq_t, S, p.hc, p.lpt, a.scale);
+            if (MMA && S <= 16) attn_fwd_mma<DH>(qkv, C3l, p.Cq, os, Cql, nullptr, nseq_t, S, p.hc, a.scale);
+            else attn_core<DH>(qkv, C3l, p.Cq, os, Cql, nullptr, nseq_t, S, p.hc, p.lpt, a.scale);
             __syncthreads();
             // ys[r][d] += sum_c os[r][c] * Wo[d][col0 + c]
             tc_gemm<MMA, 3>(os, Cql, 1, WoN + ch * p.Cq, 1, Il, ys, Dl, R, p.Dp8, p.Cq8, true, EpiNone2());
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < R * D; i += blockDim.x) {
-            const int r = i / D, d = i - r * D;
-            const long long gr = a.g.grow(s0 + r / S, r % S);
-            float v = a.alpha * (ys[(size_t)r * Dl + d] + a.bo[d]);
-            if (a.res) v += a.res[gr * D + d];
-            a.out[gr * D + d] = v;
+        {
+            const int lg = p.lg, groups = blockDim.x / lg, gi = threadIdx.x / lg, li = threadIdx.x % lg;
+            for (int r = gi; r < R; r += groups) {
+                const long long gr = rowidx[r] * D;
+                for (int d = li; d < D; d += lg) {
+                    float v = a.alpha * (ys[(size_t)r * Dl + d] + a.bo[d]);
+                    if (a.res) v += a.res[gr + d];
+                    a.out[gr + d] = v;
+                }
+            }
         }
     }
 }
@@ -110,6 +119,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_ff_fwd(FFArgs a) {
     float* xs = b1s + p.Mp8;                            // [RPT][Dl]
     float* hs = xs + (size_t)p.RPT * Dl;                // [RPT][Ml]
     float* ys = hs + (size_t)p.RPT * Ml;                // [RPT][Dl]
+    long long* rowidx = reinterpret_cast<long long*>(ys + (size_t)p.RPT * Dl);   // [RPT]
     stage_padded(a.W1, M, D, p.Mp8, Dl, W1n);
     stage_padded(a.W2, D, M, p.Dp8, Ml, W2n);
     for (int i = threadIdx.x; i < p.Mp8; i += blockDim.x) b1s[i] = i < M ? a.b1[i] : 0.f;
@@ -121,7 +131,9 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_ff_fwd(FFArgs a) {
         const int R = (int)min((long long)p.RPT, a.rows - r0);
         __syncthreads();
         if (a.ln_w) {
-            ln_rows_to_smem(a.x, flat, r0, R, D, p.Dp8, a.ln_w, a.ln_b, xs, Dl, p.lg, nullptr);
+            fill_rowidx(rowidx, flat, r0, R);
+            __syncthreads();
+            ln_rows_to_smem(a.x, rowidx, R, D, p.Dp8, a.ln_w, a.ln_b, xs, Dl, p.lg, nullptr);
         } else {
             for (int i = threadIdx.x; i < R * D; i += blockDim.x) {
                 const int r = i / D, d = i - r * D;
@@ -173,7 +185,7 @@ int plan_attn(int S, int D, int H, int dh, AttnPlan* out) {
         AttnPlan c{};
         fill_attn_plan(S, D, H, dh, hc, &c);
         const size_t fixed = (size_t)c.nchunks * c.C3p8 * c.Dl + (size_t)c.Dp8 * c.Il;
-        const size_t per_row = 2 * (size_t)c.Dl + c.C3l + c.Cql;
+        const size_t per_row = 2 * (size_t)c.Dl + c.C3l + c.Cql + 2;
         if (fixed + per_row * pad16(S) > bud) continue;
         int spt = (int)min((size_t)max(1, cap_rows / S), (bud - fixed) / (per_row * S));
         while (spt > 1 && fixed + per_row * pad16(spt * S) > bud) --spt;
@@ -195,7 +207,7 @@ int plan_ff(int D, int M, FFPlan* out) {
     fill_ff_plan(D, M, &p);
     const size_t bud = (size_t)(max_smem_optin() - 2048) / 4;
     const size_t fixed = (size_t)p.Mp8 * p.Dl + (size_t)p.Dp8 * p.Ml + p.Mp8;
-    const size_t per_row = 2 * (size_t)p.Dl + p.Ml;
+    const size_t per_row = 2 * (size_t)p.Dl + p.Ml + 2;
     int rpt = 256;
     while (rpt >= 16 && fixed + per_row * rpt > bud) rpt -= 16;
     if (rpt < 16) return RAT_ESMEM;
