@@ -27,7 +27,7 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
-@pytest.fixture(params=["fp32", "tf32"])
+@pytest.fixture(params=["fp32", "tf32", "bf16"])
 def precision(request):
     """run a GPU test in both arithmetic modes of the RAT-block projections."""
     import rat_native

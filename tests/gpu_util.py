@@ -10,12 +10,19 @@ PREC = {"mode": "fp32"}
 
 
 def tf32():
-    return PREC["mode"] == "tf32"
+    return PREC["mode"] in ("tf32", "bf16")
+
+
+def bf16():
+    return PREC["mode"] == "bf16"
 
 
 def ptol(rtol, atol, rt=1e-2, at_scale=40.0):
     """(rtol, atol) for the current precision mode: fp32 values as given; tf32 (10-bit mantissa operands,
-    fp32 accumulate): rtol 1e-2 and atol x40."""
+    fp32 accumulate): rtol 1e-2 and atol x40; bf16 (tcgen05, 8-bit mantissa operands, fp32 accumulate):
+    rtol 4e-2 and atol x640 -- unit roundoff 2^-8 over K~40..80 term dot products of O(1) operands)."""
+    if bf16():
+        return (max(rtol, 4 * rt), atol * at_scale * 16)
     return (max(rtol, rt), atol * at_scale) if tf32() else (rtol, atol)
 
 

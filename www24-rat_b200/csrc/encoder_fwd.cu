@@ -217,15 +217,22 @@ int plan_ff(int D, int M, FFPlan* out) {
     return RAT_OK;
 }
 
-static int g_precision = 1;      // 1 = tf32 tensor-core projections (default), 0 = exact fp32 SIMT
+// 0 = exact fp32 SIMT ; 1 = tf32 mma.sync projections ; 2 = bf16 tcgen05 projections (shapes the tcgen05 kernels do
+// not cover run the tf32 kernels)
+static int g_precision = 1;
 int precision_mode() { return g_precision; }
 
 }  // namespace rat
 
 using namespace rat;
 
-extern "C" int rat_set_precision(int tf32) {
-    g_precision = tf32 ? 1 : 0;
+int ff_fwd_tc_dispatch(const float* x, const float* res, float* out, const float* ln_w, const float* ln_b,
+                       const float* W1, const float* b1, const float* W2, const float* b2, long long rows, int D, int M,
+                       cudaStream_t st);
+
+extern "C" int rat_set_precision(int mode) {
+    RAT_REQUIRE(mode >= 0 && mode <= 2, "rat_set_precision: mode must be 0 (fp32), 1 (tf32) or 2 (bf16 tcgen05)");
+    g_precision = mode;
     return RAT_OK;
 }
 extern "C" int rat_get_precision(void) { return g_precision; }
@@ -298,6 +305,10 @@ extern "C" int rat_ff_fwd(const float* x, const float* res, float* out, const fl
     FFArgs a{};
     a.x = x; a.res = res; a.out = out; a.ln_w = ln_w; a.ln_b = ln_b; a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2;
     a.rows = rows; a.D = D; a.M = M;
+    if (g_precision == 2) {
+        const int rc2 = ff_fwd_tc_dispatch(x, res, out, ln_w, ln_b, W1, b1, W2, b2, rows, D, M, (cudaStream_t)stream);
+        if (rc2 <= 0) return rc2;
+    }
     int rc = plan_ff(D, M, &a.p);
     if (rc != RAT_OK) { set_error("rat_ff_fwd: D=%d M=%d does not fit in shared memory", D, M); return rc; }
     return g_precision ? launch_ff_fwd<true>(a, (cudaStream_t)stream) : launch_ff_fwd<false>(a, (cudaStream_t)stream);

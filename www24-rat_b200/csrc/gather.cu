@@ -6,6 +6,7 @@
 // and LR_Layer.forward shallow.py:36-45 -- in ONE pass over the output block.
 #include "common.cuh"
 #include "../../include/rat_b200.h"
+#include <algorithm>
 
 namespace rat {
 
@@ -142,6 +143,93 @@ __global__ void __launch_bounds__(256) k_gather(GatherArgs a) {
     }
 }
 
+// ---- K1 (fast path): one WARP per (b,t) row of the block ---------------------------------------------------
+// Lane l < L owns column l of the id matrix: it validates id[bt][l] once and keeps the table-row offset in a
+// register; every lane then produces vector chunks c = lane, lane+32, ... of the row's N*D contiguous output
+// floats.  Row offsets travel by shuffle, so all table-row loads of a lane are INDEPENDENT (CH*maxw 128-bit loads
+// in flight per lane) and the block row is written as one contiguous, fully coalesced 128-bit stream.
+// Same arithmetic as k_gather (left-to-right sum-pool, same philox element index): results are bit-identical.
+template <int VW, int CH>
+__global__ void __launch_bounds__(256) k_gather_rows(GatherArgs a) {
+    const int lane = threadIdx.x & 31;
+    int maxw = lane < a.F ? a.field_width[lane] : 0;           // F <= L <= 32 on this path
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxw = max(maxw, __shfl_xor_sync(0xffffffffu, maxw, o));
+    const int N = a.F + 1, DV = a.D / VW, NC = N * DV;
+    const long long nrows = (long long)a.B * a.T;
+    const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+    const float inv_keep = a.drop_p > 0.f ? 1.0f / (1.0f - a.drop_p) : 1.0f;
+    const int my_off = lane < a.L ? a.col_off[lane] : 0;
+    const int my_vocab = lane < a.L ? a.col_vocab[lane] : 1;
+    // per-lane chunk geometry is row independent: token n, vector dv, first column c0 and width w of its field
+    int cn[CH], cdv[CH], cc0[CH], cw[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+        const int c = lane + 32 * i;
+        cn[i] = c < NC ? c / DV : -1;
+        cdv[i] = c < NC ? c - cn[i] * DV : 0;
+        cc0[i] = 0; cw[i] = 0;
+        if (cn[i] > 0) { cc0[i] = a.field_col0[cn[i] - 1]; cw[i] = a.field_width[cn[i] - 1]; }
+    }
+    for (long long bt = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); bt < nrows; bt += wstride) {
+        const int t = (int)(bt % a.T);
+        const long long b = bt / a.T;
+        int id = 0;
+        if (lane < a.L) {
+            id = __ldg(a.ids + bt * a.L + lane);
+            if (id < 0 || id >= my_vocab) { atomicOr(a.err, 1); id = 0; }
+        }
+        const int row = my_off + id;                         // table row of column `lane`
+        int lab = __ldg(a.labels + bt);
+        if (lab < 0 || lab > 2) { if (lane == 0) atomicOr(a.err, 4); lab = 0; }
+        if (t == 0 && a.lr_out) {                            // LR_Layer (shallow.py:37-38), field order, lane 0
+            const float lrv = lane < a.L ? __ldg(a.lr_W + row) : 0.f;
+            float tot = 0.f;
+            int col = 0;
+            for (int f = 0; f < a.F; ++f) {
+                const int w = a.field_width[f];
+                float s = 0.f;
+                for (int j = 0; j < w; ++j, ++col) s += __shfl_sync(0xffffffffu, lrv, col);
+                tot += s;
+            }
+            if (lane == 0) a.lr_out[b] = tot;
+        }
+        float val[CH][VW];
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+#pragma unroll
+            for (int k = 0; k < VW; ++k) val[i][k] = 0.f;
+            if (cn[i] == 0) vload<VW>(a.label_W + (long long)lab * a.D + cdv[i] * VW, val[i]);
+        }
+        for (int j = 0; j < maxw; ++j) {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                const int src = min(cc0[i] + j, 31);
+                const int r = __shfl_sync(0xffffffffu, row, src);
+                if (j < cw[i]) {
+                    float rv[VW];
+                    vload<VW>(a.emb_W + (long long)r * a.D + cdv[i] * VW, rv);
+#pragma unroll
+                    for (int k = 0; k < VW; ++k) val[i][k] = (j == 0) ? rv[k] : val[i][k] + rv[k];
+                }
+            }
+        }
+        float* out_row = a.block + bt * (long long)NC * VW;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            if (cn[i] < 0) continue;
+            if (t == 0 && a.x_emb && cn[i] > 0)
+                vstore<VW>(a.x_emb + (b * a.F + (cn[i] - 1)) * a.D + cdv[i] * VW, val[i]);
+            if (a.drop_p > 0.f) {
+                const unsigned long long e0 = ((unsigned long long)bt * NC + (lane + 32 * i)) * VW;
+#pragma unroll
+                for (int k = 0; k < VW; ++k) val[i][k] *= dropout_scale(a.seed, a.stream, e0 + k, a.drop_p, inv_keep);
+            }
+            vstore<VW>(out_row + (size_t)(lane + 32 * i) * VW, val[i]);
+        }
+    }
+}
+
 // in-place dropout backward on the block gradient (same mask as k_gather)
 __global__ void k_dropout_bwd(float* __restrict__ g, long long n, float p, unsigned long long seed,
                               unsigned int stream) {
@@ -207,6 +295,21 @@ extern "C" int rat_gather_fwd(const float* emb_W, const float* lr_W, const float
     long long total = (long long)B * T * (F + 1) * (D / vw);
     int grid = grid_for(total, 256);
     cudaStream_t st = (cudaStream_t)stream;
+    const int nc = (F + 1) * (D / vw);                    // vector chunks per (b,t) row
+    const int ch = (nc + 31) / 32;
+    if (L <= 32 && ch <= 8 && vw >= 2) {       // warp-per-row fast path
+        const long long nrows = (long long)B * T;
+        const int rgrid = (int)std::min<long long>((nrows + 7) / 8, (long long)num_sms() * 8);
+#define RAT_GATHER_ROWS(VW_, CH_) k_gather_rows<VW_, CH_><<<rgrid, 256, 0, st>>>(a)
+        if (vw == 4) {
+            if (ch <= 2) RAT_GATHER_ROWS(4, 2); else if (ch <= 5) RAT_GATHER_ROWS(4, 5); else RAT_GATHER_ROWS(4, 8);
+        } else {
+            if (ch <= 2) RAT_GATHER_ROWS(2, 2); else if (ch <= 5) RAT_GATHER_ROWS(2, 5); else RAT_GATHER_ROWS(2, 8);
+        }
+#undef RAT_GATHER_ROWS
+        RAT_CHECK_LAUNCH("k_gather_rows");
+        return RAT_OK;
+    }
     if (vw == 4) k_gather<4><<<grid, 256, 0, st>>>(a);
     else if (vw == 2) k_gather<2><<<grid, 256, 0, st>>>(a);
     else k_gather<1><<<grid, 256, 0, st>>>(a);

@@ -74,14 +74,18 @@ class EngineSpec:
         return sum(f.vocab_size for f in self.features)
 
 
+_PREC = {"fp32": 0, "tf32": 1, "bf16": 2}
+
+
 def set_precision(mode: str):
-    """'tf32' (default): tensor-core projections (mma.sync TF32, fp32 accumulate); 'fp32': exact SIMT twin."""
-    assert mode in ("tf32", "fp32"), mode
-    call("rat_set_precision", 1 if mode == "tf32" else 0)
+    """'bf16': tcgen05 projections (bf16 operands, fp32 accumulate in TMEM); 'tf32': mma.sync TF32 projections;
+    'fp32': exact SIMT twin (parity anchor)."""
+    assert mode in _PREC, mode
+    call("rat_set_precision", _PREC[mode])
 
 
 def get_precision() -> str:
-    return "tf32" if query("rat_get_precision") else "fp32"
+    return {v: k for k, v in _PREC.items()}[int(query("rat_get_precision"))]
 
 
 def _align4(n):
