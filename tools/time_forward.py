@@ -10,6 +10,9 @@ import rat_native as rn
 shape = sys.argv[1] if len(sys.argv) > 1 else "kkbox"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 K = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+prec = sys.argv[4] if len(sys.argv) > 4 else "tf32"
+from rat_native.engine import set_precision
+set_precision(prec)
 spec = O.shape_spec(shape)
 params = O.init_params(spec, 0)
 eng = make_engine(spec, params, O.init_buffers(spec))
@@ -30,7 +33,7 @@ def timeit(fn, n=10):
     return e0.elapsed_time(e1) / n
 
 t_all = timeit(lambda: eng.forward_ids(ws, B, T, False))
-print(f"{shape} B={B} K={K}: forward {t_all:.3f} ms  -> {B / t_all * 1e3:,.0f} samples/s")
+print(f"{shape} B={B} K={K} precision={prec}: forward {t_all:.3f} ms  -> {B / t_all * 1e3:,.0f} samples/s")
 s = spec; N = s.num_fields + 1; D = s.embedding_dim
 a = ws["acts"]
 pre = "encoder.encoder.0."

@@ -230,6 +230,10 @@ int ff_fwd_tc_dispatch(const float* x, const float* res, float* out, const float
                        const float* W1, const float* b1, const float* W2, const float* b2, long long rows, int D, int M,
                        cudaStream_t st);
 
+int attn_fwd_tc_dispatch(const float* x, const float* res, float* out, const float* ln_w, const float* ln_b,
+                         const float* Wq, const float* Wk, const float* Wv, const float* Wo, const float* bo, int B, int T,
+                         int N, int D, int heads, int dh, float scale, float alpha, int mode, cudaStream_t st);
+
 extern "C" int rat_set_precision(int mode) {
     RAT_REQUIRE(mode >= 0 && mode <= 2, "rat_set_precision: mode must be 0 (fp32), 1 (tf32) or 2 (bf16 tcgen05)");
     g_precision = mode;
@@ -264,6 +268,11 @@ extern "C" int rat_attn_fwd(const float* x, const float* res, float* out, const 
     RAT_REQUIRE(B > 0 && T > 0 && N > 0 && D > 0 && heads > 0, "rat_attn_fwd: bad shape");
     RAT_REQUIRE(mode == 0 || mode == 1, "rat_attn_fwd: mode must be 0 (intra) or 1 (cross)");
     RAT_REQUIRE(Wo != nullptr && bo != nullptr, "rat_attn_fwd: identity out-projection (heads==1 && dim_head==dim) is not supported");
+    if (g_precision == 2) {
+        const int rc2 = attn_fwd_tc_dispatch(x, res, out, ln_w, ln_b, Wq, Wk, Wv, Wo, bo, B, T, N, D, heads, dim_head, scale,
+                                             alpha, mode, (cudaStream_t)stream);
+        if (rc2 <= 0) return rc2;
+    }
     AttnArgs a{};
     a.x = x; a.res = res; a.out = out; a.ln_w = ln_w; a.ln_b = ln_b; a.Wq = Wq; a.Wk = Wk; a.Wv = Wv; a.Wo = Wo; a.bo = bo;
     a.g.S = mode == 0 ? N : T; a.g.mode = mode; a.g.T = T; a.g.N = N;

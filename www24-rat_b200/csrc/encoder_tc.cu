@@ -263,6 +263,320 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_ff_fwd_tc(FFTcArgs a) {
     if (threadIdx.x < 32) tc5::tmem_dealloc(tmem_base_s, 256);
 }
 
+// ------------------------------------------------------------------------------------------------ Attention
+// out = res + alpha * ( MHA(LayerNorm(x)) Wo^T + bo )    (PreNorm RAT_m2.py:155-161, Attention :176-202, residual :224/:231)
+//
+// Per 128-row tile (whole sequences: SPT = 128 / S of them) and per chunk of hc heads:
+//   GEMM  q|k|v[128 x 3*hc*DHP] = LN(x)[128 x Kp] . Wqkv_chunk^T     tcgen05, head width zero-padded to DHP = pad16(dh),
+//                                                                    softmax scale * log2(e) folded into the Wq rows
+//   TMEM -> bf16 q|k|v tile in shared memory (canonical core-matrix layout: also what ldmatrix wants)
+//   softmax(q k^T) v per (sequence, head) on ONE WARP: ldmatrix + mma.sync.m16n8k16 bf16 (two sequences of S <= 8
+//     share the m16 tile, off-diagonal blocks masked), fp32 scores / exp2 / sums, P rounded to bf16 for P.V
+//   GEMM  y[128 x Np] (+)= o_chunk[128 x Cp] . Wo_chunk^T            tcgen05, accumulated over head chunks in TMEM
+// epilogue: out = res + alpha * (y + bo), fp32.
+struct AttnTcArgs {
+    const float* x; const float* res; float* out;
+    const float* ln_w; const float* ln_b;
+    const float* Wq; const float* Wk; const float* Wv; const float* Wo; const float* bo;
+    long long nseq;
+    SeqGeom g;
+    int D, H, I;
+    float qscale, alpha;     // qscale = softmax scale * log2(e)
+    int Kp;                  // pad16(D)
+    int Np;                  // pad16(D): N of the out-projection
+    int hc, nchunks;         // heads per chunk
+    int NCq;                 // 3 * hc * DHP: N of the q|k|v GEMM
+    int Cp;                  // pad16(hc * dh): K of the out-projection per chunk
+    int SPT;                 // sequences per tile
+    int smem_bytes;
+};
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void mma_bf16_16x8x16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float qmax(float v) {
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float qsum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+// fragment row i (0..15) of a warp task -> tile row, or -1
+struct TcTask {
+    int S, nseq, seq0;
+    bool packed;
+    __device__ __forceinline__ int row(int i) const {
+        const int seq = packed ? seq0 + (i >> 3) : seq0;
+        const int pos = packed ? (i & 7) : i;
+        return (pos < S && seq < nseq) ? seq * S + pos : -1;
+    }
+    __device__ __forceinline__ bool pair_ok(int i, int j) const { return !packed || ((i >> 3) == (j >> 3)); }
+};
+
+template <int DH>
+__device__ __forceinline__ void attn_core_bf16(const unsigned char* __restrict__ QKVt, int KCq, int hc,
+                                               unsigned char* __restrict__ Ot, int KCo, int nseq_t, int S, int warp2,
+                                               int lane) {
+    constexpr int DHP = (DH + 15) / 16 * 16, KS = DHP / 16, ND = (DH + 7) / 8;
+    const int g = lane >> 2, t = lane & 3;
+    const bool packed = S <= 8;
+    const int ntasks = (packed ? (nseq_t + 1) / 2 : nseq_t) * hc;
+    const uint32_t qkv_s = tc5::smem_u32(QKVt);
+    for (int task = warp2; task < ntasks; task += TEAM_THREADS / 32) {
+        const int sp = task / hc, hl = task - sp * hc;
+        const TcTask tm{S, nseq_t, packed ? 2 * sp : sp, packed};
+        const int r_first = tm.row(0);
+        // ldmatrix row addresses of this lane
+        int rq = tm.row((lane & 7) + ((lane >> 3) & 1) * 8);     // Q: matrices (rows 0-7|8-15) x (k chunk 0|1)
+        int rk = tm.row((lane & 7) + (lane >> 4) * 8);           // K: matrices (keys 0-7, k0|k1), (keys 8-15, k0|k1)
+        if (rq < 0) rq = r_first;
+        if (rk < 0) rk = r_first;
+        const int cq0 = (hl * DHP) >> 3, ck0 = ((hc + hl) * DHP) >> 3, cv0 = ((2 * hc + hl) * DHP) >> 3;
+        float sc[2][4] = {};
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            uint32_t a[4], b[4];
+            ldsm_x4(a, qkv_s + tc5::kmajor_off(rq, cq0 + 2 * ks + (lane >> 4), KCq));
+            ldsm_x4(b, qkv_s + tc5::kmajor_off(rk, ck0 + 2 * ks + ((lane >> 3) & 1), KCq));
+            mma_bf16_16x8x16(sc[0], a, b[0], b[1]);
+            mma_bf16_16x8x16(sc[1], a, b[2], b[3]);
+        }
+        const int rlo = tm.row(g), rhi = tm.row(g + 8);
+        float mlo = -INFINITY, mhi = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int i = (e < 2) ? g : g + 8, j = 8 * nt + 2 * t + (e & 1);
+                const bool ok = tm.row(j) >= 0 && tm.pair_ok(i, j);
+                sc[nt][e] = ok ? sc[nt][e] : -INFINITY;
+                if (e < 2) mlo = fmaxf(mlo, sc[nt][e]); else mhi = fmaxf(mhi, sc[nt][e]);
+            }
+        mlo = qmax(mlo); mhi = qmax(mhi);
+        if (rlo < 0) mlo = 0.f;
+        if (rhi < 0) mhi = 0.f;
+        float llo = 0.f, lhi = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                sc[nt][e] = ex2f(sc[nt][e] - ((e < 2) ? mlo : mhi));
+                if (e < 2) llo += sc[nt][e]; else lhi += sc[nt][e];
+            }
+        llo = qsum(llo); lhi = qsum(lhi);
+        uint32_t pa[4];
+        pa[0] = pack_bf16(sc[0][0], sc[0][1]); pa[1] = pack_bf16(sc[0][2], sc[0][3]);
+        pa[2] = pack_bf16(sc[1][0], sc[1][1]); pa[3] = pack_bf16(sc[1][2], sc[1][3]);
+        int rv = tm.row((lane & 7) + ((lane >> 3) & 1) * 8);     // V (transposed): matrices (keys 0-7|8-15) x (d chunk)
+        if (rv < 0) rv = r_first;
+        float o[2 * KS][4] = {};
+#pragma unroll
+        for (int pp = 0; pp < KS; ++pp) {
+            uint32_t vb[4];
+            ldsm_x4_t(vb, qkv_s + tc5::kmajor_off(rv, cv0 + 2 * pp + (lane >> 4), KCq));
+            mma_bf16_16x8x16(o[2 * pp], pa, vb[0], vb[1]);
+            if (2 * pp + 1 < ND) mma_bf16_16x8x16(o[2 * pp + 1], pa, vb[2], vb[3]);
+        }
+        const float ilo = rlo >= 0 ? 1.0f / llo : 0.f, ihi = rhi >= 0 ? 1.0f / lhi : 0.f;
+#pragma unroll
+        for (int nd = 0; nd < ND; ++nd) {
+            const int d = 8 * nd + 2 * t;
+            if (d < DH) {                                           // DH even: the (d, d+1) pair is valid as a whole
+                const int col = hl * DH + d;
+                if (rlo >= 0)
+                    *reinterpret_cast<uint32_t*>(Ot + tc5::kmajor_off(rlo, col >> 3, KCo) + (col & 7) * 2) =
+                        pack_bf16(o[nd][0] * ilo, o[nd][1] * ilo);
+                if (rhi >= 0)
+                    *reinterpret_cast<uint32_t*>(Ot + tc5::kmajor_off(rhi, col >> 3, KCo) + (col & 7) * 2) =
+                        pack_bf16(o[nd][2] * ihi, o[nd][3] * ihi);
+            }
+        }
+    }
+}
+
+template <int DH, int KCH, bool VEC4>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_attn_fwd_tc(AttnTcArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int DHP = (DH + 15) / 16 * 16;
+    const int D = a.D, Kp = a.Kp, Np = a.Np, hc = a.hc, NCq = a.NCq, Cp = a.Cp, S = a.g.S;
+    const int KC1 = Kp >> 3, KCq = NCq >> 3, KCo = Cp >> 3;
+    unsigned char* Wqkv_i = smem_raw;                                        // [nchunks*NCq x Kp] bf16
+    unsigned char* Wo_i = Wqkv_i + (size_t)a.nchunks * NCq * Kp * 2;         // [nchunks][Np x Cp] bf16
+    float* bos = reinterpret_cast<float*>(Wo_i + (size_t)a.nchunks * Np * Cp * 2);   // [Np]
+    unsigned char* team_base = reinterpret_cast<unsigned char*>(bos + Np);
+    const size_t team_bytes = (size_t)TILE_M * (Kp + NCq + Cp) * 2;
+    __shared__ __align__(8) uint64_t mbar[2];
+    __shared__ uint32_t tmem_base_s;
+
+    const int team = threadIdx.x / TEAM_THREADS, tid2 = threadIdx.x % TEAM_THREADS;
+    const int warp2 = tid2 >> 5, lane = tid2 & 31;
+    unsigned char* At = team_base + team * team_bytes;                       // [128 x Kp]
+    unsigned char* QKVt = At + (size_t)TILE_M * Kp * 2;                      // [128 x NCq]
+    unsigned char* Ot = QKVt + (size_t)TILE_M * NCq * 2;                     // [128 x Cp]
+
+    // ---- resident weight images
+    {
+        const int rows_img = a.nchunks * NCq, total = rows_img * KC1;
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            const int n = i % rows_img, kc = i / rows_img;
+            const int ch = n / NCq, rem = n - ch * NCq;
+            const int w = rem / (hc * DHP), rem2 = rem - w * (hc * DHP);
+            const int hl = rem2 / DHP, d = rem2 - hl * DHP;
+            const float* W = w == 0 ? a.Wq : w == 1 ? a.Wk : a.Wv;
+            const float mul = w == 0 ? a.qscale : 1.0f;
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int c = kc * 8 + k;
+                v[k] = (d < DH && c < D) ? mul * __ldg(W + (size_t)((ch * hc + hl) * DH + d) * D + c) : 0.f;
+            }
+            sts128(Wqkv_i + tc5::kmajor_off(n, kc, KC1), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
+                   pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        }
+        const int per = Np * KCo;
+        for (int i = threadIdx.x; i < a.nchunks * per; i += blockDim.x) {
+            const int ch = i / per, rem = i - ch * per;
+            const int n = rem % Np, kc = rem / Np;
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int c = kc * 8 + k;
+                v[k] = (n < D && c < hc * DH) ? __ldg(a.Wo + (size_t)n * a.I + ch * hc * DH + c) : 0.f;
+            }
+            sts128(Wo_i + (size_t)ch * Np * Cp * 2 + tc5::kmajor_off(n, kc, KCo), pack_bf16(v[0], v[1]),
+                   pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        }
+        for (int i = threadIdx.x; i < Np; i += blockDim.x) bos[i] = i < D ? a.bo[i] : 0.f;
+        // o tiles: pad columns [hc*dh, Cp) are never written by the attention core and must read as zero
+        for (int i = threadIdx.x; i < (int)(2 * team_bytes / 16); i += blockDim.x)
+            reinterpret_cast<uint4*>(team_base)[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (threadIdx.x == 0) { tc5::mbar_init(&mbar[0], 1); tc5::mbar_init(&mbar[1], 1); tc5::fence_mbar_init(); }
+    if (threadIdx.x < 32) tc5::tmem_alloc(&tmem_base_s, 512);
+    tc5::fence_proxy_async();
+    tc5::fence_before_sync();
+    __syncthreads();
+    tc5::fence_after_sync();
+    const uint32_t tmem_Q = tmem_base_s + team * 256;                // columns [0, NCq)
+    const uint32_t tmem_Y = tmem_Q + NCq;                            // columns [NCq, NCq + Np)
+    const uint32_t idesc_q = tc5::instr_desc(tc5::FMT_BF16, TILE_M, NCq);
+    const uint32_t idesc_o = tc5::instr_desc(tc5::FMT_BF16, TILE_M, Np);
+    const uint32_t lane_base = (uint32_t)((warp2 & 3) * 32) << 16;
+    const int chalf = warp2 >> 2;
+    const int row_e = (warp2 & 3) * 32 + lane;
+    uint32_t phase = 0;
+    uint64_t* bar = &mbar[team];
+    const uint32_t At_s = tc5::smem_u32(At), Ot_s = tc5::smem_u32(Ot), Wq_s = tc5::smem_u32(Wqkv_i), Wo_s = tc5::smem_u32(Wo_i);
+
+    const long long ntiles = (a.nseq + a.SPT - 1) / a.SPT;
+    for (long long tile = (long long)blockIdx.x * 2 + team; tile < ntiles; tile += (long long)gridDim.x * 2) {
+        const long long s0 = tile * a.SPT;
+        const int nseq_t = (int)min((long long)a.SPT, a.nseq - s0);
+        const int R = nseq_t * S;
+        // ---- phase 1: LN(x) tile -> bf16 A tile
+        {
+            const int row = tid2 >> 1, h = tid2 & 1;
+            const bool valid = row < R;
+            const int ls = row / S, pos = row - ls * S;
+            const long long gr = valid ? a.g.grow(s0 + ls, pos) : 0;
+            stage_row_bf16<KCH, VEC4>(a.x + gr * D, valid, D, KC1, row, h, a.ln_w, a.ln_b, At);
+        }
+        tc5::fence_proxy_async();
+        tc5::fence_before_sync();
+        team_sync(team);
+        if (tid2 == 0) {
+            tc5::fence_after_sync();
+            for (int k = 0; k < Kp / 16; ++k)
+                tc5::mma_f16(tmem_Q, tc5::smem_desc(At_s + k * 256, 128, KC1 * 128),
+                             tc5::smem_desc(Wq_s + k * 256, 128, KC1 * 128), idesc_q, k > 0);
+            tc5::mma_commit(bar);
+        }
+        for (int ch = 0; ch < a.nchunks; ++ch) {
+            tc5::mbar_wait(bar, phase);
+            phase ^= 1;
+            tc5::fence_after_sync();
+            // ---- epilogue 1: q|k|v accumulator -> bf16 tile
+            {
+                const int ng = NCq >> 4, g0 = chalf * (ng >> 1), g1 = chalf ? ng : (ng >> 1);
+                for (int gq = g0; gq < g1; ++gq) {
+                    float v[16];
+                    tc5::tmem_ld16(tmem_Q + lane_base + gq * 16, v);
+                    tc5::tmem_ld_wait();
+                    sts128(QKVt + tc5::kmajor_off(row_e, 2 * gq, KCq), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
+                           pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                    sts128(QKVt + tc5::kmajor_off(row_e, 2 * gq + 1, KCq), pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]),
+                           pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+                }
+            }
+            tc5::fence_before_sync();
+            team_sync(team);
+            // ---- softmax(q k^T) v per (sequence, head) -> bf16 o tile
+            attn_core_bf16<DH>(QKVt, KCq, hc, Ot, KCo, nseq_t, S, warp2, lane);
+            tc5::fence_proxy_async();
+            team_sync(team);
+            if (tid2 == 0) {
+                tc5::fence_after_sync();
+                const uint32_t wo = Wo_s + (uint32_t)ch * Np * Cp * 2;
+                for (int k = 0; k < Cp / 16; ++k)
+                    tc5::mma_f16(tmem_Y, tc5::smem_desc(Ot_s + k * 256, 128, KCo * 128),
+                                 tc5::smem_desc(wo + k * 256, 128, KCo * 128), idesc_o, (ch > 0 || k > 0) ? 1u : 0u);
+                if (ch + 1 < a.nchunks) {
+                    const uint32_t wq = Wq_s + (uint32_t)(ch + 1) * NCq * Kp * 2;
+                    for (int k = 0; k < Kp / 16; ++k)
+                        tc5::mma_f16(tmem_Q, tc5::smem_desc(At_s + k * 256, 128, KC1 * 128),
+                                     tc5::smem_desc(wq + k * 256, 128, KC1 * 128), idesc_q, k > 0);
+                }
+                tc5::mma_commit(bar);
+            }
+        }
+        tc5::mbar_wait(bar, phase);
+        phase ^= 1;
+        tc5::fence_after_sync();
+        // ---- epilogue 2: out = res + alpha * (y + bo)
+        {
+            const int ls = row_e / S, pos = row_e - ls * S;
+            const bool valid = row_e < R;
+            const long long gr = valid ? a.g.grow(s0 + ls, pos) : 0;
+            const int ng = Np >> 3, g0 = chalf * (ng >> 1), g1 = chalf ? ng : (ng >> 1);
+            for (int gq = g0; gq < g1; ++gq) {
+                if (gq * 8 >= D) break;
+                float v[8], rv[8];
+                tc5::tmem_ld8(tmem_Y + lane_base + gq * 8, v);
+                if (valid && a.res) load8<VEC4>(a.res + gr * D, gq * 8, D, rv);
+                tc5::tmem_ld_wait();
+                if (valid) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        v[k] = a.alpha * (v[k] + bos[gq * 8 + k]);
+                        if (a.res) v[k] += rv[k];
+                    }
+                    store8<VEC4>(a.out + gr * D, gq * 8, D, v);
+                }
+            }
+        }
+        tc5::fence_before_sync();
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) tc5::tmem_dealloc(tmem_base_s, 512);
+}
+
 static bool ff_tc_supported(int D, int M) {
     if (D < 2 || (D & 1) || D > 64 || M < 1) return false;
     const int Kp = pad16(D), Mp = pad16(M);
@@ -313,4 +627,71 @@ int ff_fwd_tc_dispatch(const float* x, const float* res, float* out, const float
         default: return 1;
     }
 #undef RAT_FF_TC
+}
+
+template <int DH, int KCH, bool VEC4>
+static int launch_attn_fwd_tc(const AttnTcArgs& a, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_attn_fwd_tc<DH, KCH, VEC4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             max_smem_optin() - 1024);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_attn_fwd_tc)");
+        attr_set = true;
+    }
+    const long long ntiles = (a.nseq + a.SPT - 1) / a.SPT;
+    const int grid = (int)std::min<long long>((ntiles + 1) / 2, (long long)num_sms());
+    k_attn_fwd_tc<DH, KCH, VEC4><<<grid, TC_THREADS, a.smem_bytes, st>>>(a);
+    RAT_CHECK_LAUNCH("k_attn_fwd_tc");
+    return RAT_OK;
+}
+
+template <int DH>
+static int launch_attn_fwd_tc_dh(const AttnTcArgs& a, cudaStream_t st) {
+    const int kch = a.Kp / 16;
+    const bool v4 = (a.D % 4) == 0;
+#define RAT_ATTN_TC(K_) (v4 ? launch_attn_fwd_tc<DH, K_, true>(a, st) : launch_attn_fwd_tc<DH, K_, false>(a, st))
+    switch (kch) {
+        case 1: return RAT_ATTN_TC(1);
+        case 2: return RAT_ATTN_TC(2);
+        case 3: return RAT_ATTN_TC(3);
+        case 4: return RAT_ATTN_TC(4);
+        default: return 1;
+    }
+#undef RAT_ATTN_TC
+}
+
+// returns RAT_OK if launched, 1 if the shape is not covered (caller falls back), <0 on error
+int attn_fwd_tc_dispatch(const float* x, const float* res, float* out, const float* ln_w, const float* ln_b,
+                         const float* Wq, const float* Wk, const float* Wv, const float* Wo, const float* bo, int B, int T,
+                         int N, int D, int heads, int dh, float scale, float alpha, int mode, cudaStream_t st) {
+    const int S = mode == 0 ? N : T;
+    if (S > 16 || S < 1 || (dh != 10 && dh != 20 && dh != 8 && dh != 16) || D < 2 || (D & 1) || D > 64) return 1;
+    const int DHP = pad16(dh);
+    AttnTcArgs a{};
+    a.x = x; a.res = res; a.out = out; a.ln_w = ln_w; a.ln_b = ln_b; a.Wq = Wq; a.Wk = Wk; a.Wv = Wv; a.Wo = Wo; a.bo = bo;
+    a.g.S = S; a.g.mode = mode; a.g.T = T; a.g.N = N;
+    a.nseq = mode == 0 ? (long long)B * T : (long long)B * N;
+    a.D = D; a.H = heads; a.I = heads * dh; a.qscale = scale * 1.4426950408889634f; a.alpha = alpha;
+    a.Kp = pad16(D); a.Np = pad16(D);
+    int hc = 0;
+    for (int c = heads; c >= 1; --c) {
+        if (heads % c) continue;
+        const int ncq = 3 * c * DHP;
+        if (ncq <= 256 && ncq + a.Np <= 256 && ((ncq >> 4) % 2 == 0)) { hc = c; break; }
+    }
+    if (!hc) return 1;
+    a.hc = hc; a.nchunks = heads / hc; a.NCq = 3 * hc * DHP; a.Cp = pad16(hc * dh);
+    a.SPT = TILE_M / S;
+    if (S <= 8) a.SPT &= ~1;                    // sequences are processed in pairs
+    const size_t fixed = (size_t)a.nchunks * a.NCq * a.Kp * 2 + (size_t)a.nchunks * a.Np * a.Cp * 2 + (size_t)a.Np * 4;
+    const size_t team = (size_t)TILE_M * (a.Kp + a.NCq + a.Cp) * 2;
+    a.smem_bytes = (int)(fixed + 2 * team);
+    if (a.smem_bytes > max_smem_optin() - 1024) return 1;
+    switch (dh) {
+        case 8: return launch_attn_fwd_tc_dh<8>(a, st);
+        case 10: return launch_attn_fwd_tc_dh<10>(a, st);
+        case 16: return launch_attn_fwd_tc_dh<16>(a, st);
+        case 20: return launch_attn_fwd_tc_dh<20>(a, st);
+        default: return 1;
+    }
 }
