@@ -13,6 +13,7 @@
 // (reduction over token rows) accumulate into a CTA-private record in global memory (L2 resident, every element
 // owned by one thread, static tile->CTA map), and k_reduce_* sums the records over CTAs in fixed order
 // => bitwise run-to-run deterministic.
+#include <algorithm>
 #include "tile.cuh"
 #include "encoder_common.cuh"
 #include "attn_mma.cuh"
@@ -526,6 +527,11 @@ static int bwd_grid(long long ntiles) { return (int)min(ntiles, (long long)num_s
 
 using namespace rat;
 
+size_t ff_bwd_tc_workspace_bytes(long long rows, int D, int M);
+int ff_bwd_tc_dispatch(const float* x, const float* dout, const float* base, float* dx, const float* ln_w,
+                       const float* W1, const float* b1, const float* W2, float* dW1, float* db1, float* dW2, float* db2,
+                       long long rows, int D, int M, float* workspace, size_t workspace_bytes, cudaStream_t st);
+
 extern "C" size_t rat_attn_bwd_workspace_bytes(int B, int T, int N, int D, int heads, int dim_head, int mode) {
     AttnPlan p{};
     const int S = mode == 0 ? N : T;
@@ -594,7 +600,7 @@ extern "C" size_t rat_ff_bwd_workspace_bytes(long long rows, int D, int M) {
     FFPlan p{};
     if (plan_ff_bwd(D, M, &p) != RAT_OK) return 0;
     const long long ntiles = (rows + p.RPT - 1) / p.RPT;
-    return (size_t)bwd_grid(ntiles) * p.psize * sizeof(float);
+    return std::max((size_t)bwd_grid(ntiles) * p.psize * sizeof(float), ff_bwd_tc_workspace_bytes(rows, D, M));
 }
 
 template <bool MMA>
@@ -616,6 +622,11 @@ extern "C" int rat_ff_bwd(const float* x, const float* dout, const float* base, 
                           float* workspace, size_t workspace_bytes, void* stream) {
     RAT_REQUIRE(rows > 0 && D > 0 && M > 0, "rat_ff_bwd: bad shape");
     RAT_REQUIRE(D <= 128 && pad8(M) <= ENC_THREADS, "rat_ff_bwd: D=%d (<=128) M=%d (<=%d) not supported", D, M, ENC_THREADS);
+    if (precision_mode() == 2) {
+        const int rc2 = ff_bwd_tc_dispatch(x, dout, base, dx, ln_w, W1, b1, W2, dW1, db1, dW2, db2, rows, D, M, workspace,
+                                           workspace_bytes, (cudaStream_t)stream);
+        if (rc2 <= 0) return rc2;
+    }
     FFBwdArgs a{};
     a.x = x; a.dout = dout; a.base = base; a.dx = dx; a.ln_w = ln_w; a.ln_b = ln_b; a.W1 = W1; a.b1 = b1; a.W2 = W2;
     a.rows = rows; a.D = D; a.M = M;
