@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--pool-rows", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=512)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"],
+                    help="RAT-block projection arithmetic: bf16 = tcgen05 (default), tf32 = mma.sync, fp32 = SIMT")
     return ap.parse_args()
 
 
@@ -155,6 +157,8 @@ def run_ours(a):
     from fuxictr.pytorch.data_generator import DeviceDataGenerator
     from fuxictr.pytorch.torch_utils import seed_everything
     rn.require_device()
+    from rat_native.engine import set_precision
+    set_precision(a.precision)
     seed_everything(2021)
     B, K, S = a.batch, a.topk, a.shape
     cfg = shapes.SHAPES[S]
@@ -255,8 +259,10 @@ def run_ours(a):
     line = {
         "metric": "RAT_m2 train samples/sec", "value": round(a.steps * gB / t_train, 1), "unit": "samples/s",
         "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(t_train / a.steps * 1e3, 4),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"bf16": "bf16", "tf32": "tf32", "fp32": "f32"}[a.precision], "data": "synthetic",
         "config": {"workload": f"RAT_m2 {cfg['dataset_id']} shape, K={K}, B={B}/GPU, train step (fwd+bwd+clip+Adam)",
+                   "precision": a.precision,
                    "global_batch": gB, "topK": K, "fields": F, "input_length": L, "embedding_dim": D, "heads": H,
                    "params": n_params, "pool_rows": a.pool_rows, "parallelism": f"dp{world}",
                    "l2": "every step uses a new batch; per-step working set (~660 MB activations) exceeds the 126 MB L2"},

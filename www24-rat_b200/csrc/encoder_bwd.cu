@@ -528,6 +528,12 @@ static int bwd_grid(long long ntiles) { return (int)min(ntiles, (long long)num_s
 using namespace rat;
 
 size_t ff_bwd_tc_workspace_bytes(long long rows, int D, int M);
+size_t attn_bwd_tc_workspace_bytes(int B, int T, int N, int D, int heads, int dh, int mode);
+int attn_bwd_tc_dispatch(const float* x, const float* dout, const float* base, float* dx, const float* ln_w,
+                         const float* ln_b, const float* Wq, const float* Wk, const float* Wv, const float* Wo, float* dWq,
+                         float* dWk, float* dWv, float* dWo, float* dbo, float* dln_w, float* dln_b, int accumulate_wq,
+                         int B, int T, int N, int D, int heads, int dh, float scale, float alpha, int mode,
+                         float* workspace, size_t workspace_bytes, cudaStream_t st);
 int ff_bwd_tc_dispatch(const float* x, const float* dout, const float* base, float* dx, const float* ln_w,
                        const float* W1, const float* b1, const float* W2, float* dW1, float* db1, float* dW2, float* db2,
                        long long rows, int D, int M, float* workspace, size_t workspace_bytes, cudaStream_t st);
@@ -538,7 +544,7 @@ extern "C" size_t rat_attn_bwd_workspace_bytes(int B, int T, int N, int D, int h
     if (plan_attn_bwd(S, D, heads, dim_head, &p) != RAT_OK) return 0;
     const long long nseq = mode == 0 ? (long long)B * T : (long long)B * N;
     const long long ntiles = (nseq + p.SPT - 1) / p.SPT;
-    return (size_t)bwd_grid(ntiles) * p.psize * sizeof(float);
+    return std::max((size_t)bwd_grid(ntiles) * p.psize * sizeof(float), attn_bwd_tc_workspace_bytes(B, T, N, D, heads, dim_head, mode));
 }
 
 template <int DH, bool MMA>
@@ -565,6 +571,12 @@ extern "C" int rat_attn_bwd(const float* x, const float* dout, const float* base
                             float alpha, int mode, float* workspace, size_t workspace_bytes, void* stream) {
     RAT_REQUIRE(B > 0 && T > 0 && N > 0 && D > 0 && heads > 0, "rat_attn_bwd: bad shape");
     RAT_REQUIRE(D <= 128, "rat_attn_bwd: D=%d > 128 not supported", D);
+    if (precision_mode() == 2) {
+        const int rc2 = attn_bwd_tc_dispatch(x, dout, base, dx, ln_w, ln_b, Wq, Wk, Wv, Wo, dWq, dWk, dWv, dWo, dbo, dln_w,
+                                             dln_b, accumulate_wq, B, T, N, D, heads, dim_head, scale, alpha, mode, workspace,
+                                             workspace_bytes, (cudaStream_t)stream);
+        if (rc2 <= 0) return rc2;
+    }
     AttnBwdArgs a{};
     a.x = x; a.dout = dout; a.base = base; a.dx = dx; a.ln_w = ln_w; a.ln_b = ln_b;
     a.Wq = Wq; a.Wk = Wk; a.Wv = Wv; a.Wo = Wo;

@@ -1,0 +1,249 @@
+// Shared device helpers of the tcgen05 RAT-block kernels (encoder_tc_*.cu): bf16 operand staging in the UMMA canonical
+// layout, ldmatrix / mma.sync bf16 fragments, the register-resident weight-gradient jobs, fast exact-erf GELU.
+#pragma once
+#include "tile.cuh"
+#include "encoder_common.cuh"
+#include "tc5.cuh"
+#include "../../include/rat_b200.h"
+#include <cuda_bf16.h>
+#include <algorithm>
+
+namespace rat {
+
+int precision_mode();
+
+constexpr int TC_THREADS = 512;
+constexpr int TEAM_THREADS = 256;
+constexpr int TILE_M = 128;
+
+__device__ __forceinline__ void team_sync(int team) {
+    asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(TEAM_THREADS) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ void sts128(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d);
+}
+
+// W [rows x cols] fp32 row-major (torch Linear layout = N x K, K-major)  ->  bf16 canonical image [rows_p x cols_p]
+// (rows_p % 8 == 0, cols_p % 16 == 0), zero padded.  One 16-byte chunk (8 bf16) per loop iteration.
+__device__ __forceinline__ void stage_weight_image(const float* __restrict__ W, int rows, int cols, int rows_p,
+                                                   int cols_p, unsigned char* __restrict__ dst) {
+    const int KC = cols_p >> 3;
+    const int total = rows_p * KC;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int r = i % rows_p, kc = i / rows_p;
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = kc * 8 + k;
+            v[k] = (r < rows && c < cols) ? __ldg(W + (size_t)r * cols + c) : 0.f;
+        }
+        sts128(dst + tc5::kmajor_off(r, kc, KC), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+               pack_bf16(v[6], v[7]));
+    }
+}
+
+// 8 consecutive floats of a token row, columns [c0, c0+8) clipped to D (zero fill)
+template <bool VEC4>
+__device__ __forceinline__ void load8(const float* __restrict__ row, int c0, int D, float (&v)[8]) {
+    if (VEC4) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c0 + 4 * q < D) t = *reinterpret_cast<const float4*>(row + c0 + 4 * q);
+            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float2 t = make_float2(0.f, 0.f);
+            if (c0 + 2 * q < D) t = *reinterpret_cast<const float2*>(row + c0 + 2 * q);
+            v[2 * q] = t.x; v[2 * q + 1] = t.y;
+        }
+    }
+}
+template <bool VEC4>
+__device__ __forceinline__ void store8(float* __restrict__ row, int c0, int D, const float (&v)[8]) {
+    if (VEC4) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+            if (c0 + 4 * q < D)
+                *reinterpret_cast<float4*>(row + c0 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (c0 + 2 * q < D) *reinterpret_cast<float2*>(row + c0 + 2 * q) = make_float2(v[2 * q], v[2 * q + 1]);
+    }
+}
+
+// Load one token row half (KCH chunks of 8 columns starting at chunk h*KCH), optionally LayerNorm it (the two lanes
+// of a row pair exchange partial sums by shuffle), convert to bf16 and store the chunks into the canonical A tile.
+//   tid2 = thread index inside the team (0..255): row = tid2 / 2, h = tid2 % 2.   valid=false -> zero row.
+template <int KCH, bool VEC4>
+__device__ __forceinline__ void stage_row_bf16(const float* __restrict__ src, bool valid, int D, int KC, int row, int h,
+                                               const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                                               unsigned char* __restrict__ At, int ones_col = -1,
+                                               float* __restrict__ stats = nullptr, float mul = 1.0f) {
+    float v[KCH][8];
+#pragma unroll
+    for (int j = 0; j < KCH; ++j) {
+        if (valid) load8<VEC4>(src, (h * KCH + j) * 8, D, v[j]);
+        else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[j][k] = 0.f;
+        }
+    }
+    if (ln_w != nullptr) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < KCH; ++j)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s += v[j][k];                    // pad columns hold zeros
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        const float mean = s / (float)D;
+        float sq = 0.f;
+#pragma unroll
+        for (int j = 0; j < KCH; ++j)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int c = (h * KCH + j) * 8 + k;
+                const float t = c < D ? v[j][k] - mean : 0.f;
+                sq = fmaf(t, t, sq);
+            }
+        sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+        const float rstd = 1.0f / sqrtf(sq / (float)D + 1e-5f);
+        if (stats != nullptr && h == 0) { stats[2 * row] = mean; stats[2 * row + 1] = rstd; }
+#pragma unroll
+        for (int j = 0; j < KCH; ++j)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int c = (h * KCH + j) * 8 + k;
+                v[j][k] = (c < D && valid) ? (v[j][k] - mean) * rstd * __ldg(ln_w + c) + __ldg(ln_b + c) : 0.f;
+            }
+    } else if (mul != 1.0f) {
+#pragma unroll
+        for (int j = 0; j < KCH; ++j)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[j][k] *= mul;
+    }
+    if (ones_col >= 0 && valid) {        // bias-gradient trick: a column of ones turns colsum(g) into a GEMM column
+#pragma unroll
+        for (int j = 0; j < KCH; ++j)
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if ((h * KCH + j) * 8 + k == ones_col) v[j][k] = 1.0f;
+    }
+#pragma unroll
+    for (int j = 0; j < KCH; ++j)
+        sts128(At + tc5::kmajor_off(row, h * KCH + j, KC), pack_bf16(v[j][0], v[j][1]), pack_bf16(v[j][2], v[j][3]),
+               pack_bf16(v[j][4], v[j][5]), pack_bf16(v[j][6], v[j][7]));
+}
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void mma_bf16_16x8x16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float qmax(float v) {
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float qsum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+// fragment row i (0..15) of a warp task -> tile row, or -1
+struct TcTask {
+    int S, nseq, seq0;
+    bool packed;
+    __device__ __forceinline__ int row(int i) const {
+        const int seq = packed ? seq0 + (i >> 3) : seq0;
+        const int pos = packed ? (i & 7) : i;
+        return (pos < S && seq < nseq) ? seq * S + pos : -1;
+    }
+    __device__ __forceinline__ bool pair_ok(int i, int j) const { return !packed || ((i >> 3) == (j >> 3)); }
+};
+
+// ------------------------------------------------------------------------------------------------ FF backward
+// Exact-erf GELU and its derivative from ONE exponential (Abramowitz-Stegun 7.1.26, |erf error| <= 1.5e-7):
+//   e = exp(-z^2/2) ; Phi(|z|) = 1 - 0.5 poly(t) e, t = 1/(1 + p |z|/sqrt2) ; gelu = z Phi(z) ; gelu' = Phi(z) + z e/sqrt(2 pi)
+__device__ __forceinline__ void gelu_fast(float z, float& g, float& dg) {
+    const float az = fabsf(z);
+    const float e = ex2f(-0.72134752044448170368f * z * z);          // exp(-z^2/2)
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.23164189f, az, 1.0f)));   // p/sqrt2 = 0.3275911/1.41421356
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    poly *= t;
+    const float q = 0.5f * poly * e;                                  // 1 - Phi(|z|)
+    const float phi = z >= 0.f ? 1.0f - q : q;
+    g = z * phi;
+    dg = fmaf(z * 0.39894228040143267794f, e, phi);
+}
+
+// C[16 x 16] (+)= sum over the 128 tile rows r of A[r][m0 + 0..15] * B[r][n0 + 0..15]   (A, B: bf16 canonical tiles,
+// rows = tokens).  Weight-gradient product: the token dimension is the reduction index, so both fragments are
+// ldmatrix.trans loads straight from the K-major activation tiles.  acc[0] = columns n0..n0+7, acc[1] = n0+8..n0+15.
+__device__ __forceinline__ void wgrad_job(const unsigned char* __restrict__ At, int KCa, int mchunk, bool a_ones,
+                                          const unsigned char* __restrict__ Bt, int KCb, int nchunk, int lane,
+                                          float (&acc)[2][4]) {
+    const uint32_t a_s = tc5::smem_u32(At), b_s = tc5::smem_u32(Bt);
+    const int ra = (lane & 7) + ((lane >> 4) & 1) * 8, ca = mchunk + ((lane >> 3) & 1);
+    const int rb = (lane & 7) + ((lane >> 3) & 1) * 8, cb = nchunk + (lane >> 4);
+#pragma unroll
+    for (int ks = 0; ks < TILE_M / 16; ++ks) {
+        uint32_t af[4], bf[4];
+        if (a_ones) af[0] = af[1] = af[2] = af[3] = 0x3F803F80u;
+        else ldsm_x4_t(af, a_s + tc5::kmajor_off(16 * ks + ra, ca, KCa));
+        ldsm_x4_t(bf, b_s + tc5::kmajor_off(16 * ks + rb, cb, KCb));
+        mma_bf16_16x8x16(acc[0], af, bf[0], bf[1]);
+        mma_bf16_16x8x16(acc[1], af, bf[2], bf[3]);
+    }
+}
+// store a job's accumulators into rec[(m0 + row) * ld + n0 + col] (fp32, row-major)
+__device__ __forceinline__ void wgrad_store(float* __restrict__ rec, int ld, int m0, int n0, int lane,
+                                            const float (&acc)[2][4], bool first_row_only) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+        const int col = n0 + 8 * nt + 2 * t;
+        if (!first_row_only || g == 0) {
+            rec[(size_t)(m0 + g) * ld + col] = acc[nt][0];
+            rec[(size_t)(m0 + g) * ld + col + 1] = acc[nt][1];
+        }
+        if (!first_row_only) {
+            rec[(size_t)(m0 + g + 8) * ld + col] = acc[nt][2];
+            rec[(size_t)(m0 + g + 8) * ld + col + 1] = acc[nt][3];
+        }
+    }
+}
+
+
+static inline bool ff_tc_supported(int D, int M) {
+    if (D < 2 || (D & 1) || D > 64 || M < 1) return false;
+    const int Kp = pad16(D), Mp = pad16(M);
+    if (Mp + Kp > 128 || Mp > 256) return false;                     // TMEM columns per team
+    return true;
+}
+
+}  // namespace rat

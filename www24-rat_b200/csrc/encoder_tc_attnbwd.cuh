@@ -1,0 +1,497 @@
+// K5 (Blackwell path): attention backward kernel + host planning (included once per head width, see encoder_tc_attnbwd_dh*.cu).
+#pragma once
+#include "encoder_tc.cuh"
+
+namespace rat {
+
+// ------------------------------------------------------------------------------------------------ Attention backward
+// Backward of  out = res + alpha * ( MHA(LayerNorm(x)) Wo^T + bo ):  dx = base + dLN(...), and all parameter gradients.
+// One team of 16 warps per CTA (the weight-gradient accumulators of all heads live in registers, 5-6 16x16 tiles per
+// warp).  Per 128-row tile and per chunk of hc heads:
+//   tcgen05: q|k|v = LN(x) Wqkv^T (recompute, padded heads)  and  dO = (alpha dout) Wo_chunk (padded heads)  -> TMEM
+//   TMEM -> bf16 tiles ; one warp per (sequence, head): recompute P, O ; dP = dO V^T ; dS = P o (dP - rowsum(P o dP)) ;
+//     dQ = scale dS K ; dK = dS^T Q ; dV = P^T dO  (mma.sync bf16, fragment transposes by movmatrix) -> COMPACT bf16
+//     dq|dk|dv tile (hc*dh columns per part, no head padding) and compact O tile
+//   tcgen05: dA[128 x Kp] += dqkv_c . Wqkv_c  (accumulated over chunks in TMEM)
+//   mma.sync weight-gradient jobs (token reduction): gWqkv_c += dqkv_c^T LN(x) ; gWo_c^T += O_c^T (alpha dout)
+// tile end: LayerNorm backward from dA (fp32), dx written once; dgamma/dbeta/dbo as ones-row jobs on bf16 tiles.
+struct AttnBwdTcArgs {
+    const float* x; const float* dout; const float* base; float* dx;
+    const float* ln_w; const float* ln_b;
+    const float* Wq; const float* Wk; const float* Wv; const float* Wo;
+    float* partials;         // [gridDim.x][psize]
+    long long nseq;
+    SeqGeom g;
+    int D, H, I;
+    float scale, alpha;
+    int Kp, hc, nchunks;
+    int NCq;                 // 3 * hc * DHP   padded q|k|v columns per chunk (N of the recompute GEMM)
+    int NCc;                 // pad16(3 * hc * dh) compact dq|dk|dv columns per chunk (K of the dA GEMM)
+    int NDo;                 // hc * DHP        padded dO columns per chunk
+    int Cc;                  // pad16(hc * dh)  compact O columns per chunk
+    int SPT, njobs, psize, smem_bytes;
+};
+
+__device__ __forceinline__ uint32_t movm_t(uint32_t a) {
+    uint32_t d;
+    asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+    return d;
+}
+
+template <int DH>
+__device__ __forceinline__ void attn_bwd_core_bf16(const unsigned char* __restrict__ QKVt, int KCq,
+                                                   const unsigned char* __restrict__ dOt, int KCd,
+                                                   unsigned char* __restrict__ dQc, int KCc, unsigned char* __restrict__ Ot,
+                                                   int KCo, int hc, int nseq_t, int S, float scale, int warp, int nwarps,
+                                                   int lane) {
+    constexpr int DHP = (DH + 15) / 16 * 16, KS = DHP / 16, ND = (DH + 7) / 8;
+    const int g = lane >> 2, t = lane & 3;
+    const bool packed = S <= 8;
+    const int ntasks = (packed ? (nseq_t + 1) / 2 : nseq_t) * hc;
+    const uint32_t qkv_s = tc5::smem_u32(QKVt), do_s = tc5::smem_u32(dOt);
+    const float inv_log2e = 0.6931471805599453f;
+    for (int task = warp; task < ntasks; task += nwarps) {
+        const int sp = task / hc, hl = task - sp * hc;
+        const TcTask tm{S, nseq_t, packed ? 2 * sp : sp, packed};
+        const int r_first = tm.row(0);
+        int ra = tm.row((lane & 7) + ((lane >> 3) & 1) * 8);     // A-fragment / transposed-B row pattern
+        int rb = tm.row((lane & 7) + (lane >> 4) * 8);           // non-transposed B row pattern
+        if (ra < 0) ra = r_first;
+        if (rb < 0) rb = r_first;
+        const int cq0 = (hl * DHP) >> 3, ck0 = ((hc + hl) * DHP) >> 3, cv0 = ((2 * hc + hl) * DHP) >> 3, cd0 = (hl * DHP) >> 3;
+        // ---- S = Q K^T (log2 domain, scale folded into Q) and dP = dO V^T
+        float sc[2][4] = {}, dp[2][4] = {};
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            uint32_t a[4], b[4];
+            ldsm_x4(a, qkv_s + tc5::kmajor_off(ra, cq0 + 2 * ks + (lane >> 4), KCq));
+            ldsm_x4(b, qkv_s + tc5::kmajor_off(rb, ck0 + 2 * ks + ((lane >> 3) & 1), KCq));
+            mma_bf16_16x8x16(sc[0], a, b[0], b[1]);
+            mma_bf16_16x8x16(sc[1], a, b[2], b[3]);
+            ldsm_x4(a, do_s + tc5::kmajor_off(ra, cd0 + 2 * ks + (lane >> 4), KCd));
+            ldsm_x4(b, qkv_s + tc5::kmajor_off(rb, cv0 + 2 * ks + ((lane >> 3) & 1), KCq));
+            mma_bf16_16x8x16(dp[0], a, b[0], b[1]);
+            mma_bf16_16x8x16(dp[1], a, b[2], b[3]);
+        }
+        const int rlo = tm.row(g), rhi = tm.row(g + 8);
+        float mlo = -INFINITY, mhi = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int i = (e < 2) ? g : g + 8, j = 8 * nt + 2 * t + (e & 1);
+                const bool ok = ((e < 2) ? rlo : rhi) >= 0 && tm.row(j) >= 0 && tm.pair_ok(i, j);
+                sc[nt][e] = ok ? sc[nt][e] : -INFINITY;
+                if (e < 2) mlo = fmaxf(mlo, sc[nt][e]); else mhi = fmaxf(mhi, sc[nt][e]);
+            }
+        mlo = qmax(mlo); mhi = qmax(mhi);
+        if (rlo < 0) mlo = 0.f;
+        if (rhi < 0) mhi = 0.f;
+        float llo = 0.f, lhi = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                sc[nt][e] = ex2f(sc[nt][e] - ((e < 2) ? mlo : mhi));
+                if (e < 2) llo += sc[nt][e]; else lhi += sc[nt][e];
+            }
+        llo = qsum(llo); lhi = qsum(lhi);
+        const float ilo = rlo >= 0 ? 1.0f / llo : 0.f, ihi = rhi >= 0 ? 1.0f / lhi : 0.f;
+        float dlo = 0.f, dhi = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                sc[nt][e] *= (e < 2) ? ilo : ihi;                                    // P
+                if (e < 2) dlo = fmaf(sc[nt][e], dp[nt][e], dlo); else dhi = fmaf(sc[nt][e], dp[nt][e], dhi);
+            }
+        dlo = qsum(dlo); dhi = qsum(dhi);                                            // delta_i = sum_j P_ij dP_ij
+        uint32_t pa[4], sa[4];
+        pa[0] = pack_bf16(sc[0][0], sc[0][1]); pa[1] = pack_bf16(sc[0][2], sc[0][3]);
+        pa[2] = pack_bf16(sc[1][0], sc[1][1]); pa[3] = pack_bf16(sc[1][2], sc[1][3]);
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) dp[nt][e] = sc[nt][e] * (dp[nt][e] - ((e < 2) ? dlo : dhi));   // dS
+        sa[0] = pack_bf16(dp[0][0], dp[0][1]); sa[1] = pack_bf16(dp[0][2], dp[0][3]);
+        sa[2] = pack_bf16(dp[1][0], dp[1][1]); sa[3] = pack_bf16(dp[1][2], dp[1][3]);
+        // transposed A fragments (P^T, dS^T): transpose each 8x8 block and swap the off-diagonal blocks
+        uint32_t pt[4], st[4];
+        pt[0] = movm_t(pa[0]); pt[1] = movm_t(pa[2]); pt[2] = movm_t(pa[1]); pt[3] = movm_t(pa[3]);
+        st[0] = movm_t(sa[0]); st[1] = movm_t(sa[2]); st[2] = movm_t(sa[1]); st[3] = movm_t(sa[3]);
+        // ---- O = P V ; dQ = dS K ; dK = dS^T Q ; dV = P^T dO      (B operands: ldmatrix.trans of [row][d] tiles)
+        float o[2 * KS][4] = {}, dq[2 * KS][4] = {}, dk[2 * KS][4] = {}, dv[2 * KS][4] = {};
+#pragma unroll
+        for (int pp = 0; pp < KS; ++pp) {
+            uint32_t b[4];
+            ldsm_x4_t(b, qkv_s + tc5::kmajor_off(ra, cv0 + 2 * pp + (lane >> 4), KCq));          // V
+            mma_bf16_16x8x16(o[2 * pp], pa, b[0], b[1]);
+            if (2 * pp + 1 < ND) mma_bf16_16x8x16(o[2 * pp + 1], pa, b[2], b[3]);
+            ldsm_x4_t(b, qkv_s + tc5::kmajor_off(ra, ck0 + 2 * pp + (lane >> 4), KCq));          // K
+            mma_bf16_16x8x16(dq[2 * pp], sa, b[0], b[1]);
+            if (2 * pp + 1 < ND) mma_bf16_16x8x16(dq[2 * pp + 1], sa, b[2], b[3]);
+            ldsm_x4_t(b, qkv_s + tc5::kmajor_off(ra, cq0 + 2 * pp + (lane >> 4), KCq));          // Q (scaled)
+            mma_bf16_16x8x16(dk[2 * pp], st, b[0], b[1]);
+            if (2 * pp + 1 < ND) mma_bf16_16x8x16(dk[2 * pp + 1], st, b[2], b[3]);
+            ldsm_x4_t(b, do_s + tc5::kmajor_off(ra, cd0 + 2 * pp + (lane >> 4), KCd));           // dO
+            mma_bf16_16x8x16(dv[2 * pp], pt, b[0], b[1]);
+            if (2 * pp + 1 < ND) mma_bf16_16x8x16(dv[2 * pp + 1], pt, b[2], b[3]);
+        }
+        // ---- compact stores: columns [q: hl*DH + d | k: hc*DH + hl*DH + d | v: 2*hc*DH + hl*DH + d], O: hl*DH + d
+#pragma unroll
+        for (int nd = 0; nd < ND; ++nd) {
+            const int d = 8 * nd + 2 * t;
+            if (d < DH) {
+                const int cq = hl * DH + d, ck = (hc + hl) * DH + d, cv = (2 * hc + hl) * DH + d;
+                if (rlo >= 0) {
+                    *reinterpret_cast<uint32_t*>(dQc + tc5::kmajor_off(rlo, cq >> 3, KCc) + (cq & 7) * 2) = pack_bf16(dq[nd][0] * scale, dq[nd][1] * scale);
+                    *reinterpret_cast<uint32_t*>(dQc + tc5::kmajor_off(rlo, ck >> 3, KCc) + (ck & 7) * 2) = pack_bf16(dk[nd][0] * inv_log2e, dk[nd][1] * inv_log2e);
+                    *reinterpret_cast<uint32_t*>(dQc + tc5::kmajor_off(rlo, cv >> 3, KCc) + (cv & 7) * 2) = pack_bf16(dv[nd][0], dv[nd][1]);
+                    *reinterpret_cast<uint32_t*>(Ot + tc5::kmajor_off(rlo, cq >> 3, KCo) + (cq & 7) * 2) = pack_bf16(o[nd][0], o[nd][1]);
+                }
+                if (rhi >= 0) {
+                    *reinterpret_cast<uint32_t*>(dQc + tc5::kmajor_off(rhi, cq >> 3, KCc) + (cq & 7) * 2) = pack_bf16(dq[nd][2] * scale, dq[nd][3] * scale);
+                    *reinterpret_cast<uint32_t*>(dQc + tc5::kmajor_off(rhi, ck >> 3, KCc) + (ck & 7) * 2) = pack_bf16(dk[nd][2] * inv_log2e, dk[nd][3] * inv_log2e);
+                    *reinterpret_cast<uint32_t*>(dQc + tc5::kmajor_off(rhi, cv >> 3, KCc) + (cv & 7) * 2) = pack_bf16(dv[nd][2], dv[nd][3]);
+                    *reinterpret_cast<uint32_t*>(Ot + tc5::kmajor_off(rhi, cq >> 3, KCo) + (cq & 7) * 2) = pack_bf16(o[nd][2], o[nd][3]);
+                }
+            }
+        }
+    }
+}
+
+template <int DH, int KCH, bool VEC4, int JW>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_attn_bwd_tc(AttnBwdTcArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int DHP = (DH + 15) / 16 * 16;
+    constexpr int NW = TC_THREADS / 32;
+    const int D = a.D, Kp = a.Kp, hc = a.hc, NCq = a.NCq, NCc = a.NCc, NDo = a.NDo, Cc = a.Cc, S = a.g.S;
+    const int KC1 = Kp >> 3, KCq = NCq >> 3, KCc = NCc >> 3, KCd = NDo >> 3, KCo = Cc >> 3;
+    unsigned char* Wqkv_i = smem_raw;                                        // [nchunks*NCq x Kp]  recompute (q rows scaled)
+    unsigned char* WqkvT_i = Wqkv_i + (size_t)a.nchunks * NCq * Kp * 2;      // [nchunks][Kp x NCc] dA GEMM  (n = d, k = compact col)
+    unsigned char* WoT_i = WqkvT_i + (size_t)a.nchunks * Kp * NCc * 2;       // [nchunks][NDo x Kp] dO GEMM  (n = padded c, k = d)
+    float* stats = reinterpret_cast<float*>(WoT_i + (size_t)a.nchunks * NDo * Kp * 2);   // [128][2] mean, rstd
+    float* parts = stats + 2 * TILE_M;                                       // [128][4][2] LayerNorm-backward row partials
+    unsigned char* At = reinterpret_cast<unsigned char*>(parts + 8 * TILE_M);            // [128 x Kp]  LN(x)
+    unsigned char* DYt = At + (size_t)TILE_M * Kp * 2;                       // [128 x Kp]  alpha * dout
+    unsigned char* QKVt = DYt + (size_t)TILE_M * Kp * 2;                     // [128 x NCq] ; after the chunk loop: G1 | G2
+    unsigned char* dQc = QKVt + (size_t)TILE_M * NCq * 2;                    // [128 x NCc] compact dq|dk|dv
+    unsigned char* Ot = dQc + (size_t)TILE_M * NCc * 2;                      // [128 x Cc]  compact O
+    unsigned char* dOt = Ot + (size_t)TILE_M * Cc * 2;                       // [128 x NDo] padded dO
+    unsigned char* G1t = QKVt;                                               // [128 x Kp]  g = dA          (aliases QKVt)
+    unsigned char* G2t = QKVt + (size_t)TILE_M * Kp * 2;                     // [128 x Kp]  g * xhat
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t tmem_base_s;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // ---- resident weight images
+    {
+        const int rows_img = a.nchunks * NCq;
+        for (int i = threadIdx.x; i < rows_img * KC1; i += blockDim.x) {
+            const int n = i % rows_img, kc = i / rows_img;
+            const int ch = n / NCq, rem = n - ch * NCq;
+            const int w = rem / (hc * DHP), rem2 = rem - w * (hc * DHP);
+            const int hl = rem2 / DHP, d = rem2 - hl * DHP;
+            const float* W = w == 0 ? a.Wq : w == 1 ? a.Wk : a.Wv;
+            const float mul = w == 0 ? a.scale * 1.4426950408889634f : 1.0f;
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int c = kc * 8 + k;
+                v[k] = (d < DH && c < D) ? mul * __ldg(W + (size_t)((ch * hc + hl) * DH + d) * D + c) : 0.f;
+            }
+            sts128(Wqkv_i + tc5::kmajor_off(n, kc, KC1), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+                   pack_bf16(v[6], v[7]));
+        }
+        const int perT = Kp * KCc;
+        for (int i = threadIdx.x; i < a.nchunks * perT; i += blockDim.x) {
+            const int ch = i / perT, rem = i - ch * perT;
+            const int d = rem % Kp, kc = rem / Kp;
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int nc = kc * 8 + k;                       // compact column: [q | k | v] x [hl][dd]
+                const int w = nc / (hc * DH), rem2 = nc - w * (hc * DH);
+                const float* W = w == 0 ? a.Wq : w == 1 ? a.Wk : a.Wv;
+                v[k] = (w < 3 && d < D) ? __ldg(W + (size_t)(ch * hc * DH + rem2) * D + d) : 0.f;
+            }
+            sts128(WqkvT_i + (size_t)ch * Kp * NCc * 2 + tc5::kmajor_off(d, kc, KCc), pack_bf16(v[0], v[1]),
+                   pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        }
+        const int perO = NDo * KC1;
+        for (int i = threadIdx.x; i < a.nchunks * perO; i += blockDim.x) {
+            const int ch = i / perO, rem = i - ch * perO;
+            const int n = rem % NDo, kc = rem / NDo;
+            const int hl = n / DHP, dd = n - hl * DHP;
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int d = kc * 8 + k;
+                v[k] = (dd < DH && d < D) ? __ldg(a.Wo + (size_t)d * a.I + (ch * hc + hl) * DH + dd) : 0.f;
+            }
+            sts128(WoT_i + (size_t)ch * NDo * Kp * 2 + tc5::kmajor_off(n, kc, KC1), pack_bf16(v[0], v[1]),
+                   pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        }
+        // activation tiles start as zeros (pad columns of the compact tiles are never written)
+        const size_t tile_bytes = (size_t)TILE_M * (2 * Kp + NCq + NCc + Cc + NDo) * 2;
+        for (int i = threadIdx.x; i < (int)(tile_bytes / 16); i += blockDim.x)
+            reinterpret_cast<uint4*>(At)[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (threadIdx.x == 0) { tc5::mbar_init(&mbar, 1); tc5::fence_mbar_init(); }
+    if (threadIdx.x < 32) tc5::tmem_alloc(&tmem_base_s, 512);
+    tc5::fence_proxy_async();
+    tc5::fence_before_sync();
+    __syncthreads();
+    tc5::fence_after_sync();
+    const uint32_t tmem_Q = tmem_base_s;                             // [0, NCq)
+    const uint32_t tmem_O = tmem_Q + NCq;                            // [NCq, NCq + NDo)
+    const uint32_t tmem_A = tmem_O + NDo;                            // [.., + Kp)
+    const uint32_t idesc_q = tc5::instr_desc(tc5::FMT_BF16, TILE_M, NCq);
+    const uint32_t idesc_o = tc5::instr_desc(tc5::FMT_BF16, TILE_M, NDo);
+    const uint32_t idesc_a = tc5::instr_desc(tc5::FMT_BF16, TILE_M, Kp);
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const int part = warp >> 2;                                      // 0..3: column share of this warp inside its lane quadrant
+    const int row_e = (warp & 3) * 32 + lane;
+    uint32_t phase = 0;
+    const uint32_t At_s = tc5::smem_u32(At), DYt_s = tc5::smem_u32(DYt), dQc_s = tc5::smem_u32(dQc);
+    const uint32_t Wq_s = tc5::smem_u32(Wqkv_i), WqT_s = tc5::smem_u32(WqkvT_i), WoT_s = tc5::smem_u32(WoT_i);
+
+    // weight-gradient jobs (16 x 16 output tiles), job id = warp + 16 j :
+    //   per chunk: [gWqkv: MTq x NP]  A = dqkv_c (m-tile), B = LN(x) (n-pair) ; [gWoT: MTo x NP]  A = O_c, B = alpha*dout
+    //   tile end : NP jobs each for dbo (ones x alpha*dout), dbeta (ones x G1), dgamma (ones x G2)
+    const int MTq = NCc >> 4, MTo = Cc >> 4, NP = KC1 >> 1;
+    const int per_chunk = (MTq + MTo) * NP;
+    const int njobs = a.nchunks * per_chunk + 3 * NP;
+    float acc[JW][2][4];
+#pragma unroll
+    for (int j = 0; j < JW; ++j)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) acc[j][q][0] = acc[j][q][1] = acc[j][q][2] = acc[j][q][3] = 0.f;
+
+    const long long ntiles = (a.nseq + a.SPT - 1) / a.SPT;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long s0 = tile * a.SPT;
+        const int nseq_t = (int)min((long long)a.SPT, a.nseq - s0);
+        const int R = nseq_t * S;
+        // ---- staging: threads 0..255 LN(x) -> At (+ row statistics), threads 256..511 alpha*dout -> DYt
+        {
+            const int tid2 = threadIdx.x & 255;
+            const int row = tid2 >> 1, h = tid2 & 1;
+            const bool valid = row < R;
+            const int ls = row / S, pos = row - ls * S;
+            const long long gr = valid ? a.g.grow(s0 + ls, pos) : 0;
+            if (threadIdx.x < 256) stage_row_bf16<KCH, VEC4>(a.x + gr * D, valid, D, KC1, row, h, a.ln_w, a.ln_b, At, -1, stats);
+            else stage_row_bf16<KCH, VEC4>(a.dout + gr * D, valid, D, KC1, row, h, nullptr, nullptr, DYt, -1, nullptr, a.alpha);
+        }
+        tc5::fence_proxy_async();
+        tc5::fence_before_sync();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tc5::fence_after_sync();
+            for (int k = 0; k < Kp / 16; ++k)
+                tc5::mma_f16(tmem_Q, tc5::smem_desc(At_s + k * 256, 128, KC1 * 128), tc5::smem_desc(Wq_s + k * 256, 128, KC1 * 128),
+                             idesc_q, k > 0);
+            for (int k = 0; k < Kp / 16; ++k)
+                tc5::mma_f16(tmem_O, tc5::smem_desc(DYt_s + k * 256, 128, KC1 * 128), tc5::smem_desc(WoT_s + k * 256, 128, KC1 * 128),
+                             idesc_o, k > 0);
+            tc5::mma_commit(&mbar);
+        }
+        for (int ch = 0; ch < a.nchunks; ++ch) {
+            tc5::mbar_wait(&mbar, phase);
+            phase ^= 1;
+            tc5::fence_after_sync();
+            // ---- epilogue 1: q|k|v and dO accumulators -> bf16 tiles (16-column groups dealt round-robin to the 4 warps of a quadrant)
+            {
+                const int ngq = NCq >> 4, ngo = NDo >> 4;
+                for (int gq = part; gq < ngq + ngo; gq += 4) {
+                    float v[16];
+                    const bool isq = gq < ngq;
+                    const int gg = isq ? gq : gq - ngq;
+                    tc5::tmem_ld16((isq ? tmem_Q : tmem_O) + lane_base + gg * 16, v);
+                    tc5::tmem_ld_wait();
+                    unsigned char* dst = isq ? QKVt : dOt;
+                    const int KCx = isq ? KCq : KCd;
+                    sts128(dst + tc5::kmajor_off(row_e, 2 * gg, KCx), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
+                           pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                    sts128(dst + tc5::kmajor_off(row_e, 2 * gg + 1, KCx), pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]),
+                           pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+                }
+            }
+            tc5::fence_before_sync();
+            __syncthreads();
+            attn_bwd_core_bf16<DH>(QKVt, KCq, dOt, KCd, dQc, KCc, Ot, KCo, hc, nseq_t, S, a.scale, warp, NW, lane);
+            tc5::fence_proxy_async();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                tc5::fence_after_sync();
+                const uint32_t wt = WqT_s + (uint32_t)ch * Kp * NCc * 2;
+                for (int k = 0; k < NCc / 16; ++k)
+                    tc5::mma_f16(tmem_A, tc5::smem_desc(dQc_s + k * 256, 128, KCc * 128), tc5::smem_desc(wt + k * 256, 128, KCc * 128),
+                                 idesc_a, (ch > 0 || k > 0) ? 1u : 0u);
+                if (ch + 1 < a.nchunks) {
+                    const uint32_t wq = Wq_s + (uint32_t)(ch + 1) * NCq * Kp * 2, wo = WoT_s + (uint32_t)(ch + 1) * NDo * Kp * 2;
+                    for (int k = 0; k < Kp / 16; ++k)
+                        tc5::mma_f16(tmem_Q, tc5::smem_desc(At_s + k * 256, 128, KC1 * 128), tc5::smem_desc(wq + k * 256, 128, KC1 * 128),
+                                     idesc_q, k > 0);
+                    for (int k = 0; k < Kp / 16; ++k)
+                        tc5::mma_f16(tmem_O, tc5::smem_desc(DYt_s + k * 256, 128, KC1 * 128), tc5::smem_desc(wo + k * 256, 128, KC1 * 128),
+                                     idesc_o, k > 0);
+                }
+                tc5::mma_commit(&mbar);
+            }
+            // ---- weight-gradient jobs of this chunk (overlap the dA MMA)
+#pragma unroll
+            for (int j = 0; j < JW; ++j) {
+                const int job = warp + NW * j;
+                const int rel = job - ch * per_chunk;
+                if (rel >= 0 && rel < per_chunk && job < njobs) {
+                    if (rel < MTq * NP) wgrad_job(dQc, KCc, 2 * (rel / NP), false, At, KC1, 2 * (rel % NP), lane, acc[j]);
+                    else { const int r2 = rel - MTq * NP; wgrad_job(Ot, KCo, 2 * (r2 / NP), false, DYt, KC1, 2 * (r2 % NP), lane, acc[j]); }
+                }
+            }
+        }
+        tc5::mbar_wait(&mbar, phase);
+        phase ^= 1;
+        tc5::fence_after_sync();
+        // ---- epilogue 2: LayerNorm backward.  g = dA ; gg = g*gamma ; dx = base + rstd*(gg - mean(gg) - xhat*mean(gg*xhat))
+        {
+            const int ls = row_e / S, pos = row_e - ls * S;
+            const bool valid = row_e < R;
+            const long long gr = valid ? a.g.grow(s0 + ls, pos) : 0;
+            const float mean = stats[2 * row_e], rstd = stats[2 * row_e + 1];
+            const int ngr = (D + 7) >> 3;
+            float gg[2][8], xh[2][8];
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int gq = part + 4 * u;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { gg[u][k] = 0.f; xh[u][k] = 0.f; }
+                if (gq < ngr) {
+                    float v[8], xv[8];
+                    tc5::tmem_ld8(tmem_A + lane_base + gq * 8, v);
+                    if (valid) load8<VEC4>(a.x + gr * D, gq * 8, D, xv);
+                    tc5::tmem_ld_wait();
+                    float g1[8], g2[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int c = gq * 8 + k;
+                        const bool okc = valid && c < D;
+                        const float gv = okc ? v[k] : 0.f;
+                        xh[u][k] = okc ? (xv[k] - mean) * rstd : 0.f;
+                        gg[u][k] = okc ? gv * __ldg(a.ln_w + c) : 0.f;
+                        s1 += gg[u][k];
+                        s2 = fmaf(gg[u][k], xh[u][k], s2);
+                        g1[k] = gv; g2[k] = gv * xh[u][k];
+                    }
+                    sts128(G1t + tc5::kmajor_off(row_e, gq, KC1), pack_bf16(g1[0], g1[1]), pack_bf16(g1[2], g1[3]),
+                           pack_bf16(g1[4], g1[5]), pack_bf16(g1[6], g1[7]));
+                    sts128(G2t + tc5::kmajor_off(row_e, gq, KC1), pack_bf16(g2[0], g2[1]), pack_bf16(g2[2], g2[3]),
+                           pack_bf16(g2[4], g2[5]), pack_bf16(g2[6], g2[7]));
+                } else if (gq < KC1) {
+                    sts128(G1t + tc5::kmajor_off(row_e, gq, KC1), 0u, 0u, 0u, 0u);
+                    sts128(G2t + tc5::kmajor_off(row_e, gq, KC1), 0u, 0u, 0u, 0u);
+                }
+            }
+            parts[(row_e * 4 + part) * 2] = s1;
+            parts[(row_e * 4 + part) * 2 + 1] = s2;
+            tc5::fence_before_sync();
+            __syncthreads();
+            const float invD = 1.0f / (float)D;
+            float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { t1 += parts[(row_e * 4 + q) * 2]; t2 += parts[(row_e * 4 + q) * 2 + 1]; }
+            t1 *= invD; t2 *= invD;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int gq = part + 4 * u;
+                if (gq < ngr && valid) {
+                    float bv[8], ov[8];
+                    if (a.base) load8<VEC4>(a.base + gr * D, gq * 8, D, bv);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        ov[k] = rstd * (gg[u][k] - t1 - xh[u][k] * t2);
+                        if (a.base) ov[k] += bv[k];
+                    }
+                    store8<VEC4>(a.dx + gr * D, gq * 8, D, ov);
+                }
+            }
+        }
+        // ---- tile-end jobs: dbo = colsum(alpha*dout), dbeta = colsum(g), dgamma = colsum(g*xhat)
+#pragma unroll
+        for (int j = 0; j < JW; ++j) {
+            const int job = warp + NW * j;
+            const int rel = job - a.nchunks * per_chunk;
+            if (rel >= 0 && job < njobs) {
+                const int which = rel / NP, np = rel - which * NP;
+                wgrad_job(At, KC1, 0, true, which == 0 ? DYt : which == 1 ? G1t : G2t, KC1, 2 * np, lane, acc[j]);
+            }
+        }
+        __syncthreads();                    // all warps are done with this tile's tiles before the next staging
+    }
+    // ---- per-CTA gradient record: [nchunks][NCc][Kp] gWqkv_c | [nchunks][Cc][Kp] gWoT_c | [3][Kp] dbo, dbeta, dgamma
+    {
+        float* rec = a.partials + (size_t)blockIdx.x * a.psize;
+        float* recO = rec + (size_t)a.nchunks * NCc * Kp;
+        float* recS = recO + (size_t)a.nchunks * Cc * Kp;
+#pragma unroll
+        for (int j = 0; j < JW; ++j) {
+            const int job = warp + NW * j;
+            if (job >= njobs) continue;
+            if (job < a.nchunks * per_chunk) {
+                const int ch = job / per_chunk, rel = job - ch * per_chunk;
+                if (rel < MTq * NP) wgrad_store(rec + (size_t)ch * NCc * Kp, Kp, 16 * (rel / NP), 16 * (rel % NP), lane, acc[j], false);
+                else { const int r2 = rel - MTq * NP; wgrad_store(recO + (size_t)ch * Cc * Kp, Kp, 16 * (r2 / NP), 16 * (r2 % NP), lane, acc[j], false); }
+            } else {
+                const int rel = job - a.nchunks * per_chunk;
+                wgrad_store(recS + (size_t)(rel / NP) * Kp, Kp, 0, 16 * (rel % NP), lane, acc[j], true);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) tc5::tmem_dealloc(tmem_base_s, 512);
+}
+
+struct AttnReduceTcArgs {
+    const float* partials; int nparts, psize;
+    float* dWq; float* dWk; float* dWv; float* dWo; float* dbo; float* dln_w; float* dln_b;
+    int accumulate_wq, D, I, dh, hc, nchunks, Kp, NCc, Cc;
+};
+static __global__ void k_reduce_attn_tc(AttnReduceTcArgs a) {
+    const int D = a.D, I = a.I;
+    const int total = 4 * I * D + 3 * D;
+    const size_t offO = (size_t)a.nchunks * a.NCc * a.Kp, offS = offO + (size_t)a.nchunks * a.Cc * a.Kp;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        size_t src;
+        float* dst;
+        bool accf = false;
+        if (i < 3 * I * D) {
+            const int which = i / (I * D), rem = i - which * (I * D);
+            const int row = rem / D, d = rem - row * D;               // row = head * dh + dd
+            const int ch = row / (a.hc * a.dh), rl = row - ch * (a.hc * a.dh);
+            src = ((size_t)ch * a.NCc + which * a.hc * a.dh + rl) * a.Kp + d;
+            dst = which == 0 ? a.dWq : which == 1 ? a.dWk : a.dWv;
+            accf = which == 0 && a.accumulate_wq;
+            if (dst) dst += rem;
+        } else if (i < 4 * I * D) {
+            const int rem = i - 3 * I * D;
+            const int d = rem / I, col = rem - d * I;
+            const int ch = col / (a.hc * a.dh), cl = col - ch * (a.hc * a.dh);
+            src = offO + ((size_t)ch * a.Cc + cl) * a.Kp + d;
+            dst = a.dWo ? a.dWo + rem : nullptr;
+        } else {
+            const int rem = i - 4 * I * D;
+            const int which = rem / D, d = rem - which * D;            // 0: dbo, 1: dgamma, 2: dbeta
+            src = offS + (size_t)(which == 0 ? 0 : which == 1 ? 2 : 1) * a.Kp + d;
+            float* b = which == 0 ? a.dbo : which == 1 ? a.dln_w : a.dln_b;
+            dst = b ? b + d : nullptr;
+        }
+        if (!dst) continue;
+        float s = 0.f;
+        for (int c = 0; c < a.nparts; ++c) s += a.partials[(size_t)c * a.psize + src];
+        *dst = accf ? *dst + s : s;
+    }
+}
+
+
+}  // namespace rat

@@ -9,143 +9,9 @@
 // the bias/GELU/residual epilogues.  While one team waits for its MMAs the other team runs its SIMT phases, so the
 // tensor pipe, the LSU and the FMA pipe overlap without warp specialisation.  The residual stream, LayerNorm
 // statistics, GELU and all accumulation are fp32; only the MMA operands are rounded to bf16.
-#include "tile.cuh"
-#include "encoder_common.cuh"
-#include "tc5.cuh"
-#include "../../include/rat_b200.h"
-#include <cuda_bf16.h>
-#include <algorithm>
+#include "encoder_tc.cuh"
 
 namespace rat {
-
-int precision_mode();
-
-constexpr int TC_THREADS = 512;
-constexpr int TEAM_THREADS = 256;
-constexpr int TILE_M = 128;
-
-__device__ __forceinline__ float ex2f(float x);
-__device__ __forceinline__ void gelu_fast(float z, float& g, float& dg);
-
-__device__ __forceinline__ void team_sync(int team) {
-    asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(TEAM_THREADS) : "memory");
-}
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-    uint32_t r;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-    return r;
-}
-__device__ __forceinline__ void sts128(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d);
-}
-
-// W [rows x cols] fp32 row-major (torch Linear layout = N x K, K-major)  ->  bf16 canonical image [rows_p x cols_p]
-// (rows_p % 8 == 0, cols_p % 16 == 0), zero padded.  One 16-byte chunk (8 bf16) per loop iteration.
-__device__ __forceinline__ void stage_weight_image(const float* __restrict__ W, int rows, int cols, int rows_p,
-                                                   int cols_p, unsigned char* __restrict__ dst) {
-    const int KC = cols_p >> 3;
-    const int total = rows_p * KC;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int r = i % rows_p, kc = i / rows_p;
-        float v[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int c = kc * 8 + k;
-            v[k] = (r < rows && c < cols) ? __ldg(W + (size_t)r * cols + c) : 0.f;
-        }
-        sts128(dst + tc5::kmajor_off(r, kc, KC), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
-               pack_bf16(v[6], v[7]));
-    }
-}
-
-// 8 consecutive floats of a token row, columns [c0, c0+8) clipped to D (zero fill)
-template <bool VEC4>
-__device__ __forceinline__ void load8(const float* __restrict__ row, int c0, int D, float (&v)[8]) {
-    if (VEC4) {
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (c0 + 4 * q < D) t = *reinterpret_cast<const float4*>(row + c0 + 4 * q);
-            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-        }
-    } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float2 t = make_float2(0.f, 0.f);
-            if (c0 + 2 * q < D) t = *reinterpret_cast<const float2*>(row + c0 + 2 * q);
-            v[2 * q] = t.x; v[2 * q + 1] = t.y;
-        }
-    }
-}
-template <bool VEC4>
-__device__ __forceinline__ void store8(float* __restrict__ row, int c0, int D, const float (&v)[8]) {
-    if (VEC4) {
-#pragma unroll
-        for (int q = 0; q < 2; ++q)
-            if (c0 + 4 * q < D)
-                *reinterpret_cast<float4*>(row + c0 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-    } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if (c0 + 2 * q < D) *reinterpret_cast<float2*>(row + c0 + 2 * q) = make_float2(v[2 * q], v[2 * q + 1]);
-    }
-}
-
-// Load one token row half (KCH chunks of 8 columns starting at chunk h*KCH), optionally LayerNorm it (the two lanes
-// of a row pair exchange partial sums by shuffle), convert to bf16 and store the chunks into the canonical A tile.
-//   tid2 = thread index inside the team (0..255): row = tid2 / 2, h = tid2 % 2.   valid=false -> zero row.
-template <int KCH, bool VEC4>
-__device__ __forceinline__ void stage_row_bf16(const float* __restrict__ src, bool valid, int D, int KC, int row, int h,
-                                               const float* __restrict__ ln_w, const float* __restrict__ ln_b,
-                                               unsigned char* __restrict__ At, int ones_col = -1) {
-    float v[KCH][8];
-#pragma unroll
-    for (int j = 0; j < KCH; ++j) {
-        if (valid) load8<VEC4>(src, (h * KCH + j) * 8, D, v[j]);
-        else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[j][k] = 0.f;
-        }
-    }
-    if (ln_w != nullptr) {
-        float s = 0.f;
-#pragma unroll
-        for (int j = 0; j < KCH; ++j)
-#pragma unroll
-            for (int k = 0; k < 8; ++k) s += v[j][k];                    // pad columns hold zeros
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        const float mean = s / (float)D;
-        float sq = 0.f;
-#pragma unroll
-        for (int j = 0; j < KCH; ++j)
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int c = (h * KCH + j) * 8 + k;
-                const float t = c < D ? v[j][k] - mean : 0.f;
-                sq = fmaf(t, t, sq);
-            }
-        sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-        const float rstd = 1.0f / sqrtf(sq / (float)D + 1e-5f);
-#pragma unroll
-        for (int j = 0; j < KCH; ++j)
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int c = (h * KCH + j) * 8 + k;
-                v[j][k] = (c < D && valid) ? (v[j][k] - mean) * rstd * __ldg(ln_w + c) + __ldg(ln_b + c) : 0.f;
-            }
-    }
-    if (ones_col >= 0 && valid) {        // bias-gradient trick: a column of ones turns colsum(g) into a GEMM column
-#pragma unroll
-        for (int j = 0; j < KCH; ++j)
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if ((h * KCH + j) * 8 + k == ones_col) v[j][k] = 1.0f;
-    }
-#pragma unroll
-    for (int j = 0; j < KCH; ++j)
-        sts128(At + tc5::kmajor_off(row, h * KCH + j, KC), pack_bf16(v[j][0], v[j][1]), pack_bf16(v[j][2], v[j][3]),
-               pack_bf16(v[j][4], v[j][5]), pack_bf16(v[j][6], v[j][7]));
-}
 
 // ------------------------------------------------------------------------------------------------ FeedForward
 struct FFTcArgs {
@@ -300,45 +166,6 @@ struct AttnTcArgs {
     int Cp;                  // pad16(hc * dh): K of the out-projection per chunk
     int SPT;                 // sequences per tile
     int smem_bytes;
-};
-
-__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t saddr) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
-}
-__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t saddr) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
-}
-__device__ __forceinline__ void mma_bf16_16x8x16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ float ex2f(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float qmax(float v) {
-    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
-    return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
-}
-__device__ __forceinline__ float qsum(float v) {
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    return v + __shfl_xor_sync(0xffffffffu, v, 2);
-}
-
-// fragment row i (0..15) of a warp task -> tile row, or -1
-struct TcTask {
-    int S, nseq, seq0;
-    bool packed;
-    __device__ __forceinline__ int row(int i) const {
-        const int seq = packed ? seq0 + (i >> 3) : seq0;
-        const int pos = packed ? (i & 7) : i;
-        return (pos < S && seq < nseq) ? seq * S + pos : -1;
-    }
-    __device__ __forceinline__ bool pair_ok(int i, int j) const { return !packed || ((i >> 3) == (j >> 3)); }
 };
 
 template <int DH>
@@ -588,292 +415,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_fwd_tc(AttnTcArgs a) {
     if (threadIdx.x < 32) tc5::tmem_dealloc(tmem_base_s, 512);
 }
 
-// ------------------------------------------------------------------------------------------------ FF backward
-// Exact-erf GELU and its derivative from ONE exponential (Abramowitz-Stegun 7.1.26, |erf error| <= 1.5e-7):
-//   e = exp(-z^2/2) ; Phi(|z|) = 1 - 0.5 poly(t) e, t = 1/(1 + p |z|/sqrt2) ; gelu = z Phi(z) ; gelu' = Phi(z) + z e/sqrt(2 pi)
-__device__ __forceinline__ void gelu_fast(float z, float& g, float& dg) {
-    const float az = fabsf(z);
-    const float e = ex2f(-0.72134752044448170368f * z * z);          // exp(-z^2/2)
-    float t;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.23164189f, az, 1.0f)));   // p/sqrt2 = 0.3275911/1.41421356
-    float poly = fmaf(1.061405429f, t, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    poly *= t;
-    const float q = 0.5f * poly * e;                                  // 1 - Phi(|z|)
-    const float phi = z >= 0.f ? 1.0f - q : q;
-    g = z * phi;
-    dg = fmaf(z * 0.39894228040143267794f, e, phi);
-}
-
-// C[16 x 16] (+)= sum over the 128 tile rows r of A[r][m0 + 0..15] * B[r][n0 + 0..15]   (A, B: bf16 canonical tiles,
-// rows = tokens).  Weight-gradient product: the token dimension is the reduction index, so both fragments are
-// ldmatrix.trans loads straight from the K-major activation tiles.  acc[0] = columns n0..n0+7, acc[1] = n0+8..n0+15.
-__device__ __forceinline__ void wgrad_job(const unsigned char* __restrict__ At, int KCa, int mchunk, bool a_ones,
-                                          const unsigned char* __restrict__ Bt, int KCb, int nchunk, int lane,
-                                          float (&acc)[2][4]) {
-    const uint32_t a_s = tc5::smem_u32(At), b_s = tc5::smem_u32(Bt);
-    const int ra = (lane & 7) + ((lane >> 4) & 1) * 8, ca = mchunk + ((lane >> 3) & 1);
-    const int rb = (lane & 7) + ((lane >> 3) & 1) * 8, cb = nchunk + (lane >> 4);
-#pragma unroll
-    for (int ks = 0; ks < TILE_M / 16; ++ks) {
-        uint32_t af[4], bf[4];
-        if (a_ones) af[0] = af[1] = af[2] = af[3] = 0x3F803F80u;
-        else ldsm_x4_t(af, a_s + tc5::kmajor_off(16 * ks + ra, ca, KCa));
-        ldsm_x4_t(bf, b_s + tc5::kmajor_off(16 * ks + rb, cb, KCb));
-        mma_bf16_16x8x16(acc[0], af, bf[0], bf[1]);
-        mma_bf16_16x8x16(acc[1], af, bf[2], bf[3]);
-    }
-}
-// store a job's accumulators into rec[(m0 + row) * ld + n0 + col] (fp32, row-major)
-__device__ __forceinline__ void wgrad_store(float* __restrict__ rec, int ld, int m0, int n0, int lane,
-                                            const float (&acc)[2][4], bool first_row_only) {
-    const int g = lane >> 2, t = lane & 3;
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt) {
-        const int col = n0 + 8 * nt + 2 * t;
-        if (!first_row_only || g == 0) {
-            rec[(size_t)(m0 + g) * ld + col] = acc[nt][0];
-            rec[(size_t)(m0 + g) * ld + col + 1] = acc[nt][1];
-        }
-        if (!first_row_only) {
-            rec[(size_t)(m0 + g + 8) * ld + col] = acc[nt][2];
-            rec[(size_t)(m0 + g + 8) * ld + col + 1] = acc[nt][3];
-        }
-    }
-}
-
-// Backward of  y = x + W2 gelu(W1 x + b1) + b2  (no pre-norm):
-//   pre = x W1^T + b1 (recomputed) ; dh = dy W2 ; dpre = dh * gelu'(pre) ; dx = base + dpre W1
-//   gW1 = dpre^T x ; gb1 = colsum(dpre) (ones column of the x tile) ; gW2^T = h^T dy ; gb2 = colsum(dy)
-// The three token-major products run on tcgen05 (accumulators in TMEM); the weight-gradient products reduce over
-// tokens with mma.sync and stay in REGISTERS across all tiles of the CTA (one record per team is written at the end
-// and k_reduce_ff_tc sums the records in fixed order: bitwise deterministic).
-struct FFBwdTcArgs {
-    const float* x; const float* dout; const float* base; float* dx;
-    const float* W1; const float* b1; const float* W2;
-    float* partials;         // [2 * gridDim.x][psize]
-    long long rows;
-    int D, M, Kp, Mp;
-    int psize;               // 2 * Mp * Kp + Kp
-    int smem_bytes;
-};
-
-template <int KCH, bool VEC4, int JW>
-__global__ void __launch_bounds__(TC_THREADS, 1) k_ff_bwd_tc(FFBwdTcArgs a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int D = a.D, M = a.M, Kp = a.Kp, Mp = a.Mp;
-    const int KC1 = Kp >> 3, KC2 = Mp >> 3;
-    unsigned char* W1i = smem_raw;                                   // [Mp x Kp]  (n = m, k = d) = W1[m][d]
-    unsigned char* W2ti = W1i + (size_t)Mp * Kp * 2;                 // [Mp x Kp]  (n = m, k = d) = W2[d][m]
-    unsigned char* W1ti = W2ti + (size_t)Mp * Kp * 2;                // [Kp x Mp]  (n = d, k = m) = W1[m][d]
-    float* b1s = reinterpret_cast<float*>(W1ti + (size_t)Kp * Mp * 2);   // [Mp]
-    unsigned char* team_base = reinterpret_cast<unsigned char*>(b1s + Mp);
-    const size_t team_bytes = (size_t)TILE_M * (2 * Kp + 2 * Mp) * 2;
-    __shared__ __align__(8) uint64_t mbar[2];
-    __shared__ uint32_t tmem_base_s;
-
-    const int team = threadIdx.x / TEAM_THREADS, tid2 = threadIdx.x % TEAM_THREADS;
-    const int warp2 = tid2 >> 5, lane = tid2 & 31;
-    unsigned char* Xt = team_base + team * team_bytes;               // [128 x Kp]  x (+ ones column)
-    unsigned char* DYt = Xt + (size_t)TILE_M * Kp * 2;               // [128 x Kp]  dy
-    unsigned char* Ht = DYt + (size_t)TILE_M * Kp * 2;               // [128 x Mp]  h = gelu(pre)
-    unsigned char* DPt = Ht + (size_t)TILE_M * Mp * 2;               // [128 x Mp]  dpre
-
-    stage_weight_image(a.W1, M, D, Mp, Kp, W1i);
-    {   // transposed images
-        const int total = Mp * KC1;
-        for (int i = threadIdx.x; i < total; i += blockDim.x) {
-            const int m = i % Mp, kc = i / Mp;
-            float v[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) { const int d = kc * 8 + k; v[k] = (m < M && d < D) ? __ldg(a.W2 + (size_t)d * M + m) : 0.f; }
-            sts128(W2ti + tc5::kmajor_off(m, kc, KC1), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
-                   pack_bf16(v[6], v[7]));
-        }
-        const int total2 = Kp * KC2;
-        for (int i = threadIdx.x; i < total2; i += blockDim.x) {
-            const int d = i % Kp, kc = i / Kp;
-            float v[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) { const int m = kc * 8 + k; v[k] = (m < M && d < D) ? __ldg(a.W1 + (size_t)m * D + d) : 0.f; }
-            sts128(W1ti + tc5::kmajor_off(d, kc, KC2), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
-                   pack_bf16(v[6], v[7]));
-        }
-    }
-    for (int i = threadIdx.x; i < Mp; i += blockDim.x) b1s[i] = i < M ? a.b1[i] : 0.f;
-    if (threadIdx.x == 0) { tc5::mbar_init(&mbar[0], 1); tc5::mbar_init(&mbar[1], 1); tc5::fence_mbar_init(); }
-    if (threadIdx.x < 32) tc5::tmem_alloc(&tmem_base_s, 512);
-    tc5::fence_proxy_async();
-    tc5::fence_before_sync();
-    __syncthreads();
-    tc5::fence_after_sync();
-    const uint32_t tmem_P = tmem_base_s + team * 256;                // pre [0, Mp)  -> later dxa [0, Kp)
-    const uint32_t tmem_H = tmem_P + Mp;                             // dh  [Mp, 2 Mp)
-    const uint32_t idesc_m = tc5::instr_desc(tc5::FMT_BF16, TILE_M, Mp);
-    const uint32_t idesc_d = tc5::instr_desc(tc5::FMT_BF16, TILE_M, Kp);
-    const uint32_t lane_base = (uint32_t)((warp2 & 3) * 32) << 16;
-    const int chalf = warp2 >> 2;
-    const int row_e = (warp2 & 3) * 32 + lane;
-    uint32_t phase = 0;
-    uint64_t* bar = &mbar[team];
-
-    // weight-gradient jobs of this warp: job id = warp2 + 8 j
-    //   [0, MT*NP): gW1 (A = dpre, B = x) ; [MT*NP, 2 MT*NP): gW2^T (A = h, B = dy) ; then NP jobs gb2 (A = ones, B = dy)
-    const int MT = Mp >> 4, NP = KC1 >> 1, njobs = 2 * MT * NP + NP;
-    float acc[JW][2][4];
-#pragma unroll
-    for (int j = 0; j < JW; ++j)
-#pragma unroll
-        for (int q = 0; q < 2; ++q) acc[j][q][0] = acc[j][q][1] = acc[j][q][2] = acc[j][q][3] = 0.f;
-
-    const long long ntiles = (a.rows + TILE_M - 1) / TILE_M;
-    for (long long tile = (long long)blockIdx.x * 2 + team; tile < ntiles; tile += (long long)gridDim.x * 2) {
-        const long long r0 = tile * TILE_M;
-        const int R = (int)min((long long)TILE_M, a.rows - r0);
-        {
-            const int row = tid2 >> 1, h = tid2 & 1;
-            stage_row_bf16<KCH, VEC4>(a.x + (r0 + row) * D, row < R, D, KC1, row, h, nullptr, nullptr, Xt, D);
-            stage_row_bf16<KCH, VEC4>(a.dout + (r0 + row) * D, row < R, D, KC1, row, h, nullptr, nullptr, DYt);
-        }
-        tc5::fence_proxy_async();
-        tc5::fence_before_sync();
-        team_sync(team);
-        if (tid2 == 0) {
-            tc5::fence_after_sync();
-            const uint32_t x0 = tc5::smem_u32(Xt), y0 = tc5::smem_u32(DYt), w1 = tc5::smem_u32(W1i), w2 = tc5::smem_u32(W2ti);
-            for (int k = 0; k < Kp / 16; ++k)
-                tc5::mma_f16(tmem_P, tc5::smem_desc(x0 + k * 256, 128, KC1 * 128), tc5::smem_desc(w1 + k * 256, 128, KC1 * 128),
-                             idesc_m, k > 0);
-            for (int k = 0; k < Kp / 16; ++k)
-                tc5::mma_f16(tmem_H, tc5::smem_desc(y0 + k * 256, 128, KC1 * 128), tc5::smem_desc(w2 + k * 256, 128, KC1 * 128),
-                             idesc_m, k > 0);
-            tc5::mma_commit(bar);
-        }
-        tc5::mbar_wait(bar, phase);
-        phase ^= 1;
-        tc5::fence_after_sync();
-        // ---- epilogue 1: h = gelu(pre + b1), dpre = dh * gelu'(pre + b1)  -> bf16 tiles
-        {
-            const int ng = Mp >> 3, g0 = chalf * (ng >> 1), g1 = chalf ? ng : (ng >> 1);
-            for (int g = g0; g < g1; ++g) {
-                float p[8], dh[8], hv[8], dp[8];
-                tc5::tmem_ld8(tmem_P + lane_base + g * 8, p);
-                tc5::tmem_ld8(tmem_H + lane_base + g * 8, dh);
-                tc5::tmem_ld_wait();
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    float gd;
-                    gelu_fast(p[k] + b1s[g * 8 + k], hv[k], gd);
-                    dp[k] = dh[k] * gd;
-                }
-                sts128(Ht + tc5::kmajor_off(row_e, g, KC2), pack_bf16(hv[0], hv[1]), pack_bf16(hv[2], hv[3]),
-                       pack_bf16(hv[4], hv[5]), pack_bf16(hv[6], hv[7]));
-                sts128(DPt + tc5::kmajor_off(row_e, g, KC2), pack_bf16(dp[0], dp[1]), pack_bf16(dp[2], dp[3]),
-                       pack_bf16(dp[4], dp[5]), pack_bf16(dp[6], dp[7]));
-            }
-        }
-        tc5::fence_proxy_async();
-        tc5::fence_before_sync();
-        team_sync(team);
-        // ---- dxa[128 x Kp] = dpre . W1   (tcgen05) overlapped with the weight-gradient jobs (mma.sync)
-        if (tid2 == 0) {
-            tc5::fence_after_sync();
-            const uint32_t p0 = tc5::smem_u32(DPt), w = tc5::smem_u32(W1ti);
-            for (int k = 0; k < Mp / 16; ++k)
-                tc5::mma_f16(tmem_P, tc5::smem_desc(p0 + k * 256, 128, KC2 * 128), tc5::smem_desc(w + k * 256, 128, KC2 * 128),
-                             idesc_d, k > 0);
-            tc5::mma_commit(bar);
-        }
-#pragma unroll
-        for (int j = 0; j < JW; ++j) {
-            const int job = warp2 + 8 * j;
-            if (job < njobs) {
-                if (job < 2 * MT * NP) {
-                    const int which = job / (MT * NP), rem = job - which * (MT * NP);
-                    const int mi = rem / NP, np = rem - mi * NP;
-                    wgrad_job(which ? Ht : DPt, KC2, 2 * mi, false, which ? DYt : Xt, KC1, 2 * np, lane, acc[j]);
-                } else {
-                    wgrad_job(Ht, KC2, 0, true, DYt, KC1, 2 * (job - 2 * MT * NP), lane, acc[j]);
-                }
-            }
-        }
-        tc5::mbar_wait(bar, phase);
-        phase ^= 1;
-        tc5::fence_after_sync();
-        // ---- epilogue 2: dx = base + dxa
-        {
-            const int ng = Kp >> 3, g0 = chalf * (ng >> 1), g1 = chalf ? ng : (ng >> 1);
-            for (int g = g0; g < g1; ++g) {
-                if (g * 8 >= D) break;
-                float v[8], bv[8];
-                tc5::tmem_ld8(tmem_P + lane_base + g * 8, v);
-                if (row_e < R && a.base) load8<VEC4>(a.base + (r0 + row_e) * D, g * 8, D, bv);
-                tc5::tmem_ld_wait();
-                if (row_e < R) {
-                    if (a.base) {
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) v[k] += bv[k];
-                    }
-                    store8<VEC4>(a.dx + (r0 + row_e) * D, g * 8, D, v);
-                }
-            }
-        }
-        tc5::fence_before_sync();
-        team_sync(team);                    // every warp is done reading this tile's operand tiles
-    }
-    // ---- per-team gradient record: gW1 [Mp][Kp] | gW2T [Mp][Kp] | gb2 [Kp]
-    {
-        float* rec = a.partials + (size_t)(blockIdx.x * 2 + team) * a.psize;
-#pragma unroll
-        for (int j = 0; j < JW; ++j) {
-            const int job = warp2 + 8 * j;
-            if (job < njobs) {
-                if (job < 2 * MT * NP) {
-                    const int which = job / (MT * NP), rem = job - which * (MT * NP);
-                    const int mi = rem / NP, np = rem - mi * NP;
-                    wgrad_store(rec + (size_t)which * Mp * Kp, Kp, 16 * mi, 16 * np, lane, acc[j], false);
-                } else {
-                    wgrad_store(rec + (size_t)2 * Mp * Kp, Kp, 0, 16 * (job - 2 * MT * NP), lane, acc[j], true);
-                }
-            }
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) tc5::tmem_dealloc(tmem_base_s, 512);
-}
-
-struct FFReduceTcArgs {
-    const float* partials; int nparts, psize;
-    float* dW1; float* db1; float* dW2; float* db2;
-    int D, M, Kp, Mp;
-};
-__global__ void k_reduce_ff_tc(FFReduceTcArgs a) {
-    const int D = a.D, M = a.M, Kp = a.Kp, Mp = a.Mp;
-    const int total = 2 * M * D + M + D;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        size_t src;
-        float* dst;
-        if (i < M * D) { const int m = i / D, d = i - m * D; src = (size_t)m * Kp + d; dst = a.dW1 ? a.dW1 + i : nullptr; }
-        else if (i < 2 * M * D) { const int rem = i - M * D; const int d = rem / M, m = rem - d * M;
-                                  src = (size_t)Mp * Kp + (size_t)m * Kp + d; dst = a.dW2 ? a.dW2 + rem : nullptr; }
-        else if (i < 2 * M * D + M) { const int m = i - 2 * M * D; src = (size_t)m * Kp + D; dst = a.db1 ? a.db1 + m : nullptr; }
-        else { const int d = i - 2 * M * D - M; src = (size_t)2 * Mp * Kp + d; dst = a.db2 ? a.db2 + d : nullptr; }
-        if (!dst) continue;
-        float s = 0.f;
-        for (int c = 0; c < a.nparts; ++c) s += a.partials[(size_t)c * a.psize + src];
-        *dst = s;
-    }
-}
-
-static bool ff_tc_supported(int D, int M) {
-    if (D < 2 || (D & 1) || D > 64 || M < 1) return false;
-    const int Kp = pad16(D), Mp = pad16(M);
-    if (Mp + Kp > 128 || Mp > 256) return false;                     // TMEM columns per team
-    if ((Mp >> 3) & 1) return false;                                 // column groups split evenly over two warps
-    return true;
-}
 
 }  // namespace rat
 
@@ -955,7 +496,7 @@ int attn_fwd_tc_dispatch(const float* x, const float* res, float* out, const flo
                          const float* Wq, const float* Wk, const float* Wv, const float* Wo, const float* bo, int B, int T,
                          int N, int D, int heads, int dh, float scale, float alpha, int mode, cudaStream_t st) {
     const int S = mode == 0 ? N : T;
-    if (S > 16 || S < 1 || (dh != 10 && dh != 20 && dh != 8 && dh != 16) || D < 2 || (D & 1) || D > 64) return 1;
+    if (S > 16 || S < 1 || (dh != 10 && dh != 20 && dh != 8) || D < 2 || (D & 1) || D > 64) return 1;
     const int DHP = pad16(dh);
     AttnTcArgs a{};
     a.x = x; a.res = res; a.out = out; a.ln_w = ln_w; a.ln_b = ln_b; a.Wq = Wq; a.Wk = Wk; a.Wv = Wv; a.Wo = Wo; a.bo = bo;
@@ -980,80 +521,8 @@ int attn_fwd_tc_dispatch(const float* x, const float* res, float* out, const flo
     switch (dh) {
         case 8: return launch_attn_fwd_tc_dh<8>(a, st);
         case 10: return launch_attn_fwd_tc_dh<10>(a, st);
-        case 16: return launch_attn_fwd_tc_dh<16>(a, st);
         case 20: return launch_attn_fwd_tc_dh<20>(a, st);
         default: return 1;
     }
 }
 
-// ---- FF backward (tcgen05) host side -------------------------------------------------------------------------
-static bool ff_bwd_tc_plan(int D, int M, FFBwdTcArgs* a) {
-    if (!ff_tc_supported(D, M)) return false;
-    const int Kp = pad16(D), Mp = pad16(M);
-    if (Kp == D) return false;                       // needs a pad column for the ones trick (gb1)
-    if (2 * Mp > 256) return false;
-    const int njobs = 2 * (Mp / 16) * (Kp / 16) + Kp / 16;
-    if ((njobs + 7) / 8 > 5) return false;
-    a->D = D; a->M = M; a->Kp = Kp; a->Mp = Mp;
-    a->psize = 2 * Mp * Kp + Kp;
-    const size_t fixed = (size_t)3 * Mp * Kp * 2 + (size_t)Mp * 4;
-    const size_t team = (size_t)TILE_M * (2 * Kp + 2 * Mp) * 2;
-    a->smem_bytes = (int)(fixed + 2 * team);
-    return a->smem_bytes <= max_smem_optin() - 1024;
-}
-static int ff_bwd_tc_grid(long long rows) {
-    const long long ntiles = (rows + TILE_M - 1) / TILE_M;
-    return (int)std::min<long long>((ntiles + 1) / 2, (long long)num_sms());
-}
-size_t ff_bwd_tc_workspace_bytes(long long rows, int D, int M) {
-    FFBwdTcArgs a{};
-    if (!ff_bwd_tc_plan(D, M, &a)) return 0;
-    return (size_t)2 * ff_bwd_tc_grid(rows) * a.psize * sizeof(float);
-}
-
-template <int KCH, bool VEC4, int JW>
-static int launch_ff_bwd_tc(const FFBwdTcArgs& a, int grid, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_ff_bwd_tc<KCH, VEC4, JW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             max_smem_optin() - 1024);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_ff_bwd_tc)");
-        attr_set = true;
-    }
-    k_ff_bwd_tc<KCH, VEC4, JW><<<grid, TC_THREADS, a.smem_bytes, st>>>(a);
-    RAT_CHECK_LAUNCH("k_ff_bwd_tc");
-    return RAT_OK;
-}
-
-int ff_bwd_tc_dispatch(const float* x, const float* dout, const float* base, float* dx, const float* ln_w,
-                       const float* W1, const float* b1, const float* W2, float* dW1, float* db1, float* dW2, float* db2,
-                       long long rows, int D, int M, float* workspace, size_t workspace_bytes, cudaStream_t st) {
-    FFBwdTcArgs a{};
-    if (ln_w != nullptr || !ff_bwd_tc_plan(D, M, &a)) return 1;
-    const int grid = ff_bwd_tc_grid(rows);
-    if (!workspace || workspace_bytes < (size_t)2 * grid * a.psize * sizeof(float)) return 1;
-    a.x = x; a.dout = dout; a.base = base; a.dx = dx; a.W1 = W1; a.b1 = b1; a.W2 = W2; a.partials = workspace; a.rows = rows;
-    const int kch = a.Kp / 16;
-    const bool v4 = (D % 4) == 0;
-    const int njobs = 2 * (a.Mp / 16) * (a.Kp / 16) + a.Kp / 16;
-    const int jw = (njobs + 7) / 8;
-    int rc = 1;
-#define RAT_FFB2(K_, V_) (jw <= 1 ? launch_ff_bwd_tc<K_, V_, 1>(a, grid, st) : jw == 2 ? launch_ff_bwd_tc<K_, V_, 2>(a, grid, st) : \
-                          jw == 3 ? launch_ff_bwd_tc<K_, V_, 3>(a, grid, st) : jw == 4 ? launch_ff_bwd_tc<K_, V_, 4>(a, grid, st) : \
-                          launch_ff_bwd_tc<K_, V_, 5>(a, grid, st))
-#define RAT_FFB(K_) (v4 ? RAT_FFB2(K_, true) : RAT_FFB2(K_, false))
-    switch (kch) {
-        case 1: rc = RAT_FFB(1); break;
-        case 2: rc = RAT_FFB(2); break;
-        case 3: rc = RAT_FFB(3); break;
-        default: return 1;
-    }
-#undef RAT_FFB
-#undef RAT_FFB2
-    if (rc != RAT_OK) return rc;
-    FFReduceTcArgs r{workspace, 2 * grid, a.psize, dW1, db1, dW2, db2, D, M, a.Kp, a.Mp};
-    const int total = 2 * M * D + M + D;
-    k_reduce_ff_tc<<<std::max(1, std::min((total + 255) / 256, 1024)), 256, 0, st>>>(r);
-    RAT_CHECK_LAUNCH("k_reduce_ff_tc");
-    return RAT_OK;
-}
