@@ -42,7 +42,7 @@ __device__ __forceinline__ void stage_weight_image(const float* __restrict__ W, 
             const int c = kc * 8 + k;
             v[k] = (r < rows && c < cols) ? __ldg(W + (size_t)r * cols + c) : 0.f;
         }
-        sts128(dst + tc5::kmajor_off(r, kc, KC), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+        sts128(dst + tc5::kmajor_off(r, kc, rows_p), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
                pack_bf16(v[6], v[7]));
     }
 }
@@ -139,7 +139,7 @@ __device__ __forceinline__ void stage_row_bf16(const float* __restrict__ src, bo
     }
 #pragma unroll
     for (int j = 0; j < KCH; ++j)
-        sts128(At + tc5::kmajor_off(row, h * KCH + j, KC), pack_bf16(v[j][0], v[j][1]), pack_bf16(v[j][2], v[j][3]),
+        sts128(At + tc5::toff(row, h * KCH + j), pack_bf16(v[j][0], v[j][1]), pack_bf16(v[j][2], v[j][3]),
                pack_bf16(v[j][4], v[j][5]), pack_bf16(v[j][6], v[j][7]));
 }
 
@@ -170,17 +170,42 @@ __device__ __forceinline__ float qsum(float v) {
     return v + __shfl_xor_sync(0xffffffffu, v, 2);
 }
 
-// fragment row i (0..15) of a warp task -> tile row, or -1
-struct TcTask {
-    int S, nseq, seq0;
+__device__ __forceinline__ float rcp_fast(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Per-lane constants of the warp-level attention cores.  A warp task is one sequence (8 < S <= 16) or a PAIR of
+// sequences (S <= 8: rows 0-7 of the m16 fragment = first sequence, rows 8-15 = second, off-diagonal blocks masked).
+// Everything that depends only on (S, lane) is computed once per kernel; a task adds its base row.
+struct CoreLane {
+    uint32_t a_off;       // A-fragment / transposed-B ldmatrix pattern: (relative row)*16 + chunk select
+    uint32_t b_off;       // non-transposed B ldmatrix pattern
+    int lo_rel, hi_rel;   // relative rows of fragment rows g and g+8 (-1: do not exist for this S)
+    float madd[2][4];     // additive score mask: 0 or -inf
     bool packed;
-    __device__ __forceinline__ int row(int i) const {
-        const int seq = packed ? seq0 + (i >> 3) : seq0;
-        const int pos = packed ? (i & 7) : i;
-        return (pos < S && seq < nseq) ? seq * S + pos : -1;
-    }
-    __device__ __forceinline__ bool pair_ok(int i, int j) const { return !packed || ((i >> 3) == (j >> 3)); }
 };
+__device__ __forceinline__ CoreLane make_core_lane(int S, int lane) {
+    CoreLane c;
+    c.packed = S <= 8;
+    const bool packed = c.packed;
+    const int g = lane >> 2, t = lane & 3;
+    auto rel = [&](int i) { const int pos = packed ? (i & 7) : i; const int sq = packed ? (i >> 3) : 0; return pos < S ? sq * S + pos : -1; };
+    const int ra = rel((lane & 7) + ((lane >> 3) & 1) * 8), rb = rel((lane & 7) + (lane >> 4) * 8);
+    c.a_off = (uint32_t)(ra < 0 ? 0 : ra) * 16u + (uint32_t)(lane >> 4) * tc5::TILE_CHUNK;
+    c.b_off = (uint32_t)(rb < 0 ? 0 : rb) * 16u + (uint32_t)((lane >> 3) & 1) * tc5::TILE_CHUNK;
+    c.lo_rel = rel(g); c.hi_rel = rel(g + 8);
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int i = (e < 2) ? g : g + 8, j = 8 * nt + 2 * t + (e & 1);
+            const bool ok = rel(j) >= 0 && (!packed || ((i >> 3) == (j >> 3)));
+            c.madd[nt][e] = ok ? 0.f : -INFINITY;
+        }
+    return c;
+}
 
 // ------------------------------------------------------------------------------------------------ FF backward
 // Exact-erf GELU and its derivative from ONE exponential (Abramowitz-Stegun 7.1.26, |erf error| <= 1.5e-7):
@@ -214,8 +239,8 @@ __device__ __forceinline__ void wgrad_job(const unsigned char* __restrict__ At, 
     for (int ks = 0; ks < TILE_M / 16; ++ks) {
         uint32_t af[4], bf[4];
         if (a_ones) af[0] = af[1] = af[2] = af[3] = 0x3F803F80u;
-        else ldsm_x4_t(af, a_s + tc5::kmajor_off(16 * ks + ra, ca, KCa));
-        ldsm_x4_t(bf, b_s + tc5::kmajor_off(16 * ks + rb, cb, KCb));
+        else ldsm_x4_t(af, a_s + tc5::toff(16 * ks + ra, ca));
+        ldsm_x4_t(bf, b_s + tc5::toff(16 * ks + rb, cb));
         mma_bf16_16x8x16(acc[0], af, bf[0], bf[1]);
         mma_bf16_16x8x16(acc[1], af, bf[2], bf[3]);
     }

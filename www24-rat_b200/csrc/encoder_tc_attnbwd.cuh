@@ -39,54 +39,51 @@ __device__ __forceinline__ uint32_t movm_t(uint32_t a) {
 }
 
 template <int DH>
-__device__ __forceinline__ void attn_bwd_core_bf16(const unsigned char* __restrict__ QKVt, int KCq,
-                                                   const unsigned char* __restrict__ dOt, int KCd,
-                                                   unsigned char* __restrict__ dQc, int KCc, unsigned char* __restrict__ Ot,
-                                                   int KCo, int hc, int nseq_t, int S, float scale, int warp, int nwarps,
-                                                   int lane) {
+__device__ __forceinline__ void attn_bwd_core_bf16(const unsigned char* __restrict__ QKVt, const unsigned char* __restrict__ dOt,
+                                                   unsigned char* __restrict__ dQc, unsigned char* __restrict__ Ot, int hc,
+                                                   int nseq_t, int S, float scale, int warp, int nwarps, int lane,
+                                                   const CoreLane& cl) {
     constexpr int DHP = (DH + 15) / 16 * 16, KS = DHP / 16, ND = (DH + 7) / 8;
-    const int g = lane >> 2, t = lane & 3;
-    const bool packed = S <= 8;
-    const int ntasks = (packed ? (nseq_t + 1) / 2 : nseq_t) * hc;
+    constexpr uint32_t HEAD = (DHP / 8) * tc5::TILE_CHUNK;
+    const int t = lane & 3;
+    const int ntasks = (cl.packed ? (nseq_t + 1) >> 1 : nseq_t) * hc;
     const uint32_t qkv_s = tc5::smem_u32(QKVt), do_s = tc5::smem_u32(dOt);
+    const uint32_t part = (uint32_t)hc * HEAD;
     const float inv_log2e = 0.6931471805599453f;
+    int sp = warp / hc, hl = warp - sp * hc;
+    const int dsp = nwarps / hc, dhl = nwarps - dsp * hc;
     for (int task = warp; task < ntasks; task += nwarps) {
-        const int sp = task / hc, hl = task - sp * hc;
-        const TcTask tm{S, nseq_t, packed ? 2 * sp : sp, packed};
-        const int r_first = tm.row(0);
-        int ra = tm.row((lane & 7) + ((lane >> 3) & 1) * 8);     // A-fragment / transposed-B row pattern
-        int rb = tm.row((lane & 7) + (lane >> 4) * 8);           // non-transposed B row pattern
-        if (ra < 0) ra = r_first;
-        if (rb < 0) rb = r_first;
-        const int cq0 = (hl * DHP) >> 3, ck0 = ((hc + hl) * DHP) >> 3, cv0 = ((2 * hc + hl) * DHP) >> 3, cd0 = (hl * DHP) >> 3;
+        const int seq0 = cl.packed ? 2 * sp : sp;
+        const uint32_t tb = (uint32_t)(seq0 * S) * 16u;
+        const uint32_t qa = qkv_s + tb + (uint32_t)hl * HEAD;         // q of this head; k at +part, v at +2 part
+        const uint32_t da = do_s + tb + (uint32_t)hl * HEAD;
         // ---- S = Q K^T (log2 domain, scale folded into Q) and dP = dO V^T
         float sc[2][4] = {}, dp[2][4] = {};
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
-            uint32_t a[4], b[4];
-            ldsm_x4(a, qkv_s + tc5::kmajor_off(ra, cq0 + 2 * ks + (lane >> 4), KCq));
-            ldsm_x4(b, qkv_s + tc5::kmajor_off(rb, ck0 + 2 * ks + ((lane >> 3) & 1), KCq));
+            uint32_t a[4], b[4], a2[4], b2[4];
+            ldsm_x4(a, qa + cl.a_off + 2 * ks * tc5::TILE_CHUNK);
+            ldsm_x4(b, qa + part + cl.b_off + 2 * ks * tc5::TILE_CHUNK);
+            ldsm_x4(a2, da + cl.a_off + 2 * ks * tc5::TILE_CHUNK);
+            ldsm_x4(b2, qa + 2 * part + cl.b_off + 2 * ks * tc5::TILE_CHUNK);
             mma_bf16_16x8x16(sc[0], a, b[0], b[1]);
             mma_bf16_16x8x16(sc[1], a, b[2], b[3]);
-            ldsm_x4(a, do_s + tc5::kmajor_off(ra, cd0 + 2 * ks + (lane >> 4), KCd));
-            ldsm_x4(b, qkv_s + tc5::kmajor_off(rb, cv0 + 2 * ks + ((lane >> 3) & 1), KCq));
-            mma_bf16_16x8x16(dp[0], a, b[0], b[1]);
-            mma_bf16_16x8x16(dp[1], a, b[2], b[3]);
+            mma_bf16_16x8x16(dp[0], a2, b2[0], b2[1]);
+            mma_bf16_16x8x16(dp[1], a2, b2[2], b2[3]);
         }
-        const int rlo = tm.row(g), rhi = tm.row(g + 8);
+        const bool has2 = !cl.packed || (seq0 + 1 < nseq_t);
+        const bool vlo = cl.lo_rel >= 0, vhi = cl.hi_rel >= 0 && has2;
         float mlo = -INFINITY, mhi = -INFINITY;
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int i = (e < 2) ? g : g + 8, j = 8 * nt + 2 * t + (e & 1);
-                const bool ok = ((e < 2) ? rlo : rhi) >= 0 && tm.row(j) >= 0 && tm.pair_ok(i, j);
-                sc[nt][e] = ok ? sc[nt][e] : -INFINITY;
+                sc[nt][e] += cl.madd[nt][e];
                 if (e < 2) mlo = fmaxf(mlo, sc[nt][e]); else mhi = fmaxf(mhi, sc[nt][e]);
             }
         mlo = qmax(mlo); mhi = qmax(mhi);
-        if (rlo < 0) mlo = 0.f;
-        if (rhi < 0) mhi = 0.f;
+        if (mlo == -INFINITY) mlo = 0.f;
+        if (mhi == -INFINITY) mhi = 0.f;
         float llo = 0.f, lhi = 0.f;
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt)
@@ -96,7 +93,8 @@ __device__ __forceinline__ void attn_bwd_core_bf16(const unsigned char* __restri
                 if (e < 2) llo += sc[nt][e]; else lhi += sc[nt][e];
             }
         llo = qsum(llo); lhi = qsum(lhi);
-        const float ilo = rlo >= 0 ? 1.0f / llo : 0.f, ihi = rhi >= 0 ? 1.0f / lhi : 0.f;
+        // rows that do not exist (or belong to a missing second sequence) get P = 0: they must not leak into dK / dV
+        const float ilo = vlo ? rcp_fast(llo) : 0.f, ihi = vhi ? rcp_fast(lhi) : 0.f;
         float dlo = 0.f, dhi = 0.f;
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt)
@@ -123,40 +121,49 @@ __device__ __forceinline__ void attn_bwd_core_bf16(const unsigned char* __restri
         float o[2 * KS][4] = {}, dq[2 * KS][4] = {}, dk[2 * KS][4] = {}, dv[2 * KS][4] = {};
 #pragma unroll
         for (int pp = 0; pp < KS; ++pp) {
-            uint32_t b[4];
-            ldsm_x4_t(b, qkv_s + tc5::kmajor_off(ra, cv0 + 2 * pp + (lane >> 4), KCq));          // V
-            mma_bf16_16x8x16(o[2 * pp], pa, b[0], b[1]);
-            if (2 * pp + 1 < ND) mma_bf16_16x8x16(o[2 * pp + 1], pa, b[2], b[3]);
-            ldsm_x4_t(b, qkv_s + tc5::kmajor_off(ra, ck0 + 2 * pp + (lane >> 4), KCq));          // K
-            mma_bf16_16x8x16(dq[2 * pp], sa, b[0], b[1]);
-            if (2 * pp + 1 < ND) mma_bf16_16x8x16(dq[2 * pp + 1], sa, b[2], b[3]);
-            ldsm_x4_t(b, qkv_s + tc5::kmajor_off(ra, cq0 + 2 * pp + (lane >> 4), KCq));          // Q (scaled)
-            mma_bf16_16x8x16(dk[2 * pp], st, b[0], b[1]);
-            if (2 * pp + 1 < ND) mma_bf16_16x8x16(dk[2 * pp + 1], st, b[2], b[3]);
-            ldsm_x4_t(b, do_s + tc5::kmajor_off(ra, cd0 + 2 * pp + (lane >> 4), KCd));           // dO
-            mma_bf16_16x8x16(dv[2 * pp], pt, b[0], b[1]);
-            if (2 * pp + 1 < ND) mma_bf16_16x8x16(dv[2 * pp + 1], pt, b[2], b[3]);
+            uint32_t bv[4], bk[4], bq[4], bo[4];
+            const uint32_t ko = cl.a_off + 2 * pp * tc5::TILE_CHUNK;
+            ldsm_x4_t(bv, qa + 2 * part + ko);          // V
+            ldsm_x4_t(bk, qa + part + ko);              // K
+            ldsm_x4_t(bq, qa + ko);                     // Q (scaled)
+            ldsm_x4_t(bo, da + ko);                     // dO
+            mma_bf16_16x8x16(o[2 * pp], pa, bv[0], bv[1]);
+            mma_bf16_16x8x16(dq[2 * pp], sa, bk[0], bk[1]);
+            mma_bf16_16x8x16(dk[2 * pp], st, bq[0], bq[1]);
+            mma_bf16_16x8x16(dv[2 * pp], pt, bo[0], bo[1]);
+            if (2 * pp + 1 < ND) {
+                mma_bf16_16x8x16(o[2 * pp + 1], pa, bv[2], bv[3]);
+                mma_bf16_16x8x16(dq[2 * pp + 1], sa, bk[2], bk[3]);
+                mma_bf16_16x8x16(dk[2 * pp + 1], st, bq[2], bq[3]);
+                mma_bf16_16x8x16(dv[2 * pp + 1], pt, bo[2], bo[3]);
+            }
         }
         // ---- compact stores: columns [q: hl*DH + d | k: hc*DH + hl*DH + d | v: 2*hc*DH + hl*DH + d], O: hl*DH + d
+        const uint32_t rlo = tb + (uint32_t)(cl.lo_rel * 16), rhi = tb + (uint32_t)(cl.hi_rel * 16);
 #pragma unroll
         for (int nd = 0; nd < ND; ++nd) {
             const int d = 8 * nd + 2 * t;
             if (d < DH) {
-                const int cq = hl * DH + d, ck = (hc + hl) * DH + d, cv = (2 * hc + hl) * DH + d;
-                if (rlo >= 0) {
-                    *reinterpret_cast<uint32_t*>(dQc + tc5::kmajor_off(rlo, cq >> 3, KCc) + (cq & 7) * 2) = pack_bf16(dq[nd][0] * scale, dq[nd][1] * scale);
-                    *reinterpret_cast<uint32_t*>(dQc + tc5::kmajor_off(rlo, ck >> 3, KCc) + (ck & 7) * 2) = pack_bf16(dk[nd][0] * inv_log2e, dk[nd][1] * inv_log2e);
-                    *reinterpret_cast<uint32_t*>(dQc + tc5::kmajor_off(rlo, cv >> 3, KCc) + (cv & 7) * 2) = pack_bf16(dv[nd][0], dv[nd][1]);
-                    *reinterpret_cast<uint32_t*>(Ot + tc5::kmajor_off(rlo, cq >> 3, KCo) + (cq & 7) * 2) = pack_bf16(o[nd][0], o[nd][1]);
+                const int cq = hl * DH + d, ck = cq + hc * DH, cv = ck + hc * DH;
+                const uint32_t oq = (uint32_t)(cq >> 3) * tc5::TILE_CHUNK + (uint32_t)(cq & 7) * 2u;
+                const uint32_t ok = (uint32_t)(ck >> 3) * tc5::TILE_CHUNK + (uint32_t)(ck & 7) * 2u;
+                const uint32_t ov = (uint32_t)(cv >> 3) * tc5::TILE_CHUNK + (uint32_t)(cv & 7) * 2u;
+                if (vlo) {
+                    *reinterpret_cast<uint32_t*>(dQc + rlo + oq) = pack_bf16(dq[nd][0] * scale, dq[nd][1] * scale);
+                    *reinterpret_cast<uint32_t*>(dQc + rlo + ok) = pack_bf16(dk[nd][0] * inv_log2e, dk[nd][1] * inv_log2e);
+                    *reinterpret_cast<uint32_t*>(dQc + rlo + ov) = pack_bf16(dv[nd][0], dv[nd][1]);
+                    *reinterpret_cast<uint32_t*>(Ot + rlo + oq) = pack_bf16(o[nd][0], o[nd][1]);
                 }
-                if (rhi >= 0) {
-                    *reinterpret_cast<uint32_t*>(dQc + tc5::kmajor_off(rhi, cq >> 3, KCc) + (cq & 7) * 2) = pack_bf16(dq[nd][2] * scale, dq[nd][3] * scale);
-                    *reinterpret_cast<uint32_t*>(dQc + tc5::kmajor_off(rhi, ck >> 3, KCc) + (ck & 7) * 2) = pack_bf16(dk[nd][2] * inv_log2e, dk[nd][3] * inv_log2e);
-                    *reinterpret_cast<uint32_t*>(dQc + tc5::kmajor_off(rhi, cv >> 3, KCc) + (cv & 7) * 2) = pack_bf16(dv[nd][2], dv[nd][3]);
-                    *reinterpret_cast<uint32_t*>(Ot + tc5::kmajor_off(rhi, cq >> 3, KCo) + (cq & 7) * 2) = pack_bf16(o[nd][2], o[nd][3]);
+                if (vhi) {
+                    *reinterpret_cast<uint32_t*>(dQc + rhi + oq) = pack_bf16(dq[nd][2] * scale, dq[nd][3] * scale);
+                    *reinterpret_cast<uint32_t*>(dQc + rhi + ok) = pack_bf16(dk[nd][2] * inv_log2e, dk[nd][3] * inv_log2e);
+                    *reinterpret_cast<uint32_t*>(dQc + rhi + ov) = pack_bf16(dv[nd][2], dv[nd][3]);
+                    *reinterpret_cast<uint32_t*>(Ot + rhi + oq) = pack_bf16(o[nd][2], o[nd][3]);
                 }
             }
         }
+        sp += dsp; hl += dhl;
+        if (hl >= hc) { hl -= hc; ++sp; }
     }
 }
 
@@ -200,7 +207,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_bwd_tc(AttnBwdTcArgs a) 
                 const int c = kc * 8 + k;
                 v[k] = (d < DH && c < D) ? mul * __ldg(W + (size_t)((ch * hc + hl) * DH + d) * D + c) : 0.f;
             }
-            sts128(Wqkv_i + tc5::kmajor_off(n, kc, KC1), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+            sts128(Wqkv_i + (size_t)ch * NCq * Kp * 2 + tc5::kmajor_off(rem, kc, NCq), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
                    pack_bf16(v[6], v[7]));
         }
         const int perT = Kp * KCc;
@@ -215,7 +222,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_bwd_tc(AttnBwdTcArgs a) 
                 const float* W = w == 0 ? a.Wq : w == 1 ? a.Wk : a.Wv;
                 v[k] = (w < 3 && d < D) ? __ldg(W + (size_t)(ch * hc * DH + rem2) * D + d) : 0.f;
             }
-            sts128(WqkvT_i + (size_t)ch * Kp * NCc * 2 + tc5::kmajor_off(d, kc, KCc), pack_bf16(v[0], v[1]),
+            sts128(WqkvT_i + (size_t)ch * Kp * NCc * 2 + tc5::kmajor_off(d, kc, Kp), pack_bf16(v[0], v[1]),
                    pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
         }
         const int perO = NDo * KC1;
@@ -229,7 +236,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_bwd_tc(AttnBwdTcArgs a) 
                 const int d = kc * 8 + k;
                 v[k] = (dd < DH && d < D) ? __ldg(a.Wo + (size_t)d * a.I + (ch * hc + hl) * DH + dd) : 0.f;
             }
-            sts128(WoT_i + (size_t)ch * NDo * Kp * 2 + tc5::kmajor_off(n, kc, KC1), pack_bf16(v[0], v[1]),
+            sts128(WoT_i + (size_t)ch * NDo * Kp * 2 + tc5::kmajor_off(n, kc, NDo), pack_bf16(v[0], v[1]),
                    pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
         }
         // activation tiles start as zeros (pad columns of the compact tiles are never written)
@@ -253,6 +260,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_bwd_tc(AttnBwdTcArgs a) 
     const int part = warp >> 2;                                      // 0..3: column share of this warp inside its lane quadrant
     const int row_e = (warp & 3) * 32 + lane;
     uint32_t phase = 0;
+    const CoreLane cl = make_core_lane(S, lane);
     const uint32_t At_s = tc5::smem_u32(At), DYt_s = tc5::smem_u32(DYt), dQc_s = tc5::smem_u32(dQc);
     const uint32_t Wq_s = tc5::smem_u32(Wqkv_i), WqT_s = tc5::smem_u32(WqkvT_i), WoT_s = tc5::smem_u32(WoT_i);
 
@@ -289,10 +297,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_bwd_tc(AttnBwdTcArgs a) 
         if (threadIdx.x == 0) {
             tc5::fence_after_sync();
             for (int k = 0; k < Kp / 16; ++k)
-                tc5::mma_f16(tmem_Q, tc5::smem_desc(At_s + k * 256, 128, KC1 * 128), tc5::smem_desc(Wq_s + k * 256, 128, KC1 * 128),
+                tc5::mma_f16(tmem_Q, tc5::kdesc(At_s, TILE_M, k), tc5::kdesc(Wq_s, NCq, k),
                              idesc_q, k > 0);
             for (int k = 0; k < Kp / 16; ++k)
-                tc5::mma_f16(tmem_O, tc5::smem_desc(DYt_s + k * 256, 128, KC1 * 128), tc5::smem_desc(WoT_s + k * 256, 128, KC1 * 128),
+                tc5::mma_f16(tmem_O, tc5::kdesc(DYt_s, TILE_M, k), tc5::kdesc(WoT_s, NDo, k),
                              idesc_o, k > 0);
             tc5::mma_commit(&mbar);
         }
@@ -311,30 +319,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_bwd_tc(AttnBwdTcArgs a) 
                     tc5::tmem_ld_wait();
                     unsigned char* dst = isq ? QKVt : dOt;
                     const int KCx = isq ? KCq : KCd;
-                    sts128(dst + tc5::kmajor_off(row_e, 2 * gg, KCx), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
+                    sts128(dst + tc5::toff(row_e, 2 * gg), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
                            pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                    sts128(dst + tc5::kmajor_off(row_e, 2 * gg + 1, KCx), pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]),
+                    sts128(dst + tc5::toff(row_e, 2 * gg + 1), pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]),
                            pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
                 }
             }
             tc5::fence_before_sync();
             __syncthreads();
-            attn_bwd_core_bf16<DH>(QKVt, KCq, dOt, KCd, dQc, KCc, Ot, KCo, hc, nseq_t, S, a.scale, warp, NW, lane);
+            attn_bwd_core_bf16<DH>(QKVt, dOt, dQc, Ot, hc, nseq_t, S, a.scale, warp, NW, lane, cl);
             tc5::fence_proxy_async();
             __syncthreads();
             if (threadIdx.x == 0) {
                 tc5::fence_after_sync();
                 const uint32_t wt = WqT_s + (uint32_t)ch * Kp * NCc * 2;
                 for (int k = 0; k < NCc / 16; ++k)
-                    tc5::mma_f16(tmem_A, tc5::smem_desc(dQc_s + k * 256, 128, KCc * 128), tc5::smem_desc(wt + k * 256, 128, KCc * 128),
+                    tc5::mma_f16(tmem_A, tc5::kdesc(dQc_s, TILE_M, k), tc5::kdesc(wt, Kp, k),
                                  idesc_a, (ch > 0 || k > 0) ? 1u : 0u);
                 if (ch + 1 < a.nchunks) {
                     const uint32_t wq = Wq_s + (uint32_t)(ch + 1) * NCq * Kp * 2, wo = WoT_s + (uint32_t)(ch + 1) * NDo * Kp * 2;
                     for (int k = 0; k < Kp / 16; ++k)
-                        tc5::mma_f16(tmem_Q, tc5::smem_desc(At_s + k * 256, 128, KC1 * 128), tc5::smem_desc(wq + k * 256, 128, KC1 * 128),
+                        tc5::mma_f16(tmem_Q, tc5::kdesc(At_s, TILE_M, k), tc5::kdesc(wq, NCq, k),
                                      idesc_q, k > 0);
                     for (int k = 0; k < Kp / 16; ++k)
-                        tc5::mma_f16(tmem_O, tc5::smem_desc(DYt_s + k * 256, 128, KC1 * 128), tc5::smem_desc(wo + k * 256, 128, KC1 * 128),
+                        tc5::mma_f16(tmem_O, tc5::kdesc(DYt_s, TILE_M, k), tc5::kdesc(wo, NDo, k),
                                      idesc_o, k > 0);
                 }
                 tc5::mma_commit(&mbar);
@@ -384,13 +392,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_bwd_tc(AttnBwdTcArgs a) 
                         s2 = fmaf(gg[u][k], xh[u][k], s2);
                         g1[k] = gv; g2[k] = gv * xh[u][k];
                     }
-                    sts128(G1t + tc5::kmajor_off(row_e, gq, KC1), pack_bf16(g1[0], g1[1]), pack_bf16(g1[2], g1[3]),
+                    sts128(G1t + tc5::toff(row_e, gq), pack_bf16(g1[0], g1[1]), pack_bf16(g1[2], g1[3]),
                            pack_bf16(g1[4], g1[5]), pack_bf16(g1[6], g1[7]));
-                    sts128(G2t + tc5::kmajor_off(row_e, gq, KC1), pack_bf16(g2[0], g2[1]), pack_bf16(g2[2], g2[3]),
+                    sts128(G2t + tc5::toff(row_e, gq), pack_bf16(g2[0], g2[1]), pack_bf16(g2[2], g2[3]),
                            pack_bf16(g2[4], g2[5]), pack_bf16(g2[6], g2[7]));
                 } else if (gq < KC1) {
-                    sts128(G1t + tc5::kmajor_off(row_e, gq, KC1), 0u, 0u, 0u, 0u);
-                    sts128(G2t + tc5::kmajor_off(row_e, gq, KC1), 0u, 0u, 0u, 0u);
+                    sts128(G1t + tc5::toff(row_e, gq), 0u, 0u, 0u, 0u);
+                    sts128(G2t + tc5::toff(row_e, gq), 0u, 0u, 0u, 0u);
                 }
             }
             parts[(row_e * 4 + part) * 2] = s1;

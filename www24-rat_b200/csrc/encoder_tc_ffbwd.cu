@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_ff_bwd_tc(FFBwdTcArgs a) {
             float v[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) { const int d = kc * 8 + k; v[k] = (m < M && d < D) ? __ldg(a.W2 + (size_t)d * M + m) : 0.f; }
-            sts128(W2ti + tc5::kmajor_off(m, kc, KC1), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+            sts128(W2ti + tc5::kmajor_off(m, kc, Mp), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
                    pack_bf16(v[6], v[7]));
         }
         const int total2 = Kp * KC2;
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_ff_bwd_tc(FFBwdTcArgs a) {
             float v[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) { const int m = kc * 8 + k; v[k] = (m < M && d < D) ? __ldg(a.W1 + (size_t)m * D + d) : 0.f; }
-            sts128(W1ti + tc5::kmajor_off(d, kc, KC2), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+            sts128(W1ti + tc5::kmajor_off(d, kc, Kp), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
                    pack_bf16(v[6], v[7]));
         }
     }
@@ -103,10 +103,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_ff_bwd_tc(FFBwdTcArgs a) {
             tc5::fence_after_sync();
             const uint32_t x0 = tc5::smem_u32(Xt), y0 = tc5::smem_u32(DYt), w1 = tc5::smem_u32(W1i), w2 = tc5::smem_u32(W2ti);
             for (int k = 0; k < Kp / 16; ++k)
-                tc5::mma_f16(tmem_P, tc5::smem_desc(x0 + k * 256, 128, KC1 * 128), tc5::smem_desc(w1 + k * 256, 128, KC1 * 128),
+                tc5::mma_f16(tmem_P, tc5::kdesc(x0, TILE_M, k), tc5::kdesc(w1, Mp, k),
                              idesc_m, k > 0);
             for (int k = 0; k < Kp / 16; ++k)
-                tc5::mma_f16(tmem_H, tc5::smem_desc(y0 + k * 256, 128, KC1 * 128), tc5::smem_desc(w2 + k * 256, 128, KC1 * 128),
+                tc5::mma_f16(tmem_H, tc5::kdesc(y0, TILE_M, k), tc5::kdesc(w2, Mp, k),
                              idesc_m, k > 0);
             tc5::mma_commit(bar);
         }
@@ -127,9 +127,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_ff_bwd_tc(FFBwdTcArgs a) {
                     gelu_fast(p[k] + b1s[g * 8 + k], hv[k], gd);
                     dp[k] = dh[k] * gd;
                 }
-                sts128(Ht + tc5::kmajor_off(row_e, g, KC2), pack_bf16(hv[0], hv[1]), pack_bf16(hv[2], hv[3]),
+                sts128(Ht + tc5::toff(row_e, g), pack_bf16(hv[0], hv[1]), pack_bf16(hv[2], hv[3]),
                        pack_bf16(hv[4], hv[5]), pack_bf16(hv[6], hv[7]));
-                sts128(DPt + tc5::kmajor_off(row_e, g, KC2), pack_bf16(dp[0], dp[1]), pack_bf16(dp[2], dp[3]),
+                sts128(DPt + tc5::toff(row_e, g), pack_bf16(dp[0], dp[1]), pack_bf16(dp[2], dp[3]),
                        pack_bf16(dp[4], dp[5]), pack_bf16(dp[6], dp[7]));
             }
         }
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_ff_bwd_tc(FFBwdTcArgs a) {
             tc5::fence_after_sync();
             const uint32_t p0 = tc5::smem_u32(DPt), w = tc5::smem_u32(W1ti);
             for (int k = 0; k < Mp / 16; ++k)
-                tc5::mma_f16(tmem_P, tc5::smem_desc(p0 + k * 256, 128, KC2 * 128), tc5::smem_desc(w + k * 256, 128, KC2 * 128),
+                tc5::mma_f16(tmem_P, tc5::kdesc(p0, TILE_M, k), tc5::kdesc(w, Kp, k),
                              idesc_d, k > 0);
             tc5::mma_commit(bar);
         }

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_ff_fwd_tc(FFTcArgs a) {
             tc5::fence_after_sync();
             const uint32_t a0 = tc5::smem_u32(At), b0 = tc5::smem_u32(W1i);
             for (int k = 0; k < Kp / 16; ++k)
-                tc5::mma_f16(tmem_H, tc5::smem_desc(a0 + k * 256, 128, KC1 * 128), tc5::smem_desc(b0 + k * 256, 128, KC1 * 128),
+                tc5::mma_f16(tmem_H, tc5::kdesc(a0, TILE_M, k), tc5::kdesc(b0, Mp, k),
                              idesc1, k > 0);
             tc5::mma_commit(bar);
         }
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_ff_fwd_tc(FFTcArgs a) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) { float dg; gelu_fast(v[k] + b1s[g * 8 + k], v[k], dg); }
                 // columns >= M: W1 image rows are zero and b1s is zero -> gelu(0) = 0
-                sts128(Ht + tc5::kmajor_off(row_e, g, KC2), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
+                sts128(Ht + tc5::toff(row_e, g), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
                        pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
             }
         }
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_ff_fwd_tc(FFTcArgs a) {
             tc5::fence_after_sync();
             const uint32_t a0 = tc5::smem_u32(Ht), b0 = tc5::smem_u32(W2i);
             for (int k = 0; k < Mp / 16; ++k)
-                tc5::mma_f16(tmem_Y, tc5::smem_desc(a0 + k * 256, 128, KC2 * 128), tc5::smem_desc(b0 + k * 256, 128, KC2 * 128),
+                tc5::mma_f16(tmem_Y, tc5::kdesc(a0, TILE_M, k), tc5::kdesc(b0, Np, k),
                              idesc2, k > 0);
             tc5::mma_commit(bar);
         }
@@ -169,47 +169,42 @@ struct AttnTcArgs {
 };
 
 template <int DH>
-__device__ __forceinline__ void attn_core_bf16(const unsigned char* __restrict__ QKVt, int KCq, int hc,
-                                               unsigned char* __restrict__ Ot, int KCo, int nseq_t, int S, int warp2,
-                                               int lane) {
+__device__ __forceinline__ void attn_core_bf16(const unsigned char* __restrict__ QKVt, int hc, unsigned char* __restrict__ Ot,
+                                               int nseq_t, int S, int warp, int nwarps, int lane, const CoreLane& cl) {
     constexpr int DHP = (DH + 15) / 16 * 16, KS = DHP / 16, ND = (DH + 7) / 8;
-    const int g = lane >> 2, t = lane & 3;
-    const bool packed = S <= 8;
-    const int ntasks = (packed ? (nseq_t + 1) / 2 : nseq_t) * hc;
+    constexpr uint32_t HEAD = (DHP / 8) * tc5::TILE_CHUNK;            // byte stride between heads inside q / k / v
+    const int t = lane & 3;
+    const int ntasks = (cl.packed ? (nseq_t + 1) >> 1 : nseq_t) * hc;
     const uint32_t qkv_s = tc5::smem_u32(QKVt);
-    for (int task = warp2; task < ntasks; task += TEAM_THREADS / 32) {
-        const int sp = task / hc, hl = task - sp * hc;
-        const TcTask tm{S, nseq_t, packed ? 2 * sp : sp, packed};
-        const int r_first = tm.row(0);
-        // ldmatrix row addresses of this lane
-        int rq = tm.row((lane & 7) + ((lane >> 3) & 1) * 8);     // Q: matrices (rows 0-7|8-15) x (k chunk 0|1)
-        int rk = tm.row((lane & 7) + (lane >> 4) * 8);           // K: matrices (keys 0-7, k0|k1), (keys 8-15, k0|k1)
-        if (rq < 0) rq = r_first;
-        if (rk < 0) rk = r_first;
-        const int cq0 = (hl * DHP) >> 3, ck0 = ((hc + hl) * DHP) >> 3, cv0 = ((2 * hc + hl) * DHP) >> 3;
+    const uint32_t part = (uint32_t)hc * HEAD;                        // q -> k -> v
+    int sp = warp / hc, hl = warp - sp * hc;
+    const int dsp = nwarps / hc, dhl = nwarps - dsp * hc;
+    for (int task = warp; task < ntasks; task += nwarps) {
+        const int seq0 = cl.packed ? 2 * sp : sp;
+        const uint32_t tb = (uint32_t)(seq0 * S) * 16u;
+        const uint32_t qa = qkv_s + tb + (uint32_t)hl * HEAD;
         float sc[2][4] = {};
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
             uint32_t a[4], b[4];
-            ldsm_x4(a, qkv_s + tc5::kmajor_off(rq, cq0 + 2 * ks + (lane >> 4), KCq));
-            ldsm_x4(b, qkv_s + tc5::kmajor_off(rk, ck0 + 2 * ks + ((lane >> 3) & 1), KCq));
+            ldsm_x4(a, qa + cl.a_off + 2 * ks * tc5::TILE_CHUNK);
+            ldsm_x4(b, qa + part + cl.b_off + 2 * ks * tc5::TILE_CHUNK);
             mma_bf16_16x8x16(sc[0], a, b[0], b[1]);
             mma_bf16_16x8x16(sc[1], a, b[2], b[3]);
         }
-        const int rlo = tm.row(g), rhi = tm.row(g + 8);
+        const bool has2 = !cl.packed || (seq0 + 1 < nseq_t);
+        const bool vlo = cl.lo_rel >= 0, vhi = cl.hi_rel >= 0 && has2;
         float mlo = -INFINITY, mhi = -INFINITY;
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int i = (e < 2) ? g : g + 8, j = 8 * nt + 2 * t + (e & 1);
-                const bool ok = tm.row(j) >= 0 && tm.pair_ok(i, j);
-                sc[nt][e] = ok ? sc[nt][e] : -INFINITY;
+                sc[nt][e] += cl.madd[nt][e];
                 if (e < 2) mlo = fmaxf(mlo, sc[nt][e]); else mhi = fmaxf(mhi, sc[nt][e]);
             }
         mlo = qmax(mlo); mhi = qmax(mhi);
-        if (rlo < 0) mlo = 0.f;
-        if (rhi < 0) mhi = 0.f;
+        if (mlo == -INFINITY) mlo = 0.f;                            // rows that do not exist: exp2(-inf) = 0, no NaN
+        if (mhi == -INFINITY) mhi = 0.f;
         float llo = 0.f, lhi = 0.f;
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt)
@@ -222,30 +217,29 @@ __device__ __forceinline__ void attn_core_bf16(const unsigned char* __restrict__
         uint32_t pa[4];
         pa[0] = pack_bf16(sc[0][0], sc[0][1]); pa[1] = pack_bf16(sc[0][2], sc[0][3]);
         pa[2] = pack_bf16(sc[1][0], sc[1][1]); pa[3] = pack_bf16(sc[1][2], sc[1][3]);
-        int rv = tm.row((lane & 7) + ((lane >> 3) & 1) * 8);     // V (transposed): matrices (keys 0-7|8-15) x (d chunk)
-        if (rv < 0) rv = r_first;
         float o[2 * KS][4] = {};
 #pragma unroll
         for (int pp = 0; pp < KS; ++pp) {
             uint32_t vb[4];
-            ldsm_x4_t(vb, qkv_s + tc5::kmajor_off(rv, cv0 + 2 * pp + (lane >> 4), KCq));
+            ldsm_x4_t(vb, qa + 2 * part + cl.a_off + 2 * pp * tc5::TILE_CHUNK);
             mma_bf16_16x8x16(o[2 * pp], pa, vb[0], vb[1]);
             if (2 * pp + 1 < ND) mma_bf16_16x8x16(o[2 * pp + 1], pa, vb[2], vb[3]);
         }
-        const float ilo = rlo >= 0 ? 1.0f / llo : 0.f, ihi = rhi >= 0 ? 1.0f / lhi : 0.f;
+        const float ilo = rcp_fast(llo), ihi = rcp_fast(lhi);
+        unsigned char* olo = Ot + tb + (uint32_t)(cl.lo_rel * 16);
+        unsigned char* ohi = Ot + tb + (uint32_t)(cl.hi_rel * 16);
 #pragma unroll
         for (int nd = 0; nd < ND; ++nd) {
             const int d = 8 * nd + 2 * t;
             if (d < DH) {                                           // DH even: the (d, d+1) pair is valid as a whole
                 const int col = hl * DH + d;
-                if (rlo >= 0)
-                    *reinterpret_cast<uint32_t*>(Ot + tc5::kmajor_off(rlo, col >> 3, KCo) + (col & 7) * 2) =
-                        pack_bf16(o[nd][0] * ilo, o[nd][1] * ilo);
-                if (rhi >= 0)
-                    *reinterpret_cast<uint32_t*>(Ot + tc5::kmajor_off(rhi, col >> 3, KCo) + (col & 7) * 2) =
-                        pack_bf16(o[nd][2] * ihi, o[nd][3] * ihi);
+                const uint32_t co = (uint32_t)(col >> 3) * tc5::TILE_CHUNK + (uint32_t)(col & 7) * 2u;
+                if (vlo) *reinterpret_cast<uint32_t*>(olo + co) = pack_bf16(o[nd][0] * ilo, o[nd][1] * ilo);
+                if (vhi) *reinterpret_cast<uint32_t*>(ohi + co) = pack_bf16(o[nd][2] * ihi, o[nd][3] * ihi);
             }
         }
+        sp += dsp; hl += dhl;
+        if (hl >= hc) { hl -= hc; ++sp; }
     }
 }
 
@@ -285,7 +279,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_fwd_tc(AttnTcArgs a) {
                 const int c = kc * 8 + k;
                 v[k] = (d < DH && c < D) ? mul * __ldg(W + (size_t)((ch * hc + hl) * DH + d) * D + c) : 0.f;
             }
-            sts128(Wqkv_i + tc5::kmajor_off(n, kc, KC1), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
+            sts128(Wqkv_i + (size_t)ch * NCq * Kp * 2 + tc5::kmajor_off(rem, kc, NCq), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
                    pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
         }
         const int per = Np * KCo;
@@ -298,7 +292,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_fwd_tc(AttnTcArgs a) {
                 const int c = kc * 8 + k;
                 v[k] = (n < D && c < hc * DH) ? __ldg(a.Wo + (size_t)n * a.I + ch * hc * DH + c) : 0.f;
             }
-            sts128(Wo_i + (size_t)ch * Np * Cp * 2 + tc5::kmajor_off(n, kc, KCo), pack_bf16(v[0], v[1]),
+            sts128(Wo_i + (size_t)ch * Np * Cp * 2 + tc5::kmajor_off(n, kc, Np), pack_bf16(v[0], v[1]),
                    pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
         }
         for (int i = threadIdx.x; i < Np; i += blockDim.x) bos[i] = i < D ? a.bo[i] : 0.f;
@@ -321,6 +315,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_fwd_tc(AttnTcArgs a) {
     const int row_e = (warp2 & 3) * 32 + lane;
     uint32_t phase = 0;
     uint64_t* bar = &mbar[team];
+    const CoreLane cl = make_core_lane(S, lane);
     const uint32_t At_s = tc5::smem_u32(At), Ot_s = tc5::smem_u32(Ot), Wq_s = tc5::smem_u32(Wqkv_i), Wo_s = tc5::smem_u32(Wo_i);
 
     const long long ntiles = (a.nseq + a.SPT - 1) / a.SPT;
@@ -342,8 +337,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_fwd_tc(AttnTcArgs a) {
         if (tid2 == 0) {
             tc5::fence_after_sync();
             for (int k = 0; k < Kp / 16; ++k)
-                tc5::mma_f16(tmem_Q, tc5::smem_desc(At_s + k * 256, 128, KC1 * 128),
-                             tc5::smem_desc(Wq_s + k * 256, 128, KC1 * 128), idesc_q, k > 0);
+                tc5::mma_f16(tmem_Q, tc5::kdesc(At_s, TILE_M, k), tc5::kdesc(Wq_s, NCq, k), idesc_q, k > 0);
             tc5::mma_commit(bar);
         }
         for (int ch = 0; ch < a.nchunks; ++ch) {
@@ -357,29 +351,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_fwd_tc(AttnTcArgs a) {
                     float v[16];
                     tc5::tmem_ld16(tmem_Q + lane_base + gq * 16, v);
                     tc5::tmem_ld_wait();
-                    sts128(QKVt + tc5::kmajor_off(row_e, 2 * gq, KCq), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
+                    sts128(QKVt + tc5::toff(row_e, 2 * gq), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
                            pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                    sts128(QKVt + tc5::kmajor_off(row_e, 2 * gq + 1, KCq), pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]),
+                    sts128(QKVt + tc5::toff(row_e, 2 * gq + 1), pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]),
                            pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
                 }
             }
             tc5::fence_before_sync();
             team_sync(team);
             // ---- softmax(q k^T) v per (sequence, head) -> bf16 o tile
-            attn_core_bf16<DH>(QKVt, KCq, hc, Ot, KCo, nseq_t, S, warp2, lane);
+            attn_core_bf16<DH>(QKVt, hc, Ot, nseq_t, S, warp2, TEAM_THREADS / 32, lane, cl);
             tc5::fence_proxy_async();
             team_sync(team);
             if (tid2 == 0) {
                 tc5::fence_after_sync();
                 const uint32_t wo = Wo_s + (uint32_t)ch * Np * Cp * 2;
                 for (int k = 0; k < Cp / 16; ++k)
-                    tc5::mma_f16(tmem_Y, tc5::smem_desc(Ot_s + k * 256, 128, KCo * 128),
-                                 tc5::smem_desc(wo + k * 256, 128, KCo * 128), idesc_o, (ch > 0 || k > 0) ? 1u : 0u);
+                    tc5::mma_f16(tmem_Y, tc5::kdesc(Ot_s, TILE_M, k), tc5::kdesc(wo, Np, k), idesc_o, (ch > 0 || k > 0) ? 1u : 0u);
                 if (ch + 1 < a.nchunks) {
                     const uint32_t wq = Wq_s + (uint32_t)(ch + 1) * NCq * Kp * 2;
                     for (int k = 0; k < Kp / 16; ++k)
-                        tc5::mma_f16(tmem_Q, tc5::smem_desc(At_s + k * 256, 128, KC1 * 128),
-                                     tc5::smem_desc(wq + k * 256, 128, KC1 * 128), idesc_q, k > 0);
+                        tc5::mma_f16(tmem_Q, tc5::kdesc(At_s, TILE_M, k), tc5::kdesc(wq, NCq, k), idesc_q, k > 0);
                 }
                 tc5::mma_commit(bar);
             }

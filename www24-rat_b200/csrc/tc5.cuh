@@ -129,11 +129,19 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// ---------------------------------------------------------------------------------------------- layout helpers
-// byte offset of the 16-byte chunk (row r, chunk kc) of a K-major operand stored row-group-major:
-//   [r/8][kc][r%8][16 B]  =>  LBO = 128, SBO = KC * 128   (KC = 16-byte chunks per row)
-__host__ __device__ constexpr uint32_t kmajor_off(int r, int kc, int KC) {
-    return (uint32_t)(((r >> 3) * KC + kc) * 128 + (r & 7) * 16);
+// descriptor of K-step `kstep` (16 bf16 = two 16-byte chunks) of a chunk-major K-major operand with `rows` rows
+__device__ __forceinline__ uint64_t kdesc(uint32_t saddr, int rows, int kstep) {
+    return smem_desc(saddr + (uint32_t)(kstep * 2 * rows * 16), (uint32_t)(rows * 16), 128u);
 }
+
+// ---------------------------------------------------------------------------------------------- layout helpers
+// byte offset of the 16-byte chunk (row r, K-chunk kc) of a K-major operand with ROWS rows, stored CHUNK-major:
+//   [kc][row][16 B]   =>   8 consecutive rows of one chunk = one 128-byte core matrix,
+//                          SBO (next 8-row group) = 128, LBO (next K chunk) = ROWS * 16.
+// The offset is linear in the row: a warp task adds its base row once and keeps per-lane constants.
+__host__ __device__ constexpr uint32_t kmajor_off(int r, int kc, int ROWS) { return (uint32_t)((kc * ROWS + r) * 16); }
+// activation tiles always have 128 rows
+__host__ __device__ constexpr uint32_t toff(int r, int kc) { return (uint32_t)((kc * 128 + r) * 16); }
+constexpr uint32_t TILE_CHUNK = 128 * 16;      // byte stride between K chunks of a 128-row tile
 
 }  // namespace tc5
