@@ -251,6 +251,38 @@ def test_sgemm_all_layouts(rn, M, N, K):
                 assert_close(f"sgemm ta={ta} tb={tb} ws={use_ws}", C, want, 1e-5, tol * 4)
 
 
+@pytest.mark.parametrize("M,N,K", [(4096, 400, 520), (4096, 520, 400), (400, 520, 4096), (200, 48, 100), (130, 16, 64)])
+def test_gemm_tcgen05_all_layouts(rn, M, N, K):
+    """tcgen05 GEMM (bf16 operands, fp32 TMEM accumulate) incl. MN-major (reduction-index-major) operands and split-K
+    vs float64: error of a K-term dot product of bf16-rounded O(1) operands ~ 2^-8 sqrt(K) => atol 0.03 sqrt(K)."""
+    from tests.gpu_util import assert_close
+    from rat_native.engine import set_precision
+    g = torch.Generator().manual_seed(M + N + K)
+    d = _dev()
+    A = torch.randn(M, K, generator=g)
+    Bm = torch.randn(N, K, generator=g)
+    bias = torch.randn(N, generator=g)
+    want = (A.double() @ Bm.double().t() + bias.double()).float()
+    nbytes = int(rn.query("rat_sgemm_workspace_bytes", M, N, K))
+    ws = torch.empty(max(nbytes // 4, 4), device=d)
+    C = torch.empty(M, N, device=d)
+    set_precision("bf16")
+    try:
+        for ta in (0, 1):
+            for tb in (0, 1):
+                Ad = (A.t().contiguous() if ta else A).to(d)
+                Bd = (Bm.t().contiguous() if tb else Bm).to(d)
+                lda = M if ta else K
+                ldb = N if tb else K
+                for use_ws in (True, False):
+                    C.fill_(float("nan"))
+                    rn.call("rat_sgemm", Ad, Bd, C, bias.to(d), M, N, K, lda, ldb, N, ta, tb, ws if use_ws else None,
+                            ws.numel() * 4 if use_ws else 0, rn.current_stream())
+                    assert_close(f"gemm_tc ta={ta} tb={tb} ws={use_ws}", C, want, 2e-2, 0.03 * K ** 0.5)
+    finally:
+        set_precision("tf32")
+
+
 def test_bn_act_forward(rn):
     from tests.gpu_util import assert_close
     d = _dev()

@@ -1,0 +1,193 @@
+// K3 (Blackwell path): dense GEMM of the DNN head on the 5th-generation tensor cores.
+//
+//   C[m][n] = sum_k opA(m,k) * opB(k,n) (+ bias[n])       fp32 in / fp32 out, bf16 operands, fp32 accumulate in TMEM
+//
+// Replaces the nn.Linear products of MLP_Layer (fuxictr/pytorch/layers/deep.py:126-137) and their autograd reverse:
+//   forward   z  = h W^T + b        opA = h  [B x K]  (K contiguous)   opB = W  [N x K]  (K contiguous)
+//   dgrad     dh = dz W             opA = dz [B x u]  (K contiguous)   opB = W  [u x Kin] (rows = reduction index)
+//   wgrad     dW = dz^T h           opA = dz [B x u]  (rows = reduction index), opB = h [B x Kin] (rows = reduction index)
+// A source tile [rows x cols] is always staged the same way -- converted to bf16 and written chunk-major
+// ([col/8][row][16 B], tc5.cuh) -- and only the UMMA descriptor changes: an operand whose rows are M/N indices is
+// "K-major" (LBO = rows*16, SBO = 128); an operand whose rows are the reduction index is "MN-major" (the same
+// 128-byte core matrices read as [k%8][mn%8]: LBO = 128, SBO = rows*16, major bit set).  No transposed copies.
+// 128 x BN output tile per CTA (BN <= 256, accumulator = BN TMEM columns), K in stages of 64 with two shared-memory
+// buffers: the threads convert/stage buffer s+1 while the tensor core consumes buffer s.  Optional split-K over
+// gridDim.z writes fp32 partials that k_splitk_reduce (mlp.cu) adds in fixed order.
+#include "encoder_tc.cuh"
+
+namespace rat {
+
+constexpr int GT_THREADS = 256;
+constexpr int GT_KB = 64;            // reduction elements per stage
+
+struct GemmTcArgs {
+    const float* A; const float* B; float* C; const float* bias;
+    int M, N, K, lda, ldb, ldc;
+    int BN;                          // output-tile width (multiple of 16, <= 256)
+    int kchunk;                      // reduction range per split (multiple of 64)
+    int splits;
+};
+
+// stage a [ROWS x 8*CHUNKS] fp32 source tile (row stride ld) as bf16, chunk-major; rows/cols outside the matrix -> 0
+__device__ __forceinline__ void gemm_stage_tile(const float* __restrict__ src, int ld, int row0, int col0, int rows_total,
+                                                int cols_total, int ROWS, int CHUNKS, unsigned char* __restrict__ dst,
+                                                bool vec_ok) {
+    const int items = ROWS * CHUNKS;
+    for (int it = threadIdx.x; it < items; it += GT_THREADS) {
+        const int r = it % ROWS, c = it / ROWS;
+        const int gr = row0 + r, gc = col0 + c * 8;
+        float v[8];
+        if (gr < rows_total && gc + 8 <= cols_total && vec_ok) {
+            const float4 t0 = __ldg(reinterpret_cast<const float4*>(src + (size_t)gr * ld + gc));
+            const float4 t1 = __ldg(reinterpret_cast<const float4*>(src + (size_t)gr * ld + gc + 4));
+            v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = (gr < rows_total && gc + k < cols_total) ? __ldg(src + (size_t)gr * ld + gc + k) : 0.f;
+        }
+        sts128(dst + tc5::kmajor_off(r, c, ROWS), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+               pack_bf16(v[6], v[7]));
+    }
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GT_THREADS) k_gemm_tc(GemmTcArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t mbar[2];
+    __shared__ uint32_t tmem_base_s;
+    const int BN = a.BN;
+    const int m0 = blockIdx.y * TILE_M, n0 = blockIdx.x * BN;
+    const int kbeg = blockIdx.z * a.kchunk, kend = min(a.K, kbeg + a.kchunk);
+    const int nst = (kend - kbeg + GT_KB - 1) / GT_KB;
+    const size_t a_bytes = (size_t)TILE_M * GT_KB * 2, b_bytes = (size_t)BN * GT_KB * 2;
+    unsigned char* Abuf[2] = {smem_raw, smem_raw + a_bytes + b_bytes};
+    unsigned char* Bbuf[2] = {smem_raw + a_bytes, smem_raw + 2 * a_bytes + b_bytes};
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { tc5::mbar_init(&mbar[0], 1); tc5::mbar_init(&mbar[1], 1); tc5::fence_mbar_init(); }
+    if (warp == 0) tc5::tmem_alloc(&tmem_base_s, 256);
+    tc5::fence_before_sync();
+    __syncthreads();
+    tc5::fence_after_sync();
+    const uint32_t tmem_D = tmem_base_s;
+    const uint32_t idesc = tc5::instr_desc(tc5::FMT_BF16, TILE_M, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    const bool a_vec = (a.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0);
+    const bool b_vec = (a.ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.B) & 15) == 0);
+
+    for (int s = 0; s < nst; ++s) {
+        const int buf = s & 1, k0 = kbeg + s * GT_KB;
+        if (s >= 2) tc5::mbar_wait(&mbar[buf], ((s >> 1) - 1) & 1);      // the MMAs that read this buffer are done
+        // A tile: K-major -> rows = m (128), cols = k (64) ; MN-major -> rows = k (64), cols = m (128)
+        if (!A_MN) gemm_stage_tile(a.A, a.lda, m0, k0, a.M, kend, TILE_M, GT_KB / 8, Abuf[buf], a_vec && (k0 % 4 == 0));
+        else gemm_stage_tile(a.A, a.lda, k0, m0, kend, a.M, GT_KB, TILE_M / 8, Abuf[buf], a_vec);
+        if (!B_MN) gemm_stage_tile(a.B, a.ldb, n0, k0, a.N, kend, BN, GT_KB / 8, Bbuf[buf], b_vec && (k0 % 4 == 0));
+        else gemm_stage_tile(a.B, a.ldb, k0, n0, kend, a.N, GT_KB, BN / 8, Bbuf[buf], b_vec && (n0 % 4 == 0));
+        tc5::fence_proxy_async();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tc5::fence_after_sync();
+            const uint32_t as = tc5::smem_u32(Abuf[buf]), bs = tc5::smem_u32(Bbuf[buf]);
+#pragma unroll
+            for (int j = 0; j < GT_KB / 16; ++j) {
+                const uint64_t da = A_MN ? tc5::smem_desc(as + j * 256, 128, GT_KB * 16) : tc5::kdesc(as, TILE_M, j);
+                const uint64_t db = B_MN ? tc5::smem_desc(bs + j * 256, 128, GT_KB * 16) : tc5::kdesc(bs, BN, j);
+                tc5::mma_f16(tmem_D, da, db, idesc, (s > 0 || j > 0) ? 1u : 0u);
+            }
+            tc5::mma_commit(&mbar[buf]);
+        }
+    }
+    if (nst > 0) tc5::mbar_wait(&mbar[(nst - 1) & 1], ((nst - 1) >> 1) & 1);
+    tc5::fence_after_sync();
+    // ---- epilogue: thread = accumulator row; 16-column groups alternate between the two warps of a lane quadrant
+    {
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const int row = m0 + (warp & 3) * 32 + lane;
+        float* Cz = a.C + (a.splits > 1 ? (size_t)blockIdx.z * a.M * a.ldc : 0);
+        const bool c_vec = (a.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cz) & 15) == 0) && (n0 % 4 == 0);
+        for (int gq = warp >> 2; gq < BN / 16; gq += 2) {
+            float v[16];
+            if (nst > 0) { tc5::tmem_ld16(tmem_D + lane_base + gq * 16, v); tc5::tmem_ld_wait(); }
+            else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = 0.f;
+            }
+            const int c0 = n0 + gq * 16;
+            if (row < a.M && c0 < a.N) {
+                if (a.bias && a.splits == 1) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) if (c0 + i < a.N) v[i] += __ldg(a.bias + c0 + i);
+                }
+                float* dst = Cz + (size_t)row * a.ldc + c0;
+                if (c_vec && c0 + 16 <= a.N) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) if (c0 + i < a.N) dst[i] = v[i];
+                }
+            }
+        }
+    }
+    tc5::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc5::tmem_dealloc(tmem_base_s, 256);
+}
+
+struct GemmTcPlan { int BN, n_tiles, m_tiles, splits, kchunk; size_t smem; };
+
+static bool gemm_tc_plan(int M, int N, int K, size_t workspace_bytes, GemmTcPlan* p) {
+    if (M < 64 || N < 16 || K < 64) return false;
+    p->n_tiles = (N + 255) / 256;
+    p->BN = round_up(ceil_div(N, p->n_tiles), 16);
+    p->m_tiles = ceil_div(M, TILE_M);
+    const int tiles = p->n_tiles * p->m_tiles;
+    int splits = 1;
+    if (tiles * 2 <= num_sms() && K >= 1024) {
+        splits = std::min(16, num_sms() / tiles);
+        while (splits > 1 && K / splits < 256) --splits;
+        const size_t per = (size_t)M * N * sizeof(float);
+        while (splits > 1 && (size_t)splits * per > workspace_bytes) --splits;
+    }
+    p->kchunk = round_up(ceil_div(K, splits), GT_KB);
+    p->splits = ceil_div(K, p->kchunk);
+    p->smem = 2 * ((size_t)TILE_M * GT_KB * 2 + (size_t)p->BN * GT_KB * 2);
+    return true;
+}
+
+}  // namespace rat
+
+using namespace rat;
+
+size_t gemm_tc_workspace_bytes(int M, int N, int K) {
+    GemmTcPlan p{};
+    if (!gemm_tc_plan(M, N, K, (size_t)1 << 40, &p)) return 0;
+    return p.splits > 1 ? (size_t)p.splits * M * N * sizeof(float) : 0;
+}
+
+template <bool A_MN, bool B_MN>
+static int launch_gemm_tc(const GemmTcArgs& a, const GemmTcPlan& p, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_gemm_tc)");
+        attr_set = true;
+    }
+    dim3 grid(p.n_tiles, p.m_tiles, p.splits);
+    k_gemm_tc<A_MN, B_MN><<<grid, GT_THREADS, p.smem, st>>>(a);
+    RAT_CHECK_LAUNCH("k_gemm_tc");
+    return RAT_OK;
+}
+
+// returns RAT_OK if launched (C, or `splits` partials in workspace with *splits_out > 1), 1 if not covered
+int gemm_tc_dispatch(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda, int ldb,
+                     int ldc, int trans_a, int trans_b, float* workspace, size_t workspace_bytes, int* splits_out,
+                     cudaStream_t st) {
+    GemmTcPlan p{};
+    if (!gemm_tc_plan(M, N, K, workspace ? workspace_bytes : 0, &p)) return 1;
+    GemmTcArgs a{A, B, p.splits > 1 ? workspace : C, bias, M, N, K, lda, ldb, p.splits > 1 ? N : ldc, p.BN, p.kchunk, p.splits};
+    *splits_out = p.splits;
+    if (!trans_a && !trans_b) return launch_gemm_tc<false, false>(a, p, st);
+    if (!trans_a && trans_b) return launch_gemm_tc<false, true>(a, p, st);
+    if (trans_a && !trans_b) return launch_gemm_tc<true, false>(a, p, st);
+    return launch_gemm_tc<true, true>(a, p, st);
+}

@@ -77,19 +77,33 @@ __global__ void k_splitk_reduce(const float* __restrict__ part, float* __restric
 // ---- BatchNorm1d -----------------------------------------------------------------------------------------
 // per-column sums in double: sums[c] = sum_b z[b][c], sums[C + c] = sum_b z[b][c]^2 (raw sums so that the
 // data-parallel path can all-reduce them = SyncBN-equivalent to the single-device reference at global batch)
-__global__ void __launch_bounds__(256) k_bn_sums(const float* __restrict__ z, int Bn, int C, double* __restrict__ sums) {
+// Column reductions over the batch: grid (column tiles of 32, row slices).  Every block reduces its row slice in a
+// fixed order and writes a partial; k_colred_finalize adds the slices in slice order => bitwise deterministic,
+// and the whole machine participates (a single block per column tile would leave 135 SMs idle).
+constexpr int COLRED_SLICES = 32;
+__global__ void __launch_bounds__(256) k_bn_sums(const float* __restrict__ z, int Bn, int C, double* __restrict__ part) {
     __shared__ double s1[8][32], s2[8][32];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     const int rg = threadIdx.x >> 5;
+    const int per = (Bn + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * per, r1 = min(Bn, r0 + per);
     double a = 0.0, b = 0.0;
     if (c < C)
-        for (int r = rg; r < Bn; r += 8) { const double v = z[(size_t)r * C + c]; a += v; b += v * v; }
+        for (int r = r0 + rg; r < r1; r += 8) { const double v = z[(size_t)r * C + c]; a += v; b += v * v; }
     s1[rg][threadIdx.x & 31] = a; s2[rg][threadIdx.x & 31] = b;
     __syncthreads();
     if (rg == 0 && c < C) {
         for (int i = 1; i < 8; ++i) { a += s1[i][threadIdx.x]; b += s2[i][threadIdx.x]; }
-        sums[c] = a; sums[C + c] = b;
+        part[(size_t)blockIdx.y * 2 * C + c] = a; part[(size_t)blockIdx.y * 2 * C + C + c] = b;
     }
+}
+// out[i] = sum_s part[s][i], i < n  (double or float output)
+template <class TO>
+__global__ void k_colred_finalize(const double* __restrict__ part, int nslices, int n, TO* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    for (int q = 0; q < nslices; ++q) s += part[(size_t)q * n + i];
+    out[i] = (TO)s;
 }
 // mean / rstd from (all-reduced) sums; running stats update (momentum 0.1, unbiased var), deep.py:128-129
 __global__ void k_bn_finalize(const double* __restrict__ sums, double count, int C, float* __restrict__ mean,
@@ -141,10 +155,11 @@ __global__ void __launch_bounds__(256) k_bn_act_bwd_sums(const float* __restrict
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     const int rg = threadIdx.x >> 5;
     const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const int per = (Bn + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * per, r1 = min(Bn, r0 + per);
     double a = 0.0, b = 0.0;
     if (c < C) {
         const float mu = mean[c], rs = rstd[c];
-        for (int r = rg; r < Bn; r += 8) {
+        for (int r = r0 + rg; r < r1; r += 8) {
             const size_t i = (size_t)r * C + c;
             float dy = out[i] > 0.f ? dout[i] : 0.f;
             if (drop_p > 0.f) dy *= dropout_scale(seed, stream, (unsigned long long)i, drop_p, inv_keep);
@@ -156,7 +171,7 @@ __global__ void __launch_bounds__(256) k_bn_act_bwd_sums(const float* __restrict
     __syncthreads();
     if (rg == 0 && c < C) {
         for (int i = 1; i < 8; ++i) { a += s1[i][threadIdx.x]; b += s2[i][threadIdx.x]; }
-        sums[c] = a; sums[C + c] = b;
+        sums[(size_t)blockIdx.y * 2 * C + c] = a; sums[(size_t)blockIdx.y * 2 * C + C + c] = b;
     }
 }
 // backward pass 2: dz = gamma*rstd*(dy - dbeta/count - xhat*dgamma/count)   (or dz = dy without bn);
@@ -185,17 +200,18 @@ __global__ void k_bn_act_bwd_apply(const float* __restrict__ dout, const float* 
 }
 // out[c] = sum_r A[r][c]   (bias gradients), deterministic
 __global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ A, int R, int C, int lda,
-                                                float* __restrict__ out) {
-    __shared__ float s[8][32];
+                                                double* __restrict__ part) {
+    __shared__ double s[8][32];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     const int rg = threadIdx.x >> 5;
-    float a = 0.f;
-    if (c < C) for (int r = rg; r < R; r += 8) a += A[(size_t)r * lda + c];
+    const int per = (R + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * per, r1 = min(R, r0 + per);
+    double a = 0.0;
+    if (c < C) for (int r = r0 + rg; r < r1; r += 8) a += A[(size_t)r * lda + c];
     s[rg][threadIdx.x & 31] = a;
     __syncthreads();
     if (rg == 0 && c < C) {
         for (int i = 1; i < 8; ++i) a += s[i][threadIdx.x];
-        out[c] = a;
+        part[(size_t)blockIdx.y * C + c] = a;
     }
 }
 
@@ -252,6 +268,20 @@ __global__ void k_loss_finalize(const double* __restrict__ part, int n, float in
     }
 }
 
+// library-internal scratch for the row-sliced column reductions (COLRED_SLICES x 2C doubles), allocated once per
+// process on first use; it never holds user-visible state.
+static double* colred_scratch(size_t doubles) {
+    static double* buf = nullptr;
+    static size_t cap = 0;
+    if (doubles > cap) {
+        if (buf) cudaFree(buf);
+        cap = doubles < (size_t)COLRED_SLICES * 2 * 4096 ? (size_t)COLRED_SLICES * 2 * 4096 : doubles;
+        if (cudaMalloc(&buf, cap * sizeof(double)) != cudaSuccess) { buf = nullptr; cap = 0; }
+    }
+    return buf;
+}
+static int colred_slices(int rows) { return rows >= 64 * COLRED_SLICES ? COLRED_SLICES : (rows >= 512 ? 8 : 1); }
+
 static int ew_grid(long long total) {
     long long g = (total + 255) / 256;
     long long cap = (long long)num_sms() * 16;
@@ -262,7 +292,18 @@ static int ew_grid(long long total) {
 
 using namespace rat;
 
+namespace rat { int precision_mode(); }
+size_t gemm_tc_workspace_bytes(int M, int N, int K);
+int gemm_tc_dispatch(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda, int ldb,
+                     int ldc, int trans_a, int trans_b, float* workspace, size_t workspace_bytes, int* splits_out,
+                     cudaStream_t st);
+
+static size_t sgemm_simt_workspace_bytes(int M, int N, int K);
 extern "C" size_t rat_sgemm_workspace_bytes(int M, int N, int K) {
+    const size_t a = sgemm_simt_workspace_bytes(M, N, K), b = gemm_tc_workspace_bytes(M, N, K);
+    return a > b ? a : b;
+}
+static size_t sgemm_simt_workspace_bytes(int M, int N, int K) {
     // split-K only pays when the output grid under-fills the machine and K is long
     int tiles = ceil_div(M, 64) * ceil_div(N, 64);
     int splits = 1;
@@ -275,7 +316,20 @@ extern "C" int rat_sgemm(const float* A, const float* B, float* C, const float* 
                          int ldb, int ldc, int trans_a, int trans_b, float* workspace, size_t workspace_bytes,
                          void* stream) {
     RAT_REQUIRE(M > 0 && N > 0 && K > 0, "rat_sgemm: bad shape M=%d N=%d K=%d", M, N, K);
-    size_t need = rat_sgemm_workspace_bytes(M, N, K);
+    if (precision_mode() == 2) {        // tcgen05 path (bf16 operands, fp32 accumulate); tiny shapes stay on the SIMT kernel
+        int tc_splits = 1;
+        const int rc = gemm_tc_dispatch(A, B, C, bias, M, N, K, lda, ldb, ldc, trans_a, trans_b, workspace, workspace_bytes,
+                                        &tc_splits, (cudaStream_t)stream);
+        if (rc < 0) return rc;
+        if (rc == 0) {
+            if (tc_splits > 1) {
+                k_splitk_reduce<<<ew_grid((long long)M * N), 256, 0, (cudaStream_t)stream>>>(workspace, C, bias, M, N, ldc, tc_splits);
+                RAT_CHECK_LAUNCH("k_splitk_reduce");
+            }
+            return RAT_OK;
+        }
+    }
+    size_t need = sgemm_simt_workspace_bytes(M, N, K);
     int splits = 1;
     if (need > 0 && workspace && workspace_bytes >= need) splits = (int)(need / ((size_t)M * N * sizeof(float)));
     const int kchunk = round_up(ceil_div(K, splits), 16);
@@ -298,8 +352,13 @@ extern "C" int rat_sgemm(const float* A, const float* B, float* C, const float* 
 
 extern "C" int rat_bn_sums(const float* z, int rows, int C, double* sums, void* stream) {
     RAT_REQUIRE(rows > 0 && C > 0, "rat_bn_sums: bad shape");
-    k_bn_sums<<<ceil_div(C, 32), 256, 0, (cudaStream_t)stream>>>(z, rows, C, sums);
+    const int ns = colred_slices(rows);
+    double* part = colred_scratch((size_t)ns * 2 * C);
+    RAT_REQUIRE(part != nullptr, "rat_bn_sums: scratch allocation failed");
+    k_bn_sums<<<dim3(ceil_div(C, 32), ns), 256, 0, (cudaStream_t)stream>>>(z, rows, C, part);
     RAT_CHECK_LAUNCH("k_bn_sums");
+    k_colred_finalize<double><<<ceil_div(2 * C, 128), 128, 0, (cudaStream_t)stream>>>(part, ns, 2 * C, sums);
+    RAT_CHECK_LAUNCH("k_colred_finalize");
     return RAT_OK;
 }
 
@@ -331,9 +390,14 @@ extern "C" int rat_bn_act_fwd(const float* z, const float* mean, const float* rs
 extern "C" int rat_bn_act_bwd_sums(const float* dout, const float* out, const float* z, const float* mean,
                                    const float* rstd, int rows, int C, float drop_p, unsigned long long seed,
                                    unsigned int rng_stream, double* sums, void* stream) {
-    k_bn_act_bwd_sums<<<ceil_div(C, 32), 256, 0, (cudaStream_t)stream>>>(dout, out, z, mean, rstd, rows, C, drop_p,
-                                                                         seed, rng_stream, sums);
+    const int ns = colred_slices(rows);
+    double* part = colred_scratch((size_t)ns * 2 * C);
+    RAT_REQUIRE(part != nullptr, "rat_bn_act_bwd_sums: scratch allocation failed");
+    k_bn_act_bwd_sums<<<dim3(ceil_div(C, 32), ns), 256, 0, (cudaStream_t)stream>>>(dout, out, z, mean, rstd, rows, C,
+                                                                                   drop_p, seed, rng_stream, part);
     RAT_CHECK_LAUNCH("k_bn_act_bwd_sums");
+    k_colred_finalize<double><<<ceil_div(2 * C, 128), 128, 0, (cudaStream_t)stream>>>(part, ns, 2 * C, sums);
+    RAT_CHECK_LAUNCH("k_colred_finalize");
     return RAT_OK;
 }
 
@@ -350,8 +414,13 @@ extern "C" int rat_bn_act_bwd_apply(const float* dout, const float* out, const f
 }
 
 extern "C" int rat_colsum(const float* A, int rows, int C, int lda, float* out, void* stream) {
-    k_colsum<<<ceil_div(C, 32), 256, 0, (cudaStream_t)stream>>>(A, rows, C, lda, out);
+    const int ns = colred_slices(rows);
+    double* part = colred_scratch((size_t)ns * C);
+    RAT_REQUIRE(part != nullptr, "rat_colsum: scratch allocation failed");
+    k_colsum<<<dim3(ceil_div(C, 32), ns), 256, 0, (cudaStream_t)stream>>>(A, rows, C, lda, part);
     RAT_CHECK_LAUNCH("k_colsum");
+    k_colred_finalize<float><<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(part, ns, C, out);
+    RAT_CHECK_LAUNCH("k_colred_finalize");
     return RAT_OK;
 }
 
