@@ -305,6 +305,8 @@ def _golden_train(rn, name):
     # step 1, split so the pre-clip gradients can be inspected
     eng.rng_step += 1
     ws["dact"].zero_()
+    if ws.get("dact_c") is not None:        # RAT_m1: only token 0 of every row receives gradient from the head
+        ws["dact_c"].zero_()
     eng.forward_ids(ws, B, T, training=True, inv_count=1.0 / B)
     eng.check_errors()
     eng.backward(ws, B, T)

@@ -27,3 +27,15 @@ tot = sum(v[0] for v in agg.values()); tots = sum(v[1] for v in agg.values())
 print(f"total warp-inst {tot:,}  samples {tots:,}")
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
     print(f"{v[0]/max(tot,1)*100:5.1f}% inst {v[1]/max(tots,1)*100:5.1f}% smp  {k[0]}:{k[1]:<5d} | {v[2].strip()[:100]}")
+
+# optional phase grouping: ncu_lines.py <rep> <regex> <skip> <top> file:lo-hi=name ...
+groups = [g for g in sys.argv[5:] if "=" in g]
+if groups:
+    print("--- phase groups (inst %, sample %)")
+    for gspec in groups:
+        rng, name = gspec.split("=")
+        f, lh = rng.split(":")
+        lo, hi = (int(x) for x in lh.split("-"))
+        gi = sum(v[0] for k, v in agg.items() if k[0] == f and lo <= k[1] <= hi)
+        gs = sum(v[1] for k, v in agg.items() if k[0] == f and lo <= k[1] <= hi)
+        print(f"  {name:28s} {gi/max(tot,1)*100:5.1f}% inst  {gs/max(tots,1)*100:5.1f}% smp")

@@ -3,6 +3,7 @@
 //
 // Round-1 implementation: fp32 SIMT shared-memory-tiled GEMM (exact fp32 parity anchor).  The tcgen05/TMEM
 // bf16 variant of the same entry point is planned on top of this (see DESIGN.md "K3").
+#include <algorithm>
 #include "common.cuh"
 #include "../../include/rat_b200.h"
 
@@ -71,6 +72,46 @@ __global__ void k_splitk_reduce(const float* __restrict__ part, float* __restric
         float s = 0.f;
         for (int z = 0; z < splits; ++z) s += part[((size_t)z * M + m) * N + n];   // fixed order: deterministic
         C[(size_t)m * ldc + n] = s + (bias ? bias[n] : 0.f);
+    }
+}
+
+// ---- degenerate GEMM shapes of the head (N = 1 logit column, M = 1 gradient row, K = 1 outer product) --------------
+// C[m] = sum_k opA(m,k) * b_k + bias   : one warp per output row (TA = 0: A row contiguous)
+__global__ void __launch_bounds__(256) k_gemv_rows(const float* __restrict__ A, const float* __restrict__ B,
+                                                   float* __restrict__ C, const float* __restrict__ bias, int M, int K,
+                                                   int lda, long long b_stride, int ldc) {
+    const int lane = threadIdx.x & 31;
+    for (int m = blockIdx.x * 8 + (threadIdx.x >> 5); m < M; m += gridDim.x * 8) {
+        const float* a = A + (size_t)m * lda;
+        float s = 0.f;
+        for (int k = lane; k < K; k += 32) s = fmaf(a[k], __ldg(B + (size_t)k * b_stride), s);
+        s = warp_sum(s);
+        if (lane == 0) C[(size_t)m * ldc] = s + (bias ? bias[0] : 0.f);
+    }
+}
+// part[slice][n] = sum_{k in slice} a_k * B[k*ldb + n]   (M = 1, B rows indexed by the reduction index)
+__global__ void __launch_bounds__(256) k_wcolsum(const float* __restrict__ a, long long a_stride, const float* __restrict__ B,
+                                                 int K, int N, int ldb, double* __restrict__ part) {
+    __shared__ double s[8][32];
+    const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int rg = threadIdx.x >> 5;
+    const int per = (K + gridDim.y - 1) / gridDim.y, k0 = blockIdx.y * per, k1 = min(K, k0 + per);
+    double acc = 0.0;
+    if (n < N) for (int k = k0 + rg; k < k1; k += 8) acc += (double)(a[(size_t)k * a_stride] * B[(size_t)k * ldb + n]);
+    s[rg][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (rg == 0 && n < N) {
+        for (int i = 1; i < 8; ++i) acc += s[i][threadIdx.x];
+        part[(size_t)blockIdx.y * N + n] = acc;
+    }
+}
+// C[m][n] = a_m * b_n (+ bias[n])   (K = 1)
+__global__ void k_outer(const float* __restrict__ a, long long a_stride, const float* __restrict__ b, long long b_stride,
+                        float* __restrict__ C, const float* __restrict__ bias, int M, int N, int ldc) {
+    const long long total = (long long)M * N;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int m = (int)(i / N), n = (int)(i % N);
+        C[(size_t)m * ldc + n] = a[(size_t)m * a_stride] * __ldg(b + (size_t)n * b_stride) + (bias ? bias[n] : 0.f);
     }
 }
 
@@ -316,6 +357,27 @@ extern "C" int rat_sgemm(const float* A, const float* B, float* C, const float* 
                          int ldb, int ldc, int trans_a, int trans_b, float* workspace, size_t workspace_bytes,
                          void* stream) {
     RAT_REQUIRE(M > 0 && N > 0 && K > 0, "rat_sgemm: bad shape M=%d N=%d K=%d", M, N, K);
+    cudaStream_t st0 = (cudaStream_t)stream;
+    if (N == 1 && !trans_a && M >= 64) {                    // logit column: C[m] = A[m,:] . b
+        k_gemv_rows<<<std::min(ceil_div(M, 8), num_sms() * 8), 256, 0, st0>>>(A, B, C, bias, M, K, lda, trans_b ? ldb : 1, ldc);
+        RAT_CHECK_LAUNCH("k_gemv_rows");
+        return RAT_OK;
+    }
+    if (M == 1 && trans_b && K >= 64 && !bias) {                     // gradient row: C[n] = sum_k a_k B[k,n]
+        const int ns = colred_slices(K);
+        double* part = colred_scratch((size_t)ns * N);
+        RAT_REQUIRE(part != nullptr, "rat_sgemm: scratch allocation failed");
+        k_wcolsum<<<dim3(ceil_div(N, 32), ns), 256, 0, st0>>>(A, trans_a ? lda : 1, B, K, N, ldb, part);
+        RAT_CHECK_LAUNCH("k_wcolsum");
+        k_colred_finalize<float><<<ceil_div(N, 128), 128, 0, st0>>>(part, ns, N, C);
+        RAT_CHECK_LAUNCH("k_colred_finalize");
+        return RAT_OK;
+    }
+    if (K == 1) {                                           // outer product
+        k_outer<<<ew_grid((long long)M * N), 256, 0, st0>>>(A, trans_a ? 1 : lda, B, trans_b ? 1 : ldb, C, bias, M, N, ldc);
+        RAT_CHECK_LAUNCH("k_outer");
+        return RAT_OK;
+    }
     if (precision_mode() == 2) {        // tcgen05 path (bf16 operands, fp32 accumulate); tiny shapes stay on the SIMT kernel
         int tc_splits = 1;
         const int rc = gemm_tc_dispatch(A, B, C, bias, M, N, K, lda, ldb, ldc, trans_a, trans_b, workspace, workspace_bytes,
