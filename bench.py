@@ -52,6 +52,12 @@ def parse():
     return ap.parse_args()
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/),
+# kkbox shape, B=4096, K=5.  The 126 MB L2 absorbs most of the 55 MB block writes, so DRAM traffic is BELOW the
+# algorithmic bytes for these kernels (no wasted re-reads).
+NCU_TRAFFIC = {"attn_bwd": 129.3e6, "gather": 19.9e6}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -234,24 +240,43 @@ def run_ours(a):
     def per_call_ms(name):
         n, ms = prof[name]
         return ms / n
-    # dominant kernel: fused attention backward (2 per block: intra S=N, cross S=T) -- FLOP-bound on the FP32 pipe
+    # dominant kernel: fused attention backward (2 per RAT block: intra S=N, cross S=T).  It is GEMM-shaped work on
+    # the tensor cores (tcgen05 projections + mma.sync softmax core), so it is reported against the bf16 tensor peak;
+    # the same launch is also shown against the HBM roofline (x + dout read, dx written, base = dout hits L2).
     attn_bwd_flops = rows_tok * (attn_flops_per_token(D, I, N) + attn_flops_per_token(D, I, T)) / 2 * 2.75
-    ach_tf = attn_bwd_flops / (per_call_ms("rat_attn_bwd") * 1e-3) / 1e12
-    roofline = {"kernel": "k_attn_bwd (+k_reduce_partials)", "bound": "tensor", "achieved": round(ach_tf, 3),
+    ab_ms = per_call_ms("rat_attn_bwd")
+    ach_tf = attn_bwd_flops / (ab_ms * 1e-3) / 1e12
+    ab_bytes = rows_tok * D * 4 * 3
+    tc_mode = a.precision == "bf16"
+    roofline = {"kernel": "k_attn_bwd_tc (+k_reduce_attn_tc)" if tc_mode else "k_attn_bwd (+k_reduce_attn)",
+                "bound": "tensor", "achieved": round(ach_tf, 3),
                 "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": round(ach_tf / pk["tf_sustained"], 5),
-                "traffic": None, "peak_source": pk["src"] + " bf16 dense (sustained)",
-                "note": "round-1 kernel runs fp32 FFMA on the SIMT pipe (nominal ~75 TFLOP/s fp32), not tcgen05 yet; "
-                        "algorithmic FLOPs = 2.75x forward (recompute + dgrad + wgrad)"}
+                "traffic": NCU_TRAFFIC.get("attn_bwd") if tc_mode else None,
+                "peak_source": pk["src"] + " bf16 dense (sustained)", "avg_launch_ms": round(ab_ms, 4),
+                "flops_per_launch": attn_bwd_flops,
+                "hbm_view": {"bytes_per_launch": ab_bytes, "achieved_gbs": round(ab_bytes / (ab_ms * 1e-3) / 1e9, 1),
+                             "frac_of_hbm_peak": round(ab_bytes / (ab_ms * 1e-3) / 1e9 / pk["hbm"], 4)},
+                "note": "algorithmic FLOPs = 2.75x forward (recompute + dgrad + wgrad); issue/latency-bound: the softmax-"
+                        "backward core runs ~380 SASS instructions per (sequence, head) task around 12 mma.sync, see "
+                        "profiles/ and DESIGN.md section 3"}
     gb = B * gather_bytes_per_sample(K, L, F, D)
     g_ms = per_call_ms("rat_gather_fwd")
-    roofline_gather = {"kernel": "k_gather", "bound": "hbm", "achieved": round(gb / (g_ms * 1e-3) / 1e9, 1),
+    roofline_gather = {"kernel": "k_gather_rows", "bound": "hbm", "achieved": round(gb / (g_ms * 1e-3) / 1e9, 1),
                        "peak": pk["hbm"], "unit": "GB/s", "frac": round(gb / (g_ms * 1e-3) / 1e9 / pk["hbm"], 4),
-                       "traffic": None, "bytes_per_launch": gb, "peak_source": pk["src"]}
+                       "traffic": NCU_TRAFFIC.get("gather"), "bytes_per_launch": gb, "peak_source": pk["src"],
+                       "avg_launch_ms": round(g_ms, 4)}
+    sc_ms = per_call_ms("rat_emb_scatter_reduce")
+    sc_bytes = B * T * N * D * 4 + B * T * L * 8 * 2 + B * T * L * D * 4
+    roofline_scatter = {"kernel": "rat_emb_scatter_reduce (keys + radix sort + segment reduce)", "bound": "hbm",
+                        "achieved": round(sc_bytes / (sc_ms * 1e-3) / 1e9, 1), "peak": pk["hbm"], "unit": "GB/s",
+                        "frac": round(sc_bytes / (sc_ms * 1e-3) / 1e9 / pk["hbm"], 4), "traffic": None,
+                        "bytes_per_launch": sc_bytes, "peak_source": pk["src"], "avg_launch_ms": round(sc_ms, 4)}
     P = model._engine.store.total
     ad_ms = per_call_ms("rat_adam_step")
     roofline_adam = {"kernel": "k_adam", "bound": "hbm", "achieved": round(P * 32 / (ad_ms * 1e-3) / 1e9, 1),
                      "peak": pk["hbm"], "unit": "GB/s", "frac": round(P * 32 / (ad_ms * 1e-3) / 1e9 / pk["hbm"], 4),
-                     "traffic": None, "bytes_per_launch": P * 32, "peak_source": pk["src"]}
+                     "traffic": None, "bytes_per_launch": P * 32, "peak_source": pk["src"],
+                     "avg_launch_ms": round(ad_ms, 4)}
 
     if rank != 0:
         return
@@ -274,7 +299,8 @@ def run_ours(a):
                           "d2h_bytes_per_step": B * 4}},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": roofline, "roofline_gather": roofline_gather, "roofline_adam": roofline_adam,
+        "roofline": roofline, "roofline_gather": roofline_gather, "roofline_scatter": roofline_scatter,
+        "roofline_adam": roofline_adam,
         "kernels": kernels,
         "reference_derived": {"note": "BASELINE.md derived (not published) reference-GPU numbers, unknown GPU, incl. dataloader",
                               "train_samples_per_s": {"kkbox": 8800, "ml": 52000, "tmall": 3300}[S],
