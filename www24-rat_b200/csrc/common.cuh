@@ -66,14 +66,40 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
     }
     return ctr;
 }
+// Dropout masks: ONE Philox4x32-10 call yields eight 16-bit uniforms = the keep decisions of the eight consecutive
+// elements [8c, 8c+8) (counter c = e >> 3).  Element e is dropped iff its 16-bit lane < round(p * 65536).
+// RAT_DROPOUT_PHILOX=1 selects Philox4x32-10 (about 100 instructions per call); the default is a keyed 32-bit integer
+// hash (lowbias32, 2 multiplies + 3 xor-shifts per word) of the counter -- dropout only needs independent
+// Bernoulli(p) decisions that the forward and backward kernels can both regenerate from (seed, stream, element).
+#ifndef RAT_DROPOUT_PHILOX
+#define RAT_DROPOUT_PHILOX 0
+#endif
+__device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ uint4 dropout_bits8(unsigned long long seed, uint32_t stream, unsigned long long c) {
+#if RAT_DROPOUT_PHILOX
+    return philox4x32(make_uint4((uint32_t)c, (uint32_t)(c >> 32), stream, 0u),
+                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+#else
+    const uint32_t key = lowbias32((uint32_t)seed ^ lowbias32((uint32_t)(seed >> 32) + 0x9E3779B9u * (stream + 1u)));
+    const uint32_t hi = lowbias32((uint32_t)(c >> 30) ^ key);          // c*4 spans 34+ bits: fold the high part
+    const uint32_t b = (uint32_t)c << 2;
+    return make_uint4(lowbias32((b + 0u) ^ hi), lowbias32((b + 1u) ^ hi), lowbias32((b + 2u) ^ hi), lowbias32((b + 3u) ^ hi));
+#endif
+}
+__device__ __forceinline__ uint32_t dropout_threshold(float p) { return (uint32_t)(p * 65536.0f + 0.5f); }
+// lane j (0..7) of the 128-bit Philox output
+__device__ __forceinline__ uint32_t dropout_lane16(const uint4& r, int j) {
+    const uint32_t w = (j >> 1) == 0 ? r.x : (j >> 1) == 1 ? r.y : (j >> 1) == 2 ? r.z : r.w;
+    return (j & 1) ? (w >> 16) : (w & 0xffffu);
+}
 // keep-mask scale for flattened element index e: 0 (dropped) or 1/(1-p)
 __device__ __forceinline__ float dropout_scale(unsigned long long seed, uint32_t stream, unsigned long long e,
                                                float p, float inv_keep) {
-    uint4 r = philox4x32(make_uint4((uint32_t)(e >> 2), (uint32_t)(e >> 34), stream, 0u),
-                         make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-    uint32_t w = (e & 3) == 0 ? r.x : (e & 3) == 1 ? r.y : (e & 3) == 2 ? r.z : r.w;
-    float u = (float)(w >> 8) * (1.0f / 16777216.0f);
-    return u < p ? 0.0f : inv_keep;
+    const uint4 r = dropout_bits8(seed, stream, e >> 3);
+    return dropout_lane16(r, (int)(e & 7)) < dropout_threshold(p) ? 0.0f : inv_keep;
 }
 #endif
 

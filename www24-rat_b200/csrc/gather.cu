@@ -144,39 +144,47 @@ __global__ void __launch_bounds__(256) k_gather(GatherArgs a) {
 }
 
 // ---- K1 (fast path): one WARP per (b,t) row of the block ---------------------------------------------------
-// Lane l < L owns column l of the id matrix: it validates id[bt][l] once and keeps the table-row offset in a
-// register; every lane then produces vector chunks c = lane, lane+32, ... of the row's N*D contiguous output
-// floats.  Row offsets travel by shuffle, so all table-row loads of a lane are INDEPENDENT (CH*maxw 128-bit loads
-// in flight per lane) and the block row is written as one contiguous, fully coalesced 128-bit stream.
-// Same arithmetic as k_gather (left-to-right sum-pool, same philox element index): results are bit-identical.
-template <int VW, int CH>
-__global__ void __launch_bounds__(256) k_gather_rows(GatherArgs a) {
+// Lane l < L owns column l of the id matrix: it validates id[bt][l] once and keeps the table row in a register;
+// every lane then produces PAIRS of adjacent vector chunks (2*VW contiguous floats = 32 B for VW = 4) of the row's
+// N*D contiguous output floats.  Table rows travel by shuffle, so all row loads of a lane are INDEPENDENT and the
+// block row is written as one contiguous, fully coalesced stream.  Extra sum-pool terms (sequence fields) are only
+// visited by the pair slots that contain a sequence token (warp-uniform test).  With VW = 4 a chunk pair is exactly
+// the eight elements of one Philox call (dropout).  Same arithmetic as k_gather (left-to-right sum-pool, same mask).
+template <int VW, int PS>
+__global__ void __launch_bounds__(256, 3) k_gather_rows(GatherArgs a) {
     const int lane = threadIdx.x & 31;
-    int maxw = lane < a.F ? a.field_width[lane] : 0;           // F <= L <= 32 on this path
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) maxw = max(maxw, __shfl_xor_sync(0xffffffffu, maxw, o));
     const int N = a.F + 1, DV = a.D / VW, NC = N * DV;
-    const long long nrows = (long long)a.B * a.T;
-    const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+    const int nrows = a.B * a.T;
+    const int wstride = gridDim.x * (blockDim.x >> 5);
     const float inv_keep = a.drop_p > 0.f ? 1.0f / (1.0f - a.drop_p) : 1.0f;
+    const uint32_t thr = dropout_threshold(a.drop_p);
     const int my_off = lane < a.L ? a.col_off[lane] : 0;
     const int my_vocab = lane < a.L ? a.col_vocab[lane] : 1;
     // per-lane chunk geometry is row independent: token n, vector dv, first column c0 and width w of its field
-    int cn[CH], cdv[CH], cc0[CH], cw[CH];
+    int cn[PS][2], cdv[PS][2], cc0[PS][2], cw[PS][2], slotw[PS];
 #pragma unroll
-    for (int i = 0; i < CH; ++i) {
-        const int c = lane + 32 * i;
-        cn[i] = c < NC ? c / DV : -1;
-        cdv[i] = c < NC ? c - cn[i] * DV : 0;
-        cc0[i] = 0; cw[i] = 0;
-        if (cn[i] > 0) { cc0[i] = a.field_col0[cn[i] - 1]; cw[i] = a.field_width[cn[i] - 1]; }
+    for (int i = 0; i < PS; ++i) {
+        int mw = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int c = 2 * (lane + 32 * i) + h;
+            cn[i][h] = c < NC ? c / DV : -1;
+            cdv[i][h] = c < NC ? c - cn[i][h] * DV : 0;
+            cc0[i][h] = 0; cw[i][h] = 0;
+            if (cn[i][h] > 0) { cc0[i][h] = a.field_col0[cn[i][h] - 1]; cw[i][h] = a.field_width[cn[i][h] - 1]; }
+            mw = max(mw, cw[i][h]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mw = max(mw, __shfl_xor_sync(0xffffffffu, mw, o));
+        slotw[i] = mw;                                           // warp-uniform: widest field touched by pair slot i
     }
-    for (long long bt = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); bt < nrows; bt += wstride) {
-        const int t = (int)(bt % a.T);
-        const long long b = bt / a.T;
+    int bt = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int t = bt % a.T, b = bt / a.T;
+    const int dt = wstride % a.T, db = wstride / a.T;
+    for (; bt < nrows; bt += wstride) {
         int id = 0;
         if (lane < a.L) {
-            id = __ldg(a.ids + bt * a.L + lane);
+            id = __ldg(a.ids + (size_t)bt * a.L + lane);
             if (id < 0 || id >= my_vocab) { atomicOr(a.err, 1); id = 0; }
         }
         const int row = my_off + id;                         // table row of column `lane`
@@ -194,49 +202,79 @@ __global__ void __launch_bounds__(256) k_gather_rows(GatherArgs a) {
             }
             if (lane == 0) a.lr_out[b] = tot;
         }
-        float val[CH][VW];
+        float val[PS][2][VW];
 #pragma unroll
-        for (int i = 0; i < CH; ++i) {
+        for (int i = 0; i < PS; ++i)
 #pragma unroll
-            for (int k = 0; k < VW; ++k) val[i][k] = 0.f;
-            if (cn[i] == 0) vload<VW>(a.label_W + (long long)lab * a.D + cdv[i] * VW, val[i]);
-        }
-        for (int j = 0; j < maxw; ++j) {
+            for (int h = 0; h < 2; ++h) {
 #pragma unroll
-            for (int i = 0; i < CH; ++i) {
-                const int src = min(cc0[i] + j, 31);
-                const int r = __shfl_sync(0xffffffffu, row, src);
-                if (j < cw[i]) {
-                    float rv[VW];
-                    vload<VW>(a.emb_W + (long long)r * a.D + cdv[i] * VW, rv);
+                for (int k = 0; k < VW; ++k) val[i][h][k] = 0.f;
+                if (cn[i][h] == 0) vload<VW>(a.label_W + (size_t)lab * a.D + cdv[i][h] * VW, val[i][h]);
+                const int r = __shfl_sync(0xffffffffu, row, min(cc0[i][h], 31));
+                if (cw[i][h] > 0) vload<VW>(a.emb_W + (size_t)r * a.D + cdv[i][h] * VW, val[i][h]);
+            }
 #pragma unroll
-                    for (int k = 0; k < VW; ++k) val[i][k] = (j == 0) ? rv[k] : val[i][k] + rv[k];
+        for (int i = 0; i < PS; ++i)
+            for (int j = 1; j < slotw[i]; ++j)               // sum-pool terms 1.. of sequence fields (rare slots only)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int r = __shfl_sync(0xffffffffu, row, min(cc0[i][h] + j, 31));
+                    if (j < cw[i][h]) {
+                        float rv[VW];
+                        vload<VW>(a.emb_W + (size_t)r * a.D + cdv[i][h] * VW, rv);
+#pragma unroll
+                        for (int k = 0; k < VW; ++k) val[i][h][k] += rv[k];
+                    }
                 }
+        float* out_row = a.block + (size_t)bt * NC * VW;
+#pragma unroll
+        for (int i = 0; i < PS; ++i) {
+            const int c0 = 2 * (lane + 32 * i);
+            uint4 bits = make_uint4(0u, 0u, 0u, 0u);
+            const unsigned long long e0 = ((unsigned long long)bt * NC + c0) * VW;
+            if (a.drop_p > 0.f && cn[i][0] >= 0) bits = dropout_bits8(a.seed, a.stream, e0 >> 3);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (cn[i][h] < 0) continue;
+                if (t == 0 && a.x_emb && cn[i][h] > 0)
+                    vstore<VW>(a.x_emb + ((size_t)b * a.F + (cn[i][h] - 1)) * a.D + cdv[i][h] * VW, val[i][h]);
+                if (a.drop_p > 0.f) {
+                    const unsigned long long eh = e0 + (unsigned long long)h * VW;
+                    uint4 bh = bits;
+                    if ((eh >> 3) != (e0 >> 3)) bh = dropout_bits8(a.seed, a.stream, eh >> 3);   // never for VW=4, even NC
+#pragma unroll
+                    for (int k = 0; k < VW; ++k)
+                        val[i][h][k] *= dropout_lane16(bh, (int)((eh + k) & 7)) < thr ? 0.0f : inv_keep;
+                }
+                vstore<VW>(out_row + (size_t)(c0 + h) * VW, val[i][h]);
             }
         }
-        float* out_row = a.block + bt * (long long)NC * VW;
-#pragma unroll
-        for (int i = 0; i < CH; ++i) {
-            if (cn[i] < 0) continue;
-            if (t == 0 && a.x_emb && cn[i] > 0)
-                vstore<VW>(a.x_emb + (b * a.F + (cn[i] - 1)) * a.D + cdv[i] * VW, val[i]);
-            if (a.drop_p > 0.f) {
-                const unsigned long long e0 = ((unsigned long long)bt * NC + (lane + 32 * i)) * VW;
-#pragma unroll
-                for (int k = 0; k < VW; ++k) val[i][k] *= dropout_scale(a.seed, a.stream, e0 + k, a.drop_p, inv_keep);
-            }
-            vstore<VW>(out_row + (size_t)(lane + 32 * i) * VW, val[i]);
-        }
+        t += dt; b += db;
+        if (t >= a.T) { t -= a.T; ++b; }
     }
 }
 
-// in-place dropout backward on the block gradient (same mask as k_gather)
+// in-place dropout backward on the block gradient (same mask as the gather); one Philox call per 8 elements
 __global__ void k_dropout_bwd(float* __restrict__ g, long long n, float p, unsigned long long seed,
                               unsigned int stream) {
     const float inv_keep = 1.0f / (1.0f - p);
+    const uint32_t thr = dropout_threshold(p);
+    const long long n8 = (n + 7) >> 3;
     long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride)
-        g[e] *= dropout_scale(seed, stream, (unsigned long long)e, p, inv_keep);
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n8; c += stride) {
+        const uint4 bits = dropout_bits8(seed, stream, (unsigned long long)c);
+        const long long e0 = c << 3;
+        if (e0 + 8 <= n && (reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+            float4 v0 = *reinterpret_cast<float4*>(g + e0), v1 = *reinterpret_cast<float4*>(g + e0 + 4);
+            v0.x *= dropout_lane16(bits, 0) < thr ? 0.f : inv_keep; v0.y *= dropout_lane16(bits, 1) < thr ? 0.f : inv_keep;
+            v0.z *= dropout_lane16(bits, 2) < thr ? 0.f : inv_keep; v0.w *= dropout_lane16(bits, 3) < thr ? 0.f : inv_keep;
+            v1.x *= dropout_lane16(bits, 4) < thr ? 0.f : inv_keep; v1.y *= dropout_lane16(bits, 5) < thr ? 0.f : inv_keep;
+            v1.z *= dropout_lane16(bits, 6) < thr ? 0.f : inv_keep; v1.w *= dropout_lane16(bits, 7) < thr ? 0.f : inv_keep;
+            *reinterpret_cast<float4*>(g + e0) = v0; *reinterpret_cast<float4*>(g + e0 + 4) = v1;
+        } else {
+            for (int k = 0; k < 8 && e0 + k < n; ++k) g[e0 + k] *= dropout_lane16(bits, k) < thr ? 0.f : inv_keep;
+        }
+    }
 }
 
 // dst[r*dst_stride + d] = src[r*src_stride + d], d < D  (token-0 pooling of RAT_m1 and its backward scatter)
@@ -296,15 +334,15 @@ extern "C" int rat_gather_fwd(const float* emb_W, const float* lr_W, const float
     int grid = grid_for(total, 256);
     cudaStream_t st = (cudaStream_t)stream;
     const int nc = (F + 1) * (D / vw);                    // vector chunks per (b,t) row
-    const int ch = (nc + 31) / 32;
-    if (L <= 32 && ch <= 8 && vw >= 2) {       // warp-per-row fast path
+    const int ps = (nc + 63) / 64;                        // chunk-pair slots per lane
+    if (L <= 32 && ps <= 4 && vw >= 2 && (long long)B * T < (1ll << 30)) {       // warp-per-row fast path
         const long long nrows = (long long)B * T;
         const int rgrid = (int)std::min<long long>((nrows + 7) / 8, (long long)num_sms() * 8);
-#define RAT_GATHER_ROWS(VW_, CH_) k_gather_rows<VW_, CH_><<<rgrid, 256, 0, st>>>(a)
+#define RAT_GATHER_ROWS(VW_, PS_) k_gather_rows<VW_, PS_><<<rgrid, 256, 0, st>>>(a)
         if (vw == 4) {
-            if (ch <= 2) RAT_GATHER_ROWS(4, 2); else if (ch <= 5) RAT_GATHER_ROWS(4, 5); else RAT_GATHER_ROWS(4, 8);
+            if (ps <= 1) RAT_GATHER_ROWS(4, 1); else if (ps <= 2) RAT_GATHER_ROWS(4, 2); else if (ps <= 3) RAT_GATHER_ROWS(4, 3); else RAT_GATHER_ROWS(4, 4);
         } else {
-            if (ch <= 2) RAT_GATHER_ROWS(2, 2); else if (ch <= 5) RAT_GATHER_ROWS(2, 5); else RAT_GATHER_ROWS(2, 8);
+            if (ps <= 1) RAT_GATHER_ROWS(2, 1); else if (ps <= 2) RAT_GATHER_ROWS(2, 2); else if (ps <= 3) RAT_GATHER_ROWS(2, 3); else RAT_GATHER_ROWS(2, 4);
         }
 #undef RAT_GATHER_ROWS
         RAT_CHECK_LAUNCH("k_gather_rows");
@@ -320,7 +358,7 @@ extern "C" int rat_gather_fwd(const float* emb_W, const float* lr_W, const float
 extern "C" int rat_dropout_bwd(float* grad, long long n, float p, unsigned long long seed, unsigned int rng_stream,
                                void* stream) {
     if (p <= 0.f) return RAT_OK;
-    k_dropout_bwd<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(grad, n, p, seed, rng_stream);
+    k_dropout_bwd<<<grid_for((n + 7) / 8, 256), 256, 0, (cudaStream_t)stream>>>(grad, n, p, seed, rng_stream);
     RAT_CHECK_LAUNCH("k_dropout_bwd");
     return RAT_OK;
 }

@@ -46,13 +46,23 @@ __global__ void __launch_bounds__(256) k_grad_sqnorm(const float4* __restrict__ 
     }
 }
 
-// single thread: total norm (+ optional externally reduced extra sum), clip coefficient, Adam bias corrections
-__global__ void k_optim_prepare(const double* __restrict__ partial, int nparts, const double* __restrict__ extra_sq,
-                                float max_norm, const float* __restrict__ lr, float beta1, float beta2,
-                                float* __restrict__ state, int advance_step) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// one block: total norm (+ optional externally reduced extra sum), clip coefficient, Adam bias corrections.
+// Thread t adds partials t, t+256, ... in order; the 256 thread sums are then combined by a fixed tree: deterministic.
+__global__ void __launch_bounds__(256) k_optim_prepare(const double* __restrict__ partial, int nparts,
+                                                       const double* __restrict__ extra_sq, float max_norm,
+                                                       const float* __restrict__ lr, float beta1, float beta2,
+                                                       float* __restrict__ state, int advance_step) {
+    __shared__ double st[256], sr[256];
     double t = 0.0, reg = 0.0;
-    for (int i = 0; i < nparts; ++i) { t += partial[i]; reg += partial[nparts + i]; }
+    for (int i = threadIdx.x; i < nparts; i += 256) { t += partial[i]; reg += partial[nparts + i]; }
+    st[threadIdx.x] = t; sr[threadIdx.x] = reg;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { st[threadIdx.x] += st[threadIdx.x + o]; sr[threadIdx.x] += sr[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x != 0) return;
+    t = st[0]; reg = sr[0];
     if (extra_sq) { t += extra_sq[0]; reg += extra_sq[1]; }
     const float norm = (float)sqrt(t);
     float coef = max_norm > 0.f ? max_norm / (norm + 1e-6f) : 1.0f;     // clip_grad_norm_: clamp(max_norm/(norm+1e-6), max=1)
@@ -120,7 +130,7 @@ extern "C" int rat_grad_sqnorm(const float* G, const float* W, long long n, long
 extern "C" int rat_optim_prepare(const double* partial, int nparts, const double* extra_sq, float max_norm,
                                  const float* lr, float beta1, float beta2, float* state, int advance_step,
                                  void* stream) {
-    k_optim_prepare<<<1, 32, 0, (cudaStream_t)stream>>>(partial, nparts, extra_sq, max_norm, lr, beta1, beta2, state,
+    k_optim_prepare<<<1, 256, 0, (cudaStream_t)stream>>>(partial, nparts, extra_sq, max_norm, lr, beta1, beta2, state,
                                                         advance_step);
     RAT_CHECK_LAUNCH("k_optim_prepare");
     return RAT_OK;
