@@ -70,6 +70,16 @@ int rat_gather_fwd(const float* emb_W, const float* lr_W, const float* label_W, 
                    const int* col_off, const int* col_vocab, const int* field_col0, const int* field_width,
                    float* block, float* x_emb, float* lr_out, int B, int T, int L, int F, int D, float drop_p,
                    unsigned long long seed, unsigned int rng_stream, int* err_flag, void* stream);
+/* Row-sharded tables (tmall configuration): the concatenated table index space is range-partitioned,
+ * rank o owns rows [o*rows_per_shard, (o+1)*rows_per_shard).  W_peers[o] is the base of rank o's flat parameter
+ * buffer mapped into this process (symmetric memory over NVLink/NVSwitch); its [rows_per_shard, D] embedding shard
+ * starts at float offset emb_off and its LR shard at lr_off.  The gather kernel loads remote rows straight from
+ * peer memory (no staging all-to-all); everything else is identical to rat_gather_fwd (bit-exact). */
+int rat_gather_fwd_sharded(const float* const* W_peers, long long emb_off, long long lr_off, int rows_per_shard,
+                           int world, const float* label_W, const int* ids, const int* labels, const int* col_off,
+                           const int* col_vocab, const int* field_col0, const int* field_width, float* block,
+                           float* x_emb, float* lr_out, int B, int T, int L, int F, int D, float drop_p,
+                           unsigned long long seed, unsigned int rng_stream, int* err_flag, void* stream);
 /* backward of the embedding dropout: grad *= mask/(1-p), same philox mask as rat_gather_fwd */
 int rat_dropout_bwd(float* grad, long long n, float p, unsigned long long seed, unsigned int rng_stream,
                     void* stream);

@@ -84,7 +84,20 @@ struct GatherArgs {
     int B, T, L, F, D;
     float drop_p; unsigned long long seed; unsigned int stream;
     int* err;
+    // row-sharded tables (range partition, `vs` rows per rank): the flat parameter buffer of every rank is mapped
+    // into this process (symmetric memory over NVLink / NVSwitch); peers[o] + emb_off is rank o's [vs, D] shard.
+    const float* const* peers; long long emb_off, lr_off; int vs;
 };
+__device__ __forceinline__ const float* emb_row_ptr(const GatherArgs& a, int r) {
+    if (a.peers == nullptr) return a.emb_W + (size_t)r * a.D;
+    const int o = r / a.vs;
+    return a.peers[o] + a.emb_off + (size_t)(r - o * a.vs) * a.D;
+}
+__device__ __forceinline__ float lr_value(const GatherArgs& a, int r) {
+    if (a.peers == nullptr) return __ldg(a.lr_W + r);
+    const int o = r / a.vs;
+    return a.peers[o][a.lr_off + (r - o * a.vs)];
+}
 
 template <int VW>
 __global__ void __launch_bounds__(256) k_gather(GatherArgs a) {
@@ -191,7 +204,7 @@ __global__ void __launch_bounds__(256, 3) k_gather_rows(GatherArgs a) {
         int lab = __ldg(a.labels + bt);
         if (lab < 0 || lab > 2) { if (lane == 0) atomicOr(a.err, 4); lab = 0; }
         if (t == 0 && a.lr_out) {                            // LR_Layer (shallow.py:37-38), field order, lane 0
-            const float lrv = lane < a.L ? __ldg(a.lr_W + row) : 0.f;
+            const float lrv = lane < a.L ? lr_value(a, row) : 0.f;
             float tot = 0.f;
             int col = 0;
             for (int f = 0; f < a.F; ++f) {
@@ -211,7 +224,7 @@ __global__ void __launch_bounds__(256, 3) k_gather_rows(GatherArgs a) {
                 for (int k = 0; k < VW; ++k) val[i][h][k] = 0.f;
                 if (cn[i][h] == 0) vload<VW>(a.label_W + (size_t)lab * a.D + cdv[i][h] * VW, val[i][h]);
                 const int r = __shfl_sync(0xffffffffu, row, min(cc0[i][h], 31));
-                if (cw[i][h] > 0) vload<VW>(a.emb_W + (size_t)r * a.D + cdv[i][h] * VW, val[i][h]);
+                if (cw[i][h] > 0) vload<VW>(emb_row_ptr(a, r) + cdv[i][h] * VW, val[i][h]);
             }
 #pragma unroll
         for (int i = 0; i < PS; ++i)
@@ -221,7 +234,7 @@ __global__ void __launch_bounds__(256, 3) k_gather_rows(GatherArgs a) {
                     const int r = __shfl_sync(0xffffffffu, row, min(cc0[i][h] + j, 31));
                     if (j < cw[i][h]) {
                         float rv[VW];
-                        vload<VW>(a.emb_W + (size_t)r * a.D + cdv[i][h] * VW, rv);
+                        vload<VW>(emb_row_ptr(a, r) + cdv[i][h] * VW, rv);
 #pragma unroll
                         for (int k = 0; k < VW; ++k) val[i][h][k] += rv[k];
                     }
@@ -320,19 +333,11 @@ extern "C" int rat_assemble_ids(const int* q_ids, const unsigned char* q_labels,
     return RAT_OK;
 }
 
-extern "C" int rat_gather_fwd(const float* emb_W, const float* lr_W, const float* label_W, const int* ids,
-                              const int* labels, const int* col_off, const int* col_vocab, const int* field_col0,
-                              const int* field_width, float* block, float* x_emb, float* lr_out, int B, int T, int L,
-                              int F, int D, float drop_p, unsigned long long seed, unsigned int rng_stream,
-                              int* err_flag, void* stream) {
-    RAT_REQUIRE(B > 0 && T > 0 && L > 0 && F > 0 && D > 0, "rat_gather_fwd: bad shape");
-    RAT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "rat_gather_fwd: dropout p=%f", drop_p);
-    GatherArgs a{emb_W, lr_W, label_W, ids, labels, col_off, col_vocab, field_col0, field_width,
-                 block, x_emb, lr_out, B, T, L, F, D, drop_p, seed, rng_stream, err_flag};
+static int launch_gather(GatherArgs a, cudaStream_t st) {
+    const int B = a.B, T = a.T, L = a.L, F = a.F, D = a.D;
     const int vw = (D % 4 == 0) ? 4 : (D % 2 == 0) ? 2 : 1;
     long long total = (long long)B * T * (F + 1) * (D / vw);
     int grid = grid_for(total, 256);
-    cudaStream_t st = (cudaStream_t)stream;
     const int nc = (F + 1) * (D / vw);                    // vector chunks per (b,t) row
     const int ps = (nc + 63) / 64;                        // chunk-pair slots per lane
     if (L <= 32 && ps <= 4 && vw >= 2 && (long long)B * T < (1ll << 30)) {       // warp-per-row fast path
@@ -348,11 +353,40 @@ extern "C" int rat_gather_fwd(const float* emb_W, const float* lr_W, const float
         RAT_CHECK_LAUNCH("k_gather_rows");
         return RAT_OK;
     }
+    RAT_REQUIRE(a.peers == nullptr, "rat_gather_fwd_sharded: shape outside the warp-per-row path (L=%d <= 32, even D, <= 512 "
+                                    "vector chunks per row)", L);
     if (vw == 4) k_gather<4><<<grid, 256, 0, st>>>(a);
     else if (vw == 2) k_gather<2><<<grid, 256, 0, st>>>(a);
     else k_gather<1><<<grid, 256, 0, st>>>(a);
     RAT_CHECK_LAUNCH("k_gather");
     return RAT_OK;
+}
+
+extern "C" int rat_gather_fwd(const float* emb_W, const float* lr_W, const float* label_W, const int* ids,
+                              const int* labels, const int* col_off, const int* col_vocab, const int* field_col0,
+                              const int* field_width, float* block, float* x_emb, float* lr_out, int B, int T, int L,
+                              int F, int D, float drop_p, unsigned long long seed, unsigned int rng_stream,
+                              int* err_flag, void* stream) {
+    RAT_REQUIRE(B > 0 && T > 0 && L > 0 && F > 0 && D > 0, "rat_gather_fwd: bad shape");
+    RAT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "rat_gather_fwd: dropout p=%f", drop_p);
+    GatherArgs a{emb_W, lr_W, label_W, ids, labels, col_off, col_vocab, field_col0, field_width,
+                 block, x_emb, lr_out, B, T, L, F, D, drop_p, seed, rng_stream, err_flag, nullptr, 0, 0, 1};
+    return launch_gather(a, (cudaStream_t)stream);
+}
+
+extern "C" int rat_gather_fwd_sharded(const float* const* W_peers, long long emb_off, long long lr_off,
+                                      int rows_per_shard, int world, const float* label_W, const int* ids,
+                                      const int* labels, const int* col_off, const int* col_vocab,
+                                      const int* field_col0, const int* field_width, float* block, float* x_emb,
+                                      float* lr_out, int B, int T, int L, int F, int D, float drop_p,
+                                      unsigned long long seed, unsigned int rng_stream, int* err_flag, void* stream) {
+    RAT_REQUIRE(B > 0 && T > 0 && L > 0 && F > 0 && D > 0, "rat_gather_fwd_sharded: bad shape");
+    RAT_REQUIRE(W_peers != nullptr && rows_per_shard > 0 && world > 0, "rat_gather_fwd_sharded: bad shard description");
+    RAT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "rat_gather_fwd_sharded: dropout p=%f", drop_p);
+    GatherArgs a{nullptr, nullptr, label_W, ids, labels, col_off, col_vocab,
+                 field_col0, field_width, block, x_emb, lr_out, B, T, L, F, D, drop_p, seed, rng_stream, err_flag,
+                 W_peers, emb_off, lr_off, rows_per_shard};
+    return launch_gather(a, (cudaStream_t)stream);
 }
 
 extern "C" int rat_dropout_bwd(float* grad, long long n, float p, unsigned long long seed, unsigned int rng_stream,

@@ -146,6 +146,13 @@ class BaseModel(nn.Module):
                     v.zero_()
                 elif v.ndim == 2:
                     nn.init.xavier_normal_(v)
+            if e.store.shard is not None:          # row-sharded tables: every rank initialises its own rows
+                import re
+                m = re.search(r"std\s*=\s*([0-9.eE+-]+)", str(self._embedding_initializer or ""))
+                if self._embedding_initializer is not None and m is None:
+                    raise NotImplementedError("embedding_initializer={} is not supported with shard_embeddings"
+                                              .format(self._embedding_initializer))
+                e.init_sharded_tables(float(m.group(1)) if m else 0.0, self._seed)
             for k, b in e.buffers.items():
                 if k.endswith("running_mean"):
                     b.zero_()
@@ -175,7 +182,11 @@ class BaseModel(nn.Module):
         return {}
 
     def state_dict(self, *args, **kwargs):
+        """reference key set.  With shard_embeddings the per-field tables are assembled from all ranks (collective:
+        every rank must call it)."""
         sd = OrderedDict((k, v.detach()) for k, v in self._engine.p.items())
+        if self._engine.store.shard is not None:
+            sd.update(self._engine.gather_tables())
         for alias, target in self._alias_keys().items():
             sd[alias] = sd[target]
         for k, v in self._engine.buffers.items():
@@ -184,6 +195,11 @@ class BaseModel(nn.Module):
 
     def load_state_dict(self, state_dict, strict=True):
         own = self.state_dict()
+        if self._engine.store.shard is not None:
+            self._engine.scatter_tables(state_dict)
+            own = OrderedDict((k, v) for k, v in own.items() if k in self._engine.p or k in self._engine.buffers)
+            state_dict = OrderedDict((k, v) for k, v in state_dict.items()
+                                     if "embedding_layer.embedding_layer.embedding_layer." not in k)
         missing = [k for k in own if k not in state_dict]
         unexpected = [k for k in state_dict if k not in own]
         if strict and (missing or unexpected):
@@ -201,6 +217,9 @@ class BaseModel(nn.Module):
                 continue
             if p.requires_grad:
                 total += p.numel()
+        if self._engine.store.shard is not None and count_embedding:      # sharded tables are not nn.Parameters
+            sp = self._engine.spec
+            total += sp.V * (sp.embedding_dim + (1 if sp.use_wide else 0))
         logging.info("Total number of parameters: {}.".format(total))
         return total
 

@@ -29,7 +29,8 @@ class _RATBase(BaseModel):
             dnn_hidden_units=tuple(dnn_hidden_units or ()), batch_norm=bool(batch_norm), use_wide=bool(use_wide),
             emb_dropout=float(emb_dropout), net_dropout=float(net_dropout),
             embedding_regularizer=l2_lambda(embedding_regularizer), net_regularizer=l2_lambda(net_regularizer),
-            learning_rate=float(learning_rate), seed=self._seed)
+            learning_rate=float(learning_rate), seed=self._seed,
+            shard_tables=bool(kwargs.get("shard_embeddings", False)))
         self._build_engine(spec)
         self.output_activation = self.get_output_activation(task)
         self.compile(kwargs["optimizer"], loss=kwargs["loss"], lr=learning_rate)

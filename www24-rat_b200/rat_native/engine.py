@@ -60,6 +60,7 @@ class EngineSpec:
     learning_rate: float = 1e-3
     max_gradient_norm: float = 10.0
     seed: int = 2021
+    shard_tables: bool = False      # row-shard the embedding / LR tables over the data-parallel ranks
 
     @property
     def F(self):
@@ -182,10 +183,24 @@ def param_shapes(spec: EngineSpec) -> Tuple["OrderedDict[str, tuple]", "OrderedD
     return net, emb
 
 
-class ParamStore:
-    """Flat fp32 parameter buffer + gradient + Adam moments, with named views."""
+def shard_rows(V: int, world: int) -> int:
+    """rows per rank of the range partition of the concatenated table index space (multiple of 4)."""
+    return _align4((V + world - 1) // world)
 
-    def __init__(self, spec: EngineSpec, device):
+
+class ParamStore:
+    """Flat fp32 parameter buffer + gradient + Adam moments, with named views.
+
+    Replicated mode: [ net | label table | emb_W [V, D] | lr_W [V] ].
+    Row-sharded mode (`shard=(rank, world)`): [ net | label table | emb shard [Vs, D] | lr shard [Vs] ], rank o owns
+    global rows [o*Vs, (o+1)*Vs); W lives in symmetric memory so that every rank's gather kernel can load any
+    shard over NVLink, and per-field tables exist only as (global row offset, vocab) ranges."""
+
+    def __init__(self, spec: EngineSpec, device, shard=None):
+        if shard is not None:
+            self._init_sharded(spec, device, *shard)
+            return
+        self.shard = None
         net, emb = param_shapes(spec)
         self.offsets: "OrderedDict[str, Tuple[int, tuple]]" = OrderedDict()
         off = 0
@@ -220,6 +235,51 @@ class ParamStore:
         self.emb_W = self.W[self.emb_off:self.emb_off + V * D].view(V, D)
         self.lr_W = self.W[self.lr_off:self.lr_off + V] if spec.use_wide else None
 
+    def _init_sharded(self, spec, device, rank, world):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        net, emb = param_shapes(spec)
+        self.shard = (rank, world)
+        self.offsets = OrderedDict()
+        off = 0
+        for k, shp in net.items():
+            self.offsets[k] = (off, shp)
+            off = _align4(off + math.prod(shp))
+        self.net_end = off
+        D, V = spec.embedding_dim, spec.V
+        k = "label_embedding_layer.weight"
+        self.offsets[k] = (off, emb[k])
+        off = _align4(off + 3 * D)
+        self.rows_per_shard = Vs = shard_rows(V, world)
+        self.row0 = rank * Vs
+        self.emb_off = off
+        off = _align4(off + Vs * D)
+        self.lr_off = off
+        if spec.use_wide:
+            off = _align4(off + Vs)
+        self.total = off
+        # per-field tables: global row ranges (field order = concatenation order)
+        self.table_rows = OrderedDict()
+        r = 0
+        for f in spec.features:
+            self.table_rows[f.name] = (r, f.vocab_size)
+            r += f.vocab_size
+        self.W = symm.empty(off, dtype=torch.float32, device=device)
+        self.W.zero_()
+        handle = symm.rendezvous(self.W, dist.group.WORLD.group_name)
+        self.peer_ptrs = torch.tensor([int(p) for p in handle.buffer_ptrs], dtype=torch.int64, device=device)
+        self._symm_handle = handle
+        self.G = torch.zeros(off, dtype=torch.float32, device=device)
+        self.M = torch.zeros(off, dtype=torch.float32, device=device)
+        self.Vv = torch.zeros(off, dtype=torch.float32, device=device)
+        self.views = OrderedDict((k, self.W[o:o + math.prod(s)].view(s)) for k, (o, s) in self.offsets.items())
+        self.grad_views = OrderedDict((k, self.G[o:o + math.prod(s)].view(s)) for k, (o, s) in self.offsets.items())
+        self.emb_W = self.W[self.emb_off:self.emb_off + Vs * D].view(Vs, D)            # LOCAL shard
+        self.lr_W = self.W[self.lr_off:self.lr_off + Vs] if spec.use_wide else None
+        # local dense gradient over the padded global row space; reduce-scattered to the owners every step
+        self.G_emb_full = torch.zeros(world * Vs * D, dtype=torch.float32, device=device)
+        self.G_lr_full = torch.zeros(world * Vs, dtype=torch.float32, device=device) if spec.use_wide else None
+
     def numel_params(self):
         return sum(math.prod(s) for _, s in self.offsets.values())
 
@@ -235,7 +295,13 @@ class RatEngine:
         require_device()
         self.spec = spec
         self.device = torch.device(device)
-        self.store = ParamStore(spec, self.device)
+        shard = None
+        if spec.shard_tables:
+            import torch.distributed as dist
+            if not (dist.is_available() and dist.is_initialized()):
+                raise RuntimeError("shard_tables=True needs an initialised torch.distributed process group (NCCL)")
+            shard = (dist.get_rank(), dist.get_world_size())
+        self.store = ParamStore(spec, self.device, shard)
         self.p = self.store.views
         D = spec.embedding_dim
         # schema arrays
@@ -492,9 +558,16 @@ class RatEngine:
         D, F, L = s.embedding_dim, s.F, s.L
         drop = s.emb_dropout if training else 0.0
         self.err_flag.zero_()
-        call("rat_gather_fwd", self.store.emb_W, self.store.lr_W, self.p["label_embedding_layer.weight"], ws["ids"],
-             ws["labels"], self.col_off, self.col_vocab, self.field_col0, self.field_width, ws["acts"][0],
-             ws["x_emb"], ws["lr_out"], B, T, L, F, D, float(drop), s.seed, self._rng_stream(0), self.err_flag, st)
+        if self.store.shard is None:
+            call("rat_gather_fwd", self.store.emb_W, self.store.lr_W, self.p["label_embedding_layer.weight"], ws["ids"],
+                 ws["labels"], self.col_off, self.col_vocab, self.field_col0, self.field_width, ws["acts"][0],
+                 ws["x_emb"], ws["lr_out"], B, T, L, F, D, float(drop), s.seed, self._rng_stream(0), self.err_flag, st)
+        else:       # rows are loaded straight from the owners' shards over NVLink (peer pointers)
+            gs = self.store
+            call("rat_gather_fwd_sharded", gs.peer_ptrs, gs.emb_off, gs.lr_off, gs.rows_per_shard, gs.shard[1],
+                 self.p["label_embedding_layer.weight"], ws["ids"], ws["labels"], self.col_off, self.col_vocab,
+                 self.field_col0, self.field_width, ws["acts"][0], ws["x_emb"], ws["lr_out"], B, T, L, F, D,
+                 float(drop), s.seed, self._rng_stream(0), self.err_flag, st)
         enc = self.encode(ws, B, T, training)
         ws["enc_out"] = enc
         if len(s.dnn_hidden_units):
@@ -635,14 +708,48 @@ class RatEngine:
             call("rat_dropout_bwd", d, d.numel(), float(s.emb_dropout), s.seed, self._rng_stream(0), st)
         sw = ws["scatter_ws"]
         gs = self.store
-        g_emb = gs.G[gs.emb_off:gs.emb_off + s.V * D]
-        g_lr = gs.G[gs.lr_off:gs.lr_off + s.V] if s.use_wide else None
+        if gs.shard is None:
+            g_emb = gs.G[gs.emb_off:gs.emb_off + s.V * D]
+            g_lr = gs.G[gs.lr_off:gs.lr_off + s.V] if s.use_wide else None
+        else:       # local dense gradient over the global row space; optimizer_step reduce-scatters it to the owners
+            g_emb, g_lr = gs.G_emb_full, gs.G_lr_full
         call("rat_emb_scatter_reduce", ws["ids"], ws["labels"], d, ws["dxemb"] if has_dnn else None,
              ws["dlogit"] if s.use_wide else None, self.col_off, self.col_pad, self.col_vocab, self.col_field,
              g_emb, g_lr, g["label_embedding_layer.weight"], B, T, L, F, D, s.V, sw, sw.numel() * 4, st)
 
+    def _optimizer_step_sharded(self):
+        """net + label gradients: all-reduce; table gradients: reduce-scatter to the row owners; global-norm clip with
+        the shard norms all-reduced; Adam on [net | label | local shard]; a final barrier orders the W update before
+        the peers' next gather."""
+        import torch.distributed as dist
+        s, gs, st = self.spec, self.store, current_stream()
+        Vs, D = gs.rows_per_shard, s.embedding_dim
+        dist.all_reduce(gs.G[:gs.emb_off], group=self.dist_group)
+        dist.reduce_scatter_tensor(gs.G[gs.emb_off:gs.emb_off + Vs * D], gs.G_emb_full, group=self.dist_group)
+        gs.G_emb_full.zero_()
+        if s.use_wide:
+            dist.reduce_scatter_tensor(gs.G[gs.lr_off:gs.lr_off + Vs], gs.G_lr_full, group=self.dist_group)
+            gs.G_lr_full.zero_()
+        nb = int(query("rat_optim_blocks"))
+        lam_n, lam_e = float(s.net_regularizer or 0.0), float(s.embedding_regularizer or 0.0)
+        if not hasattr(self, "_shard_partial"):
+            self._shard_partial = torch.zeros(2 * nb, dtype=torch.float64, device=self.device)
+        # replicated part (identical on every rank: counted once) and the local shard (summed over ranks)
+        call("rat_grad_sqnorm", gs.G, gs.W, gs.emb_off, gs.net_end, lam_n, lam_e, self.opt_partial, st)
+        call("rat_grad_sqnorm", gs.G[gs.emb_off:], gs.W[gs.emb_off:], gs.total - gs.emb_off, 0, lam_n, lam_e,
+             self._shard_partial, st)
+        extra = self._shard_partial.view(2, nb).sum(dim=1)
+        dist.all_reduce(extra, group=self.dist_group)
+        call("rat_optim_prepare", self.opt_partial, nb, extra, float(s.max_gradient_norm), self.lr, 0.9, 0.999,
+             self.opt_state, 1, st)
+        call("rat_adam_step", gs.W, gs.G, gs.M, gs.Vv, gs.total, gs.net_end, lam_n, lam_e, self.opt_state, 0.9, 0.999,
+             1e-8, st)
+        dist.all_reduce(self._shard_partial[:1], group=self.dist_group)      # barrier: shards updated before any gather
+
     def optimizer_step(self):
         s, gs, st = self.spec, self.store, current_stream()
+        if gs.shard is not None:
+            return self._optimizer_step_sharded()
         if self.world > 1:
             import torch.distributed as dist
             dist.all_reduce(gs.G, group=self.dist_group)
@@ -675,6 +782,71 @@ class RatEngine:
         import math as _m
         return OrderedDict((k, out[o:o + _m.prod(shp)].view(shp)) for k, (o, shp) in gs.offsets.items())
 
+    # ------------------------------------------------------------------ row-sharded tables
+    def init_sharded_tables(self, std: float, seed: int):
+        """N(0, std) rows, padding rows of sequence fields zero (embedding.py:96-100); every rank draws its own shard."""
+        gs, s = self.store, self.spec
+        rank, world = gs.shard
+        g = torch.Generator(device=self.device).manual_seed(int(seed) * 1000003 + rank)
+        gs.emb_W.normal_(0.0, std, generator=g)
+        if gs.lr_W is not None:
+            gs.lr_W.normal_(0.0, std, generator=g)
+        lo, hi = gs.row0, gs.row0 + gs.rows_per_shard
+        gs.emb_W[max(0, min(s.V, hi) - lo):].zero_()                  # rows beyond V_total (padding of the partition)
+        if gs.lr_W is not None:
+            gs.lr_W[max(0, min(s.V, hi) - lo):].zero_()
+        for f in s.features:
+            if f.pad is None:
+                continue
+            r = gs.table_rows[f.name][0] + f.pad
+            if lo <= r < hi:
+                gs.emb_W[r - lo].zero_()
+                if gs.lr_W is not None:
+                    gs.lr_W[r - lo] = 0.0
+        self.shard_barrier()
+
+    def shard_barrier(self):
+        import torch.distributed as dist
+        t = torch.zeros(1, device=self.device)
+        dist.all_reduce(t, group=self.dist_group)
+
+    def gather_tables(self) -> Dict[str, torch.Tensor]:
+        """full per-field tables (state_dict names) assembled from all shards -- checkpoints stay reference-compatible."""
+        import torch.distributed as dist
+        gs, s = self.store, self.spec
+        rank, world = gs.shard
+        Vs, D = gs.rows_per_shard, s.embedding_dim
+        full = torch.empty(world * Vs, D, device=self.device)
+        dist.all_gather_into_tensor(full, gs.emb_W.contiguous(), group=self.dist_group)
+        out = OrderedDict()
+        for f in s.features:
+            r0, v = gs.table_rows[f.name]
+            out[EMB + f.name + ".weight"] = full[r0:r0 + v].clone()
+        if s.use_wide:
+            fl = torch.empty(world * Vs, device=self.device)
+            dist.all_gather_into_tensor(fl, gs.lr_W.contiguous(), group=self.dist_group)
+            for f in s.features:
+                r0, v = gs.table_rows[f.name]
+                out[LRP + f.name + ".weight"] = fl[r0:r0 + v].clone().view(v, 1)
+        return out
+
+    def scatter_tables(self, sd: Dict[str, torch.Tensor]):
+        """load full per-field tables (every rank passes the same state dict) into the local shard."""
+        gs, s = self.store, self.spec
+        lo, hi = gs.row0, gs.row0 + gs.rows_per_shard
+        for f in s.features:
+            r0, v = gs.table_rows[f.name]
+            a, b = max(lo, r0), min(hi, r0 + v)
+            if a >= b:
+                continue
+            for prefix, dst in ((EMB, gs.emb_W), (LRP, gs.lr_W)):
+                k = prefix + f.name + ".weight"
+                if dst is None or k not in sd:
+                    continue
+                src = sd[k].to(device=self.device, dtype=torch.float32)
+                dst[a - lo:b - lo].copy_(src[a - r0:b - r0].view(dst[a - lo:b - lo].shape))
+        self.shard_barrier()
+
     # ------------------------------------------------------------------ state
     def load_params(self, sd: Dict[str, torch.Tensor], strict=True):
         missing = []
@@ -686,5 +858,7 @@ class RatEngine:
         for k, v in self.buffers.items():
             if k in sd:
                 v.copy_(sd[k].to(self.device))
+        if self.store.shard is not None:
+            self.scatter_tables(sd)
         if strict and missing:
             raise KeyError(f"missing parameters: {missing[:5]}...")
