@@ -173,16 +173,25 @@ int rat_layernorm_bwd(const float* x, const float* dout, float* dx, const float*
 /* ---------------------------------------------------------------------------------------------------------
  * K6: embedding gradient = deterministic sorted segment-reduce.  Replaces ATen embedding_dense_backward for
  * every nn.Embedding of EmbeddingDictLayer (layers/embedding.py:79-100), LR_Layer (layers/shallow.py:31) and the
- * label table (RAT_m2.py:64).  Occurrence (b,t,l) contributes dblock[b,t,1+field(l),:] (+ dxemb[b,field(l),:] when
- * t==0) to row col_off[l]+ids[b,t,l] of g_emb, and dlogit[b] (t==0 only) to the same row of g_lr; padding ids
- * contribute nothing (torch padding_idx semantics).  g_label [3,D] = sum of dblock[b,t,0,:] by labels[b,t].
- * Only touched rows of g_emb/g_lr are written (each exactly once); the caller keeps the rest zero.
+ * label table (RAT_m2.py:64), and the backward of nn.Dropout(emb_dropout) (RAT_m2.py:135).  Occurrence (b,t,l)
+ * contributes mask*dblock[b,t,1+field(l),:] (+ dxemb[b,field(l),:] when t==0) to row col_off[l]+ids[b,t,l] of g_emb,
+ * and dlogit[b] (t==0 only) to the same row of g_lr; padding ids contribute nothing (torch padding_idx semantics).
+ * g_label [3,D] = sum of mask*dblock[b,t,0,:] by labels[b,t].  mask = the rat_gather_fwd dropout mask of
+ * (drop_p, seed, rng_stream) times 1/(1-p); drop_p = 0 means no mask (dblock is never modified).
+ * Only touched rows of g_emb / g_lr / g_label are written (each exactly once); the caller keeps the rest zero.
+ * rat_emb_scatter_plan builds and sorts the occurrence keys; it needs the ids only, so the caller may run it on
+ * another stream while the forward/backward kernels run, then call rat_emb_scatter_reduce(planned=1) with the same
+ * workspace.  planned=0 makes rat_emb_scatter_reduce run the plan itself first.  n_occ = B*T*(L+1).
  * ------------------------------------------------------------------------------------------------------- */
 size_t rat_emb_scatter_workspace_bytes(long long n_occ, int D);
+int rat_emb_scatter_plan(const int* ids, const int* labels, const int* col_off, const int* col_pad,
+                         const int* col_vocab, int B, int T, int L, int F, int D, long long V_total, void* workspace,
+                         size_t workspace_bytes, void* stream);
 int rat_emb_scatter_reduce(const int* ids, const int* labels, const float* dblock, const float* dxemb,
                            const float* dlogit, const int* col_off, const int* col_pad, const int* col_vocab,
                            const int* col_field, float* g_emb, float* g_lr, float* g_label, int B, int T, int L, int F,
-                           int D, long long V_total, void* workspace, size_t workspace_bytes, void* stream);
+                           int D, long long V_total, float drop_p, unsigned long long seed, unsigned int rng_stream,
+                           int planned, void* workspace, size_t workspace_bytes, void* stream);
 /* the stable LSD radix sort used above, exposed for tests: sorts (keys, vals) by the low `bits` bits of keys.
  * hist: scratch of 256*ceil(n/2048) uint32.  *result_in_tmp = 1 if the sorted data ended in the tmp buffers. */
 int rat_radix_sort_pairs(unsigned int* keys, unsigned int* vals, unsigned int* keys_tmp, unsigned int* vals_tmp,

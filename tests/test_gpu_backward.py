@@ -202,8 +202,8 @@ def test_emb_scatter_reduce_matches_index_add_and_is_deterministic(rn, shape, B,
         sw = ws["scatter_ws"]
         sw.fill_(-1 if rep else 0)                     # results must not depend on stale workspace contents
         rn.call("rat_emb_scatter_reduce", ws["ids"], ws["labels"], dblock.cuda(), dxemb.cuda(), dlogit.cuda(),
-                eng.col_off, eng.col_pad, eng.col_vocab, eng.col_field, g_emb, g_lr, g_lab, B, T, L, F, D, V, sw,
-                sw.numel() * 4, rn.current_stream())
+                eng.col_off, eng.col_pad, eng.col_vocab, eng.col_field, g_emb, g_lr, g_lab, B, T, L, F, D, V, 0.0, 0, 0,
+                0, sw, sw.numel() * 4, rn.current_stream())
         outs.append((g_emb.clone(), g_lr.clone(), g_lab.clone()))
     for a, b in zip(*outs):
         assert torch.equal(a, b), "sorted segment-reduce must be bitwise run-to-run deterministic"
@@ -217,6 +217,43 @@ def test_emb_scatter_reduce_matches_index_add_and_is_deterministic(rn, shape, B,
         if feat.pad is not None:
             assert float(outs[0][0][off + feat.pad].abs().sum()) == 0.0
         off += feat.vocab_size
+
+
+def test_emb_scatter_fused_dropout_and_plan_split(rn):
+    """the dropout backward fused into the segment reduce uses the gather's mask: identical (bitwise) to masking the
+    block gradient first with rat_dropout_bwd; a plan built ahead (rat_emb_scatter_plan) gives the same result."""
+    from tests.gpu_util import make_engine, rand_params_nontrivial
+    spec = O.shape_spec("kkbox", vocab_scale=0.005)
+    eng = make_engine(spec, rand_params_nontrivial(spec, seed=3))
+    B, K = 96, 5
+    pool = O.synthetic_pool(spec, 3000, seed=5)
+    nbr = O.synthetic_neighbours(B, 3000, K, seed=5, missing=0.1)
+    X, y = O.assemble_batch(pool[:B], pool, nbr, np.arange(B))
+    T, L, F, D, V = K + 1, spec.input_length, spec.num_fields, spec.embedding_dim, spec.total_vocab
+    ws = eng.load_wire(torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda(), training=True)
+    g = torch.Generator().manual_seed(2)
+    dblock = torch.randn(B, T, F + 1, D, generator=g).cuda()
+    dxemb = torch.randn(B, F * D, generator=g).cuda()
+    dlogit = torch.randn(B, generator=g).cuda()
+    sw, st = ws["scatter_ws"], rn.current_stream()
+
+    def run(db, p, planned):
+        g_emb, g_lr, g_lab = torch.zeros(V, D, device=DEV), torch.zeros(V, device=DEV), torch.zeros(3, D, device=DEV)
+        if planned:
+            rn.call("rat_emb_scatter_plan", ws["ids"], ws["labels"], eng.col_off, eng.col_pad, eng.col_vocab, B, T, L, F,
+                    D, V, sw, sw.numel() * 4, st)
+        rn.call("rat_emb_scatter_reduce", ws["ids"], ws["labels"], db, dxemb, dlogit, eng.col_off, eng.col_pad,
+                eng.col_vocab, eng.col_field, g_emb, g_lr, g_lab, B, T, L, F, D, V, float(p), 77, 5, int(planned), sw,
+                sw.numel() * 4, st)
+        return g_emb, g_lr, g_lab
+    fused = run(dblock, 0.3, False)
+    masked = dblock.clone()
+    rn.call("rat_dropout_bwd", masked, masked.numel(), 0.3, 77, 5, st)
+    assert 0.25 < float((masked == 0).float().mean()) < 0.35
+    two_step = run(masked, 0.0, False)
+    planned = run(dblock, 0.3, True)
+    for a, b, c in zip(fused, two_step, planned):
+        assert torch.equal(a, b) and torch.equal(a, c)
 
 
 def test_bn_act_backward_matches_autograd(rn):

@@ -78,12 +78,15 @@ __device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
     return x;
 }
+__device__ __forceinline__ uint32_t dropout_key(unsigned long long seed, uint32_t stream) {
+    return lowbias32((uint32_t)seed ^ lowbias32((uint32_t)(seed >> 32) + 0x9E3779B9u * (stream + 1u)));
+}
 __device__ __forceinline__ uint4 dropout_bits8(unsigned long long seed, uint32_t stream, unsigned long long c) {
 #if RAT_DROPOUT_PHILOX
     return philox4x32(make_uint4((uint32_t)c, (uint32_t)(c >> 32), stream, 0u),
                       make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
 #else
-    const uint32_t key = lowbias32((uint32_t)seed ^ lowbias32((uint32_t)(seed >> 32) + 0x9E3779B9u * (stream + 1u)));
+    const uint32_t key = dropout_key(seed, stream);
     const uint32_t hi = lowbias32((uint32_t)(c >> 30) ^ key);          // c*4 spans 34+ bits: fold the high part
     const uint32_t b = (uint32_t)c << 2;
     return make_uint4(lowbias32((b + 0u) ^ hi), lowbias32((b + 1u) ^ hi), lowbias32((b + 2u) ^ hi), lowbias32((b + 3u) ^ hi));
@@ -101,6 +104,65 @@ __device__ __forceinline__ float dropout_scale(unsigned long long seed, uint32_t
     const uint4 r = dropout_bits8(seed, stream, e >> 3);
     return dropout_lane16(r, (int)(e & 7)) < dropout_threshold(p) ? 0.0f : inv_keep;
 }
+
+// ---- VW-wide (1, 2 or 4 floats) vector loads / stores
+template <int VW> struct Vec;
+template <> struct Vec<4> { typedef float4 T; };
+template <> struct Vec<2> { typedef float2 T; };
+template <> struct Vec<1> { typedef float T; };
+
+template <int VW>
+__device__ __forceinline__ void vload(const float* p, float (&v)[VW]) {
+    typename Vec<VW>::T t = __ldg(reinterpret_cast<const typename Vec<VW>::T*>(p));
+    const float* f = reinterpret_cast<const float*>(&t);
+#pragma unroll
+    for (int i = 0; i < VW; ++i) v[i] = f[i];
+}
+template <int VW>
+__device__ __forceinline__ void vstore(float* p, const float (&v)[VW]) {
+    typename Vec<VW>::T t;
+    float* f = reinterpret_cast<float*>(&t);
+#pragma unroll
+    for (int i = 0; i < VW; ++i) f[i] = v[i];
+    *reinterpret_cast<typename Vec<VW>::T*>(p) = t;
+}
+
+// ---- exact n / d for 0 <= n < 2^31 by multiply-high (round-up magic, Granlund-Montgomery); built on the host
+struct FastDiv {
+    uint32_t m, l;
+    __device__ __forceinline__ uint32_t div(uint32_t n) const { return (__umulhi(m, n) + n) >> l; }
+};
+static inline FastDiv make_fastdiv(uint32_t d) {
+    uint32_t l = 0;
+    while ((1u << l) < d) ++l;
+    const unsigned long long m = (((1ull << l) - d) << 32) / d + 1;
+    return FastDiv{(uint32_t)m, l};
+}
+
+template <int VW>
+__device__ __forceinline__ void dropout_chunk(float (&val)[VW], unsigned long long idx, uint32_t key, uint32_t hk0,
+                                              uint32_t thr, float inv_keep) {
+    // element e = idx*VW + k uses 16-bit half (e & 1) of hash word e >> 1 (see dropout_bits8: word gw of counter
+    // c = gw >> 2 is lowbias32(low32(gw) ^ lowbias32(high32(gw) ^ key)))
+    if (VW >= 2) {
+        const unsigned long long gw0 = idx * (VW / 2);
+        const uint32_t hi32 = (uint32_t)(gw0 >> 32);
+        const uint32_t hk = hi32 == 0u ? hk0 : lowbias32(hi32 ^ key);
+#pragma unroll
+        for (int q = 0; q < VW / 2; ++q) {
+            const uint32_t w = lowbias32(((uint32_t)gw0 + (uint32_t)q) ^ hk);
+            val[2 * q] *= (w & 0xffffu) < thr ? 0.0f : inv_keep;
+            val[2 * q + 1] *= (w >> 16) < thr ? 0.0f : inv_keep;
+        }
+    } else {
+        const unsigned long long gw = idx >> 1;
+        const uint32_t hi32 = (uint32_t)(gw >> 32);
+        const uint32_t hk = hi32 == 0u ? hk0 : lowbias32(hi32 ^ key);
+        const uint32_t w = lowbias32((uint32_t)gw ^ hk);
+        val[0] *= ((idx & 1) ? (w >> 16) : (w & 0xffffu)) < thr ? 0.0f : inv_keep;
+    }
+}
+
 #endif
 
 }  // namespace rat

@@ -55,27 +55,6 @@ __global__ void k_assemble(const int* __restrict__ q_ids, const unsigned char* _
 }
 
 // ---- K1: fused gather -> block [B,T,N,D], x_emb [B,F*D], lr_out [B] -------------------------------------
-template <int VW> struct Vec;
-template <> struct Vec<4> { typedef float4 T; };
-template <> struct Vec<2> { typedef float2 T; };
-template <> struct Vec<1> { typedef float T; };
-
-template <int VW>
-__device__ __forceinline__ void vload(const float* p, float (&v)[VW]) {
-    typename Vec<VW>::T t = __ldg(reinterpret_cast<const typename Vec<VW>::T*>(p));
-    const float* f = reinterpret_cast<const float*>(&t);
-#pragma unroll
-    for (int i = 0; i < VW; ++i) v[i] = f[i];
-}
-template <int VW>
-__device__ __forceinline__ void vstore(float* p, const float (&v)[VW]) {
-    typename Vec<VW>::T t;
-    float* f = reinterpret_cast<float*>(&t);
-#pragma unroll
-    for (int i = 0; i < VW; ++i) f[i] = v[i];
-    *reinterpret_cast<typename Vec<VW>::T*>(p) = t;
-}
-
 struct GatherArgs {
     const float* emb_W; const float* lr_W; const float* label_W;
     const int* ids; const int* labels;
@@ -156,55 +135,32 @@ __global__ void __launch_bounds__(256) k_gather(GatherArgs a) {
     }
 }
 
-// ---- K1 (fast path): one WARP per (b,t) row of the block ---------------------------------------------------
-// Lane l < L owns column l of the id matrix: it validates id[bt][l] once and keeps the table row in a register;
-// every lane then produces PAIRS of adjacent vector chunks (2*VW contiguous floats = 32 B for VW = 4) of the row's
-// N*D contiguous output floats.  Table rows travel by shuffle, so all row loads of a lane are INDEPENDENT and the
-// block row is written as one contiguous, fully coalesced stream.  Extra sum-pool terms (sequence fields) are only
-// visited by the pair slots that contain a sequence token (warp-uniform test).  With VW = 4 a chunk pair is exactly
-// the eight elements of one Philox call (dropout).  Same arithmetic as k_gather (left-to-right sum-pool, same mask).
-template <int VW, int PS>
-__global__ void __launch_bounds__(256, 3) k_gather_rows(GatherArgs a) {
-    const int lane = threadIdx.x & 31;
-    const int N = a.F + 1, DV = a.D / VW, NC = N * DV;
+// ---- K1 (fast path): one THREAD per 16-byte vector chunk of the block, fixed chunk geometry per thread ------
+// A block owns RPB consecutive (b,t) rows per pass; thread tid is chunk c = tid % NC of row r = tid / NC of the pass
+// (NC = (F+1) * D/VW chunks per row), so everything that depends on the chunk only -- token, vector lane, id column,
+// table base, vocabulary, sum-pool width -- is computed ONCE and the pass loop is: id load -> bounds check -> one
+// 16-byte table-row load -> (sequence fields: w-1 more) -> dropout -> one 16-byte store.  Consecutive threads write
+// consecutive chunks (a warp stores 512 contiguous bytes) and U passes are in flight per thread.  The LR logit
+// (t == 0 rows only) is done by extra blocks, one warp per target row.  Same arithmetic as k_gather (left-to-right
+// sum-pool, same dropout mask function), so the output is bit-identical.
+template <int VW, bool SHARDED, int U>
+__global__ void __launch_bounds__(320, 4) k_gather_flat(GatherArgs a, int NC, int RPB, int RB, int SROWS, int main_blocks,
+                                                     FastDiv divT) {
     const int nrows = a.B * a.T;
-    const int wstride = gridDim.x * (blockDim.x >> 5);
-    const float inv_keep = a.drop_p > 0.f ? 1.0f / (1.0f - a.drop_p) : 1.0f;
-    const uint32_t thr = dropout_threshold(a.drop_p);
-    const int my_off = lane < a.L ? a.col_off[lane] : 0;
-    const int my_vocab = lane < a.L ? a.col_vocab[lane] : 1;
-    // per-lane chunk geometry is row independent: token n, vector dv, first column c0 and width w of its field
-    int cn[PS][2], cdv[PS][2], cc0[PS][2], cw[PS][2], slotw[PS];
-#pragma unroll
-    for (int i = 0; i < PS; ++i) {
-        int mw = 0;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int c = 2 * (lane + 32 * i) + h;
-            cn[i][h] = c < NC ? c / DV : -1;
-            cdv[i][h] = c < NC ? c - cn[i][h] * DV : 0;
-            cc0[i][h] = 0; cw[i][h] = 0;
-            if (cn[i][h] > 0) { cc0[i][h] = a.field_col0[cn[i][h] - 1]; cw[i][h] = a.field_width[cn[i][h] - 1]; }
-            mw = max(mw, cw[i][h]);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mw = max(mw, __shfl_xor_sync(0xffffffffu, mw, o));
-        slotw[i] = mw;                                           // warp-uniform: widest field touched by pair slot i
-    }
-    int bt = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    int t = bt % a.T, b = bt / a.T;
-    const int dt = wstride % a.T, db = wstride / a.T;
-    for (; bt < nrows; bt += wstride) {
-        int id = 0;
-        if (lane < a.L) {
-            id = __ldg(a.ids + (size_t)bt * a.L + lane);
-            if (id < 0 || id >= my_vocab) { atomicOr(a.err, 1); id = 0; }
-        }
-        const int row = my_off + id;                         // table row of column `lane`
-        int lab = __ldg(a.labels + bt);
-        if (lab < 0 || lab > 2) { if (lane == 0) atomicOr(a.err, 4); lab = 0; }
-        if (t == 0 && a.lr_out) {                            // LR_Layer (shallow.py:37-38), field order, lane 0
-            const float lrv = lane < a.L ? lr_value(a, row) : 0.f;
+    if ((int)blockIdx.x >= main_blocks) {
+        // ---- LR_Layer (shallow.py:37-38): one warp per target row, lane l owns id column l, sum in field order
+        const int lane = threadIdx.x & 31;
+        const int wpb = blockDim.x >> 5;
+        const int my_off = lane < a.L ? a.col_off[lane] : 0;
+        const int my_vocab = lane < a.L ? a.col_vocab[lane] : 1;
+        for (int b = ((int)blockIdx.x - main_blocks) * wpb + (threadIdx.x >> 5); b < a.B;
+             b += ((int)gridDim.x - main_blocks) * wpb) {
+            float lrv = 0.f;
+            if (lane < a.L) {
+                int id = __ldg(a.ids + (size_t)b * a.T * a.L + lane);
+                if (id < 0 || id >= my_vocab) id = 0;               // flagged by the chunk threads
+                lrv = SHARDED ? lr_value(a, my_off + id) : __ldg(a.lr_W + my_off + id);
+            }
             float tot = 0.f;
             int col = 0;
             for (int f = 0; f < a.F; ++f) {
@@ -215,55 +171,95 @@ __global__ void __launch_bounds__(256, 3) k_gather_rows(GatherArgs a) {
             }
             if (lane == 0) a.lr_out[b] = tot;
         }
-        float val[PS][2][VW];
+        return;
+    }
+    extern __shared__ int s_ids[];                          // [SROWS][L + 2]: validated ids | label | b if t == 0 else -1
+    const int tid = threadIdx.x;
+    const int r = tid / NC, c = tid - r * NC;
+    const int DV = a.D / VW;
+    const int n = c / DV, dv = c - n * DV;
+    // chunk geometry (row independent)
+    const bool is_label = n == 0;
+    const int c0 = is_label ? 0 : a.field_col0[n - 1];
+    const int w = is_label ? 1 : a.field_width[n - 1];
+    const int row0 = is_label ? 0 : a.col_off[c0];
+    const int idcol = is_label ? a.L : c0;
+    const int LS = a.L + 2;
+    const float* src = (is_label ? a.label_W : (SHARDED ? (const float*)nullptr : a.emb_W + (size_t)row0 * a.D)) + dv * VW;
+    float* xdst = (is_label || a.x_emb == nullptr) ? nullptr : a.x_emb + (size_t)(n - 1) * a.D + dv * VW;
+    const size_t xstride = (size_t)a.F * a.D;
+    const bool drop = a.drop_p > 0.f;
+    const float inv_keep = drop ? 1.0f / (1.0f - a.drop_p) : 1.0f;
+    const uint32_t thr = dropout_threshold(a.drop_p);
+    const uint32_t key = dropout_key(a.seed, a.stream), hk0 = lowbias32(key);
+    const int row_begin = blockIdx.x * RB, row_end = min(nrows, row_begin + RB);
+
+    for (int s0 = row_begin; s0 < row_end; s0 += SROWS) {
+        const int srows = min(SROWS, row_end - s0);
+        if (s0 != row_begin) __syncthreads();
+        // ---- stage + validate this block's ids / labels once (coalesced), so the chunk loop below has ONE global
+        //      load on its critical path (the table row)
+        for (int i = tid; i < srows * a.L; i += blockDim.x) {
+            const int rr = i / a.L, l = i - rr * a.L;
+            int id = __ldg(a.ids + (size_t)s0 * a.L + i);
+            if (id < 0 || id >= __ldg(a.col_vocab + l)) { atomicOr(a.err, 1); id = 0; }
+            s_ids[rr * LS + l] = id;
+        }
+        for (int i = tid; i < srows; i += blockDim.x) {
+            int lab = __ldg(a.labels + s0 + i);
+            if (lab < 0 || lab > 2) { atomicOr(a.err, 4); lab = 0; }
+            s_ids[i * LS + a.L] = lab;
+            const uint32_t bt = (uint32_t)(s0 + i), b = divT.div(bt);
+            s_ids[i * LS + a.L + 1] = (bt == b * (uint32_t)a.T) ? (int)b : -1;
+        }
+        __syncthreads();
+        if (r >= RPB) continue;
+        for (int g0 = 0; g0 * RPB < srows; g0 += U) {
+            int ri[U];
+            bool ok[U];
+            float val[U][VW];
 #pragma unroll
-        for (int i = 0; i < PS; ++i)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-#pragma unroll
-                for (int k = 0; k < VW; ++k) val[i][h][k] = 0.f;
-                if (cn[i][h] == 0) vload<VW>(a.label_W + (size_t)lab * a.D + cdv[i][h] * VW, val[i][h]);
-                const int r = __shfl_sync(0xffffffffu, row, min(cc0[i][h], 31));
-                if (cw[i][h] > 0) vload<VW>(emb_row_ptr(a, r) + cdv[i][h] * VW, val[i][h]);
+            for (int u = 0; u < U; ++u) {
+                ri[u] = (g0 + u) * RPB + r;
+                ok[u] = ri[u] < srows;
+                if (ok[u]) {
+                    const int id = s_ids[ri[u] * LS + idcol];
+                    if (SHARDED && !is_label) vload<VW>(emb_row_ptr(a, row0 + id) + dv * VW, val[u]);
+                    else vload<VW>(src + (size_t)id * a.D, val[u]);
+                }
             }
+            if (w > 1) {                                    // sequence field: left-to-right sum-pool of its columns
+                for (int j = 1; j < w; ++j) {
 #pragma unroll
-        for (int i = 0; i < PS; ++i)
-            for (int j = 1; j < slotw[i]; ++j)               // sum-pool terms 1.. of sequence fields (rare slots only)
+                    for (int h = 0; h < U; h += 2) {        // two rows in flight (keeps the register count at 48)
+                        float rv[2][VW];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int r = __shfl_sync(0xffffffffu, row, min(cc0[i][h] + j, 31));
-                    if (j < cw[i][h]) {
-                        float rv[VW];
-                        vload<VW>(emb_row_ptr(a, r) + cdv[i][h] * VW, rv);
+                        for (int q = 0; q < 2; ++q) {
+                            if (h + q >= U || !ok[h + q]) continue;
+                            const int idj = s_ids[ri[h + q] * LS + idcol + j];
+                            if (SHARDED) vload<VW>(emb_row_ptr(a, row0 + idj) + dv * VW, rv[q]);
+                            else vload<VW>(src + (size_t)idj * a.D, rv[q]);
+                        }
 #pragma unroll
-                        for (int k = 0; k < VW; ++k) val[i][h][k] += rv[k];
+                        for (int q = 0; q < 2; ++q)
+#pragma unroll
+                            for (int k = 0; k < VW; ++k)
+                                if (h + q < U && ok[h + q]) val[h + q][k] += rv[q][k];
                     }
                 }
-        float* out_row = a.block + (size_t)bt * NC * VW;
+            }
 #pragma unroll
-        for (int i = 0; i < PS; ++i) {
-            const int c0 = 2 * (lane + 32 * i);
-            uint4 bits = make_uint4(0u, 0u, 0u, 0u);
-            const unsigned long long e0 = ((unsigned long long)bt * NC + c0) * VW;
-            if (a.drop_p > 0.f && cn[i][0] >= 0) bits = dropout_bits8(a.seed, a.stream, e0 >> 3);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                if (cn[i][h] < 0) continue;
-                if (t == 0 && a.x_emb && cn[i][h] > 0)
-                    vstore<VW>(a.x_emb + ((size_t)b * a.F + (cn[i][h] - 1)) * a.D + cdv[i][h] * VW, val[i][h]);
-                if (a.drop_p > 0.f) {
-                    const unsigned long long eh = e0 + (unsigned long long)h * VW;
-                    uint4 bh = bits;
-                    if ((eh >> 3) != (e0 >> 3)) bh = dropout_bits8(a.seed, a.stream, eh >> 3);   // never for VW=4, even NC
-#pragma unroll
-                    for (int k = 0; k < VW; ++k)
-                        val[i][h][k] *= dropout_lane16(bh, (int)((eh + k) & 7)) < thr ? 0.0f : inv_keep;
+            for (int u = 0; u < U; ++u) {
+                if (!ok[u]) continue;
+                if (xdst != nullptr) {                      // X_emb: target row, never dropped out (RAT_m2.py:120)
+                    const int b = s_ids[ri[u] * LS + a.L + 1];
+                    if (b >= 0) vstore<VW>(xdst + (size_t)b * xstride, val[u]);
                 }
-                vstore<VW>(out_row + (size_t)(c0 + h) * VW, val[i][h]);
+                const unsigned long long idx = (unsigned long long)(s0 + ri[u]) * NC + c;
+                if (drop) dropout_chunk<VW>(val[u], idx, key, hk0, thr, inv_keep);
+                vstore<VW>(a.block + idx * VW, val[u]);
             }
         }
-        t += dt; b += db;
-        if (t >= a.T) { t -= a.T; ++b; }
     }
 }
 
@@ -339,21 +335,40 @@ static int launch_gather(GatherArgs a, cudaStream_t st) {
     long long total = (long long)B * T * (F + 1) * (D / vw);
     int grid = grid_for(total, 256);
     const int nc = (F + 1) * (D / vw);                    // vector chunks per (b,t) row
-    const int ps = (nc + 63) / 64;                        // chunk-pair slots per lane
-    if (L <= 32 && ps <= 4 && vw >= 2 && (long long)B * T < (1ll << 30)) {       // warp-per-row fast path
-        const long long nrows = (long long)B * T;
-        const int rgrid = (int)std::min<long long>((nrows + 7) / 8, (long long)num_sms() * 8);
-#define RAT_GATHER_ROWS(VW_, PS_) k_gather_rows<VW_, PS_><<<rgrid, 256, 0, st>>>(a)
-        if (vw == 4) {
-            if (ps <= 1) RAT_GATHER_ROWS(4, 1); else if (ps <= 2) RAT_GATHER_ROWS(4, 2); else if (ps <= 3) RAT_GATHER_ROWS(4, 3); else RAT_GATHER_ROWS(4, 4);
-        } else {
-            if (ps <= 1) RAT_GATHER_ROWS(2, 1); else if (ps <= 2) RAT_GATHER_ROWS(2, 2); else if (ps <= 3) RAT_GATHER_ROWS(2, 3); else RAT_GATHER_ROWS(2, 4);
+    if (nc <= 320 && L <= 32 && (long long)B * T < (1ll << 30)) {       // thread-per-chunk fast path
+        const int nrows = B * T;
+        int rpb = 1, best = 0;                                          // rows per pass: fill the block's warps
+        for (int r = 1; r * nc <= 320 && r <= 16; ++r) {
+            const int thr = round_up(r * nc, 32);
+            const int util = r * nc * 1000 / thr;
+            if (util > best + 10 || util >= best) { best = std::max(best, util); rpb = r; }
         }
-#undef RAT_GATHER_ROWS
-        RAT_CHECK_LAUNCH("k_gather_rows");
+        const int threads = round_up(rpb * nc, 32);
+        const FastDiv dT = make_fastdiv((uint32_t)T);
+        const bool sh = a.peers != nullptr;
+        const int lr_blocks = a.lr_out ? std::min((B + threads / 32 - 1) / (threads / 32), num_sms()) : 0;
+        const int unit = rpb * 4;                                       // rows of one unrolled trip (U = 4)
+        // each block owns RB consecutive rows (one resident wave), staged SROWS rows at a time
+#define RAT_GATHER_FLAT(VW_, SH_) do {                                                                                 \
+            int per_sm = 1;                                                                                            \
+            const int srows_max = std::max(unit, 128 / unit * unit);                                                   \
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gather_flat<VW_, SH_, 4>, threads,                \
+                                                          (size_t)srows_max * (L + 2) * 4);                            \
+            const int want = num_sms() * std::max(1, per_sm);                                                          \
+            const int rb = round_up((nrows + want - 1) / want, rpb);                                                   \
+            const int main_blocks = (nrows + rb - 1) / rb;                                                             \
+            const int srows = std::min(srows_max, round_up(rb, unit));                                                 \
+            k_gather_flat<VW_, SH_, 4><<<main_blocks + lr_blocks, threads, (size_t)srows * (L + 2) * 4, st>>>(         \
+                a, nc, rpb, rb, srows, main_blocks, dT);                                                               \
+        } while (0)
+        if (vw == 4) { if (sh) RAT_GATHER_FLAT(4, true); else RAT_GATHER_FLAT(4, false); }
+        else if (vw == 2) { if (sh) RAT_GATHER_FLAT(2, true); else RAT_GATHER_FLAT(2, false); }
+        else { if (sh) RAT_GATHER_FLAT(1, true); else RAT_GATHER_FLAT(1, false); }
+#undef RAT_GATHER_FLAT
+        RAT_CHECK_LAUNCH("k_gather_flat");
         return RAT_OK;
     }
-    RAT_REQUIRE(a.peers == nullptr, "rat_gather_fwd_sharded: shape outside the warp-per-row path (L=%d <= 32, even D, <= 512 "
+    RAT_REQUIRE(a.peers == nullptr, "rat_gather_fwd_sharded: shape outside the thread-per-chunk path (L=%d <= 32, <= 320 "
                                     "vector chunks per row)", L);
     if (vw == 4) k_gather<4><<<grid, 256, 0, st>>>(a);
     else if (vw == 2) k_gather<2><<<grid, 256, 0, st>>>(a);

@@ -2,15 +2,22 @@
 //
 // Replaces ATen embedding_dense_backward reached from loss.backward() (base_model.py:223) for every per-field
 // nn.Embedding of EmbeddingDictLayer (embedding.py:79-100) and LR_Layer (shallow.py:31), plus the 3-row label
-// table (RAT_m2.py:64).  Pipeline per step:
-//   k_build_keys        key[i] = table row of occurrence i=(b,t,l)  (padding ids -> sentinel), val[i] = i
-//   k_radix_{hist,scan,scatter} x passes   stable LSD radix sort (8-bit digits) of (key, val)
-//   k_segment_reduce    one warp per 32 sorted positions: runs wholly inside the chunk are summed in sorted
-//                       (= canonical occurrence) order and stored once; runs that cross chunk boundaries leave
-//                       partials that k_segment_fixup adds up in chunk order  => bitwise deterministic
-//   k_label_grad        per-CTA partial sums of the label-token rows, reduced in fixed order
-// The gradient of occurrence (b,t,l) is dBlock[b,t,1+field(l),:] (+ dXemb[b,field(l),:] for the target row t=0,
-// the DNN path) and, for the LR table, dlogit[b] for t=0.
+// table (RAT_m2.py:64) and the backward of nn.Dropout(emb_dropout) (RAT_m2.py:135).  Two phases:
+//   PLAN (depends on the ids only -> the engine runs it on a side stream under the forward/backward kernels)
+//     k_build_keys        key[i] = table row of occurrence i=(b,t,l) (padding ids -> sentinel); the label token of
+//                         row (b,t) is pseudo column L with key V + label;  val[i] = packed (bt, is-target, column)
+//     k_radix_{hist,scan,scatter} x passes   stable LSD radix sort (8-bit digits) of (key, val)
+//   REDUCE (critical path, 3 launches)
+//     k_segment_scan      one warp per 32 sorted positions, LANE = POSITION: every lane loads its occurrence's
+//                         gradient row (all vectors independent -> deep memory-level parallelism), applies the
+//                         dropout mask, and a shuffle segmented scan sums each run of equal keys in a fixed tree
+//                         order; the run's last lane stores the row once.  Runs crossing chunk boundaries leave
+//                         per-chunk partials and the chunk holding the run head is appended to a list.
+//     k_fixup_short       one warp per listed head whose run ends within 32 chunks: partials added in chunk order
+//     k_fixup_long        one block per remaining (hot-id) head: 8 warps add fixed sub-ranges, combined in warp order
+// For a given input every sum has one fixed association => bitwise run-to-run deterministic.
+// The gradient of occurrence (b,t,l) is mask*dBlock[b,t,1+field(l),:] (+ dXemb[b,field(l),:] for the target row
+// t=0, the DNN path) and, for the LR table, dlogit[b] for t=0.
 #include <algorithm>
 #include "common.cuh"
 #include "../../include/rat_b200.h"
@@ -21,20 +28,31 @@ constexpr int RS_THREADS = 256;
 constexpr int RS_ITEMS = 8;                       // keys per thread
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;    // 2048 keys per block
 
-// val = (bt << 6) | (t == 0 ? 32 : 0) | l : the segment reduce decodes an occurrence with shifts only (L <= 32);
-// because (bt, l) is lexicographic in the occurrence index the stable sort still yields the canonical order.
-__global__ void k_build_keys(const int* __restrict__ ids, const int* __restrict__ col_off,
+// val = (bt << 6) | (t == 0 ? 32 : 0) | l : the segment reduce decodes an occurrence with shifts only (L <= 31,
+// column code 31 = label token); because (bt, l) is lexicographic in the occurrence index the stable sort still
+// yields the canonical order.  n = B*T*(L+1) occurrences.
+constexpr unsigned int LABEL_COL = 31u;
+__global__ void k_build_keys(const int* __restrict__ ids, const int* __restrict__ labels, const int* __restrict__ col_off,
                              const int* __restrict__ col_pad, const int* __restrict__ col_vocab, long long n, int L, int T,
-                             unsigned int sentinel, unsigned int* __restrict__ keys, unsigned int* __restrict__ vals,
+                             unsigned int V, unsigned int* __restrict__ keys, unsigned int* __restrict__ vals,
                              unsigned int* __restrict__ totals, int ntotals) {
+    const unsigned int sentinel = V + 3u;
+    const int L1 = L + 1;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const unsigned int bt = (unsigned int)(i / L);
-        const int l = (int)(i - (long long)bt * L);
-        const int id = ids[i];
+        const unsigned int bt = (unsigned int)(i / L1);
+        const int l = (int)(i - (long long)bt * L1);
         unsigned int k = sentinel;
-        if (id >= 0 && id < col_vocab[l] && id != col_pad[l]) k = (unsigned int)(col_off[l] + id);
+        const unsigned int tflag = (bt % (unsigned int)T) == 0u ? 32u : 0u;
+        if (l < L) {
+            const int id = ids[(long long)bt * L + l];
+            if (id >= 0 && id < col_vocab[l] && id != col_pad[l]) k = (unsigned int)(col_off[l] + id);
+            vals[i] = (bt << 6) | tflag | (unsigned int)l;
+        } else {
+            const int lab = labels[bt];
+            if (lab >= 0 && lab <= 2) k = V + (unsigned int)lab;
+            vals[i] = (bt << 6) | LABEL_COL;                 // never the "target row" path: no dXemb / dlogit term
+        }
         keys[i] = k;
-        vals[i] = (bt << 6) | ((bt % (unsigned int)T) == 0u ? 32u : 0u) | (unsigned int)l;
     }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ntotals; i += gridDim.x * blockDim.x) totals[i] = 0u;
 }
@@ -167,176 +185,204 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const unsigned int
 
 // ---- segment reduce ------------------------------------------------------------------------------------------
 struct SegArgs {
-    const unsigned int* keys; const unsigned int* vals; long long n; unsigned int sentinel;
+    const unsigned int* keys; const unsigned int* vals; long long n; unsigned int sentinel, V;
     const float* dblock;     // [B,T,N,D]
     const float* dxemb;      // [B,F*D] or nullptr
     const float* dlogit;     // [B] or nullptr
     const int* col_field;    // [L]
     float* g_emb;            // [V,D]
     float* g_lr;             // [V] or nullptr
-    float* carryF; float* carryL;   // [nchunks][D+1]
-    int T, L, N, D, F;
+    float* g_label;          // [3,D] or nullptr
+    float* carryF; float* carryL;   // [nchunks][DS]  (DS = round_up(D+1, 4); element D = LR scalar)
+    unsigned int* counters;  // [0] = #heads, [1] = #long heads
+    unsigned int* heads; unsigned int* longs;
+    int T, L, N, D, F, DS;
+    FastDiv divT;
+    float drop_p; unsigned long long seed; unsigned int stream;
 };
 
-template <int NPER>   // floats per lane: D <= 32*NPER
-__device__ __forceinline__ void seg_load_add(const SegArgs& a, unsigned int src, int lane, float (&acc)[NPER], float& lr) {
-    const int l = (int)(src & 31u);
-    const long long bt = src >> 6;
-    const int t = (src & 32u) ? 0 : 1;                    // only "is this the target row" matters
-    const long long b = t == 0 ? bt / a.T : 0;
-    const int f = a.col_field[l];
-    const float* g = a.dblock + ((bt * a.N) + 1 + f) * a.D;
-#pragma unroll
-    for (int k = 0; k < NPER; ++k) {
-        const int d = lane + 32 * k;
-        if (d < a.D) {
-            float v = g[d];
-            if (t == 0 && a.dxemb) v += a.dxemb[(b * a.F + f) * a.D + d];
-            acc[k] += v;
-        }
-    }
-    if (t == 0 && a.dlogit) lr += a.dlogit[b];
+__device__ __forceinline__ float* seg_final_row(const SegArgs& a, unsigned int key) {
+    if (key < a.V) return a.g_emb + (size_t)key * a.D;
+    return a.g_label ? a.g_label + (size_t)(key - a.V) * a.D : nullptr;
 }
 
-template <int NPER>
-__global__ void __launch_bounds__(256) k_segment_reduce(SegArgs a) {
+constexpr int SEG_G = 5;      // vectors of a gradient row scanned together (D = 40: two groups of five float4)
+
+template <int VW>
+__global__ void __launch_bounds__(256) k_segment_scan(SegArgs a) {
+    const unsigned int FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const long long chunk = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long p0 = chunk * 32;
     if (p0 >= a.n) return;
     const long long p = p0 + lane;
-    const unsigned int mykey = p < a.n ? a.keys[p] : a.sentinel;
-    const unsigned int mysrc = p < a.n ? a.vals[p] : 0u;
-    const unsigned int prev_key = p0 > 0 ? a.keys[p0 - 1] : a.sentinel;           // sentinel == "different"
-    const unsigned int next_key = p0 + 32 < a.n ? a.keys[p0 + 32] : a.sentinel;
-    float acc[NPER];
+    const unsigned int key = p < a.n ? a.keys[p] : a.sentinel;
+    const unsigned int src = p < a.n ? a.vals[p] : 0u;
+    const unsigned int prev_g = p0 > 0 ? a.keys[p0 - 1] : a.sentinel;             // sentinel == "different"
+    const unsigned int next_g = p0 + 32 < a.n ? a.keys[p0 + 32] : a.sentinel;
+    const unsigned int prevk = __shfl_up_sync(FULL, key, 1);
+    const bool head = lane == 0 || key != prevk;
+    const unsigned int hm = __ballot_sync(FULL, head);
+    const int start = 31 - __clz(hm & (FULL >> (31 - lane)));                    // first lane of my run
+    const bool tail = lane == 31 || ((hm >> (lane + 1)) & 1u);
+    const bool valid = key != a.sentinel;
+    // ---- decode the occurrence
+    const unsigned int l = src & 31u, bt = src >> 6;
+    const bool t0 = (src & 32u) != 0u, is_lab = l == LABEL_COL;
+    const int f = is_lab ? 0 : a.col_field[l];
+    const size_t e0 = ((size_t)bt * a.N + (is_lab ? 0 : 1 + f)) * a.D;           // element index inside the block
+    const float* grow = a.dblock + e0;
+    const float* xrow = nullptr;
     float lr = 0.f;
+    if (valid && t0) {
+        const unsigned int b = a.divT.div(bt);
+        if (a.dxemb) xrow = a.dxemb + ((size_t)b * a.F + f) * a.D;
+        if (a.dlogit) lr = a.dlogit[b];
+    }
+    // ---- where the run that ends at this lane goes
+    float* dst = nullptr;
+    float* dst_lr = nullptr;
+    if (tail && valid) {
+        const bool cont = start == 0 && p0 > 0 && prev_g == key;
+        const bool fwd = lane == 31 && next_g == key;
+        if (cont) { dst = a.carryF + chunk * a.DS; dst_lr = dst + a.D; }
+        else if (fwd) {
+            dst = a.carryL + chunk * a.DS; dst_lr = dst + a.D;
+            a.heads[atomicAdd(&a.counters[0], 1u)] = (unsigned int)chunk;        // list order is irrelevant
+        } else { dst = seg_final_row(a, key); dst_lr = (a.g_lr && key < a.V) ? a.g_lr + key : nullptr; }
+    }
+    bool okk[5];
 #pragma unroll
-    for (int k = 0; k < NPER; ++k) acc[k] = 0.f;
-    int run_start = 0;
-    for (int j = 0; j < 32; ++j) {
-        const unsigned int kj = __shfl_sync(0xffffffffu, mykey, j);
-        if (kj == a.sentinel) break;                                           // sentinels are sorted last
-        const unsigned int sj = __shfl_sync(0xffffffffu, mysrc, j);
-        seg_load_add<NPER>(a, sj, lane, acc, lr);
-        const unsigned int kn = j < 31 ? __shfl_sync(0xffffffffu, mykey, j + 1) : next_key;
-        const bool run_ends_here = (j == 31) || (kn != kj);
-        if (run_ends_here) {
-            const bool continues_from_prev = (run_start == 0) && (p0 > 0) && (prev_key == kj);
-            const bool spans_forward = (j == 31) && (next_key == kj);
-            float* dst;
-            float* dst_lr;
-            if (continues_from_prev) { dst = a.carryF + chunk * (a.D + 1); dst_lr = dst + a.D; }
-            else if (spans_forward) { dst = a.carryL + chunk * (a.D + 1); dst_lr = dst + a.D; }
-            else { dst = a.g_emb + (size_t)kj * a.D; dst_lr = a.g_lr ? a.g_lr + kj : nullptr; }
+    for (int s = 0; s < 5; ++s) okk[s] = lane - (1 << s) >= start;
+    const bool drop = a.drop_p > 0.f;
+    const float inv_keep = drop ? 1.0f / (1.0f - a.drop_p) : 1.0f;
+    const uint32_t thr = dropout_threshold(a.drop_p);
+    const uint32_t dkey = dropout_key(a.seed, a.stream), hk0 = lowbias32(dkey);
+    const int DV = a.D / VW;
+    for (int v0 = 0; v0 < DV; v0 += SEG_G) {
+        float v[SEG_G][VW];
 #pragma unroll
-            for (int k = 0; k < NPER; ++k) { const int d = lane + 32 * k; if (d < a.D) dst[d] = acc[k]; acc[k] = 0.f; }
-            if (lane == 0 && dst_lr) *dst_lr = lr;
-            lr = 0.f;
-            run_start = j + 1;
+        for (int g = 0; g < SEG_G; ++g) {
+#pragma unroll
+            for (int k = 0; k < VW; ++k) v[g][k] = 0.f;
+            if (valid && v0 + g < DV) vload<VW>(grow + (v0 + g) * VW, v[g]);
+        }
+        if (drop) {
+#pragma unroll
+            for (int g = 0; g < SEG_G; ++g)
+                if (valid && v0 + g < DV) dropout_chunk<VW>(v[g], e0 / VW + (v0 + g), dkey, hk0, thr, inv_keep);
+        }
+        if (xrow != nullptr) {
+#pragma unroll
+            for (int g = 0; g < SEG_G; ++g)
+                if (v0 + g < DV) {
+                    float x[VW];
+                    vload<VW>(xrow + (v0 + g) * VW, x);
+#pragma unroll
+                    for (int k = 0; k < VW; ++k) v[g][k] += x[k];
+                }
+        }
+#pragma unroll
+        for (int s = 0; s < 5; ++s)
+#pragma unroll
+            for (int g = 0; g < SEG_G; ++g)
+#pragma unroll
+                for (int k = 0; k < VW; ++k) {
+                    const float t = __shfl_up_sync(FULL, v[g][k], 1 << s);
+                    if (okk[s]) v[g][k] += t;
+                }
+        if (dst != nullptr) {
+#pragma unroll
+            for (int g = 0; g < SEG_G; ++g)
+                if (v0 + g < DV) vstore<VW>(dst + (v0 + g) * VW, v[g]);
+        }
+    }
+    if (a.dlogit) {
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+            const float t = __shfl_up_sync(FULL, lr, 1 << s);
+            if (okk[s]) lr += t;
+        }
+        if (dst_lr != nullptr) *dst_lr = lr;
+    }
+}
+
+// Runs that cross chunk boundaries.  `heads` lists the chunks that hold the HEAD of a forward-spanning run.
+// last chunk `end` of the run = the first cc > c that is the final chunk or does not end inside the run; the result is
+// carryL[c] + carryF[c+1] + ... + carryF[end], added in chunk order.
+__device__ __forceinline__ bool seg_chunk_stops(const SegArgs& a, long long cc, unsigned int key) {
+    const long long cl = cc * 32 + 31;
+    return (cl >= a.n - 1) || a.keys[cl] != key || a.keys[cl + 1] != key;
+}
+
+__global__ void __launch_bounds__(256) k_fixup_short(SegArgs a) {
+    const int lane = threadIdx.x & 31;
+    const unsigned int nheads = a.counters[0];
+    const long long nchunks = (a.n + 31) / 32;
+    const unsigned int nwarps = gridDim.x * (blockDim.x >> 5);
+    for (unsigned int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < nheads; i += nwarps) {
+        const long long c = a.heads[i];
+        const unsigned int key = a.keys[c * 32 + 31];
+        const long long cc = c + 1 + lane;
+        const bool stop = cc < nchunks && seg_chunk_stops(a, cc, key);
+        const unsigned int sm = __ballot_sync(0xffffffffu, stop);
+        if (sm == 0u) {                                               // hot id: more than 32 chunks -> block-level kernel
+            if (lane == 0) a.longs[atomicAdd(&a.counters[1], 1u)] = (unsigned int)c;
+            continue;
+        }
+        const int m = __ffs(sm);                                      // carryF records c+1 .. c+m
+        float* row = seg_final_row(a, key);
+        for (int e = lane; e <= a.D; e += 32) {
+            float s = a.carryL[c * a.DS + e];
+#pragma unroll 4
+            for (int j = 1; j <= m; ++j) s += a.carryF[(c + j) * a.DS + e];
+            if (e < a.D) { if (row) row[e] = s; }
+            else if (a.g_lr && key < a.V) a.g_lr[key] = s;
         }
     }
 }
 
-// Runs that cross chunk boundaries.  One BLOCK per chunk; only blocks whose chunk holds the HEAD of a forward-spanning
-// run do work: the threads find the last chunk of the run in parallel, the 8 warps add contiguous sub-ranges of the
-// per-chunk partials (lane = embedding dimension), and the 8 warp sums are combined in warp order.  For a given
-// input the partition is fixed => bitwise deterministic; a hot id spanning hundreds of chunks costs ~m/8 dependent
-// loads instead of m.
-template <int NPER>
-__global__ void __launch_bounds__(256) k_segment_fixup(SegArgs a) {
+// One BLOCK per long head: the threads find the last chunk of the run in parallel, the 8 warps add contiguous
+// sub-ranges of the per-chunk partials (lane = embedding dimension), and the 8 warp sums are combined in warp order.
+__global__ void __launch_bounds__(256) k_fixup_long(SegArgs a) {
     __shared__ long long end_s;
-    __shared__ float part[8][32 * NPER + 1];
+    __shared__ float part[8][132];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long nchunks = (a.n + 31) / 32;
-    const long long c = blockIdx.x;
-    if (c >= nchunks - 1) return;                                   // the last chunk cannot span forward
-    const long long last = c * 32 + 31;
-    const unsigned int key = a.keys[last];
-    if (key == a.sentinel || a.keys[last + 1] != key) return;       // last run does not span forward
-    const bool covers_start = a.keys[c * 32] == key;
-    if (covers_start && c > 0 && a.keys[c * 32 - 1] == key) return; // it continues from an earlier chunk: not the head
-    // ---- last chunk `end` of the run: the first cc > c that is the final chunk or does not end inside the run
-    if (threadIdx.x == 0) end_s = nchunks - 1;
-    __syncthreads();
-    for (long long base = c + 1; base < nchunks; base += 256) {
-        const long long cc = base + threadIdx.x;
-        bool stop = false;
-        if (cc < nchunks) {
-            const long long cl = cc * 32 + 31;
-            stop = (cl >= a.n - 1) || a.keys[cl] != key || a.keys[cl + 1] != key;
-        }
-        if (stop) atomicMin(&end_s, cc);
+    const unsigned int nlong = a.counters[1];
+    for (unsigned int i = blockIdx.x; i < nlong; i += gridDim.x) {
+        const long long c = a.longs[i];
+        const unsigned int key = a.keys[c * 32 + 31];
+        __syncthreads();                                              // part / end_s of the previous head consumed
+        if (threadIdx.x == 0) end_s = nchunks - 1;
         __syncthreads();
-        if (end_s < base + 256) break;
-    }
-    __syncthreads();
-    const long long end = end_s;
-    // ---- partial sums: warp w adds chunks c+1+w*per .. (fixed partition), lane = dimension
-    const long long m = end - c;                                    // number of carryF records
-    const long long per = (m + 7) / 8;
-    const long long lo = c + 1 + warp * per, hi = min(end + 1, lo + per);
-    float acc[NPER], lr = 0.f;
-#pragma unroll
-    for (int k = 0; k < NPER; ++k) acc[k] = 0.f;
-    for (long long cc = lo; cc < hi; ++cc) {
-        const float* f = a.carryF + cc * (a.D + 1);
-#pragma unroll
-        for (int k = 0; k < NPER; ++k) { const int d = lane + 32 * k; if (d < a.D) acc[k] += f[d]; }
-        lr += f[a.D];
-    }
-#pragma unroll
-    for (int k = 0; k < NPER; ++k) part[warp][lane + 32 * k] = acc[k];
-    if (lane == 0) part[warp][32 * NPER] = lr;
-    __syncthreads();
-    if (warp == 0) {
-        const float* h = a.carryL + c * (a.D + 1);
-        float* dst = a.g_emb + (size_t)key * a.D;
-#pragma unroll
-        for (int k = 0; k < NPER; ++k) {
-            const int d = lane + 32 * k;
-            if (d < a.D) {
-                float s = h[d];
-                for (int w = 0; w < 8; ++w) s += part[w][d];
-                dst[d] = s;
+        for (long long base = c + 1; base < nchunks; base += 256) {
+            const long long cc = base + threadIdx.x;
+            if (cc < nchunks && seg_chunk_stops(a, cc, key)) atomicMin(&end_s, cc);
+            __syncthreads();
+            if (end_s < base + 256) break;
+        }
+        __syncthreads();
+        const long long end = end_s;
+        const long long m = end - c;                                  // number of carryF records
+        const long long per = (m + 7) / 8;
+        const long long lo = c + 1 + warp * per, hi = min(end + 1, lo + per);
+        for (int e = lane; e <= a.D; e += 32) {
+            float s = 0.f;
+#pragma unroll 4
+            for (long long cc = lo; cc < hi; ++cc) s += a.carryF[cc * a.DS + e];
+            part[warp][e] = s;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            float* row = seg_final_row(a, key);
+            for (int e = lane; e <= a.D; e += 32) {
+                float s = a.carryL[c * a.DS + e];
+                for (int w = 0; w < 8; ++w) s += part[w][e];
+                if (e < a.D) { if (row) row[e] = s; }
+                else if (a.g_lr && key < a.V) a.g_lr[key] = s;
             }
         }
-        if (lane == 0 && a.g_lr) {
-            float s = h[a.D];
-            for (int w = 0; w < 8; ++w) s += part[w][32 * NPER];
-            a.g_lr[key] = s;
-        }
-    }
-}
-
-// label-token gradient: partial[cta][lab][d] = sum over the cta's (b,t) rows with labels[b,t]==lab of dblock[b,t,0,d]
-__global__ void __launch_bounds__(256) k_label_grad(const float* __restrict__ dblock, const int* __restrict__ labels,
-                                                    long long nrows, int N, int D, float* __restrict__ partials) {
-    extern __shared__ float sm[];           // [8 warps][3][D]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int i = threadIdx.x; i < nw * 3 * D; i += blockDim.x) sm[i] = 0.f;
-    __syncthreads();
-    const long long per = (nrows + gridDim.x - 1) / gridDim.x;
-    const long long beg = blockIdx.x * per, end = min(nrows, beg + per);
-    for (long long r = beg + warp; r < end; r += nw) {
-        const int lab = labels[r];
-        if (lab < 0 || lab > 2) continue;
-        const float* g = dblock + r * (long long)N * D;
-        float* dst = sm + (warp * 3 + lab) * D;
-        for (int d = lane; d < D; d += 32) dst[d] += g[d];
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) {
-        float s = 0.f;
-        for (int w = 0; w < nw; ++w) s += sm[w * 3 * D + i];
-        partials[(size_t)blockIdx.x * 3 * D + i] = s;
-    }
-}
-__global__ void k_label_reduce(const float* __restrict__ partials, int nparts, int len, float* __restrict__ out) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) {
-        float s = 0.f;
-        for (int c = 0; c < nparts; ++c) s += partials[(size_t)c * len + i];
-        out[i] = s;
     }
 }
 
@@ -346,81 +392,115 @@ static int key_bits(unsigned int maxkey) { int b = 1; while ((maxkey >> b) != 0)
 
 using namespace rat;
 
+namespace {
+struct ScatterLayout {
+    unsigned int *k0, *v0, *k1, *v1, *hist, *totals, *counters, *heads, *longs;
+    float *carryF, *carryL;
+    long long n, nchunks;
+    int nblk, DS;
+    size_t bytes;
+};
+ScatterLayout scatter_layout(void* workspace, long long n, int D) {
+    ScatterLayout w{};
+    w.n = n;
+    w.nblk = (int)((n + RS_TILE - 1) / RS_TILE);
+    w.nchunks = (n + 31) / 32;
+    w.DS = round_up(D + 1, 4);
+    const size_t nk = (size_t)((n + 3) / 4 * 4);
+    const size_t nc = (size_t)((w.nchunks + 3) / 4 * 4);
+    unsigned int* p = (unsigned int*)workspace;
+    w.k0 = p; p += nk; w.v0 = p; p += nk; w.k1 = p; p += nk; w.v1 = p; p += nk;
+    w.hist = p; p += ((size_t)256 * w.nblk + 3) / 4 * 4;
+    w.totals = p; p += 4 * 256;                                     // [4 passes][256] per-digit key counts
+    w.counters = p; p += 16;
+    w.heads = p; p += nc; w.longs = p; p += nc;
+    w.carryF = (float*)p; p += nc * w.DS;
+    w.carryL = (float*)p; p += nc * w.DS;
+    w.bytes = (size_t)((char*)p - (char*)workspace);
+    return w;
+}
+}  // namespace
+
 extern "C" size_t rat_emb_scatter_workspace_bytes(long long n_occ, int D) {
-    // keys/vals double buffers + histogram + carries + label partials
-    const long long nblk = (n_occ + RS_TILE - 1) / RS_TILE;
-    const long long nchunks = (n_occ + 31) / 32;
-    size_t b = 0;
-    b += 4 * (size_t)round_up((int)n_occ, 4) * sizeof(unsigned int);
-    b += (size_t)256 * nblk * sizeof(unsigned int) + 64 + 4 * 256 * sizeof(unsigned int);
-    b += 2 * (size_t)nchunks * (D + 1) * sizeof(float) + 64;
-    b += (size_t)num_sms() * 3 * D * sizeof(float) + 64;
-    return b;
+    return scatter_layout(nullptr, n_occ, D).bytes + 64;
+}
+
+static int scatter_check(int B, int T, int L, int F, int D, long long V_total, const void* workspace, size_t workspace_bytes,
+                         const char* who) {
+    RAT_REQUIRE(B > 0 && T > 0 && L > 0 && F > 0 && D > 0 && V_total > 0, "%s: bad shape", who);
+    RAT_REQUIRE(D <= 128, "%s: D=%d > 128 not supported", who, D);
+    const long long n = (long long)B * T * (L + 1);
+    RAT_REQUIRE(n < (1ll << 31), "%s: too many occurrences", who);
+    RAT_REQUIRE(L <= 31 && (long long)B * T < (1ll << 26), "%s: L=%d (<=31) or B*T too large for the packed occurrence index", who, L);
+    RAT_REQUIRE(V_total + 3 < (1ll << 32), "%s: V_total too large", who);
+    RAT_REQUIRE(workspace && ((uintptr_t)workspace & 15) == 0 && workspace_bytes >= rat_emb_scatter_workspace_bytes(n, D),
+                "%s: workspace missing, unaligned or too small", who);
+    return RAT_OK;
+}
+
+extern "C" int rat_emb_scatter_plan(const int* ids, const int* labels, const int* col_off, const int* col_pad,
+                                    const int* col_vocab, int B, int T, int L, int F, int D, long long V_total,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = scatter_check(B, T, L, F, D, V_total, workspace, workspace_bytes, "rat_emb_scatter_plan");
+    if (rc != RAT_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n = (long long)B * T * (L + 1);
+    ScatterLayout w = scatter_layout(workspace, n, D);
+    const unsigned int V = (unsigned int)V_total;
+    int grid = (int)min((n + 255) / 256, (long long)num_sms() * 16);
+    k_build_keys<<<grid, 256, 0, st>>>(ids, labels, col_off, col_pad, col_vocab, n, L, T, V, w.k0, w.v0, w.totals, 4 * 256 + 16);
+    RAT_CHECK_LAUNCH("k_build_keys");
+    const int bits = key_bits(V + 3u);
+    unsigned int *ki = w.k0, *vi = w.v0, *ko = w.k1, *vo = w.v1;
+    for (int shift = 0; shift < bits; shift += 8) {
+        unsigned int* tot = w.totals + (shift / 8) * 256;
+        k_radix_hist<<<w.nblk, RS_THREADS, 0, st>>>(ki, n, shift, w.hist, w.nblk, tot);
+        RAT_CHECK_LAUNCH("k_radix_hist");
+        k_scan_digits<<<256, 256, 0, st>>>(w.hist, w.nblk, tot);
+        RAT_CHECK_LAUNCH("k_scan_digits");
+        k_radix_scatter<<<w.nblk, RS_THREADS, 0, st>>>(ki, vi, ko, vo, n, shift, w.hist, w.nblk);
+        RAT_CHECK_LAUNCH("k_radix_scatter");
+        std::swap(ki, ko);
+        std::swap(vi, vo);
+    }
+    return RAT_OK;
 }
 
 extern "C" int rat_emb_scatter_reduce(const int* ids, const int* labels, const float* dblock, const float* dxemb,
                                       const float* dlogit, const int* col_off, const int* col_pad,
                                       const int* col_vocab, const int* col_field, float* g_emb, float* g_lr,
                                       float* g_label, int B, int T, int L, int F, int D, long long V_total,
+                                      float drop_p, unsigned long long seed, unsigned int rng_stream, int planned,
                                       void* workspace, size_t workspace_bytes, void* stream) {
-    RAT_REQUIRE(B > 0 && T > 0 && L > 0 && F > 0 && D > 0 && V_total > 0, "rat_emb_scatter_reduce: bad shape");
-    RAT_REQUIRE(D <= 128, "rat_emb_scatter_reduce: D=%d > 128 not supported", D);
-    const long long n = (long long)B * T * L;
-    RAT_REQUIRE(n < (1ll << 31), "rat_emb_scatter_reduce: too many occurrences");
-    RAT_REQUIRE(L <= 32 && (long long)B * T < (1ll << 26), "rat_emb_scatter_reduce: L=%d (<=32) or B*T too large for the packed occurrence index", L);
-    RAT_REQUIRE(workspace && workspace_bytes >= rat_emb_scatter_workspace_bytes(n, D), "rat_emb_scatter_reduce: workspace too small");
+    int rc = scatter_check(B, T, L, F, D, V_total, workspace, workspace_bytes, "rat_emb_scatter_reduce");
+    if (rc != RAT_OK) return rc;
+    RAT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "rat_emb_scatter_reduce: dropout p=%f", drop_p);
     cudaStream_t st = (cudaStream_t)stream;
-    const int nblk = (int)((n + RS_TILE - 1) / RS_TILE);
-    const long long nchunks = (n + 31) / 32;
-    const size_t nk = (size_t)round_up((int)n, 4);
-    unsigned int* k0 = (unsigned int*)workspace;
-    unsigned int* v0 = k0 + nk;
-    unsigned int* k1 = v0 + nk;
-    unsigned int* v1 = k1 + nk;
-    unsigned int* hist = v1 + nk;
-    unsigned int* totals = hist + (size_t)256 * nblk + 16;          // [4 passes][256] per-digit key counts
-    float* carryF = (float*)(totals + 4 * 256);
-    float* carryL = carryF + (size_t)nchunks * (D + 1);
-    float* lab_part = carryL + (size_t)nchunks * (D + 1) + 16;
-    const unsigned int sentinel = (unsigned int)V_total;
-    const int N = F + 1;
-
-    int grid = (int)min((n + 255) / 256, (long long)num_sms() * 16);
-    k_build_keys<<<grid, 256, 0, st>>>(ids, col_off, col_pad, col_vocab, n, L, T, sentinel, k0, v0, totals, 4 * 256);
-    RAT_CHECK_LAUNCH("k_build_keys");
-    const int bits = key_bits(sentinel);
-    unsigned int *ki = k0, *vi = v0, *ko = k1, *vo = v1;
-    for (int shift = 0; shift < bits; shift += 8) {
-        unsigned int* tot = totals + (shift / 8) * 256;
-        k_radix_hist<<<nblk, RS_THREADS, 0, st>>>(ki, n, shift, hist, nblk, tot);
-        RAT_CHECK_LAUNCH("k_radix_hist");
-        k_scan_digits<<<256, 256, 0, st>>>(hist, nblk, tot);
-        RAT_CHECK_LAUNCH("k_scan_digits");
-        k_radix_scatter<<<nblk, RS_THREADS, 0, st>>>(ki, vi, ko, vo, n, shift, hist, nblk);
-        RAT_CHECK_LAUNCH("k_radix_scatter");
-        unsigned int* t;
-        t = ki; ki = ko; ko = t;
-        t = vi; vi = vo; vo = t;
+    if (!planned) {
+        rc = rat_emb_scatter_plan(ids, labels, col_off, col_pad, col_vocab, B, T, L, F, D, V_total, workspace,
+                                  workspace_bytes, stream);
+        if (rc != RAT_OK) return rc;
     }
-    SegArgs a{ki, vi, n, sentinel, dblock, dxemb, dlogit, col_field, g_emb, g_lr, carryF, carryL, T, L, N, D, F};
-    const int wpb = 8;
-    const int sgrid = (int)((nchunks + wpb - 1) / wpb);
-    const int fgrid = (int)std::max<long long>(1, nchunks - 1);      // one block per chunk that may hold a run head
-    if (D <= 32) { k_segment_reduce<1><<<sgrid, 256, 0, st>>>(a); RAT_CHECK_LAUNCH("k_segment_reduce");
-                   k_segment_fixup<1><<<fgrid, 256, 0, st>>>(a); }
-    else if (D <= 64) { k_segment_reduce<2><<<sgrid, 256, 0, st>>>(a); RAT_CHECK_LAUNCH("k_segment_reduce");
-                        k_segment_fixup<2><<<fgrid, 256, 0, st>>>(a); }
-    else { k_segment_reduce<4><<<sgrid, 256, 0, st>>>(a); RAT_CHECK_LAUNCH("k_segment_reduce");
-           k_segment_fixup<4><<<fgrid, 256, 0, st>>>(a); }
-    RAT_CHECK_LAUNCH("k_segment_fixup");
-    if (g_label) {
-        const long long nrows = (long long)B * T;
-        const int lgrid = (int)min((nrows + 255) / 256, (long long)num_sms());
-        k_label_grad<<<lgrid, 256, (size_t)8 * 3 * D * sizeof(float), st>>>(dblock, labels, nrows, N, D, lab_part);
-        RAT_CHECK_LAUNCH("k_label_grad");
-        k_label_reduce<<<1, 128, 0, st>>>(lab_part, lgrid, 3 * D, g_label);
-        RAT_CHECK_LAUNCH("k_label_reduce");
-    }
+    const long long n = (long long)B * T * (L + 1);
+    ScatterLayout w = scatter_layout(workspace, n, D);
+    const unsigned int V = (unsigned int)V_total;
+    const int passes = (key_bits(V + 3u) + 7) / 8;
+    const unsigned int* keys = (passes & 1) ? w.k1 : w.k0;
+    const unsigned int* vals = (passes & 1) ? w.v1 : w.v0;
+    cudaError_t e = cudaMemsetAsync(w.counters, 0, 16 * sizeof(unsigned int), st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(scatter counters)");
+    SegArgs a{keys, vals, n, V + 3u, V, dblock, dxemb, dlogit, col_field, g_emb, g_lr, g_label, w.carryF, w.carryL,
+              w.counters, w.heads, w.longs, T, L, F + 1, D, F, w.DS, make_fastdiv((uint32_t)T), drop_p, seed, rng_stream};
+    const int sgrid = (int)((w.nchunks + 7) / 8);
+    if (D % 4 == 0) k_segment_scan<4><<<sgrid, 256, 0, st>>>(a);
+    else if (D % 2 == 0) k_segment_scan<2><<<sgrid, 256, 0, st>>>(a);
+    else k_segment_scan<1><<<sgrid, 256, 0, st>>>(a);
+    RAT_CHECK_LAUNCH("k_segment_scan");
+    const int fgrid = (int)std::min<long long>((w.nchunks + 7) / 8, (long long)num_sms() * 2);
+    k_fixup_short<<<fgrid, 256, 0, st>>>(a);
+    RAT_CHECK_LAUNCH("k_fixup_short");
+    k_fixup_long<<<(int)std::min<long long>(w.nchunks, (long long)num_sms()), 256, 0, st>>>(a);
+    RAT_CHECK_LAUNCH("k_fixup_long");
     return RAT_OK;
 }
 

@@ -338,6 +338,7 @@ class RatEngine:
         self.lr = torch.full((1,), float(spec.learning_rate), dtype=torch.float32, device=self.device)
         self.world = 1
         self.dist_group = None
+        self._side = None
         try:
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized():
@@ -402,7 +403,7 @@ class RatEngine:
             if nb == 0:
                 raise RuntimeError("RAT backward kernels: tile does not fit in shared memory for this shape")
             ws["bwd_ws"] = torch.empty(nb // 4 + 4, **f32)
-            sb = int(query("rat_emb_scatter_workspace_bytes", B * T * L, D))
+            sb = int(query("rat_emb_scatter_workspace_bytes", B * T * (L + 1), D))
             ws["scatter_ws"] = torch.empty(sb // 4 + 4, dtype=torch.int32, device=dev)
         self._ws[key] = ws
         return ws
@@ -704,8 +705,6 @@ class RatEngine:
         if has_dnn:
             self._dnn_backward(ws, B)
         d = self.encode_backward(ws, B, T)
-        if s.emb_dropout > 0:
-            call("rat_dropout_bwd", d, d.numel(), float(s.emb_dropout), s.seed, self._rng_stream(0), st)
         sw = ws["scatter_ws"]
         gs = self.store
         if gs.shard is None:
@@ -713,9 +712,14 @@ class RatEngine:
             g_lr = gs.G[gs.lr_off:gs.lr_off + s.V] if s.use_wide else None
         else:       # local dense gradient over the global row space; optimizer_step reduce-scatters it to the owners
             g_emb, g_lr = gs.G_emb_full, gs.G_lr_full
+        planned = ws.get("plan_event") is not None
+        if planned:                 # the sorted occurrence index was built on the side stream during fwd / bwd
+            torch.cuda.current_stream().wait_event(ws["plan_event"])
+            ws["plan_event"] = None
         call("rat_emb_scatter_reduce", ws["ids"], ws["labels"], d, ws["dxemb"] if has_dnn else None,
              ws["dlogit"] if s.use_wide else None, self.col_off, self.col_pad, self.col_vocab, self.col_field,
-             g_emb, g_lr, g["label_embedding_layer.weight"], B, T, L, F, D, s.V, sw, sw.numel() * 4, st)
+             g_emb, g_lr, g["label_embedding_layer.weight"], B, T, L, F, D, s.V, float(s.emb_dropout), s.seed,
+             self._rng_stream(0), 1 if planned else 0, sw, sw.numel() * 4, st)      # dropout backward fused (same mask)
 
     def _optimizer_step_sharded(self):
         """net + label gradients: all-reduce; table gradients: reduce-scatter to the row owners; global-norm clip with
@@ -765,6 +769,7 @@ class RatEngine:
         """one full training step on the ids/labels/y_true already in ws. Returns ws['loss'] (device):
         [sum BCE, mean BCE of the local shard]; opt_state[5] holds the regularisation loss."""
         self.rng_step += 1
+        self._plan_scatter(ws, B, T)
         ws["dact"].zero_()
         if ws.get("dact_c") is not None:
             ws["dact_c"].zero_()
@@ -772,6 +777,23 @@ class RatEngine:
         self.backward(ws, B, T)
         self.optimizer_step()
         return ws["loss"]
+
+    def _plan_scatter(self, ws, B, T):
+        """key build + radix sort of the step's occurrences (ids only) on a side stream: off the critical path."""
+        s = self.spec
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(main)                              # ids / labels of this step are in ws
+        self._side.wait_event(ready)
+        sw = ws["scatter_ws"]
+        with torch.cuda.stream(self._side):
+            call("rat_emb_scatter_plan", ws["ids"], ws["labels"], self.col_off, self.col_pad, self.col_vocab, B, T, s.L,
+                 s.F, s.embedding_dim, s.V, sw, sw.numel() * 4, self._side.cuda_stream)
+            done = torch.cuda.Event()
+            done.record(self._side)
+        ws["plan_event"] = done
 
     def materialize_grads(self) -> Dict[str, torch.Tensor]:
         """dense gradients incl. the regulariser (what the reference's .grad holds before clipping). Tests only."""
