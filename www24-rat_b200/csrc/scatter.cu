@@ -7,14 +7,18 @@
 //     k_build_keys        key[i] = table row of occurrence i=(b,t,l) (padding ids -> sentinel); the label token of
 //                         row (b,t) is pseudo column L with key V + label;  val[i] = packed (bt, is-target, column)
 //     k_radix_{hist,scan,scatter} x passes   stable LSD radix sort (8-bit digits) of (key, val)
+//     k_plan_runs         runs of equal keys that cross 32-position chunk boundaries: for every chunk holding the
+//                         HEAD of such a run, find the run's last chunk and emit fix-up work items (<= 32 partial
+//                         records each): short runs get one FINAL item, hot ids get PARTIAL items (second-level
+//                         records) plus one LONG item that combines them
 //   REDUCE (critical path, 3 launches)
 //     k_segment_scan      one warp per 32 sorted positions, LANE = POSITION: every lane loads its occurrence's
 //                         gradient row (all vectors independent -> deep memory-level parallelism), applies the
 //                         dropout mask, and a shuffle segmented scan sums each run of equal keys in a fixed tree
 //                         order; the run's last lane stores the row once.  Runs crossing chunk boundaries leave
-//                         per-chunk partials and the chunk holding the run head is appended to a list.
-//     k_fixup_short       one warp per listed head whose run ends within 32 chunks: partials added in chunk order
-//     k_fixup_long        one block per remaining (hot-id) head: 8 warps add fixed sub-ranges, combined in warp order
+//                         per-chunk partial records (carryL: run head, carryF: continuation).
+//     k_fixup_items       one warp per work item: <= 32 records added in chunk order -> final row or 2nd-level record
+//     k_fixup_long        one block per hot id: its 2nd-level records, 8 warps add fixed sub-ranges, combined in order
 // For a given input every sum has one fixed association => bitwise run-to-run deterministic.
 // The gradient of occurrence (b,t,l) is mask*dBlock[b,t,1+field(l),:] (+ dXemb[b,field(l),:] for the target row
 // t=0, the DNN path) and, for the LR table, dlogit[b] for t=0.
@@ -194,8 +198,11 @@ struct SegArgs {
     float* g_lr;             // [V] or nullptr
     float* g_label;          // [3,D] or nullptr
     float* carryF; float* carryL;   // [nchunks][DS]  (DS = round_up(D+1, 4); element D = LR scalar)
-    unsigned int* counters;  // [0] = #heads, [1] = #long heads
-    unsigned int* heads; unsigned int* longs;
+    float* carry2;           // [..][DS] second-level records of hot ids
+    unsigned int* counters;  // [0] = #items, [1] = #long items, [2] = #second-level records
+    uint4* items;            // {first record chunk, count, kind (0 FINAL: carryL[first] + carryF[first+1..first+count],
+                             //  1 PARTIAL: carryF[first..first+count-1]), destination (key | carry2 slot)}
+    uint4* longs;            // {head chunk, first carry2 slot, #slots, key}
     int T, L, N, D, F, DS;
     FastDiv divT;
     float drop_p; unsigned long long seed; unsigned int stream;
@@ -246,44 +253,40 @@ __global__ void __launch_bounds__(256) k_segment_scan(SegArgs a) {
         const bool cont = start == 0 && p0 > 0 && prev_g == key;
         const bool fwd = lane == 31 && next_g == key;
         if (cont) { dst = a.carryF + chunk * a.DS; dst_lr = dst + a.D; }
-        else if (fwd) {
-            dst = a.carryL + chunk * a.DS; dst_lr = dst + a.D;
-            a.heads[atomicAdd(&a.counters[0], 1u)] = (unsigned int)chunk;        // list order is irrelevant
-        } else { dst = seg_final_row(a, key); dst_lr = (a.g_lr && key < a.V) ? a.g_lr + key : nullptr; }
+        else if (fwd) { dst = a.carryL + chunk * a.DS; dst_lr = dst + a.D; }
+        else { dst = seg_final_row(a, key); dst_lr = (a.g_lr && key < a.V) ? a.g_lr + key : nullptr; }
     }
     bool okk[5];
+    unsigned int rounds = 0;                                 // scan rounds some lane of the warp needs (warp-uniform)
 #pragma unroll
-    for (int s = 0; s < 5; ++s) okk[s] = lane - (1 << s) >= start;
+    for (int s = 0; s < 5; ++s) {
+        okk[s] = lane - (1 << s) >= start;
+        if (__any_sync(FULL, okk[s])) rounds |= 1u << s;
+    }
     const bool drop = a.drop_p > 0.f;
     const float inv_keep = drop ? 1.0f / (1.0f - a.drop_p) : 1.0f;
     const uint32_t thr = dropout_threshold(a.drop_p);
     const uint32_t dkey = dropout_key(a.seed, a.stream), hk0 = lowbias32(dkey);
     const int DV = a.D / VW;
+    const unsigned long long idx0 = e0 / VW;
     for (int v0 = 0; v0 < DV; v0 += SEG_G) {
-        float v[SEG_G][VW];
+        float v[SEG_G][VW], x[SEG_G][VW];
+#pragma unroll
+        for (int g = 0; g < SEG_G; ++g) {                    // every load of the group is issued before any is used
+#pragma unroll
+            for (int k = 0; k < VW; ++k) { v[g][k] = 0.f; x[g][k] = 0.f; }
+            if (valid && v0 + g < DV) vload<VW>(grow + (v0 + g) * VW, v[g]);
+            if (xrow != nullptr && v0 + g < DV) vload<VW>(xrow + (v0 + g) * VW, x[g]);
+        }
 #pragma unroll
         for (int g = 0; g < SEG_G; ++g) {
+            if (drop && valid && v0 + g < DV) dropout_chunk<VW>(v[g], idx0 + (v0 + g), dkey, hk0, thr, inv_keep);
 #pragma unroll
-            for (int k = 0; k < VW; ++k) v[g][k] = 0.f;
-            if (valid && v0 + g < DV) vload<VW>(grow + (v0 + g) * VW, v[g]);
-        }
-        if (drop) {
-#pragma unroll
-            for (int g = 0; g < SEG_G; ++g)
-                if (valid && v0 + g < DV) dropout_chunk<VW>(v[g], e0 / VW + (v0 + g), dkey, hk0, thr, inv_keep);
-        }
-        if (xrow != nullptr) {
-#pragma unroll
-            for (int g = 0; g < SEG_G; ++g)
-                if (v0 + g < DV) {
-                    float x[VW];
-                    vload<VW>(xrow + (v0 + g) * VW, x);
-#pragma unroll
-                    for (int k = 0; k < VW; ++k) v[g][k] += x[k];
-                }
+            for (int k = 0; k < VW; ++k) v[g][k] += x[g][k];
         }
 #pragma unroll
-        for (int s = 0; s < 5; ++s)
+        for (int s = 0; s < 5; ++s) {
+            if (!((rounds >> s) & 1u)) continue;
 #pragma unroll
             for (int g = 0; g < SEG_G; ++g)
 #pragma unroll
@@ -291,6 +294,7 @@ __global__ void __launch_bounds__(256) k_segment_scan(SegArgs a) {
                     const float t = __shfl_up_sync(FULL, v[g][k], 1 << s);
                     if (okk[s]) v[g][k] += t;
                 }
+        }
         if (dst != nullptr) {
 #pragma unroll
             for (int g = 0; g < SEG_G; ++g)
@@ -300,6 +304,7 @@ __global__ void __launch_bounds__(256) k_segment_scan(SegArgs a) {
     if (a.dlogit) {
 #pragma unroll
         for (int s = 0; s < 5; ++s) {
+            if (!((rounds >> s) & 1u)) continue;
             const float t = __shfl_up_sync(FULL, lr, 1 << s);
             if (okk[s]) lr += t;
         }
@@ -307,70 +312,101 @@ __global__ void __launch_bounds__(256) k_segment_scan(SegArgs a) {
     }
 }
 
-// Runs that cross chunk boundaries.  `heads` lists the chunks that hold the HEAD of a forward-spanning run.
-// last chunk `end` of the run = the first cc > c that is the final chunk or does not end inside the run; the result is
-// carryL[c] + carryF[c+1] + ... + carryF[end], added in chunk order.
-__device__ __forceinline__ bool seg_chunk_stops(const SegArgs& a, long long cc, unsigned int key) {
+// ---- runs that cross chunk boundaries --------------------------------------------------------------------------
+// Chunk c holds the HEAD of a forward-spanning run when its last key continues into chunk c+1 and the run did not
+// already enter c from c-1.  The run's last chunk `end` is the first cc > c that is the final chunk or does not end
+// inside the run; the result row is carryL[c] + carryF[c+1] + ... + carryF[end], added in chunk order.
+struct PlanRunsArgs {
+    const unsigned int* keys; long long n; unsigned int sentinel;
+    unsigned int* counters; uint4* items; uint4* longs;
+};
+__device__ __forceinline__ bool seg_chunk_stops(const unsigned int* __restrict__ keys, long long n, long long cc,
+                                                unsigned int key) {
     const long long cl = cc * 32 + 31;
-    return (cl >= a.n - 1) || a.keys[cl] != key || a.keys[cl + 1] != key;
+    return (cl >= n - 1) || keys[cl] != key || keys[cl + 1] != key;
+}
+__global__ void __launch_bounds__(256) k_plan_runs(PlanRunsArgs a) {
+    const int lane = threadIdx.x & 31;
+    const long long nchunks = (a.n + 31) / 32;
+    const long long c = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= nchunks - 1) return;                                       // the last chunk cannot span forward
+    const long long last = c * 32 + 31;
+    const unsigned int key = a.keys[last];
+    if (key == a.sentinel || a.keys[last + 1] != key) return;           // last run does not span forward
+    if (a.keys[c * 32] == key && c > 0 && a.keys[c * 32 - 1] == key) return;   // continues from before: not the head
+    long long end = -1;
+    for (long long base = c + 1; base < nchunks && end < 0; base += 32) {
+        const long long cc = base + lane;
+        const bool stop = cc < nchunks && seg_chunk_stops(a.keys, a.n, cc, key);
+        const unsigned int sm = __ballot_sync(0xffffffffu, stop);
+        if (sm) end = base + __ffs(sm) - 1;
+    }
+    const unsigned int m = (unsigned int)(end - c);                     // carryF records c+1 .. end
+    if (m <= 32u) {
+        if (lane == 0) a.items[atomicAdd(&a.counters[0], 1u)] = make_uint4((unsigned int)c, m, 0u, key);
+        return;
+    }
+    const unsigned int nseg = (m + 31u) / 32u;
+    unsigned int slot0 = 0, item0 = 0;
+    if (lane == 0) {
+        slot0 = atomicAdd(&a.counters[2], nseg);                        // slot numbers do not affect the arithmetic
+        item0 = atomicAdd(&a.counters[0], nseg);
+        a.longs[atomicAdd(&a.counters[1], 1u)] = make_uint4((unsigned int)c, slot0, nseg, key);
+    }
+    slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+    item0 = __shfl_sync(0xffffffffu, item0, 0);
+    for (unsigned int j = lane; j < nseg; j += 32)
+        a.items[item0 + j] = make_uint4((unsigned int)c + 1u + 32u * j, min(32u, m - 32u * j), 1u, slot0 + j);
 }
 
-__global__ void __launch_bounds__(256) k_fixup_short(SegArgs a) {
+__global__ void __launch_bounds__(256) k_fixup_items(SegArgs a) {
     const int lane = threadIdx.x & 31;
-    const unsigned int nheads = a.counters[0];
-    const long long nchunks = (a.n + 31) / 32;
+    const unsigned int nitems = a.counters[0];
     const unsigned int nwarps = gridDim.x * (blockDim.x >> 5);
-    for (unsigned int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < nheads; i += nwarps) {
-        const long long c = a.heads[i];
-        const unsigned int key = a.keys[c * 32 + 31];
-        const long long cc = c + 1 + lane;
-        const bool stop = cc < nchunks && seg_chunk_stops(a, cc, key);
-        const unsigned int sm = __ballot_sync(0xffffffffu, stop);
-        if (sm == 0u) {                                               // hot id: more than 32 chunks -> block-level kernel
-            if (lane == 0) a.longs[atomicAdd(&a.counters[1], 1u)] = (unsigned int)c;
-            continue;
-        }
-        const int m = __ffs(sm);                                      // carryF records c+1 .. c+m
-        float* row = seg_final_row(a, key);
-        for (int e = lane; e <= a.D; e += 32) {
-            float s = a.carryL[c * a.DS + e];
-#pragma unroll 4
-            for (int j = 1; j <= m; ++j) s += a.carryF[(c + j) * a.DS + e];
-            if (e < a.D) { if (row) row[e] = s; }
-            else if (a.g_lr && key < a.V) a.g_lr[key] = s;
+    for (unsigned int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < nitems; i += nwarps) {
+        const uint4 it = a.items[i];
+        const long long c = it.x;
+        const int m = (int)it.y;
+        if (it.z == 0u) {                                              // FINAL: whole run
+            const unsigned int key = it.w;
+            float* row = seg_final_row(a, key);
+            for (int e = lane; e <= a.D; e += 32) {
+                float s = a.carryL[c * a.DS + e];
+#pragma unroll 8
+                for (int j = 1; j <= m; ++j) s += a.carryF[(c + j) * a.DS + e];
+                if (e < a.D) { if (row) row[e] = s; }
+                else if (a.g_lr && key < a.V) a.g_lr[key] = s;
+            }
+        } else {                                                       // PARTIAL: 32 records of a hot id
+            float* dst = a.carry2 + (size_t)it.w * a.DS;
+            for (int e = lane; e <= a.D; e += 32) {
+                float s = a.carryF[c * a.DS + e];
+#pragma unroll 8
+                for (int j = 1; j < m; ++j) s += a.carryF[(c + j) * a.DS + e];
+                dst[e] = s;
+            }
         }
     }
 }
 
-// One BLOCK per long head: the threads find the last chunk of the run in parallel, the 8 warps add contiguous
-// sub-ranges of the per-chunk partials (lane = embedding dimension), and the 8 warp sums are combined in warp order.
+// One BLOCK per hot id: the 8 warps add contiguous sub-ranges of its second-level records (lane = embedding
+// dimension) and the 8 warp sums are combined in warp order after the head partial.
 __global__ void __launch_bounds__(256) k_fixup_long(SegArgs a) {
-    __shared__ long long end_s;
     __shared__ float part[8][132];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long nchunks = (a.n + 31) / 32;
     const unsigned int nlong = a.counters[1];
     for (unsigned int i = blockIdx.x; i < nlong; i += gridDim.x) {
-        const long long c = a.longs[i];
-        const unsigned int key = a.keys[c * 32 + 31];
-        __syncthreads();                                              // part / end_s of the previous head consumed
-        if (threadIdx.x == 0) end_s = nchunks - 1;
-        __syncthreads();
-        for (long long base = c + 1; base < nchunks; base += 256) {
-            const long long cc = base + threadIdx.x;
-            if (cc < nchunks && seg_chunk_stops(a, cc, key)) atomicMin(&end_s, cc);
-            __syncthreads();
-            if (end_s < base + 256) break;
-        }
-        __syncthreads();
-        const long long end = end_s;
-        const long long m = end - c;                                  // number of carryF records
-        const long long per = (m + 7) / 8;
-        const long long lo = c + 1 + warp * per, hi = min(end + 1, lo + per);
+        const uint4 it = a.longs[i];
+        const long long c = it.x;
+        const unsigned int key = it.w;
+        const int nseg = (int)it.z;
+        const int per = (nseg + 7) / 8;
+        const int lo = warp * per, hi = min(nseg, lo + per);
+        __syncthreads();                                              // part of the previous id consumed
         for (int e = lane; e <= a.D; e += 32) {
             float s = 0.f;
 #pragma unroll 4
-            for (long long cc = lo; cc < hi; ++cc) s += a.carryF[cc * a.DS + e];
+            for (int j = lo; j < hi; ++j) s += a.carry2[(size_t)(it.y + j) * a.DS + e];
             part[warp][e] = s;
         }
         __syncthreads();
@@ -394,8 +430,9 @@ using namespace rat;
 
 namespace {
 struct ScatterLayout {
-    unsigned int *k0, *v0, *k1, *v1, *hist, *totals, *counters, *heads, *longs;
-    float *carryF, *carryL;
+    unsigned int *k0, *v0, *k1, *v1, *hist, *totals, *counters;
+    uint4 *items, *longs;
+    float *carryF, *carryL, *carry2;
     long long n, nchunks;
     int nblk, DS;
     size_t bytes;
@@ -413,9 +450,12 @@ ScatterLayout scatter_layout(void* workspace, long long n, int D) {
     w.hist = p; p += ((size_t)256 * w.nblk + 3) / 4 * 4;
     w.totals = p; p += 4 * 256;                                     // [4 passes][256] per-digit key counts
     w.counters = p; p += 16;
-    w.heads = p; p += nc; w.longs = p; p += nc;
+    const size_t n2 = nc / 16 + 8;                                  // second-level records: sum ceil(m_i / 32), m_i > 32
+    w.items = (uint4*)p; p += 4 * (nc + n2);
+    w.longs = (uint4*)p; p += 4 * (nc / 32 + 4);
     w.carryF = (float*)p; p += nc * w.DS;
     w.carryL = (float*)p; p += nc * w.DS;
+    w.carry2 = (float*)p; p += n2 * w.DS;
     w.bytes = (size_t)((char*)p - (char*)workspace);
     return w;
 }
@@ -463,6 +503,9 @@ extern "C" int rat_emb_scatter_plan(const int* ids, const int* labels, const int
         std::swap(ki, ko);
         std::swap(vi, vo);
     }
+    PlanRunsArgs pr{ki, n, V + 3u, w.counters, w.items, w.longs};
+    k_plan_runs<<<(int)((w.nchunks + 7) / 8), 256, 0, st>>>(pr);
+    RAT_CHECK_LAUNCH("k_plan_runs");
     return RAT_OK;
 }
 
@@ -487,18 +530,16 @@ extern "C" int rat_emb_scatter_reduce(const int* ids, const int* labels, const f
     const int passes = (key_bits(V + 3u) + 7) / 8;
     const unsigned int* keys = (passes & 1) ? w.k1 : w.k0;
     const unsigned int* vals = (passes & 1) ? w.v1 : w.v0;
-    cudaError_t e = cudaMemsetAsync(w.counters, 0, 16 * sizeof(unsigned int), st);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(scatter counters)");
     SegArgs a{keys, vals, n, V + 3u, V, dblock, dxemb, dlogit, col_field, g_emb, g_lr, g_label, w.carryF, w.carryL,
-              w.counters, w.heads, w.longs, T, L, F + 1, D, F, w.DS, make_fastdiv((uint32_t)T), drop_p, seed, rng_stream};
+              w.carry2, w.counters, w.items, w.longs, T, L, F + 1, D, F, w.DS, make_fastdiv((uint32_t)T), drop_p, seed, rng_stream};
     const int sgrid = (int)((w.nchunks + 7) / 8);
     if (D % 4 == 0) k_segment_scan<4><<<sgrid, 256, 0, st>>>(a);
     else if (D % 2 == 0) k_segment_scan<2><<<sgrid, 256, 0, st>>>(a);
     else k_segment_scan<1><<<sgrid, 256, 0, st>>>(a);
     RAT_CHECK_LAUNCH("k_segment_scan");
     const int fgrid = (int)std::min<long long>((w.nchunks + 7) / 8, (long long)num_sms() * 2);
-    k_fixup_short<<<fgrid, 256, 0, st>>>(a);
-    RAT_CHECK_LAUNCH("k_fixup_short");
+    k_fixup_items<<<fgrid, 256, 0, st>>>(a);
+    RAT_CHECK_LAUNCH("k_fixup_items");
     k_fixup_long<<<(int)std::min<long long>(w.nchunks, (long long)num_sms()), 256, 0, st>>>(a);
     RAT_CHECK_LAUNCH("k_fixup_long");
     return RAT_OK;
