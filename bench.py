@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--pool-rows", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=512)
+    ap.add_argument("--shard-tables", action="store_true",
+                    help="row-shard the embedding / LR tables over the ranks (BASELINE configs[2]; needs --gpus > 1)")
+    ap.add_argument("--vocab-scale", type=float, default=1.0, help="scale every vocabulary (scaled-vocab tmall variant)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"],
                     help="RAT-block projection arithmetic: bf16 = tcgen05 (default), tf32 = mma.sync, fp32 = SIMT")
     return ap.parse_args()
@@ -168,12 +171,17 @@ def run_ours(a):
     seed_everything(2021)
     B, K, S = a.batch, a.topk, a.shape
     cfg = shapes.SHAPES[S]
-    fm = shapes.make_feature_map(S)
+    fm = shapes.make_feature_map(S, vocab_scale=a.vocab_scale)
     params = shapes.model_params(S, K=K, gpu=local)
+    sharded = bool(a.shard_tables and world > 1)
+    if sharded:
+        params["shard_embeddings"] = True
     os.makedirs(os.path.join(params["model_root"], fm.dataset_id), exist_ok=True)
     model = models.RAT_m2(fm, **params)
-    if world > 1:                               # identical replicas: broadcast rank 0's initial weights
+    if world > 1 and not sharded:               # identical replicas: broadcast rank 0's initial weights
         dist.broadcast(model._engine.store.W, 0)
+    elif sharded:                               # replicated part only; every rank keeps its own table shard
+        dist.broadcast(model._engine.store.W[:model._engine.store.emb_off], 0)
     n_params = model.count_parameters()
     hp = cfg["hp"]
     F, L, D, H = fm.num_fields, fm.input_length, hp["embedding_dim"], hp["num_heads"]
@@ -263,8 +271,8 @@ def run_ours(a):
                         "backward core runs ~380 SASS instructions per (sequence, head) task around 12 mma.sync, see "
                         "profiles/ and DESIGN.md section 3"}
     gb = B * gather_bytes_per_sample(K, L, F, D)
-    g_ms = per_call_ms("rat_gather_fwd")
-    roofline_gather = {"kernel": "k_gather_flat", "bound": "hbm", "achieved": round(gb / (g_ms * 1e-3) / 1e9, 1),
+    g_ms = per_call_ms("rat_gather_fwd_sharded" if sharded else "rat_gather_fwd")
+    roofline_gather = {"kernel": "k_gather_flat" + (" (rows loaded from the owners' shards over NVLink peer pointers)" if sharded else ""), "bound": "hbm", "achieved": round(gb / (g_ms * 1e-3) / 1e9, 1),
                        "peak": pk["hbm"], "unit": "GB/s", "frac": round(gb / (g_ms * 1e-3) / 1e9 / pk["hbm"], 4),
                        "traffic": NCU_TRAFFIC.get("gather"), "bytes_per_launch": gb, "peak_source": pk["src"],
                        "avg_launch_ms": round(g_ms, 4)}
@@ -300,7 +308,8 @@ def run_ours(a):
         "config": {"workload": f"RAT_m2 {cfg['dataset_id']} shape, K={K}, B={B}/GPU, train step (fwd+bwd+clip+Adam)",
                    "precision": a.precision,
                    "global_batch": gB, "topK": K, "fields": F, "input_length": L, "embedding_dim": D, "heads": H,
-                   "params": n_params, "pool_rows": a.pool_rows, "parallelism": f"dp{world}",
+                   "params": n_params, "pool_rows": a.pool_rows, "parallelism": f"dp{world}" + ("+row-sharded tables (NVLink peer loads, reduce-scatter)" if sharded else ""),
+                   "vocab_scale": a.vocab_scale,
                    "l2": "every step uses a new batch; per-step working set (~660 MB activations) exceeds the 126 MB L2"},
         "e2e": {"value": round(a.steps * gB / t_e2e, 1), "unit": "samples/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "api": "fuxictr.pytorch.models.RAT_m2.train_step(host f64 wire batch)"},

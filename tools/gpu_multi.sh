@@ -1,0 +1,21 @@
+#!/bin/bash
+# multi-GPU checks (run with gpurun --gpus N): sharded == replicated, bench at N (kkbox replicated, tmall row-sharded)
+N=${1:-2}
+mkdir -p gpurun_out
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
+{
+echo "== check_sharded tmall"; timeout 600 $TR tools/check_sharded.py tmall 512 0.05 2>&1 | tail -3
+echo "== check_sharded kkbox"; timeout 600 $TR tools/check_sharded.py kkbox 256 0.05 2>&1 | tail -3
+echo "== bench kkbox N=$N"; timeout 900 $TR bench.py --gpus $N --steps 10 --warmup 3 2>&1 | tail -2
+echo "== bench tmall N=$N row-sharded"; timeout 900 $TR bench.py --gpus $N --steps 10 --warmup 3 --shape tmall --shard-tables 2>&1 | tail -2
+echo "== bench tmall N=$N row-sharded x20 vocab"; timeout 900 $TR bench.py --gpus $N --steps 10 --warmup 3 --shape tmall --shard-tables --vocab-scale 20 2>&1 | tail -2
+echo "== bench tmall N=$N replicated"; timeout 900 $TR bench.py --gpus $N --steps 10 --warmup 3 --shape tmall 2>&1 | tail -2
+} > gpurun_out/multi_$N.log 2>&1
+python - <<PY
+import json
+for l in open("gpurun_out/multi_$N.log"):
+    if l.startswith("{"):
+        d = json.loads(l); print("  ", d["config"]["workload"][:40], d["config"]["parallelism"][:30], "train", d["value"], "ms", d["ms_per_step"], "e2e", d["e2e"]["value"], "infer", d["infer"]["value"])
+    else:
+        print(l.rstrip()[-400:])
+PY

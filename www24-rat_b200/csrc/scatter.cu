@@ -11,14 +11,14 @@
 //                         HEAD of such a run, find the run's last chunk and emit fix-up work items (<= 32 partial
 //                         records each): short runs get one FINAL item, hot ids get PARTIAL items (second-level
 //                         records) plus one LONG item that combines them
-//   REDUCE (critical path, 3 launches)
+//   REDUCE (critical path, 2 launches)
 //     k_segment_scan      one warp per 32 sorted positions, LANE = POSITION: every lane loads its occurrence's
 //                         gradient row (all vectors independent -> deep memory-level parallelism), applies the
 //                         dropout mask, and a shuffle segmented scan sums each run of equal keys in a fixed tree
 //                         order; the run's last lane stores the row once.  Runs crossing chunk boundaries leave
 //                         per-chunk partial records (carryL: run head, carryF: continuation).
-//     k_fixup_items       one warp per work item: <= 32 records added in chunk order -> final row or 2nd-level record
-//     k_fixup_long        one block per hot id: its 2nd-level records, 8 warps add fixed sub-ranges, combined in order
+//     k_fixup_items       one warp per work item: <= 32 records (lane = record, fixed butterfly) -> final row or
+//                         2nd-level record; the warp finishing a hot id's last item combines its 2nd-level records
 // For a given input every sum has one fixed association => bitwise run-to-run deterministic.
 // The gradient of occurrence (b,t,l) is mask*dBlock[b,t,1+field(l),:] (+ dXemb[b,field(l),:] for the target row
 // t=0, the DNN path) and, for the LR table, dlogit[b] for t=0.
@@ -201,8 +201,9 @@ struct SegArgs {
     float* carry2;           // [..][DS] second-level records of hot ids
     unsigned int* counters;  // [0] = #items, [1] = #long items, [2] = #second-level records
     uint4* items;            // {first record chunk, count, kind (0 FINAL: carryL[first] + carryF[first+1..first+count],
-                             //  1 PARTIAL: carryF[first..first+count-1]), destination (key | carry2 slot)}
+                             //  1+i PARTIAL of hot id i: carryF[first..first+count-1]), destination (key | carry2 slot)}
     uint4* longs;            // {head chunk, first carry2 slot, #slots, key}
+    unsigned int* done;      // [#hot ids] finished PARTIAL items (the warp finishing the last one combines them)
     int T, L, N, D, F, DS;
     FastDiv divT;
     float drop_p; unsigned long long seed; unsigned int stream;
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(256) k_segment_scan(SegArgs a) {
 // inside the run; the result row is carryL[c] + carryF[c+1] + ... + carryF[end], added in chunk order.
 struct PlanRunsArgs {
     const unsigned int* keys; long long n; unsigned int sentinel;
-    unsigned int* counters; uint4* items; uint4* longs;
+    unsigned int* counters; uint4* items; uint4* longs; unsigned int* done;
 };
 __device__ __forceinline__ bool seg_chunk_stops(const unsigned int* __restrict__ keys, long long n, long long cc,
                                                 unsigned int key) {
@@ -342,82 +343,130 @@ __global__ void __launch_bounds__(256) k_plan_runs(PlanRunsArgs a) {
         if (sm) end = base + __ffs(sm) - 1;
     }
     const unsigned int m = (unsigned int)(end - c);                     // carryF records c+1 .. end
-    if (m <= 32u) {
+    if (m <= 31u) {                                                     // head partial + m records fit one warp
         if (lane == 0) a.items[atomicAdd(&a.counters[0], 1u)] = make_uint4((unsigned int)c, m, 0u, key);
         return;
     }
     const unsigned int nseg = (m + 31u) / 32u;
-    unsigned int slot0 = 0, item0 = 0;
+    unsigned int slot0 = 0, item0 = 0, li = 0;
     if (lane == 0) {
         slot0 = atomicAdd(&a.counters[2], nseg);                        // slot numbers do not affect the arithmetic
         item0 = atomicAdd(&a.counters[0], nseg);
-        a.longs[atomicAdd(&a.counters[1], 1u)] = make_uint4((unsigned int)c, slot0, nseg, key);
+        li = atomicAdd(&a.counters[1], 1u);
+        a.longs[li] = make_uint4((unsigned int)c, slot0, nseg, key);
+        a.done[li] = 0u;
     }
     slot0 = __shfl_sync(0xffffffffu, slot0, 0);
     item0 = __shfl_sync(0xffffffffu, item0, 0);
+    li = __shfl_sync(0xffffffffu, li, 0);
     for (unsigned int j = lane; j < nseg; j += 32)
-        a.items[item0 + j] = make_uint4((unsigned int)c + 1u + 32u * j, min(32u, m - 32u * j), 1u, slot0 + j);
+        a.items[item0 + j] = make_uint4((unsigned int)c + 1u + 32u * j, min(32u, m - 32u * j), 1u + li, slot0 + j);
 }
 
-__global__ void __launch_bounds__(256) k_fixup_items(SegArgs a) {
+// LANE = RECORD: lane j loads record j of the item (all loads independent: one memory round trip), a fixed xor
+// butterfly adds the <= 32 records, lane q of every group of 4 vectors stores vector q.  DS % 4 == 0, 16-byte records.
+// The warp that finishes the LAST partial item of a hot id combines that id's second-level records (slot order, 32 at
+// a time, same butterfly) after the head partial -- whichever warp it is, the association is the same.
+// FX_G groups of 4 float4 are handled together (3: 12 vectors = 48 floats >= DS of D <= 44 in one pass)
+template <int FX_G>
+__device__ __forceinline__ void seg_store_vecs(const SegArgs& a, const float4 (&v)[FX_G][4], int vb, int NV, int lane,
+                                               float* row, float* dst_lr) {
+#pragma unroll
+    for (int g = 0; g < FX_G; ++g)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int vec = vb + 4 * g + q;
+            if (lane != 4 * g + q || vec >= NV) continue;              // lane 4g+q stores vector 4g+q of the pass
+            const float f[4] = {v[g][q].x, v[g][q].y, v[g][q].z, v[g][q].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int e = 4 * vec + k;
+                if (e < a.D) { if (row) row[e] = f[k]; }
+                else if (e == a.D && dst_lr) *dst_lr = f[k];
+            }
+        }
+}
+template <int FX_G>
+__device__ __forceinline__ void seg_butterfly(float4 (&v)[FX_G][4]) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int g = 0; g < FX_G; ++g)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                v[g][q].x += __shfl_xor_sync(0xffffffffu, v[g][q].x, o); v[g][q].y += __shfl_xor_sync(0xffffffffu, v[g][q].y, o);
+                v[g][q].z += __shfl_xor_sync(0xffffffffu, v[g][q].z, o); v[g][q].w += __shfl_xor_sync(0xffffffffu, v[g][q].w, o);
+            }
+}
+// v[g][q] = vector vb + 4g + q of record `rec` (zeros when rec == nullptr or past the record); CG = bypass L1
+template <bool CG, int FX_G>
+__device__ __forceinline__ void seg_load_vecs(const float* rec, int vb, int NV, float4 (&v)[FX_G][4]) {
+#pragma unroll
+    for (int g = 0; g < FX_G; ++g)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int vec = vb + 4 * g + q;
+            v[g][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rec != nullptr && vec < NV) {
+                const float4* p = reinterpret_cast<const float4*>(rec + 4 * vec);
+                v[g][q] = CG ? __ldcg(p) : *p;
+            }
+        }
+}
+
+__global__ void __launch_bounds__(256, 3) k_fixup_items(SegArgs a) {
     const int lane = threadIdx.x & 31;
     const unsigned int nitems = a.counters[0];
     const unsigned int nwarps = gridDim.x * (blockDim.x >> 5);
+    const int NV = a.DS >> 2;
     for (unsigned int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < nitems; i += nwarps) {
         const uint4 it = a.items[i];
         const long long c = it.x;
         const int m = (int)it.y;
-        if (it.z == 0u) {                                              // FINAL: whole run
-            const unsigned int key = it.w;
-            float* row = seg_final_row(a, key);
-            for (int e = lane; e <= a.D; e += 32) {
-                float s = a.carryL[c * a.DS + e];
-#pragma unroll 8
-                for (int j = 1; j <= m; ++j) s += a.carryF[(c + j) * a.DS + e];
-                if (e < a.D) { if (row) row[e] = s; }
-                else if (a.g_lr && key < a.V) a.g_lr[key] = s;
-            }
-        } else {                                                       // PARTIAL: 32 records of a hot id
-            float* dst = a.carry2 + (size_t)it.w * a.DS;
-            for (int e = lane; e <= a.D; e += 32) {
-                float s = a.carryF[c * a.DS + e];
-#pragma unroll 8
-                for (int j = 1; j < m; ++j) s += a.carryF[(c + j) * a.DS + e];
-                dst[e] = s;
-            }
+        const bool fin = it.z == 0u;
+        // FINAL: records carryL[c], carryF[c+1 .. c+m] (m <= 31);  PARTIAL: carryF[c .. c+m-1] (m <= 32)
+        const float* rec = nullptr;
+        if (fin) { if (lane <= m) rec = (lane == 0 ? a.carryL : a.carryF) + (c + lane) * a.DS; }
+        else if (lane < m) rec = a.carryF + (c + lane) * a.DS;
+        float* row = nullptr;
+        float* dst_lr = nullptr;
+        if (fin) { row = seg_final_row(a, it.w); dst_lr = (a.g_lr && it.w < a.V) ? a.g_lr + it.w : nullptr; }
+        else { row = a.carry2 + (size_t)it.w * a.DS; dst_lr = row + a.D; }
+        for (int vb = 0; vb < NV; vb += 12) {                            // one memory round trip for D <= 44
+            float4 v[3][4];
+            seg_load_vecs<false, 3>(rec, vb, NV, v);
+            seg_butterfly<3>(v);
+            seg_store_vecs<3>(a, v, vb, NV, lane, row, dst_lr);
         }
-    }
-}
-
-// One BLOCK per hot id: the 8 warps add contiguous sub-ranges of its second-level records (lane = embedding
-// dimension) and the 8 warp sums are combined in warp order after the head partial.
-__global__ void __launch_bounds__(256) k_fixup_long(SegArgs a) {
-    __shared__ float part[8][132];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned int nlong = a.counters[1];
-    for (unsigned int i = blockIdx.x; i < nlong; i += gridDim.x) {
-        const uint4 it = a.longs[i];
-        const long long c = it.x;
-        const unsigned int key = it.w;
-        const int nseg = (int)it.z;
-        const int per = (nseg + 7) / 8;
-        const int lo = warp * per, hi = min(nseg, lo + per);
-        __syncthreads();                                              // part of the previous id consumed
-        for (int e = lane; e <= a.D; e += 32) {
-            float s = 0.f;
-#pragma unroll 4
-            for (int j = lo; j < hi; ++j) s += a.carry2[(size_t)(it.y + j) * a.DS + e];
-            part[warp][e] = s;
+        if (fin) continue;
+        // ---- hot id: am I the last partial item of it?
+        const unsigned int li = it.z - 1u;
+        const uint4 lg = a.longs[li];                                    // {head chunk, first slot, #slots, key}
+        unsigned int last = 0;
+        __threadfence();                                                 // this warp's second-level record is visible
+        __syncwarp();
+        if (lane == 0) {
+            last = atomicAdd(&a.done[li], 1u) == lg.z - 1u ? 1u : 0u;
+            if (last) a.done[li] = 0u;                                   // the plan stays reusable
         }
-        __syncthreads();
-        if (warp == 0) {
-            float* row = seg_final_row(a, key);
-            for (int e = lane; e <= a.D; e += 32) {
-                float s = a.carryL[c * a.DS + e];
-                for (int w = 0; w < 8; ++w) s += part[w][e];
-                if (e < a.D) { if (row) row[e] = s; }
-                else if (a.g_lr && key < a.V) a.g_lr[key] = s;
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (!last) continue;
+        __threadfence();
+        float* frow = seg_final_row(a, lg.w);
+        float* flr = (a.g_lr && lg.w < a.V) ? a.g_lr + lg.w : nullptr;
+        for (int vb = 0; vb < NV; vb += 4) {                             // rare path: 4 vectors at a time (registers)
+            float4 tot[1][4];
+            seg_load_vecs<true, 1>(a.carryL + (size_t)lg.x * a.DS, vb, NV, tot);     // head partial first
+            for (unsigned int s0 = 0; s0 < lg.z; s0 += 32) {
+                float4 v[1][4];
+                seg_load_vecs<true, 1>(s0 + lane < lg.z ? a.carry2 + (size_t)(lg.y + s0 + lane) * a.DS : nullptr, vb, NV, v);
+                seg_butterfly<1>(v);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    tot[0][q].x += v[0][q].x; tot[0][q].y += v[0][q].y; tot[0][q].z += v[0][q].z; tot[0][q].w += v[0][q].w;
+                }
             }
+            seg_store_vecs<1>(a, tot, vb, NV, lane, frow, flr);
         }
     }
 }
@@ -432,6 +481,7 @@ namespace {
 struct ScatterLayout {
     unsigned int *k0, *v0, *k1, *v1, *hist, *totals, *counters;
     uint4 *items, *longs;
+    unsigned int* done;
     float *carryF, *carryL, *carry2;
     long long n, nchunks;
     int nblk, DS;
@@ -453,6 +503,7 @@ ScatterLayout scatter_layout(void* workspace, long long n, int D) {
     const size_t n2 = nc / 16 + 8;                                  // second-level records: sum ceil(m_i / 32), m_i > 32
     w.items = (uint4*)p; p += 4 * (nc + n2);
     w.longs = (uint4*)p; p += 4 * (nc / 32 + 4);
+    w.done = p; p += (nc / 32 + 4 + 3) / 4 * 4;
     w.carryF = (float*)p; p += nc * w.DS;
     w.carryL = (float*)p; p += nc * w.DS;
     w.carry2 = (float*)p; p += n2 * w.DS;
@@ -503,7 +554,7 @@ extern "C" int rat_emb_scatter_plan(const int* ids, const int* labels, const int
         std::swap(ki, ko);
         std::swap(vi, vo);
     }
-    PlanRunsArgs pr{ki, n, V + 3u, w.counters, w.items, w.longs};
+    PlanRunsArgs pr{ki, n, V + 3u, w.counters, w.items, w.longs, w.done};
     k_plan_runs<<<(int)((w.nchunks + 7) / 8), 256, 0, st>>>(pr);
     RAT_CHECK_LAUNCH("k_plan_runs");
     return RAT_OK;
@@ -531,17 +582,15 @@ extern "C" int rat_emb_scatter_reduce(const int* ids, const int* labels, const f
     const unsigned int* keys = (passes & 1) ? w.k1 : w.k0;
     const unsigned int* vals = (passes & 1) ? w.v1 : w.v0;
     SegArgs a{keys, vals, n, V + 3u, V, dblock, dxemb, dlogit, col_field, g_emb, g_lr, g_label, w.carryF, w.carryL,
-              w.carry2, w.counters, w.items, w.longs, T, L, F + 1, D, F, w.DS, make_fastdiv((uint32_t)T), drop_p, seed, rng_stream};
+              w.carry2, w.counters, w.items, w.longs, w.done, T, L, F + 1, D, F, w.DS, make_fastdiv((uint32_t)T), drop_p, seed, rng_stream};
     const int sgrid = (int)((w.nchunks + 7) / 8);
     if (D % 4 == 0) k_segment_scan<4><<<sgrid, 256, 0, st>>>(a);
     else if (D % 2 == 0) k_segment_scan<2><<<sgrid, 256, 0, st>>>(a);
     else k_segment_scan<1><<<sgrid, 256, 0, st>>>(a);
     RAT_CHECK_LAUNCH("k_segment_scan");
-    const int fgrid = (int)std::min<long long>((w.nchunks + 7) / 8, (long long)num_sms() * 2);
+    const int fgrid = (int)std::min<long long>((w.nchunks + 7) / 8, (long long)num_sms() * 4);
     k_fixup_items<<<fgrid, 256, 0, st>>>(a);
     RAT_CHECK_LAUNCH("k_fixup_items");
-    k_fixup_long<<<(int)std::min<long long>(w.nchunks, (long long)num_sms()), 256, 0, st>>>(a);
-    RAT_CHECK_LAUNCH("k_fixup_long");
     return RAT_OK;
 }
 

@@ -569,6 +569,8 @@ class RatEngine:
                  self.p["label_embedding_layer.weight"], ws["ids"], ws["labels"], self.col_off, self.col_vocab,
                  self.field_col0, self.field_width, ws["acts"][0], ws["x_emb"], ws["lr_out"], B, T, L, F, D,
                  float(drop), s.seed, self._rng_stream(0), self.err_flag, st)
+        if training:                # after the gather is queued: the sort overlaps the RAT-block kernels, not the gather
+            self._plan_scatter(ws, B, T)
         enc = self.encode(ws, B, T, training)
         ws["enc_out"] = enc
         if len(s.dnn_hidden_units):
@@ -769,7 +771,6 @@ class RatEngine:
         """one full training step on the ids/labels/y_true already in ws. Returns ws['loss'] (device):
         [sum BCE, mean BCE of the local shard]; opt_state[5] holds the regularisation loss."""
         self.rng_step += 1
-        self._plan_scatter(ws, B, T)
         ws["dact"].zero_()
         if ws.get("dact_c") is not None:
             ws["dact_c"].zero_()
