@@ -50,8 +50,9 @@ def parse():
     ap.add_argument("--shard-tables", action="store_true",
                     help="row-shard the embedding / LR tables over the ranks (BASELINE configs[2]; needs --gpus > 1)")
     ap.add_argument("--vocab-scale", type=float, default=1.0, help="scale every vocabulary (scaled-vocab tmall variant)")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"],
-                    help="RAT-block projection arithmetic: bf16 = tcgen05 (default), tf32 = mma.sync, fp32 = SIMT")
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "tf32", "fp32"],
+                    help="projection / DNN GEMM arithmetic: fp16 = tcgen05, fp16 operands + fp32 accumulate (default), "
+                         "tf32 = mma.sync, fp32 = SIMT")
     return ap.parse_args()
 
 
@@ -258,7 +259,7 @@ def run_ours(a):
     ab_ms = per_call_ms("rat_attn_bwd")
     ach_tf = attn_bwd_flops / (ab_ms * 1e-3) / 1e12
     ab_bytes = rows_tok * D * 4 * 3
-    tc_mode = a.precision == "bf16"
+    tc_mode = a.precision == "fp16"
     roofline = {"kernel": "k_attn_bwd_tc (+k_reduce_attn_tc)" if tc_mode else "k_attn_bwd (+k_reduce_attn)",
                 "bound": "tensor", "achieved": round(ach_tf, 3),
                 "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": round(ach_tf / pk["tf_sustained"], 5),
@@ -304,7 +305,7 @@ def run_ours(a):
         "metric": "RAT_m2 train samples/sec", "value": round(a.steps * gB / t_train, 1), "unit": "samples/s",
         "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(t_train / a.steps * 1e3, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"bf16": "bf16", "tf32": "tf32", "fp32": "f32"}[a.precision], "data": "synthetic",
+        "dtype": {"fp16": "f16", "tf32": "tf32", "fp32": "f32"}[a.precision], "data": "synthetic",
         "config": {"workload": f"RAT_m2 {cfg['dataset_id']} shape, K={K}, B={B}/GPU, train step (fwd+bwd+clip+Adam)",
                    "precision": a.precision,
                    "global_batch": gB, "topK": K, "fields": F, "input_length": L, "embedding_dim": D, "heads": H,

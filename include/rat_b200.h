@@ -115,8 +115,17 @@ int rat_layernorm_fwd(const float* x, float* out, const float* w, const float* b
  * ------------------------------------------------------------------------------------------------------- */
 /* C[M,N] = opA(A) opB(B) (+bias[n]).  trans_a=0: A[m*lda+k], 1: A[k*lda+m]; trans_b=0: B[n*ldb+k] (torch Linear
  * weight), 1: B[k*ldb+n].  Replaces the nn.Linear calls of MLP_Layer (layers/deep.py:126,137) and their
- * autograd backward.  Deterministic split-K when a workspace of rat_sgemm_workspace_bytes() is supplied. */
+ * autograd backward.  Deterministic split-K when a workspace of rat_sgemm_workspace_bytes() is supplied.
+ * rat_sgemm_scaled: backward products (A = dz).  a_amax (device float, may be NULL) holds max|A| (rat_absmax); in the
+ * tensor-core precision mode (fp16 operands) A is lifted by the power of two that puts that maximum into [4, 8) while
+ * it is converted and the fp32 accumulator is unscaled, so that small gradients stay in the fp16 normal range and
+ * large ones cannot overflow.  The fp32 / tf32 kernels ignore it.  rat_sgemm == a_amax NULL.
+ * rat_absmax: *out = max(*out, max |x[r*row_stride + c]|) over r < rows, c < cols (caller zeroes *out). */
 size_t rat_sgemm_workspace_bytes(int M, int N, int K);
+int rat_sgemm_scaled(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda, int ldb,
+                     int ldc, int trans_a, int trans_b, const float* a_amax, float* workspace, size_t workspace_bytes,
+                     void* stream);
+int rat_absmax(const float* x, long long rows, int cols, long long row_stride, float* out, void* stream);
 int rat_sgemm(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda, int ldb,
               int ldc, int trans_a, int trans_b, float* workspace, size_t workspace_bytes, void* stream);
 /* BatchNorm1d (layers/deep.py:128-129), train mode: raw per-column sums (double, [2C]: sum, sum of squares) so a
@@ -154,18 +163,21 @@ int rat_head(const float* enc, long long enc_stride, const float* fc_w, const fl
  * deterministically (per-CTA partials in `workspace`, fixed-order reduction) and STORED to dW* (dWq is
  * accumulated instead when accumulate_wq != 0: RAT_m3 shares W_q between its two attentions).
  * dx may alias dout/base (in place).  Any dW* pointer may be NULL (gradient discarded).
+ * dout_amax / dx_amax (device floats, may be NULL): dynamic gradient scaling of the fp16 tensor-core mode.  *dout_amax
+ * = max|dout| lets the kernel lift dout by a power of two into the fp16 normal range (results are unscaled in fp32);
+ * max|dx| is merged into *dx_amax (caller-zeroed) for the next kernel of the chain.  NULL dout_amax = no scaling.
  * ------------------------------------------------------------------------------------------------------- */
 size_t rat_attn_bwd_workspace_bytes(int B, int T, int N, int D, int heads, int dim_head, int mode);
 int rat_attn_bwd(const float* x, const float* dout, const float* base, float* dx, const float* ln_w,
                  const float* ln_b, const float* Wq, const float* Wk, const float* Wv, const float* Wo, float* dWq,
                  float* dWk, float* dWv, float* dWo, float* dbo, float* dln_w, float* dln_b, int accumulate_wq, int B,
-                 int T, int N, int D, int heads, int dim_head, float scale, float alpha, int mode, float* workspace,
-                 size_t workspace_bytes, void* stream);
+                 int T, int N, int D, int heads, int dim_head, float scale, float alpha, int mode,
+                 const float* dout_amax, float* dx_amax, float* workspace, size_t workspace_bytes, void* stream);
 size_t rat_ff_bwd_workspace_bytes(long long rows, int D, int M);
 int rat_ff_bwd(const float* x, const float* dout, const float* base, float* dx, const float* ln_w, const float* ln_b,
                const float* W1, const float* b1, const float* W2, float* dW1, float* db1, float* dW2, float* db2,
-               float* dln_w, float* dln_b, long long rows, int D, int M, float* workspace, size_t workspace_bytes,
-               void* stream);
+               float* dln_w, float* dln_b, long long rows, int D, int M, const float* dout_amax, float* dx_amax,
+               float* workspace, size_t workspace_bytes, void* stream);
 size_t rat_layernorm_bwd_workspace_bytes(long long rows, int D);
 int rat_layernorm_bwd(const float* x, const float* dout, float* dx, const float* w, float* dw, float* db,
                       long long rows, int D, float* workspace, size_t workspace_bytes, void* stream);

@@ -27,7 +27,7 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
-@pytest.fixture(params=["fp32", "tf32", "bf16"])
+@pytest.fixture(params=["fp32", "tf32", "fp16"])
 def precision(request):
     """run a GPU test in both arithmetic modes of the RAT-block projections."""
     import rat_native
@@ -36,5 +36,5 @@ def precision(request):
     set_precision(request.param)
     gpu_util.PREC["mode"] = request.param
     yield request.param
-    set_precision("tf32")
-    gpu_util.PREC["mode"] = "tf32"
+    set_precision("fp16")     # back to the library default
+    gpu_util.PREC["mode"] = "fp16"

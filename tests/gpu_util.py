@@ -6,15 +6,15 @@ from oracle import rat_oracle as O
 from rat_native.engine import EngineSpec, FeatureSpec, RatEngine
 
 
-PREC = {"mode": "fp32"}
+PREC = {"mode": "fp16"}
 
 
 def tf32():
-    return PREC["mode"] in ("tf32", "bf16")
+    return PREC["mode"] in ("tf32", "bf16", "fp16")
 
 
 def bf16():
-    return PREC["mode"] == "bf16"
+    return PREC["mode"] in ("bf16", "fp16")
 
 
 def ptol(rtol, atol, rt=1e-2, at_scale=40.0):

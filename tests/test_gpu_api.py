@@ -70,7 +70,7 @@ def test_state_dict_keys_and_forward_match_reference(name, tmp_path):
     model.load_weights(model.checkpoint)
     for k, v in model.state_dict().items():
         assert torch.equal(v, before[k]), k
-    set_precision("tf32")
+    set_precision("fp16")     # back to the library default
 
 
 def _write_dataset(tmp_path, fm, n_train=1500, n_valid=400, K=5, seed=0):

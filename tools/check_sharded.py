@@ -16,7 +16,7 @@ from fuxictr.pytorch.data_generator import DeviceDataGenerator
 shape = sys.argv[1] if len(sys.argv) > 1 else "tmall"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 vscale = float(sys.argv[3]) if len(sys.argv) > 3 else 0.05
-set_precision("bf16")
+set_precision("fp16")
 K = 5
 fm = shapes.make_feature_map(shape, vocab_scale=vscale)
 

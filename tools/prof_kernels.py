@@ -13,7 +13,7 @@ B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 K = 5
 from rat_native.engine import set_precision
-set_precision(sys.argv[4] if len(sys.argv) > 4 else "bf16")
+set_precision(sys.argv[4] if len(sys.argv) > 4 else "fp16")
 fm = shapes.make_feature_map(shape)
 params = shapes.model_params(shape, K=K, gpu=0)
 os.makedirs(os.path.join(params["model_root"], fm.dataset_id), exist_ok=True)

@@ -105,6 +105,25 @@ __device__ __forceinline__ float dropout_scale(unsigned long long seed, uint32_t
     return dropout_lane16(r, (int)(e & 7)) < dropout_threshold(p) ? 0.0f : inv_keep;
 }
 
+// ---- dynamic gradient scaling of the fp16 tensor-core path.  Every kernel that writes a gradient tensor publishes
+// max|dx| into a device slot (order-independent integer atomicMax on the bits of a non-negative float); the kernel
+// that consumes the tensor lifts it by the power of two that puts that maximum into [4, 8) -- 2^13 of fp16 headroom for
+// growth inside the kernel, 2^-17 of the maximum still a normal number -- and unscales its fp32 results.
+__device__ __forceinline__ float grad_scale_from_amax(const float* amax) {
+    if (amax == nullptr) return 1.0f;
+    const float m = *amax;
+    if (!(m > 0.f) || m > 3.0e38f) return 1.0f;
+    int e;
+    (void)frexpf(m, &e);                                  // m = f * 2^e, f in [0.5, 1)
+    e = min(30, max(-24, 3 - e));
+    return ldexpf(1.0f, e);
+}
+__device__ __forceinline__ void publish_amax(float* slot, float v) {      // v >= 0; called by whole warps
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (slot != nullptr && (threadIdx.x & 31) == 0 && v > 0.f) atomicMax(reinterpret_cast<int*>(slot), __float_as_int(v));
+}
+
 // ---- VW-wide (1, 2 or 4 floats) vector loads / stores
 template <int VW> struct Vec;
 template <> struct Vec<4> { typedef float4 T; };

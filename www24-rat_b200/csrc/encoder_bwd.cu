@@ -533,10 +533,11 @@ int attn_bwd_tc_dispatch(const float* x, const float* dout, const float* base, f
                          const float* ln_b, const float* Wq, const float* Wk, const float* Wv, const float* Wo, float* dWq,
                          float* dWk, float* dWv, float* dWo, float* dbo, float* dln_w, float* dln_b, int accumulate_wq,
                          int B, int T, int N, int D, int heads, int dh, float scale, float alpha, int mode,
-                         float* workspace, size_t workspace_bytes, cudaStream_t st);
+                         const float* dout_amax, float* dx_amax, float* workspace, size_t workspace_bytes, cudaStream_t st);
 int ff_bwd_tc_dispatch(const float* x, const float* dout, const float* base, float* dx, const float* ln_w,
                        const float* W1, const float* b1, const float* W2, float* dW1, float* db1, float* dW2, float* db2,
-                       long long rows, int D, int M, float* workspace, size_t workspace_bytes, cudaStream_t st);
+                       long long rows, int D, int M, const float* dout_amax, float* dx_amax, float* workspace,
+                       size_t workspace_bytes, cudaStream_t st);
 
 extern "C" size_t rat_attn_bwd_workspace_bytes(int B, int T, int N, int D, int heads, int dim_head, int mode) {
     AttnPlan p{};
@@ -568,13 +569,14 @@ extern "C" int rat_attn_bwd(const float* x, const float* dout, const float* base
                             const float* ln_b, const float* Wq, const float* Wk, const float* Wv, const float* Wo,
                             float* dWq, float* dWk, float* dWv, float* dWo, float* dbo, float* dln_w, float* dln_b,
                             int accumulate_wq, int B, int T, int N, int D, int heads, int dim_head, float scale,
-                            float alpha, int mode, float* workspace, size_t workspace_bytes, void* stream) {
+                            float alpha, int mode, const float* dout_amax, float* dx_amax, float* workspace,
+                            size_t workspace_bytes, void* stream) {
     RAT_REQUIRE(B > 0 && T > 0 && N > 0 && D > 0 && heads > 0, "rat_attn_bwd: bad shape");
     RAT_REQUIRE(D <= 128, "rat_attn_bwd: D=%d > 128 not supported", D);
     if (precision_mode() == 2) {
         const int rc2 = attn_bwd_tc_dispatch(x, dout, base, dx, ln_w, ln_b, Wq, Wk, Wv, Wo, dWq, dWk, dWv, dWo, dbo, dln_w,
-                                             dln_b, accumulate_wq, B, T, N, D, heads, dim_head, scale, alpha, mode, workspace,
-                                             workspace_bytes, (cudaStream_t)stream);
+                                             dln_b, accumulate_wq, B, T, N, D, heads, dim_head, scale, alpha, mode, dout_amax, dx_amax,
+                                             workspace, workspace_bytes, (cudaStream_t)stream);
         if (rc2 <= 0) return rc2;
     }
     AttnBwdArgs a{};
@@ -605,6 +607,8 @@ extern "C" int rat_attn_bwd(const float* x, const float* dout, const float* base
     const int total = 4 * a.I * D + 3 * D;
     k_reduce_attn<<<max(1, min(ceil_div(total, 256), 1024)), 256, 0, st>>>(r);
     RAT_CHECK_LAUNCH("k_reduce_attn");
+    if (dx_amax)            // fp32 / tf32 kernels do not track the maximum themselves
+        return rat_absmax(dx, (long long)B * T * N, D, D, dx_amax, stream);
     return RAT_OK;
 }
 
@@ -631,12 +635,12 @@ static int launch_ff_bwd(const FFBwdArgs& a, int grid, cudaStream_t st) {
 extern "C" int rat_ff_bwd(const float* x, const float* dout, const float* base, float* dx, const float* ln_w,
                           const float* ln_b, const float* W1, const float* b1, const float* W2, float* dW1, float* db1,
                           float* dW2, float* db2, float* dln_w, float* dln_b, long long rows, int D, int M,
-                          float* workspace, size_t workspace_bytes, void* stream) {
+                          const float* dout_amax, float* dx_amax, float* workspace, size_t workspace_bytes, void* stream) {
     RAT_REQUIRE(rows > 0 && D > 0 && M > 0, "rat_ff_bwd: bad shape");
     RAT_REQUIRE(D <= 128 && pad8(M) <= ENC_THREADS, "rat_ff_bwd: D=%d (<=128) M=%d (<=%d) not supported", D, M, ENC_THREADS);
     if (precision_mode() == 2) {
-        const int rc2 = ff_bwd_tc_dispatch(x, dout, base, dx, ln_w, W1, b1, W2, dW1, db1, dW2, db2, rows, D, M, workspace,
-                                           workspace_bytes, (cudaStream_t)stream);
+        const int rc2 = ff_bwd_tc_dispatch(x, dout, base, dx, ln_w, W1, b1, W2, dW1, db1, dW2, db2, rows, D, M, dout_amax, dx_amax,
+                                           workspace, workspace_bytes, (cudaStream_t)stream);
         if (rc2 <= 0) return rc2;
     }
     FFBwdArgs a{};
@@ -655,6 +659,7 @@ extern "C" int rat_ff_bwd(const float* x, const float* dout, const float* base, 
     const int total = 2 * M * D + M + 3 * D;
     k_reduce_ff<<<max(1, min(ceil_div(total, 256), 1024)), 256, 0, st>>>(r);
     RAT_CHECK_LAUNCH("k_reduce_ff");
+    if (dx_amax) return rat_absmax(dx, rows, D, D, dx_amax, stream);
     return RAT_OK;
 }
 

@@ -219,7 +219,7 @@ int plan_ff(int D, int M, FFPlan* out) {
 
 // 0 = exact fp32 SIMT ; 1 = tf32 mma.sync projections ; 2 = bf16 tcgen05 projections (shapes the tcgen05 kernels do
 // not cover run the tf32 kernels)
-static int g_precision = 1;
+static int g_precision = 2;     // default: tcgen05 path (fp16 operands, fp32 accumulate); 1 = mma.sync TF32, 0 = fp32 SIMT
 int precision_mode() { return g_precision; }
 
 }  // namespace rat
@@ -235,7 +235,7 @@ int attn_fwd_tc_dispatch(const float* x, const float* res, float* out, const flo
                          int N, int D, int heads, int dh, float scale, float alpha, int mode, cudaStream_t st);
 
 extern "C" int rat_set_precision(int mode) {
-    RAT_REQUIRE(mode >= 0 && mode <= 2, "rat_set_precision: mode must be 0 (fp32), 1 (tf32) or 2 (bf16 tcgen05)");
+    RAT_REQUIRE(mode >= 0 && mode <= 2, "rat_set_precision: mode must be 0 (fp32), 1 (tf32) or 2 (fp16 tcgen05)");
     g_precision = mode;
     return RAT_OK;
 }

@@ -19,9 +19,35 @@ constexpr int TILE_M = 128;
 __device__ __forceinline__ void team_sync(int team) {
     asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(TEAM_THREADS) : "memory");
 }
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+// 16-bit operand format of every tcgen05 / mma.sync product of the tensor-core path.  fp16 (default) has the 10-bit
+// mantissa of TF32, i.e. 8x less operand rounding than bf16; its narrow exponent range is handled by lifting every
+// gradient-domain tile by a per-launch power of two derived from max|dout| (grad_scale_from_amax, common.cuh): the
+// backward is linear in dout, so dout is scaled while it is staged and dx / the weight-gradient records are unscaled
+// in fp32 on the way out.  RAT_TC_FP16=0 selects bf16 operands (no scaling needed).
+#ifndef RAT_TC_FP16
+#define RAT_TC_FP16 1
+#endif
+#if RAT_TC_FP16
+constexpr uint32_t TC_FMT = tc5::FMT_F16;
+constexpr uint32_t TC_ONES2 = 0x3C003C00u;           // {1.0, 1.0}
+#else
+constexpr uint32_t TC_FMT = TC_FMT;
+constexpr uint32_t TC_ONES2 = 0x3F803F80u;
+#endif
+__device__ __forceinline__ float tc_grad_scale(const float* amax) {
+#if RAT_TC_FP16
+    return grad_scale_from_amax(amax);
+#else
+    return 1.0f;
+#endif
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
     uint32_t r;
+#if RAT_TC_FP16
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+#else
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+#endif
     return r;
 }
 __device__ __forceinline__ void sts128(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -42,8 +68,8 @@ __device__ __forceinline__ void stage_weight_image(const float* __restrict__ W, 
             const int c = kc * 8 + k;
             v[k] = (r < rows && c < cols) ? __ldg(W + (size_t)r * cols + c) : 0.f;
         }
-        sts128(dst + tc5::kmajor_off(r, kc, rows_p), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
-               pack_bf16(v[6], v[7]));
+        sts128(dst + tc5::kmajor_off(r, kc, rows_p), pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]),
+               pack_h2(v[6], v[7]));
     }
 }
 
@@ -84,7 +110,7 @@ __device__ __forceinline__ void store8(float* __restrict__ row, int c0, int D, c
 // of a row pair exchange partial sums by shuffle), convert to bf16 and store the chunks into the canonical A tile.
 //   tid2 = thread index inside the team (0..255): row = tid2 / 2, h = tid2 % 2.   valid=false -> zero row.
 template <int KCH, bool VEC4>
-__device__ __forceinline__ void stage_row_bf16(const float* __restrict__ src, bool valid, int D, int KC, int row, int h,
+__device__ __forceinline__ void stage_row_h(const float* __restrict__ src, bool valid, int D, int KC, int row, int h,
                                                const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                                                unsigned char* __restrict__ At, int ones_col = -1,
                                                float* __restrict__ stats = nullptr, float mul = 1.0f) {
@@ -139,8 +165,8 @@ __device__ __forceinline__ void stage_row_bf16(const float* __restrict__ src, bo
     }
 #pragma unroll
     for (int j = 0; j < KCH; ++j)
-        sts128(At + tc5::toff(row, h * KCH + j), pack_bf16(v[j][0], v[j][1]), pack_bf16(v[j][2], v[j][3]),
-               pack_bf16(v[j][4], v[j][5]), pack_bf16(v[j][6], v[j][7]));
+        sts128(At + tc5::toff(row, h * KCH + j), pack_h2(v[j][0], v[j][1]), pack_h2(v[j][2], v[j][3]),
+               pack_h2(v[j][4], v[j][5]), pack_h2(v[j][6], v[j][7]));
 }
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t saddr) {
@@ -151,10 +177,16 @@ __device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t saddr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
 }
-__device__ __forceinline__ void mma_bf16_16x8x16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+__device__ __forceinline__ void mma_h_16x8x16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+#if RAT_TC_FP16
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+#else
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+#endif
 }
 __device__ __forceinline__ float ex2f(float x) {
     float y;
@@ -238,27 +270,27 @@ __device__ __forceinline__ void wgrad_job(const unsigned char* __restrict__ At, 
 #pragma unroll
     for (int ks = 0; ks < TILE_M / 16; ++ks) {
         uint32_t af[4], bf[4];
-        if (a_ones) af[0] = af[1] = af[2] = af[3] = 0x3F803F80u;
+        if (a_ones) af[0] = af[1] = af[2] = af[3] = TC_ONES2;
         else ldsm_x4_t(af, a_s + tc5::toff(16 * ks + ra, ca));
         ldsm_x4_t(bf, b_s + tc5::toff(16 * ks + rb, cb));
-        mma_bf16_16x8x16(acc[0], af, bf[0], bf[1]);
-        mma_bf16_16x8x16(acc[1], af, bf[2], bf[3]);
+        mma_h_16x8x16(acc[0], af, bf[0], bf[1]);
+        mma_h_16x8x16(acc[1], af, bf[2], bf[3]);
     }
 }
 // store a job's accumulators into rec[(m0 + row) * ld + n0 + col] (fp32, row-major)
 __device__ __forceinline__ void wgrad_store(float* __restrict__ rec, int ld, int m0, int n0, int lane,
-                                            const float (&acc)[2][4], bool first_row_only) {
+                                            const float (&acc)[2][4], bool first_row_only, float mul = 1.0f) {
     const int g = lane >> 2, t = lane & 3;
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt) {
         const int col = n0 + 8 * nt + 2 * t;
         if (!first_row_only || g == 0) {
-            rec[(size_t)(m0 + g) * ld + col] = acc[nt][0];
-            rec[(size_t)(m0 + g) * ld + col + 1] = acc[nt][1];
+            rec[(size_t)(m0 + g) * ld + col] = acc[nt][0] * mul;
+            rec[(size_t)(m0 + g) * ld + col + 1] = acc[nt][1] * mul;
         }
         if (!first_row_only) {
-            rec[(size_t)(m0 + g + 8) * ld + col] = acc[nt][2];
-            rec[(size_t)(m0 + g + 8) * ld + col + 1] = acc[nt][3];
+            rec[(size_t)(m0 + g + 8) * ld + col] = acc[nt][2] * mul;
+            rec[(size_t)(m0 + g + 8) * ld + col + 1] = acc[nt][3] * mul;
         }
     }
 }

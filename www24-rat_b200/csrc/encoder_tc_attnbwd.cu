@@ -50,7 +50,7 @@ int attn_bwd_tc_dispatch(const float* x, const float* dout, const float* base, f
                          const float* ln_b, const float* Wq, const float* Wk, const float* Wv, const float* Wo, float* dWq,
                          float* dWk, float* dWv, float* dWo, float* dbo, float* dln_w, float* dln_b, int accumulate_wq,
                          int B, int T, int N, int D, int heads, int dh, float scale, float alpha, int mode,
-                         float* workspace, size_t workspace_bytes, cudaStream_t st) {
+                         const float* dout_amax, float* dx_amax, float* workspace, size_t workspace_bytes, cudaStream_t st) {
     AttnBwdTcArgs a{};
     const int S = mode == 0 ? N : T;
     if (!attn_bwd_tc_plan(S, D, heads, dh, &a)) return 1;
@@ -58,7 +58,7 @@ int attn_bwd_tc_dispatch(const float* x, const float* dout, const float* base, f
     const int grid = attn_bwd_tc_grid(a, a.nseq);
     if (!workspace || workspace_bytes < (size_t)grid * a.psize * sizeof(float)) return 1;
     a.x = x; a.dout = dout; a.base = base; a.dx = dx; a.ln_w = ln_w; a.ln_b = ln_b; a.Wq = Wq; a.Wk = Wk; a.Wv = Wv; a.Wo = Wo;
-    a.partials = workspace;
+    a.partials = workspace; a.dout_amax = dout_amax; a.dx_amax = dx_amax;
     a.g.S = S; a.g.mode = mode; a.g.T = T; a.g.N = N;
     a.scale = scale; a.alpha = alpha;
     int rc;

@@ -20,6 +20,8 @@ struct AttnBwdTcArgs {
     const float* ln_w; const float* ln_b;
     const float* Wq; const float* Wk; const float* Wv; const float* Wo;
     float* partials;         // [gridDim.x][psize]
+    const float* dout_amax;  // device: max|dout| (nullptr: no gradient scaling)
+    float* dx_amax;          // device: receives max|dx| (nullptr: not wanted)
     long long nseq;
     SeqGeom g;
     int D, H, I;
@@ -66,10 +68,10 @@ __device__ __forceinline__ void attn_bwd_core_bf16(const unsigned char* __restri
             ldsm_x4(b, qa + part + cl.b_off + 2 * ks * tc5::TILE_CHUNK);
             ldsm_x4(a2, da + cl.a_off + 2 * ks * tc5::TILE_CHUNK);
             ldsm_x4(b2, qa + 2 * part + cl.b_off + 2 * ks * tc5::TILE_CHUNK);
-            mma_bf16_16x8x16(sc[0], a, b[0], b[1]);
-            mma_bf16_16x8x16(sc[1], a, b[2], b[3]);
-            mma_bf16_16x8x16(dp[0], a2, b2[0], b2[1]);
-            mma_bf16_16x8x16(dp[1], a2, b2[2], b2[3]);
+            mma_h_16x8x16(sc[0], a, b[0], b[1]);
+            mma_h_16x8x16(sc[1], a, b[2], b[3]);
+            mma_h_16x8x16(dp[0], a2, b2[0], b2[1]);
+            mma_h_16x8x16(dp[1], a2, b2[2], b2[3]);
         }
         const bool has2 = !cl.packed || (seq0 + 1 < nseq_t);
         const bool vlo = cl.lo_rel >= 0, vhi = cl.hi_rel >= 0 && has2;
@@ -105,14 +107,14 @@ __device__ __forceinline__ void attn_bwd_core_bf16(const unsigned char* __restri
             }
         dlo = qsum(dlo); dhi = qsum(dhi);                                            // delta_i = sum_j P_ij dP_ij
         uint32_t pa[4], sa[4];
-        pa[0] = pack_bf16(sc[0][0], sc[0][1]); pa[1] = pack_bf16(sc[0][2], sc[0][3]);
-        pa[2] = pack_bf16(sc[1][0], sc[1][1]); pa[3] = pack_bf16(sc[1][2], sc[1][3]);
+        pa[0] = pack_h2(sc[0][0], sc[0][1]); pa[1] = pack_h2(sc[0][2], sc[0][3]);
+        pa[2] = pack_h2(sc[1][0], sc[1][1]); pa[3] = pack_h2(sc[1][2], sc[1][3]);
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
             for (int e = 0; e < 4; ++e) dp[nt][e] = sc[nt][e] * (dp[nt][e] - ((e < 2) ? dlo : dhi));   // dS
-        sa[0] = pack_bf16(dp[0][0], dp[0][1]); sa[1] = pack_bf16(dp[0][2], dp[0][3]);
-        sa[2] = pack_bf16(dp[1][0], dp[1][1]); sa[3] = pack_bf16(dp[1][2], dp[1][3]);
+        sa[0] = pack_h2(dp[0][0], dp[0][1]); sa[1] = pack_h2(dp[0][2], dp[0][3]);
+        sa[2] = pack_h2(dp[1][0], dp[1][1]); sa[3] = pack_h2(dp[1][2], dp[1][3]);
         // transposed A fragments (P^T, dS^T): transpose each 8x8 block and swap the off-diagonal blocks
         uint32_t pt[4], st[4];
         pt[0] = movm_t(pa[0]); pt[1] = movm_t(pa[2]); pt[2] = movm_t(pa[1]); pt[3] = movm_t(pa[3]);
@@ -127,15 +129,15 @@ __device__ __forceinline__ void attn_bwd_core_bf16(const unsigned char* __restri
             ldsm_x4_t(bk, qa + part + ko);              // K
             ldsm_x4_t(bq, qa + ko);                     // Q (scaled)
             ldsm_x4_t(bo, da + ko);                     // dO
-            mma_bf16_16x8x16(o[2 * pp], pa, bv[0], bv[1]);
-            mma_bf16_16x8x16(dq[2 * pp], sa, bk[0], bk[1]);
-            mma_bf16_16x8x16(dk[2 * pp], st, bq[0], bq[1]);
-            mma_bf16_16x8x16(dv[2 * pp], pt, bo[0], bo[1]);
+            mma_h_16x8x16(o[2 * pp], pa, bv[0], bv[1]);
+            mma_h_16x8x16(dq[2 * pp], sa, bk[0], bk[1]);
+            mma_h_16x8x16(dk[2 * pp], st, bq[0], bq[1]);
+            mma_h_16x8x16(dv[2 * pp], pt, bo[0], bo[1]);
             if (2 * pp + 1 < ND) {
-                mma_bf16_16x8x16(o[2 * pp + 1], pa, bv[2], bv[3]);
-                mma_bf16_16x8x16(dq[2 * pp + 1], sa, bk[2], bk[3]);
-                mma_bf16_16x8x16(dk[2 * pp + 1], st, bq[2], bq[3]);
-                mma_bf16_16x8x16(dv[2 * pp + 1], pt, bo[2], bo[3]);
+                mma_h_16x8x16(o[2 * pp + 1], pa, bv[2], bv[3]);
+                mma_h_16x8x16(dq[2 * pp + 1], sa, bk[2], bk[3]);
+                mma_h_16x8x16(dk[2 * pp + 1], st, bq[2], bq[3]);
+                mma_h_16x8x16(dv[2 * pp + 1], pt, bo[2], bo[3]);
             }
         }
         // ---- compact stores: columns [q: hl*DH + d | k: hc*DH + hl*DH + d | v: 2*hc*DH + hl*DH + d], O: hl*DH + d
@@ -149,16 +151,16 @@ __device__ __forceinline__ void attn_bwd_core_bf16(const unsigned char* __restri
                 const uint32_t ok = (uint32_t)(ck >> 3) * tc5::TILE_CHUNK + (uint32_t)(ck & 7) * 2u;
                 const uint32_t ov = (uint32_t)(cv >> 3) * tc5::TILE_CHUNK + (uint32_t)(cv & 7) * 2u;
                 if (vlo) {
-                    *reinterpret_cast<uint32_t*>(dQc + rlo + oq) = pack_bf16(dq[nd][0] * scale, dq[nd][1] * scale);
-                    *reinterpret_cast<uint32_t*>(dQc + rlo + ok) = pack_bf16(dk[nd][0] * inv_log2e, dk[nd][1] * inv_log2e);
-                    *reinterpret_cast<uint32_t*>(dQc + rlo + ov) = pack_bf16(dv[nd][0], dv[nd][1]);
-                    *reinterpret_cast<uint32_t*>(Ot + rlo + oq) = pack_bf16(o[nd][0], o[nd][1]);
+                    *reinterpret_cast<uint32_t*>(dQc + rlo + oq) = pack_h2(dq[nd][0] * scale, dq[nd][1] * scale);
+                    *reinterpret_cast<uint32_t*>(dQc + rlo + ok) = pack_h2(dk[nd][0] * inv_log2e, dk[nd][1] * inv_log2e);
+                    *reinterpret_cast<uint32_t*>(dQc + rlo + ov) = pack_h2(dv[nd][0], dv[nd][1]);
+                    *reinterpret_cast<uint32_t*>(Ot + rlo + oq) = pack_h2(o[nd][0], o[nd][1]);
                 }
                 if (vhi) {
-                    *reinterpret_cast<uint32_t*>(dQc + rhi + oq) = pack_bf16(dq[nd][2] * scale, dq[nd][3] * scale);
-                    *reinterpret_cast<uint32_t*>(dQc + rhi + ok) = pack_bf16(dk[nd][2] * inv_log2e, dk[nd][3] * inv_log2e);
-                    *reinterpret_cast<uint32_t*>(dQc + rhi + ov) = pack_bf16(dv[nd][2], dv[nd][3]);
-                    *reinterpret_cast<uint32_t*>(Ot + rhi + oq) = pack_bf16(o[nd][2], o[nd][3]);
+                    *reinterpret_cast<uint32_t*>(dQc + rhi + oq) = pack_h2(dq[nd][2] * scale, dq[nd][3] * scale);
+                    *reinterpret_cast<uint32_t*>(dQc + rhi + ok) = pack_h2(dk[nd][2] * inv_log2e, dk[nd][3] * inv_log2e);
+                    *reinterpret_cast<uint32_t*>(dQc + rhi + ov) = pack_h2(dv[nd][2], dv[nd][3]);
+                    *reinterpret_cast<uint32_t*>(Ot + rhi + oq) = pack_h2(o[nd][2], o[nd][3]);
                 }
             }
         }
@@ -190,6 +192,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_bwd_tc(AttnBwdTcArgs a) 
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t tmem_base_s;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float gs = tc_grad_scale(a.dout_amax), inv_gs = 1.0f / gs;
+    float dx_max = 0.f;
 
     // ---- resident weight images
     {
@@ -207,8 +211,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_bwd_tc(AttnBwdTcArgs a) 
                 const int c = kc * 8 + k;
                 v[k] = (d < DH && c < D) ? mul * __ldg(W + (size_t)((ch * hc + hl) * DH + d) * D + c) : 0.f;
             }
-            sts128(Wqkv_i + (size_t)ch * NCq * Kp * 2 + tc5::kmajor_off(rem, kc, NCq), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
-                   pack_bf16(v[6], v[7]));
+            sts128(Wqkv_i + (size_t)ch * NCq * Kp * 2 + tc5::kmajor_off(rem, kc, NCq), pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]),
+                   pack_h2(v[6], v[7]));
         }
         const int perT = Kp * KCc;
         for (int i = threadIdx.x; i < a.nchunks * perT; i += blockDim.x) {
@@ -222,8 +226,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_bwd_tc(AttnBwdTcArgs a) 
                 const float* W = w == 0 ? a.Wq : w == 1 ? a.Wk : a.Wv;
                 v[k] = (w < 3 && d < D) ? __ldg(W + (size_t)(ch * hc * DH + rem2) * D + d) : 0.f;
             }
-            sts128(WqkvT_i + (size_t)ch * Kp * NCc * 2 + tc5::kmajor_off(d, kc, Kp), pack_bf16(v[0], v[1]),
-                   pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            sts128(WqkvT_i + (size_t)ch * Kp * NCc * 2 + tc5::kmajor_off(d, kc, Kp), pack_h2(v[0], v[1]),
+                   pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
         }
         const int perO = NDo * KC1;
         for (int i = threadIdx.x; i < a.nchunks * perO; i += blockDim.x) {
@@ -236,8 +240,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_bwd_tc(AttnBwdTcArgs a) 
                 const int d = kc * 8 + k;
                 v[k] = (dd < DH && d < D) ? __ldg(a.Wo + (size_t)d * a.I + (ch * hc + hl) * DH + dd) : 0.f;
             }
-            sts128(WoT_i + (size_t)ch * NDo * Kp * 2 + tc5::kmajor_off(n, kc, NDo), pack_bf16(v[0], v[1]),
-                   pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            sts128(WoT_i + (size_t)ch * NDo * Kp * 2 + tc5::kmajor_off(n, kc, NDo), pack_h2(v[0], v[1]),
+                   pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
         }
         // activation tiles start as zeros (pad columns of the compact tiles are never written)
         const size_t tile_bytes = (size_t)TILE_M * (2 * Kp + NCq + NCc + Cc + NDo) * 2;
@@ -253,9 +257,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_bwd_tc(AttnBwdTcArgs a) 
     const uint32_t tmem_Q = tmem_base_s;                             // [0, NCq)
     const uint32_t tmem_O = tmem_Q + NCq;                            // [NCq, NCq + NDo)
     const uint32_t tmem_A = tmem_O + NDo;                            // [.., + Kp)
-    const uint32_t idesc_q = tc5::instr_desc(tc5::FMT_BF16, TILE_M, NCq);
-    const uint32_t idesc_o = tc5::instr_desc(tc5::FMT_BF16, TILE_M, NDo);
-    const uint32_t idesc_a = tc5::instr_desc(tc5::FMT_BF16, TILE_M, Kp);
+    const uint32_t idesc_q = tc5::instr_desc(TC_FMT, TILE_M, NCq);
+    const uint32_t idesc_o = tc5::instr_desc(TC_FMT, TILE_M, NDo);
+    const uint32_t idesc_a = tc5::instr_desc(TC_FMT, TILE_M, Kp);
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const int part = warp >> 2;                                      // 0..3: column share of this warp inside its lane quadrant
     const int row_e = (warp & 3) * 32 + lane;
@@ -288,8 +292,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_bwd_tc(AttnBwdTcArgs a) 
             const bool valid = row < R;
             const int ls = row / S, pos = row - ls * S;
             const long long gr = valid ? a.g.grow(s0 + ls, pos) : 0;
-            if (threadIdx.x < 256) stage_row_bf16<KCH, VEC4>(a.x + gr * D, valid, D, KC1, row, h, a.ln_w, a.ln_b, At, -1, stats);
-            else stage_row_bf16<KCH, VEC4>(a.dout + gr * D, valid, D, KC1, row, h, nullptr, nullptr, DYt, -1, nullptr, a.alpha);
+            if (threadIdx.x < 256) stage_row_h<KCH, VEC4>(a.x + gr * D, valid, D, KC1, row, h, a.ln_w, a.ln_b, At, -1, stats);
+            else stage_row_h<KCH, VEC4>(a.dout + gr * D, valid, D, KC1, row, h, nullptr, nullptr, DYt, -1, nullptr, a.alpha * gs);
         }
         tc5::fence_proxy_async();
         tc5::fence_before_sync();
@@ -319,10 +323,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_bwd_tc(AttnBwdTcArgs a) 
                     tc5::tmem_ld_wait();
                     unsigned char* dst = isq ? QKVt : dOt;
                     const int KCx = isq ? KCq : KCd;
-                    sts128(dst + tc5::toff(row_e, 2 * gg), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
-                           pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                    sts128(dst + tc5::toff(row_e, 2 * gg + 1), pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]),
-                           pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+                    sts128(dst + tc5::toff(row_e, 2 * gg), pack_h2(v[0], v[1]), pack_h2(v[2], v[3]),
+                           pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+                    sts128(dst + tc5::toff(row_e, 2 * gg + 1), pack_h2(v[8], v[9]), pack_h2(v[10], v[11]),
+                           pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
                 }
             }
             tc5::fence_before_sync();
@@ -392,10 +396,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_bwd_tc(AttnBwdTcArgs a) 
                         s2 = fmaf(gg[u][k], xh[u][k], s2);
                         g1[k] = gv; g2[k] = gv * xh[u][k];
                     }
-                    sts128(G1t + tc5::toff(row_e, gq), pack_bf16(g1[0], g1[1]), pack_bf16(g1[2], g1[3]),
-                           pack_bf16(g1[4], g1[5]), pack_bf16(g1[6], g1[7]));
-                    sts128(G2t + tc5::toff(row_e, gq), pack_bf16(g2[0], g2[1]), pack_bf16(g2[2], g2[3]),
-                           pack_bf16(g2[4], g2[5]), pack_bf16(g2[6], g2[7]));
+                    sts128(G1t + tc5::toff(row_e, gq), pack_h2(g1[0], g1[1]), pack_h2(g1[2], g1[3]),
+                           pack_h2(g1[4], g1[5]), pack_h2(g1[6], g1[7]));
+                    sts128(G2t + tc5::toff(row_e, gq), pack_h2(g2[0], g2[1]), pack_h2(g2[2], g2[3]),
+                           pack_h2(g2[4], g2[5]), pack_h2(g2[6], g2[7]));
                 } else if (gq < KC1) {
                     sts128(G1t + tc5::toff(row_e, gq), 0u, 0u, 0u, 0u);
                     sts128(G2t + tc5::toff(row_e, gq), 0u, 0u, 0u, 0u);
@@ -418,8 +422,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_bwd_tc(AttnBwdTcArgs a) 
                     if (a.base) load8<VEC4>(a.base + gr * D, gq * 8, D, bv);
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        ov[k] = rstd * (gg[u][k] - t1 - xh[u][k] * t2);
+                        ov[k] = (rstd * inv_gs) * (gg[u][k] - t1 - xh[u][k] * t2);
                         if (a.base) ov[k] += bv[k];
+                        dx_max = fmaxf(dx_max, fabsf(ov[k]));
                     }
                     store8<VEC4>(a.dx + gr * D, gq * 8, D, ov);
                 }
@@ -448,14 +453,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_bwd_tc(AttnBwdTcArgs a) 
             if (job >= njobs) continue;
             if (job < a.nchunks * per_chunk) {
                 const int ch = job / per_chunk, rel = job - ch * per_chunk;
-                if (rel < MTq * NP) wgrad_store(rec + (size_t)ch * NCc * Kp, Kp, 16 * (rel / NP), 16 * (rel % NP), lane, acc[j], false);
-                else { const int r2 = rel - MTq * NP; wgrad_store(recO + (size_t)ch * Cc * Kp, Kp, 16 * (r2 / NP), 16 * (r2 % NP), lane, acc[j], false); }
+                if (rel < MTq * NP) wgrad_store(rec + (size_t)ch * NCc * Kp, Kp, 16 * (rel / NP), 16 * (rel % NP), lane, acc[j], false, inv_gs);
+                else { const int r2 = rel - MTq * NP; wgrad_store(recO + (size_t)ch * Cc * Kp, Kp, 16 * (r2 / NP), 16 * (r2 % NP), lane, acc[j], false, inv_gs); }
             } else {
                 const int rel = job - a.nchunks * per_chunk;
-                wgrad_store(recS + (size_t)(rel / NP) * Kp, Kp, 0, 16 * (rel % NP), lane, acc[j], true);
+                wgrad_store(recS + (size_t)(rel / NP) * Kp, Kp, 0, 16 * (rel % NP), lane, acc[j], true, inv_gs);
             }
         }
     }
+    publish_amax(a.dx_amax, dx_max);
     __syncthreads();
     if (threadIdx.x < 32) tc5::tmem_dealloc(tmem_base_s, 512);
 }

@@ -13,6 +13,8 @@ struct FFBwdTcArgs {
     const float* x; const float* dout; const float* base; float* dx;
     const float* W1; const float* b1; const float* W2;
     float* partials;         // [2 * gridDim.x][psize]
+    const float* dout_amax;  // device: max|dout| (nullptr: no gradient scaling)
+    float* dx_amax;          // device: receives max|dx| (nullptr: not wanted)
     long long rows;
     int D, M, Kp, Mp;
     int psize;               // 2 * Mp * Kp + Kp
@@ -48,8 +50,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_ff_bwd_tc(FFBwdTcArgs a) {
             float v[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) { const int d = kc * 8 + k; v[k] = (m < M && d < D) ? __ldg(a.W2 + (size_t)d * M + m) : 0.f; }
-            sts128(W2ti + tc5::kmajor_off(m, kc, Mp), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
-                   pack_bf16(v[6], v[7]));
+            sts128(W2ti + tc5::kmajor_off(m, kc, Mp), pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]),
+                   pack_h2(v[6], v[7]));
         }
         const int total2 = Kp * KC2;
         for (int i = threadIdx.x; i < total2; i += blockDim.x) {
@@ -57,8 +59,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_ff_bwd_tc(FFBwdTcArgs a) {
             float v[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) { const int m = kc * 8 + k; v[k] = (m < M && d < D) ? __ldg(a.W1 + (size_t)m * D + d) : 0.f; }
-            sts128(W1ti + tc5::kmajor_off(d, kc, Kp), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
-                   pack_bf16(v[6], v[7]));
+            sts128(W1ti + tc5::kmajor_off(d, kc, Kp), pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]),
+                   pack_h2(v[6], v[7]));
         }
     }
     for (int i = threadIdx.x; i < Mp; i += blockDim.x) b1s[i] = i < M ? a.b1[i] : 0.f;
@@ -70,8 +72,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_ff_bwd_tc(FFBwdTcArgs a) {
     tc5::fence_after_sync();
     const uint32_t tmem_P = tmem_base_s + team * 256;                // pre [0, Mp)  -> later dxa [0, Kp)
     const uint32_t tmem_H = tmem_P + Mp;                             // dh  [Mp, 2 Mp)
-    const uint32_t idesc_m = tc5::instr_desc(tc5::FMT_BF16, TILE_M, Mp);
-    const uint32_t idesc_d = tc5::instr_desc(tc5::FMT_BF16, TILE_M, Kp);
+    const uint32_t idesc_m = tc5::instr_desc(TC_FMT, TILE_M, Mp);
+    const uint32_t idesc_d = tc5::instr_desc(TC_FMT, TILE_M, Kp);
     const uint32_t lane_base = (uint32_t)((warp2 & 3) * 32) << 16;
     const int chalf = warp2 >> 2;
     const int row_e = (warp2 & 3) * 32 + lane;
@@ -87,14 +89,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_ff_bwd_tc(FFBwdTcArgs a) {
 #pragma unroll
         for (int q = 0; q < 2; ++q) acc[j][q][0] = acc[j][q][1] = acc[j][q][2] = acc[j][q][3] = 0.f;
 
+    const float gs = tc_grad_scale(a.dout_amax), inv_gs = 1.0f / gs;
+    float dx_max = 0.f;
     const long long ntiles = (a.rows + TILE_M - 1) / TILE_M;
     for (long long tile = (long long)blockIdx.x * 2 + team; tile < ntiles; tile += (long long)gridDim.x * 2) {
         const long long r0 = tile * TILE_M;
         const int R = (int)min((long long)TILE_M, a.rows - r0);
         {
             const int row = tid2 >> 1, h = tid2 & 1;
-            stage_row_bf16<KCH, VEC4>(a.x + (r0 + row) * D, row < R, D, KC1, row, h, nullptr, nullptr, Xt, D);
-            stage_row_bf16<KCH, VEC4>(a.dout + (r0 + row) * D, row < R, D, KC1, row, h, nullptr, nullptr, DYt);
+            stage_row_h<KCH, VEC4>(a.x + (r0 + row) * D, row < R, D, KC1, row, h, nullptr, nullptr, Xt, D);
+            stage_row_h<KCH, VEC4>(a.dout + (r0 + row) * D, row < R, D, KC1, row, h, nullptr, nullptr, DYt, -1, nullptr, gs);
         }
         tc5::fence_proxy_async();
         tc5::fence_before_sync();
@@ -127,10 +131,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_ff_bwd_tc(FFBwdTcArgs a) {
                     gelu_fast(p[k] + b1s[g * 8 + k], hv[k], gd);
                     dp[k] = dh[k] * gd;
                 }
-                sts128(Ht + tc5::toff(row_e, g), pack_bf16(hv[0], hv[1]), pack_bf16(hv[2], hv[3]),
-                       pack_bf16(hv[4], hv[5]), pack_bf16(hv[6], hv[7]));
-                sts128(DPt + tc5::toff(row_e, g), pack_bf16(dp[0], dp[1]), pack_bf16(dp[2], dp[3]),
-                       pack_bf16(dp[4], dp[5]), pack_bf16(dp[6], dp[7]));
+                sts128(Ht + tc5::toff(row_e, g), pack_h2(hv[0], hv[1]), pack_h2(hv[2], hv[3]),
+                       pack_h2(hv[4], hv[5]), pack_h2(hv[6], hv[7]));
+                sts128(DPt + tc5::toff(row_e, g), pack_h2(dp[0], dp[1]), pack_h2(dp[2], dp[3]),
+                       pack_h2(dp[4], dp[5]), pack_h2(dp[6], dp[7]));
             }
         }
         tc5::fence_proxy_async();
@@ -171,10 +175,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_ff_bwd_tc(FFBwdTcArgs a) {
                 if (row_e < R && a.base) load8<VEC4>(a.base + (r0 + row_e) * D, g * 8, D, bv);
                 tc5::tmem_ld_wait();
                 if (row_e < R) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[k] *= inv_gs;
                     if (a.base) {
 #pragma unroll
                         for (int k = 0; k < 8; ++k) v[k] += bv[k];
                     }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (g * 8 + k < D) dx_max = fmaxf(dx_max, fabsf(v[k]));
                     store8<VEC4>(a.dx + (r0 + row_e) * D, g * 8, D, v);
                 }
             }
@@ -192,13 +201,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_ff_bwd_tc(FFBwdTcArgs a) {
                 if (job < 2 * MT * NP) {
                     const int which = job / (MT * NP), rem = job - which * (MT * NP);
                     const int mi = rem / NP, np = rem - mi * NP;
-                    wgrad_store(rec + (size_t)which * Mp * Kp, Kp, 16 * mi, 16 * np, lane, acc[j], false);
+                    wgrad_store(rec + (size_t)which * Mp * Kp, Kp, 16 * mi, 16 * np, lane, acc[j], false, inv_gs);
                 } else {
-                    wgrad_store(rec + (size_t)2 * Mp * Kp, Kp, 0, 16 * (job - 2 * MT * NP), lane, acc[j], true);
+                    wgrad_store(rec + (size_t)2 * Mp * Kp, Kp, 0, 16 * (job - 2 * MT * NP), lane, acc[j], true, inv_gs);
                 }
             }
         }
     }
+    publish_amax(a.dx_amax, dx_max);
     __syncthreads();
     if (threadIdx.x < 32) tc5::tmem_dealloc(tmem_base_s, 512);
 }
@@ -272,12 +282,14 @@ static int launch_ff_bwd_tc(const FFBwdTcArgs& a, int grid, cudaStream_t st) {
 
 int ff_bwd_tc_dispatch(const float* x, const float* dout, const float* base, float* dx, const float* ln_w,
                        const float* W1, const float* b1, const float* W2, float* dW1, float* db1, float* dW2, float* db2,
-                       long long rows, int D, int M, float* workspace, size_t workspace_bytes, cudaStream_t st) {
+                       long long rows, int D, int M, const float* dout_amax, float* dx_amax, float* workspace,
+                       size_t workspace_bytes, cudaStream_t st) {
     FFBwdTcArgs a{};
     if (ln_w != nullptr || !ff_bwd_tc_plan(D, M, &a)) return 1;
     const int grid = ff_bwd_tc_grid(rows);
     if (!workspace || workspace_bytes < (size_t)2 * grid * a.psize * sizeof(float)) return 1;
     a.x = x; a.dout = dout; a.base = base; a.dx = dx; a.W1 = W1; a.b1 = b1; a.W2 = W2; a.partials = workspace; a.rows = rows;
+    a.dout_amax = dout_amax; a.dx_amax = dx_amax;
     const int kch = a.Kp / 16;
     const bool v4 = (D % 4) == 0;
     const int njobs = 2 * (a.Mp / 16) * (a.Kp / 16) + a.Kp / 16;

@@ -57,8 +57,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_ff_fwd_tc(FFTcArgs a) {
     tc5::fence_after_sync();
     const uint32_t tmem_H = tmem_base_s + team * 128;                // columns [0, Mp)
     const uint32_t tmem_Y = tmem_H + Mp;                             // columns [Mp, Mp+Np)
-    const uint32_t idesc1 = tc5::instr_desc(tc5::FMT_BF16, TILE_M, Mp);
-    const uint32_t idesc2 = tc5::instr_desc(tc5::FMT_BF16, TILE_M, Np);
+    const uint32_t idesc1 = tc5::instr_desc(TC_FMT, TILE_M, Mp);
+    const uint32_t idesc2 = tc5::instr_desc(TC_FMT, TILE_M, Np);
     const uint32_t lane_base = (uint32_t)((warp2 & 3) * 32) << 16;   // this warp's TMEM lane quadrant
     const int chalf = warp2 >> 2;                                    // column half handled by this warp
     const int row_e = (warp2 & 3) * 32 + lane;                       // accumulator row of this thread
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_ff_fwd_tc(FFTcArgs a) {
         // ---- phase 1: x tile -> (LayerNorm) -> bf16 A tile
         {
             const int row = tid2 >> 1, h = tid2 & 1;
-            stage_row_bf16<KCH, VEC4>(a.x + (r0 + row) * D, row < R, D, KC1, row, h, a.ln_w, a.ln_b, At);
+            stage_row_h<KCH, VEC4>(a.x + (r0 + row) * D, row < R, D, KC1, row, h, a.ln_w, a.ln_b, At);
         }
         tc5::fence_proxy_async();
         tc5::fence_before_sync();
@@ -99,8 +99,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_ff_fwd_tc(FFTcArgs a) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) { float dg; gelu_fast(v[k] + b1s[g * 8 + k], v[k], dg); }
                 // columns >= M: W1 image rows are zero and b1s is zero -> gelu(0) = 0
-                sts128(Ht + tc5::toff(row_e, g), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
-                       pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                sts128(Ht + tc5::toff(row_e, g), pack_h2(v[0], v[1]), pack_h2(v[2], v[3]),
+                       pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
             }
         }
         tc5::fence_proxy_async();
@@ -189,8 +189,8 @@ __device__ __forceinline__ void attn_core_bf16(const unsigned char* __restrict__
             uint32_t a[4], b[4];
             ldsm_x4(a, qa + cl.a_off + 2 * ks * tc5::TILE_CHUNK);
             ldsm_x4(b, qa + part + cl.b_off + 2 * ks * tc5::TILE_CHUNK);
-            mma_bf16_16x8x16(sc[0], a, b[0], b[1]);
-            mma_bf16_16x8x16(sc[1], a, b[2], b[3]);
+            mma_h_16x8x16(sc[0], a, b[0], b[1]);
+            mma_h_16x8x16(sc[1], a, b[2], b[3]);
         }
         const bool has2 = !cl.packed || (seq0 + 1 < nseq_t);
         const bool vlo = cl.lo_rel >= 0, vhi = cl.hi_rel >= 0 && has2;
@@ -215,15 +215,15 @@ __device__ __forceinline__ void attn_core_bf16(const unsigned char* __restrict__
             }
         llo = qsum(llo); lhi = qsum(lhi);
         uint32_t pa[4];
-        pa[0] = pack_bf16(sc[0][0], sc[0][1]); pa[1] = pack_bf16(sc[0][2], sc[0][3]);
-        pa[2] = pack_bf16(sc[1][0], sc[1][1]); pa[3] = pack_bf16(sc[1][2], sc[1][3]);
+        pa[0] = pack_h2(sc[0][0], sc[0][1]); pa[1] = pack_h2(sc[0][2], sc[0][3]);
+        pa[2] = pack_h2(sc[1][0], sc[1][1]); pa[3] = pack_h2(sc[1][2], sc[1][3]);
         float o[2 * KS][4] = {};
 #pragma unroll
         for (int pp = 0; pp < KS; ++pp) {
             uint32_t vb[4];
             ldsm_x4_t(vb, qa + 2 * part + cl.a_off + 2 * pp * tc5::TILE_CHUNK);
-            mma_bf16_16x8x16(o[2 * pp], pa, vb[0], vb[1]);
-            if (2 * pp + 1 < ND) mma_bf16_16x8x16(o[2 * pp + 1], pa, vb[2], vb[3]);
+            mma_h_16x8x16(o[2 * pp], pa, vb[0], vb[1]);
+            if (2 * pp + 1 < ND) mma_h_16x8x16(o[2 * pp + 1], pa, vb[2], vb[3]);
         }
         const float ilo = rcp_fast(llo), ihi = rcp_fast(lhi);
         unsigned char* olo = Ot + tb + (uint32_t)(cl.lo_rel * 16);
@@ -234,8 +234,8 @@ __device__ __forceinline__ void attn_core_bf16(const unsigned char* __restrict__
             if (d < DH) {                                           // DH even: the (d, d+1) pair is valid as a whole
                 const int col = hl * DH + d;
                 const uint32_t co = (uint32_t)(col >> 3) * tc5::TILE_CHUNK + (uint32_t)(col & 7) * 2u;
-                if (vlo) *reinterpret_cast<uint32_t*>(olo + co) = pack_bf16(o[nd][0] * ilo, o[nd][1] * ilo);
-                if (vhi) *reinterpret_cast<uint32_t*>(ohi + co) = pack_bf16(o[nd][2] * ihi, o[nd][3] * ihi);
+                if (vlo) *reinterpret_cast<uint32_t*>(olo + co) = pack_h2(o[nd][0] * ilo, o[nd][1] * ilo);
+                if (vhi) *reinterpret_cast<uint32_t*>(ohi + co) = pack_h2(o[nd][2] * ihi, o[nd][3] * ihi);
             }
         }
         sp += dsp; hl += dhl;
@@ -279,8 +279,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_fwd_tc(AttnTcArgs a) {
                 const int c = kc * 8 + k;
                 v[k] = (d < DH && c < D) ? mul * __ldg(W + (size_t)((ch * hc + hl) * DH + d) * D + c) : 0.f;
             }
-            sts128(Wqkv_i + (size_t)ch * NCq * Kp * 2 + tc5::kmajor_off(rem, kc, NCq), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
-                   pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            sts128(Wqkv_i + (size_t)ch * NCq * Kp * 2 + tc5::kmajor_off(rem, kc, NCq), pack_h2(v[0], v[1]), pack_h2(v[2], v[3]),
+                   pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
         }
         const int per = Np * KCo;
         for (int i = threadIdx.x; i < a.nchunks * per; i += blockDim.x) {
@@ -292,8 +292,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_fwd_tc(AttnTcArgs a) {
                 const int c = kc * 8 + k;
                 v[k] = (n < D && c < hc * DH) ? __ldg(a.Wo + (size_t)n * a.I + ch * hc * DH + c) : 0.f;
             }
-            sts128(Wo_i + (size_t)ch * Np * Cp * 2 + tc5::kmajor_off(n, kc, Np), pack_bf16(v[0], v[1]),
-                   pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            sts128(Wo_i + (size_t)ch * Np * Cp * 2 + tc5::kmajor_off(n, kc, Np), pack_h2(v[0], v[1]),
+                   pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
         }
         for (int i = threadIdx.x; i < Np; i += blockDim.x) bos[i] = i < D ? a.bo[i] : 0.f;
         // o tiles: pad columns [hc*dh, Cp) are never written by the attention core and must read as zero
@@ -308,8 +308,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_fwd_tc(AttnTcArgs a) {
     tc5::fence_after_sync();
     const uint32_t tmem_Q = tmem_base_s + team * 256;                // columns [0, NCq)
     const uint32_t tmem_Y = tmem_Q + NCq;                            // columns [NCq, NCq + Np)
-    const uint32_t idesc_q = tc5::instr_desc(tc5::FMT_BF16, TILE_M, NCq);
-    const uint32_t idesc_o = tc5::instr_desc(tc5::FMT_BF16, TILE_M, Np);
+    const uint32_t idesc_q = tc5::instr_desc(TC_FMT, TILE_M, NCq);
+    const uint32_t idesc_o = tc5::instr_desc(TC_FMT, TILE_M, Np);
     const uint32_t lane_base = (uint32_t)((warp2 & 3) * 32) << 16;
     const int chalf = warp2 >> 2;
     const int row_e = (warp2 & 3) * 32 + lane;
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_fwd_tc(AttnTcArgs a) {
             const bool valid = row < R;
             const int ls = row / S, pos = row - ls * S;
             const long long gr = valid ? a.g.grow(s0 + ls, pos) : 0;
-            stage_row_bf16<KCH, VEC4>(a.x + gr * D, valid, D, KC1, row, h, a.ln_w, a.ln_b, At);
+            stage_row_h<KCH, VEC4>(a.x + gr * D, valid, D, KC1, row, h, a.ln_w, a.ln_b, At);
         }
         tc5::fence_proxy_async();
         tc5::fence_before_sync();
@@ -351,10 +351,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_fwd_tc(AttnTcArgs a) {
                     float v[16];
                     tc5::tmem_ld16(tmem_Q + lane_base + gq * 16, v);
                     tc5::tmem_ld_wait();
-                    sts128(QKVt + tc5::toff(row_e, 2 * gq), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
-                           pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                    sts128(QKVt + tc5::toff(row_e, 2 * gq + 1), pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]),
-                           pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+                    sts128(QKVt + tc5::toff(row_e, 2 * gq), pack_h2(v[0], v[1]), pack_h2(v[2], v[3]),
+                           pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+                    sts128(QKVt + tc5::toff(row_e, 2 * gq + 1), pack_h2(v[8], v[9]), pack_h2(v[10], v[11]),
+                           pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
                 }
             }
             tc5::fence_before_sync();

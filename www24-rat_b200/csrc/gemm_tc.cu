@@ -23,6 +23,8 @@ constexpr int GT_KB = 64;            // reduction elements per stage
 struct GemmTcArgs {
     const float* A; const float* B; float* C; const float* bias;
     int M, N, K, lda, ldb, ldc;
+    const float* a_amax;             // device max|A| (nullptr: no scaling): A is lifted by grad_scale_from_amax while it
+                                     // is staged and the fp32 accumulator is unscaled in the epilogue
     int BN;                          // output-tile width (multiple of 16, <= 256)
     int kchunk;                      // reduction range per split (multiple of 64)
     int splits;
@@ -31,7 +33,7 @@ struct GemmTcArgs {
 // stage a [ROWS x 8*CHUNKS] fp32 source tile (row stride ld) as bf16, chunk-major; rows/cols outside the matrix -> 0
 __device__ __forceinline__ void gemm_stage_tile(const float* __restrict__ src, int ld, int row0, int col0, int rows_total,
                                                 int cols_total, int ROWS, int CHUNKS, unsigned char* __restrict__ dst,
-                                                bool vec_ok) {
+                                                bool vec_ok, float mul = 1.0f) {
     const int items = ROWS * CHUNKS;
     for (int it = threadIdx.x; it < items; it += GT_THREADS) {
         const int r = it % ROWS, c = it / ROWS;
@@ -45,8 +47,12 @@ __device__ __forceinline__ void gemm_stage_tile(const float* __restrict__ src, i
 #pragma unroll
             for (int k = 0; k < 8; ++k) v[k] = (gr < rows_total && gc + k < cols_total) ? __ldg(src + (size_t)gr * ld + gc + k) : 0.f;
         }
-        sts128(dst + tc5::kmajor_off(r, c, ROWS), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
-               pack_bf16(v[6], v[7]));
+        if (mul != 1.0f) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] *= mul;
+        }
+        sts128(dst + tc5::kmajor_off(r, c, ROWS), pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]),
+               pack_h2(v[6], v[7]));
     }
 }
 
@@ -69,7 +75,8 @@ __global__ void __launch_bounds__(GT_THREADS) k_gemm_tc(GemmTcArgs a) {
     __syncthreads();
     tc5::fence_after_sync();
     const uint32_t tmem_D = tmem_base_s;
-    const uint32_t idesc = tc5::instr_desc(tc5::FMT_BF16, TILE_M, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    const float a_scale = tc_grad_scale(a.a_amax), c_scale = 1.0f / a_scale;
+    const uint32_t idesc = tc5::instr_desc(TC_FMT, TILE_M, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     const bool a_vec = (a.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0);
     const bool b_vec = (a.ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.B) & 15) == 0);
 
@@ -77,8 +84,8 @@ __global__ void __launch_bounds__(GT_THREADS) k_gemm_tc(GemmTcArgs a) {
         const int buf = s & 1, k0 = kbeg + s * GT_KB;
         if (s >= 2) tc5::mbar_wait(&mbar[buf], ((s >> 1) - 1) & 1);      // the MMAs that read this buffer are done
         // A tile: K-major -> rows = m (128), cols = k (64) ; MN-major -> rows = k (64), cols = m (128)
-        if (!A_MN) gemm_stage_tile(a.A, a.lda, m0, k0, a.M, kend, TILE_M, GT_KB / 8, Abuf[buf], a_vec && (k0 % 4 == 0));
-        else gemm_stage_tile(a.A, a.lda, k0, m0, kend, a.M, GT_KB, TILE_M / 8, Abuf[buf], a_vec);
+        if (!A_MN) gemm_stage_tile(a.A, a.lda, m0, k0, a.M, kend, TILE_M, GT_KB / 8, Abuf[buf], a_vec && (k0 % 4 == 0), a_scale);
+        else gemm_stage_tile(a.A, a.lda, k0, m0, kend, a.M, GT_KB, TILE_M / 8, Abuf[buf], a_vec, a_scale);
         if (!B_MN) gemm_stage_tile(a.B, a.ldb, n0, k0, a.N, kend, BN, GT_KB / 8, Bbuf[buf], b_vec && (k0 % 4 == 0));
         else gemm_stage_tile(a.B, a.ldb, k0, n0, kend, a.N, GT_KB, BN / 8, Bbuf[buf], b_vec && (n0 % 4 == 0));
         tc5::fence_proxy_async();
@@ -111,6 +118,10 @@ __global__ void __launch_bounds__(GT_THREADS) k_gemm_tc(GemmTcArgs a) {
                 for (int i = 0; i < 16; ++i) v[i] = 0.f;
             }
             const int c0 = n0 + gq * 16;
+            if (c_scale != 1.0f) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] *= c_scale;
+            }
             if (row < a.M && c0 < a.N) {
                 if (a.bias && a.splits == 1) {
 #pragma unroll
@@ -180,11 +191,12 @@ static int launch_gemm_tc(const GemmTcArgs& a, const GemmTcPlan& p, cudaStream_t
 
 // returns RAT_OK if launched (C, or `splits` partials in workspace with *splits_out > 1), 1 if not covered
 int gemm_tc_dispatch(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda, int ldb,
-                     int ldc, int trans_a, int trans_b, float* workspace, size_t workspace_bytes, int* splits_out,
-                     cudaStream_t st) {
+                     int ldc, int trans_a, int trans_b, const float* a_amax, float* workspace, size_t workspace_bytes,
+                     int* splits_out, cudaStream_t st) {
     GemmTcPlan p{};
     if (!gemm_tc_plan(M, N, K, workspace ? workspace_bytes : 0, &p)) return 1;
-    GemmTcArgs a{A, B, p.splits > 1 ? workspace : C, bias, M, N, K, lda, ldb, p.splits > 1 ? N : ldc, p.BN, p.kchunk, p.splits};
+    GemmTcArgs a{A, B, p.splits > 1 ? workspace : C, bias, M, N, K, lda, ldb, p.splits > 1 ? N : ldc, a_amax,
+                 p.BN, p.kchunk, p.splits};
     *splits_out = p.splits;
     if (!trans_a && !trans_b) return launch_gemm_tc<false, false>(a, p, st);
     if (!trans_a && trans_b) return launch_gemm_tc<false, true>(a, p, st);

@@ -331,13 +331,34 @@ static int ew_grid(long long total) {
 
 }  // namespace rat
 
+namespace rat {
+// out = max(out, max |x[r*stride + c]|), r < rows, c < cols  (out zeroed by the caller; integer atomicMax on float bits)
+__global__ void k_absmax(const float* __restrict__ x, long long rows, int cols, long long stride, float* __restrict__ out) {
+    const long long total = rows * cols;
+    float m = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / cols;
+        m = fmaxf(m, fabsf(x[r * stride + (i - r * cols)]));
+    }
+    publish_amax(out, m);
+}
+
+}  // namespace rat
+
 using namespace rat;
+
+extern "C" int rat_absmax(const float* x, long long rows, int cols, long long row_stride, float* out, void* stream) {
+    RAT_REQUIRE(rows > 0 && cols > 0 && row_stride >= cols, "rat_absmax: bad shape");
+    k_absmax<<<ew_grid(rows * cols), 256, 0, (cudaStream_t)stream>>>(x, rows, cols, row_stride, out);
+    RAT_CHECK_LAUNCH("k_absmax");
+    return RAT_OK;
+}
 
 namespace rat { int precision_mode(); }
 size_t gemm_tc_workspace_bytes(int M, int N, int K);
 int gemm_tc_dispatch(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda, int ldb,
-                     int ldc, int trans_a, int trans_b, float* workspace, size_t workspace_bytes, int* splits_out,
-                     cudaStream_t st);
+                     int ldc, int trans_a, int trans_b, const float* a_amax, float* workspace, size_t workspace_bytes,
+                     int* splits_out, cudaStream_t st);
 
 static size_t sgemm_simt_workspace_bytes(int M, int N, int K);
 extern "C" size_t rat_sgemm_workspace_bytes(int M, int N, int K) {
@@ -356,6 +377,12 @@ static size_t sgemm_simt_workspace_bytes(int M, int N, int K) {
 extern "C" int rat_sgemm(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda,
                          int ldb, int ldc, int trans_a, int trans_b, float* workspace, size_t workspace_bytes,
                          void* stream) {
+    return rat_sgemm_scaled(A, B, C, bias, M, N, K, lda, ldb, ldc, trans_a, trans_b, nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" int rat_sgemm_scaled(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda,
+                                int ldb, int ldc, int trans_a, int trans_b, const float* a_amax, float* workspace,
+                                size_t workspace_bytes, void* stream) {
     RAT_REQUIRE(M > 0 && N > 0 && K > 0, "rat_sgemm: bad shape M=%d N=%d K=%d", M, N, K);
     cudaStream_t st0 = (cudaStream_t)stream;
     if (N == 1 && !trans_a && M >= 64) {                    // logit column: C[m] = A[m,:] . b
@@ -380,7 +407,7 @@ extern "C" int rat_sgemm(const float* A, const float* B, float* C, const float* 
     }
     if (precision_mode() == 2) {        // tcgen05 path (bf16 operands, fp32 accumulate); tiny shapes stay on the SIMT kernel
         int tc_splits = 1;
-        const int rc = gemm_tc_dispatch(A, B, C, bias, M, N, K, lda, ldb, ldc, trans_a, trans_b, workspace, workspace_bytes,
+        const int rc = gemm_tc_dispatch(A, B, C, bias, M, N, K, lda, ldb, ldc, trans_a, trans_b, a_amax, workspace, workspace_bytes,
                                         &tc_splits, (cudaStream_t)stream);
         if (rc < 0) return rc;
         if (rc == 0) {

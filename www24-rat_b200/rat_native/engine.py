@@ -75,18 +75,18 @@ class EngineSpec:
         return sum(f.vocab_size for f in self.features)
 
 
-_PREC = {"fp32": 0, "tf32": 1, "bf16": 2}
+_PREC = {"fp32": 0, "tf32": 1, "fp16": 2, "bf16": 2}     # "bf16": round-1 alias of the tensor-core mode
 
 
 def set_precision(mode: str):
-    """'bf16': tcgen05 projections (bf16 operands, fp32 accumulate in TMEM); 'tf32': mma.sync TF32 projections;
-    'fp32': exact SIMT twin (parity anchor)."""
+    """'fp16': tcgen05 projections + DNN GEMMs (fp16 operands, fp32 accumulate in TMEM, gradients pre-scaled by 2^10);
+    'tf32': mma.sync TF32 projections; 'fp32': exact SIMT twin (parity anchor)."""
     assert mode in _PREC, mode
     call("rat_set_precision", _PREC[mode])
 
 
 def get_precision() -> str:
-    return {v: k for k, v in _PREC.items()}[int(query("rat_get_precision"))]
+    return {0: "fp32", 1: "tf32", 2: "fp16"}[int(query("rat_get_precision"))]
 
 
 def _align4(n):
@@ -339,6 +339,10 @@ class RatEngine:
         self.world = 1
         self.dist_group = None
         self._side = None
+        self.amax = torch.zeros(256, dtype=torch.float32, device=self.device)
+        self._amax_next = 0
+        self._amax_of = {}
+        self._amax_on = False
         try:
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized():
@@ -510,6 +514,7 @@ class RatEngine:
         bw = ws["bwd_ws"]
         call("rat_layernorm_bwd", a[2 * s.depth], d, d, self.p[prefix + "norm.weight"], g[prefix + "norm.weight"],
              g[prefix + "norm.bias"], rows, s.embedding_dim, bw, bw.numel() * 4, current_stream())
+        self._amax_forget(d)                     # written by a kernel that does not publish max|dx|
         for l in reversed(range(s.depth)):
             self._ff_bwd(ws, a[2 * l + 1], d, d, d, f"{prefix}layers.{l}.1.fn.", rows, ln=f"{prefix}layers.{l}.1.norm.")
             self._attn_bwd(ws, a[2 * l], d, d, d, f"{prefix}layers.{l}.0.", 0, B, T, N)
@@ -592,6 +597,44 @@ class RatEngine:
 
 
     # ------------------------------------------------------------------ backward
+    # Dynamic gradient scaling (fp16 tensor-core mode): every backward kernel publishes max|dx| into a device slot and
+    # the kernel consuming that tensor reads it (include/rat_b200.h, K5).  Slots are zeroed once per step.
+    def _amax_reset(self):
+        self._amax_on = int(query("rat_get_precision")) == 2
+        if self._amax_on:
+            self.amax.zero_()
+        self._amax_next = 0
+        self._amax_of = {}
+
+    def _amax_new(self):
+        if not self._amax_on:
+            return None
+        i = self._amax_next
+        self._amax_next += 1
+        return self.amax[i:i + 1]
+
+    def _amax_in(self, t):
+        """slot holding max|t|; measured with rat_absmax when the last writer of t did not publish it."""
+        if not self._amax_on:
+            return None
+        slot = self._amax_of.get(t.data_ptr())
+        if slot is None:
+            slot = self._amax_new()
+            D = t.shape[-1]
+            call("rat_absmax", t, t.numel() // D, D, D, slot, current_stream())
+            self._amax_of[t.data_ptr()] = slot
+        return slot
+
+    def _amax_out(self, t):
+        if not self._amax_on:
+            return None
+        slot = self._amax_new()
+        self._amax_of[t.data_ptr()] = slot
+        return slot
+
+    def _amax_forget(self, t):
+        self._amax_of.pop(t.data_ptr(), None)
+
     def _attn_bwd(self, ws, x, d_in, base, d_out, pre, mode, B, T, N, alpha=1.0, heads=None, dh=None,
                   wq=None, wk=None, wv=None, names=None, acc_wq=0):
         s, p, g = self.spec, self.p, self.store.grad_views
@@ -608,7 +651,8 @@ class RatEngine:
         call("rat_attn_bwd", x, d_in, base, d_out, p[pre + "norm.weight"], p[pre + "norm.bias"], wq, wk, wv,
              p[pre + "fn.to_out.0.weight"], gq, gk, gv, g[pre + "fn.to_out.0.weight"], g[pre + "fn.to_out.0.bias"],
              g[pre + "norm.weight"], g[pre + "norm.bias"], acc_wq, B, T, N, s.embedding_dim, H, d_h,
-             float(s.dim_head ** -0.5), float(alpha), mode, bw, bw.numel() * 4, current_stream())
+             float(s.dim_head ** -0.5), float(alpha), mode, self._amax_in(d_in), self._amax_out(d_out), bw,
+             bw.numel() * 4, current_stream())
 
     def _ff_bwd(self, ws, x, d_in, base, d_out, pre, rows, ln=None):
         s, p, g = self.spec, self.p, self.store.grad_views
@@ -617,7 +661,8 @@ class RatEngine:
         call("rat_ff_bwd", x, d_in, base, d_out, p[ln + "weight"] if ln else None, p[ln + "bias"] if ln else None,
              p[pre + "net.0.weight"], p[pre + "net.0.bias"], p[pre + "net.3.weight"], g[pre + "net.0.weight"],
              g[pre + "net.0.bias"], g[pre + "net.3.weight"], g[pre + "net.3.bias"], g[ln + "weight"] if ln else None,
-             g[ln + "bias"] if ln else None, rows, D, M, bw, bw.numel() * 4, current_stream())
+             g[ln + "bias"] if ln else None, rows, D, M, self._amax_in(d_in), self._amax_out(d_out), bw,
+             bw.numel() * 4, current_stream())
 
     def encode_backward(self, ws, B, T):
         """ws['dact'] holds d(loss)/d(encoder output); on return it holds d(loss)/d(block after dropout)."""
@@ -655,6 +700,7 @@ class RatEngine:
             self._transformer_bwd(ws, ws["acts_c"], dc, "cross_transformer.", B, 1, T)
             call("rat_strided_copy", dc, d, B * T, s.embedding_dim, s.embedding_dim, N * s.embedding_dim,
                  current_stream())          # d was zeroed by train_step_ids: only token 0 of each row gets gradient
+            self._amax_forget(d)
             self._transformer_bwd(ws, acts, d, "intra_transformer.", B, T, N)
             return d
         raise NotImplementedError(s.model)
@@ -691,15 +737,25 @@ class RatEngine:
             h_prev = ws["h"][li - 1] if li > 0 else ws["x_emb"]
             Kin = units[li - 1] if li > 0 else s.F * s.embedding_dim
             d_prev = ws["dh"][li - 1] if li > 0 else ws["dxemb"]
-            call("rat_sgemm", dh, h_prev, g[f"dnn.dnn.{lin}.weight"], None, u, Kin, B, u, Kin, Kin, 1, 1, gw, gwb, st)
+            am = self._amax_new()                    # max|dz|: the fp16 GEMMs lift dz by a power of two
+            if am is not None:
+                call("rat_absmax", dh, B, u, u, am, st)
+            call("rat_sgemm_scaled", dh, h_prev, g[f"dnn.dnn.{lin}.weight"], None, u, Kin, B, u, Kin, Kin, 1, 1, am,
+                 gw, gwb, st)
             call("rat_colsum", dh, B, u, u, g[f"dnn.dnn.{lin}.bias"], st)
-            call("rat_sgemm", dh, p[f"dnn.dnn.{lin}.weight"], d_prev, None, B, Kin, u, u, Kin, Kin, 0, 1, gw, gwb, st)
+            call("rat_sgemm_scaled", dh, p[f"dnn.dnn.{lin}.weight"], d_prev, None, B, Kin, u, u, Kin, Kin, 0, 1, am,
+                 gw, gwb, st)
 
     def backward(self, ws, B, T):
         """after forward_ids(training=True): fill self.store.G with the data gradient of the mean BCE."""
         s, g, st = self.spec, self.store.grad_views, current_stream()
         N, D, F, L = s.F + 1, s.embedding_dim, s.F, s.L
         enc = ws["enc_out"]
+        self._amax_reset()
+        # d(loss)/d(encoder output) is non-zero only in the pooled token [b,0,0,:] (written by rat_head)
+        slot = self._amax_out(ws["denc"])
+        if slot is not None:
+            call("rat_absmax", ws["denc"], B, D, ws["enc_stride"], slot, st)
         # fc
         call("rat_sgemm", ws["dlogit"], enc, g["fc.weight"], None, 1, D, B, 1, ws["enc_stride"], D, 1, 1, None, 0, st)
         call("rat_colsum", ws["dlogit"], B, 1, 1, g["fc.bias"], st)
