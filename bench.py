@@ -346,20 +346,27 @@ def _oracle_setup(S, K, Bc):
 
 
 def cpu_baseline(a, S, K):
-    """bounded sample of the same workload on the host cores: 1 warm-up + 2 timed oracle training steps at B=cpu_batch."""
+    """bounded sample of the same workload on the host cores: 2 warm-up steps, then oracle training steps at
+    B=cpu_batch (retrieval-set assembly included) for about 12 s of CPU work."""
     Bc = a.cpu_batch
+    torch.set_num_threads(os.cpu_count() or 1)
     O, spec, params, bufs, pool, nbr = _oracle_setup(S, K, Bc)
     st = O.AdamState()
-    ts = []
-    for i in range(3):
-        X, y = O.assemble_batch(pool[i * Bc:(i + 1) * Bc], pool, nbr[i * Bc:(i + 1) * Bc], np.arange(Bc))
-        t0 = time.perf_counter()
+
+    def step(i):
+        j = i % 4
+        X, y = O.assemble_batch(pool[j * Bc:(j + 1) * Bc], pool, nbr[j * Bc:(j + 1) * Bc], np.arange(Bc))
         O.train_step(params, bufs, spec, st, torch.from_numpy(X), torch.from_numpy(y))
-        ts.append(time.perf_counter() - t0)
-    t = min(ts[1:])
-    return {"value": round(Bc / t, 1), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"2 timed oracle (torch-CPU fp32 restatement of the reference) training steps at B={Bc}, "
-                      f"{torch.get_num_threads()} threads, host cpu_count={os.cpu_count()}"}
+    for i in range(2):
+        step(i)
+    n, t0 = 0, time.perf_counter()
+    while n < 3 or (time.perf_counter() - t0 < 12.0 and n < 400):
+        step(n + 2)
+        n += 1
+    t = time.perf_counter() - t0
+    return {"value": round(n * Bc / t, 1), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} timed oracle (torch-CPU fp32 restatement of the reference) training steps at B={Bc} "
+                      f"({t:.1f} s), {torch.get_num_threads()} threads, host cpu_count={os.cpu_count()}"}
 
 
 def run_reference(a):
@@ -371,7 +378,7 @@ def run_reference(a):
     torch.set_num_threads(os.cpu_count() or 1)
     O, spec, params, bufs, pool, nbr = _oracle_setup(S, K, Bc)
     st = O.AdamState()
-    steps, warmup = min(a.steps, 6), min(a.warmup, 1)
+    steps, warmup = max(1, min(a.steps, 200)), max(0, min(a.warmup, 20))
 
     def step(i):
         j = i % 4
