@@ -124,6 +124,20 @@ __device__ __forceinline__ void publish_amax(float* slot, float v) {      // v >
     if (slot != nullptr && (threadIdx.x & 31) == 0 && v > 0.f) atomicMax(reinterpret_cast<int*>(slot), __float_as_int(v));
 }
 
+// block-wide variant (ONE atomic per block: same-address atomics serialise in L2); all threads of the block call it
+__device__ __forceinline__ void publish_amax_block(float* slot, float v) {
+    __shared__ float amax_w[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) amax_w[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0 && slot != nullptr) {
+        const int nw = (blockDim.x + 31) >> 5;
+        for (int w = 1; w < nw; ++w) v = fmaxf(v, amax_w[w]);
+        if (v > 0.f) atomicMax(reinterpret_cast<int*>(slot), __float_as_int(v));
+    }
+}
+
 // ---- VW-wide (1, 2 or 4 floats) vector loads / stores
 template <int VW> struct Vec;
 template <> struct Vec<4> { typedef float4 T; };

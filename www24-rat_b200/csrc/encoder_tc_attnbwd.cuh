@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_bwd_tc(AttnBwdTcArgs a) 
             }
         }
     }
-    publish_amax(a.dx_amax, dx_max);
+    publish_amax_block(a.dx_amax, dx_max);
     __syncthreads();
     if (threadIdx.x < 32) tc5::tmem_dealloc(tmem_base_s, 512);
 }

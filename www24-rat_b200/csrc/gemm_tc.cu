@@ -30,29 +30,43 @@ struct GemmTcArgs {
     int splits;
 };
 
-// stage a [ROWS x 8*CHUNKS] fp32 source tile (row stride ld) as bf16, chunk-major; rows/cols outside the matrix -> 0
+// stage a [ROWS x 8*CHUNKS] fp32 source tile (row stride ld) as fp16, chunk-major; rows/cols outside the matrix -> 0
 __device__ __forceinline__ void gemm_stage_tile(const float* __restrict__ src, int ld, int row0, int col0, int rows_total,
                                                 int cols_total, int ROWS, int CHUNKS, unsigned char* __restrict__ dst,
                                                 bool vec_ok, float mul = 1.0f) {
     const int items = ROWS * CHUNKS;
-    for (int it = threadIdx.x; it < items; it += GT_THREADS) {
-        const int r = it % ROWS, c = it / ROWS;
-        const int gr = row0 + r, gc = col0 + c * 8;
-        float v[8];
-        if (gr < rows_total && gc + 8 <= cols_total && vec_ok) {
-            const float4 t0 = __ldg(reinterpret_cast<const float4*>(src + (size_t)gr * ld + gc));
-            const float4 t1 = __ldg(reinterpret_cast<const float4*>(src + (size_t)gr * ld + gc + 4));
-            v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
-        } else {
+    constexpr int U = 4;                                   // items in flight per thread: all loads first, then the stores
+    for (int it0 = threadIdx.x; it0 < items; it0 += U * GT_THREADS) {
+        float v[U][8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = (gr < rows_total && gc + k < cols_total) ? __ldg(src + (size_t)gr * ld + gc + k) : 0.f;
-        }
-        if (mul != 1.0f) {
+        for (int u = 0; u < U; ++u) {
+            const int it = it0 + u * GT_THREADS;
+            if (it >= items) break;
+            const int r = it % ROWS, c = it / ROWS;
+            const int gr = row0 + r, gc = col0 + c * 8;
+            if (gr < rows_total && gc + 8 <= cols_total && vec_ok) {
+                const float4 t0 = __ldg(reinterpret_cast<const float4*>(src + (size_t)gr * ld + gc));
+                const float4 t1 = __ldg(reinterpret_cast<const float4*>(src + (size_t)gr * ld + gc + 4));
+                v[u][0] = t0.x; v[u][1] = t0.y; v[u][2] = t0.z; v[u][3] = t0.w;
+                v[u][4] = t1.x; v[u][5] = t1.y; v[u][6] = t1.z; v[u][7] = t1.w;
+            } else {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] *= mul;
+                for (int k = 0; k < 8; ++k)
+                    v[u][k] = (gr < rows_total && gc + k < cols_total) ? __ldg(src + (size_t)gr * ld + gc + k) : 0.f;
+            }
         }
-        sts128(dst + tc5::kmajor_off(r, c, ROWS), pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]),
-               pack_h2(v[6], v[7]));
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int it = it0 + u * GT_THREADS;
+            if (it >= items) break;
+            const int r = it % ROWS, c = it / ROWS;
+            if (mul != 1.0f) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[u][k] *= mul;
+            }
+            sts128(dst + tc5::kmajor_off(r, c, ROWS), pack_h2(v[u][0], v[u][1]), pack_h2(v[u][2], v[u][3]),
+                   pack_h2(v[u][4], v[u][5]), pack_h2(v[u][6], v[u][7]));
+        }
     }
 }
 
@@ -148,9 +162,13 @@ struct GemmTcPlan { int BN, n_tiles, m_tiles, splits, kchunk; size_t smem; };
 
 static bool gemm_tc_plan(int M, int N, int K, size_t workspace_bytes, GemmTcPlan* p) {
     if (M < 64 || N < 16 || K < 64) return false;
-    p->n_tiles = (N + 255) / 256;
-    p->BN = round_up(ceil_div(N, p->n_tiles), 16);
     p->m_tiles = ceil_div(M, TILE_M);
+    // narrow output tiles until every SM has a CTA (two CTAs fit per SM: 256 TMEM columns and < 100 KB smem each);
+    // the A tile re-reads of the extra column tiles hit L2
+    p->n_tiles = (N + 255) / 256;
+    if (K < 1024) p->n_tiles = std::max(p->n_tiles, std::min(ceil_div(N, 64), ceil_div(num_sms(), p->m_tiles)));   // long K: split-K instead
+    p->BN = round_up(ceil_div(N, p->n_tiles), 16);
+    p->n_tiles = ceil_div(N, p->BN);
     const int tiles = p->n_tiles * p->m_tiles;
     int splits = 1;
     if (tiles * 2 <= num_sms() && K >= 1024) {

@@ -333,14 +333,31 @@ static int ew_grid(long long total) {
 
 namespace rat {
 // out = max(out, max |x[r*stride + c]|), r < rows, c < cols  (out zeroed by the caller; integer atomicMax on float bits)
-__global__ void k_absmax(const float* __restrict__ x, long long rows, int cols, long long stride, float* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_absmax(const float* __restrict__ x, long long rows, int cols, long long stride,
+                                                float* __restrict__ out) {
+    __shared__ float wm[8];
     const long long total = rows * cols;
     float m = 0.f;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / cols;
-        m = fmaxf(m, fabsf(x[r * stride + (i - r * cols)]));
+    if (stride == cols) {                                   // contiguous: no index arithmetic, 4 loads in flight
+        const long long step = (long long)gridDim.x * blockDim.x;
+        long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; i + 3 * step < total; i += 4 * step)
+            m = fmaxf(fmaxf(m, fmaxf(fabsf(x[i]), fabsf(x[i + step]))), fmaxf(fabsf(x[i + 2 * step]), fabsf(x[i + 3 * step])));
+        for (; i < total; i += step) m = fmaxf(m, fabsf(x[i]));
+    } else {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+            const long long r = i / cols;
+            m = fmaxf(m, fabsf(x[r * stride + (i - r * cols)]));
+        }
     }
-    publish_amax(out, m);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {                                 // ONE atomic per block: same-address atomics serialise in L2
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, wm[w]);
+        if (m > 0.f) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));
+    }
 }
 
 }  // namespace rat
@@ -349,7 +366,8 @@ using namespace rat;
 
 extern "C" int rat_absmax(const float* x, long long rows, int cols, long long row_stride, float* out, void* stream) {
     RAT_REQUIRE(rows > 0 && cols > 0 && row_stride >= cols, "rat_absmax: bad shape");
-    k_absmax<<<ew_grid(rows * cols), 256, 0, (cudaStream_t)stream>>>(x, rows, cols, row_stride, out);
+    const int grid = (int)std::min<long long>((rows * cols + 1023) / 1024, (long long)num_sms() * 4);
+    k_absmax<<<std::max(grid, 1), 256, 0, (cudaStream_t)stream>>>(x, rows, cols, row_stride, out);
     RAT_CHECK_LAUNCH("k_absmax");
     return RAT_OK;
 }
