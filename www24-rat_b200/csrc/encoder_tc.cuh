@@ -296,6 +296,35 @@ __device__ __forceinline__ void wgrad_store(float* __restrict__ rec, int ld, int
 }
 
 
+// Fixed-order sum of the per-CTA gradient records: blockDim = (32 outputs, 8 record slices).  Thread (tx, ty) adds records
+// ty, ty+8, ... of output tx into four interleaved accumulators (four loads in flight; consecutive tx read
+// consecutive floats), the 8 slice sums are combined in slice order through shared memory.  The association depends
+// only on nparts => bitwise deterministic.  Returns the total in slice 0 (other slices return 0); contains
+// __syncthreads, so every thread of the block must call it (active = false contributes nothing).
+__device__ __forceinline__ float record_sum_sliced(const float* __restrict__ partials, size_t psize, int nparts, size_t src,
+                                                   bool active) {
+    __shared__ float red[8][33];
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (active) {
+        int c = threadIdx.y;
+        for (; c + 24 < nparts; c += 32) {
+            const float v0 = partials[(size_t)c * psize + src], v1 = partials[(size_t)(c + 8) * psize + src];
+            const float v2 = partials[(size_t)(c + 16) * psize + src], v3 = partials[(size_t)(c + 24) * psize + src];
+            acc[0] += v0; acc[1] += v1; acc[2] += v2; acc[3] += v3;
+        }
+        for (int k = 0; c < nparts; c += 8, ++k) acc[k] += partials[(size_t)c * psize + src];
+    }
+    __syncthreads();                                   // red of the previous call consumed
+    red[threadIdx.y][threadIdx.x] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    __syncthreads();
+    float s = 0.f;
+    if (threadIdx.y == 0) {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    }
+    return s;
+}
+
 static inline bool ff_tc_supported(int D, int M) {
     if (D < 2 || (D & 1) || D > 64 || M < 1) return false;
     const int Kp = pad16(D), Mp = pad16(M);

@@ -475,7 +475,9 @@ static __global__ void k_reduce_attn_tc(AttnReduceTcArgs a) {
     const int D = a.D, I = a.I;
     const int total = 4 * I * D + 3 * D;
     const size_t offO = (size_t)a.nchunks * a.NCc * a.Kp, offS = offO + (size_t)a.nchunks * a.Cc * a.Kp;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    for (int base = blockIdx.x * 32; base < total; base += gridDim.x * 32) {
+        const int i = min(base + (int)threadIdx.x, total - 1);
+        const bool active = base + (int)threadIdx.x < total;
         size_t src;
         float* dst;
         bool accf = false;
@@ -500,10 +502,8 @@ static __global__ void k_reduce_attn_tc(AttnReduceTcArgs a) {
             float* b = which == 0 ? a.dbo : which == 1 ? a.dln_w : a.dln_b;
             dst = b ? b + d : nullptr;
         }
-        if (!dst) continue;
-        float s = 0.f;
-        for (int c = 0; c < a.nparts; ++c) s += a.partials[(size_t)c * a.psize + src];
-        *dst = accf ? *dst + s : s;
+        const float s = record_sum_sliced(a.partials, a.psize, a.nparts, src, active && dst != nullptr);
+        if (active && dst != nullptr && threadIdx.y == 0) *dst = accf ? *dst + s : s;
     }
 }
 

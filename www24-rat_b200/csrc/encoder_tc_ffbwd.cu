@@ -221,7 +221,9 @@ struct FFReduceTcArgs {
 __global__ void k_reduce_ff_tc(FFReduceTcArgs a) {
     const int D = a.D, M = a.M, Kp = a.Kp, Mp = a.Mp;
     const int total = 2 * M * D + M + D;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    for (int base = blockIdx.x * 32; base < total; base += gridDim.x * 32) {
+        const int i = min(base + (int)threadIdx.x, total - 1);
+        const bool active = base + (int)threadIdx.x < total;
         size_t src;
         float* dst;
         if (i < M * D) { const int m = i / D, d = i - m * D; src = (size_t)m * Kp + d; dst = a.dW1 ? a.dW1 + i : nullptr; }
@@ -229,10 +231,8 @@ __global__ void k_reduce_ff_tc(FFReduceTcArgs a) {
                                   src = (size_t)Mp * Kp + (size_t)m * Kp + d; dst = a.dW2 ? a.dW2 + rem : nullptr; }
         else if (i < 2 * M * D + M) { const int m = i - 2 * M * D; src = (size_t)m * Kp + D; dst = a.db1 ? a.db1 + m : nullptr; }
         else { const int d = i - 2 * M * D - M; src = (size_t)2 * Mp * Kp + d; dst = a.db2 ? a.db2 + d : nullptr; }
-        if (!dst) continue;
-        float s = 0.f;
-        for (int c = 0; c < a.nparts; ++c) s += a.partials[(size_t)c * a.psize + src];
-        *dst = s;
+        const float s = record_sum_sliced(a.partials, a.psize, a.nparts, src, active && dst != nullptr);
+        if (active && dst != nullptr && threadIdx.y == 0) *dst = s;
     }
 }
 
@@ -310,7 +310,7 @@ int ff_bwd_tc_dispatch(const float* x, const float* dout, const float* base, flo
     if (rc != RAT_OK) return rc;
     FFReduceTcArgs r{workspace, 2 * grid, a.psize, dW1, db1, dW2, db2, D, M, a.Kp, a.Mp};
     const int total = 2 * M * D + M + D;
-    k_reduce_ff_tc<<<std::max(1, std::min((total + 255) / 256, 1024)), 256, 0, st>>>(r);
+    k_reduce_ff_tc<<<std::max(1, std::min((total + 31) / 32, 1024)), dim3(32, 8), 0, st>>>(r);
     RAT_CHECK_LAUNCH("k_reduce_ff_tc");
     return RAT_OK;
 }
