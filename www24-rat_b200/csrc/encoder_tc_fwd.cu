@@ -243,7 +243,111 @@ __device__ __forceinline__ void attn_core_bf16(const unsigned char* __restrict__
     }
 }
 
-template <int DH, int KCH, bool VEC4>
+// Long sequences (16 < S <= 128: cross attention at K = 16..64 retrieved neighbours, RAT_m0's flat T*N sequence): a warp
+// task is (sequence, head, block of 16 query rows).  All NKB = ceil(S/16) score blocks of the 16 rows stay in registers
+// (fp32), the softmax statistics are quad reductions as in the short core, P is rounded to fp16 block by block for
+// P.V.  ldmatrix rows beyond the sequence are clamped to its last row (always finite data); their scores are masked.
+template <int DH, int NKB>
+__device__ __forceinline__ void attn_core_long(const unsigned char* __restrict__ QKVt, int hc, unsigned char* __restrict__ Ot,
+                                               int nseq_t, int S, int warp, int nwarps, int lane) {
+    constexpr int DHP = (DH + 15) / 16 * 16, KS = DHP / 16, ND = (DH + 7) / 8;
+    constexpr uint32_t HEAD = (DHP / 8) * tc5::TILE_CHUNK;
+    const int g = lane >> 2, t = lane & 3;
+    const int nrb = (S + 15) >> 4;
+    const int ntasks = nseq_t * hc * nrb;
+    const uint32_t qkv_s = tc5::smem_u32(QKVt);
+    const uint32_t part = (uint32_t)hc * HEAD;
+    const uint32_t a_chunk = (uint32_t)(lane >> 4) * tc5::TILE_CHUNK, b_chunk = (uint32_t)((lane >> 3) & 1) * tc5::TILE_CHUNK;
+    const int a_row = lane & 15, b_row = (lane & 7) + (lane >> 4) * 8;
+    for (int task = warp; task < ntasks; task += nwarps) {
+        const int rb = task % nrb, sh = task / nrb;
+        const int hl = sh % hc, sq = sh / hc;
+        const uint32_t tb = (uint32_t)(sq * S) * 16u;
+        const uint32_t qa = qkv_s + tb + (uint32_t)hl * HEAD;
+        const uint32_t q_off = (uint32_t)min(rb * 16 + a_row, S - 1) * 16u + a_chunk;
+        float sc[NKB][2][4];
+#pragma unroll
+        for (int kb = 0; kb < NKB; ++kb) {
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) sc[kb][nt][0] = sc[kb][nt][1] = sc[kb][nt][2] = sc[kb][nt][3] = 0.f;
+            if (kb < nrb) {
+                const uint32_t k_off = (uint32_t)min(kb * 16 + b_row, S - 1) * 16u + b_chunk;
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    uint32_t a[4], b[4];
+                    ldsm_x4(a, qa + q_off + 2 * ks * tc5::TILE_CHUNK);
+                    ldsm_x4(b, qa + part + k_off + 2 * ks * tc5::TILE_CHUNK);
+                    mma_h_16x8x16(sc[kb][0], a, b[0], b[1]);
+                    mma_h_16x8x16(sc[kb][1], a, b[2], b[3]);
+                }
+            }
+        }
+        float mlo = -INFINITY, mhi = -INFINITY;
+#pragma unroll
+        for (int kb = 0; kb < NKB; ++kb)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int j = kb * 16 + 8 * nt + 2 * t + (e & 1);
+                    if (j >= S) sc[kb][nt][e] = -INFINITY;
+                    if (e < 2) mlo = fmaxf(mlo, sc[kb][nt][e]); else mhi = fmaxf(mhi, sc[kb][nt][e]);
+                }
+        mlo = qmax(mlo); mhi = qmax(mhi);
+        float llo = 0.f, lhi = 0.f;
+#pragma unroll
+        for (int kb = 0; kb < NKB; ++kb)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    sc[kb][nt][e] = ex2f(sc[kb][nt][e] - ((e < 2) ? mlo : mhi));
+                    if (e < 2) llo += sc[kb][nt][e]; else lhi += sc[kb][nt][e];
+                }
+        llo = qsum(llo); lhi = qsum(lhi);
+        float o[2 * KS][4] = {};
+#pragma unroll
+        for (int kb = 0; kb < NKB; ++kb) {
+            if (kb >= nrb) continue;
+            uint32_t pa[4];
+            pa[0] = pack_h2(sc[kb][0][0], sc[kb][0][1]); pa[1] = pack_h2(sc[kb][0][2], sc[kb][0][3]);
+            pa[2] = pack_h2(sc[kb][1][0], sc[kb][1][1]); pa[3] = pack_h2(sc[kb][1][2], sc[kb][1][3]);
+            const uint32_t v_off = (uint32_t)min(kb * 16 + a_row, S - 1) * 16u + a_chunk;
+#pragma unroll
+            for (int pp = 0; pp < KS; ++pp) {
+                uint32_t vb[4];
+                ldsm_x4_t(vb, qa + 2 * part + v_off + 2 * pp * tc5::TILE_CHUNK);
+                mma_h_16x8x16(o[2 * pp], pa, vb[0], vb[1]);
+                if (2 * pp + 1 < ND) mma_h_16x8x16(o[2 * pp + 1], pa, vb[2], vb[3]);
+            }
+        }
+        const float ilo = rcp_fast(llo), ihi = rcp_fast(lhi);
+        const int rlo = rb * 16 + g, rhi = rlo + 8;
+        unsigned char* olo = Ot + tb + (uint32_t)(rlo * 16);
+        unsigned char* ohi = Ot + tb + (uint32_t)(rhi * 16);
+#pragma unroll
+        for (int nd = 0; nd < ND; ++nd) {
+            const int d = 8 * nd + 2 * t;
+            if (d < DH) {
+                const int col = hl * DH + d;
+                const uint32_t co = (uint32_t)(col >> 3) * tc5::TILE_CHUNK + (uint32_t)(col & 7) * 2u;
+                if (rlo < S) *reinterpret_cast<uint32_t*>(olo + co) = pack_h2(o[nd][0] * ilo, o[nd][1] * ilo);
+                if (rhi < S) *reinterpret_cast<uint32_t*>(ohi + co) = pack_h2(o[nd][2] * ihi, o[nd][3] * ihi);
+            }
+        }
+    }
+}
+template <int DH>
+__device__ __forceinline__ void attn_core_long_any(const unsigned char* __restrict__ QKVt, int hc, unsigned char* __restrict__ Ot,
+                                                   int nseq_t, int S, int warp, int nwarps, int lane) {
+    if (S <= 48) attn_core_long<DH, 3>(QKVt, hc, Ot, nseq_t, S, warp, nwarps, lane);
+    else if (S <= 80) attn_core_long<DH, 5>(QKVt, hc, Ot, nseq_t, S, warp, nwarps, lane);
+    else attn_core_long<DH, 8>(QKVt, hc, Ot, nseq_t, S, warp, nwarps, lane);
+}
+
+// LONG = false: sequences of <= 16 tokens (short core, two sequences packed per m16 tile when S <= 8);
+// LONG = true : 16 < S <= 128 (long core).  Separate instantiations keep the short kernel's register allocation intact.
+template <int DH, int KCH, bool VEC4, bool LONG>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_fwd_tc(AttnTcArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int DHP = (DH + 15) / 16 * 16;
@@ -360,7 +464,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_fwd_tc(AttnTcArgs a) {
             tc5::fence_before_sync();
             team_sync(team);
             // ---- softmax(q k^T) v per (sequence, head) -> bf16 o tile
-            attn_core_bf16<DH>(QKVt, hc, Ot, nseq_t, S, warp2, TEAM_THREADS / 32, lane, cl);
+            if (!LONG) attn_core_bf16<DH>(QKVt, hc, Ot, nseq_t, S, warp2, TEAM_THREADS / 32, lane, cl);
+            else attn_core_long_any<DH>(QKVt, hc, Ot, nseq_t, S, warp2, TEAM_THREADS / 32, lane);
             tc5::fence_proxy_async();
             team_sync(team);
             if (tid2 == 0) {
@@ -452,20 +557,24 @@ int ff_fwd_tc_dispatch(const float* x, const float* res, float* out, const float
 #undef RAT_FF_TC
 }
 
-template <int DH, int KCH, bool VEC4>
-static int launch_attn_fwd_tc(const AttnTcArgs& a, cudaStream_t st) {
+template <int DH, int KCH, bool VEC4, bool LONG>
+static int launch_attn_fwd_tc_l(const AttnTcArgs& a, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_attn_fwd_tc<DH, KCH, VEC4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(k_attn_fwd_tc<DH, KCH, VEC4, LONG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              max_smem_optin() - 1024);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_attn_fwd_tc)");
         attr_set = true;
     }
     const long long ntiles = (a.nseq + a.SPT - 1) / a.SPT;
     const int grid = (int)std::min<long long>((ntiles + 1) / 2, (long long)num_sms());
-    k_attn_fwd_tc<DH, KCH, VEC4><<<grid, TC_THREADS, a.smem_bytes, st>>>(a);
+    k_attn_fwd_tc<DH, KCH, VEC4, LONG><<<grid, TC_THREADS, a.smem_bytes, st>>>(a);
     RAT_CHECK_LAUNCH("k_attn_fwd_tc");
     return RAT_OK;
+}
+template <int DH, int KCH, bool VEC4>
+static int launch_attn_fwd_tc(const AttnTcArgs& a, cudaStream_t st) {
+    return a.g.S <= 16 ? launch_attn_fwd_tc_l<DH, KCH, VEC4, false>(a, st) : launch_attn_fwd_tc_l<DH, KCH, VEC4, true>(a, st);
 }
 
 template <int DH>
@@ -488,7 +597,7 @@ int attn_fwd_tc_dispatch(const float* x, const float* res, float* out, const flo
                          const float* Wq, const float* Wk, const float* Wv, const float* Wo, const float* bo, int B, int T,
                          int N, int D, int heads, int dh, float scale, float alpha, int mode, cudaStream_t st) {
     const int S = mode == 0 ? N : T;
-    if (S > 16 || S < 1 || (dh != 10 && dh != 20 && dh != 8) || D < 2 || (D & 1) || D > 64) return 1;
+    if (S > TILE_M || S < 1 || (dh != 10 && dh != 20 && dh != 8) || D < 2 || (D & 1) || D > 64) return 1;
     const int DHP = pad16(dh);
     AttnTcArgs a{};
     a.x = x; a.res = res; a.out = out; a.ln_w = ln_w; a.ln_b = ln_b; a.Wq = Wq; a.Wk = Wk; a.Wv = Wv; a.Wo = Wo; a.bo = bo;
