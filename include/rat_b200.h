@@ -227,6 +227,16 @@ int rat_adam_step(float* W, float* G, float* M, float* V, long long n, long long
 int rat_materialize_grad(const float* G, const float* W, long long n, long long reg_boundary, float lambda_net,
                          float lambda_emb, float* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Validation metrics on the device.  Replaces evaluate_metrics (fuxictr/metrics.py:21-41:
+ * sklearn roc_auc_score + log_loss on predictions clipped to [1e-7, 1-1e-7]) for a whole evaluation pass:
+ * out[0] = exact tie-aware AUC (integer rank statistics), out[1] = logloss (float64), out[2] = #positives,
+ * out[3] = #negatives.  y_true > 0.5 counts as positive.  Deterministic.
+ * ------------------------------------------------------------------------------------------------------- */
+size_t rat_auc_logloss_workspace_bytes(long long n);
+int rat_auc_logloss(const float* y_pred, const float* y_true, long long n, double* out, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -164,6 +164,29 @@ def test_metrics_agree_with_oracle(tmp_path):
     assert r["logloss"] == pytest.approx(O.logloss(y, p), abs=1e-12)
 
 
+@pytest.mark.parametrize("n,ties", [(1, False), (1000, False), (5000, True), (300_000, True)])
+def test_device_auc_logloss_match_sklearn(n, ties):
+    """rat_auc_logloss vs sklearn (the reference's evaluate_metrics): exact tie-aware AUC and float64 logloss; 1e-9."""
+    from sklearn.metrics import log_loss, roc_auc_score
+    from rat_native.engine import EngineSpec, FeatureSpec, RatEngine
+    eng = RatEngine(EngineSpec(features=[FeatureSpec("a", "categorical", 8)]), "cuda:0")
+    g = torch.Generator().manual_seed(n)
+    p = torch.rand(n, generator=g)
+    if ties:
+        p = (p * 50).round() / 50                          # heavy ties incl. exact 0.0 and 1.0
+    y = (torch.rand(n, generator=g) < 0.3 + 0.4 * p).float()
+    if n == 1:
+        auc, ll = eng.auc_logloss(p.cuda(), y.cuda())
+        assert np.isnan(auc)                               # one class only (sklearn raises)
+        return
+    auc, ll = eng.auc_logloss(p.cuda(), y.cuda())
+    pn, yn = p.double().numpy(), y.double().numpy()
+    assert auc == pytest.approx(roc_auc_score(yn, pn), abs=1e-9)
+    assert ll == pytest.approx(log_loss(yn, np.clip(pn, 1e-7, 1 - 1e-7)), abs=1e-9)
+    auc2, ll2 = eng.auc_logloss(p.cuda(), y.cuda())
+    assert auc2 == auc and ll2 == ll                       # deterministic
+
+
 def test_dropout_training_is_statistically_sane(tmp_path):
     """emb_dropout / net_dropout > 0 (kkbox, tmall configs): the reference philox stream cannot be reproduced
     (SURVEY H4); check that training with the device-side masks still decreases the loss and stays finite."""

@@ -616,3 +616,155 @@ extern "C" int rat_radix_sort_pairs(unsigned int* keys, unsigned int* vals, unsi
     *result_in_tmp = flips & 1;
     return RAT_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Device-side validation metrics.  Replaces the per-pass host work of evaluate_metrics
+// (fuxictr/metrics.py:21-41: sklearn roc_auc_score + log_loss with predictions clipped to [1e-7, 1-1e-7]).
+//   AUC  = sum over positives of (#negatives with a smaller score + 0.5 #negatives with an equal score) / (P N):
+//          stable radix sort of the score bits, prefix count of negatives, tie groups located by binary search;
+//          the sum is accumulated as an exact integer (2x contributions, 64-bit atomics: order independent).
+//   logloss in float64, per-block partial sums reduced in block order (deterministic).
+namespace rat {
+
+__global__ void k_metric_keys(const float* __restrict__ pred, const float* __restrict__ y, long long n,
+                              unsigned int* __restrict__ keys, unsigned int* __restrict__ vals,
+                              double* __restrict__ ll_part) {
+    __shared__ double wsum[8];
+    double s = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float p = pred[i];
+        const unsigned int b = __float_as_uint(p);
+        keys[i] = (b & 0x80000000u) ? ~b : (b | 0x80000000u);          // order-preserving map of IEEE floats
+        const bool pos = y[i] > 0.5f;
+        vals[i] = pos ? 1u : 0u;
+        const double pc = fmin(fmax((double)p, 1e-7), 1.0 - 1e-7);
+        s -= pos ? log(pc) : log(1.0 - pc);
+    }
+    s = warp_sum_d(s);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += wsum[w];
+        ll_part[blockIdx.x] = t;
+    }
+}
+
+// negatives per 1024-element block of the sorted order
+__global__ void __launch_bounds__(1024) k_metric_block_neg(const unsigned int* __restrict__ lab, long long n,
+                                                           unsigned int* __restrict__ blockneg) {
+    __shared__ unsigned int ws[32];
+    const long long i = (long long)blockIdx.x * 1024 + threadIdx.x;
+    const unsigned int neg = (i < n && lab[i] == 0u) ? 1u : 0u;
+    const unsigned int c = __popc(__ballot_sync(0xffffffffu, neg));
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) { unsigned int t = 0; for (int w = 0; w < 32; ++w) t += ws[w]; blockneg[blockIdx.x] = t; }
+}
+
+// cneg[i] = number of negatives at sorted positions < i  (blockneg already exclusive-scanned)
+__global__ void __launch_bounds__(1024) k_metric_cneg(const unsigned int* __restrict__ lab, long long n,
+                                                      const unsigned int* __restrict__ blockneg,
+                                                      unsigned int* __restrict__ cneg) {
+    __shared__ unsigned int ws[32];
+    const long long i = (long long)blockIdx.x * 1024 + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int neg = (i < n && lab[i] == 0u) ? 1u : 0u;
+    const unsigned int bal = __ballot_sync(0xffffffffu, neg);
+    if (lane == 0) ws[warp] = __popc(bal);
+    __syncthreads();
+    unsigned int base = blockneg[blockIdx.x];
+    for (int w = 0; w < warp; ++w) base += ws[w];
+    if (i < n) cneg[i] = base + __popc(bal & ((1u << lane) - 1u));
+}
+
+// acc[0] += 2 * (#neg below) + (#neg tied) over positives ; acc[1] += #positives
+__global__ void k_metric_auc(const unsigned int* __restrict__ keys, const unsigned int* __restrict__ lab,
+                             const unsigned int* __restrict__ cneg, long long n, unsigned long long* __restrict__ acc) {
+    unsigned long long s = 0, np = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (lab[i] == 0u) continue;
+        const unsigned int k = keys[i];
+        long long lo = i, hi = i;                                        // tie group [lo, hi]
+        if (i > 0 && keys[i - 1] == k) {                                 // lower bound of k in [0, i)
+            long long a = 0, b = i;
+            while (a < b) { const long long m = (a + b) >> 1; if (keys[m] < k) a = m + 1; else b = m; }
+            lo = a;
+        }
+        if (i + 1 < n && keys[i + 1] == k) {                             // upper bound of k in (i, n)
+            long long a = i + 1, b = n;
+            while (a < b) { const long long m = (a + b) >> 1; if (keys[m] <= k) a = m + 1; else b = m; }
+            hi = a - 1;
+        }
+        const unsigned long long below = cneg[lo];
+        const unsigned long long upto = (unsigned long long)cneg[hi] + (lab[hi] == 0u ? 1u : 0u);   // negatives in [0, hi]
+        s += 2ull * below + (upto - below);
+        ++np;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); np += __shfl_xor_sync(0xffffffffu, np, o); }
+    if ((threadIdx.x & 31) == 0) { if (s) atomicAdd(&acc[0], s); if (np) atomicAdd(&acc[1], np); }
+}
+
+__global__ void k_metric_finalize(const unsigned long long* __restrict__ acc, const double* __restrict__ ll_part, int nparts,
+                                  long long n, double* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double ll = 0.0;
+    for (int i = 0; i < nparts; ++i) ll += ll_part[i];
+    const double P = (double)acc[1], N = (double)n - P;
+    out[0] = (P > 0 && N > 0) ? (double)acc[0] / (2.0 * P * N) : nan("");
+    out[1] = ll / (double)n;
+    out[2] = P;
+    out[3] = N;
+}
+
+struct MetricLayout { unsigned int *k0, *v0, *k1, *v1, *hist, *blockneg, *cneg; double* ll_part; unsigned long long* acc; size_t bytes; int nblk, nb1k; };
+static MetricLayout metric_layout(void* ws, long long n) {
+    MetricLayout w{};
+    const size_t nk = (size_t)((n + 3) / 4 * 4);
+    w.nblk = (int)((n + RS_TILE - 1) / RS_TILE);
+    w.nb1k = (int)((n + 1023) / 1024);
+    unsigned int* p = (unsigned int*)ws;
+    w.k0 = p; p += nk; w.v0 = p; p += nk; w.k1 = p; p += nk; w.v1 = p; p += nk;
+    w.hist = p; p += ((size_t)256 * w.nblk + 3) / 4 * 4;
+    w.blockneg = p; p += ((size_t)w.nb1k + 4) / 4 * 4;
+    w.cneg = p; p += nk;
+    w.ll_part = (double*)p; p += 2 * 1024;
+    w.acc = (unsigned long long*)p; p += 8;
+    w.bytes = (size_t)((char*)p - (char*)ws);
+    return w;
+}
+
+}  // namespace rat
+
+extern "C" size_t rat_auc_logloss_workspace_bytes(long long n) { return rat::metric_layout(nullptr, n).bytes + 64; }
+
+extern "C" int rat_auc_logloss(const float* y_pred, const float* y_true, long long n, double* out, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+    RAT_REQUIRE(n > 0 && n < (1ll << 31), "rat_auc_logloss: bad n");
+    RAT_REQUIRE(workspace && ((uintptr_t)workspace & 15) == 0 && workspace_bytes >= rat_auc_logloss_workspace_bytes(n),
+                "rat_auc_logloss: workspace missing, unaligned or too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    MetricLayout w = metric_layout(workspace, n);
+    const int kgrid = (int)std::min<long long>((n + 255) / 256, 1024);
+    cudaError_t e = cudaMemsetAsync(w.acc, 0, 2 * sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(metric accumulators)");
+    k_metric_keys<<<kgrid, 256, 0, st>>>(y_pred, y_true, n, w.k0, w.v0, w.ll_part);
+    RAT_CHECK_LAUNCH("k_metric_keys");
+    unsigned int *ki = w.k0, *vi = w.v0, *ko = w.k1, *vo = w.v1;
+    for (int shift = 0; shift < 32; shift += 8) {
+        k_radix_hist<<<w.nblk, RS_THREADS, 0, st>>>(ki, n, shift, w.hist, w.nblk, nullptr);
+        k_scan_exclusive<<<1, 1024, 0, st>>>(w.hist, 256 * w.nblk);
+        k_radix_scatter<<<w.nblk, RS_THREADS, 0, st>>>(ki, vi, ko, vo, n, shift, w.hist, w.nblk);
+        RAT_CHECK_LAUNCH("metric radix pass");
+        std::swap(ki, ko);
+        std::swap(vi, vo);
+    }
+    k_metric_block_neg<<<w.nb1k, 1024, 0, st>>>(vi, n, w.blockneg);
+    k_scan_exclusive<<<1, 1024, 0, st>>>(w.blockneg, w.nb1k);
+    k_metric_cneg<<<w.nb1k, 1024, 0, st>>>(vi, n, w.blockneg, w.cneg);
+    k_metric_auc<<<kgrid, 256, 0, st>>>(ki, vi, w.cneg, n, w.acc);
+    k_metric_finalize<<<1, 32, 0, st>>>(w.acc, w.ll_part, kgrid, n, out);
+    RAT_CHECK_LAUNCH("metric reduce");
+    return RAT_OK;
+}

@@ -371,8 +371,26 @@ class BaseModel(nn.Module):
         return y_pred, y_true
 
     def evaluate_generator(self, data_generator):
-        y_pred, y_true = self._predict_all(data_generator, True)
-        return self.evaluate_metrics(y_true, y_pred, self._validation_metrics)
+        """reference :232-247.  AUC / logloss of the whole pass are computed on the device (rat_auc_logloss: exact
+        tie-aware AUC from a radix sort of the scores, float64 logloss with the reference's 1e-7 clip) and only the two
+        numbers travel to the host; any other metric falls back to evaluate_metrics on host copies."""
+        metrics = list(self._validation_metrics)
+        if not all(m in ("AUC", "logloss", "binary_crossentropy") for m in metrics):
+            y_pred, y_true = self._predict_all(data_generator, True)
+            return self.evaluate_metrics(y_true, y_pred, metrics)
+        self.eval()
+        preds, trues = [], []
+        for batch_data in data_generator:
+            ws, B, T = self._load_batch(batch_data, training=False)
+            preds.append(self._engine.forward_ids(ws, B, T, training=False).clone())
+            trues.append(ws["y_true"].clone())
+        self._engine.check_errors()
+        auc, ll = self._engine.auc_logloss(torch.cat(preds), torch.cat(trues))
+        result = dict()
+        for m in metrics:
+            result[m] = auc if m == "AUC" else ll
+        logging.info("[Metrics] " + " - ".join("{}: {:.6f}".format(k, v) for k, v in result.items()))
+        return result
 
     def evaluate_metrics(self, y_true, y_pred, metrics):
         return evaluate_metrics(y_true, y_pred, metrics)

@@ -852,6 +852,18 @@ class RatEngine:
             done.record(self._side)
         ws["plan_event"] = done
 
+    def auc_logloss(self, y_pred: torch.Tensor, y_true: torch.Tensor):
+        """(AUC, logloss) of device vectors y_pred / y_true [n] -- fuxictr/metrics.py:21-41 on the device."""
+        n = int(y_pred.numel())
+        y_pred = y_pred.reshape(-1).float().contiguous()
+        y_true = y_true.reshape(-1).float().contiguous()
+        nb = int(query("rat_auc_logloss_workspace_bytes", n))
+        ws = torch.empty(nb // 4 + 4, dtype=torch.int32, device=self.device)
+        out = torch.empty(4, dtype=torch.float64, device=self.device)
+        call("rat_auc_logloss", y_pred, y_true, n, out, ws, ws.numel() * 4, current_stream())
+        r = out.cpu()
+        return float(r[0]), float(r[1])
+
     def materialize_grads(self) -> Dict[str, torch.Tensor]:
         """dense gradients incl. the regulariser (what the reference's .grad holds before clipping). Tests only."""
         s, gs = self.spec, self.store
