@@ -109,12 +109,10 @@ __device__ __forceinline__ void store8(float* __restrict__ row, int c0, int D, c
 // Load one token row half (KCH chunks of 8 columns starting at chunk h*KCH), optionally LayerNorm it (the two lanes
 // of a row pair exchange partial sums by shuffle), convert to bf16 and store the chunks into the canonical A tile.
 //   tid2 = thread index inside the team (0..255): row = tid2 / 2, h = tid2 % 2.   valid=false -> zero row.
+// The load and the (LayerNorm, convert, store) halves are separate so that a kernel can issue the loads of its NEXT tile
+// early (registers) and finish them when the tile starts.
 template <int KCH, bool VEC4>
-__device__ __forceinline__ void stage_row_h(const float* __restrict__ src, bool valid, int D, int KC, int row, int h,
-                                               const float* __restrict__ ln_w, const float* __restrict__ ln_b,
-                                               unsigned char* __restrict__ At, int ones_col = -1,
-                                               float* __restrict__ stats = nullptr, float mul = 1.0f) {
-    float v[KCH][8];
+__device__ __forceinline__ void stage_row_load(const float* __restrict__ src, bool valid, int D, int h, float (&v)[KCH][8]) {
 #pragma unroll
     for (int j = 0; j < KCH; ++j) {
         if (valid) load8<VEC4>(src, (h * KCH + j) * 8, D, v[j]);
@@ -123,6 +121,12 @@ __device__ __forceinline__ void stage_row_h(const float* __restrict__ src, bool 
             for (int k = 0; k < 8; ++k) v[j][k] = 0.f;
         }
     }
+}
+template <int KCH>
+__device__ __forceinline__ void stage_row_finish(float (&v)[KCH][8], bool valid, int D, int row, int h,
+                                                 const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                                                 unsigned char* __restrict__ At, int ones_col = -1,
+                                                 float* __restrict__ stats = nullptr, float mul = 1.0f) {
     if (ln_w != nullptr) {
         float s = 0.f;
 #pragma unroll
@@ -167,6 +171,15 @@ __device__ __forceinline__ void stage_row_h(const float* __restrict__ src, bool 
     for (int j = 0; j < KCH; ++j)
         sts128(At + tc5::toff(row, h * KCH + j), pack_h2(v[j][0], v[j][1]), pack_h2(v[j][2], v[j][3]),
                pack_h2(v[j][4], v[j][5]), pack_h2(v[j][6], v[j][7]));
+}
+template <int KCH, bool VEC4>
+__device__ __forceinline__ void stage_row_h(const float* __restrict__ src, bool valid, int D, int KC, int row, int h,
+                                               const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                                               unsigned char* __restrict__ At, int ones_col = -1,
+                                               float* __restrict__ stats = nullptr, float mul = 1.0f) {
+    float v[KCH][8];
+    stage_row_load<KCH, VEC4>(src, valid, D, h, v);
+    stage_row_finish<KCH>(v, valid, D, row, h, ln_w, ln_b, At, ones_col, stats, mul);
 }
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t saddr) {

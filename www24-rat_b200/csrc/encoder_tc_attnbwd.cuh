@@ -430,6 +430,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_bwd_tc(AttnBwdTcArgs a) 
                 }
             }
         }
+        // ---- pull the rows the NEXT tile will stage towards L2 (x was written a whole forward pass ago: DRAM) while the
+        //      tile-end jobs run; no registers are held
+        if (tile + gridDim.x < ntiles) {
+            const long long s1 = (tile + gridDim.x) * a.SPT;
+            const int R1 = (int)min((long long)a.SPT, a.nseq - s1) * S;
+            const int tid2 = threadIdx.x & 255, row = tid2 >> 1;
+            if (row < R1) {
+                const int ls = row / S, pos = row - ls * S;
+                const float* p = (threadIdx.x < 256 ? a.x : a.dout) + a.g.grow(s1 + ls, pos) * D + (tid2 & 1) * 32;
+                if ((tid2 & 1) * 32 < D) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+            }
+        }
         // ---- tile-end jobs: dbo = colsum(alpha*dout), dbeta = colsum(g), dgamma = colsum(g*xhat)
 #pragma unroll
         for (int j = 0; j < JW; ++j) {
