@@ -42,6 +42,7 @@ for K in Ks:
         ms = e0.elapsed_time(e1) / n
         cells.append(f"{B / ms * 1e3:,.0f}")
         model._engine._ws.clear()
+        model._engine._graphs.clear()
         torch.cuda.empty_cache()
     print(f"| {K} | " + " | ".join(cells) + " |", flush=True)
     del model

@@ -339,6 +339,8 @@ class RatEngine:
         self.world = 1
         self.dist_group = None
         self._side = None
+        self.graph_inference = True         # CUDA-graph replay of the eval forward (see forward_ids)
+        self._graphs: Dict[tuple, object] = {}
         self.amax = torch.zeros(256, dtype=torch.float32, device=self.device)
         self._amax_next = 0
         self._amax_of = {}
@@ -424,6 +426,7 @@ class RatEngine:
         B, T, L = X.shape
         assert L == self.spec.L, f"input_length {L} != schema {self.spec.L}"
         ws = self._workspace(B, T, training)
+        self.err_flag.zero_()
         call("rat_convert_wire_f64", X, y, ws["ids"], ws["labels"], ws["y_true"], B, T, L, current_stream())
         return ws
 
@@ -559,11 +562,34 @@ class RatEngine:
         return (self.rng_step * 64 + slot) & 0xFFFFFFFF
 
     def forward_ids(self, ws, B, T, training=False, with_loss=False, inv_count=None):
-        """ids/labels already in ws -> y_pred [B]; keeps activations in ws when training."""
+        """ids/labels already in ws -> y_pred [B]; keeps activations in ws when training.
+
+        Inference (eval, no loss) is launch-bound at small batches (~25 kernels of a few microseconds each), so the
+        second call with the same (B, T, precision) captures the kernel sequence into a CUDA graph and later calls
+        replay it; every buffer the kernels touch (workspace, flat parameter buffer, BN buffers) is persistent."""
+        import rat_native as _rn
+        if (self.graph_inference and not training and not with_loss and self.store.shard is None
+                and _rn._profile is None and not torch.cuda.is_current_stream_capturing()):
+            key = (B, T, int(query("rat_get_precision")))
+            entry = self._graphs.get(key)
+            if entry is None or entry[1] is not ws:         # first call (or a new workspace): eager, warms up lazy state
+                self._graphs[key] = ("warm", ws)
+            else:
+                if entry[0] == "warm":
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._forward_ids_impl(ws, B, T, False, False, None)
+                    entry = (g, ws)                         # the graph keeps its workspace alive
+                    self._graphs[key] = entry
+                entry[0].replay()
+                return ws["y_pred"]
+        return self._forward_ids_impl(ws, B, T, training, with_loss, inv_count)
+
+    def _forward_ids_impl(self, ws, B, T, training, with_loss, inv_count):
         s, st = self.spec, current_stream()
         D, F, L = s.embedding_dim, s.F, s.L
         drop = s.emb_dropout if training else 0.0
-        self.err_flag.zero_()
         if self.store.shard is None:
             call("rat_gather_fwd", self.store.emb_W, self.store.lr_W, self.p["label_embedding_layer.weight"], ws["ids"],
                  ws["labels"], self.col_off, self.col_vocab, self.field_col0, self.field_width, ws["acts"][0],
