@@ -56,10 +56,11 @@ def parse():
     return ap.parse_args()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/),
-# kkbox shape, B=4096, K=5.  The 126 MB L2 absorbs most of the 55 MB block writes, so DRAM traffic is BELOW the
-# algorithmic bytes for these kernels (no wasted re-reads).
-NCU_TRAFFIC = {"attn_bwd": 129.3e6, "gather": 19.9e6}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/
+# r01_final_backward_kernels_ncu_full.txt, r01_v3_gather_scatter_ncu_full.txt + the k_gather_flat capture quoted in
+# DESIGN.md), kkbox shape, B=4096, K=5.  The 126 MB L2 absorbs most of the 55 MB block writes, so DRAM traffic is BELOW
+# the algorithmic bytes for these kernels (no wasted re-reads).
+NCU_TRAFFIC = {"attn_bwd": 133.9e6, "gather": 18.4e6, "scatter": 74.3e6}
 
 
 def peaks():
@@ -263,19 +264,21 @@ def run_ours(a):
     roofline = {"kernel": "k_attn_bwd_tc (+k_reduce_attn_tc)" if tc_mode else "k_attn_bwd (+k_reduce_attn)",
                 "bound": "tensor", "achieved": round(ach_tf, 3),
                 "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": round(ach_tf / pk["tf_sustained"], 5),
-                "traffic": NCU_TRAFFIC.get("attn_bwd") if tc_mode else None,
+                "traffic": NCU_TRAFFIC.get("attn_bwd") if tc_mode and S == "kkbox" and B == 4096 and K == 5 else None,
                 "peak_source": pk["src"] + " bf16 dense (sustained)", "avg_launch_ms": round(ab_ms, 4),
                 "flops_per_launch": attn_bwd_flops,
                 "hbm_view": {"bytes_per_launch": ab_bytes, "achieved_gbs": round(ab_bytes / (ab_ms * 1e-3) / 1e9, 1),
                              "frac_of_hbm_peak": round(ab_bytes / (ab_ms * 1e-3) / 1e9 / pk["hbm"], 4)},
-                "note": "algorithmic FLOPs = 2.75x forward (recompute + dgrad + wgrad); issue/latency-bound: the softmax-"
-                        "backward core runs ~380 SASS instructions per (sequence, head) task around 12 mma.sync, see "
-                        "profiles/ and DESIGN.md section 3"}
+                "note": "algorithmic FLOPs = 2.75x forward (recompute + dgrad + wgrad); issue/latency-bound: every GEMM has "
+                        "K <= 80, N <= 192 and the softmax-backward core between them runs ~450 SASS instructions per "
+                        "(sequence, head) task around 12 mma.sync; see profiles/r01_final_backward_kernels_ncu_full.txt and "
+                        "DESIGN.md section 3"}
     gb = B * gather_bytes_per_sample(K, L, F, D)
     g_ms = per_call_ms("rat_gather_fwd_sharded" if sharded else "rat_gather_fwd")
     roofline_gather = {"kernel": "k_gather_flat" + (" (rows loaded from the owners' shards over NVLink peer pointers)" if sharded else ""), "bound": "hbm", "achieved": round(gb / (g_ms * 1e-3) / 1e9, 1),
                        "peak": pk["hbm"], "unit": "GB/s", "frac": round(gb / (g_ms * 1e-3) / 1e9 / pk["hbm"], 4),
-                       "traffic": NCU_TRAFFIC.get("gather"), "bytes_per_launch": gb, "peak_source": pk["src"],
+                       "traffic": NCU_TRAFFIC.get("gather") if S == "kkbox" and B == 4096 and K == 5 and not sharded else None,
+                       "bytes_per_launch": gb, "peak_source": pk["src"],
                        "avg_launch_ms": round(g_ms, 4)}
     # scatter: the critical-path call (segment scan + fix-ups; dropout backward fused).  Algorithmic bytes:
     # block gradient read once + sorted key/occurrence index + one gradient row per occurrence written... i.e.
@@ -285,9 +288,10 @@ def run_ours(a):
     sc_ms = per_call_ms("rat_emb_scatter_reduce")
     plan_ms = per_call_ms("rat_emb_scatter_plan") if "rat_emb_scatter_plan" in prof else 0.0
     sc_bytes = B * T * N * D * 4 + B * T * (L + 1) * 8 + B * T * L * D * 4
-    roofline_scatter = {"kernel": "rat_emb_scatter_reduce (k_segment_scan + k_fixup_short + k_fixup_long)", "bound": "hbm",
+    roofline_scatter = {"kernel": "rat_emb_scatter_reduce (k_segment_scan + k_fixup_items)", "bound": "hbm",
                         "achieved": round(sc_bytes / (sc_ms * 1e-3) / 1e9, 1), "peak": pk["hbm"], "unit": "GB/s",
-                        "frac": round(sc_bytes / (sc_ms * 1e-3) / 1e9 / pk["hbm"], 4), "traffic": None,
+                        "frac": round(sc_bytes / (sc_ms * 1e-3) / 1e9 / pk["hbm"], 4),
+                        "traffic": NCU_TRAFFIC.get("scatter") if S == "kkbox" and B == 4096 and K == 5 else None,
                         "bytes_per_launch": sc_bytes, "peak_source": pk["src"], "avg_launch_ms": round(sc_ms, 4),
                         "plan_ms_side_stream": round(plan_ms, 4),
                         "frac_incl_plan": round(sc_bytes / ((sc_ms + plan_ms) * 1e-3) / 1e9 / pk["hbm"], 4)}
