@@ -274,18 +274,60 @@ def run_ours(a):
                         "(sequence, head) task around 12 mma.sync; see profiles/r01_final_backward_kernels_ncu_full.txt and "
                         "DESIGN.md section 3"}
     gb = B * gather_bytes_per_sample(K, L, F, D)
-    g_ms = per_call_ms("rat_gather_fwd_sharded" if sharded else "rat_gather_fwd")
+    g_step_ms = per_call_ms("rat_gather_fwd_sharded" if sharded else "rat_gather_fwd")
+    # A 30 us kernel bracketed by its own event pair also pays ~4 us of event + launch turnaround on the device, so
+    # the gather / scatter-reduce launch durations are taken from 24 back-to-back launches between ONE event pair
+    # (rotating output blocks: 6 x 55 MB > L2); the single-launch in-step figure is reported next to it.
+    eng = model._engine
+    ws = eng._workspace(B, T, True)
+    st_ = rn.current_stream()
+    blocks = [torch.empty_like(ws["acts"][0]) for _ in range(6)]
+
+    def loop_ms(fn, n=24):
+        for i in range(4):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+    drop = float(eng.spec.emb_dropout)
+    if sharded:
+        g_ms = g_step_ms
+    else:
+        g_ms = loop_ms(lambda i: rn.call(
+            "rat_gather_fwd", eng.store.emb_W, eng.store.lr_W, eng.p["label_embedding_layer.weight"], ws["ids"], ws["labels"],
+            eng.col_off, eng.col_vocab, eng.field_col0, eng.field_width, blocks[i % 6], ws["x_emb"], ws["lr_out"], B, T, L,
+            F, D, drop, eng.spec.seed, 7, eng.err_flag, st_))
     roofline_gather = {"kernel": "k_gather_flat" + (" (rows loaded from the owners' shards over NVLink peer pointers)" if sharded else ""), "bound": "hbm", "achieved": round(gb / (g_ms * 1e-3) / 1e9, 1),
                        "peak": pk["hbm"], "unit": "GB/s", "frac": round(gb / (g_ms * 1e-3) / 1e9 / pk["hbm"], 4),
                        "traffic": NCU_TRAFFIC.get("gather") if S == "kkbox" and B == 4096 and K == 5 and not sharded else None,
                        "bytes_per_launch": gb, "peak_source": pk["src"],
-                       "avg_launch_ms": round(g_ms, 4)}
+                       "avg_launch_ms": round(g_ms, 4), "in_step_single_launch_ms": round(g_step_ms, 4)}
     # scatter: the critical-path call (segment scan + fix-ups; dropout backward fused).  Algorithmic bytes:
     # block gradient read once + sorted key/occurrence index + one gradient row per occurrence written... i.e.
     # B*T*N*D*4 (block grad) + B*T*(L+1)*8 (sorted keys, vals) + B*T*L*D*4 (per-occurrence row reads, sequence
     # columns re-read their token from L2).  The key build + radix sort (rat_emb_scatter_plan) only needs the ids and
     # runs on a side stream under the forward kernels; its duration is reported next to it.
-    sc_ms = per_call_ms("rat_emb_scatter_reduce")
+    sc_step_ms = per_call_ms("rat_emb_scatter_reduce")
+    sw = ws["scatter_ws"]
+    if sharded:
+        sc_ms = sc_step_ms
+    else:
+        gs_ = eng.store
+        rn.call("rat_emb_scatter_plan", ws["ids"], ws["labels"], eng.col_off, eng.col_pad, eng.col_vocab, B, T, L, F, D,
+                eng.spec.V, sw, sw.numel() * 4, st_)
+        g_emb = gs_.G[gs_.emb_off:gs_.emb_off + eng.spec.V * D]
+        g_lr = gs_.G[gs_.lr_off:gs_.lr_off + eng.spec.V] if eng.spec.use_wide else None
+        sc_ms = loop_ms(lambda i: rn.call(
+            "rat_emb_scatter_reduce", ws["ids"], ws["labels"], blocks[i % 6], ws["dxemb"], ws["dlogit"] if eng.spec.use_wide
+            else None, eng.col_off, eng.col_pad, eng.col_vocab, eng.col_field, g_emb, g_lr,
+            gs_.grad_views["label_embedding_layer.weight"], B, T, L, F, D, eng.spec.V, drop, eng.spec.seed, 7, 1, sw,
+            sw.numel() * 4, st_))
+        gs_.G.zero_()
     plan_ms = per_call_ms("rat_emb_scatter_plan") if "rat_emb_scatter_plan" in prof else 0.0
     sc_bytes = B * T * N * D * 4 + B * T * (L + 1) * 8 + B * T * L * D * 4
     roofline_scatter = {"kernel": "rat_emb_scatter_reduce (k_segment_scan + k_fixup_items)", "bound": "hbm",
@@ -293,6 +335,7 @@ def run_ours(a):
                         "frac": round(sc_bytes / (sc_ms * 1e-3) / 1e9 / pk["hbm"], 4),
                         "traffic": NCU_TRAFFIC.get("scatter") if S == "kkbox" and B == 4096 and K == 5 else None,
                         "bytes_per_launch": sc_bytes, "peak_source": pk["src"], "avg_launch_ms": round(sc_ms, 4),
+                        "in_step_single_call_ms": round(sc_step_ms, 4),
                         "plan_ms_side_stream": round(plan_ms, 4),
                         "frac_incl_plan": round(sc_bytes / ((sc_ms + plan_ms) * 1e-3) / 1e9 / pk["hbm"], 4)}
     P = model._engine.store.total
