@@ -46,7 +46,7 @@ static bool attn_bwd_tc_plan(int S, int D, int heads, int dh, AttnBwdTcArgs* a) 
     const size_t tiles = (size_t)TILE_M * (2 * a->Kp + a->NCq + a->NCc + a->Cc + a->NDo) * 2;
     if ((size_t)2 * TILE_M * a->Kp * 2 > (size_t)TILE_M * a->NCq * 2) return false;      // G1|G2 alias the q|k|v tile
     a->smem_bytes = (int)(images + tiles + (size_t)(2 + 8) * TILE_M * 4);
-    return a->smem_bytes <= max_smem_optin() - 1024;
+    return a->smem_bytes <= max_smem_optin() - 2048;
 }
 static int attn_bwd_tc_grid(const AttnBwdTcArgs& a, long long nseq) {
     return (int)std::min<long long>((nseq + a.SPT - 1) / a.SPT, (long long)num_sms());

@@ -44,7 +44,7 @@ template <int DH>
 __device__ __forceinline__ void attn_bwd_core_bf16(const unsigned char* __restrict__ QKVt, const unsigned char* __restrict__ dOt,
                                                    unsigned char* __restrict__ dQc, unsigned char* __restrict__ Ot, int hc,
                                                    int nseq_t, int S, float scale, int warp, int nwarps, int lane,
-                                                   const CoreLane& cl) {
+                                                   const CoreLane& cl, const uint32_t* __restrict__ coltab) {
     constexpr int DHP = (DH + 15) / 16 * 16, KS = DHP / 16, ND = (DH + 7) / 8;
     constexpr uint32_t HEAD = (DHP / 8) * tc5::TILE_CHUNK;
     const int t = lane & 3;
@@ -146,10 +146,9 @@ __device__ __forceinline__ void attn_bwd_core_bf16(const unsigned char* __restri
         for (int nd = 0; nd < ND; ++nd) {
             const int d = 8 * nd + 2 * t;
             if (d < DH) {
-                const int cq = hl * DH + d, ck = cq + hc * DH, cv = ck + hc * DH;
-                const uint32_t oq = (uint32_t)(cq >> 3) * tc5::TILE_CHUNK + (uint32_t)(cq & 7) * 2u;
-                const uint32_t ok = (uint32_t)(ck >> 3) * tc5::TILE_CHUNK + (uint32_t)(ck & 7) * 2u;
-                const uint32_t ov = (uint32_t)(cv >> 3) * tc5::TILE_CHUNK + (uint32_t)(cv & 7) * 2u;
+                // byte offset of compact column c inside a tile row: (c >> 3) * TILE_CHUNK + (c & 7) * 2, from a table
+                const int cq = hl * DH + d;
+                const uint32_t oq = coltab[cq], ok = coltab[cq + hc * DH], ov = coltab[cq + 2 * hc * DH];
                 if (vlo) {
                     *reinterpret_cast<uint32_t*>(dQc + rlo + oq) = pack_h2(dq[nd][0] * scale, dq[nd][1] * scale);
                     *reinterpret_cast<uint32_t*>(dQc + rlo + ok) = pack_h2(dk[nd][0] * inv_log2e, dk[nd][1] * inv_log2e);
@@ -191,6 +190,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_bwd_tc(AttnBwdTcArgs a) 
     unsigned char* G2t = QKVt + (size_t)TILE_M * Kp * 2;                     // [128 x Kp]  g * xhat
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t tmem_base_s;
+    __shared__ uint32_t coltab[272];                                         // compact column -> byte offset in a tile row
+    for (int c = threadIdx.x; c < 272; c += blockDim.x) coltab[c] = (uint32_t)(c >> 3) * tc5::TILE_CHUNK + (uint32_t)(c & 7) * 2u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float gs = tc_grad_scale(a.dout_amax), inv_gs = 1.0f / gs;
     float dx_max = 0.f;
@@ -331,7 +332,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_bwd_tc(AttnBwdTcArgs a) 
             }
             tc5::fence_before_sync();
             __syncthreads();
-            attn_bwd_core_bf16<DH>(QKVt, dOt, dQc, Ot, hc, nseq_t, S, a.scale, warp, NW, lane, cl);
+            attn_bwd_core_bf16<DH>(QKVt, dOt, dQc, Ot, hc, nseq_t, S, a.scale, warp, NW, lane, cl, coltab);
             tc5::fence_proxy_async();
             __syncthreads();
             if (threadIdx.x == 0) {

@@ -8,7 +8,7 @@ static int launch_attn_bwd_tc(const AttnBwdTcArgs& a, int grid, cudaStream_t st)
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(k_attn_bwd_tc<DH, KCH, VEC4, JW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             max_smem_optin() - 1024);
+                                             max_smem_optin() - 2048);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_attn_bwd_tc)");
         attr_set = true;
     }
