@@ -249,6 +249,13 @@ __device__ __forceinline__ CoreLane make_core_lane(int S, int lane) {
             const bool ok = rel(j) >= 0 && (!packed || ((i >> 3) == (j >> 3)));
             c.madd[nt][e] = ok ? 0.f : -INFINITY;
         }
+    // make the constants opaque: at the register cap the compiler otherwise REMATERIALISES this whole function inside
+    // every warp task (5 % of the attention-backward kernel's instructions) instead of keeping / spilling 12 values
+    asm volatile("" : "+r"(c.a_off), "+r"(c.b_off), "+r"(c.lo_rel), "+r"(c.hi_rel));
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) asm volatile("" : "+f"(c.madd[nt][e]));
     return c;
 }
 
