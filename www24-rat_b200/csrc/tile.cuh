@@ -265,7 +265,7 @@ struct SeqGeom {
     int T, N;
     __device__ __forceinline__ long long grow(long long s, int p) const {
         if (mode == 0) return s * S + p;
-        long long b = s / N;
+        const long long b = (s >> 31) == 0 ? (long long)((unsigned int)s / (unsigned int)N) : s / N;   // 32-bit divide when possible
         int n = (int)(s - b * N);
         return b * (long long)T * N + (long long)p * N + n;
     }
