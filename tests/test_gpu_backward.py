@@ -281,8 +281,10 @@ def test_bn_act_backward_matches_autograd(rn):
     rn.call("rat_bn_act_fwd", zd, mean, rstd, gamma.detach().cuda(), beta.detach().cuda(), outd, rows, C, 0.0, 0, 0, st)
     dz, dg, db = dout.cuda().clone(), torch.empty(C, device=d), torch.empty(C, device=d)
     rn.call("rat_bn_act_bwd_sums", dz, outd, zd, mean, rstd, rows, C, 0.0, 0, 0, sums, st)
+    am = torch.zeros(1, device=d)
     rn.call("rat_bn_act_bwd_apply", dz, outd, zd, mean, rstd, gamma.detach().cuda(), sums, float(rows), dz, dg, db,
-            rows, C, 0.0, 0, 0, st)
+            rows, C, 0.0, 0, 0, am, st)
+    assert float(am) == float(dz.abs().max())
     assert_close("bn dz", dz, z.grad, 1e-4, 1e-5)
     assert_close("bn dgamma", dg, gamma.grad, 1e-4, 1e-4)
     assert_close("bn dbeta", db, beta.grad, 1e-4, 1e-4)

@@ -222,22 +222,26 @@ __global__ void k_bn_act_bwd_apply(const float* __restrict__ dout, const float* 
                                    const float* __restrict__ rstd, const float* __restrict__ gamma,
                                    const double* __restrict__ sums, double count, float* __restrict__ dz,
                                    float* __restrict__ dgamma, float* __restrict__ dbeta, long long total, int C,
-                                   float drop_p, unsigned long long seed, unsigned int stream) {
+                                   float drop_p, unsigned long long seed, unsigned int stream,
+                                   float* __restrict__ dz_amax) {
     const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    float amax = 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % C);
         float dy = out[i] > 0.f ? dout[i] : 0.f;
         if (drop_p > 0.f) dy *= dropout_scale(seed, stream, (unsigned long long)i, drop_p, inv_keep);
+        float r = dy;
         if (mean) {
             const float xh = (z[i] - mean[c]) * rstd[c];
             const float db = (float)(sums[c] / count), dg = (float)(sums[C + c] / count);
-            dz[i] = gamma[c] * rstd[c] * (dy - db - xh * dg);
+            r = gamma[c] * rstd[c] * (dy - db - xh * dg);
             if (i < C) { dgamma[c] = (float)sums[C + c]; dbeta[c] = (float)sums[c]; }
-        } else {
-            dz[i] = dy;
         }
+        dz[i] = r;
+        amax = fmaxf(amax, fabsf(r));
     }
+    if (dz_amax != nullptr) publish_amax_block(dz_amax, amax);     // max|dz| for the fp16 GEMMs that consume dz
 }
 // out[c] = sum_r A[r][c]   (bias gradients), deterministic
 __global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ A, int R, int C, int lda,
@@ -511,11 +515,12 @@ extern "C" int rat_bn_act_bwd_sums(const float* dout, const float* out, const fl
 extern "C" int rat_bn_act_bwd_apply(const float* dout, const float* out, const float* z, const float* mean,
                                     const float* rstd, const float* gamma, const double* sums, double count,
                                     float* dz, float* dgamma, float* dbeta, int rows, int C, float drop_p,
-                                    unsigned long long seed, unsigned int rng_stream, void* stream) {
+                                    unsigned long long seed, unsigned int rng_stream, float* dz_amax,
+                                    void* stream) {
     const long long total = (long long)rows * C;
     k_bn_act_bwd_apply<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(dout, out, z, mean, rstd, gamma, sums, count,
                                                                          dz, dgamma, dbeta, total, C, drop_p, seed,
-                                                                         rng_stream);
+                                                                         rng_stream, dz_amax);
     RAT_CHECK_LAUNCH("k_bn_act_bwd_apply");
     return RAT_OK;
 }

@@ -750,22 +750,20 @@ class RatEngine:
             u = units[li]
             dh, out, z = ws["dh"][li], ws["h"][li], ws["z"][li]
             drop = float(s.net_dropout)
+            am = self._amax_new()       # max|dz| (published by bn_act_bwd_apply): the fp16 GEMMs lift dz by a power of two
             if bn is not None:
                 call("rat_bn_act_bwd_sums", dh, out, z, ws["bn_mean"][li], ws["bn_rstd"][li], B, u, drop, s.seed,
                      self._rng_stream(16 + li), ws["bn_sums"][li], st)
                 self._allreduce_sums(ws["bn_sums"][li])
                 call("rat_bn_act_bwd_apply", dh, out, z, ws["bn_mean"][li], ws["bn_rstd"][li], p[f"dnn.dnn.{bn}.weight"],
                      ws["bn_sums"][li], count, dh, g[f"dnn.dnn.{bn}.weight"], g[f"dnn.dnn.{bn}.bias"], B, u, drop,
-                     s.seed, self._rng_stream(16 + li), st)
+                     s.seed, self._rng_stream(16 + li), am, st)
             else:
                 call("rat_bn_act_bwd_apply", dh, out, z, None, None, None, None, count, dh, None, None, B, u, drop,
-                     s.seed, self._rng_stream(16 + li), st)
+                     s.seed, self._rng_stream(16 + li), am, st)
             h_prev = ws["h"][li - 1] if li > 0 else ws["x_emb"]
             Kin = units[li - 1] if li > 0 else s.F * s.embedding_dim
             d_prev = ws["dh"][li - 1] if li > 0 else ws["dxemb"]
-            am = self._amax_new()                    # max|dz|: the fp16 GEMMs lift dz by a power of two
-            if am is not None:
-                call("rat_absmax", dh, B, u, u, am, st)
             call("rat_sgemm_scaled", dh, h_prev, g[f"dnn.dnn.{lin}.weight"], None, u, Kin, B, u, Kin, Kin, 1, 1, am,
                  gw, gwb, st)
             call("rat_colsum", dh, B, u, u, g[f"dnn.dnn.{lin}.bias"], st)
