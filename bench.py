@@ -443,7 +443,9 @@ def run_reference(a):
     line = {"impl": "reference", "metric": "RAT_m2 train samples/sec", "value": v, "unit": "samples/s",
             "n_gpus": a.gpus, "steps": steps, "warmup": warmup, "ms_per_step": round(t / steps * 1e3, 2),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"RAT_m2 {cfg['dataset_id']} shape, K={K}, train step; bounded sample B={Bc} per step on CPU"},
+            "config": {"workload": f"RAT_m2 {cfg['dataset_id']} shape, K={K}, B={a.batch}/GPU, train step (fwd+bwd+clip+Adam)",
+                       "cpu_sample": f"each CPU step is a bounded sample of that workload: B={Bc} samples, retrieval-set assembly "
+                                     f"included; fp32 torch-CPU oracle port on all host threads"},
             "cpu_baseline": {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
                              "sample": f"{steps} oracle training steps at B={Bc} on {torch.get_num_threads()} host threads"},
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
