@@ -355,6 +355,11 @@ def run_ours(a):
         "dtype": {"fp16": "f16", "tf32": "tf32", "fp32": "f32"}[a.precision], "data": "synthetic",
         "config": {"workload": f"RAT_m2 {cfg['dataset_id']} shape, K={K}, B={B}/GPU, train step (fwd+bwd+clip+Adam)",
                    "precision": a.precision,
+                   "arithmetic": {"fp16": "tcgen05 / mma.sync fp16 operands (10-bit mantissa) with fp32 accumulation and dynamic "
+                                          "power-of-two gradient scaling; residual stream, LayerNorm, softmax statistics, GELU, "
+                                          "BatchNorm, loss and optimizer in fp32",
+                                  "tf32": "mma.sync TF32 operands, fp32 accumulation; everything else fp32",
+                                  "fp32": "fp32 SIMT"}[a.precision],
                    "global_batch": gB, "topK": K, "fields": F, "input_length": L, "embedding_dim": D, "heads": H,
                    "params": n_params, "pool_rows": a.pool_rows, "parallelism": f"dp{world}" + ("+row-sharded tables (NVLink peer loads, reduce-scatter)" if sharded else ""),
                    "vocab_scale": a.vocab_scale,
