@@ -41,6 +41,11 @@ static bool attn_bwd_tc_plan(int S, int D, int heads, int dh, AttnBwdTcArgs* a) 
     const int NP = a->Kp / 16;
     a->njobs = a->nchunks * ((a->NCc / 16 + a->Cc / 16) * NP) + 3 * NP;
     if ((a->njobs + 15) / 16 > 6) return false;
+    {   // TMEM: q|k|v + dO + dA accumulators + the parking columns of the weight-gradient accumulators (4 warps per
+        // lane quadrant x JW x 8; JW as instantiated: 3, 5 or 6)
+        const int jw = (a->njobs + 15) / 16, jwi = jw <= 3 ? 3 : jw <= 5 ? 5 : 6;
+        if (a->NCq + a->NDo + a->Kp + 4 * jwi * 8 > 512) return false;
+    }
     a->psize = a->nchunks * (a->NCc + a->Cc) * a->Kp + 3 * a->Kp;
     const size_t images = (size_t)a->nchunks * (a->NCq + a->NCc + a->NDo) * a->Kp * 2;
     const size_t tiles = (size_t)TILE_M * (2 * a->Kp + a->NCq + a->NCc + a->Cc + a->NDo) * 2;

@@ -263,6 +263,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_bwd_tc(AttnBwdTcArgs a) 
     const uint32_t idesc_a = tc5::instr_desc(TC_FMT, TILE_M, Kp);
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const int part = warp >> 2;                                      // 0..3: column share of this warp inside its lane quadrant
+    const uint32_t tmem_P = tmem_A + Kp + (uint32_t)(part * JW * 8); // parking columns of this warp's accumulators
     const int row_e = (warp & 3) * 32 + lane;
     uint32_t phase = 0;
     const CoreLane cl = make_core_lane(S, lane);
@@ -330,11 +331,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_bwd_tc(AttnBwdTcArgs a) 
                            pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
                 }
             }
+            // park the weight-gradient accumulators (8 JW registers per thread, dead during the core) in spare TMEM
+            // columns: the core is the register-hungry phase and the kernel sits at the 128-register cap
+#pragma unroll
+            for (int j = 0; j < JW; ++j) {
+                const float t8[8] = {acc[j][0][0], acc[j][0][1], acc[j][0][2], acc[j][0][3],
+                                     acc[j][1][0], acc[j][1][1], acc[j][1][2], acc[j][1][3]};
+                tc5::tmem_st8(tmem_P + lane_base + j * 8, t8);
+            }
+            tc5::tmem_st_wait();
             tc5::fence_before_sync();
             __syncthreads();
             attn_bwd_core_bf16<DH>(QKVt, dOt, dQc, Ot, hc, nseq_t, S, a.scale, warp, NW, lane, cl, coltab);
             tc5::fence_proxy_async();
             __syncthreads();
+#pragma unroll
+            for (int j = 0; j < JW; ++j) {
+                float t8[8];
+                tc5::tmem_ld8(tmem_P + lane_base + j * 8, t8);
+                tc5::tmem_ld_wait();
+                acc[j][0][0] = t8[0]; acc[j][0][1] = t8[1]; acc[j][0][2] = t8[2]; acc[j][0][3] = t8[3];
+                acc[j][1][0] = t8[4]; acc[j][1][1] = t8[5]; acc[j][1][2] = t8[6]; acc[j][1][3] = t8[7];
+            }
             if (threadIdx.x == 0) {
                 tc5::fence_after_sync();
                 const uint32_t wt = WqT_s + (uint32_t)ch * Kp * NCc * 2;
