@@ -182,6 +182,56 @@ def test_device_generator_sharding_logic_on_cpu():
     assert [b.row0 for b in bs][:3] == [0, 128, 256] and bs[-1].size == 1000 - 7 * 128
 
 
+@pytest.mark.parametrize("shape,count", [("ml", 1337241), ("kkbox", 4714649), ("tmall", 16970282)])
+def test_flat_parameter_layout_reproduces_the_reference_counts(shape, count):
+    """the product's flat parameter buffer (ParamStore, built on CPU here): same parameter count as the reference logs
+    (SURVEY 8c known answers), the reference's state_dict key set (query_proj included), 16-byte aligned net segments
+    and table regions, the per-field tables contiguous as emb_W / lr_W, and [net | embedding-named] split at
+    reg_boundary."""
+    sys.path.insert(0, os.path.join(ROOT, "www24-rat_b200"))
+    from rat_native import shapes
+    from rat_native.engine import EMB, LRP, EngineSpec, FeatureSpec, ParamStore
+    fm = shapes.make_feature_map(shape)
+    hp = shapes.SHAPES[shape]["hp"]
+    feats = [FeatureSpec(n, sp["type"], sp["vocab_size"], sp.get("max_len", 1), sp.get("padding_idx")) for n, sp in
+             fm.feature_specs.items()]
+    spec = EngineSpec(features=feats, model="RAT_m2", embedding_dim=hp["embedding_dim"], num_heads=hp["num_heads"],
+                      dim_head=10, scale_dim=hp["scale_dim"], depth=4, dnn_hidden_units=tuple(hp["dnn_hidden_units"]),
+                      batch_norm=hp["batch_norm"], use_wide=True, emb_dropout=hp["emb_dropout"],
+                      net_dropout=hp["net_dropout"])           # net_dropout shifts the nn.Sequential indices (deep.py:126-137)
+    st = ParamStore(spec, "cpu")
+    assert st.numel_params() == count
+    ospec = O.shape_spec(shape)
+    want = O.init_params(ospec, 0)
+    assert set(st.offsets) == set(want), set(st.offsets) ^ set(want)
+    for k, (off, shp) in st.offsets.items():
+        assert tuple(want[k].shape) == tuple(shp), k
+        if off < st.emb_off:                          # net parameters and the label table start on 16-byte boundaries
+            assert off % 4 == 0, k
+    assert st.emb_off % 4 == 0 and st.lr_off % 4 == 0 and st.net_end % 4 == 0
+    V, D = spec.V, spec.embedding_dim
+    assert st.emb_W.shape == (V, D) and st.lr_W.shape == (V,)
+    row = 0
+    for f in feats:                                   # field tables are consecutive row ranges of emb_W / lr_W
+        assert st.offsets[EMB + f.name + ".weight"][0] == st.emb_off + row * D
+        assert st.offsets[LRP + f.name + ".weight"][0] == st.lr_off + row
+        row += f.vocab_size
+    assert row == V == shapes.SHAPES[shape]["total_vocab"]
+    emb_named = [k for k in st.offsets if "embedding_layer" in k]
+    assert all(st.offsets[k][0] >= st.net_end for k in emb_named)
+    assert all(st.offsets[k][0] < st.net_end for k in st.offsets if k not in emb_named)
+
+
+def test_bench_algorithmic_bytes_match_the_survey():
+    """bench.py's gather bytes per sample = SURVEY 8(d)'s figures (1,810 / 30,282 / 4,350 B) + the X_emb write."""
+    sys.path.insert(0, ROOT)
+    import importlib
+    bench = importlib.import_module("bench")
+    for (K, L, F, D), survey in (((5, 3, 3, 10), 1810), ((5, 17, 13, 40), 30282), ((5, 8, 8, 10), 4350)):
+        assert bench.gather_bytes_per_sample(K, L, F, D) == survey + F * D * 4
+    assert bench.encoder_flops_per_sample(5, 13, 40, 8, 10, 2) == pytest.approx(23.7e6, rel=0.01)
+
+
 def _dp_worker(rank, world, port, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
