@@ -31,9 +31,10 @@ long long rat_launch_count(void);
 /* 0 if an sm_100 device is current, else RAT_ECUDA (the product path refuses to run anywhere else) */
 int rat_device_check(void);
 
-/* Arithmetic of the RAT-block projections: 2 = 5th-gen tensor cores (tcgen05.mma kind::f16, bf16 operands, fp32
- * accumulate in TMEM; residual stream / LayerNorm / softmax / GELU in fp32); 1 = mma.sync TF32 operands with fp32
- * accumulate (parity tolerance 3e-3 relative); 0 = exact fp32 on the SIMT pipe (parity anchor, ~1e-5). */
+/* Arithmetic of the RAT-block projections and DNN GEMMs: 2 (default) = 5th-gen tensor cores (tcgen05.mma kind::f16,
+ * fp16 operands, fp32 accumulate in TMEM, dynamic power-of-two gradient scaling; residual stream / LayerNorm /
+ * softmax / GELU / BatchNorm in fp32); 1 = mma.sync TF32 operands with fp32 accumulate (parity tolerance 3e-3
+ * relative); 0 = exact fp32 on the SIMT pipe (parity anchor, ~1e-5). */
 int rat_set_precision(int mode);
 int rat_get_precision(void);
 
