@@ -143,11 +143,13 @@ int rat_bn_act_fwd(const float* z, const float* mean, const float* rstd, const f
 int rat_bn_act_bwd_sums(const float* dout, const float* out, const float* z, const float* mean, const float* rstd,
                         int rows, int C, float drop_p, unsigned long long seed, unsigned int rng_stream, double* sums,
                         void* stream);
-/* dz_amax (device float, caller-zeroed, may be NULL): receives max|dz| (see rat_sgemm_scaled) */
+/* dz_amax (device float, caller-zeroed, may be NULL): receives max|dz| (see rat_sgemm_scaled).
+ * param_grad_scale multiplies the emitted dgamma / dbeta: `sums` are GLOBAL sums in data-parallel training (all-reduced
+ * by the caller), so each rank writes 1/world of them and the later SUM all-reduce of the gradient restores them. */
 int rat_bn_act_bwd_apply(const float* dout, const float* out, const float* z, const float* mean, const float* rstd,
                          const float* gamma, const double* sums, double count, float* dz, float* dgamma,
                          float* dbeta, int rows, int C, float drop_p, unsigned long long seed,
-                         unsigned int rng_stream, float* dz_amax, void* stream);
+                         unsigned int rng_stream, float* dz_amax, float param_grad_scale, void* stream);
 int rat_colsum(const float* A, int rows, int C, int lda, float* out, void* stream);
 /* logit = fc(enc[b,0,0,:]) + dnn_out[b] + lr_out[b]; y_pred = sigmoid; BCE(mean, log clamp -100) and, when dlogit
  * is non-NULL, dlogit[b] = dBCE/dlogit * inv_count and denc[b,0,0,:] = dlogit[b]*fc_w (denc pre-zeroed by the

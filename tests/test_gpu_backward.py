@@ -283,7 +283,7 @@ def test_bn_act_backward_matches_autograd(rn):
     rn.call("rat_bn_act_bwd_sums", dz, outd, zd, mean, rstd, rows, C, 0.0, 0, 0, sums, st)
     am = torch.zeros(1, device=d)
     rn.call("rat_bn_act_bwd_apply", dz, outd, zd, mean, rstd, gamma.detach().cuda(), sums, float(rows), dz, dg, db,
-            rows, C, 0.0, 0, 0, am, st)
+            rows, C, 0.0, 0, 0, am, 1.0, st)
     assert float(am) == float(dz.abs().max())
     assert_close("bn dz", dz, z.grad, 1e-4, 1e-5)
     assert_close("bn dgamma", dg, gamma.grad, 1e-4, 1e-4)

@@ -17,6 +17,7 @@
 // reshape/transpose/flatten copies (RAT_m2.py:221-235) are pure indexing here.
 #include "tile.cuh"
 #include "encoder_common.cuh"
+#include <cstdlib>
 #include "attn_mma.cuh"
 #include "../../include/rat_b200.h"
 
@@ -234,6 +235,17 @@ int attn_fwd_tc_dispatch(const float* x, const float* res, float* out, const flo
                          const float* Wq, const float* Wk, const float* Wv, const float* Wo, const float* bo, int B, int T,
                          int N, int D, int heads, int dh, float scale, float alpha, int mode, cudaStream_t st);
 
+int attn_fwd_tc2_dispatch(const float* x, const float* res, float* out, const float* ln_w, const float* ln_b,
+                          const float* Wq, const float* Wk, const float* Wv, const float* Wo, const float* bo, int B, int T,
+                          int N, int D, int heads, int dh, float scale, float alpha, int mode, cudaStream_t st);
+
+// RAT_TC2=0 in the environment keeps the first-generation tcgen05 attention kernels (A/B measurements)
+bool tc2_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("RAT_TC2"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on == 1;
+}
+
 extern "C" int rat_set_precision(int mode) {
     RAT_REQUIRE(mode >= 0 && mode <= 2, "rat_set_precision: mode must be 0 (fp32), 1 (tf32) or 2 (fp16 tcgen05)");
     g_precision = mode;
@@ -269,6 +281,11 @@ extern "C" int rat_attn_fwd(const float* x, const float* res, float* out, const 
     RAT_REQUIRE(mode == 0 || mode == 1, "rat_attn_fwd: mode must be 0 (intra) or 1 (cross)");
     RAT_REQUIRE(Wo != nullptr && bo != nullptr, "rat_attn_fwd: identity out-projection (heads==1 && dim_head==dim) is not supported");
     if (g_precision == 2) {
+        if (tc2_enabled()) {
+            const int rc3 = attn_fwd_tc2_dispatch(x, res, out, ln_w, ln_b, Wq, Wk, Wv, Wo, bo, B, T, N, D, heads, dim_head,
+                                                  scale, alpha, mode, (cudaStream_t)stream);
+            if (rc3 <= 0) return rc3;
+        }
         const int rc2 = attn_fwd_tc_dispatch(x, res, out, ln_w, ln_b, Wq, Wk, Wv, Wo, bo, B, T, N, D, heads, dim_head, scale,
                                              alpha, mode, (cudaStream_t)stream);
         if (rc2 <= 0) return rc2;

@@ -223,7 +223,7 @@ __global__ void k_bn_act_bwd_apply(const float* __restrict__ dout, const float* 
                                    const double* __restrict__ sums, double count, float* __restrict__ dz,
                                    float* __restrict__ dgamma, float* __restrict__ dbeta, long long total, int C,
                                    float drop_p, unsigned long long seed, unsigned int stream,
-                                   float* __restrict__ dz_amax) {
+                                   float* __restrict__ dz_amax, float param_grad_scale) {
     const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
     float amax = 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -236,7 +236,7 @@ __global__ void k_bn_act_bwd_apply(const float* __restrict__ dout, const float* 
             const float xh = (z[i] - mean[c]) * rstd[c];
             const float db = (float)(sums[c] / count), dg = (float)(sums[C + c] / count);
             r = gamma[c] * rstd[c] * (dy - db - xh * dg);
-            if (i < C) { dgamma[c] = (float)sums[C + c]; dbeta[c] = (float)sums[c]; }
+            if (i < C) { dgamma[c] = (float)sums[C + c] * param_grad_scale; dbeta[c] = (float)sums[c] * param_grad_scale; }
         }
         dz[i] = r;
         amax = fmaxf(amax, fabsf(r));
@@ -516,11 +516,11 @@ extern "C" int rat_bn_act_bwd_apply(const float* dout, const float* out, const f
                                     const float* rstd, const float* gamma, const double* sums, double count,
                                     float* dz, float* dgamma, float* dbeta, int rows, int C, float drop_p,
                                     unsigned long long seed, unsigned int rng_stream, float* dz_amax,
-                                    void* stream) {
+                                    float param_grad_scale, void* stream) {
     const long long total = (long long)rows * C;
     k_bn_act_bwd_apply<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(dout, out, z, mean, rstd, gamma, sums, count,
                                                                          dz, dgamma, dbeta, total, C, drop_p, seed,
-                                                                         rng_stream, dz_amax);
+                                                                         rng_stream, dz_amax, param_grad_scale);
     RAT_CHECK_LAUNCH("k_bn_act_bwd_apply");
     return RAT_OK;
 }

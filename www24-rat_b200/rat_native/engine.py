@@ -757,10 +757,10 @@ class RatEngine:
                 self._allreduce_sums(ws["bn_sums"][li])
                 call("rat_bn_act_bwd_apply", dh, out, z, ws["bn_mean"][li], ws["bn_rstd"][li], p[f"dnn.dnn.{bn}.weight"],
                      ws["bn_sums"][li], count, dh, g[f"dnn.dnn.{bn}.weight"], g[f"dnn.dnn.{bn}.bias"], B, u, drop,
-                     s.seed, self._rng_stream(16 + li), am, st)
+                     s.seed, self._rng_stream(16 + li), am, 1.0 / self.world, st)
             else:
                 call("rat_bn_act_bwd_apply", dh, out, z, None, None, None, None, count, dh, None, None, B, u, drop,
-                     s.seed, self._rng_stream(16 + li), am, st)
+                     s.seed, self._rng_stream(16 + li), am, 1.0, st)
             h_prev = ws["h"][li - 1] if li > 0 else ws["x_emb"]
             Kin = units[li - 1] if li > 0 else s.F * s.embedding_dim
             d_prev = ws["dh"][li - 1] if li > 0 else ws["dxemb"]
