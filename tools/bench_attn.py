@@ -39,11 +39,11 @@ for mode in (0, 1):
         rn.call("rat_attn_bwd", xs[i % nbuf], douts[i % nbuf], douts[i % nbuf], outs[i % nbuf], lnw, lnb, wqkv[:I], wqkv[I:2 * I],
                 wqkv[2 * I:], wo, gq, gk, gv, gwo, gbo, glw, glb, 0, B, T, N, D, H, dh, dh ** -0.5, 1.0, mode, amax_in, amax_out,
                 bw, bw.numel() * 4, st)
-    for name, fn, passes in (("fwd", fwd, 2), ("bwd", bwd, 3)):
-        for i in range(6): fn(i)
+    for name, fn, passes in ((("fwd", fwd, 2),) if os.environ.get("ONLY_FWD") else (("fwd", fwd, 2), ("bwd", bwd, 3))):
+        for i in range(int(os.environ.get("WARM", "6"))): fn(i)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        iters = 40
+        iters = int(os.environ.get("ITERS", "40"))
         e0.record()
         for i in range(iters): fn(i)
         e1.record(); torch.cuda.synchronize()

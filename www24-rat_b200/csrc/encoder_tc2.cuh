@@ -24,6 +24,9 @@ namespace rat {
 constexpr int T2_THREADS = 512;
 constexpr int T2_HALF_BYTES = 64 * 64 * 2;          // one block-diagonal [64 x 64] fp16 tile
 
+// warp index as a value ptxas can prove warp-uniform (descriptor math then stays in uniform registers)
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 __device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
 
 __device__ __forceinline__ void tmem_ld16u(uint32_t taddr, float (&v)[16]) { tc5::tmem_ld16(taddr, v); }
@@ -38,63 +41,80 @@ __device__ __forceinline__ float slot_pick(const float (&v)[16], int sb, int j) 
     return sb ? v[8 + j] : v[j];
 }
 
-// Stage the rows [32*grp, 32*grp + 32) of a tile: 4 threads per row, LayerNorm (optional affine) in fp32, fp16 store
-// into the chunk-major K-major tile.  gt = thread index inside the group (0..127).  Pad columns [D, Kp) are never
-// written (zero-initialised once); invalid rows are written as zeros.  stats (nullable): [128][2] mean, rstd.
+// Staging of a tile's token rows, 4 threads per row (group grp stages rows [32*grp, 32*grp + 32)), split in two so that
+// the global loads of the NEXT tile can be in flight under the head loop of the current one:
+//   t2_rows_load   : the row's 16-/8-byte units part, part+4, .. -> registers
+//   t2_rows_finish : LayerNorm WITHOUT the affine part (gamma is folded into the weight image, beta rides on a column of
+//                    ones at column D), fp16, chunk-major K-major tile.  Pad columns (> D) are never written
+//                    (zero-initialised once); invalid rows are written as zeros.  stats (nullable): [128][2] mean, rstd.
+template <bool VEC4>
+struct XRegs { float v[4][VEC4 ? 4 : 2]; bool valid; };
+
 template <bool VEC4, int SLSH>
-__device__ __forceinline__ void t2_stage_rows(const float* __restrict__ x, const SeqGeom& g, long long s0, long long nseq,
-                                              int D, const float* __restrict__ lnw_s, const float* __restrict__ lnb_s,
-                                              unsigned char* __restrict__ Xt, int grp, int gt, float* __restrict__ stats) {
+__device__ __forceinline__ void t2_rows_load(const float* __restrict__ x, const SeqGeom& g, long long s0, long long nseq,
+                                             int D, int grp, int gt, XRegs<VEC4>& r) {
     constexpr int U = VEC4 ? 4 : 2;
     const int row = 32 * grp + (gt >> 2), part = gt & 3;
     const int slot = row >> SLSH, pos = row & ((1 << SLSH) - 1);
     const long long seq = s0 + slot;
-    const bool valid = pos < g.S && seq < nseq;
+    r.valid = pos < g.S && seq < nseq;
     const int nun = D / U;
-    const float* src = x + (valid ? g.grow(seq, pos) : 0) * D;
-    float v[4][U];
-    float s = 0.f;
+    const float* src = x + (r.valid ? g.grow(seq, pos) : 0) * D;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int u = part + 4 * k;
 #pragma unroll
-        for (int e = 0; e < U; ++e) v[k][e] = 0.f;
-        if (valid && u < nun) {
-            if constexpr (VEC4) { const float4 t = *reinterpret_cast<const float4*>(src + u * 4); v[k][0] = t.x; v[k][1] = t.y; v[k][2] = t.z; v[k][3] = t.w; }
-            else { const float2 t = *reinterpret_cast<const float2*>(src + u * 2); v[k][0] = t.x; v[k][1] = t.y; }
+        for (int e = 0; e < U; ++e) r.v[k][e] = 0.f;
+        if (r.valid && u < nun) {
+            if constexpr (VEC4) { const float4 t = *reinterpret_cast<const float4*>(src + u * 4); r.v[k][0] = t.x; r.v[k][1] = t.y; r.v[k][2] = t.z; r.v[k][3] = t.w; }
+            else { const float2 t = *reinterpret_cast<const float2*>(src + u * 2); r.v[k][0] = t.x; r.v[k][1] = t.y; }
         }
-#pragma unroll
-        for (int e = 0; e < U; ++e) s += v[k][e];
     }
+}
+
+template <bool VEC4>
+__device__ __forceinline__ void t2_rows_finish(const XRegs<VEC4>& r, int D, unsigned char* __restrict__ Xt, int grp, int gt,
+                                               float* __restrict__ stats) {
+    constexpr int U = VEC4 ? 4 : 2;
+    const int row = 32 * grp + (gt >> 2), part = gt & 3;
+    const int nun = D / U;
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int e = 0; e < U; ++e) s += r.v[k][e];                  // units beyond the row hold zeros
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
-    const float mean = s / (float)D;
+    const float invD = 1.0f / (float)D;
+    const float mean = s * invD;
     float sq = 0.f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const int u = part + 4 * k;
-        if (u < nun) {
+        if (part + 4 * k < nun) {
 #pragma unroll
-            for (int e = 0; e < U; ++e) { const float t = v[k][e] - mean; sq = fmaf(t, t, sq); }
+            for (int e = 0; e < U; ++e) { const float t = r.v[k][e] - mean; sq = fmaf(t, t, sq); }
         }
     }
     sq += __shfl_xor_sync(0xffffffffu, sq, 1);
     sq += __shfl_xor_sync(0xffffffffu, sq, 2);
-    const float rstd = 1.0f / sqrtf(sq / (float)D + 1e-5f);
+    const float rstd = r.valid ? rsqrtf(fmaf(sq, invD, 1e-5f)) : 0.f;
+    const float nm = -mean * rstd;
     if (stats != nullptr && part == 0) { stats[2 * row] = mean; stats[2 * row + 1] = rstd; }
+    unsigned char* dst = Xt + (size_t)row * 16 + (VEC4 ? (part & 1) * 8 : (part & 3) * 4);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int u = part + 4 * k;
         if (u < nun) {
-            const int c = u * U;
-            float y[U];
-#pragma unroll
-            for (int e = 0; e < U; ++e) y[e] = valid ? (v[k][e] - mean) * rstd * lnw_s[c + e] + lnb_s[c + e] : 0.f;
-            unsigned char* dst = Xt + tc5::toff(row, c >> 3) + (c & 7) * 2;
-            if constexpr (VEC4) *reinterpret_cast<uint2*>(dst) = make_uint2(pack_h2(y[0], y[1]), pack_h2(y[2], y[3]));
-            else *reinterpret_cast<uint32_t*>(dst) = pack_h2(y[0], y[1]);
+            // VEC4: unit u = columns [4u, 4u+4) = half (u & 1) of chunk u >> 1 ; else unit u = quarter (u & 3) of chunk u >> 2
+            unsigned char* d2 = dst + (VEC4 ? (u >> 1) : (u >> 2)) * tc5::TILE_CHUNK;
+            if constexpr (VEC4)
+                *reinterpret_cast<uint2*>(d2) = make_uint2(pack_h2(fmaf(r.v[k][0], rstd, nm), fmaf(r.v[k][1], rstd, nm)),
+                                                           pack_h2(fmaf(r.v[k][2], rstd, nm), fmaf(r.v[k][3], rstd, nm)));
+            else *reinterpret_cast<uint32_t*>(d2) = pack_h2(fmaf(r.v[k][0], rstd, nm), fmaf(r.v[k][1], rstd, nm));
         }
     }
+    if (part == (nun & 3))                                           // the column of ones (beta / bias row of the weight image)
+        *reinterpret_cast<unsigned short*>(Xt + tc5::toff(row, D >> 3) + (D & 7) * 2) = r.valid ? (unsigned short)(TC_ONES2 & 0xffffu) : (unsigned short)0;
 }
 
 }  // namespace rat

@@ -30,28 +30,70 @@ struct AttnTc2Args {
     int o_alias;                // the o tile aliases the q region (single chunk)
     int smem_bytes;
     int off_wqkv, off_wo, off_f32, off_x, off_q, off_k, off_v, off_o, off_p;
-    long long* dbg;             // RAT_T2_DBG=1: per-phase clock totals of CTA 0 (16 slots per group)
+    long long* dbg;             // RAT_T2_DBG=1: per-phase clock totals of CTA 0
 };
 
-template <int DHP, int SL, int ST, bool VEC4>
+// weight images shared by the forward and backward kernels (all threads of the CTA):
+//   Wqkv image of chunk ch: rows n = [group][u][q|k|v][DHP] (head hl = group + 4u), K-major, Kp columns:
+//       [n][c] = mul * W[n][c] * gamma[c]  (c < D),   [n][D] = mul * sum_c W[n][c] beta[c]   (the LayerNorm affine, folded)
+__device__ __forceinline__ void t2_stage_wqkv(const float* __restrict__ Wq, const float* __restrict__ Wk,
+                                              const float* __restrict__ Wv, const float* __restrict__ ln_w,
+                                              const float* __restrict__ ln_b, float qscale, int D, int dh, int hc, int nchunks,
+                                              int NG, int Kp, unsigned char* __restrict__ img) {
+    constexpr int DHP = 16;
+    const int RI = 4 * NG, KC1 = Kp >> 3;
+    for (int i = threadIdx.x; i < nchunks * RI * KC1; i += blockDim.x) {
+        const int n = i % RI, rest = i / RI, kc = rest % KC1, ch = rest / KC1;
+        const int gr = n / NG, rem = n - gr * NG;
+        const int u = rem / (3 * DHP), rem2 = rem - u * 3 * DHP;
+        const int w = rem2 / DHP, dd = rem2 - w * DHP;
+        const int hl = gr + 4 * u;
+        const bool live = hl < hc && dd < dh;
+        const float* W = (w == 0 ? Wq : w == 1 ? Wk : Wv) + (size_t)((ch * hc + hl) * dh + dd) * D;
+        const float mul = w == 0 ? qscale : 1.0f;
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = kc * 8 + k;
+            v[k] = 0.f;
+            if (live && c < D) v[k] = mul * __ldg(W + c) * (ln_w ? __ldg(ln_w + c) : 1.0f);
+            else if (live && c == D && ln_b) {
+                float acc = 0.f;
+                for (int c2 = 0; c2 < D; ++c2) acc = fmaf(__ldg(W + c2), __ldg(ln_b + c2), acc);
+                v[k] = mul * acc;
+            }
+        }
+        sts128(img + (size_t)ch * RI * Kp * 2 + tc5::kmajor_off(n, kc, RI), pack_h2(v[0], v[1]), pack_h2(v[2], v[3]),
+               pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+    }
+}
+
+#define T2_S_MMA(hl_)                                                                                              \
+    do {                                                                                                           \
+        _Pragma("unroll") for (int h2 = 0; h2 < 2; ++h2) {                                                          \
+            const uint32_t o_ = (uint32_t)((((hl_) * DC) * 128 + 64 * h2) * 16);                                   \
+            tc5::mma_f16_w(t_S + ((uint32_t)(16 * h2) << 16), tc5::smem_desc(Qs + o_, tc5::TILE_CHUNK, 128u),       \
+                           tc5::smem_desc(Ks + o_, tc5::TILE_CHUNK, 128u), idesc_s, 0u);                           \
+        }                                                                                                          \
+        tc5::mma_commit_w(&bar_s[grp]);                                                                            \
+    } while (0)
+
+template <int HPG, int SL, int ST, bool VEC4>
 __global__ void __launch_bounds__(T2_THREADS, 1) k_attn_fwd_tc2(AttnTc2Args a) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar_x, bar_q[4], bar_s[4], bar_o[4], bar_og, bar_y;
     __shared__ uint32_t tmem_base_s;
+    constexpr int DHP = 16, DC = DHP / 8;             // padded head width, 16-byte chunks per head
     constexpr int SLSH = SL == 16 ? 4 : 3;
-    constexpr int DC = DHP / 8;                       // 16-byte chunks per head
     constexpr int NV = ST > 0 ? ST : SL;              // keys visited by the softmax loops
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int NG = HPG * 3 * DHP, RI = 4 * NG;    // q|k|v accumulator columns of one group, rows of a chunk's weight image
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const int grp = warp >> 2, q = warp & 3, gt = threadIdx.x & 127;
-    const bool elected = gt == 0;
-    const int D = a.D, Kp = a.Kp, Np = a.Np, hc = a.hc, NG = a.NG, KO = a.KO, S = a.g.S;
-    const int RI = 4 * NG;                            // rows of one chunk's q|k|v weight image
+    const int D = a.D, Kp = a.Kp, Np = a.Np, hc = a.hc, KO = a.KO, S = a.g.S;
     unsigned char* Wqkv_i = smem + a.off_wqkv;        // [nchunks][RI x Kp]
     unsigned char* Wo_i = smem + a.off_wo;            // [nchunks][Np x KO]
     float* bos = reinterpret_cast<float*>(smem + a.off_f32);     // [Np]
-    float* lnw_s = bos + Np;                          // [Kp]
-    float* lnb_s = lnw_s + Kp;                        // [Kp]
-    unsigned char* Xt = smem + a.off_x;               // [128 x Kp]      LN(x)
+    unsigned char* Xt = smem + a.off_x;               // [128 x Kp]      normalised x | 1
     unsigned char* Qt = smem + a.off_q;               // [128 x hc*DHP]  q (scaled)
     unsigned char* Kt = smem + a.off_k;
     unsigned char* Vt = smem + a.off_v;
@@ -60,25 +102,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) k_attn_fwd_tc2(AttnTc2Args a) {
     const int nh = hc > grp ? (hc - grp + 3) / 4 : 0; // heads of this group in a chunk: hl = grp + 4u
 
     // ---- resident weight images, zero-initialised activation tiles
+    t2_stage_wqkv(a.Wq, a.Wk, a.Wv, a.ln_w, a.ln_b, a.qscale, D, a.dh, hc, a.nchunks, NG, Kp, Wqkv_i);
     {
-        const int KC1 = Kp >> 3;
-        for (int i = threadIdx.x; i < a.nchunks * RI * KC1; i += blockDim.x) {
-            const int n = i % RI, rest = i / RI, kc = rest % KC1, ch = rest / KC1;
-            const int gr = n / NG, rem = n - gr * NG;
-            const int u = rem / (3 * DHP), rem2 = rem - u * 3 * DHP;
-            const int w = rem2 / DHP, dd = rem2 - w * DHP;
-            const int hl = gr + 4 * u;
-            const float* W = w == 0 ? a.Wq : w == 1 ? a.Wk : a.Wv;
-            const float mul = w == 0 ? a.qscale : 1.0f;
-            float v[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int c = kc * 8 + k;
-                v[k] = (hl < hc && dd < a.dh && c < D) ? mul * __ldg(W + (size_t)((ch * hc + hl) * a.dh + dd) * D + c) : 0.f;
-            }
-            sts128(Wqkv_i + (size_t)ch * RI * Kp * 2 + tc5::kmajor_off(n, kc, RI), pack_h2(v[0], v[1]), pack_h2(v[2], v[3]),
-                   pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-        }
         const int KCo = KO >> 3;
         for (int i = threadIdx.x; i < a.nchunks * Np * KCo; i += blockDim.x) {
             const int n = i % Np, rest = i / Np, kc = rest % KCo, ch = rest / KCo;
@@ -92,10 +117,6 @@ __global__ void __launch_bounds__(T2_THREADS, 1) k_attn_fwd_tc2(AttnTc2Args a) {
                    pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
         }
         for (int i = threadIdx.x; i < Np; i += blockDim.x) bos[i] = i < D ? a.bo[i] : 0.f;
-        for (int i = threadIdx.x; i < Kp; i += blockDim.x) {
-            lnw_s[i] = i < D ? a.ln_w[i] : 0.f;
-            lnb_s[i] = i < D ? a.ln_b[i] : 0.f;
-        }
         // x tile (pad columns stay zero) ... P tiles (off-diagonal blocks stay zero): everything from off_x on
         for (int i = threadIdx.x; i < (a.smem_bytes - a.off_x) / 16; i += blockDim.x)
             reinterpret_cast<uint4*>(smem + a.off_x)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -105,7 +126,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) k_attn_fwd_tc2(AttnTc2Args a) {
         for (int i = 0; i < 4; ++i) { tc5::mbar_init(&bar_q[i], 1); tc5::mbar_init(&bar_s[i], 1); tc5::mbar_init(&bar_o[i], 1); }
         tc5::fence_mbar_init();
     }
-    if (threadIdx.x < 32) tc5::tmem_alloc(&tmem_base_s, 512);
+    if (warp == 0) tc5::tmem_alloc(&tmem_base_s, 512);
     tc5::fence_proxy_async();
     tc5::fence_before_sync();
     __syncthreads();
@@ -125,81 +146,108 @@ __global__ void __launch_bounds__(T2_THREADS, 1) k_attn_fwd_tc2(AttnTc2Args a) {
     const int hf = lane >> 4, li = lane & 15;
     const int row_s = 64 * hf + 16 * q + li;
     const int sb = (li >> 3) & 1;                                       // sub-slot inside the row group (SL == 8)
+    unsigned char* const p_row = Pg + hf * T2_HALF_BYTES + poff(16 * q + li, 2 * q + (SL == 8 ? sb : 0));
     uint32_t ph_x = 0, ph_q = 0, ph_s = 0, ph_o = 0, ph_og = 0, ph_y = 0;
-    long long tk[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) tk[i] = 0;
+    const int nck = (D + 7) >> 3;
+    __shared__ long long tks[8][16];
+    if (threadIdx.x < 128) tks[threadIdx.x >> 4][threadIdx.x & 15] = 0;
+    const bool prof = a.dbg != nullptr && (gt == 0 || gt == 127);
     long long t_prev = clock64();
-#define T2_TICK(i) do { if (a.dbg) { const long long t_now = clock64(); tk[i] += t_now - t_prev; t_prev = t_now; } } while (0)
+#define T2_TICK(i) do { if (prof) { const long long t_now = clock64(); tks[grp * 2 + (gt ? 1 : 0)][i] += t_now - t_prev; t_prev = t_now; } } while (0)
 
     const long long ntiles = (a.nseq + a.SPT - 1) / a.SPT;
+    XRegs<VEC4> xr;
     if ((long long)blockIdx.x < ntiles) {
-        t2_stage_rows<VEC4, SLSH>(a.x, a.g, (long long)blockIdx.x * a.SPT, a.nseq, D, lnw_s, lnb_s, Xt, grp, gt, nullptr);
+        t2_rows_load<VEC4, SLSH>(a.x, a.g, (long long)blockIdx.x * a.SPT, a.nseq, D, grp, gt, xr);
+        t2_rows_finish<VEC4>(xr, D, Xt, grp, gt, nullptr);
         tc5::fence_proxy_async();
         group_sync(grp);
-        if (elected) tc5::mbar_arrive(&bar_x);
+        if (q == 0) tc5::mbar_arrive_w(&bar_x);
     }
+    // epilogue of the PREVIOUS tile (runs under the q|k|v MMA of the current one): out = res + alpha * (y + bo)
+    long long gr_prev = -1;                          // global row of accumulator row row_e in the previous tile (-1: none)
     int it = 0;
-    T2_TICK(0);                                       // prologue
+    auto y_epilogue = [&](int it_prev) {
+        tc5::mbar_wait_sleep(&bar_y, ph_y);
+        ph_y ^= 1;
+        tc5::fence_after_sync();
+        for (int c = (grp + 4 - (it_prev & 3)) & 3; c < nck; c += 4) {
+            float v[8], rv[8];
+            tc5::tmem_ld8(t_Y + lane_base + c * 8, v);
+            if (gr_prev >= 0 && a.res) load8<VEC4>(a.res + gr_prev * D, c * 8, D, rv);
+            tc5::tmem_ld_wait();
+            if (gr_prev >= 0) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    v[k] = a.alpha * (v[k] + bos[c * 8 + k]);
+                    if (a.res) v[k] += rv[k];
+                }
+                store8<VEC4>(a.out + gr_prev * D, c * 8, D, v);
+            }
+        }
+        tc5::fence_before_sync();
+    };
+    bool y_pending = false;                           // an out-projection whose completion has not been waited for yet
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const long long s0 = tile * a.SPT;
-        bool y_pending = false;                       // an out-projection whose completion has not been waited for yet
+        const bool has_next = tile + gridDim.x < ntiles;
         for (int ch = 0; ch < a.nchunks; ++ch) {
             // ---- q|k|v of this group's heads
-            if (nh > 0) {
-                if (elected) {
-                    if (ch == 0) tc5::mbar_wait(&bar_x, ph_x);
-                    tc5::fence_after_sync();
-                    const uint32_t wq = Wqs + (uint32_t)ch * RI * Kp * 2;
-                    for (int k = 0; k < Kp / 16; ++k)
-                        tc5::mma_f16(t_reg, tc5::kdesc(Xs, 128, k),
-                                     tc5::smem_desc(wq + (uint32_t)((k * 2 * RI + grp * NG) * 16), (uint32_t)RI * 16, 128u), idesc_q, k > 0);
-                    tc5::mma_commit(&bar_q[grp]);
-                }
-                tc5::mbar_wait(&bar_q[grp], ph_q);
+            if (nh > 0 && q == 0) {
+                if (ch == 0) tc5::mbar_wait_sleep(&bar_x, ph_x);
                 tc5::fence_after_sync();
-                T2_TICK(1);                           // wait: x staged by all groups + q|k|v MMA
-                if (a.o_alias && y_pending) { tc5::mbar_wait(&bar_y, ph_y); ph_y ^= 1; y_pending = false; }
+                const uint32_t wq = Wqs + (uint32_t)ch * RI * Kp * 2 + (uint32_t)(grp * NG * 16);
+                for (int k = 0; k < Kp / 16; ++k)
+                    tc5::mma_f16_w(t_reg, tc5::kdesc(Xs, 128, k), tc5::smem_desc(wq + (uint32_t)(k * 2 * RI * 16), (uint32_t)RI * 16, 128u),
+                                   idesc_q, k > 0);
+                tc5::mma_commit_w(&bar_q[grp]);
+            }
+            T2_TICK(0);
+            if (ch == 0 && y_pending) { y_epilogue(it - 1); y_pending = false; }
+            T2_TICK(1);
+            if (nh > 0) {
+                tc5::mbar_wait_sleep(&bar_q[grp], ph_q);
+                tc5::fence_after_sync();
+                T2_TICK(2);
+                if (a.o_alias && y_pending) { tc5::mbar_wait_sleep(&bar_y, ph_y); ph_y ^= 1; y_pending = false; }
                 // accumulator -> fp16 q | k | v tiles (thread = row row_e)
-                for (int b = 0; b < NG / 16; ++b) {
-                    float v[16];
-                    tc5::tmem_ld16(t_reg + lane_base + b * 16, v);
+#pragma unroll
+                for (int u = 0; u < HPG; ++u) {
+                    float v[3][16];
+#pragma unroll
+                    for (int w = 0; w < 3; ++w) tc5::tmem_ld16(t_reg + lane_base + (u * 3 + w) * 16, v[w]);
                     tc5::tmem_ld_wait();
-                    const int per_head = 3 * DHP / 16, u = b / per_head, r2 = b - u * per_head;
-                    const int w = r2 / (DHP / 16), sub = r2 - w * (DHP / 16);
-                    const int hl = grp + 4 * u;
-                    unsigned char* dst = (w == 0 ? Qt : w == 1 ? Kt : Vt) + tc5::toff(row_e, hl * DC + 2 * sub);
-                    sts128(dst, pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-                    sts128(dst + tc5::TILE_CHUNK, pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+                    const uint32_t ro = tc5::toff(row_e, (grp + 4 * u) * DC);
+#pragma unroll
+                    for (int w = 0; w < 3; ++w) {
+                        unsigned char* dst = (w == 0 ? Qt : w == 1 ? Kt : Vt) + ro;
+                        sts128(dst, pack_h2(v[w][0], v[w][1]), pack_h2(v[w][2], v[w][3]), pack_h2(v[w][4], v[w][5]), pack_h2(v[w][6], v[w][7]));
+                        sts128(dst + tc5::TILE_CHUNK, pack_h2(v[w][8], v[w][9]), pack_h2(v[w][10], v[w][11]), pack_h2(v[w][12], v[w][13]),
+                               pack_h2(v[w][14], v[w][15]));
+                    }
                 }
                 tc5::fence_proxy_async();
                 tc5::fence_before_sync();
                 group_sync(grp);
-                T2_TICK(2);                           // q|k|v evacuation
-                if (elected) {                        // scores of the first head
+                T2_TICK(3);
+                if (q == 0) {                         // scores of the first head
                     tc5::fence_after_sync();
-                    const int hl = grp;
-#pragma unroll
-                    for (int h2 = 0; h2 < 2; ++h2)
-#pragma unroll
-                        for (int ks = 0; ks < DHP / 16; ++ks) {
-                            const uint32_t o = (uint32_t)(((hl * DC + 2 * ks) * 128 + 64 * h2) * 16);
-                            tc5::mma_f16(t_S + ((uint32_t)(16 * h2) << 16), tc5::smem_desc(Qs + o, tc5::TILE_CHUNK, 128u),
-                                         tc5::smem_desc(Ks + o, tc5::TILE_CHUNK, 128u), idesc_s, ks > 0);
-                        }
-                    tc5::mma_commit(&bar_s[grp]);
+                    T2_S_MMA(grp);
                 }
             }
             ph_q ^= 1;
+            // ---- the next tile's rows start their trip from HBM now and are consumed after the head loop
+            if (ch == a.nchunks - 1 && has_next) t2_rows_load<VEC4, SLSH>(a.x, a.g, (tile + gridDim.x) * a.SPT, a.nseq, D, grp, gt, xr);
+            T2_TICK(4);
             const long long seq_s = s0 + (row_s >> SLSH);
             const bool valid_s = (row_s & (SL - 1)) < S && seq_s < a.nseq;
             for (int u = 0; u < nh; ++u) {
                 const int hl = grp + 4 * u;
                 // ---- softmax of this thread's row
-                tc5::mbar_wait(&bar_s[grp], ph_s);
+                tc5::mbar_wait_sleep(&bar_s[grp], ph_s);
                 ph_s ^= 1;
                 tc5::fence_after_sync();
-                T2_TICK(3);                           // wait: scores MMA
+                T2_TICK(5);
                 float v[16];
                 tc5::tmem_ld16(t_S + lane_base + 16 * q, v);
                 tc5::tmem_ld_wait();
@@ -221,151 +269,111 @@ __global__ void __launch_bounds__(T2_THREADS, 1) k_attn_fwd_tc2(AttnTc2Args a) {
 #pragma unroll
                 for (int j = 0; j < SL / 2; ++j)
                     pk[j] = (2 * j < NV) ? pack_h2(xs[2 * j] * inv, (2 * j + 1 < NV) ? xs[2 * j + 1] * inv : 0.f) : 0u;
-                {
-                    unsigned char* pr = Pg + hf * T2_HALF_BYTES + poff(16 * q + li, 2 * q + (SL == 8 ? sb : 0));
-                    sts128(pr, pk[0], pk[1], pk[2], pk[3]);
-                    if (SL == 16) sts128(pr + 64 * 16, pk[SL / 2 - 4], pk[SL / 2 - 3], pk[SL / 2 - 2], pk[SL / 2 - 1]);
-                }
+                sts128(p_row, pk[0], pk[1], pk[2], pk[3]);
+                if (SL == 16) sts128(p_row + 64 * 16, pk[SL / 2 - 4], pk[SL / 2 - 3], pk[SL / 2 - 2], pk[SL / 2 - 1]);
                 tc5::fence_proxy_async();
                 tc5::fence_before_sync();
                 group_sync(grp);
-                T2_TICK(4);                           // softmax + P store + group barrier
-                if (elected) {
+                T2_TICK(6);
+                if (q == 0) {
                     tc5::fence_after_sync();
 #pragma unroll
                     for (int h2 = 0; h2 < 2; ++h2)
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            tc5::mma_f16(t_O + ((uint32_t)(16 * h2) << 16),
-                                         tc5::smem_desc(Ps + h2 * T2_HALF_BYTES + k * 2 * 64 * 16, 64 * 16, 128u),
-                                         tc5::smem_desc(Vs + (uint32_t)((hl * DC * 128 + 64 * h2 + 16 * k) * 16), 128u, tc5::TILE_CHUNK),
-                                         idesc_pv, k > 0);
-                    tc5::mma_commit(&bar_o[grp]);
-                    if (u + 1 < nh) {                 // scores of the next head run under this head's o evacuation
-                        const int hn = hl + 4;
-#pragma unroll
-                        for (int h2 = 0; h2 < 2; ++h2)
-#pragma unroll
-                            for (int ks = 0; ks < DHP / 16; ++ks) {
-                                const uint32_t o = (uint32_t)(((hn * DC + 2 * ks) * 128 + 64 * h2) * 16);
-                                tc5::mma_f16(t_S + ((uint32_t)(16 * h2) << 16), tc5::smem_desc(Qs + o, tc5::TILE_CHUNK, 128u),
-                                             tc5::smem_desc(Ks + o, tc5::TILE_CHUNK, 128u), idesc_s, ks > 0);
-                            }
-                        tc5::mma_commit(&bar_s[grp]);
-                    }
+                            tc5::mma_f16_w(t_O + ((uint32_t)(16 * h2) << 16),
+                                           tc5::smem_desc(Ps + h2 * T2_HALF_BYTES + k * 2 * 64 * 16, 64 * 16, 128u),
+                                           tc5::smem_desc(Vs + (uint32_t)((hl * DC * 128 + 64 * h2 + 16 * k) * 16), 128u, tc5::TILE_CHUNK),
+                                           idesc_pv, k > 0);
+                    tc5::mma_commit_w(&bar_o[grp]);
+                    if (u + 1 < nh) T2_S_MMA(hl + 4);   // scores of the next head run under this head's o evacuation
                 }
+                T2_TICK(7);
                 // ---- o of this head -> fp16 o tile
-                T2_TICK(5);                           // MMA issue (P.V, next scores)
-                tc5::mbar_wait(&bar_o[grp], ph_o);
+                tc5::mbar_wait_sleep(&bar_o[grp], ph_o);
                 ph_o ^= 1;
                 tc5::fence_after_sync();
-                T2_TICK(6);                           // wait: P.V MMA
-                if (!a.o_alias && y_pending && u == 0) { tc5::mbar_wait(&bar_y, ph_y); ph_y ^= 1; y_pending = false; }
-#pragma unroll
-                for (int b = 0; b < DHP / 16; ++b) {
+                T2_TICK(8);
+                if (!a.o_alias && y_pending && u == 0) { tc5::mbar_wait_sleep(&bar_y, ph_y); ph_y ^= 1; y_pending = false; }
+                {
                     float o[16];
-                    tc5::tmem_ld16(t_O + lane_base + b * 16, o);
+                    tc5::tmem_ld16(t_O + lane_base, o);
                     tc5::tmem_ld_wait();
-                    unsigned char* dst = Ot + tc5::toff(row_s, hl * DC + 2 * b);
+                    unsigned char* dst = Ot + tc5::toff(row_s, hl * DC);
                     sts128(dst, pack_h2(o[0], o[1]), pack_h2(o[2], o[3]), pack_h2(o[4], o[5]), pack_h2(o[6], o[7]));
                     sts128(dst + tc5::TILE_CHUNK, pack_h2(o[8], o[9]), pack_h2(o[10], o[11]), pack_h2(o[12], o[13]), pack_h2(o[14], o[15]));
                 }
             }
-            if (nh == 0 && y_pending) { tc5::mbar_wait(&bar_y, ph_y); ph_y ^= 1; y_pending = false; }
+            if (nh == 0 && y_pending && ch > 0) { tc5::mbar_wait_sleep(&bar_y, ph_y); ph_y ^= 1; y_pending = false; }
             tc5::fence_proxy_async();
             tc5::fence_before_sync();
             group_sync(grp);
-            T2_TICK(7);                               // o evacuation + group barrier
-            // ---- out-projection of this chunk: issued by one group's elected thread once all four groups have arrived
-            if (elected) {
-                tc5::mbar_arrive(&bar_og);
+            T2_TICK(9);
+            // ---- out-projection of this chunk: issued by one group's warp 0 once all four groups have arrived
+            if (q == 0) {
+                tc5::mbar_arrive_w(&bar_og);
                 if (grp == ((it + ch) & 3)) {
-                    tc5::mbar_wait(&bar_og, ph_og);
+                    tc5::mbar_wait_sleep(&bar_og, ph_og);
                     tc5::fence_after_sync();
                     const uint32_t wo = Wos + (uint32_t)ch * Np * KO * 2;
                     for (int k = 0; k < KO / 16; ++k)
-                        tc5::mma_f16(t_Y, tc5::kdesc(Os, 128, k), tc5::kdesc(wo, Np, k), idesc_y, (ch > 0 || k > 0) ? 1u : 0u);
-                    tc5::mma_commit(&bar_y);
+                        tc5::mma_f16_w(t_Y, tc5::kdesc(Os, 128, k), tc5::kdesc(wo, Np, k), idesc_y, (ch > 0 || k > 0) ? 1u : 0u);
+                    tc5::mma_commit_w(&bar_y);
                 }
             }
             ph_og ^= 1;
             y_pending = true;
-            T2_TICK(8);                               // out-projection issue (issuer waits for all groups)
+            T2_TICK(10);
         }
-        // ---- stage the next tile while the out-projection runs (the x tile is free once every group's q|k|v MMAs are done)
-        if (tile + gridDim.x < ntiles) {
+        // ---- finish staging the next tile (the x tile is free once every group's q|k|v MMAs are done)
+        if (has_next) {
             for (int g2 = 0; g2 < 4; ++g2)
-                if (hc > g2 && g2 != grp) tc5::mbar_wait(&bar_q[g2], ph_q ^ 1);
-            t2_stage_rows<VEC4, SLSH>(a.x, a.g, (tile + gridDim.x) * a.SPT, a.nseq, D, lnw_s, lnb_s, Xt, grp, gt, nullptr);
+                if (hc > g2 && g2 != grp) tc5::mbar_wait_sleep(&bar_q[g2], ph_q ^ 1);
+            T2_TICK(11);
+            t2_rows_finish<VEC4>(xr, D, Xt, grp, gt, nullptr);
             tc5::fence_proxy_async();
             group_sync(grp);
-            if (elected) tc5::mbar_arrive(&bar_x);
+            if (q == 0) tc5::mbar_arrive_w(&bar_x);
         }
         ph_x ^= 1;
-        T2_TICK(9);                                   // staging of the next tile
-        // ---- epilogue: out = res + alpha * (y + bo) ; 8-column chunks dealt round-robin to the groups
-        tc5::mbar_wait(&bar_y, ph_y);
-        ph_y ^= 1;
-        tc5::fence_after_sync();
-        T2_TICK(10);                                  // wait: out-projection MMA
-        {
+        T2_TICK(12);
+        {   // global row of this thread's accumulator row, for the deferred epilogue
             const int slot = row_e >> SLSH, pos = row_e & (SL - 1);
             const long long seq = s0 + slot;
-            const bool valid = pos < S && seq < a.nseq;
-            const long long gr = valid ? a.g.grow(seq, pos) : 0;
-            const int nck = (D + 7) >> 3;
-            for (int c = (grp + 4 - (it & 3)) & 3; c < nck; c += 4) {
-                float v[8], rv[8];
-                tc5::tmem_ld8(t_Y + lane_base + c * 8, v);
-                if (valid && a.res) load8<VEC4>(a.res + gr * D, c * 8, D, rv);
-                tc5::tmem_ld_wait();
-                if (valid) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        v[k] = a.alpha * (v[k] + bos[c * 8 + k]);
-                        if (a.res) v[k] += rv[k];
-                    }
-                    store8<VEC4>(a.out + gr * D, c * 8, D, v);
-                }
-            }
+            gr_prev = (pos < S && seq < a.nseq) ? a.g.grow(seq, pos) : -1;
         }
-        tc5::fence_before_sync();
-        T2_TICK(11);                                  // y epilogue
     }
-    if (a.dbg && blockIdx.x == 0 && (gt == 0 || gt == 127)) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) a.dbg[(grp * 2 + (gt ? 1 : 0)) * 16 + i] = tk[i];
-        if (gt == 0) a.dbg[grp * 32 + 15] = it;
-    }
+    if (y_pending) y_epilogue(it - 1);
     __syncthreads();
-    if (threadIdx.x < 32) tc5::tmem_dealloc(tmem_base_s, 512);
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x < 128) a.dbg[threadIdx.x] = (threadIdx.x & 15) == 15 ? it : tks[threadIdx.x >> 4][threadIdx.x & 15];
+    if (warp == 0) tc5::tmem_dealloc(tmem_base_s, 512);
 }
 
 }  // namespace rat
 
 using namespace rat;
 
-template <int DHP, int SL, int ST, bool VEC4>
+template <int HPG, int SL, int ST, bool VEC4>
 static int launch_attn_fwd_tc2(const AttnTc2Args& a, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_attn_fwd_tc2<DHP, SL, ST, VEC4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             max_smem_optin() - 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_attn_fwd_tc2<HPG, SL, ST, VEC4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             max_smem_optin() - 2048);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_attn_fwd_tc2)");
         attr_set = true;
     }
     const long long ntiles = (a.nseq + a.SPT - 1) / a.SPT;
     const int grid = (int)std::min<long long>(ntiles, (long long)num_sms());
-    k_attn_fwd_tc2<DHP, SL, ST, VEC4><<<grid, T2_THREADS, a.smem_bytes, st>>>(a);
+    k_attn_fwd_tc2<HPG, SL, ST, VEC4><<<grid, T2_THREADS, a.smem_bytes, st>>>(a);
     RAT_CHECK_LAUNCH("k_attn_fwd_tc2");
     return RAT_OK;
 }
 
-template <int DHP, bool VEC4>
+template <int HPG, bool VEC4>
 static int launch_attn_fwd_tc2_s(const AttnTc2Args& a, cudaStream_t st) {
     const int S = a.g.S;
-    if (S > 8) return S == 14 ? launch_attn_fwd_tc2<DHP, 16, 14, VEC4>(a, st) : launch_attn_fwd_tc2<DHP, 16, 0, VEC4>(a, st);
-    return S == 6 ? launch_attn_fwd_tc2<DHP, 8, 6, VEC4>(a, st) : launch_attn_fwd_tc2<DHP, 8, 0, VEC4>(a, st);
+    if (S > 8) return S == 14 ? launch_attn_fwd_tc2<HPG, 16, 14, VEC4>(a, st) : launch_attn_fwd_tc2<HPG, 16, 0, VEC4>(a, st);
+    return S == 6 ? launch_attn_fwd_tc2<HPG, 8, 6, VEC4>(a, st) : launch_attn_fwd_tc2<HPG, 8, 0, VEC4>(a, st);
 }
 
 // Shared planning of the second-generation attention kernels: head chunking, TMEM regions, shared-memory map.
@@ -375,7 +383,7 @@ bool attn_tc2_plan(int S, int D, int heads, int dh, AttnTc2Args* a) {
     if ((D % 4) != 0 && D > 32) return false;
     const int DHP = 16;
     a->D = D; a->H = heads; a->dh = dh; a->I = heads * dh;
-    a->Kp = pad16(D); a->Np = pad16(D);
+    a->Kp = pad16(D + 1); a->Np = pad16(D);          // + 1: the column of ones that carries the LayerNorm beta
     const int SL = S > 8 ? 16 : 8;
     a->SPT = 128 / SL;
     for (int hc = 8; hc >= 1; hc >>= 1) {
@@ -387,7 +395,7 @@ bool attn_tc2_plan(int S, int D, int heads, int dh, AttnTc2Args* a) {
         size_t off = 0;
         const int off_wqkv = (int)off; off += (size_t)nchunks * 4 * NG * a->Kp * 2;
         const int off_wo = (int)off; off += (size_t)nchunks * a->Np * KO * 2;
-        const int off_f32 = (int)off; off += (size_t)(a->Np + 2 * a->Kp) * 4;
+        const int off_f32 = (int)off; off += (size_t)a->Np * 4;
         off = (off + 127) & ~(size_t)127;
         const int off_x = (int)off; off += (size_t)128 * a->Kp * 2;
         const int off_q = (int)off; off += (size_t)128 * KO * 2;
@@ -420,17 +428,19 @@ int attn_fwd_tc2_dispatch(const float* x, const float* res, float* out, const fl
     static int dbg_on = -1;
     if (dbg_on < 0) { const char* e = getenv("RAT_T2_DBG"); dbg_on = (e && e[0] == '1') ? 1 : 0; if (dbg_on) cudaMalloc(&dbg, 128 * 8); }
     a.dbg = dbg_on ? dbg : nullptr;
-    const int rc = (D % 4) == 0 ? launch_attn_fwd_tc2_s<16, true>(a, st) : launch_attn_fwd_tc2_s<16, false>(a, st);
+    int rc;
+    if (a.HPG == 2) rc = (D % 4) == 0 ? launch_attn_fwd_tc2_s<2, true>(a, st) : launch_attn_fwd_tc2_s<2, false>(a, st);
+    else rc = (D % 4) == 0 ? launch_attn_fwd_tc2_s<1, true>(a, st) : launch_attn_fwd_tc2_s<1, false>(a, st);
     if (dbg_on && rc == RAT_OK) {
         long long h[128];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
-        static const char* names[12] = {"prologue", "wait x+qkv MMA", "qkv evac", "wait S MMA", "softmax+P", "MMA issue", "wait PV MMA",
-                                        "o evac", "outproj issue", "stage next", "wait outproj", "y epilogue"};
+        static const char* names[13] = {"qkv issue(+wait x)", "y epilogue(prev)", "wait qkv MMA", "qkv evac+sync", "x prefetch issue", "wait S MMA",
+                                        "softmax+P+sync", "PV/S issue", "wait PV MMA", "o evac+sync", "outproj issue", "peek qkv bars", "stage finish"};
         fprintf(stderr, "[t2 fwd dbg] S=%d mode=%d tiles(CTA0)=%lld ; cycles per tile, group: thread0 / thread127\n", S, mode, h[15]);
-        for (int i = 0; i < 12; ++i) {
-            fprintf(stderr, "  %-16s", names[i]);
-            for (int g = 0; g < 4; ++g) fprintf(stderr, "  g%d %7.0f /%7.0f", g, (double)h[(g * 2) * 16 + i] / (i ? h[15] : 1), (double)h[(g * 2 + 1) * 16 + i] / (i ? h[15] : 1));
+        for (int i = 0; i < 13; ++i) {
+            fprintf(stderr, "  %-20s", names[i]);
+            for (int g = 0; g < 4; ++g) fprintf(stderr, "  g%d %6.0f /%6.0f", g, (double)h[(g * 2) * 16 + i] / h[15], (double)h[(g * 2 + 1) * 16 + i] / h[15]);
             fprintf(stderr, "\n");
         }
     }

@@ -137,6 +137,57 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---- warp-uniform issue: called by ALL lanes of a converged warp with warp-uniform operands; one elected lane issues.
+// Keeping the C++ control flow uniform lets ptxas hold descriptors in uniform registers (a divergent `if (tid == 0)`
+// costs an ELECT / R2UR.BROADCAST waterfall of ~100 cycles per MMA).
+__device__ __forceinline__ void mma_f16_w(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, e;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "elect.sync _|e, 0xffffffff;\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_w(uint64_t* bar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred e;\n"
+        "elect.sync _|e, 0xffffffff;\n"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+        "}\n" ::"r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_w(uint64_t* bar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred e;\n"
+        ".reg .b64 st;\n"
+        "elect.sync _|e, 0xffffffff;\n"
+        "@e mbarrier.arrive.shared::cta.b64 st, [%0];\n"
+        "}\n" ::"r"(smem_u32(bar))
+        : "memory");
+}
+// wait with a hardware suspend-time hint: the thread sleeps inside try_wait instead of spinning through issue slots
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+    for (uint32_t it = 0; it < (1u << 16); ++it) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(200000u)
+            : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+
 // descriptor of K-step `kstep` (16 bf16 = two 16-byte chunks) of a chunk-major K-major operand with `rows` rows
 __device__ __forceinline__ uint64_t kdesc(uint32_t saddr, int rows, int kstep) {
     return smem_desc(saddr + (uint32_t)(kstep * 2 * rows * 16), (uint32_t)(rows * 16), 128u);
