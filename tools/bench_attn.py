@@ -1,5 +1,5 @@
 """Time rat_attn_fwd / rat_attn_bwd alone (CUDA events, rotating buffers larger than L2) at a dataset shape.
-   python tools/bench_attn.py [kkbox|tmall|ml] [B] [K]      (RAT_TC2=0 selects the first-generation kernels)"""
+   python tools/bench_attn.py [kkbox|tmall|ml] [B] [K]      (RAT_TC2=1 selects the second-generation forward kernel)"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "www24-rat_b200"))
@@ -50,4 +50,4 @@ for mode in (0, 1):
         us = e0.elapsed_time(e1) / iters * 1e3
         mb = tokens * D * 4 * passes / 1e6
         print(f"{shape} B={B} K={K} mode={mode} attn_{name}: {us:.1f} us/call  ({mb:.0f} MB algorithmic -> {mb / us * 1e3:.0f} GB/s)"
-              f"  gen={'1' if os.environ.get('RAT_TC2') == '0' else '2'}")
+              f"  gen={'2' if os.environ.get('RAT_TC2') == '1' else '1'}")

@@ -239,10 +239,12 @@ int attn_fwd_tc2_dispatch(const float* x, const float* res, float* out, const fl
                           const float* Wq, const float* Wk, const float* Wv, const float* Wo, const float* bo, int B, int T,
                           int N, int D, int heads, int dh, float scale, float alpha, int mode, cudaStream_t st);
 
-// RAT_TC2=0 in the environment keeps the first-generation tcgen05 attention kernels (A/B measurements)
+// RAT_TC2=1 in the environment selects the second-generation attention forward (every product on tcgen05, one tile per
+// 4-warp group; encoder_tc2_fwd.cu).  It is parity-green but measured no faster than the first generation on B200
+// (kkbox B=4096: 128 / 144 us vs 129 / 135 us; DESIGN.md "Attention, second generation"), so it is opt-in.
 bool tc2_enabled() {
     static int on = -1;
-    if (on < 0) { const char* e = getenv("RAT_TC2"); on = (e && e[0] == '0') ? 0 : 1; }
+    if (on < 0) { const char* e = getenv("RAT_TC2"); on = (e && e[0] == '1') ? 1 : 0; }
     return on == 1;
 }
 

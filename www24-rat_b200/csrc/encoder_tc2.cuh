@@ -13,9 +13,12 @@
 // (A = that tile, K-major; B = the v tile read MN-major).  In the backward the same block-diagonal tiles are read
 // MN-major to get P^T and dS^T for free.
 //
-// Threads.  512 = 4 head GROUPS of 4 warps (one warp per TMEM lane quadrant).  A group owns heads {g, g+4, ..} of a
-// head chunk and runs them as an independent pipeline (own TMEM column region, own named barrier, own mbarriers, its
-// MMAs issued by its own elected thread), so while one group waits for the tensor pipe the other three compute.
+// Threads.  512 = 4 GROUPS of 4 warps (one warp per TMEM lane quadrant).  Every group is an independent pipeline working
+// on its OWN tile (own activation tiles in shared memory, own 128 TMEM columns, own named barrier and mbarriers, its
+// MMAs issued by one of its own warps), heads streamed one at a time; only the weight images are shared.  Each step of a
+// tile is a short latency chain (MMA -> mbarrier -> tcgen05.ld -> thread-per-row math -> st.shared -> fence -> MMA):
+// four chains in flight per SM keep the issue slots and the tensor pipe busy while any one of them waits
+// (tools/tc5_timing.cu: ~28 cycles per small MMA, ~200 cycles commit -> wake-up).
 #pragma once
 #include "encoder_tc.cuh"
 
@@ -41,8 +44,8 @@ __device__ __forceinline__ float slot_pick(const float (&v)[16], int sb, int j) 
     return sb ? v[8 + j] : v[j];
 }
 
-// Staging of a tile's token rows, 4 threads per row (group grp stages rows [32*grp, 32*grp + 32)), split in two so that
-// the global loads of the NEXT tile can be in flight under the head loop of the current one:
+// Staging of a tile's token rows, 4 threads per row (thread = (row, part)), split in two so that several rows' global loads can
+// be in flight before the first is consumed:
 //   t2_rows_load   : the row's 16-/8-byte units part, part+4, .. -> registers
 //   t2_rows_finish : LayerNorm WITHOUT the affine part (gamma is folded into the weight image, beta rides on a column of
 //                    ones at column D), fp16, chunk-major K-major tile.  Pad columns (> D) are never written
@@ -52,9 +55,8 @@ struct XRegs { float v[4][VEC4 ? 4 : 2]; bool valid; };
 
 template <bool VEC4, int SLSH>
 __device__ __forceinline__ void t2_rows_load(const float* __restrict__ x, const SeqGeom& g, long long s0, long long nseq,
-                                             int D, int grp, int gt, XRegs<VEC4>& r) {
+                                             int D, int row, int part, XRegs<VEC4>& r) {
     constexpr int U = VEC4 ? 4 : 2;
-    const int row = 32 * grp + (gt >> 2), part = gt & 3;
     const int slot = row >> SLSH, pos = row & ((1 << SLSH) - 1);
     const long long seq = s0 + slot;
     r.valid = pos < g.S && seq < nseq;
@@ -73,10 +75,9 @@ __device__ __forceinline__ void t2_rows_load(const float* __restrict__ x, const 
 }
 
 template <bool VEC4>
-__device__ __forceinline__ void t2_rows_finish(const XRegs<VEC4>& r, int D, unsigned char* __restrict__ Xt, int grp, int gt,
+__device__ __forceinline__ void t2_rows_finish(const XRegs<VEC4>& r, int D, unsigned char* __restrict__ Xt, int row, int part,
                                                float* __restrict__ stats) {
     constexpr int U = VEC4 ? 4 : 2;
-    const int row = 32 * grp + (gt >> 2), part = gt & 3;
     const int nun = D / U;
     float s = 0.f;
 #pragma unroll
