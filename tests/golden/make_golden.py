@@ -116,6 +116,16 @@ for _m in ("RAT_m0", "RAT_m1", "RAT_m3"):
                                          embedding_regularizer=0.001), 6, 4)
 
 
+# BASELINE configs[3]: the variants on the kkbox SCHEMA (13 fields incl. two sum-pooled sequence fields, D=40, 8 heads of
+# width 10, K=5): RAT_m0 attends over one flat sequence of 6*14 = 84 tokens, RAT_m1 over 14 then 6, RAT_m3 uses 4 heads of
+# width 20.  Vocabulary, depth and DNN widths are reduced to keep the fixtures small.
+for _m in ("RAT_m0", "RAT_m1", "RAT_m3"):
+    CASES[_m.lower() + "_kkbox"] = (_m, CASES["kkbox_small"][1],
+                                    dict(embedding_dim=40, num_heads=8, dim_head=10, scale_dim=2, depth=2,
+                                         dnn_hidden_units=[48, 32, 16], batch_norm=True, use_wide=(_m != "RAT_m1"),
+                                         embedding_regularizer=0.0005), 8, 5)
+
+
 def run_case(name, models, Dataset, FeatureMap):
     model_name, feats, hp, B, K = CASES[name]
     rng = np.random.default_rng(abs(hash(name)) % (2 ** 31) if False else sum(map(ord, name)))
@@ -220,6 +230,9 @@ def param_counts(models, FeatureMap):
 if __name__ == "__main__":
     models, Dataset, FeatureMap = import_reference()
     os.makedirs("/tmp/rat_golden", exist_ok=True)
+    only = sys.argv[1:]
     for name in CASES:
-        run_case(name, models, Dataset, FeatureMap)
-    param_counts(models, FeatureMap)
+        if not only or name in only:
+            run_case(name, models, Dataset, FeatureMap)
+    if not only:
+        param_counts(models, FeatureMap)

@@ -18,11 +18,12 @@ def bf16():
 
 
 def ptol(rtol, atol, rt=1e-2, at_scale=40.0):
-    """(rtol, atol) for the current precision mode: fp32 values as given; tf32 (10-bit mantissa operands,
-    fp32 accumulate): rtol 1e-2 and atol x40; bf16 (tcgen05, 8-bit mantissa operands, fp32 accumulate):
-    rtol 4e-2 and atol x640 -- unit roundoff 2^-8 over K~40..80 term dot products of O(1) operands)."""
+    """(rtol, atol) for the current precision mode: fp32 values as given; tf32 (mma.sync) and fp16 (tcgen05, the
+    benchmarked mode) both round their operands to a 10-bit mantissa (unit roundoff 2^-11) and accumulate in fp32:
+    rtol 1e-2 and atol x40 (x80 in fp16: the gradient-domain tiles are additionally scaled to a power of two and the
+    LayerNorm / GELU inputs of the backward kernels are recomputed from fp16 tiles)."""
     if bf16():
-        return (max(rtol, 4 * rt), atol * at_scale * 16)
+        return (max(rtol, rt), atol * at_scale * 2)
     return (max(rtol, rt), atol * at_scale) if tf32() else (rtol, atol)
 
 

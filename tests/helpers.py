@@ -11,6 +11,8 @@ from oracle import rat_oracle as O
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES_M2 = ["ml_small", "kkbox_small", "tmall_small"]
 CASES_VAR = ["rat_m0_small", "rat_m1_small", "rat_m3_small"]
+# the variants on the kkbox schema (BASELINE configs[3]: S = 84 flat / 14 + 6 / head width 20)
+CASES_VAR_KKBOX = ["rat_m0_kkbox", "rat_m1_kkbox", "rat_m3_kkbox"]
 
 
 def load_case(name):

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import rat_oracle as O
-from tests.helpers import CASES_M2, CASES_VAR, load_case, split_state
+from tests.helpers import CASES_M2, CASES_VAR, CASES_VAR_KKBOX, load_case, split_state
 
 pytestmark = pytest.mark.gpu
 
@@ -33,7 +33,7 @@ def _model_from_case(c, tmp_path, **over):
     return getattr(models, meta["model"])(fm, **kw), fm
 
 
-@pytest.mark.parametrize("name", CASES_M2 + CASES_VAR)
+@pytest.mark.parametrize("name", CASES_M2 + CASES_VAR + CASES_VAR_KKBOX)
 def test_state_dict_keys_and_forward_match_reference(name, tmp_path):
     """state_dict key set/shapes == the reference's (checkpoint compatibility), and after load_state_dict of the
     reference weights, forward() returns the reference's y_pred (fixture), as [B,1] tensors like RAT_m2.py:151."""

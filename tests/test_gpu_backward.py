@@ -328,7 +328,8 @@ def test_clip_and_adam_match_torch(rn):
 
 
 # ------------------------------------------------------------------------------------------ whole training step
-@pytest.mark.parametrize("name", CASES_M2 + ["rat_m3_small", "rat_m0_small", "rat_m1_small"])
+@pytest.mark.parametrize("name", CASES_M2 + ["rat_m3_small", "rat_m0_small", "rat_m1_small", "rat_m0_kkbox", "rat_m1_kkbox",
+                                  "rat_m3_kkbox"])
 def test_two_train_steps_match_reference_golden(rn, name):
     from rat_native.engine import set_precision
     set_precision("fp32")
@@ -341,7 +342,7 @@ def test_two_train_steps_match_reference_golden(rn, name):
 def _golden_train(rn, name):
     """loss, grad-norm, every gradient of step 1 and every parameter / BN buffer after step 2 vs the values the
     REFERENCE produced (tests/golden).  Tolerances: grads rtol 2e-3 / atol 1e-5*max; weights atol 5e-5."""
-    from tests.gpu_util import assert_close, make_engine
+    from tests.gpu_util import assert_close, assert_close_adam, make_engine
     c = load_case(name)
     spec = c["spec"]
     params, bufs = split_state(c["sd0"])
@@ -376,8 +377,14 @@ def _golden_train(rn, name):
     assert float(eng.opt_state[0]) == pytest.approx(float(c["z"]["train/norm2"]), rel=2e-3)
     ref_p, ref_b = split_state(c["sd2"])
     for k, w in ref_p.items():
-        atol = 4e-3 if noise_grad_param(k, spec) else 5e-5
-        assert_close(f"param {k}", eng.p[k], w, 1e-4, atol)
+        if noise_grad_param(k, spec):
+            assert_close(f"param {k}", eng.p[k], w, 1e-4, 4e-3)
+        elif name.endswith("_kkbox"):
+            # 150 k encoder weights per case: a handful whose gradient is at the fp32 summation-order noise level can take
+            # a different Adam sign on one of the two steps (<= 0.2 % of a tensor, each bounded by 2 steps x lr)
+            assert_close_adam(f"param {k}", eng.p[k], w, 1e-4, 5e-5, lr_steps=2.5e-3, max_outlier_frac=2e-3)
+        else:
+            assert_close(f"param {k}", eng.p[k], w, 1e-4, 5e-5)
     for k, w in ref_b.items():
         # running_mean tracks mean(z) where z includes the Linear bias that Adam moves by +-lr of pure rounding noise
         # (noise_grad_param): momentum 0.1 * lr 1e-3 * 2 steps => up to 2e-4 of legitimate divergence
@@ -385,19 +392,64 @@ def _golden_train(rn, name):
         assert_close(f"buffer {k}", eng.buffers[k].float(), w.float(), 1e-4, atol)
 
 
-@pytest.mark.parametrize("shape,B,K", [("kkbox", 96, 5), ("tmall", 128, 5), ("ml", 256, 5)])
-def test_train_steps_full_width_vs_oracle(rn, shape, B, K):
+@pytest.mark.parametrize("name", CASES_M2 + ["rat_m3_kkbox", "rat_m0_kkbox", "rat_m1_kkbox"])
+def test_step1_gradients_fp16_vs_reference(rn, name):
+    """every gradient of training step 1 in the BENCHMARKED precision (fp16 tensor-core operands, dynamic gradient
+    scaling) against the gradients the reference produced: per tensor, max |error| <= 2e-2 of the tensor's max |g|
+    (measured ~2e-3 .. 8e-3) and relative L2 error <= 1.5e-2."""
     from rat_native.engine import set_precision
-    set_precision("fp32")
+    from tests.gpu_util import make_engine
+    set_precision("fp16")
     try:
-        _full_width_train(rn, shape, B, K)
+        c = load_case(name)
+        spec = c["spec"]
+        params, bufs = split_state(c["sd0"])
+        eng = make_engine(spec, params, bufs)
+        X, y = c["X"].cuda(), c["y"].cuda()
+        B, T = X.shape[0], X.shape[1]
+        ws = eng.load_wire(X, y, training=True)
+        eng.rng_step += 1
+        ws["dact"].zero_()
+        if ws.get("dact_c") is not None:
+            ws["dact_c"].zero_()
+        eng.forward_ids(ws, B, T, training=True, inv_count=1.0 / B)
+        eng.backward(ws, B, T)
+        grads = eng.materialize_grads()
+        worst = []
+        for k, gref in c["grad1"].items():
+            if ".fn.W_" in k or noise_grad_param(k, spec):
+                continue
+            g = grads[k].detach().float().cpu()
+            assert torch.isfinite(g).all(), k
+            gmax = float(gref.abs().max())
+            if gmax < 1e-7:
+                continue
+            e_max = float((g - gref).abs().max()) / gmax
+            e_l2 = float((g - gref).norm() / gref.norm())
+            worst.append((e_max, e_l2, k))
+            assert e_max <= 2e-2 and e_l2 <= 1.5e-2, f"{k}: max err / max|g| = {e_max:.2e}, rel L2 = {e_l2:.2e}"
+        worst.sort(reverse=True)
+        print(f"{name}: worst gradient tensors (max err / max|g|, rel L2): {worst[:3]}")
+    finally:
+        set_precision("fp16")
+
+
+@pytest.mark.parametrize("mode", ["fp32", "fp16"])
+@pytest.mark.parametrize("shape,B,K", [("kkbox", 96, 5), ("tmall", 128, 5), ("ml", 256, 5)])
+def test_train_steps_full_width_vs_oracle(rn, shape, B, K, mode):
+    from rat_native.engine import set_precision
+    set_precision(mode)
+    try:
+        _full_width_train(rn, shape, B, K, mode)
     finally:
         set_precision("fp16")     # back to the library default
 
 
-def _full_width_train(rn, shape, B, K):
-    """full-width architecture (reduced vocabulary), 3 steps, oracle as checker; dropout off."""
+def _full_width_train(rn, shape, B, K, mode="fp32"):
+    """full-width architecture (reduced vocabulary), 3 steps, oracle as checker; dropout off.  fp16 (benchmarked mode):
+    loss 3e-3 rel, grad-norm 2e-2 rel, post-Adam weights 6e-4 (+4e-3 rel) with <= 6 % Adam sign-flip outliers."""
     from tests.gpu_util import assert_close, assert_close_adam, make_engine, rand_params_nontrivial
+    f16 = mode != "fp32"
     spec = O.shape_spec(shape, vocab_scale=0.02, emb_dropout=0.0, net_dropout=0.0)
     params = rand_params_nontrivial(spec, seed=11)
     bufs = O.init_buffers(spec)
@@ -413,13 +465,15 @@ def _full_width_train(rn, shape, B, K):
         eng.train_step_ids(ws, B, K + 1)
         eng.check_errors()
         got_loss = float(ws["loss"][1]) + float(eng.opt_state[5])
-        assert got_loss == pytest.approx(r["loss"], rel=2e-4), f"step {step}"
-        assert float(eng.opt_state[0]) == pytest.approx(r["grad_norm"], rel=3e-3), f"step {step}"
+        assert got_loss == pytest.approx(r["loss"], rel=3e-3 if f16 else 2e-4), f"step {step}"
+        assert float(eng.opt_state[0]) == pytest.approx(r["grad_norm"], rel=2e-2 if f16 else 3e-3), f"step {step}"
     for k, w in params.items():
         if k.startswith("query_proj"):
             continue
         if noise_grad_param(k, spec):
-            assert_close(f"param {k}", eng.p[k], w, 2e-4, 5.5e-3)
+            assert_close(f"param {k}", eng.p[k], w, 2e-4, 6.5e-3)
+        elif f16:
+            assert_close_adam(f"param {k}", eng.p[k], w, 4e-3, 6e-4, lr_steps=6.5e-3, max_outlier_frac=0.06)
         else:
             assert_close_adam(f"param {k}", eng.p[k], w, 2e-4, 1e-4, lr_steps=3.5e-3)
 
@@ -452,11 +506,12 @@ def test_two_train_steps_tf32_close_to_reference(rn, name):
     set_precision("fp16")     # back to the library default
 
 
-@pytest.mark.parametrize("name", CASES_M2 + ["rat_m3_small", "rat_m0_small", "rat_m1_small"])
+@pytest.mark.parametrize("name", CASES_M2 + ["rat_m3_small", "rat_m0_small", "rat_m1_small", "rat_m0_kkbox", "rat_m1_kkbox",
+                                  "rat_m3_kkbox"])
 def test_two_train_steps_fp16_close_to_reference(rn, name):
-    """bench precision (tcgen05: bf16 operands, fp32 TMEM accumulate; everything else fp32) against the reference
+    """bench precision (tcgen05: fp16 operands, fp32 TMEM accumulate; everything else fp32) against the reference
     fixtures: loss within 5e-3 rel, grad-norm within 3e-2 rel, post-Adam weights within 6e-4 (+4e-3 rel) allowing 6 %
-    Adam sign-flip outliers: an element whose gradient is below the bf16 noise can step +lr here and -lr in the
+    Adam sign-flip outliers: an element whose gradient is below the fp16 operand noise can step +lr here and -lr in the
     reference on both steps, so each outlier is bounded by 2 steps x 2 lr (+ slack) = 4.5e-3."""
     from rat_native.engine import set_precision
     from tests.gpu_util import assert_close, assert_close_adam, make_engine
@@ -485,8 +540,9 @@ def test_two_train_steps_fp16_close_to_reference(rn, name):
 
 
 @pytest.mark.parametrize("mode", ["fp32", "tf32", "fp16"])
-@pytest.mark.parametrize("shape,B,steps", [("ml", 512, 30), ("kkbox", 256, 15)])
-def test_auc_logloss_after_fixed_steps_match_oracle(rn, mode, shape, B, steps):
+@pytest.mark.parametrize("shape,B,steps,vocab_scale", [("ml", 512, 30, 0.02), ("kkbox", 256, 15, 0.02), ("tmall", 256, 15, 0.02),
+                                                       ("kkbox", 4096, 4, 1.0)])
+def test_auc_logloss_after_fixed_steps_match_oracle(rn, mode, shape, B, steps, vocab_scale):
     """north-star acceptance: the same `steps` training steps from the same weights on the same batches, CUDA path vs
     the CPU oracle, then AUC / logloss of both on a held-out batch agree to 1e-3 (every precision mode)."""
     from rat_native.engine import set_precision
@@ -494,13 +550,17 @@ def test_auc_logloss_after_fixed_steps_match_oracle(rn, mode, shape, B, steps):
     set_precision(mode)
     try:
         K = 5
-        spec = O.shape_spec(shape, vocab_scale=0.02, emb_dropout=0.0, net_dropout=0.0)
+        if B == 4096 and mode == "tf32":
+            pytest.skip("the full-size case runs in the parity anchor (fp32) and the benchmarked mode (fp16)")
+        spec = O.shape_spec(shape, vocab_scale=vocab_scale, emb_dropout=0.0, net_dropout=0.0)
         params = O.init_params(spec, 5)
         for k, v in params.items():                     # embeddings large enough to matter after a few steps
             if "embedding_layer.embedding_layer" in k:
                 v.mul_(300.0)
         bufs = O.init_buffers(spec)
-        n_pool = 6000
+        n_hold = 2000
+        n_train = max(4000, B)
+        n_pool = n_train + n_hold
         pool = O.synthetic_pool(spec, n_pool, seed=21)
         rng = np.random.default_rng(4)
         noise = rng.random(n_pool) < 0.15
@@ -511,14 +571,14 @@ def test_auc_logloss_after_fixed_steps_match_oracle(rn, mode, shape, B, steps):
         eng = make_engine(spec, params, bufs)
         st = O.AdamState()
         for i in range(steps):
-            rows = np.arange(i * B, (i + 1) * B) % 4000
+            rows = np.arange(i * B, (i + 1) * B) % n_train
             X, y = O.assemble_batch(pool[rows], pool, nbr[rows], np.arange(len(rows)))
             X, y = torch.from_numpy(X), torch.from_numpy(y)
             O.train_step(params, bufs, spec, st, X, y)
             ws = eng.load_wire(X.cuda(), y.cuda(), training=True)
             eng.train_step_ids(ws, B, K + 1)
         eng.check_errors()
-        rows = np.arange(4000, 6000)
+        rows = np.arange(n_train, n_pool)
         X, y = O.assemble_batch(pool[rows], pool, nbr[rows], np.arange(len(rows)))
         X, y = torch.from_numpy(X), torch.from_numpy(y)
         with torch.no_grad():
@@ -529,7 +589,12 @@ def test_auc_logloss_after_fixed_steps_match_oracle(rn, mode, shape, B, steps):
         auc_o, auc_g = O.auc(yt, want), O.auc(yt, got)
         ll_o, ll_g = O.logloss(yt, want), O.logloss(yt, got)
         print(f"{mode} {shape}: AUC oracle {auc_o:.5f} cuda {auc_g:.5f} | logloss oracle {ll_o:.5f} cuda {ll_g:.5f}")
-        assert auc_o > 0.53, "the task must be learnable for the comparison to mean something"
+        if B < 4096:
+            assert auc_o > 0.53, "the task must be learnable for the comparison to mean something"
+        else:   # full batch / full vocabulary, few steps: also pin the probabilities themselves.  After 4 Adam steps the
+            # weights whose gradient is at the rounding-noise level have moved +-lr independently on the two sides
+            # (measured max |dp|: fp32 6.8e-4, fp16 3.5e-3)
+            assert float(np.abs(got - want).max()) < (2e-3 if mode == "fp32" else 6e-3)
         assert abs(auc_o - auc_g) < 1e-3 and abs(ll_o - ll_g) < 1e-3
     finally:
         set_precision("fp16")     # back to the library default

@@ -321,9 +321,11 @@ def test_bn_act_forward(rn):
 
 
 # ------------------------------------------------------------------------------------------ whole forward
-@pytest.mark.parametrize("name", CASES_M2 + ["rat_m3_small", "rat_m0_small", "rat_m1_small"])
+@pytest.mark.parametrize("name", CASES_M2 + ["rat_m3_small", "rat_m0_small", "rat_m1_small", "rat_m0_kkbox", "rat_m1_kkbox",
+                                  "rat_m3_kkbox"])
 def test_eval_forward_matches_reference_golden(rn, precision, name):
-    """engine forward (eval) vs the y_pred the REFERENCE produced (fixture). fp32: rtol 1e-4 atol 1e-5."""
+    """engine forward (eval) vs the y_pred the REFERENCE produced (fixture). fp32: rtol 1e-4 atol 1e-5; tf32 / fp16
+    (the benchmarked mode): 3e-3 absolute on the probability."""
     from tests.gpu_util import assert_close, make_engine, ptol
     c = load_case(name)
     params, bufs = split_state(c["sd0"])
@@ -332,9 +334,10 @@ def test_eval_forward_matches_reference_golden(rn, precision, name):
     ws = eng.load_wire(X, y, training=False)
     y_pred = eng.forward_ids(ws, X.shape[0], X.shape[1], training=False, with_loss=True)
     eng.check_errors()
-    assert_close("y_pred", y_pred, torch.from_numpy(c["z"]["eval/y_pred"][:, 0]), *ptol(1e-4, 1e-5, at_scale=300.0))
+    tol = (1e-4, 1e-5) if precision == "fp32" else (0.0, 3e-3)
+    assert_close("y_pred", y_pred, torch.from_numpy(c["z"]["eval/y_pred"][:, 0]), *tol)
     want_loss = O.bce_mean(torch.from_numpy(c["z"]["eval/y_pred"]), c["y"][:, 0:1].float())
-    assert_close("bce", ws["loss"][1:2], want_loss.reshape(1), *ptol(1e-4, 1e-6, at_scale=3000.0))
+    assert_close("bce", ws["loss"][1:2], want_loss.reshape(1), *((1e-4, 1e-6) if precision == "fp32" else (5e-3, 1e-4)))
 
 
 @pytest.mark.parametrize("shape,B,K", [("ml", 512, 5), ("kkbox", 192, 5), ("tmall", 160, 5), ("kkbox", 24, 16)])
@@ -359,5 +362,5 @@ def test_eval_forward_full_width_vs_oracle(rn, precision, shape, B, K):
     ws = eng.load_wire(X.cuda(), y.cuda(), training=False)
     y_pred = eng.forward_ids(ws, B, K + 1, training=False)
     eng.check_errors()
-    assert_close("pooled", ws["enc_out"][:, 0, 0, :], parts["pooled"], *ptol(3e-4, 3e-5 * float(parts["pooled"].abs().max()), rt=2e-2, at_scale=300.0))
-    assert_close("y_pred", y_pred, want[:, 0], *ptol(2e-4, 2e-5, at_scale=300.0))
+    assert_close("pooled", ws["enc_out"][:, 0, 0, :], parts["pooled"], *ptol(3e-4, 3e-5 * float(parts["pooled"].abs().max()), rt=2e-2, at_scale=150.0))
+    assert_close("y_pred", y_pred, want[:, 0], *((2e-4, 2e-5) if precision == "fp32" else (0.0, 3e-3)))

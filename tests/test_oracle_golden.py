@@ -8,14 +8,14 @@ import pytest
 import torch
 
 from oracle import rat_oracle as O
-from tests.helpers import (CASES_M2, CASES_VAR, GOLDEN, add_dead_params, load_case, noise_grad_param,
+from tests.helpers import (CASES_M2, CASES_VAR, CASES_VAR_KKBOX, GOLDEN, add_dead_params, load_case, noise_grad_param,
                            split_state)
 
 FWD_TOL = dict(rtol=2e-5, atol=2e-6)     # fp32 vs fp32, different op order
 GRAD_TOL = dict(rtol=2e-4, atol=2e-6)
 
 
-@pytest.mark.parametrize("name", CASES_M2 + CASES_VAR)
+@pytest.mark.parametrize("name", CASES_M2 + CASES_VAR + CASES_VAR_KKBOX)
 def test_assembly_matches_reference_dataset(name):
     """a1: numpy fancy-index assembly incl. the -1 -> last-pool-row wraparound (data_generator.py:66-78)."""
     c = load_case(name)
@@ -30,7 +30,7 @@ def test_assembly_matches_reference_dataset(name):
     np.testing.assert_array_equal(X[b, 1 + k], z["pool"][-1, :-1])
 
 
-@pytest.mark.parametrize("name", CASES_M2 + CASES_VAR)
+@pytest.mark.parametrize("name", CASES_M2 + CASES_VAR + CASES_VAR_KKBOX)
 def test_eval_forward_matches_reference(name):
     c = load_case(name)
     params, bufs = split_state(c["sd0"])
@@ -40,7 +40,7 @@ def test_eval_forward_matches_reference(name):
     np.testing.assert_array_equal(c["y"][:, 0:1].float().numpy(), c["z"]["eval/y_true"])
 
 
-@pytest.mark.parametrize("name", CASES_M2 + CASES_VAR)
+@pytest.mark.parametrize("name", CASES_M2 + CASES_VAR + CASES_VAR_KKBOX)
 def test_two_train_steps_match_reference(name):
     c = load_case(name)
     spec = c["spec"]
@@ -67,7 +67,7 @@ def test_two_train_steps_match_reference(name):
         np.testing.assert_allclose(bufs[k].numpy(), w.numpy(), rtol=1e-4, atol=1e-6, err_msg=k)
 
 
-@pytest.mark.parametrize("name", CASES_M2 + CASES_VAR)
+@pytest.mark.parametrize("name", CASES_M2 + CASES_VAR + CASES_VAR_KKBOX)
 def test_param_count_small(name):
     c = load_case(name)
     params, _ = split_state(c["sd0"])

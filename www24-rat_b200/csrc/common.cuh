@@ -37,6 +37,10 @@ extern long long g_launches;     // kernels launched by this library (one RAT_CH
 
 int num_sms();
 int max_smem_optin();
+// Device-resident training-step counter of the dropout streams: kernels with dropout add 64 * (*ptr) to the rng stream
+// they are given, so a CUDA graph of the training step replays with a fresh mask every time (the counter is advanced by
+// a kernel INSIDE the graph: rat_rng_step_advance).
+const unsigned int* rng_step_ptr();
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
@@ -91,6 +95,9 @@ __device__ __forceinline__ uint4 dropout_bits8(unsigned long long seed, uint32_t
     const uint32_t b = (uint32_t)c << 2;
     return make_uint4(lowbias32((b + 0u) ^ hi), lowbias32((b + 1u) ^ hi), lowbias32((b + 2u) ^ hi), lowbias32((b + 3u) ^ hi));
 #endif
+}
+__device__ __forceinline__ uint32_t rng_stream_of_step(uint32_t stream, const unsigned int* __restrict__ step) {
+    return step ? stream + 64u * __ldg(step) : stream;
 }
 __device__ __forceinline__ uint32_t dropout_threshold(float p) { return (uint32_t)(p * 65536.0f + 0.5f); }
 // lane j (0..7) of the 128-bit Philox output

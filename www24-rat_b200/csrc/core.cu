@@ -30,6 +30,15 @@ static void query() {
     if (g_sms <= 0) g_sms = 148;
     if (g_smem <= 0) g_smem = 227 * 1024;
 }
+static unsigned int* g_rng_step = nullptr;
+const unsigned int* rng_step_ptr() {
+    if (!g_rng_step) {
+        if (cudaMalloc(&g_rng_step, sizeof(unsigned int)) != cudaSuccess) return nullptr;
+        cudaMemset(g_rng_step, 0, sizeof(unsigned int));
+    }
+    return g_rng_step;
+}
+__global__ void k_rng_step(unsigned int* p, unsigned int set, int advance) { *p = advance ? *p + 1u : set; }
 int num_sms() { if (!g_sms) query(); return g_sms; }
 int max_smem_optin() { if (!g_smem) query(); return g_smem; }
 
@@ -50,5 +59,20 @@ extern "C" int rat_device_check(void) {
         rat::set_error("rat_device_check: device %d is sm_%d%d; librat_b200 contains sm_100a code only", dev, major, minor);
         return RAT_ECUDA;
     }
+    return RAT_OK;
+}
+
+extern "C" int rat_rng_step_set(unsigned int value, void* stream) {
+    unsigned int* p = const_cast<unsigned int*>(rat::rng_step_ptr());
+    RAT_REQUIRE(p != nullptr, "rat_rng_step_set: allocation failed");
+    rat::k_rng_step<<<1, 1, 0, (cudaStream_t)stream>>>(p, value, 0);
+    RAT_CHECK_LAUNCH("k_rng_step");
+    return RAT_OK;
+}
+extern "C" int rat_rng_step_advance(void* stream) {
+    unsigned int* p = const_cast<unsigned int*>(rat::rng_step_ptr());
+    RAT_REQUIRE(p != nullptr, "rat_rng_step_advance: allocation failed");
+    rat::k_rng_step<<<1, 1, 0, (cudaStream_t)stream>>>(p, 0u, 1);
+    RAT_CHECK_LAUNCH("k_rng_step");
     return RAT_OK;
 }

@@ -62,6 +62,7 @@ struct GatherArgs {
     float* block; float* x_emb; float* lr_out;
     int B, T, L, F, D;
     float drop_p; unsigned long long seed; unsigned int stream;
+    const unsigned int* step;      // device step counter of the dropout streams (rng_step_ptr)
     int* err;
     // row-sharded tables (range partition, `vs` rows per rank): the flat parameter buffer of every rank is mapped
     // into this process (symmetric memory over NVLink / NVSwitch); peers[o] + emb_off is rank o's [vs, D] shard.
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(256) k_gather(GatherArgs a) {
         if (a.drop_p > 0.f) {
             const unsigned long long e0 = (unsigned long long)v * VW;
 #pragma unroll
-            for (int i = 0; i < VW; ++i) val[i] *= dropout_scale(a.seed, a.stream, e0 + i, a.drop_p, inv_keep);
+            for (int i = 0; i < VW; ++i) val[i] *= dropout_scale(a.seed, rng_stream_of_step(a.stream, a.step), e0 + i, a.drop_p, inv_keep);
         }
         vstore<VW>(a.block + v * VW, val);
     }
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(320, 4) k_gather_flat(GatherArgs a, int NC, in
     const bool drop = a.drop_p > 0.f;
     const float inv_keep = drop ? 1.0f / (1.0f - a.drop_p) : 1.0f;
     const uint32_t thr = dropout_threshold(a.drop_p);
-    const uint32_t key = dropout_key(a.seed, a.stream), hk0 = lowbias32(key);
+    const uint32_t key = dropout_key(a.seed, rng_stream_of_step(a.stream, a.step)), hk0 = lowbias32(key);
     const int row_begin = blockIdx.x * RB, row_end = min(nrows, row_begin + RB);
 
     for (int s0 = row_begin; s0 < row_end; s0 += SROWS) {
@@ -265,7 +266,8 @@ __global__ void __launch_bounds__(320, 4) k_gather_flat(GatherArgs a, int NC, in
 
 // in-place dropout backward on the block gradient (same mask as the gather); one Philox call per 8 elements
 __global__ void k_dropout_bwd(float* __restrict__ g, long long n, float p, unsigned long long seed,
-                              unsigned int stream) {
+                              unsigned int stream0, const unsigned int* __restrict__ step) {
+    const unsigned int stream = rng_stream_of_step(stream0, step);
     const float inv_keep = 1.0f / (1.0f - p);
     const uint32_t thr = dropout_threshold(p);
     const long long n8 = (n + 7) >> 3;
@@ -407,7 +409,7 @@ extern "C" int rat_gather_fwd_sharded(const float* const* W_peers, long long emb
 extern "C" int rat_dropout_bwd(float* grad, long long n, float p, unsigned long long seed, unsigned int rng_stream,
                                void* stream) {
     if (p <= 0.f) return RAT_OK;
-    k_dropout_bwd<<<grid_for((n + 7) / 8, 256), 256, 0, (cudaStream_t)stream>>>(grad, n, p, seed, rng_stream);
+    k_dropout_bwd<<<grid_for((n + 7) / 8, 256), 256, 0, (cudaStream_t)stream>>>(grad, n, p, seed, rng_stream, rng_step_ptr());
     RAT_CHECK_LAUNCH("k_dropout_bwd");
     return RAT_OK;
 }
