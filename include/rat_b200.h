@@ -81,7 +81,14 @@ int rat_gather_fwd_sharded(const float* const* W_peers, long long emb_off, long 
                            const int* col_vocab, const int* field_col0, const int* field_width, float* block,
                            float* x_emb, float* lr_out, int B, int T, int L, int F, int D, float drop_p,
                            unsigned long long seed, unsigned int rng_stream, int* err_flag, void* stream);
-/* backward of the embedding dropout: grad *= mask/(1-p), same philox mask as rat_gather_fwd */
+/* Dropout streams.  Every kernel with dropout derives its mask from (seed, rng_stream + 64 * step, element) where `step` is
+ * a DEVICE-resident counter owned by the library: nn.Dropout's "a new mask every training step" (RAT_m2.py:83,135,
+ * layers/deep.py:134) without a host-side value baked into the launch, so that a CUDA graph of the whole training step
+ * replays with fresh masks.  rat_rng_step_advance enqueues step += 1 (call it once at the start of a training step, inside
+ * the captured region); rat_rng_step_set enqueues step = value (tests, checkpoint resume). */
+int rat_rng_step_set(unsigned int value, void* stream);
+int rat_rng_step_advance(void* stream);
+/* backward of the embedding dropout: grad *= mask/(1-p), same mask as rat_gather_fwd */
 int rat_dropout_bwd(float* grad, long long n, float p, unsigned long long seed, unsigned int rng_stream,
                     void* stream);
 
@@ -89,6 +96,10 @@ int rat_dropout_bwd(float* grad, long long n, float p, unsigned long long seed, 
  * Transformers of RAT_m1 (models/RAT_m1.py:125-126) and, with the strides swapped, its backward scatter. */
 int rat_strided_copy(const float* src, float* dst, long long rows, int D, long long src_stride, long long dst_stride,
                      void* stream);
+/* dst [rows*group, D]: dst[r*group + 0] = src[r], every other row zero.  RAT_m2 consumes only token (t=0, n=0) of the
+ * encoder output (models/RAT_m2.py:138-140), so the last block's cross attention / FeedForward run on the field-token-0
+ * rows only; this scatters their gradient back into the full [B,T,N,D] block gradient (and replaces its memset). */
+int rat_expand_rows(const float* src, float* dst, long long rows, int D, int group, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * K2: fused RAT block (forward)

@@ -299,6 +299,23 @@ __global__ void k_strided_copy(const float* __restrict__ src, float* __restrict_
     }
 }
 
+// dst[(r*group + g)*D + d] = g == 0 ? src[r*D + d] : 0   (vectorised when D % 4 == 0): the gradient of the field-token-0 rows of
+// the last RAT block scattered back into the full [B,T,N,D] block gradient, which it also zero-fills (no separate memset)
+template <int VW>
+__global__ void k_expand_rows(const float* __restrict__ src, float* __restrict__ dst, long long rows, int DV, int group) {
+    const long long total = rows * group * DV;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / DV;
+        const int dv = (int)(i - row * DV);
+        const long long r = row / group;
+        float v[VW];
+#pragma unroll
+        for (int k = 0; k < VW; ++k) v[k] = 0.f;
+        if (row - r * group == 0) vload<VW>(src + (r * DV + dv) * VW, v);
+        vstore<VW>(dst + i * VW, v);
+    }
+}
+
 static int grid_for(long long total, int block) {
     long long g = (total + block - 1) / block;
     long long cap = (long long)num_sms() * 32;
@@ -387,7 +404,7 @@ extern "C" int rat_gather_fwd(const float* emb_W, const float* lr_W, const float
     RAT_REQUIRE(B > 0 && T > 0 && L > 0 && F > 0 && D > 0, "rat_gather_fwd: bad shape");
     RAT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "rat_gather_fwd: dropout p=%f", drop_p);
     GatherArgs a{emb_W, lr_W, label_W, ids, labels, col_off, col_vocab, field_col0, field_width,
-                 block, x_emb, lr_out, B, T, L, F, D, drop_p, seed, rng_stream, err_flag, nullptr, 0, 0, 1};
+                 block, x_emb, lr_out, B, T, L, F, D, drop_p, seed, rng_stream, rng_step_ptr(), err_flag, nullptr, 0, 0, 1};
     return launch_gather(a, (cudaStream_t)stream);
 }
 
@@ -401,7 +418,7 @@ extern "C" int rat_gather_fwd_sharded(const float* const* W_peers, long long emb
     RAT_REQUIRE(W_peers != nullptr && rows_per_shard > 0 && world > 0, "rat_gather_fwd_sharded: bad shard description");
     RAT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "rat_gather_fwd_sharded: dropout p=%f", drop_p);
     GatherArgs a{nullptr, nullptr, label_W, ids, labels, col_off, col_vocab,
-                 field_col0, field_width, block, x_emb, lr_out, B, T, L, F, D, drop_p, seed, rng_stream, err_flag,
+                 field_col0, field_width, block, x_emb, lr_out, B, T, L, F, D, drop_p, seed, rng_stream, rng_step_ptr(), err_flag,
                  W_peers, emb_off, lr_off, rows_per_shard};
     return launch_gather(a, (cudaStream_t)stream);
 }
@@ -411,6 +428,15 @@ extern "C" int rat_dropout_bwd(float* grad, long long n, float p, unsigned long 
     if (p <= 0.f) return RAT_OK;
     k_dropout_bwd<<<grid_for((n + 7) / 8, 256), 256, 0, (cudaStream_t)stream>>>(grad, n, p, seed, rng_stream, rng_step_ptr());
     RAT_CHECK_LAUNCH("k_dropout_bwd");
+    return RAT_OK;
+}
+
+extern "C" int rat_expand_rows(const float* src, float* dst, long long rows, int D, int group, void* stream) {
+    RAT_REQUIRE(rows > 0 && D > 0 && group > 0, "rat_expand_rows: bad shape");
+    const bool v4 = (D % 4) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+    if (v4) k_expand_rows<4><<<grid_for(rows * group * (D / 4), 256), 256, 0, (cudaStream_t)stream>>>(src, dst, rows, D / 4, group);
+    else k_expand_rows<1><<<grid_for(rows * group * D, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, rows, D, group);
+    RAT_CHECK_LAUNCH("k_expand_rows");
     return RAT_OK;
 }
 

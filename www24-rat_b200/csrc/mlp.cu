@@ -174,7 +174,9 @@ __global__ void k_bn_eval_stats(const float* __restrict__ running_mean, const fl
 __global__ void k_bn_act_fwd(const float* __restrict__ z, const float* __restrict__ mean,
                              const float* __restrict__ rstd, const float* __restrict__ gamma,
                              const float* __restrict__ beta, float* __restrict__ out, long long total, int C,
-                             float drop_p, unsigned long long seed, unsigned int stream) {
+                             float drop_p, unsigned long long seed, unsigned int stream0,
+                             const unsigned int* __restrict__ step) {
+    const unsigned int stream = rng_stream_of_step(stream0, step);
     const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -190,8 +192,10 @@ __global__ void k_bn_act_fwd(const float* __restrict__ z, const float* __restric
 __global__ void __launch_bounds__(256) k_bn_act_bwd_sums(const float* __restrict__ dout, const float* __restrict__ out,
                                                          const float* __restrict__ z, const float* __restrict__ mean,
                                                          const float* __restrict__ rstd, int Bn, int C, float drop_p,
-                                                         unsigned long long seed, unsigned int stream,
+                                                         unsigned long long seed, unsigned int stream0,
+                                                         const unsigned int* __restrict__ step,
                                                          double* __restrict__ sums) {
+    const unsigned int stream = rng_stream_of_step(stream0, step);
     __shared__ double s1[8][32], s2[8][32];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     const int rg = threadIdx.x >> 5;
@@ -222,8 +226,10 @@ __global__ void k_bn_act_bwd_apply(const float* __restrict__ dout, const float* 
                                    const float* __restrict__ rstd, const float* __restrict__ gamma,
                                    const double* __restrict__ sums, double count, float* __restrict__ dz,
                                    float* __restrict__ dgamma, float* __restrict__ dbeta, long long total, int C,
-                                   float drop_p, unsigned long long seed, unsigned int stream,
+                                   float drop_p, unsigned long long seed, unsigned int stream0,
+                                   const unsigned int* __restrict__ step,
                                    float* __restrict__ dz_amax, float param_grad_scale) {
+    const unsigned int stream = rng_stream_of_step(stream0, step);
     const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
     float amax = 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -493,7 +499,7 @@ extern "C" int rat_bn_act_fwd(const float* z, const float* mean, const float* rs
                               unsigned int rng_stream, void* stream) {
     const long long total = (long long)rows * C;
     k_bn_act_fwd<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(z, mean, rstd, gamma, beta, out, total, C, drop_p,
-                                                                   seed, rng_stream);
+                                                                   seed, rng_stream, rng_step_ptr());
     RAT_CHECK_LAUNCH("k_bn_act_fwd");
     return RAT_OK;
 }
@@ -505,7 +511,7 @@ extern "C" int rat_bn_act_bwd_sums(const float* dout, const float* out, const fl
     double* part = colred_scratch((size_t)ns * 2 * C);
     RAT_REQUIRE(part != nullptr, "rat_bn_act_bwd_sums: scratch allocation failed");
     k_bn_act_bwd_sums<<<dim3(ceil_div(C, 32), ns), 256, 0, (cudaStream_t)stream>>>(dout, out, z, mean, rstd, rows, C,
-                                                                                   drop_p, seed, rng_stream, part);
+                                                                                   drop_p, seed, rng_stream, rng_step_ptr(), part);
     RAT_CHECK_LAUNCH("k_bn_act_bwd_sums");
     k_colred_finalize<double><<<ceil_div(2 * C, 128), 128, 0, (cudaStream_t)stream>>>(part, ns, 2 * C, sums);
     RAT_CHECK_LAUNCH("k_colred_finalize");
@@ -520,7 +526,7 @@ extern "C" int rat_bn_act_bwd_apply(const float* dout, const float* out, const f
     const long long total = (long long)rows * C;
     k_bn_act_bwd_apply<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(dout, out, z, mean, rstd, gamma, sums, count,
                                                                          dz, dgamma, dbeta, total, C, drop_p, seed,
-                                                                         rng_stream, dz_amax, param_grad_scale);
+                                                                         rng_stream, rng_step_ptr(), dz_amax, param_grad_scale);
     RAT_CHECK_LAUNCH("k_bn_act_bwd_apply");
     return RAT_OK;
 }

@@ -207,6 +207,7 @@ struct SegArgs {
     int T, L, N, D, F, DS;
     FastDiv divT;
     float drop_p; unsigned long long seed; unsigned int stream;
+    const unsigned int* step;    // device step counter of the dropout streams (rng_step_ptr)
 };
 
 __device__ __forceinline__ float* seg_final_row(const SegArgs& a, unsigned int key) {
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(256) k_segment_scan(SegArgs a) {
     const bool drop = a.drop_p > 0.f;
     const float inv_keep = drop ? 1.0f / (1.0f - a.drop_p) : 1.0f;
     const uint32_t thr = dropout_threshold(a.drop_p);
-    const uint32_t dkey = dropout_key(a.seed, a.stream), hk0 = lowbias32(dkey);
+    const uint32_t dkey = dropout_key(a.seed, rng_stream_of_step(a.stream, a.step)), hk0 = lowbias32(dkey);
     const int DV = a.D / VW;
     const unsigned long long idx0 = e0 / VW;
     for (int v0 = 0; v0 < DV; v0 += SEG_G) {
@@ -582,7 +583,7 @@ extern "C" int rat_emb_scatter_reduce(const int* ids, const int* labels, const f
     const unsigned int* keys = (passes & 1) ? w.k1 : w.k0;
     const unsigned int* vals = (passes & 1) ? w.v1 : w.v0;
     SegArgs a{keys, vals, n, V + 3u, V, dblock, dxemb, dlogit, col_field, g_emb, g_lr, g_label, w.carryF, w.carryL,
-              w.carry2, w.counters, w.items, w.longs, w.done, T, L, F + 1, D, F, w.DS, make_fastdiv((uint32_t)T), drop_p, seed, rng_stream};
+              w.carry2, w.counters, w.items, w.longs, w.done, T, L, F + 1, D, F, w.DS, make_fastdiv((uint32_t)T), drop_p, seed, rng_stream, rng_step_ptr()};
     const int sgrid = (int)((w.nchunks + 7) / 8);
     if (D % 4 == 0) k_segment_scan<4><<<sgrid, 256, 0, st>>>(a);
     else if (D % 2 == 0) k_segment_scan<2><<<sgrid, 256, 0, st>>>(a);

@@ -340,6 +340,7 @@ class RatEngine:
         self.dist_group = None
         self._side = None
         self.graph_inference = True         # CUDA-graph replay of the eval forward (see forward_ids)
+        self.graph_training = True          # ... and of the whole training step (see train_step_ids)
         self._graphs: Dict[tuple, object] = {}
         self.amax = torch.zeros(256, dtype=torch.float32, device=self.device)
         self._amax_next = 0
@@ -375,7 +376,11 @@ class RatEngine:
         n_act = self._num_acts() if (training or s.model in ("RAT_m0", "RAT_m1")) else 3
         ws["acts"] = [torch.empty(B, T, N, D, **f32) for _ in range(n_act)]
         ws["acts_c"] = [torch.empty(B, T, D, **f32) for _ in range(n_act)] if s.model == "RAT_m1" else None
-        ws["enc_stride"] = T * D if s.model == "RAT_m1" else T * N * D
+        ws["enc_stride"] = T * D if s.model in ("RAT_m1", "RAT_m2") else T * N * D
+        # RAT_m2, last block: only token (t=0, n=0) of the encoder output is consumed (RAT_m2.py:138-140), so its cross
+        # attention runs on the B sequences of field token 0 and its FeedForward on those B*T rows (dead-token
+        # elimination; the reference computes all B*T*N rows and drops them)
+        ws["last_c"] = [torch.empty(B, T, D, **f32) for _ in range(3)] if s.model == "RAT_m2" else None
         units = list(s.dnn_hidden_units)
         ws["z"] = [torch.empty(B, u, **f32) for u in units]
         ws["h"] = [torch.empty(B, u, **f32) for u in units]
@@ -393,8 +398,8 @@ class RatEngine:
             ws["dact"] = torch.empty(B, T, N, D, **f32)
             ws["dact2"] = torch.empty(B, T, N, D, **f32) if s.model == "RAT_m3" else None
             ws["dlogit"] = torch.empty(B, **f32)
-            ws["dact_c"] = torch.empty(B, T, D, **f32) if s.model == "RAT_m1" else None
-            ws["denc"] = ws["dact_c"] if s.model == "RAT_m1" else ws["dact"]
+            ws["dact_c"] = torch.empty(B, T, D, **f32) if s.model in ("RAT_m1", "RAT_m2") else None
+            ws["denc"] = ws["dact_c"] if s.model in ("RAT_m1", "RAT_m2") else ws["dact"]
             ws["dxemb"] = torch.zeros(B, F * D, **f32)
             ws["dh"] = [torch.empty(B, u, **f32) for u in units]
             hh, dd = (max(1, int(H / 2)), (H * dh) // max(1, int(H / 2))) if s.model == "RAT_m3" else (H, dh)
@@ -466,6 +471,13 @@ class RatEngine:
                 else:
                     i0, i1, i2, i3 = cur, (cur + 1) % 3, (cur + 2) % 3, cur
                 self._attn(acts[i0], acts[i0], acts[i1], pre + "intra_attention.", 0, B, T, N)
+                if l == s.depth - 1:            # last block: field token 0 only (see _workspace)
+                    c = ws["last_c"]
+                    call("rat_strided_copy", acts[i1], c[0], B * T, s.embedding_dim, N * s.embedding_dim, s.embedding_dim,
+                         current_stream())
+                    self._attn(c[0], c[0], c[1], pre + "cross_attention.", 1, B, T, 1)
+                    self._ff(c[1], c[1], c[2], pre + "mlp.", B * T)
+                    return c[2]
                 self._attn(acts[i1], acts[i1], acts[i2], pre + "cross_attention.", 1, B, T, N)
                 self._ff(acts[i2], acts[i2], acts[i3], pre + "mlp.", rows)
                 cur = i3
@@ -559,7 +571,9 @@ class RatEngine:
         return self.world
 
     def _rng_stream(self, slot: int) -> int:
-        return (self.rng_step * 64 + slot) & 0xFFFFFFFF
+        """dropout stream of a call site; the training-step counter is device-resident (rat_rng_step_advance), so the
+        value passed to the kernels is step-independent and a CUDA graph of the step replays with fresh masks."""
+        return slot
 
     def forward_ids(self, ws, B, T, training=False, with_loss=False, inv_count=None):
         """ids/labels already in ws -> y_pred [B]; keeps activations in ws when training.
@@ -699,8 +713,16 @@ class RatEngine:
         if s.model == "RAT_m2":
             for l in reversed(range(s.depth)):
                 pre = f"encoder.encoder.{l}."
-                self._ff_bwd(ws, acts[3 * l + 2], d, d, d, pre + "mlp.", rows)
-                self._attn_bwd(ws, acts[3 * l + 1], d, d, d, pre + "cross_attention.", 1, B, T, N)
+                if l == s.depth - 1:            # last block ran on field token 0 only: dc [B,T,D] -> d[b,t,0,:], zeros elsewhere
+                    c, dc = ws["last_c"], ws["dact_c"]
+                    self._ff_bwd(ws, c[1], dc, dc, dc, pre + "mlp.", B * T)
+                    self._attn_bwd(ws, c[0], dc, dc, dc, pre + "cross_attention.", 1, B, T, 1)
+                    call("rat_expand_rows", dc, d, B * T, s.embedding_dim, N, current_stream())
+                    if dc.data_ptr() in self._amax_of:
+                        self._amax_of[d.data_ptr()] = self._amax_of[dc.data_ptr()]
+                else:
+                    self._ff_bwd(ws, acts[3 * l + 2], d, d, d, pre + "mlp.", rows)
+                    self._attn_bwd(ws, acts[3 * l + 1], d, d, d, pre + "cross_attention.", 1, B, T, N)
                 self._attn_bwd(ws, acts[3 * l], d, d, d, pre + "intra_attention.", 0, B, T, N)
             return d
         if s.model == "RAT_m3":
@@ -850,8 +872,38 @@ class RatEngine:
     def train_step_ids(self, ws, B, T):
         """one full training step on the ids/labels/y_true already in ws. Returns ws['loss'] (device):
         [sum BCE, mean BCE of the local shard]; opt_state[5] holds the regularisation loss."""
+        import rat_native as _rn
+        if (self.graph_training and self.store.shard is None and _rn._profile is None
+                and not torch.cuda.is_current_stream_capturing()):
+            key = ("train", B, T, int(query("rat_get_precision")), float(self.spec.max_gradient_norm))
+            entry = self._graphs.get(key)
+            if entry is None or entry[1] is not ws:      # first call (or a new workspace): eager, warms up lazy state
+                self._graphs[key] = ("warm", ws)
+            else:
+                if entry[0] == "warm":
+                    try:
+                        torch.cuda.synchronize()
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            self._train_step_impl(ws, B, T)
+                        entry = (g, ws)
+                    except Exception as exc:             # capture not possible here: stay eager for this key
+                        import logging
+                        logging.warning("CUDA-graph capture of the training step failed (%s); running eagerly", exc)
+                        torch.cuda.synchronize()
+                        entry = ("eager", ws)
+                    self._graphs[key] = entry
+                if entry[0] != "eager":
+                    entry[0].replay()
+                    return ws["loss"]
+        return self._train_step_impl(ws, B, T)
+
+    def _train_step_impl(self, ws, B, T):
+        st = current_stream()
+        call("rat_rng_step_advance", st)
         self.rng_step += 1
-        ws["dact"].zero_()
+        if self.spec.model != "RAT_m2":
+            ws["dact"].zero_()          # RAT_m2: written in full by rat_expand_rows (encode_backward)
         if ws.get("dact_c") is not None:
             ws["dact_c"].zero_()
         self.forward_ids(ws, B, T, training=True, inv_count=1.0 / (B * self.world))
