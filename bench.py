@@ -14,7 +14,10 @@ Printed JSON line (rank 0):
           pinned memory: H2D of every batch and a D2H read of the loss inside the timed region
   infer   the same two numbers for model.forward (eval mode)
   roofline / roofline_gather / roofline_adam / kernels   per-kernel CUDA-event timings vs measured peaks
-  cpu_baseline   the oracle (CPU restatement of the reference) on a bounded sample, N=1 only
+  cpu_baseline   the oracle (CPU restatement of the reference) at the SAME batch size on the host cores, N=1 only
+  secondary      the other BASELINE.json workloads measured in the same run (a few steps each): `strict` (TF32 arithmetic),
+                 `shapes` (movielens / tmall), `infer_sweep` (K x B inference sweep, configs[4]), `strong` (global batch
+                 4096 split over the N GPUs) and, when N > 1, `tmall_sharded` (row-sharded tables, configs[2])
 Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks; every step uses a
 different batch and the step's working set (>600 MB of activations) is larger than L2, so no L2 flush is needed.
 """
@@ -46,7 +49,8 @@ def parse():
     ap.add_argument("--topk", type=int, default=5)
     ap.add_argument("--pool-rows", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-batch", type=int, default=512)
+    ap.add_argument("--cpu-batch", type=int, default=4096, help="batch size of the CPU arms (default: the GPU arm's)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads (strict / shapes / sweep / strong / sharded)")
     ap.add_argument("--shard-tables", action="store_true",
                     help="row-shard the embedding / LR tables over the ranks (BASELINE configs[2]; needs --gpus > 1)")
     ap.add_argument("--vocab-scale", type=float, default=1.0, help="scale every vocabulary (scaled-vocab tmall variant)")
@@ -56,11 +60,24 @@ def parse():
     return ap.parse_args()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/
-# r01_final_backward_kernels_ncu_full.txt, r01_v3_gather_scatter_ncu_full.txt + the k_gather_flat capture quoted in
-# DESIGN.md), kkbox shape, B=4096, K=5.  The 126 MB L2 absorbs most of the 55 MB block writes, so DRAM traffic is BELOW
-# the algorithmic bytes for these kernels (no wasted re-reads).
-NCU_TRAFFIC = {"attn_bwd": 133.9e6, "gather": 18.4e6, "scatter": 74.3e6}
+def ncu_traffic(key, shape, B, K):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json, written by tools/ncu_traffic.py).  Every entry records the sha256 of the kernel's source
+    files at capture time and the workload it was taken on: a stale capture (source changed since) or another workload
+    reports null instead of a number that no longer belongs to the code."""
+    import hashlib
+    try:
+        db = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        e = db[key]
+        if (e["shape"], e["B"], e["K"]) != (shape, B, K):
+            return None
+        h = hashlib.sha256()
+        for f in e["sources"]:
+            h.update(open(os.path.join(ROOT, f), "rb").read())
+        return float(e["traffic_bytes"]) if h.hexdigest()[:16] == e["sha16"] else None
+    except Exception:
+        return None
+
 
 
 def peaks():
@@ -209,9 +226,13 @@ def run_ours(a):
     model.train()
     model._max_gradient_norm = 10.0
     sampler = ClockSampler(local) if rank == 0 else None
-    launches0 = rn.query("rat_launch_count")
-    t_train = timed(lambda i: model.train_step(dev_batches[i]), a.steps, a.warmup, dist)
-    launches = (rn.query("rat_launch_count") - launches0) * a.steps // n_steps_total
+    def launch_count():         # direct C-ABI launches + kernels replayed through the CUDA graph of the training step
+        return int(rn.query("rat_launch_count")) + int(model._engine.replayed_launches)
+    for i in range(a.warmup):                      # warm-up here so that the launch count brackets exactly the timed steps
+        model.train_step(dev_batches[i])
+    launches0 = launch_count()
+    t_train = timed(lambda i: model.train_step(dev_batches[a.warmup + i]), a.steps, 0, dist)
+    launches = launch_count() - launches0
     clocks = sampler.stop() if sampler else None
     model._engine.check_errors()
 
@@ -264,7 +285,7 @@ def run_ours(a):
     roofline = {"kernel": "k_attn_bwd_tc (+k_reduce_attn_tc)" if tc_mode else "k_attn_bwd (+k_reduce_attn)",
                 "bound": "tensor", "achieved": round(ach_tf, 3),
                 "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": round(ach_tf / pk["tf_sustained"], 5),
-                "traffic": NCU_TRAFFIC.get("attn_bwd") if tc_mode and S == "kkbox" and B == 4096 and K == 5 else None,
+                "traffic": ncu_traffic("attn_bwd", S, B, K) if tc_mode else None,
                 "peak_source": pk["src"] + " bf16 dense (sustained)", "avg_launch_ms": round(ab_ms, 4),
                 "flops_per_launch": attn_bwd_flops,
                 "hbm_view": {"bytes_per_launch": ab_bytes, "achieved_gbs": round(ab_bytes / (ab_ms * 1e-3) / 1e9, 1),
@@ -304,7 +325,7 @@ def run_ours(a):
             F, D, drop, eng.spec.seed, 7, eng.err_flag, st_))
     roofline_gather = {"kernel": "k_gather_flat" + (" (rows loaded from the owners' shards over NVLink peer pointers)" if sharded else ""), "bound": "hbm", "achieved": round(gb / (g_ms * 1e-3) / 1e9, 1),
                        "peak": pk["hbm"], "unit": "GB/s", "frac": round(gb / (g_ms * 1e-3) / 1e9 / pk["hbm"], 4),
-                       "traffic": NCU_TRAFFIC.get("gather") if S == "kkbox" and B == 4096 and K == 5 and not sharded else None,
+                       "traffic": None if sharded else ncu_traffic("gather", S, B, K),
                        "bytes_per_launch": gb, "peak_source": pk["src"],
                        "avg_launch_ms": round(g_ms, 4), "in_step_single_launch_ms": round(g_step_ms, 4)}
     # scatter: the critical-path call (segment scan + fix-ups; dropout backward fused).  Algorithmic bytes:
@@ -333,7 +354,7 @@ def run_ours(a):
     roofline_scatter = {"kernel": "rat_emb_scatter_reduce (k_segment_scan + k_fixup_items)", "bound": "hbm",
                         "achieved": round(sc_bytes / (sc_ms * 1e-3) / 1e9, 1), "peak": pk["hbm"], "unit": "GB/s",
                         "frac": round(sc_bytes / (sc_ms * 1e-3) / 1e9 / pk["hbm"], 4),
-                        "traffic": NCU_TRAFFIC.get("scatter") if S == "kkbox" and B == 4096 and K == 5 else None,
+                        "traffic": ncu_traffic("scatter", S, B, K),
                         "bytes_per_launch": sc_bytes, "peak_source": pk["src"], "avg_launch_ms": round(sc_ms, 4),
                         "in_step_single_call_ms": round(sc_step_ms, 4),
                         "plan_ms_side_stream": round(plan_ms, 4),
@@ -347,7 +368,15 @@ def run_ours(a):
                      "note": "W, G, M, V (P*32 B = 151 MB at kkbox) were just touched by the gradient-norm / scatter kernels and "
                              "largely sit in the 126 MB L2, so the effective rate can exceed the DRAM copy peak"}
 
+    # free the headline model's buffers before the secondary workloads
+    model._engine._ws.clear()
+    model._engine._graphs.clear()
+    del blocks, dev_batches, gen
+    torch.cuda.empty_cache()
+    secondary = {} if a.no_secondary else secondary_workloads(a, rank, world, local, dist)
     if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
         return
     gB = B * world
     line = {
@@ -381,6 +410,7 @@ def run_ours(a):
                               "train_samples_per_s": {"kkbox": 8800, "ml": 52000, "tmall": 3300}[S],
                               "infer_samples_per_s": {"kkbox": 37500, "ml": 110000, "tmall": 22900}[S]},
     }
+    line["secondary"] = secondary
     if world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(a, S, K)
     print(json.dumps(line), flush=True)
@@ -388,73 +418,199 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+def small_workload(shape, B, K, precision, rank, world, local, dist, steps=6, warmup=3, sharded=False, vocab_scale=1.0,
+                   pool_rows=262144, legs=("train", "infer")):
+    """train / inference samples/s of one secondary workload (device-resident inputs, CUDA events, max over ranks)."""
+    import rat_native as rn
+    from rat_native import shapes
+    from rat_native.engine import set_precision
+    from fuxictr.pytorch import models
+    from fuxictr.pytorch.data_generator import DeviceDataGenerator
+    set_precision(precision)
+    fm = shapes.make_feature_map(shape, vocab_scale=vocab_scale)
+    params = shapes.model_params(shape, K=K, gpu=local)
+    if sharded:
+        params["shard_embeddings"] = True
+    os.makedirs(os.path.join(params["model_root"], fm.dataset_id), exist_ok=True)
+    model = models.RAT_m2(fm, **params)
+    if world > 1:
+        eng = model._engine
+        dist.broadcast(eng.store.W[:eng.store.emb_off] if sharded else eng.store.W, 0)
+    pool = shapes.synthetic_array(fm.feature_specs, pool_rows, seed=77, pos_ratio=shapes.SHAPES[shape]["pos_ratio"])
+    nbr = shapes.synthetic_neighbours(pool_rows, pool_rows, K, seed=77)
+    gen = DeviceDataGenerator(pool, pool, nbr, batch_size=B * world, shuffle=True, device=f"cuda:{local}", seed=77, rank=rank,
+                              world=world, drop_last=True)
+    it = iter(gen)
+    batches = [next(it) for _ in range(min(len(gen), steps + warmup))]
+    out = {"shape": shape, "B_per_gpu": B, "K": K, "precision": precision, "n_gpus": world, "params": model.count_parameters()}
+    if "train" in legs:
+        model.train()
+        t = timed(lambda i: model.train_step(batches[i % len(batches)]), steps, warmup, dist)
+        model._engine.check_errors()
+        out["train_samples_per_s"] = round(steps * B * world / t, 1)
+        out["train_ms_per_step"] = round(t / steps * 1e3, 4)
+    if "infer" in legs:
+        model.eval()
+        with torch.no_grad():
+            t = timed(lambda i: model.forward(batches[i % len(batches)]), steps, warmup, dist)
+        out["infer_samples_per_s"] = round(steps * B * world / t, 1)
+        out["infer_ms_per_step"] = round(t / steps * 1e3, 4)
+    model._engine._ws.clear()
+    model._engine._graphs.clear()
+    del model, gen, batches
+    torch.cuda.empty_cache()
+    set_precision("fp16")
+    return out
+
+
+def secondary_workloads(a, rank, world, local, dist):
+    """the other BASELINE.json configs, measured with the same code in the same run (rank 0 keeps the results)."""
+    sec = {}
+    # configs[1] in strict arithmetic: TF32 tensor-core operands (mma.sync), everything else fp32
+    sec["strict"] = small_workload(a.shape, a.batch, a.topk, "tf32", rank, world, local, dist, steps=4, warmup=2, legs=("train",))
+    sec["strict"]["note"] = "same workload as the headline line with precision=tf32 (mma.sync TF32 operands, fp32 accumulate)"
+    # configs[0] / configs[2] shapes, replicated tables
+    sec["shapes"] = [small_workload(sh, a.batch, a.topk, a.precision, rank, world, local, dist) for sh in ("ml", "tmall")
+                     if sh != a.shape]
+    # strong scaling: the reference's global batch of 4096 split over the ranks
+    if world > 1 and a.batch % world == 0:
+        sec["strong"] = small_workload(a.shape, a.batch // world, a.topk, a.precision, rank, world, local, dist, steps=10, warmup=4,
+                                       legs=("train",))
+        sec["strong"]["scaling"] = "strong"
+        sec["strong"]["global_batch"] = a.batch
+    # configs[2]: tmall shape, embedding / LR tables row-sharded over the ranks (NVLink peer loads + row-gradient exchange)
+    if world > 1:
+        sec["tmall_sharded"] = small_workload("tmall", a.batch, a.topk, a.precision, rank, world, local, dist, sharded=True,
+                                              legs=("train",))
+        sec["tmall_sharded_x50"] = small_workload("tmall", a.batch, a.topk, a.precision, rank, world, local, dist, sharded=True,
+                                                  vocab_scale=50.0, legs=("train",))
+    # configs[4]: K x B inference sweep on this many GPUs (data-parallel replicas; B is per GPU)
+    sweep = []
+    for K in (1, 5, 16, 64):
+        for B in (256, 4096, 65536):
+            if B * (K + 1) * 14 * 40 * 4 * 3 > 60e9:
+                continue
+            r = small_workload(a.shape, B, K, a.precision, rank, world, local, dist, steps=3 if B >= 65536 else 10, warmup=3,
+                               pool_rows=max(262144, B * world), legs=("infer",))
+            sweep.append({"K": K, "B_per_gpu": B, "infer_samples_per_s": r["infer_samples_per_s"],
+                          "ms_per_batch": r["infer_ms_per_step"]})
+    sec["infer_sweep"] = {"shape": a.shape, "n_gpus": world, "precision": a.precision, "grid": sweep}
+    return sec
+
+
 # ----------------------------------------------------------------------------------------- CPU arms (oracle port)
+# The reference is pure Python / PyTorch and cannot travel to the GPU box (/root/reference does not exist there), so the CPU
+# arm is the oracle: the same torch-CPU fp32 arithmetic, pinned against the imported reference by tests/golden (BASELINE.md
+# section 2 protocol: pre-collated synthetic batches of the SAME batch size, all host threads and one thread, a training
+# step = zero_grad -> loss -> backward -> clip -> Adam, and an eval forward under no_grad; the retrieval-set assembly of
+# Dataset.__getitem__ + collate is timed separately).
 def _oracle_setup(S, K, Bc):
     from oracle import rat_oracle as O
     spec = O.shape_spec(S)
     params = O.init_params(spec, 0)
     bufs = O.init_buffers(spec)
     pool = O.synthetic_pool(spec, 20000, seed=1)
-    nbr = O.synthetic_neighbours(Bc * 4, 20000, K, seed=1)
+    nbr = O.synthetic_neighbours(Bc * 2, 20000, K, seed=1)
     return O, spec, params, bufs, pool, nbr
 
 
-def cpu_baseline(a, S, K):
-    """bounded sample of the same workload on the host cores: 2 warm-up steps, then oracle training steps at
-    B=cpu_batch (retrieval-set assembly included) for about 12 s of CPU work."""
-    Bc = a.cpu_batch
-    torch.set_num_threads(os.cpu_count() or 1)
-    O, spec, params, bufs, pool, nbr = _oracle_setup(S, K, Bc)
-    st = O.AdamState()
+def _cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
 
-    def step(i):
-        j = i % 4
+
+def _cpu_steps(O, spec, params, bufs, pool, nbr, Bc, threads, n_train, n_eval):
+    """samples/s of n_train training steps and n_eval eval forwards at batch Bc on `threads` host threads (1 warm-up each)."""
+    torch.set_num_threads(threads)
+    st = O.AdamState()
+    batches = []
+    t0 = time.perf_counter()
+    for j in range(2):
         X, y = O.assemble_batch(pool[j * Bc:(j + 1) * Bc], pool, nbr[j * Bc:(j + 1) * Bc], np.arange(Bc))
-        O.train_step(params, bufs, spec, st, torch.from_numpy(X), torch.from_numpy(y))
-    for i in range(2):
-        step(i)
-    n, t0 = 0, time.perf_counter()
-    while n < 3 or (time.perf_counter() - t0 < 12.0 and n < 400):
-        step(n + 2)
-        n += 1
+        batches.append((torch.from_numpy(X), torch.from_numpy(y)))
+    t_asm = (time.perf_counter() - t0) / 2
+    res = {"threads": threads, "batch": Bc, "assembly_samples_per_s": round(Bc / t_asm, 1)}
+    if n_train:
+        O.train_step(params, bufs, spec, st, *batches[0])
+        t0 = time.perf_counter()
+        for i in range(n_train):
+            O.train_step(params, bufs, spec, st, *batches[(i + 1) % 2])
+        res["train_samples_per_s"] = round(n_train * Bc / (time.perf_counter() - t0), 1)
+    if n_eval:
+        with torch.no_grad():
+            O.forward(params, bufs, spec, *batches[0], training=False)
+            t0 = time.perf_counter()
+            for i in range(n_eval):
+                O.forward(params, bufs, spec, *batches[(i + 1) % 2], training=False)
+            res["infer_samples_per_s"] = round(n_eval * Bc / (time.perf_counter() - t0), 1)
+    return res
+
+
+def cpu_baseline(a, S, K):
+    """the CPU arm on the GPU box's host cores, bounded to ~30 s: all threads at the GPU arm's batch size (train + eval), one
+    thread on a smaller batch (a 1-thread step at B=4096 alone takes 40 s on the kkbox shape)."""
+    Bc = a.cpu_batch
+    nthr = os.cpu_count() or 1
+    O, spec, params, bufs, pool, nbr = _oracle_setup(S, K, Bc)
+    t0 = time.perf_counter()
+    allt = _cpu_steps(O, spec, params, bufs, pool, nbr, Bc, nthr, 2, 2)
+    one = _cpu_steps(O, spec, params, bufs, pool, nbr, min(Bc, 256), 1, 1, 1)
+    torch.set_num_threads(nthr)
     t = time.perf_counter() - t0
-    return {"value": round(n * Bc / t, 1), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{n} timed oracle (torch-CPU fp32 restatement of the reference) training steps at B={Bc} "
-                      f"({t:.1f} s), {torch.get_num_threads()} threads, host cpu_count={os.cpu_count()}"}
+    return {"value": allt["train_samples_per_s"], "unit": "samples/s", "cores": nthr, "kind": "port",
+            "cpu_model": _cpu_model(), "torch": torch.__version__,
+            "sample": f"oracle (torch-CPU fp32 restatement of the reference, pinned by tests/golden) on {nthr} host threads: 2 timed "
+                      f"training steps + 2 timed eval forwards at B={Bc} (same batch size as the GPU arm), pre-collated batches; "
+                      f"1-thread figures at B={min(Bc, 256)}; {t:.0f} s of CPU work",
+            "all_threads": allt, "one_thread": one}
 
 
 def run_reference(a):
     """--impl reference: the reference algorithm on the host cores (the Python reference cannot travel to the GPU box;
-    the oracle port is the same torch-CPU arithmetic, pinned against it by tests/golden)."""
+    the oracle port is the same torch-CPU arithmetic, pinned against it by tests/golden), same workload / batch size."""
     if int(os.environ.get("RANK", 0)) != 0:
         return
     S, K, Bc = a.shape, a.topk, a.cpu_batch
-    torch.set_num_threads(os.cpu_count() or 1)
+    nthr = os.cpu_count() or 1
+    torch.set_num_threads(nthr)
     O, spec, params, bufs, pool, nbr = _oracle_setup(S, K, Bc)
     st = O.AdamState()
-    steps, warmup = max(1, min(a.steps, 200)), max(0, min(a.warmup, 20))
-
-    def step(i):
-        j = i % 4
+    # every step is one full batch of the GPU arm's workload (B=4096: 1.5 - 8 s of CPU work), so the step counts are
+    # bounded to keep the run within a few minutes
+    steps, warmup = max(1, min(a.steps, 6)), max(0, min(a.warmup, 1))
+    batches = []
+    for j in range(2):
         X, y = O.assemble_batch(pool[j * Bc:(j + 1) * Bc], pool, nbr[j * Bc:(j + 1) * Bc], np.arange(Bc))
-        O.train_step(params, bufs, spec, st, torch.from_numpy(X), torch.from_numpy(y))
+        batches.append((torch.from_numpy(X), torch.from_numpy(y)))
     for i in range(warmup):
-        step(i)
+        O.train_step(params, bufs, spec, st, *batches[i % 2])
     t0 = time.perf_counter()
     for i in range(steps):
-        step(warmup + i)
+        O.train_step(params, bufs, spec, st, *batches[(warmup + i) % 2])
     t = time.perf_counter() - t0
     v = round(steps * Bc / t, 1)
+    with torch.no_grad():
+        O.forward(params, bufs, spec, *batches[0], training=False)
+        t1 = time.perf_counter()
+        O.forward(params, bufs, spec, *batches[1], training=False)
+        v_inf = round(Bc / (time.perf_counter() - t1), 1)
     from rat_native import shapes
     cfg = shapes.SHAPES[S]
     line = {"impl": "reference", "metric": "RAT_m2 train samples/sec", "value": v, "unit": "samples/s",
             "n_gpus": a.gpus, "steps": steps, "warmup": warmup, "ms_per_step": round(t / steps * 1e3, 2),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"RAT_m2 {cfg['dataset_id']} shape, K={K}, B={a.batch}/GPU, train step (fwd+bwd+clip+Adam)",
-                       "cpu_sample": f"each CPU step is a bounded sample of that workload: B={Bc} samples, retrieval-set assembly "
-                                     f"included; fp32 torch-CPU oracle port on all host threads"},
-            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": f"{steps} oracle training steps at B={Bc} on {torch.get_num_threads()} host threads"},
+                       "cpu_sample": f"each CPU step is one batch of B={Bc} samples (the GPU arm's batch size) on all {nthr} host threads; "
+                                     f"step count bounded to {steps} (+{warmup} warm-up); fp32 torch-CPU oracle port of the reference"},
+            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": nthr, "kind": "port", "cpu_model": _cpu_model(),
+                             "sample": f"{steps} oracle training steps at B={Bc} on {nthr} host threads",
+                             "infer_samples_per_s": v_inf},
+            "infer": {"value": v_inf, "unit": "samples/s"},
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 

@@ -341,6 +341,8 @@ class RatEngine:
         self._side = None
         self.graph_inference = True         # CUDA-graph replay of the eval forward (see forward_ids)
         self.graph_training = True          # ... and of the whole training step (see train_step_ids)
+        self.replayed_launches = 0          # kernels of librat_b200.so launched through graph replays (rat_launch_count
+                                            # only sees direct C-ABI calls)
         self._graphs: Dict[tuple, object] = {}
         self.amax = torch.zeros(256, dtype=torch.float32, device=self.device)
         self._amax_next = 0
@@ -592,11 +594,13 @@ class RatEngine:
                 if entry[0] == "warm":
                     torch.cuda.synchronize()
                     g = torch.cuda.CUDAGraph()
+                    n0 = int(query("rat_launch_count"))
                     with torch.cuda.graph(g):
                         self._forward_ids_impl(ws, B, T, False, False, None)
-                    entry = (g, ws)                         # the graph keeps its workspace alive
+                    entry = (g, ws, int(query("rat_launch_count")) - n0)     # the graph keeps its workspace alive
                     self._graphs[key] = entry
                 entry[0].replay()
+                self.replayed_launches += entry[2]
                 return ws["y_pred"]
         return self._forward_ids_impl(ws, B, T, training, with_loss, inv_count)
 
@@ -884,17 +888,19 @@ class RatEngine:
                     try:
                         torch.cuda.synchronize()
                         g = torch.cuda.CUDAGraph()
+                        n0 = int(query("rat_launch_count"))
                         with torch.cuda.graph(g):
                             self._train_step_impl(ws, B, T)
-                        entry = (g, ws)
+                        entry = (g, ws, int(query("rat_launch_count")) - n0)
                     except Exception as exc:             # capture not possible here: stay eager for this key
                         import logging
                         logging.warning("CUDA-graph capture of the training step failed (%s); running eagerly", exc)
                         torch.cuda.synchronize()
-                        entry = ("eager", ws)
+                        entry = ("eager", ws, 0)
                     self._graphs[key] = entry
                 if entry[0] != "eager":
                     entry[0].replay()
+                    self.replayed_launches += entry[2]
                     return ws["loss"]
         return self._train_step_impl(ws, B, T)
 
