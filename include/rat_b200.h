@@ -81,6 +81,15 @@ int rat_gather_fwd_sharded(const float* const* W_peers, long long emb_off, long 
                            const int* col_vocab, const int* field_col0, const int* field_width, float* block,
                            float* x_emb, float* lr_out, int B, int T, int L, int F, int D, float drop_p,
                            unsigned long long seed, unsigned int rng_stream, int* err_flag, void* stream);
+/* One-shot all-reduce (SUM) of a small float64 vector over NVLink peer memory: the data-parallel hook for the raw BatchNorm
+ * sums of MLP_Layer (layers/deep.py:128-135 at the GLOBAL batch) and the shard-norm partials.  peer_bufs: device array of
+ * `world` pointers to the ranks' symmetric buffers (rat_oneshot_workspace_bytes each, zero-initialised once); every rank
+ * must enqueue the call the same number of times.  in == out is allowed.  No host value changes between calls, so the call
+ * captures into a CUDA graph. */
+size_t rat_oneshot_workspace_bytes(int world);
+int rat_oneshot_allreduce_f64(const void* const* peer_bufs, int rank, int world, const double* in, int n, double* out,
+                              void* stream);
+
 /* Dropout streams.  Every kernel with dropout derives its mask from (seed, rng_stream + 64 * step, element) where `step` is
  * a DEVICE-resident counter owned by the library: nn.Dropout's "a new mask every training step" (RAT_m2.py:83,135,
  * layers/deep.py:134) without a host-side value baked into the launch, so that a CUDA graph of the whole training step
@@ -219,6 +228,20 @@ int rat_emb_scatter_reduce(const int* ids, const int* labels, const float* dbloc
                            const int* col_field, float* g_emb, float* g_lr, float* g_label, int B, int T, int L, int F,
                            int D, long long V_total, float drop_p, unsigned long long seed, unsigned int rng_stream,
                            int planned, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Row-sharded tables (all-to-all #3; the tables are the nn.Embedding's of layers/embedding.py:79-100 and
+ * layers/shallow.py:31): after rat_emb_scatter_reduce has written this rank's reduced rows into a dense scratch indexed by
+ * GLOBAL row (g_emb_full [world*rows_per_shard, D], g_lr_full), rat_shard_send_rows stores every touched row once into its
+ * owner's receive buffer over NVLink (recv_peers: device array of the ranks' symmetric receive buffers,
+ * rat_shard_recv_bytes each; `counts`: `world` zero-initialised device counters) and clears it in the scratch.  After a
+ * cross-rank barrier rat_shard_apply_rows adds the received records into the local shard's gradient, source ranks in rank
+ * order (deterministic).  Traffic is proportional to the batch (<= B*T*L rows), not to the vocabulary. */
+size_t rat_shard_recv_bytes(int B, int T, int L, int D, int world);
+int rat_shard_send_rows(void* workspace, size_t workspace_bytes, int B, int T, int L, int F, int D, long long V_total,
+                        int rows_per_shard, int world, int rank, float* g_emb_full, float* g_lr_full,
+                        const void* const* recv_peers, unsigned int* counts, int* err_flag, void* stream);
+int rat_shard_apply_rows(const void* recv_local, int B, int T, int L, int D, int world, int rank, int rows_per_shard,
+                         float* g_emb_local, float* g_lr_local, int* err_flag, void* stream);
 /* the stable LSD radix sort used above, exposed for tests: sorts (keys, vals) by the low `bits` bits of keys.
  * hist: scratch of 256*ceil(n/2048) uint32.  *result_in_tmp = 1 if the sorted data ended in the tmp buffers. */
 int rat_radix_sort_pairs(unsigned int* keys, unsigned int* vals, unsigned int* keys_tmp, unsigned int* vals_tmp,

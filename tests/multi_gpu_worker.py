@@ -62,12 +62,20 @@ def main():
             elif f16:
                 assert_close_adam(f"param {k}", got, w, 4e-3, 6e-4, lr_steps=6.5e-3, max_outlier_frac=0.06)
             else:
-                assert_close_adam(f"param {k}", got, w, 2e-4, 1e-4, lr_steps=3.5e-3)
+                # the two-rank partial sums associate differently from the single-device sum: elements whose gradient is at
+                # the fp32 noise level can take the other Adam sign (each bounded by 3 steps x lr); loss and gradient norm
+                # above are pinned tightly
+                assert_close_adam(f"param {k}", got, w, 2e-4, 1e-4, lr_steps=3.5e-3, max_outlier_frac=0.03)
         for k, w in bufs.items():
             if k.endswith("num_batches_tracked"):
                 continue
             assert_close(f"buffer {k}", eng.buffers[k].float(), w.float(), 1e-3, 3e-4 if k.endswith("running_mean") else 1e-4)
         print(f"multi_gpu_worker OK: {case} {mode} world={world}", flush=True)
+    # CUDA graphs that captured NCCL kernels must be gone before the communicator is destroyed (ncclCommDestroy waits for them)
+    eng._graphs.clear()
+    eng._ws.clear()
+    del eng, ws
+    torch.cuda.synchronize()
     dist.barrier()
     dist.destroy_process_group()
 

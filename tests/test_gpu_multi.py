@@ -17,7 +17,7 @@ def _run(case, mode, nproc=2):
     port = 29600 + (os.getpid() % 1000)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "multi_gpu_worker.py"), case, mode]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert r.returncode == 0 and "multi_gpu_worker OK" in r.stdout, (r.stdout[-3000:], r.stderr[-3000:])
 
 

@@ -30,47 +30,49 @@ struct GemmTcArgs {
     int splits;
 };
 
-// stage a [ROWS x 8*CHUNKS] fp32 source tile (row stride ld) as fp16, chunk-major; rows/cols outside the matrix -> 0
-__device__ __forceinline__ void gemm_stage_tile(const float* __restrict__ src, int ld, int row0, int col0, int rows_total,
-                                                int cols_total, int ROWS, int CHUNKS, unsigned char* __restrict__ dst,
-                                                bool vec_ok, float mul = 1.0f) {
+// Staging of a [ROWS x 8*CHUNKS] fp32 source tile (row stride ld) as fp16, chunk-major; rows/cols outside the matrix -> 0.
+// Split in two halves so that the global loads of stage s+1 are in flight while stage s is converted, stored and multiplied:
+//   gemm_tile_load  : this thread's <= U items (8 floats each) -> registers
+//   gemm_tile_store : registers -> fp16 -> shared memory
+template <int U>
+__device__ __forceinline__ void gemm_tile_load(const float* __restrict__ src, int ld, int row0, int col0, int rows_total,
+                                               int cols_total, int ROWS, int CHUNKS, bool vec_ok, float (&v)[U][8]) {
     const int items = ROWS * CHUNKS;
-    constexpr int U = 4;                                   // items in flight per thread: all loads first, then the stores
-    for (int it0 = threadIdx.x; it0 < items; it0 += U * GT_THREADS) {
-        float v[U][8];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int it = it0 + u * GT_THREADS;
-            if (it >= items) break;
-            const int r = it % ROWS, c = it / ROWS;
-            const int gr = row0 + r, gc = col0 + c * 8;
-            if (gr < rows_total && gc + 8 <= cols_total && vec_ok) {
-                const float4 t0 = __ldg(reinterpret_cast<const float4*>(src + (size_t)gr * ld + gc));
-                const float4 t1 = __ldg(reinterpret_cast<const float4*>(src + (size_t)gr * ld + gc + 4));
-                v[u][0] = t0.x; v[u][1] = t0.y; v[u][2] = t0.z; v[u][3] = t0.w;
-                v[u][4] = t1.x; v[u][5] = t1.y; v[u][6] = t1.z; v[u][7] = t1.w;
-            } else {
+    for (int u = 0; u < U; ++u) {
+        const int it = threadIdx.x + u * GT_THREADS;
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    v[u][k] = (gr < rows_total && gc + k < cols_total) ? __ldg(src + (size_t)gr * ld + gc + k) : 0.f;
-            }
-        }
+        for (int k = 0; k < 8; ++k) v[u][k] = 0.f;
+        if (it >= items) continue;
+        const int r = it % ROWS, c = it / ROWS;
+        const int gr = row0 + r, gc = col0 + c * 8;
+        if (gr < rows_total && gc + 8 <= cols_total && vec_ok) {
+            const float4 t0 = __ldg(reinterpret_cast<const float4*>(src + (size_t)gr * ld + gc));
+            const float4 t1 = __ldg(reinterpret_cast<const float4*>(src + (size_t)gr * ld + gc + 4));
+            v[u][0] = t0.x; v[u][1] = t0.y; v[u][2] = t0.z; v[u][3] = t0.w;
+            v[u][4] = t1.x; v[u][5] = t1.y; v[u][6] = t1.z; v[u][7] = t1.w;
+        } else if (gr < rows_total) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int it = it0 + u * GT_THREADS;
-            if (it >= items) break;
-            const int r = it % ROWS, c = it / ROWS;
-            if (mul != 1.0f) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) v[u][k] *= mul;
-            }
-            sts128(dst + tc5::kmajor_off(r, c, ROWS), pack_h2(v[u][0], v[u][1]), pack_h2(v[u][2], v[u][3]),
-                   pack_h2(v[u][4], v[u][5]), pack_h2(v[u][6], v[u][7]));
+            for (int k = 0; k < 8; ++k)
+                if (gc + k < cols_total) v[u][k] = __ldg(src + (size_t)gr * ld + gc + k);
         }
     }
 }
+template <int U>
+__device__ __forceinline__ void gemm_tile_store(const float (&v)[U][8], int ROWS, int CHUNKS, unsigned char* __restrict__ dst,
+                                                float mul) {
+    const int items = ROWS * CHUNKS;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int it = threadIdx.x + u * GT_THREADS;
+        if (it >= items) continue;
+        const int r = it % ROWS, c = it / ROWS;
+        sts128(dst + tc5::kmajor_off(r, c, ROWS), pack_h2(v[u][0] * mul, v[u][1] * mul), pack_h2(v[u][2] * mul, v[u][3] * mul),
+               pack_h2(v[u][4] * mul, v[u][5] * mul), pack_h2(v[u][6] * mul, v[u][7] * mul));
+    }
+}
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int UB>
 __global__ void __launch_bounds__(GT_THREADS) k_gemm_tc(GemmTcArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar[2];
@@ -84,7 +86,8 @@ __global__ void __launch_bounds__(GT_THREADS) k_gemm_tc(GemmTcArgs a) {
     unsigned char* Bbuf[2] = {smem_raw + a_bytes, smem_raw + 2 * a_bytes + b_bytes};
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) { tc5::mbar_init(&mbar[0], 1); tc5::mbar_init(&mbar[1], 1); tc5::fence_mbar_init(); }
-    if (warp == 0) tc5::tmem_alloc(&tmem_base_s, 256);
+    const uint32_t tcols = BN <= 32 ? 32u : BN <= 64 ? 64u : BN <= 128 ? 128u : 256u;    // several CTAs share an SM's 512 columns
+    if (warp == 0) tc5::tmem_alloc(&tmem_base_s, tcols);
     tc5::fence_before_sync();
     __syncthreads();
     tc5::fence_after_sync();
@@ -94,14 +97,26 @@ __global__ void __launch_bounds__(GT_THREADS) k_gemm_tc(GemmTcArgs a) {
     const bool a_vec = (a.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0);
     const bool b_vec = (a.ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.B) & 15) == 0);
 
+    // A tile: K-major -> rows = m (128), cols = k (64) ; MN-major -> rows = k (64), cols = m (128): 1024 items = 4 per thread;
+    // B tile: BN x 64 -> <= 2048 items = 8 per thread (BN <= 256), 2 when BN <= 64
+    constexpr int UA = TILE_M * (GT_KB / 8) / GT_THREADS;
+    float ra[UA][8], rb[UB][8];
+    auto load_stage = [&](int s) {
+        const int k0 = kbeg + s * GT_KB;
+        if (!A_MN) gemm_tile_load<UA>(a.A, a.lda, m0, k0, a.M, kend, TILE_M, GT_KB / 8, a_vec && (k0 % 4 == 0), ra);
+        else gemm_tile_load<UA>(a.A, a.lda, k0, m0, kend, a.M, GT_KB, TILE_M / 8, a_vec, ra);
+        if (!B_MN) gemm_tile_load<UB>(a.B, a.ldb, n0, k0, a.N, kend, BN, GT_KB / 8, b_vec && (k0 % 4 == 0), rb);
+        else gemm_tile_load<UB>(a.B, a.ldb, k0, n0, kend, a.N, GT_KB, BN / 8, b_vec && (n0 % 4 == 0), rb);
+    };
+    if (nst > 0) load_stage(0);
     for (int s = 0; s < nst; ++s) {
-        const int buf = s & 1, k0 = kbeg + s * GT_KB;
+        const int buf = s & 1;
         if (s >= 2) tc5::mbar_wait(&mbar[buf], ((s >> 1) - 1) & 1);      // the MMAs that read this buffer are done
-        // A tile: K-major -> rows = m (128), cols = k (64) ; MN-major -> rows = k (64), cols = m (128)
-        if (!A_MN) gemm_stage_tile(a.A, a.lda, m0, k0, a.M, kend, TILE_M, GT_KB / 8, Abuf[buf], a_vec && (k0 % 4 == 0), a_scale);
-        else gemm_stage_tile(a.A, a.lda, k0, m0, kend, a.M, GT_KB, TILE_M / 8, Abuf[buf], a_vec, a_scale);
-        if (!B_MN) gemm_stage_tile(a.B, a.ldb, n0, k0, a.N, kend, BN, GT_KB / 8, Bbuf[buf], b_vec && (k0 % 4 == 0));
-        else gemm_stage_tile(a.B, a.ldb, k0, n0, kend, a.N, GT_KB, BN / 8, Bbuf[buf], b_vec && (n0 % 4 == 0));
+        if (!A_MN) gemm_tile_store<UA>(ra, TILE_M, GT_KB / 8, Abuf[buf], a_scale);
+        else gemm_tile_store<UA>(ra, GT_KB, TILE_M / 8, Abuf[buf], a_scale);
+        if (!B_MN) gemm_tile_store<UB>(rb, BN, GT_KB / 8, Bbuf[buf], 1.0f);
+        else gemm_tile_store<UB>(rb, GT_KB, BN / 8, Bbuf[buf], 1.0f);
+        if (s + 1 < nst) load_stage(s + 1);        // in flight under this stage's barrier, MMA issue and the next buffer wait
         tc5::fence_proxy_async();
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -155,7 +170,7 @@ __global__ void __launch_bounds__(GT_THREADS) k_gemm_tc(GemmTcArgs a) {
     }
     tc5::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc5::tmem_dealloc(tmem_base_s, 256);
+    if (warp == 0) tc5::tmem_dealloc(tmem_base_s, tcols);
 }
 
 struct GemmTcPlan { int BN, n_tiles, m_tiles, splits, kchunk; size_t smem; };
@@ -163,16 +178,17 @@ struct GemmTcPlan { int BN, n_tiles, m_tiles, splits, kchunk; size_t smem; };
 static bool gemm_tc_plan(int M, int N, int K, size_t workspace_bytes, GemmTcPlan* p) {
     if (M < 64 || N < 16 || K < 64) return false;
     p->m_tiles = ceil_div(M, TILE_M);
-    // narrow output tiles until every SM has a CTA (two CTAs fit per SM: 256 TMEM columns and < 100 KB smem each);
-    // the A tile re-reads of the extra column tiles hit L2
+    // narrow output tiles until every SM has TWO CTAs (each is a short latency chain of K/64 load -> convert -> MMA stages;
+    // a second resident CTA fills the first one's waits; TMEM is allocated per CTA as the next power of two >= BN); the
+    // A tile re-reads of the extra column tiles hit L2
     p->n_tiles = (N + 255) / 256;
-    if (K < 1024) p->n_tiles = std::max(p->n_tiles, std::min(ceil_div(N, 64), ceil_div(num_sms(), p->m_tiles)));   // long K: split-K instead
+    if (K < 1024) p->n_tiles = std::max(p->n_tiles, std::min(ceil_div(N, 32), ceil_div(2 * num_sms(), p->m_tiles)));   // long K: split-K instead
     p->BN = round_up(ceil_div(N, p->n_tiles), 16);
     p->n_tiles = ceil_div(N, p->BN);
     const int tiles = p->n_tiles * p->m_tiles;
     int splits = 1;
     if (tiles * 2 <= num_sms() && K >= 1024) {
-        splits = std::min(16, num_sms() / tiles);
+        splits = std::min(32, 2 * num_sms() / tiles);
         while (splits > 1 && K / splits < 256) --splits;
         const size_t per = (size_t)M * N * sizeof(float);
         while (splits > 1 && (size_t)splits * per > workspace_bytes) --splits;
@@ -193,18 +209,25 @@ size_t gemm_tc_workspace_bytes(int M, int N, int K) {
     return p.splits > 1 ? (size_t)p.splits * M * N * sizeof(float) : 0;
 }
 
-template <bool A_MN, bool B_MN>
-static int launch_gemm_tc(const GemmTcArgs& a, const GemmTcPlan& p, cudaStream_t st) {
+template <bool A_MN, bool B_MN, int UB>
+static int launch_gemm_tc_u(const GemmTcArgs& a, const GemmTcPlan& p, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<A_MN, B_MN, UB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_gemm_tc)");
         attr_set = true;
     }
     dim3 grid(p.n_tiles, p.m_tiles, p.splits);
-    k_gemm_tc<A_MN, B_MN><<<grid, GT_THREADS, p.smem, st>>>(a);
+    k_gemm_tc<A_MN, B_MN, UB><<<grid, GT_THREADS, p.smem, st>>>(a);
     RAT_CHECK_LAUNCH("k_gemm_tc");
     return RAT_OK;
+}
+template <bool A_MN, bool B_MN>
+static int launch_gemm_tc(const GemmTcArgs& a, const GemmTcPlan& p, cudaStream_t st) {
+    // B tile items per thread: BN * 8 / 256
+    if (p.BN <= 64) return launch_gemm_tc_u<A_MN, B_MN, 2>(a, p, st);
+    if (p.BN <= 128) return launch_gemm_tc_u<A_MN, B_MN, 4>(a, p, st);
+    return launch_gemm_tc_u<A_MN, B_MN, 8>(a, p, st);
 }
 
 // returns RAT_OK if launched (C, or `splits` partials in workspace with *splits_out > 1), 1 if not covered

@@ -595,6 +595,120 @@ extern "C" int rat_emb_scatter_reduce(const int* ids, const int* labels, const f
     return RAT_OK;
 }
 
+// ---- row-sharded tables: sparse exchange of the reduced row gradients (all-to-all #3) ---------------------
+// After the segment reduce every rank holds one reduced row per table row its local batch touched, in a dense scratch
+// indexed by GLOBAL row.  Each touched row travels once, straight into its owner's receive buffer over NVLink (peer
+// stores), instead of a dense reduce-scatter over the whole row space: traffic is proportional to the batch, not to V.
+//   receive buffer of an owner: `world` segments; segment r (written by rank r): [0] uint32 count, records from byte 16:
+//   {uint32 key, float lr, float row[D]} padded to DS2 = round_up(D + 2, 4) floats.
+// Within one segment keys are unique (a rank sends a row once), so the owner can apply a segment fully in parallel; the
+// segments are applied one after the other in rank order => the sum over ranks has a fixed association (deterministic).
+namespace rat {
+struct ShardSendArgs {
+    const unsigned int* keys; long long n; unsigned int V; int rows_per_shard, world, rank, D, DS2;
+    float* g_emb_full; float* g_lr_full;
+    unsigned char* const* recv_peers; long long seg_bytes; unsigned int cap;
+    unsigned int* counts;        // [world] local counters (zeroed by the caller's previous k_shard_counts)
+    int* err;
+};
+__global__ void __launch_bounds__(256) k_shard_send_rows(ShardSendArgs a) {
+    const int lane = threadIdx.x & 31;
+    const long long p0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
+    if (p0 >= a.n) return;
+    const long long p = p0 + lane;
+    const unsigned int key = p < a.n ? a.keys[p] : 0xffffffffu;
+    const unsigned int prev = p > 0 && p < a.n ? a.keys[p - 1] : 0xffffffffu;
+    const bool head = p < a.n && key < a.V && (p == 0 || key != prev);
+    unsigned int hm = __ballot_sync(0xffffffffu, head);
+    while (hm) {
+        const int src = __ffs(hm) - 1;
+        hm &= hm - 1;
+        const unsigned int k = __shfl_sync(0xffffffffu, key, src);
+        const int owner = (int)(k / (unsigned int)a.rows_per_shard);
+        unsigned int idx = 0;
+        if (lane == 0) idx = atomicAdd(&a.counts[owner], 1u);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        float* row = a.g_emb_full + (size_t)k * a.D;
+        if (idx >= a.cap) { if (lane == 0 && a.err) atomicOr(a.err, 8); continue; }
+        float* rec = reinterpret_cast<float*>(a.recv_peers[owner] + (size_t)a.rank * a.seg_bytes + 16) + (size_t)idx * a.DS2;
+        for (int d = lane; d < a.D; d += 32) { rec[2 + d] = row[d]; row[d] = 0.f; }
+        if (lane == 0) {
+            reinterpret_cast<unsigned int*>(rec)[0] = k;
+            rec[1] = a.g_lr_full ? a.g_lr_full[k] : 0.f;
+            if (a.g_lr_full) a.g_lr_full[k] = 0.f;
+        }
+    }
+}
+// publish the per-owner record counts into the owners' segment headers and clear the local counters
+__global__ void k_shard_counts(unsigned int* counts, unsigned char* const* recv_peers, long long seg_bytes, int rank, int world) {
+    const int o = threadIdx.x;
+    if (o < world) {
+        *reinterpret_cast<unsigned int*>(recv_peers[o] + (size_t)rank * seg_bytes) = counts[o];
+        counts[o] = 0u;
+    }
+}
+// owner side: g_local[key - row0] += record, one warp per record
+__global__ void __launch_bounds__(256) k_shard_apply_rows(const unsigned char* __restrict__ seg, int D, int DS2, unsigned int row0,
+                                                          int rows_per_shard, float* __restrict__ g_emb, float* __restrict__ g_lr,
+                                                          int* err) {
+    const unsigned int count = *reinterpret_cast<const unsigned int*>(seg);
+    const float* recs = reinterpret_cast<const float*>(seg + 16);
+    const int lane = threadIdx.x & 31;
+    const unsigned int nw = gridDim.x * (blockDim.x >> 5);
+    for (unsigned int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < count; i += nw) {
+        const float* rec = recs + (size_t)i * DS2;
+        const unsigned int key = reinterpret_cast<const unsigned int*>(rec)[0];
+        const unsigned int r = key - row0;
+        if (r >= (unsigned int)rows_per_shard) { if (lane == 0 && err) atomicOr(err, 16); continue; }
+        for (int d = lane; d < D; d += 32) g_emb[(size_t)r * D + d] += rec[2 + d];
+        if (lane == 0 && g_lr) g_lr[r] += rec[1];
+    }
+}
+}  // namespace rat
+
+extern "C" size_t rat_shard_recv_bytes(int B, int T, int L, int D, int world) {
+    const size_t cap = (size_t)B * T * (L + 1);
+    const size_t seg = 16 + cap * (size_t)round_up(D + 2, 4) * sizeof(float);
+    return (size_t)world * ((seg + 127) / 128 * 128);
+}
+
+extern "C" int rat_shard_send_rows(void* workspace, size_t workspace_bytes, int B, int T, int L, int F, int D, long long V_total,
+                                   int rows_per_shard, int world, int rank, float* g_emb_full, float* g_lr_full,
+                                   const void* const* recv_peers, unsigned int* counts, int* err_flag, void* stream) {
+    int rc = scatter_check(B, T, L, F, D, V_total, workspace, workspace_bytes, "rat_shard_send_rows");
+    if (rc != RAT_OK) return rc;
+    RAT_REQUIRE(world >= 1 && world <= 1024 && rank >= 0 && rank < world && rows_per_shard > 0 && recv_peers && counts,
+                "rat_shard_send_rows: bad shard description");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n = (long long)B * T * (L + 1);
+    ScatterLayout w = scatter_layout(workspace, n, D);
+    const unsigned int V = (unsigned int)V_total;
+    const int passes = (key_bits(V + 3u) + 7) / 8;
+    const unsigned int* keys = (passes & 1) ? w.k1 : w.k0;
+    const long long seg_bytes = (long long)(rat_shard_recv_bytes(B, T, L, D, world) / world);
+    ShardSendArgs a{keys, n, V, rows_per_shard, world, rank, D, round_up(D + 2, 4), g_emb_full, g_lr_full,
+                    (unsigned char* const*)recv_peers, seg_bytes, (unsigned int)n, counts, err_flag};
+    k_shard_send_rows<<<(int)((w.nchunks + 7) / 8), 256, 0, st>>>(a);
+    RAT_CHECK_LAUNCH("k_shard_send_rows");
+    k_shard_counts<<<1, 1024, 0, st>>>(counts, (unsigned char* const*)recv_peers, seg_bytes, rank, world);
+    RAT_CHECK_LAUNCH("k_shard_counts");
+    return RAT_OK;
+}
+
+extern "C" int rat_shard_apply_rows(const void* recv_local, int B, int T, int L, int D, int world, int rank, int rows_per_shard,
+                                    float* g_emb_local, float* g_lr_local, int* err_flag, void* stream) {
+    RAT_REQUIRE(recv_local && world >= 1 && rows_per_shard > 0, "rat_shard_apply_rows: bad arguments");
+    const size_t seg_bytes = rat_shard_recv_bytes(B, T, L, D, world) / world;
+    const int grid = num_sms() * 4;
+    for (int src = 0; src < world; ++src) {           // rank order: the sum over ranks has one fixed association
+        k_shard_apply_rows<<<grid, 256, 0, (cudaStream_t)stream>>>((const unsigned char*)recv_local + (size_t)src * seg_bytes, D,
+                                                                   round_up(D + 2, 4), (unsigned int)rank * (unsigned int)rows_per_shard,
+                                                                   rows_per_shard, g_emb_local, g_lr_local, err_flag);
+        RAT_CHECK_LAUNCH("k_shard_apply_rows");
+    }
+    return RAT_OK;
+}
+
 // exposed for tests: stable sort of (key,val) pairs with the same kernels
 extern "C" int rat_radix_sort_pairs(unsigned int* keys, unsigned int* vals, unsigned int* keys_tmp,
                                     unsigned int* vals_tmp, unsigned int* hist, long long n, int bits,

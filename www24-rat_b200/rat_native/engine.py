@@ -348,12 +348,36 @@ class RatEngine:
         self._amax_next = 0
         self._amax_of = {}
         self._amax_on = False
+        self.rank = 0
+        self._os_peers = None               # one-shot all-reduce over NVLink peer memory (csrc/collective.cu)
         try:
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized():
                 self.world = dist.get_world_size()
+                self.rank = dist.get_rank()
         except Exception:
             pass
+        if self.world > 1:
+            self._init_oneshot()
+
+    def _init_oneshot(self):
+        """symmetric buffer for the small-message all-reduce (raw BatchNorm sums, shard-norm partials); NCCL stays the
+        fallback when symmetric memory is not available."""
+        import torch.distributed as dist
+        try:
+            import torch.distributed._symmetric_memory as symm
+            n = (int(query("rat_oneshot_workspace_bytes", self.world)) + 3) // 4
+            buf = symm.empty(n, dtype=torch.int32, device=self.device)
+            buf.zero_()
+            handle = symm.rendezvous(buf, dist.group.WORLD.group_name)
+            torch.cuda.synchronize()
+            dist.barrier()                  # every rank's buffer is zeroed before any peer stores into it
+            self._os_buf, self._os_handle = buf, handle
+            self._os_peers = torch.tensor([int(p) for p in handle.buffer_ptrs], dtype=torch.int64, device=self.device)
+        except Exception as exc:            # pragma: no cover - depends on the platform
+            import logging
+            logging.warning("one-shot all-reduce unavailable (%s): using NCCL for the BatchNorm sums", exc)
+            self._os_peers = None
 
     # ------------------------------------------------------------------ workspaces
     def _workspace(self, B: int, T: int, training: bool) -> dict:
@@ -568,8 +592,11 @@ class RatEngine:
     def _allreduce_sums(self, t) -> int:
         """data-parallel hook (SyncBN-equivalent): all-reduce raw BN sums; returns the world size."""
         if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(t, group=self.dist_group)
+            if self._os_peers is not None and t.dtype == torch.float64 and t.numel() <= 2048:
+                call("rat_oneshot_allreduce_f64", self._os_peers, self.rank, self.world, t, t.numel(), t, current_stream())
+            else:
+                import torch.distributed as dist
+                dist.all_reduce(t, group=self.dist_group)
         return self.world
 
     def _rng_stream(self, slot: int) -> int:
@@ -801,6 +828,7 @@ class RatEngine:
         s, g, st = self.spec, self.store.grad_views, current_stream()
         N, D, F, L = s.F + 1, s.embedding_dim, s.F, s.L
         enc = ws["enc_out"]
+        self._last_bwd = (ws, B, T)
         self._amax_reset()
         # d(loss)/d(encoder output) is non-zero only in the pooled token [b,0,0,:] (written by rat_head)
         slot = self._amax_out(ws["denc"])
@@ -815,6 +843,10 @@ class RatEngine:
         d = self.encode_backward(ws, B, T)
         sw = ws["scatter_ws"]
         gs = self.store
+        self._net_work = None
+        if self.world > 1 and gs.shard is None:     # dense-net gradients are final: their all-reduce runs under the scatter
+            import torch.distributed as dist
+            self._net_work = dist.all_reduce(gs.G[:gs.net_end], group=self.dist_group, async_op=True)
         if gs.shard is None:
             g_emb = gs.G[gs.emb_off:gs.emb_off + s.V * D]
             g_lr = gs.G[gs.lr_off:gs.lr_off + s.V] if s.use_wide else None
@@ -829,42 +861,84 @@ class RatEngine:
              g_emb, g_lr, g["label_embedding_layer.weight"], B, T, L, F, D, s.V, float(s.emb_dropout), s.seed,
              self._rng_stream(0), 1 if planned else 0, sw, sw.numel() * 4, st)      # dropout backward fused (same mask)
 
-    def _optimizer_step_sharded(self):
-        """net + label gradients: all-reduce; table gradients: reduce-scatter to the row owners; global-norm clip with
-        the shard norms all-reduced; Adam on [net | label | local shard]; a final barrier orders the W update before
-        the peers' next gather."""
+    def _shard_recv(self, B, T):
+        """symmetric receive buffer of the sparse row-gradient exchange (one per (B, T))."""
+        key = ("recv", B, T)
+        ent = self._ws.get(key)
+        if ent is None:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm
+            s = self.spec
+            nbytes = int(query("rat_shard_recv_bytes", B, T, s.L, s.embedding_dim, self.world))
+            buf = symm.empty((nbytes + 3) // 4, dtype=torch.int32, device=self.device)
+            buf.zero_()
+            handle = symm.rendezvous(buf, dist.group.WORLD.group_name)
+            peers = torch.tensor([int(p) for p in handle.buffer_ptrs], dtype=torch.int64, device=self.device)
+            counts = torch.zeros(max(self.world, 4), dtype=torch.int32, device=self.device)
+            torch.cuda.synchronize()
+            dist.barrier()
+            ent = dict(buf=buf, handle=handle, peers=peers, counts=counts)
+            self._ws[key] = ent
+        return ent
+
+    def _barrier_sums(self, t):
+        """all-reduce of a small float64 vector that doubles as a cross-rank barrier of the compute streams."""
+        if self._os_peers is not None:
+            call("rat_oneshot_allreduce_f64", self._os_peers, self.rank, self.world, t, t.numel(), t, current_stream())
+        else:
+            import torch.distributed as dist
+            dist.all_reduce(t, group=self.dist_group)
+
+    def _optimizer_step_sharded(self, ws=None, B=None, T=None):
+        """net + label gradients: all-reduce; table gradients: every touched row is sent once to its owner over NVLink
+        (rat_shard_send_rows / rat_shard_apply_rows: traffic proportional to the batch, not to the vocabulary);
+        global-norm clip with the shard norms all-reduced; Adam on [net | label | local shard]; a final barrier orders the
+        W update before the peers' next gather."""
         import torch.distributed as dist
         s, gs, st = self.spec, self.store, current_stream()
+        if ws is None:
+            ws, B, T = self._last_bwd                   # optimizer_step() called on its own after backward()
         Vs, D = gs.rows_per_shard, s.embedding_dim
-        dist.all_reduce(gs.G[:gs.emb_off], group=self.dist_group)
-        dist.reduce_scatter_tensor(gs.G[gs.emb_off:gs.emb_off + Vs * D], gs.G_emb_full, group=self.dist_group)
-        gs.G_emb_full.zero_()
-        if s.use_wide:
-            dist.reduce_scatter_tensor(gs.G[gs.lr_off:gs.lr_off + Vs], gs.G_lr_full, group=self.dist_group)
-            gs.G_lr_full.zero_()
+        net_work = dist.all_reduce(gs.G[:gs.emb_off], group=self.dist_group, async_op=True)
+        rv = self._shard_recv(B, T)
+        sw = ws["scatter_ws"]
+        call("rat_shard_send_rows", sw, sw.numel() * 4, B, T, s.L, s.F, D, s.V, Vs, self.world, self.rank, gs.G_emb_full,
+             gs.G_lr_full, rv["peers"], rv["counts"], self.err_flag, st)
         nb = int(query("rat_optim_blocks"))
-        lam_n, lam_e = float(s.net_regularizer or 0.0), float(s.embedding_regularizer or 0.0)
         if not hasattr(self, "_shard_partial"):
             self._shard_partial = torch.zeros(2 * nb, dtype=torch.float64, device=self.device)
+            self._shard_extra = torch.zeros(2, dtype=torch.float64, device=self.device)
+        self._shard_extra.zero_()
+        self._barrier_sums(self._shard_extra)               # every rank's records have landed in their owners' buffers
+        call("rat_shard_apply_rows", rv["buf"], B, T, s.L, D, self.world, self.rank, Vs,
+             gs.G[gs.emb_off:gs.emb_off + Vs * D], gs.G[gs.lr_off:gs.lr_off + Vs] if s.use_wide else None, self.err_flag, st)
+        net_work.wait()
+        lam_n, lam_e = float(s.net_regularizer or 0.0), float(s.embedding_regularizer or 0.0)
         # replicated part (identical on every rank: counted once) and the local shard (summed over ranks)
         call("rat_grad_sqnorm", gs.G, gs.W, gs.emb_off, gs.net_end, lam_n, lam_e, self.opt_partial, st)
         call("rat_grad_sqnorm", gs.G[gs.emb_off:], gs.W[gs.emb_off:], gs.total - gs.emb_off, 0, lam_n, lam_e,
              self._shard_partial, st)
-        extra = self._shard_partial.view(2, nb).sum(dim=1)
-        dist.all_reduce(extra, group=self.dist_group)
-        call("rat_optim_prepare", self.opt_partial, nb, extra, float(s.max_gradient_norm), self.lr, 0.9, 0.999,
+        torch.sum(self._shard_partial.view(2, nb), dim=1, out=self._shard_extra)
+        self._barrier_sums(self._shard_extra)
+        call("rat_optim_prepare", self.opt_partial, nb, self._shard_extra, float(s.max_gradient_norm), self.lr, 0.9, 0.999,
              self.opt_state, 1, st)
         call("rat_adam_step", gs.W, gs.G, gs.M, gs.Vv, gs.total, gs.net_end, lam_n, lam_e, self.opt_state, 0.9, 0.999,
              1e-8, st)
-        dist.all_reduce(self._shard_partial[:1], group=self.dist_group)      # barrier: shards updated before any gather
+        self._shard_extra.zero_()
+        self._barrier_sums(self._shard_extra)               # barrier: shards updated before any peer's next gather
 
-    def optimizer_step(self):
+    def optimizer_step(self, ws=None, B=None, T=None):
         s, gs, st = self.spec, self.store, current_stream()
         if gs.shard is not None:
-            return self._optimizer_step_sharded()
+            return self._optimizer_step_sharded(ws, B, T)
         if self.world > 1:
             import torch.distributed as dist
-            dist.all_reduce(gs.G, group=self.dist_group)
+            if getattr(self, "_net_work", None) is not None:
+                dist.all_reduce(gs.G[gs.net_end:], group=self.dist_group)     # label / embedding / LR table gradients
+                self._net_work.wait()
+                self._net_work = None
+            else:
+                dist.all_reduce(gs.G, group=self.dist_group)
         nb = int(query("rat_optim_blocks"))
         lam_n, lam_e = float(s.net_regularizer or 0.0), float(s.embedding_regularizer or 0.0)
         call("rat_grad_sqnorm", gs.G, gs.W, gs.total, gs.net_end, lam_n, lam_e, self.opt_partial, st)
@@ -914,7 +988,7 @@ class RatEngine:
             ws["dact_c"].zero_()
         self.forward_ids(ws, B, T, training=True, inv_count=1.0 / (B * self.world))
         self.backward(ws, B, T)
-        self.optimizer_step()
+        self.optimizer_step(ws, B, T)
         return ws["loss"]
 
     def _plan_scatter(self, ws, B, T):
