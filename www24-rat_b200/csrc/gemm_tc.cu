@@ -34,40 +34,76 @@ struct GemmTcArgs {
 // Split in two halves so that the global loads of stage s+1 are in flight while stage s is converted, stored and multiplied:
 //   gemm_tile_load  : this thread's <= U items (8 floats each) -> registers
 //   gemm_tile_store : registers -> fp16 -> shared memory
+// item -> (row, chunk) of a staged tile: a warp covers 8 rows x 4 chunks, lane = (chunk % 4) * 8 + row % 8.  Its global loads
+// touch 8 cache lines (each row contributes 4 x 32 B = one 128-byte line) instead of 32, and every quarter-warp stores 8
+// consecutive rows of ONE chunk = 128 contiguous bytes of shared memory (conflict-free).  ROWS % 8 == 0.
+__device__ __forceinline__ bool gemm_item(int it, int ROWS, int CHUNKS, int& r, int& c) {
+    const int lane = it & 31, tile = it >> 5, rbs = ROWS >> 3;
+    r = (tile % rbs) * 8 + (lane & 7);
+    c = (tile / rbs) * 4 + (lane >> 3);
+    return c < CHUNKS;
+}
+// Per-thread description of its <= U items of one operand tile, computed ONCE before the stage loop (the first version
+// recomputed the item -> (row, chunk) mapping with divisions every stage: 37 % of the kernel's instructions).
+//   K-major tile  (rows = m/n index, cols = k):   stage s adds s*64 floats to the source pointer;
+//   MN-major tile (rows = k index,  cols = m/n):  stage s adds s*64 rows.
 template <int U>
-__device__ __forceinline__ void gemm_tile_load(const float* __restrict__ src, int ld, int row0, int col0, int rows_total,
-                                               int cols_total, int ROWS, int CHUNKS, bool vec_ok, float (&v)[U][8]) {
-    const int items = ROWS * CHUNKS;
+struct TileItems {
+    const float* src[U];         // source of the item in stage 0 (nullptr: outside the matrix in the fixed dimension)
+    uint32_t soff[U];            // byte offset inside the staged tile
+    int kpos[U];                 // position along the reduction dimension inside the stage (first of 8 for K-major, row for MN-major)
+    int mnrem[U];                // MN-major: valid columns of the 8 (clipped at the matrix edge); K-major: unused
+};
+template <int U, bool MN>
+__device__ __forceinline__ void gemm_items_init(TileItems<U>& t, const float* __restrict__ base, int ld, int mn0, int mn_total,
+                                                int k0, int ROWS, int CHUNKS) {
+    const int items = ROWS * ((CHUNKS + 3) & ~3);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const int it = threadIdx.x + u * GT_THREADS;
+        int r = 0, c = 0;
+        t.src[u] = nullptr; t.soff[u] = 0; t.kpos[u] = 0; t.mnrem[u] = 0;
+        if (it >= items || !gemm_item(it, ROWS, CHUNKS, r, c)) continue;
+        t.soff[u] = tc5::kmajor_off(r, c, ROWS);
+        if (!MN) {                                   // row r = m/n index, chunk c = 8 reduction positions
+            t.kpos[u] = c * 8;
+            if (mn0 + r < mn_total) t.src[u] = base + (size_t)(mn0 + r) * ld + k0 + c * 8;
+            else t.kpos[u] = -1;                     // zero row: still stored (the tile is rewritten every stage)
+        } else {                                     // row r = reduction position, chunk c = 8 m/n indices
+            t.kpos[u] = r;
+            t.mnrem[u] = min(8, mn_total - (mn0 + c * 8));
+            if (t.mnrem[u] > 0) t.src[u] = base + (size_t)(k0 + r) * ld + mn0 + c * 8;
+        }
+    }
+}
+// klen = reduction positions left in this stage's range (kend - k0 of the stage)
+template <int U, bool MN>
+__device__ __forceinline__ void gemm_tile_load(const TileItems<U>& t, size_t adv, int klen, bool vec_ok, float (&v)[U][8]) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) v[u][k] = 0.f;
-        if (it >= items) continue;
-        const int r = it % ROWS, c = it / ROWS;
-        const int gr = row0 + r, gc = col0 + c * 8;
-        if (gr < rows_total && gc + 8 <= cols_total && vec_ok) {
-            const float4 t0 = __ldg(reinterpret_cast<const float4*>(src + (size_t)gr * ld + gc));
-            const float4 t1 = __ldg(reinterpret_cast<const float4*>(src + (size_t)gr * ld + gc + 4));
+        if (t.src[u] == nullptr) continue;
+        const float* p = t.src[u] + adv;
+        const int n = MN ? (t.kpos[u] < klen ? t.mnrem[u] : 0) : min(8, klen - t.kpos[u]);
+        if (n == 8 && vec_ok) {
+            const float4 t0 = __ldg(reinterpret_cast<const float4*>(p)), t1 = __ldg(reinterpret_cast<const float4*>(p + 4));
             v[u][0] = t0.x; v[u][1] = t0.y; v[u][2] = t0.z; v[u][3] = t0.w;
             v[u][4] = t1.x; v[u][5] = t1.y; v[u][6] = t1.z; v[u][7] = t1.w;
-        } else if (gr < rows_total) {
+        } else {
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-                if (gc + k < cols_total) v[u][k] = __ldg(src + (size_t)gr * ld + gc + k);
+                if (k < n) v[u][k] = __ldg(p + k);
         }
     }
 }
 template <int U>
-__device__ __forceinline__ void gemm_tile_store(const float (&v)[U][8], int ROWS, int CHUNKS, unsigned char* __restrict__ dst,
-                                                float mul) {
-    const int items = ROWS * CHUNKS;
+__device__ __forceinline__ void gemm_tile_store(const TileItems<U>& t, int nitems_thread, const float (&v)[U][8],
+                                                unsigned char* __restrict__ dst, float mul) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        const int it = threadIdx.x + u * GT_THREADS;
-        if (it >= items) continue;
-        const int r = it % ROWS, c = it / ROWS;
-        sts128(dst + tc5::kmajor_off(r, c, ROWS), pack_h2(v[u][0] * mul, v[u][1] * mul), pack_h2(v[u][2] * mul, v[u][3] * mul),
+        if (u >= nitems_thread) continue;
+        sts128(dst + t.soff[u], pack_h2(v[u][0] * mul, v[u][1] * mul), pack_h2(v[u][2] * mul, v[u][3] * mul),
                pack_h2(v[u][4] * mul, v[u][5] * mul), pack_h2(v[u][6] * mul, v[u][7] * mul));
     }
 }
@@ -100,22 +136,38 @@ __global__ void __launch_bounds__(GT_THREADS) k_gemm_tc(GemmTcArgs a) {
     // A tile: K-major -> rows = m (128), cols = k (64) ; MN-major -> rows = k (64), cols = m (128): 1024 items = 4 per thread;
     // B tile: BN x 64 -> <= 2048 items = 8 per thread (BN <= 256), 2 when BN <= 64
     constexpr int UA = TILE_M * (GT_KB / 8) / GT_THREADS;
+    TileItems<UA> ia;
+    TileItems<UB> ib;
+    if (!A_MN) gemm_items_init<UA, false>(ia, a.A, a.lda, m0, a.M, kbeg, TILE_M, GT_KB / 8);
+    else gemm_items_init<UA, true>(ia, a.A, a.lda, m0, a.M, kbeg, GT_KB, TILE_M / 8);
+    if (!B_MN) gemm_items_init<UB, false>(ib, a.B, a.ldb, n0, a.N, kbeg, BN, GT_KB / 8);
+    else gemm_items_init<UB, true>(ib, a.B, a.ldb, n0, a.N, kbeg, GT_KB, BN / 8);
+    // items of this thread that exist in the tile (their slots are rewritten every stage, zeros included)
+    int na = 0, nb = 0;
+    {
+        const int items_a = (A_MN ? GT_KB * (TILE_M / 8) : TILE_M * (GT_KB / 8));
+        const int items_b = B_MN ? GT_KB * ((BN / 8 + 3) & ~3) : BN * (GT_KB / 8);
+        for (int u = 0; u < UA; ++u) if ((int)threadIdx.x + u * GT_THREADS < items_a) na = u + 1;
+        for (int u = 0; u < UB; ++u) {
+            const int it = threadIdx.x + u * GT_THREADS;
+            int r, c;
+            if (it < items_b && gemm_item(it, B_MN ? GT_KB : BN, B_MN ? BN / 8 : GT_KB / 8, r, c)) nb = u + 1;
+        }
+    }
+    const size_t adv_a = A_MN ? (size_t)GT_KB * a.lda : (size_t)GT_KB, adv_b = B_MN ? (size_t)GT_KB * a.ldb : (size_t)GT_KB;
+    const bool a_v = a_vec && (A_MN || (kbeg % 4 == 0)), b_v = b_vec && (B_MN ? (n0 % 4 == 0) : (kbeg % 4 == 0));
     float ra[UA][8], rb[UB][8];
     auto load_stage = [&](int s) {
-        const int k0 = kbeg + s * GT_KB;
-        if (!A_MN) gemm_tile_load<UA>(a.A, a.lda, m0, k0, a.M, kend, TILE_M, GT_KB / 8, a_vec && (k0 % 4 == 0), ra);
-        else gemm_tile_load<UA>(a.A, a.lda, k0, m0, kend, a.M, GT_KB, TILE_M / 8, a_vec, ra);
-        if (!B_MN) gemm_tile_load<UB>(a.B, a.ldb, n0, k0, a.N, kend, BN, GT_KB / 8, b_vec && (k0 % 4 == 0), rb);
-        else gemm_tile_load<UB>(a.B, a.ldb, k0, n0, kend, a.N, GT_KB, BN / 8, b_vec && (n0 % 4 == 0), rb);
+        const int klen = kend - (kbeg + s * GT_KB);
+        if (!A_MN) gemm_tile_load<UA, false>(ia, adv_a * s, klen, a_v, ra); else gemm_tile_load<UA, true>(ia, adv_a * s, klen, a_v, ra);
+        if (!B_MN) gemm_tile_load<UB, false>(ib, adv_b * s, klen, b_v, rb); else gemm_tile_load<UB, true>(ib, adv_b * s, klen, b_v, rb);
     };
     if (nst > 0) load_stage(0);
     for (int s = 0; s < nst; ++s) {
         const int buf = s & 1;
         if (s >= 2) tc5::mbar_wait(&mbar[buf], ((s >> 1) - 1) & 1);      // the MMAs that read this buffer are done
-        if (!A_MN) gemm_tile_store<UA>(ra, TILE_M, GT_KB / 8, Abuf[buf], a_scale);
-        else gemm_tile_store<UA>(ra, GT_KB, TILE_M / 8, Abuf[buf], a_scale);
-        if (!B_MN) gemm_tile_store<UB>(rb, BN, GT_KB / 8, Bbuf[buf], 1.0f);
-        else gemm_tile_store<UB>(rb, GT_KB, BN / 8, Bbuf[buf], 1.0f);
+        gemm_tile_store<UA>(ia, na, ra, Abuf[buf], a_scale);
+        gemm_tile_store<UB>(ib, nb, rb, Bbuf[buf], 1.0f);
         if (s + 1 < nst) load_stage(s + 1);        // in flight under this stage's barrier, MMA issue and the next buffer wait
         tc5::fence_proxy_async();
         __syncthreads();
@@ -224,9 +276,10 @@ static int launch_gemm_tc_u(const GemmTcArgs& a, const GemmTcPlan& p, cudaStream
 }
 template <bool A_MN, bool B_MN>
 static int launch_gemm_tc(const GemmTcArgs& a, const GemmTcPlan& p, cudaStream_t st) {
-    // B tile items per thread: BN * 8 / 256
-    if (p.BN <= 64) return launch_gemm_tc_u<A_MN, B_MN, 2>(a, p, st);
-    if (p.BN <= 128) return launch_gemm_tc_u<A_MN, B_MN, 4>(a, p, st);
+    // B tile items per thread: K-major BN x 8 chunks, MN-major 64 rows x round_up(BN / 8, 4) chunks; / 256 threads
+    const int items = B_MN ? GT_KB * ((p.BN / 8 + 3) & ~3) : round_up(p.BN, 8) * (GT_KB / 8);
+    if (items <= 2 * GT_THREADS) return launch_gemm_tc_u<A_MN, B_MN, 2>(a, p, st);
+    if (items <= 4 * GT_THREADS) return launch_gemm_tc_u<A_MN, B_MN, 4>(a, p, st);
     return launch_gemm_tc_u<A_MN, B_MN, 8>(a, p, st);
 }
 
