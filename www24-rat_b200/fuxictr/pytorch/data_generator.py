@@ -160,11 +160,13 @@ class DeviceDataGenerator(object):
         for b in range(self.num_batches):
             lo, hi = b * bs, min(Q, (b + 1) * bs)
             n = hi - lo
-            # contiguous per-rank slice of the global batch (data-parallel batch sharding)
-            per = (n + self.world - 1) // self.world
-            s, e = lo + self.rank * per, min(hi, lo + (self.rank + 1) * per)
-            if e <= s:
-                s, e = lo, min(hi, lo + 1)
+            # contiguous per-rank slice of the global batch (data-parallel batch sharding).  Every rank must get the SAME
+            # number of samples (the engine scales the loss by 1 / (B_local * world) and BatchNorm counts B_local * world):
+            # a ragged last batch is truncated to a multiple of the world size (at most world - 1 samples are dropped)
+            per = n // self.world
+            if per == 0:
+                continue
+            s, e = lo + self.rank * per, lo + (self.rank + 1) * per
             if perm is not None:
                 yield DeviceBatch(self, perm[s:e], 0, e - s)
             else:
@@ -183,8 +185,11 @@ class DeviceDataFileGenerator(DeviceDataGenerator):
         data_array = _load_array(data_path)
         pool = data_array if retrieval_pool_fname == "self" else _load_array(retrieval_pool_fname)
         idx, _, _ = _load_retrieval(data_path, retrieval_configs)
-        rank = int(os.environ.get("RANK", 0)) if kwargs.get("data_parallel") else 0
-        world = int(os.environ.get("WORLD_SIZE", 1)) if kwargs.get("data_parallel") else 1
+        # only the (shuffled) training generator is sharded over the ranks: validation / test generators serve the whole set on
+        # every rank, so all ranks compute identical metrics and take identical early-stop / lr-decay decisions
+        dp = bool(kwargs.get("data_parallel")) and bool(shuffle)
+        rank = int(os.environ.get("RANK", 0)) if dp else 0
+        world = int(os.environ.get("WORLD_SIZE", 1)) if dp else 1
         super().__init__(data_array, pool, idx, batch_size, shuffle, device, seed, rank, world)
 
 

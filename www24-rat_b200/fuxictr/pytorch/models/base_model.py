@@ -132,8 +132,16 @@ class BaseModel(nn.Module):
                     v.normal_(0.0, 1.0)
                 elif "embedding_layer.embedding_layer.embedding_layer." in k:
                     feat = k.split(".")[-2]
-                    v.zero_()
-                    w = v[0:-1, :] if pads[feat] is not None else v
+                    pad = pads[feat]
+                    if pad is not None and pad != v.shape[0] - 1:
+                        # reference semantics for a padding_idx that is not the last row (embedding.py:96-100 +
+                        # base_model.py:110-112): nn.Embedding's N(0,1) init with the padding row zeroed, then rows
+                        # [0:-1] -- including the padding row -- re-drawn by the initializer; the last row keeps N(0,1)
+                        v.normal_(0.0, 1.0)
+                        v[pad].zero_()
+                    else:
+                        v.zero_()
+                    w = v[0:-1, :] if pad is not None else v
                     if self._embedding_initializer is not None:
                         try:
                             eval(self._embedding_initializer.replace("(", "(w,", 1))
@@ -405,6 +413,11 @@ class BaseModel(nn.Module):
 
     def load_weights(self, checkpoint):
         state_dict = torch.load(checkpoint, map_location="cpu")
-        self.load_state_dict(state_dict, strict=False)
+        # strict like the reference (base_model.py:281): a checkpoint of another variant / use_wide / batch_norm setting fails loudly.
+        # query_proj is a dead parameter that older checkpoints of this package did not store.
+        for k, v in self.state_dict().items():
+            if k.startswith("query_proj") and k not in state_dict:
+                state_dict[k] = v.detach().cpu()
+        self.load_state_dict(state_dict, strict=True)
         del state_dict
         torch.cuda.empty_cache()

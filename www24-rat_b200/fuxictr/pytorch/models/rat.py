@@ -23,6 +23,13 @@ class _RATBase(BaseModel):
         if num_heads == 1 and dim_head == embedding_dim:
             raise NotImplementedError("identity out-projection (heads==1 and dim_head==dim) is not supported")
         _ = kwargs["retrieval_configs"]["topK"]           # required key, unused at run time like the reference
+        # arithmetic of the projections / DNN GEMMs (not a reference option): config key `precision`, default fp16
+        # tensor-core operands with fp32 accumulation; "fp32" reproduces the reference arithmetic exactly
+        if kwargs.get("precision") is not None:
+            import logging
+            from rat_native.engine import set_precision
+            set_precision(str(kwargs["precision"]))
+            logging.info("RAT precision mode: {}".format(kwargs["precision"]))
         spec = EngineSpec(
             features=self._feature_specs(), model=self._variant, embedding_dim=int(embedding_dim),
             num_heads=int(num_heads), dim_head=int(dim_head), scale_dim=int(scale_dim), depth=int(depth),

@@ -75,13 +75,16 @@ class EngineSpec:
         return sum(f.vocab_size for f in self.features)
 
 
-_PREC = {"fp32": 0, "tf32": 1, "fp16": 2, "bf16": 2}     # "bf16": round-1 alias of the tensor-core mode
+_PREC = {"fp32": 0, "tf32": 1, "fp16": 2}
 
 
 def set_precision(mode: str):
-    """'fp16': tcgen05 projections + DNN GEMMs (fp16 operands, fp32 accumulate in TMEM, gradients pre-scaled by 2^10);
-    'tf32': mma.sync TF32 projections; 'fp32': exact SIMT twin (parity anchor)."""
-    assert mode in _PREC, mode
+    """'fp16' (default): tcgen05 projections + DNN GEMMs with fp16 operands (10-bit mantissa), fp32 accumulation in TMEM and
+    dynamic power-of-two gradient scaling; 'tf32': mma.sync TF32 projections; 'fp32': exact SIMT twin (parity anchor).
+    Process-wide (the library holds one mode); models expose it as the `precision` keyword / config key."""
+    if mode not in _PREC:
+        raise ValueError(f"precision={mode!r}: choose one of {sorted(_PREC)} (there is no bf16 mode: bf16 operands missed "
+                         f"the 1e-3 AUC bar, DESIGN.md section 1)")
     call("rat_set_precision", _PREC[mode])
 
 
@@ -681,6 +684,8 @@ class RatEngine:
         if not self._amax_on:
             return None
         i = self._amax_next
+        if i >= self.amax.numel():
+            raise RuntimeError(f"gradient-scale slots exhausted ({self.amax.numel()}): depth too large for the amax buffer")
         self._amax_next += 1
         return self.amax[i:i + 1]
 
