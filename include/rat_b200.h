@@ -197,6 +197,16 @@ int rat_attn_bwd(const float* x, const float* dout, const float* base, float* dx
                  float* dWk, float* dWv, float* dWo, float* dbo, float* dln_w, float* dln_b, int accumulate_wq, int B,
                  int T, int N, int D, int heads, int dim_head, float scale, float alpha, int mode,
                  const float* dout_amax, float* dx_amax, float* workspace, size_t workspace_bytes, void* stream);
+/* rat_attn_bwd with the backward of an nn.Dropout on dx fused into its last store: dx *= mask / (1 - p) with the mask of
+ * (out_drop_p, seed, rng_stream) over the flattened [B,T,N,D] element index -- for the encoder's first sub-block this is the
+ * backward of nn.Dropout(emb_dropout) (models/RAT_m2.py:83,135) with the mask rat_gather_fwd drew, so that the segment
+ * reduce reads a ready gradient.  out_drop_p = 0 is rat_attn_bwd. */
+int rat_attn_bwd_dropout(const float* x, const float* dout, const float* base, float* dx, const float* ln_w,
+                         const float* ln_b, const float* Wq, const float* Wk, const float* Wv, const float* Wo, float* dWq,
+                         float* dWk, float* dWv, float* dWo, float* dbo, float* dln_w, float* dln_b, int accumulate_wq, int B,
+                         int T, int N, int D, int heads, int dim_head, float scale, float alpha, int mode,
+                         const float* dout_amax, float* dx_amax, float* workspace, size_t workspace_bytes, float out_drop_p,
+                         unsigned long long seed, unsigned int rng_stream, void* stream);
 size_t rat_ff_bwd_workspace_bytes(long long rows, int D, int M);
 int rat_ff_bwd(const float* x, const float* dout, const float* base, float* dx, const float* ln_w, const float* ln_b,
                const float* W1, const float* b1, const float* W2, float* dW1, float* db1, float* dW2, float* db2,

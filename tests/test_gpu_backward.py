@@ -81,6 +81,17 @@ def test_attn_bwd_matches_autograd(rn, precision, B, T, N, D, H, dh, mode):
             scale, alpha, mode, am[0:1], None, ws, ws.numel() * 4, rn.current_stream())
     assert torch.equal(dd2, dx)
     assert torch.equal(dW2, dW)
+    # dropout backward fused into the dx store == the same mask applied afterwards (rat_dropout_bwd), bit for bit;
+    # the parameter gradients do not see the mask
+    dx3, dW3 = torch.empty_like(dx), torch.empty_like(dW)
+    rn.call("rat_attn_bwd_dropout", xd, dd, dd, dx3, lnw.detach().to(d), lnb.detach().to(d), wq[:I], wq[I:2 * I],
+            wq[2 * I:], wo.detach().to(d), dW3[:I], dW3[I:2 * I], dW3[2 * I:], dWo, dbo, dlw, dlb, 0, B, T, N, D, H, dh,
+            scale, alpha, mode, am[0:1], None, ws, ws.numel() * 4, 0.3, 77, 5, rn.current_stream())
+    masked = dx.clone()
+    rn.call("rat_dropout_bwd", masked, masked.numel(), 0.3, 77, 5, rn.current_stream())
+    assert torch.equal(dx3, masked)
+    assert torch.equal(dW3, dW)
+    assert 0.2 < float((dx3 == 0).float().mean()) < 0.4
 
 
 @pytest.mark.parametrize("rows,D,M,prenorm", [(120, 10, 40, False), (5000, 40, 80, False), (333, 10, 20, False),

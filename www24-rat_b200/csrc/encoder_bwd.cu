@@ -533,7 +533,8 @@ int attn_bwd_tc_dispatch(const float* x, const float* dout, const float* base, f
                          const float* ln_b, const float* Wq, const float* Wk, const float* Wv, const float* Wo, float* dWq,
                          float* dWk, float* dWv, float* dWo, float* dbo, float* dln_w, float* dln_b, int accumulate_wq,
                          int B, int T, int N, int D, int heads, int dh, float scale, float alpha, int mode,
-                         const float* dout_amax, float* dx_amax, float* workspace, size_t workspace_bytes, cudaStream_t st);
+                         const float* dout_amax, float* dx_amax, float* workspace, size_t workspace_bytes, float out_drop_p,
+                         unsigned long long seed, unsigned int rng_stream, cudaStream_t st);
 int ff_bwd_tc_dispatch(const float* x, const float* dout, const float* base, float* dx, const float* ln_w,
                        const float* W1, const float* b1, const float* W2, float* dW1, float* db1, float* dW2, float* db2,
                        long long rows, int D, int M, const float* dout_amax, float* dx_amax, float* workspace,
@@ -571,12 +572,27 @@ extern "C" int rat_attn_bwd(const float* x, const float* dout, const float* base
                             int accumulate_wq, int B, int T, int N, int D, int heads, int dim_head, float scale,
                             float alpha, int mode, const float* dout_amax, float* dx_amax, float* workspace,
                             size_t workspace_bytes, void* stream) {
+    return rat_attn_bwd_dropout(x, dout, base, dx, ln_w, ln_b, Wq, Wk, Wv, Wo, dWq, dWk, dWv, dWo, dbo, dln_w, dln_b, accumulate_wq,
+                                B, T, N, D, heads, dim_head, scale, alpha, mode, dout_amax, dx_amax, workspace, workspace_bytes,
+                                0.0f, 0ull, 0u, stream);
+}
+
+extern "C" int rat_dropout_bwd(float* grad, long long n, float p, unsigned long long seed, unsigned int rng_stream, void* stream);
+
+extern "C" int rat_attn_bwd_dropout(const float* x, const float* dout, const float* base, float* dx, const float* ln_w,
+                                    const float* ln_b, const float* Wq, const float* Wk, const float* Wv, const float* Wo,
+                                    float* dWq, float* dWk, float* dWv, float* dWo, float* dbo, float* dln_w, float* dln_b,
+                                    int accumulate_wq, int B, int T, int N, int D, int heads, int dim_head, float scale,
+                                    float alpha, int mode, const float* dout_amax, float* dx_amax, float* workspace,
+                                    size_t workspace_bytes, float out_drop_p, unsigned long long seed, unsigned int rng_stream,
+                                    void* stream) {
     RAT_REQUIRE(B > 0 && T > 0 && N > 0 && D > 0 && heads > 0, "rat_attn_bwd: bad shape");
     RAT_REQUIRE(D <= 128, "rat_attn_bwd: D=%d > 128 not supported", D);
+    RAT_REQUIRE(out_drop_p >= 0.f && out_drop_p < 1.f, "rat_attn_bwd_dropout: dropout p=%f", out_drop_p);
     if (precision_mode() == 2) {
         const int rc2 = attn_bwd_tc_dispatch(x, dout, base, dx, ln_w, ln_b, Wq, Wk, Wv, Wo, dWq, dWk, dWv, dWo, dbo, dln_w,
                                              dln_b, accumulate_wq, B, T, N, D, heads, dim_head, scale, alpha, mode, dout_amax, dx_amax,
-                                             workspace, workspace_bytes, (cudaStream_t)stream);
+                                             workspace, workspace_bytes, out_drop_p, seed, rng_stream, (cudaStream_t)stream);
         if (rc2 <= 0) return rc2;
     }
     AttnBwdArgs a{};
@@ -607,6 +623,10 @@ extern "C" int rat_attn_bwd(const float* x, const float* dout, const float* base
     const int total = 4 * a.I * D + 3 * D;
     k_reduce_attn<<<max(1, min(ceil_div(total, 256), 1024)), 256, 0, st>>>(r);
     RAT_CHECK_LAUNCH("k_reduce_attn");
+    if (out_drop_p > 0.f) {  // these kernels do not fuse the output mask: same mask as a separate pass
+        rc = rat_dropout_bwd(dx, (long long)B * T * N * D, out_drop_p, seed, rng_stream, stream);
+        if (rc != RAT_OK) return rc;
+    }
     if (dx_amax)            // fp32 / tf32 kernels do not track the maximum themselves
         return rat_absmax(dx, (long long)B * T * N, D, D, dx_amax, stream);
     return RAT_OK;

@@ -68,7 +68,8 @@ int attn_bwd_tc_dispatch(const float* x, const float* dout, const float* base, f
                          const float* ln_b, const float* Wq, const float* Wk, const float* Wv, const float* Wo, float* dWq,
                          float* dWk, float* dWv, float* dWo, float* dbo, float* dln_w, float* dln_b, int accumulate_wq,
                          int B, int T, int N, int D, int heads, int dh, float scale, float alpha, int mode,
-                         const float* dout_amax, float* dx_amax, float* workspace, size_t workspace_bytes, cudaStream_t st) {
+                         const float* dout_amax, float* dx_amax, float* workspace, size_t workspace_bytes, float out_drop_p,
+                         unsigned long long seed, unsigned int rng_stream, cudaStream_t st) {
     AttnBwdTcArgs a{};
     const int S = mode == 0 ? N : T;
     if (!attn_bwd_tc_plan(S, D, heads, dh, &a)) return 1;
@@ -79,6 +80,7 @@ int attn_bwd_tc_dispatch(const float* x, const float* dout, const float* base, f
     a.partials = workspace; a.dout_amax = dout_amax; a.dx_amax = dx_amax;
     a.g.S = S; a.g.mode = mode; a.g.T = T; a.g.N = N;
     a.scale = scale; a.alpha = alpha;
+    a.out_drop_p = out_drop_p; a.seed = seed; a.rng_stream = rng_stream; a.rng_step = rng_step_ptr();
     int rc;
     switch (dh) {
         case 8: rc = attn_bwd_tc_launch_dh8(a, grid, st); break;

@@ -32,6 +32,9 @@ struct AttnBwdTcArgs {
     int NDo;                 // hc * DHP        padded dO columns per chunk
     int Cc;                  // pad16(hc * dh)  compact O columns per chunk
     int SPT, njobs, psize, smem_bytes;
+    // optional mask on dx: the backward of nn.Dropout(emb_dropout) (RAT_m2.py:135) fused into the LAST backward kernel of the
+    // encoder, with the mask of rat_gather_fwd (same seed / stream / element index), so the segment reduce reads a ready gradient
+    float out_drop_p; unsigned long long seed; unsigned int rng_stream; const unsigned int* rng_step;
 };
 
 __device__ __forceinline__ uint32_t movm_t(uint32_t a) {
@@ -443,8 +446,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_attn_bwd_tc(AttnBwdTcArgs a) 
                     for (int k = 0; k < 8; ++k) {
                         ov[k] = (rstd * inv_gs) * (gg[u][k] - t1 - xh[u][k] * t2);
                         if (a.base) ov[k] += bv[k];
-                        dx_max = fmaxf(dx_max, fabsf(ov[k]));
                     }
+                    if (a.out_drop_p > 0.f) {
+                        const unsigned long long e0 = (unsigned long long)gr * D + gq * 8;
+                        const uint32_t strm = rng_stream_of_step(a.rng_stream, a.rng_step);
+                        const float inv_keep = 1.0f / (1.0f - a.out_drop_p);
+                        if ((e0 & 7ull) == 0ull) {                       // D % 8 == 0: the 8 decisions of one counter
+                            const uint4 bits = dropout_bits8(a.seed, strm, e0 >> 3);
+                            const uint32_t thr = dropout_threshold(a.out_drop_p);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) ov[k] *= dropout_lane16(bits, k) < thr ? 0.f : inv_keep;
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k)
+                                if (gq * 8 + k < D) ov[k] *= dropout_scale(a.seed, strm, e0 + k, a.out_drop_p, inv_keep);
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) dx_max = fmaxf(dx_max, fabsf(ov[k]));
                     store8<VEC4>(a.dx + gr * D, gq * 8, D, ov);
                 }
             }
