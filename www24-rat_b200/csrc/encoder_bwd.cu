@@ -535,6 +535,14 @@ int attn_bwd_tc_dispatch(const float* x, const float* dout, const float* base, f
                          int B, int T, int N, int D, int heads, int dh, float scale, float alpha, int mode,
                          const float* dout_amax, float* dx_amax, float* workspace, size_t workspace_bytes, float out_drop_p,
                          unsigned long long seed, unsigned int rng_stream, cudaStream_t st);
+int attn_bwd_rr_dispatch(const float* x, const float* dout, const float* base, float* dx, const float* ln_w,
+                         const float* ln_b, const float* Wq, const float* Wk, const float* Wv, const float* Wo, float* dWq,
+                         float* dWk, float* dWv, float* dWo, float* dbo, float* dln_w, float* dln_b, int accumulate_wq,
+                         int B, int T, int N, int D, int heads, int dh, float scale, float alpha, int mode,
+                         const float* dout_amax, float* dx_amax, float* workspace, size_t workspace_bytes, float out_drop_p,
+                         unsigned long long seed, unsigned int rng_stream, cudaStream_t st);
+size_t attn_bwd_rr_workspace_bytes(int B, int T, int N, int D, int heads, int dh, int mode);
+bool rr_enabled();
 int ff_bwd_tc_dispatch(const float* x, const float* dout, const float* base, float* dx, const float* ln_w,
                        const float* W1, const float* b1, const float* W2, float* dW1, float* db1, float* dW2, float* db2,
                        long long rows, int D, int M, const float* dout_amax, float* dx_amax, float* workspace,
@@ -546,7 +554,8 @@ extern "C" size_t rat_attn_bwd_workspace_bytes(int B, int T, int N, int D, int h
     if (plan_attn_bwd(S, D, heads, dim_head, &p) != RAT_OK) return 0;
     const long long nseq = mode == 0 ? (long long)B * T : (long long)B * N;
     const long long ntiles = (nseq + p.SPT - 1) / p.SPT;
-    return std::max((size_t)bwd_grid(ntiles) * p.psize * sizeof(float), attn_bwd_tc_workspace_bytes(B, T, N, D, heads, dim_head, mode));
+    return std::max({(size_t)bwd_grid(ntiles) * p.psize * sizeof(float), attn_bwd_tc_workspace_bytes(B, T, N, D, heads, dim_head, mode),
+                     attn_bwd_rr_workspace_bytes(B, T, N, D, heads, dim_head, mode)});
 }
 
 template <int DH, bool MMA>
@@ -589,6 +598,12 @@ extern "C" int rat_attn_bwd_dropout(const float* x, const float* dout, const flo
     RAT_REQUIRE(B > 0 && T > 0 && N > 0 && D > 0 && heads > 0, "rat_attn_bwd: bad shape");
     RAT_REQUIRE(D <= 128, "rat_attn_bwd: D=%d > 128 not supported", D);
     RAT_REQUIRE(out_drop_p >= 0.f && out_drop_p < 1.f, "rat_attn_bwd_dropout: dropout p=%f", out_drop_p);
+    if (precision_mode() == 2 && rr_enabled()) {
+        const int rc3 = attn_bwd_rr_dispatch(x, dout, base, dx, ln_w, ln_b, Wq, Wk, Wv, Wo, dWq, dWk, dWv, dWo, dbo, dln_w,
+                                             dln_b, accumulate_wq, B, T, N, D, heads, dim_head, scale, alpha, mode, dout_amax, dx_amax,
+                                             workspace, workspace_bytes, out_drop_p, seed, rng_stream, (cudaStream_t)stream);
+        if (rc3 <= 0) return rc3;
+    }
     if (precision_mode() == 2) {
         const int rc2 = attn_bwd_tc_dispatch(x, dout, base, dx, ln_w, ln_b, Wq, Wk, Wv, Wo, dWq, dWk, dWv, dWo, dbo, dln_w,
                                              dln_b, accumulate_wq, B, T, N, D, heads, dim_head, scale, alpha, mode, dout_amax, dx_amax,

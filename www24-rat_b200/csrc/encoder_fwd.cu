@@ -242,6 +242,18 @@ int attn_fwd_tc2_dispatch(const float* x, const float* res, float* out, const fl
 // RAT_TC2=1 in the environment selects the second-generation attention forward (every product on tcgen05, one tile per
 // 4-warp group; encoder_tc2_fwd.cu).  It is parity-green but measured no faster than the first generation on B200
 // (kkbox B=4096: 128 / 144 us vs 129 / 135 us; DESIGN.md "Attention, second generation"), so it is opt-in.
+int attn_fwd_rr_dispatch(const float* x, const float* res, float* out, const float* ln_w, const float* ln_b,
+                         const float* Wq, const float* Wk, const float* Wv, const float* Wo, const float* bo, int B, int T,
+                         int N, int D, int heads, int dh, float scale, float alpha, int mode, cudaStream_t st);
+
+// The register-resident attention kernels (encoder_rr_*.cu) are the default of the fp16 mode for sequences <= 16 tokens;
+// RAT_RR=0 in the environment selects the tile-based tcgen05 kernels for every shape (A/B measurements).
+bool rr_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("RAT_RR"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on == 1;
+}
+
 bool tc2_enabled() {
     static int on = -1;
     if (on < 0) { const char* e = getenv("RAT_TC2"); on = (e && e[0] == '1') ? 1 : 0; }
@@ -283,6 +295,11 @@ extern "C" int rat_attn_fwd(const float* x, const float* res, float* out, const 
     RAT_REQUIRE(mode == 0 || mode == 1, "rat_attn_fwd: mode must be 0 (intra) or 1 (cross)");
     RAT_REQUIRE(Wo != nullptr && bo != nullptr, "rat_attn_fwd: identity out-projection (heads==1 && dim_head==dim) is not supported");
     if (g_precision == 2) {
+        if (rr_enabled()) {
+            const int rc4 = attn_fwd_rr_dispatch(x, res, out, ln_w, ln_b, Wq, Wk, Wv, Wo, bo, B, T, N, D, heads, dim_head, scale,
+                                                 alpha, mode, (cudaStream_t)stream);
+            if (rc4 <= 0) return rc4;
+        }
         if (tc2_enabled()) {
             const int rc3 = attn_fwd_tc2_dispatch(x, res, out, ln_w, ln_b, Wq, Wk, Wv, Wo, bo, B, T, N, D, heads, dim_head,
                                                   scale, alpha, mode, (cudaStream_t)stream);
