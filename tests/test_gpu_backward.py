@@ -29,6 +29,8 @@ ATTN_SHAPES = [  # B, T, N, D, H, dh
     (2, 1, 84, 40, 8, 10),     # RAT_m0 flat sequence (S=84 > 32 lanes)
     (4, 3, 5, 20, 2, 20),      # RAT_m3 head width
     (70, 2, 3, 16, 4, 8),      # several tiles per CTA / ragged last tile
+    (420, 6, 14, 40, 8, 10),   # kkbox shape, 2520 / 5880 sequences: several tiles per persistent CTA (deferred epilogues)
+    (333, 6, 9, 10, 32, 10),   # tmall shape, several tiles per CTA and several head chunks per tile
 ]
 
 

@@ -160,6 +160,7 @@ ATTN_SHAPES = [  # B, T, N, D, H, dh
     (2, 1, 84, 40, 8, 10),     # RAT_m0: one flat sequence of T*N tokens
     (4, 3, 5, 20, 2, 20),      # RAT_m3 head width 2*dim_head
     (300, 2, 3, 16, 4, 8),     # many tiles / ragged last tile
+    (420, 6, 14, 40, 8, 10),   # kkbox shape, several tasks per warp (double-buffered bulk row staging)
 ]
 
 

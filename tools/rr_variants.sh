@@ -1,2 +1,4 @@
-for v in 0 1 2 3 4; do echo "== fwd variant $v"; RAT_RR_FWD_VARIANT=$v timeout 200 python -m pytest tests -m gpu -x -q -k "attn_fwd" 2>&1 | tail -2; RAT_RR_FWD_VARIANT=$v ONLY_FWD=1 timeout 100 python tools/bench_attn.py kkbox 4096 5 2>&1 | tail -2; done
-for v in 1 2; do echo "== bwd variant $v"; RAT_RR_BWD_VARIANT=$v timeout 200 python -m pytest tests -m gpu -x -q -k "attn_bwd" 2>&1 | tail -2; RAT_RR_BWD_VARIANT=$v timeout 100 python tools/bench_attn.py kkbox 4096 5 2>&1 | grep bwd; done
+timeout 600 python -m pytest tests -m gpu -x -q -k "attn_fwd or attn_bwd" 2>&1 | tail -15
+T='tests/test_gpu_backward.py::test_auc_logloss_after_fixed_steps_match_oracle'
+for i in 1 2 3; do timeout 300 python -m pytest "$T" -m gpu -q -k "fp16 and tmall" -s 2>&1 | grep -E "AUC oracle"; done
+for i in 1 2; do RAT_RR=0 timeout 300 python -m pytest "$T" -m gpu -q -k "fp16 and tmall" -s 2>&1 | grep -E "AUC oracle"; done

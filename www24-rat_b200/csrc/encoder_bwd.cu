@@ -598,7 +598,7 @@ extern "C" int rat_attn_bwd_dropout(const float* x, const float* dout, const flo
     RAT_REQUIRE(B > 0 && T > 0 && N > 0 && D > 0 && heads > 0, "rat_attn_bwd: bad shape");
     RAT_REQUIRE(D <= 128, "rat_attn_bwd: D=%d > 128 not supported", D);
     RAT_REQUIRE(out_drop_p >= 0.f && out_drop_p < 1.f, "rat_attn_bwd_dropout: dropout p=%f", out_drop_p);
-    if (precision_mode() == 2 && rr_enabled()) {
+    if (precision_mode() == 2 && rr_enabled() && !getenv("RAT_RR_BWD_OFF")) {
         const int rc3 = attn_bwd_rr_dispatch(x, dout, base, dx, ln_w, ln_b, Wq, Wk, Wv, Wo, dWq, dWk, dWv, dWo, dbo, dln_w,
                                              dln_b, accumulate_wq, B, T, N, D, heads, dim_head, scale, alpha, mode, dout_amax, dx_amax,
                                              workspace, workspace_bytes, out_drop_p, seed, rng_stream, (cudaStream_t)stream);

@@ -295,7 +295,7 @@ extern "C" int rat_attn_fwd(const float* x, const float* res, float* out, const 
     RAT_REQUIRE(mode == 0 || mode == 1, "rat_attn_fwd: mode must be 0 (intra) or 1 (cross)");
     RAT_REQUIRE(Wo != nullptr && bo != nullptr, "rat_attn_fwd: identity out-projection (heads==1 && dim_head==dim) is not supported");
     if (g_precision == 2) {
-        if (rr_enabled()) {
+        if (rr_enabled() && !getenv("RAT_RR_FWD_OFF")) {
             const int rc4 = attn_fwd_rr_dispatch(x, res, out, ln_w, ln_b, Wq, Wk, Wv, Wo, bo, B, T, N, D, heads, dim_head, scale,
                                                  alpha, mode, (cudaStream_t)stream);
             if (rc4 <= 0) return rc4;

@@ -102,6 +102,21 @@ __device__ __forceinline__ void c_to_a(const float (&c)[2][4], uint32_t (&a)[4])
     a[2] = pack_h2(c[1][0], c[1][1]); a[3] = pack_h2(c[1][2], c[1][3]);
 }
 
+// One projection pair-of-n-tiles step  c[16 x 16] += a[16 x 16] . (f.x, f.y | f.z, f.w)  with fp16 (F16P) or fp32 accumulators.
+// ProjAcc<true> keeps packed fp16 accumulators, ProjAcc<false> fp32 ones; frag() returns the 8x8 blocks
+// {rows g cols 0-7, rows g+8 cols 0-7, rows g cols 8-15, rows g+8 cols 8-15} as packed operand registers.
+template <bool F16P> struct ProjAcc;
+template <> struct ProjAcc<true> {
+    uint32_t c[2][2] = {};
+    __device__ __forceinline__ void mma(int nt, const uint32_t (&a)[4], uint32_t b0, uint32_t b1) { mma_hh_16x8x16(c[nt], a, b0, b1); }
+    __device__ __forceinline__ void frag(uint32_t (&f)[4]) const { f[0] = c[0][0]; f[1] = c[0][1]; f[2] = c[1][0]; f[3] = c[1][1]; }
+};
+template <> struct ProjAcc<false> {
+    float c[2][4] = {};
+    __device__ __forceinline__ void mma(int nt, const uint32_t (&a)[4], uint32_t b0, uint32_t b1) { mma_h_16x8x16(c[nt], a, b0, b1); }
+    __device__ __forceinline__ void frag(uint32_t (&f)[4]) const { c_to_a(c, f); }
+};
+
 // Loads the two token rows of this thread (columns 8 nt + 2t, 8 nt + 2t + 1 for nt < NTO, zero beyond D or for absent rows)
 template <int NTO>
 __device__ __forceinline__ void rr_load_rows(const float* __restrict__ plo, const float* __restrict__ phi, bool vlo, bool vhi,
@@ -115,14 +130,15 @@ __device__ __forceinline__ void rr_load_rows(const float* __restrict__ plo, cons
     }
 }
 
-// LayerNorm statistics of one row spread over the 4 threads of a quad (values beyond D are zero on entry)
+// LayerNorm statistics of one row spread over the 4 threads of a quad (values beyond D are zero on entry).
+// invD = 1 / D.  rsqrt.approx (2 ulp) is far below the fp16 rounding of the normalised row that follows.
 template <int NTO>
-__device__ __forceinline__ void rr_row_stats(const float2 (&x)[NTO], int D, int t, float& mean, float& rstd) {
+__device__ __forceinline__ void rr_row_stats(const float2 (&x)[NTO], int D, float invD, int t, float& mean, float& rstd) {
     float s = 0.f;
 #pragma unroll
     for (int nt = 0; nt < NTO; ++nt) s += x[nt].x + x[nt].y;
     s = qsum(s);
-    mean = s / (float)D;
+    mean = s * invD;
     float sq = 0.f;
 #pragma unroll
     for (int nt = 0; nt < NTO; ++nt) {
@@ -131,7 +147,18 @@ __device__ __forceinline__ void rr_row_stats(const float2 (&x)[NTO], int D, int 
         sq = fmaf(a, a, sq); sq = fmaf(b, b, sq);
     }
     sq = qsum(sq);
-    rstd = 1.0f / sqrtf(sq / (float)D + 1e-5f);
+    rstd = rsqrtf(fmaf(sq, invD, 1e-5f));
+}
+
+// ---- bulk asynchronous copies (TMA unit, 1-D): global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc5::smem_u32(bar)), "r"(bytes) : "memory");
+}
+// size and both addresses multiples of 16 bytes
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(tc5::smem_u32(bar))
+                 : "memory");
 }
 
 }  // namespace rat

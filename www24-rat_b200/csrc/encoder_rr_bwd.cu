@@ -43,7 +43,7 @@ constexpr int RRB_THREADS = RRB_CWARPS * 32;
 __device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 5, 256;" ::: "memory"); }
 
-template <int KS, int NTO, bool VEC4, int UNR>
+template <int KS, int NTO, bool VEC4, bool F16P, bool F16C>
 __global__ void __launch_bounds__(RRB_THREADS, 1) k_attn_bwd_rr(AttnBwdRRArgs a) {
     extern __shared__ __align__(128) unsigned char rrb_smem[];
     constexpr int Kp = 16 * KS, KC1 = 2 * KS;
@@ -101,7 +101,8 @@ __global__ void __launch_bounds__(RRB_THREADS, 1) k_attn_bwd_rr(AttnBwdRRArgs a)
                 const int nc = kc * 8 + k;                       // compact column: [q | k | v] x [hl][dd]
                 const int w = nc / (hc * dh), rem2 = nc - w * (hc * dh);
                 const float* W = w == 0 ? a.Wq : w == 1 ? a.Wk : a.Wv;
-                v[k] = (w < 3 && d < D) ? __ldg(W + (size_t)(ch * hc * dh + rem2) * D + d) : 0.f;
+                const float mul = w == 0 ? a.scale : w == 1 ? 0.6931471805599453f : 1.0f;     // dq = scale dQ', dk = ln2 dK'
+                v[k] = (w < 3 && d < D) ? mul * __ldg(W + (size_t)(ch * hc * dh + rem2) * D + d) : 0.f;
             }
             sts128(WT_i + (size_t)ch * Kp * NCc * 2 + tc5::kmajor_off(d, kc, Kp), pack_h2(v[0], v[1]), pack_h2(v[2], v[3]),
                    pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(RRB_THREADS, 1) k_attn_bwd_rr(AttnBwdRRArgs a)
 
     {
         const RRLane cl = make_rr_lane(S, lane);
-        const float kscale = a.scale, ln2 = 0.6931471805599453f;
+        const float invD_ = 1.0f / (float)D;
         const uint32_t row_lo = (uint32_t)(warp * 16 + g) * 16u, row_hi = row_lo + 128u;     // byte offsets of the tile rows
         uint32_t dph = 0;
         int it = 0;
@@ -253,8 +254,8 @@ __global__ void __launch_bounds__(RRB_THREADS, 1) k_attn_bwd_rr(AttnBwdRRArgs a)
                 float2 dl[NTO], dh2[NTO];
                 rr_load_rows<NTO>(a.dout + rlo * D, a.dout + rhi * D, vlo, vhi, D, t, dl, dh2);
                 float ml, rl, mh, rh;
-                rr_row_stats<NTO>(xl, D, t, ml, rl);
-                rr_row_stats<NTO>(xh2, D, t, mh, rh);
+                rr_row_stats<NTO>(xl, D, invD_, t, ml, rl);
+                rr_row_stats<NTO>(xh2, D, invD_, t, mh, rh);
                 if (t == 0) {
                     stats[(pp * 128 + warp * 16 + g) * 2] = ml; stats[(pp * 128 + warp * 16 + g) * 2 + 1] = rl;
                     stats[(pp * 128 + warp * 16 + g + 8) * 2] = mh; stats[(pp * 128 + warp * 16 + g + 8) * 2 + 1] = rh;
@@ -307,29 +308,30 @@ __global__ void __launch_bounds__(RRB_THREADS, 1) k_attn_bwd_rr(AttnBwdRRArgs a)
                 const uint4* wk = Wk_i + (size_t)ch * hc * KS * 32 + lane;
                 const uint4* wv = Wv_i + (size_t)ch * hc * KS * 32 + lane;
                 const uint4* wd = Wd_i + (size_t)ch * hc * KS * 32 + lane;
-#pragma unroll UNR
+#pragma unroll 1
                 for (int hl = 0; hl < hc; ++hl) {
-                    float q[2][4] = {}, k[2][4] = {}, vt[2][4] = {}, dO[2][4] = {};
+                    // the core's outputs (one k-step each) accumulate in fp16: packed accumulators are tile rows as they are;
+                    // the projections (three k-steps) do the same when F16P
+                    ProjAcc<F16P> q, k, vt, dO;
 #pragma unroll
                     for (int ks = 0; ks < KS; ++ks) {
                         const uint4 fq = wq[ks * 32], fk = wk[ks * 32], fv = wv[ks * 32], fd = wd[ks * 32];
-                        mma_h_16x8x16(q[0], xa[ks], fq.x, fq.y);
-                        mma_h_16x8x16(q[1], xa[ks], fq.z, fq.w);
-                        mma_h_16x8x16(k[0], xa[ks], fk.x, fk.y);
-                        mma_h_16x8x16(k[1], xa[ks], fk.z, fk.w);
+                        q.mma(0, xa[ks], fq.x, fq.y);
+                        q.mma(1, xa[ks], fq.z, fq.w);
+                        k.mma(0, xa[ks], fk.x, fk.y);
+                        k.mma(1, xa[ks], fk.z, fk.w);
                         const uint32_t av[4] = {fv.x, fv.z, fv.y, fv.w};
-                        mma_h_16x8x16(vt[0], av, xa[ks][0], xa[ks][2]);
-                        mma_h_16x8x16(vt[1], av, xa[ks][1], xa[ks][3]);
-                        mma_h_16x8x16(dO[0], da[ks], fd.x, fd.y);
-                        mma_h_16x8x16(dO[1], da[ks], fd.z, fd.w);
+                        vt.mma(0, av, xa[ks][0], xa[ks][2]);
+                        vt.mma(1, av, xa[ks][1], xa[ks][3]);
+                        dO.mma(0, da[ks], fd.x, fd.y);
+                        dO.mma(1, da[ks], fd.z, fd.w);
                     }
                     wq += KS * 32; wk += KS * 32; wv += KS * 32; wd += KS * 32;
-                    uint32_t qa[4], ka[4], doa[4];
-                    c_to_a(q, qa); c_to_a(k, ka); c_to_a(dO, doa);
-                    // packed 8x8 blocks of v^T: [dd block][token block]
-                    const uint32_t v00 = pack_h2(vt[0][0], vt[0][1]), v10 = pack_h2(vt[0][2], vt[0][3]);
-                    const uint32_t v01 = pack_h2(vt[1][0], vt[1][1]), v11 = pack_h2(vt[1][2], vt[1][3]);
-                    // ---- S = q k^T (keys 0..7: rows g of k, keys 8..15: rows g + 8) ; dP = dO v^T
+                    // 8x8 blocks {rows g / cols 0-7, rows g+8 / cols 0-7, rows g / cols 8-15, rows g+8 / cols 8-15} of q, k, dO, v^T
+                    uint32_t qa[4], ka[4], doa[4], va[4];
+                    q.frag(qa); k.frag(ka); dO.frag(doa); vt.frag(va);
+                    const uint32_t v00 = va[0], v10 = va[1], v01 = va[2], v11 = va[3];     // [dd block][token block]
+                    // ---- S = q k^T (keys 0..7: rows g of k, keys 8..15: rows g + 8) ; dP = dO v^T   (fp32)
                     float sc[2][4] = {}, dp[2][4] = {};
                     mma_h_16x8x16(sc[0], qa, ka[0], ka[2]);
                     mma_h_16x8x16(sc[1], qa, ka[1], ka[3]);
@@ -353,16 +355,19 @@ __global__ void __launch_bounds__(RRB_THREADS, 1) k_attn_bwd_rr(AttnBwdRRArgs a)
                     c_to_a(dp, sa);
                     const uint32_t pt[4] = {movm_t(pa[0]), movm_t(pa[2]), movm_t(pa[1]), movm_t(pa[3])};             // P^T
                     const uint32_t st[4] = {movm_t(sa[0]), movm_t(sa[2]), movm_t(sa[1]), movm_t(sa[3])};             // dS^T
-                    // ---- O = P v ; dV = P^T dO ; dQ = dS k ; dK = dS^T q
-                    float o[2][4] = {}, dv[2][4] = {}, dq[2][4] = {}, dk[2][4] = {};
-                    mma_h_16x8x16(o[0], pa, v00, v01);
-                    mma_h_16x8x16(o[1], pa, v10, v11);
-                    mma_h_16x8x16(dv[0], pt, movm_t(doa[0]), movm_t(doa[1]));
-                    mma_h_16x8x16(dv[1], pt, movm_t(doa[2]), movm_t(doa[3]));
-                    mma_h_16x8x16(dq[0], sa, movm_t(ka[0]), movm_t(ka[1]));
-                    mma_h_16x8x16(dq[1], sa, movm_t(ka[2]), movm_t(ka[3]));
-                    mma_h_16x8x16(dk[0], st, movm_t(qa[0]), movm_t(qa[1]));
-                    mma_h_16x8x16(dk[1], st, movm_t(qa[2]), movm_t(qa[3]));
+                    // ---- O = P v ; dV = P^T dO ; dQ' = dS k ; dK' = dS^T q'   (dq = scale dQ', dk = ln2 dK': folded into the
+                    //      dA weight image and the record reduction, so the packed accumulators go to the tile as they are)
+                    ProjAcc<F16C> o, dv, dq, dk;
+                    o.mma(0, pa, v00, v01);
+                    o.mma(1, pa, v10, v11);
+                    dv.mma(0, pt, movm_t(doa[0]), movm_t(doa[1]));
+                    dv.mma(1, pt, movm_t(doa[2]), movm_t(doa[3]));
+                    dq.mma(0, sa, movm_t(ka[0]), movm_t(ka[1]));
+                    dq.mma(1, sa, movm_t(ka[2]), movm_t(ka[3]));
+                    dk.mma(0, st, movm_t(qa[0]), movm_t(qa[1]));
+                    dk.mma(1, st, movm_t(qa[2]), movm_t(qa[3]));
+                    uint32_t of[4], dvf[4], dqf[4], dkf[4];          // {rows g / d 0-7, rows g+8 / d 0-7, rows g / d 8-15, rows g+8 / d 8-15}
+                    o.frag(of); dv.frag(dvf); dq.frag(dqf); dk.frag(dkf);
                     // ---- compact fp16 rows of the token tile: dq | dk | dv at columns [part * hc*dh + hl*dh + d], O after them
 #pragma unroll
                     for (int nd = 0; nd < 2; ++nd) {
@@ -371,14 +376,14 @@ __global__ void __launch_bounds__(RRB_THREADS, 1) k_attn_bwd_rr(AttnBwdRRArgs a)
                             const int cq = hl * dh + d;
                             const uint32_t oq = Gt_s + coltab[cq], ok = Gt_s + coltab[cq + hc * dh], ov = Gt_s + coltab[cq + 2 * hc * dh];
                             const uint32_t oo = Gt_s + coltab[NCc + cq];
-                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(oq + row_lo), "r"(pack_h2(dq[nd][0] * kscale, dq[nd][1] * kscale)) : "memory");
-                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(oq + row_hi), "r"(pack_h2(dq[nd][2] * kscale, dq[nd][3] * kscale)) : "memory");
-                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(ok + row_lo), "r"(pack_h2(dk[nd][0] * ln2, dk[nd][1] * ln2)) : "memory");
-                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(ok + row_hi), "r"(pack_h2(dk[nd][2] * ln2, dk[nd][3] * ln2)) : "memory");
-                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(ov + row_lo), "r"(pack_h2(dv[nd][0], dv[nd][1])) : "memory");
-                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(ov + row_hi), "r"(pack_h2(dv[nd][2], dv[nd][3])) : "memory");
-                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(oo + row_lo), "r"(pack_h2(o[nd][0], o[nd][1])) : "memory");
-                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(oo + row_hi), "r"(pack_h2(o[nd][2], o[nd][3])) : "memory");
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(oq + row_lo), "r"(dqf[2 * nd]) : "memory");
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(oq + row_hi), "r"(dqf[2 * nd + 1]) : "memory");
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(ok + row_lo), "r"(dkf[2 * nd]) : "memory");
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(ok + row_hi), "r"(dkf[2 * nd + 1]) : "memory");
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(ov + row_lo), "r"(dvf[2 * nd]) : "memory");
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(ov + row_hi), "r"(dvf[2 * nd + 1]) : "memory");
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(oo + row_lo), "r"(of[2 * nd]) : "memory");
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(oo + row_hi), "r"(of[2 * nd + 1]) : "memory");
                         }
                     }
                 }
@@ -461,25 +466,25 @@ __global__ void __launch_bounds__(RRB_THREADS, 1) k_attn_bwd_rr(AttnBwdRRArgs a)
     if (warp == 0) tc5::tmem_dealloc(tmem_base_s, (uint32_t)a.tmem_cols);
 }
 
-template <int KS, int NTO, bool VEC4, int UNR>
+template <int KS, int NTO, bool VEC4, bool F16P, bool F16C>
 static int launch_attn_bwd_rr_v(const AttnBwdRRArgs& a, int grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_attn_bwd_rr<KS, NTO, VEC4, UNR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(k_attn_bwd_rr<KS, NTO, VEC4, F16P, F16C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              max_smem_optin() - 2048);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_attn_bwd_rr)");
         attr_set = true;
     }
-    k_attn_bwd_rr<KS, NTO, VEC4, UNR><<<grid, RRB_THREADS, a.smem_bytes, st>>>(a);
+    k_attn_bwd_rr<KS, NTO, VEC4, F16P, F16C><<<grid, RRB_THREADS, a.smem_bytes, st>>>(a);
     RAT_CHECK_LAUNCH("k_attn_bwd_rr");
     return RAT_OK;
 }
 template <int KS, int NTO, bool VEC4>
 static int launch_attn_bwd_rr(const AttnBwdRRArgs& a, int grid, cudaStream_t st) {
-    static int variant = -1;     // RAT_RR_BWD_VARIANT (tuning aid): heads in flight per warp
-    if (variant < 0) { const char* e = getenv("RAT_RR_BWD_VARIANT"); variant = e ? atoi(e) : 1; }
-    if (variant == 2) return launch_attn_bwd_rr_v<KS, NTO, VEC4, 2>(a, grid, st);
-    return launch_attn_bwd_rr_v<KS, NTO, VEC4, 1>(a, grid, st);
+    static int variant = -1;     // RAT_RR_BWD_VARIANT (tuning aid): 1 = fp16 accumulators for everything but S and dP (see the forward)
+    if (variant < 0) { const char* e = getenv("RAT_RR_BWD_VARIANT"); variant = e ? atoi(e) : 0; }
+    if (variant == 1) return launch_attn_bwd_rr_v<KS, NTO, VEC4, true, true>(a, grid, st);
+    return launch_attn_bwd_rr_v<KS, NTO, VEC4, false, false>(a, grid, st);
 }
 
 static bool attn_bwd_rr_plan(int S, int D, int heads, int dh, AttnBwdRRArgs* a) {
@@ -558,7 +563,7 @@ int attn_bwd_rr_dispatch(const float* x, const float* dout, const float* base, f
 #undef RAT_RRB
     if (rc != RAT_OK) return rc;
     AttnReduceTcArgs r{workspace, grid, a.psize, dWq, dWk, dWv, dWo, dbo, dln_w, dln_b, accumulate_wq, D, a.I, dh, a.hc,
-                       a.nchunks, pad16(D), a.NCc, a.Cc};
+                       a.nchunks, pad16(D), a.NCc, a.Cc, scale, 0.6931471805599453f};
     const int total = 4 * a.I * D + 3 * D;
     k_reduce_attn_tc<<<std::max(1, std::min((total + 31) / 32, 1024)), dim3(32, 8), 0, st>>>(r);
     RAT_CHECK_LAUNCH("k_reduce_attn_tc");

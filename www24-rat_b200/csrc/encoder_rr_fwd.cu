@@ -16,15 +16,15 @@ struct AttnRRArgs {
     float qscale, alpha;
 };
 
-// KS = pad16(D) / 16 k-steps of the projections, NTO = ceil(D / 8) n-tiles of a token row.
-// WARPS x CTAS warps per SM and UNR heads in flight per warp trade registers for latency hiding (HMMA latency on B200 is
-// ~100 cycles: tools/hmma_probe.cu, so one head at a time leaves a warp mostly waiting on its own dependency chain).
-template <int KS, int NTO, int WARPS, int CTAS, int UNR>
+// KS = pad16(D) / 16 k-steps of the projections, NTO = ceil(D / 8) n-tiles of a token row.  WARPS x CTAS warps per SM.
+// BULK (D % 4 == 0): every warp keeps the token rows of its NEXT task in flight as 1-D bulk asynchronous copies
+// (cp.async.bulk, one per row, completion counted on a per-warp mbarrier) into a private double buffer, so a task starts on
+// rows that are already in shared memory and the residual add re-reads them there instead of from L2.
+template <int KS, int NTO, int WARPS, int CTAS, bool BULK, bool F16P, bool F16C>
 __global__ void __launch_bounds__(WARPS * 32, CTAS) k_attn_fwd_rr(AttnRRArgs a) {
-    constexpr int RR_FWD_THREADS = WARPS * 32;
     extern __shared__ __align__(16) uint4 rr_smem[];
     constexpr int NP = (NTO + 1) / 2;                     // n-tile pairs of the out-projection
-    const int H = a.H, D = a.D, dh = a.dh;
+    const int H = a.H, D = a.D, dh = a.dh, I = a.I;
     uint4* Wq_i = rr_smem;                                // [H][KS][32]
     uint4* Wk_i = Wq_i + H * KS * 32;
     uint4* Wv_i = Wk_i + H * KS * 32;
@@ -32,46 +32,84 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_attn_fwd_rr(AttnRRArgs a) 
     float* lnw_s = reinterpret_cast<float*>(Wo_i + H * NP * 32);   // [KS * 16], zero padded
     float* lnb_s = lnw_s + KS * 16;
     float* bo_s = lnb_s + KS * 16;                        // [NP * 16]
+    float* stage = bo_s + NP * 16;                        // BULK: [WARPS][2][16 rows][D] ; during setup: raw fp32 weights
+    __shared__ __align__(8) uint64_t row_bar[WARPS][2];
     {
-        const int nqkv = H * KS * 32;
-        for (int i = threadIdx.x; i < 3 * nqkv; i += blockDim.x) {
-            const int w = i / nqkv, r = i - w * nqkv;
-            const int h = r / (KS * 32), ks = (r >> 5) % KS, ln = r & 31;
-            const float* W = (w == 0 ? a.Wq : w == 1 ? a.Wk : a.Wv) + (size_t)h * dh * D;
-            const float mul = w == 0 ? a.qscale : 1.0f;
-            rr_smem[i] = frag_pair_entry(ln, 0, 16 * ks, [&](int n, int k) {
-                return (n < dh && k < D) ? mul * __ldg(W + (size_t)n * D + k) : 0.f; });
-        }
-        for (int i = threadIdx.x; i < H * NP * 32; i += blockDim.x) {
-            const int h = i / (NP * 32), p = (i >> 5) % NP, ln = i & 31;
-            const float* W = a.Wo + h * dh;
-            Wo_i[i] = frag_pair_entry(ln, 16 * p, 0, [&](int c, int dd) {
-                return (c < D && dd < dh) ? __ldg(W + (size_t)c * a.I + dd) : 0.f; });
+        // raw weights with coalesced loads (one memory latency), then the fragment-order images from shared memory
+        float* raw = stage;                               // Wq | Wk | Wv [3][I][D], Wo [D][I]
+        const int nw = I * D;
+        for (int i = threadIdx.x; i < nw; i += blockDim.x) {
+            raw[i] = __ldg(a.Wq + i); raw[nw + i] = __ldg(a.Wk + i); raw[2 * nw + i] = __ldg(a.Wv + i); raw[3 * nw + i] = __ldg(a.Wo + i);
         }
         for (int i = threadIdx.x; i < KS * 16; i += blockDim.x) {
             lnw_s[i] = i < D ? a.ln_w[i] : 0.f;
             lnb_s[i] = i < D ? a.ln_b[i] : 0.f;
         }
         for (int i = threadIdx.x; i < NP * 16; i += blockDim.x) bo_s[i] = i < D ? a.bo[i] : 0.f;
+        __syncthreads();
+        const int nqkv = H * KS * 32;
+        for (int i = threadIdx.x; i < 3 * nqkv; i += blockDim.x) {
+            const int w = i / nqkv, r = i - w * nqkv;
+            const int h = r / (KS * 32), ks = (r >> 5) % KS, ln = r & 31;
+            const float* W = raw + w * nw + h * dh * D;
+            const float mul = w == 0 ? a.qscale : 1.0f;
+            rr_smem[i] = frag_pair_entry(ln, 0, 16 * ks, [&](int n, int k) { return (n < dh && k < D) ? mul * W[n * D + k] : 0.f; });
+        }
+        for (int i = threadIdx.x; i < H * NP * 32; i += blockDim.x) {
+            const int h = i / (NP * 32), p = (i >> 5) % NP, ln = i & 31;
+            const float* W = raw + 3 * nw + h * dh;
+            Wo_i[i] = frag_pair_entry(ln, 16 * p, 0, [&](int c, int dd) { return (c < D && dd < dh) ? W[c * I + dd] : 0.f; });
+        }
+        if (threadIdx.x < WARPS * 2) tc5::mbar_init(&row_bar[0][0] + threadIdx.x, 1);
+        tc5::fence_mbar_init();
+        tc5::fence_proxy_async();        // the raw-weight region becomes the target of bulk copies
     }
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = lane & 3;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = lane & 3, g = lane >> 2;
     const int S = a.g.S;
+    const float invD = 1.0f / (float)D;
     const RRLane cl = make_rr_lane(S, lane);
     const long long ntasks = cl.packed ? (a.nseq + 1) >> 1 : a.nseq;
-    const long long wstride = (long long)gridDim.x * (RR_FWD_THREADS / 32);
-    for (long long task = (long long)blockIdx.x * (RR_FWD_THREADS / 32) + warp; task < ntasks; task += wstride) {
+    const long long wstride = (long long)gridDim.x * WARPS;
+    const bool res_is_x = a.res == a.x;
+    // bulk staging: lane i < 16 owns fragment row i of the task
+    float* my_stage = stage + (size_t)warp * 2 * 16 * D;
+    const int c_sq = cl.packed ? (lane >> 3) & 1 : 0, c_pos = cl.packed ? (lane & 7) : lane;
+    const bool c_row = lane < 16 && c_pos < S;
+    auto issue_rows = [&](long long task, int buf) {
+        const long long seq0 = cl.packed ? 2 * task : task;
+        const bool ok = c_row && seq0 + c_sq < a.nseq;
+        const unsigned int m = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) mbar_arrive_expect_tx(&row_bar[warp][buf], (uint32_t)(__popc(m) * D * 4));
+        __syncwarp();
+        if (ok) bulk_g2s(tc5::smem_u32(my_stage + (size_t)(buf * 16 + lane) * D), a.x + a.g.grow(seq0 + c_sq, c_pos) * D, (uint32_t)(D * 4),
+                         &row_bar[warp][buf]);
+    };
+    long long task = (long long)blockIdx.x * WARPS + warp;
+    uint32_t ph0 = 0, ph1 = 0;
+    int buf = 0;
+    if (BULK && task < ntasks) issue_rows(task, 0);
+    for (; task < ntasks; task += wstride, buf ^= 1) {
         const long long seq0 = cl.packed ? 2 * task : task;
         const bool vlo = cl.lo_pos >= 0, vhi = cl.hi_pos >= 0 && seq0 + cl.hi_sq < a.nseq;
         const long long rlo = vlo ? a.g.grow(seq0, cl.lo_pos) : 0, rhi = vhi ? a.g.grow(seq0 + cl.hi_sq, cl.hi_pos) : 0;
+        const float* slo = my_stage + (size_t)(buf * 16 + g) * D;          // staged rows g and g + 8
+        const float* shi = slo + 8 * D;
         // ---- rows -> LayerNorm -> A fragments
         uint32_t xa[KS][4];
         {
             float2 xl[NTO], xh[NTO];
-            rr_load_rows<NTO>(a.x + rlo * D, a.x + rhi * D, vlo, vhi, D, t, xl, xh);
+            if (BULK) {
+                if (task + wstride < ntasks) issue_rows(task + wstride, buf ^ 1);     // the other buffer was consumed a task ago
+                tc5::mbar_wait(&row_bar[warp][buf], buf ? ph1 : ph0);
+                if (buf) ph1 ^= 1; else ph0 ^= 1;
+                rr_load_rows<NTO>(slo, shi, vlo, vhi, D, t, xl, xh);
+            } else {
+                rr_load_rows<NTO>(a.x + rlo * D, a.x + rhi * D, vlo, vhi, D, t, xl, xh);
+            }
             float ml, rl, mh, rh;
-            rr_row_stats<NTO>(xl, D, t, ml, rl);
-            rr_row_stats<NTO>(xh, D, t, mh, rh);
+            rr_row_stats<NTO>(xl, D, invD, t, ml, rl);
+            rr_row_stats<NTO>(xh, D, invD, t, mh, rh);
 #pragma unroll
             for (int nt = 0; nt < 2 * KS; ++nt) {
                 uint32_t lo = 0u, hi = 0u;
@@ -92,34 +130,36 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_attn_fwd_rr(AttnRRArgs a) 
         const uint4* wk = Wk_i + lane;
         const uint4* wv = Wv_i + lane;
         const uint4* wo = Wo_i + lane;
-#pragma unroll UNR
+#pragma unroll 1
         for (int h = 0; h < H; ++h) {
-            float q[2][4] = {}, k[2][4] = {}, vt[2][4] = {};
+            // O (one k-step) accumulates in fp16: its packed accumulators ARE the out-projection's operand fragment; the
+            // projections (three k-steps) do the same when F16P
+            ProjAcc<F16P> q, k, vt;
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
                 const uint4 fq = wq[ks * 32], fk = wk[ks * 32], fv = wv[ks * 32];
-                mma_h_16x8x16(q[0], xa[ks], fq.x, fq.y);
-                mma_h_16x8x16(q[1], xa[ks], fq.z, fq.w);
-                mma_h_16x8x16(k[0], xa[ks], fk.x, fk.y);
-                mma_h_16x8x16(k[1], xa[ks], fk.z, fk.w);
+                q.mma(0, xa[ks], fq.x, fq.y);
+                q.mma(1, xa[ks], fq.z, fq.w);
+                k.mma(0, xa[ks], fk.x, fk.y);
+                k.mma(1, xa[ks], fk.z, fk.w);
                 const uint32_t av[4] = {fv.x, fv.z, fv.y, fv.w};
-                mma_h_16x8x16(vt[0], av, xa[ks][0], xa[ks][2]);      // tokens 0..7  (fragment rows g)
-                mma_h_16x8x16(vt[1], av, xa[ks][1], xa[ks][3]);      // tokens 8..15 (fragment rows g + 8)
+                vt.mma(0, av, xa[ks][0], xa[ks][2]);                 // tokens 0..7  (fragment rows g)
+                vt.mma(1, av, xa[ks][1], xa[ks][3]);                 // tokens 8..15 (fragment rows g + 8)
             }
             wq += KS * 32; wk += KS * 32; wv += KS * 32;
-            uint32_t qa[4];
-            c_to_a(q, qa);
+            uint32_t qa[4], ka[4], va[4];                            // 8x8 blocks {lo/0-7, hi/0-7, lo/8-15, hi/8-15}
+            q.frag(qa); k.frag(ka); vt.frag(va);
             float sc[2][4] = {};
-            mma_h_16x8x16(sc[0], qa, pack_h2(k[0][0], k[0][1]), pack_h2(k[1][0], k[1][1]));     // keys 0..7
-            mma_h_16x8x16(sc[1], qa, pack_h2(k[0][2], k[0][3]), pack_h2(k[1][2], k[1][3]));     // keys 8..15
+            mma_h_16x8x16(sc[0], qa, ka[0], ka[2]);                  // keys 0..7  (rows g of k)
+            mma_h_16x8x16(sc[1], qa, ka[1], ka[3]);                  // keys 8..15 (rows g + 8)
             rr_softmax(sc, cl, vlo, vhi);
             uint32_t pa[4];
             c_to_a(sc, pa);
-            float o[2][4] = {};
-            mma_h_16x8x16(o[0], pa, pack_h2(vt[0][0], vt[0][1]), pack_h2(vt[1][0], vt[1][1]));  // d 0..7
-            mma_h_16x8x16(o[1], pa, pack_h2(vt[0][2], vt[0][3]), pack_h2(vt[1][2], vt[1][3]));  // d 8..15
+            ProjAcc<F16C> o;
+            o.mma(0, pa, va[0], va[2]);                              // d 0..7
+            o.mma(1, pa, va[1], va[3]);                              // d 8..15
             uint32_t oa[4];
-            c_to_a(o, oa);
+            o.frag(oa);
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
                 const uint4 f = wo[p * 32];
@@ -130,8 +170,9 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_attn_fwd_rr(AttnRRArgs a) 
         }
         // ---- out = res + alpha * (acc + bo)
         {
-            const float* rl_p = a.res ? a.res + rlo * D : nullptr;
-            const float* rh_p = a.res ? a.res + rhi * D : nullptr;
+            const bool from_stage = BULK && res_is_x;
+            const float* rl_p = from_stage ? slo : a.res ? a.res + rlo * D : nullptr;
+            const float* rh_p = from_stage ? shi : a.res ? a.res + rhi * D : nullptr;
             float* ol = a.out + rlo * D;
             float* oh = a.out + rhi * D;
 #pragma unroll
@@ -152,39 +193,41 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_attn_fwd_rr(AttnRRArgs a) 
                 }
             }
         }
+        if (BULK) __syncwarp();          // every lane is done with this buffer before it is refilled (next iteration's issue)
     }
 }
 
-template <int KS, int NTO, int WARPS, int CTAS, int UNR>
+template <int KS, int NTO, int WARPS, int CTAS, bool BULK, bool F16P, bool F16C>
 static int launch_attn_fwd_rr_v(const AttnRRArgs& a, cudaStream_t st) {
     constexpr int NP = (NTO + 1) / 2;
-    const size_t smem = ((size_t)3 * a.H * KS * 32 + (size_t)a.H * NP * 32) * sizeof(uint4) + (size_t)(2 * KS * 16 + NP * 16) * 4;
+    const size_t stage_bytes = std::max((size_t)(BULK ? WARPS * 2 * 16 * a.D * 4 : 0), (size_t)4 * a.I * a.D * 4);
+    const size_t smem = ((size_t)3 * a.H * KS * 32 + (size_t)a.H * NP * 32) * sizeof(uint4) + (size_t)(2 * KS * 16 + NP * 16) * 4 + stage_bytes;
     if (smem > (size_t)max_smem_optin() / CTAS - 2048) return 1;
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
-        cudaError_t e = cudaFuncSetAttribute(k_attn_fwd_rr<KS, NTO, WARPS, CTAS, UNR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_attn_fwd_rr<KS, NTO, WARPS, CTAS, BULK, F16P, F16C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_attn_fwd_rr)");
         attr_smem = smem;
     }
     const long long ntasks = a.g.S <= 8 ? (a.nseq + 1) / 2 : a.nseq;
     const long long nblk = (ntasks + WARPS - 1) / WARPS;
     const int grid = (int)std::min<long long>(nblk, (long long)CTAS * num_sms());
-    k_attn_fwd_rr<KS, NTO, WARPS, CTAS, UNR><<<grid, WARPS * 32, smem, st>>>(a);
+    k_attn_fwd_rr<KS, NTO, WARPS, CTAS, BULK, F16P, F16C><<<grid, WARPS * 32, smem, st>>>(a);
     RAT_CHECK_LAUNCH("k_attn_fwd_rr");
     return RAT_OK;
 }
-// RAT_RR_FWD_VARIANT (tuning aid): 0 = 8 warps x 2 CTAs, one head in flight ; 1 = 12 warps, 2 heads ; 2 = 8 warps, 4 heads
+// RAT_RR_FWD_VARIANT (tuning aid): 0 = bulk row staging, fp32 accumulators (default) ; 1 = fp16 accumulators for q, k, v^T, O
+// (4 % faster, but the 15-step AUC / logloss comparison with the fp32 oracle drifts past the 1e-3 bar) ; 2 = direct loads
 template <int KS, int NTO>
 static int launch_attn_fwd_rr(const AttnRRArgs& a, cudaStream_t st) {
     static int variant = -1;
     if (variant < 0) { const char* e = getenv("RAT_RR_FWD_VARIANT"); variant = e ? atoi(e) : 0; }
-    switch (variant) {
-        case 1: return launch_attn_fwd_rr_v<KS, NTO, 12, 1, 2>(a, st);
-        case 2: return launch_attn_fwd_rr_v<KS, NTO, 8, 1, 4>(a, st);
-        case 3: return launch_attn_fwd_rr_v<KS, NTO, 8, 2, 2>(a, st);
-        case 4: return launch_attn_fwd_rr_v<KS, NTO, 16, 1, 1>(a, st);
-        default: return launch_attn_fwd_rr_v<KS, NTO, 8, 2, 1>(a, st);
-    }
+    const bool bulk_ok = (a.D % 4) == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0;
+    int rc = 1;
+    if (bulk_ok && variant == 0) rc = launch_attn_fwd_rr_v<KS, NTO, 16, 1, true, false, false>(a, st);
+    if (bulk_ok && variant == 1) rc = launch_attn_fwd_rr_v<KS, NTO, 16, 1, true, true, true>(a, st);
+    if (rc == 1) rc = launch_attn_fwd_rr_v<KS, NTO, 16, 1, false, false, false>(a, st);
+    return rc;
 }
 
 }  // namespace rat

@@ -201,6 +201,14 @@ __device__ __forceinline__ void mma_h_16x8x16(float (&c)[4], const uint32_t (&a)
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 #endif
 }
+// fp16 ACCUMULATORS (two packed registers: c[0] = row g, columns 2t, 2t+1 ; c[1] = row g + 8): the result is directly the
+// packed operand fragment of a following product -- no cvt.f16x2 (F2FP runs on the XU pipe at 16 cycles per warp instruction
+// on B200 and was the busiest unit of the register-resident attention kernels).  Only the fp16 build has it.
+__device__ __forceinline__ void mma_hh_16x8x16(uint32_t (&c)[2], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f16.f16.f16.f16 {%0,%1}, {%2,%3,%4,%5}, {%6,%7}, {%0,%1};"
+                 : "+r"(c[0]), "+r"(c[1])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 __device__ __forceinline__ float ex2f(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

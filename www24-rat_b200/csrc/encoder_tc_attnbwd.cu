@@ -90,7 +90,7 @@ int attn_bwd_tc_dispatch(const float* x, const float* dout, const float* base, f
     }
     if (rc != RAT_OK) return rc;
     AttnReduceTcArgs r{workspace, grid, a.psize, dWq, dWk, dWv, dWo, dbo, dln_w, dln_b, accumulate_wq, D, a.I, dh, a.hc,
-                       a.nchunks, a.Kp, a.NCc, a.Cc};
+                       a.nchunks, a.Kp, a.NCc, a.Cc, 1.0f, 1.0f};
     const int total = 4 * a.I * D + 3 * D;
     k_reduce_attn_tc<<<std::max(1, std::min((total + 31) / 32, 1024)), dim3(32, 8), 0, st>>>(r);
     RAT_CHECK_LAUNCH("k_reduce_attn_tc");

@@ -520,6 +520,7 @@ struct AttnReduceTcArgs {
     const float* partials; int nparts, psize;
     float* dWq; float* dWk; float* dWv; float* dWo; float* dbo; float* dln_w; float* dln_b;
     int accumulate_wq, D, I, dh, hc, nchunks, Kp, NCc, Cc;
+    float qmul, kmul;        // multipliers of the dWq / dWk records (the register-resident kernel stores dq / scale, dk / ln2)
 };
 static __global__ void k_reduce_attn_tc(AttnReduceTcArgs a) {
     const int D = a.D, I = a.I;
@@ -552,7 +553,8 @@ static __global__ void k_reduce_attn_tc(AttnReduceTcArgs a) {
             float* b = which == 0 ? a.dbo : which == 1 ? a.dln_w : a.dln_b;
             dst = b ? b + d : nullptr;
         }
-        const float s = record_sum_sliced(a.partials, a.psize, a.nparts, src, active && dst != nullptr);
+        float s = record_sum_sliced(a.partials, a.psize, a.nparts, src, active && dst != nullptr);
+        if (i < I * D) s *= a.qmul; else if (i < 2 * I * D) s *= a.kmul;
         if (active && dst != nullptr && threadIdx.y == 0) *dst = accf ? *dst + s : s;
     }
 }
