@@ -1,4 +1,5 @@
-timeout 600 python -m pytest tests -m gpu -x -q -k "attn_fwd or attn_bwd" 2>&1 | tail -15
+timeout 600 python -m pytest tests -m gpu -x -q -k "attn_bwd" 2>&1 | tail -3
+timeout 100 python tools/bench_attn.py kkbox 4096 5 2>&1 | grep bwd
 T='tests/test_gpu_backward.py::test_auc_logloss_after_fixed_steps_match_oracle'
-for i in 1 2 3; do timeout 300 python -m pytest "$T" -m gpu -q -k "fp16 and tmall" -s 2>&1 | grep -E "AUC oracle"; done
-for i in 1 2; do RAT_RR=0 timeout 300 python -m pytest "$T" -m gpu -q -k "fp16 and tmall" -s 2>&1 | grep -E "AUC oracle"; done
+timeout 300 python -m pytest "$T" -m gpu -q -k "tmall" -s 2>&1 | grep -E "AUC oracle|passed|failed"
+RAT_RR=0 timeout 300 python -m pytest "$T" -m gpu -q -k "tmall and fp16" -s 2>&1 | grep -E "AUC oracle|passed|failed"

@@ -74,21 +74,30 @@ __global__ void __launch_bounds__(RRB_THREADS, 1) k_attn_bwd_rr(AttnBwdRRArgs a)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = lane & 3, g = lane >> 2;
     const float gs = tc_grad_scale(a.dout_amax), inv_gs = 1.0f / gs;
-    // ---- images
+    // ---- images (raw weights first, with coalesced loads, into the token-tile region; then fragment order from shared memory)
     {
+        float* raw = reinterpret_cast<float*>(Xt);        // Wq | Wk | Wv [3][I][D], Wo [D][I]: 16 I D bytes <= the tile region (plan)
+        const int nw = a.I * D;
+        for (int i = threadIdx.x; i < nw; i += blockDim.x) {
+            raw[i] = __ldg(a.Wq + i); raw[nw + i] = __ldg(a.Wk + i); raw[2 * nw + i] = __ldg(a.Wv + i); raw[3 * nw + i] = __ldg(a.Wo + i);
+        }
+        for (int i = threadIdx.x; i < Kp; i += blockDim.x) {
+            lnw_s[i] = i < D ? a.ln_w[i] : 0.f;
+            lnb_s[i] = i < D ? a.ln_b[i] : 0.f;
+        }
+        for (int c = threadIdx.x; c < NCc + Cc; c += blockDim.x) coltab[c] = (uint32_t)(c >> 3) * tc5::TILE_CHUNK + (uint32_t)(c & 7) * 2u;
+        __syncthreads();
         const int nqkv = H * KS * 32;
         for (int i = threadIdx.x; i < 4 * nqkv; i += blockDim.x) {
             const int w = i / nqkv, r = i - w * nqkv;
             const int h = r / (KS * 32), ks = (r >> 5) % KS, ln = r & 31;
             if (w < 3) {
-                const float* W = (w == 0 ? a.Wq : w == 1 ? a.Wk : a.Wv) + (size_t)h * dh * D;
+                const float* W = raw + w * nw + h * dh * D;
                 const float mul = w == 0 ? a.scale * 1.4426950408889634f : 1.0f;
-                Wq_i[i] = frag_pair_entry(ln, 0, 16 * ks, [&](int n, int k) {
-                    return (n < dh && k < D) ? mul * __ldg(W + (size_t)n * D + k) : 0.f; });
+                Wq_i[i] = frag_pair_entry(ln, 0, 16 * ks, [&](int n, int k) { return (n < dh && k < D) ? mul * W[n * D + k] : 0.f; });
             } else {
-                const float* W = a.Wo + h * dh;
-                Wq_i[i] = frag_pair_entry(ln, 0, 16 * ks, [&](int dd, int c) {
-                    return (dd < dh && c < D) ? __ldg(W + (size_t)c * a.I + dd) : 0.f; });
+                const float* W = raw + 3 * nw + h * dh;
+                Wq_i[i] = frag_pair_entry(ln, 0, 16 * ks, [&](int dd, int c) { return (dd < dh && c < D) ? W[c * a.I + dd] : 0.f; });
             }
         }
         const int KCc = NCc >> 3, perT = Kp * KCc;
@@ -100,18 +109,13 @@ __global__ void __launch_bounds__(RRB_THREADS, 1) k_attn_bwd_rr(AttnBwdRRArgs a)
             for (int k = 0; k < 8; ++k) {
                 const int nc = kc * 8 + k;                       // compact column: [q | k | v] x [hl][dd]
                 const int w = nc / (hc * dh), rem2 = nc - w * (hc * dh);
-                const float* W = w == 0 ? a.Wq : w == 1 ? a.Wk : a.Wv;
                 const float mul = w == 0 ? a.scale : w == 1 ? 0.6931471805599453f : 1.0f;     // dq = scale dQ', dk = ln2 dK'
-                v[k] = (w < 3 && d < D) ? mul * __ldg(W + (size_t)(ch * hc * dh + rem2) * D + d) : 0.f;
+                v[k] = (w < 3 && d < D) ? mul * raw[w * nw + (ch * hc * dh + rem2) * D + d] : 0.f;
             }
             sts128(WT_i + (size_t)ch * Kp * NCc * 2 + tc5::kmajor_off(d, kc, Kp), pack_h2(v[0], v[1]), pack_h2(v[2], v[3]),
                    pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
         }
-        for (int i = threadIdx.x; i < Kp; i += blockDim.x) {
-            lnw_s[i] = i < D ? a.ln_w[i] : 0.f;
-            lnb_s[i] = i < D ? a.ln_b[i] : 0.f;
-        }
-        for (int c = threadIdx.x; c < NCc + Cc; c += blockDim.x) coltab[c] = (uint32_t)(c >> 3) * tc5::TILE_CHUNK + (uint32_t)(c & 7) * 2u;
+        __syncthreads();
         const int tile16 = (2 * KC1 + ((NCc + Cc) >> 3)) * (int)tc5::TILE_CHUNK / 16;   // pad columns are never written: zero once
         for (int i = threadIdx.x; i < tile16; i += blockDim.x) reinterpret_cast<uint4*>(Xt)[i] = make_uint4(0u, 0u, 0u, 0u);
     }
@@ -253,6 +257,18 @@ __global__ void __launch_bounds__(RRB_THREADS, 1) k_attn_bwd_rr(AttnBwdRRArgs a)
                 rr_load_rows<NTO>(a.x + rlo * D, a.x + rhi * D, vlo, vhi, D, t, xl, xh2);
                 float2 dl[NTO], dh2[NTO];
                 rr_load_rows<NTO>(a.dout + rlo * D, a.dout + rhi * D, vlo, vhi, D, t, dl, dh2);
+                // pull the rows of this warp's NEXT tile towards L2 (x was written a whole forward pass ago)
+                if (tile + gridDim.x < ntiles) {
+                    const long long task1 = task + (long long)gridDim.x * RRB_CWARPS;
+                    const long long seq1 = packed ? 2 * task1 : task1;
+                    const int r16 = lane & 15;
+                    const int p_sq = packed ? r16 >> 3 : 0, p_pos = packed ? r16 & 7 : r16;
+                    if (p_pos < S && seq1 + p_sq < a.nseq) {
+                        const float* p = (lane < 16 ? a.x : a.dout) + a.g.grow(seq1 + p_sq, p_pos) * D;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+                        if (D > 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 32));
+                    }
+                }
                 float ml, rl, mh, rh;
                 rr_row_stats<NTO>(xl, D, invD_, t, ml, rl);
                 rr_row_stats<NTO>(xh2, D, invD_, t, mh, rh);
@@ -504,6 +520,7 @@ static bool attn_bwd_rr_plan(int S, int D, int heads, int dh, AttnBwdRRArgs* a) 
                             3 * 128 * 8 + (size_t)(NCc + Cc) * 4;
         if (smem > (size_t)max_smem_optin() - 4096) continue;
         if ((size_t)RRB_CWARPS * 3 * Kp * 4 > (size_t)((NCc + Cc) / 8) * tc5::TILE_CHUNK) continue;
+        if ((size_t)16 * heads * dh * D > (size_t)(2 * KC1 + (NCc + Cc) / 8) * tc5::TILE_CHUNK) continue;     // raw weights staged in the tile region
         a->hc = hc; a->nchunks = nch; a->NCc = NCc; a->Cc = Cc; a->tmem_cols = alloc; a->smem_bytes = (int)smem;
         a->psize = nch * (NCc + Cc) * Kp + 3 * Kp;
         return true;
