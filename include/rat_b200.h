@@ -285,6 +285,26 @@ size_t rat_auc_logloss_workspace_bytes(long long n);
 int rat_auc_logloss(const float* y_pred, const float* y_true, long long n, double* out, void* workspace,
                     size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * BM25 top-K retrieval on the device.  Replaces the compare-scan + top-K of
+ * BM25_topk_retrieval_v4 (fuxictr/datasets/data_utils.py:773-1064; called from
+ * fuxictr/pytorch/data_generator.py:141-168,192-207):
+ *   db [N][E + F] int32, qry [Q][E + F] int32 (the E exact-match columns first), qry_idf [Q][F] float64 = IDF of the
+ *   query's value in each scored column (0 when the value does not occur in the db; data_utils.py:842-846,879-887).
+ *   score = sum_f (qry == db) * qry_idf (float64, in the association torch's sum(-1) uses for < 20 elements: bit-exact
+ *   `values`; data_utils.py:950), restricted to db rows that agree with
+ *   the query on all E exact-match columns, +1 when E > 0 (data_utils.py:947); unit_scores: every candidate scores 1
+ *   (pure exact matching, data_utils.py:912-917,1033-1038).
+ *   Outputs (data_utils.py:787-797): values [Q][K] float64 descending, indices [Q][K] int64 (-1 = fewer than K rows with
+ *   a non-zero score), lens [Q] int64.  Equal scores: smaller db index first (prefer_last: larger first -- the
+ *   `truncating="pre"` of the reference's pad_sequences keeps the LAST K members of an exact-match group).
+ *   K <= 32, E + F <= 24, F <= 19.  Deterministic.
+ * ------------------------------------------------------------------------------------------------------- */
+size_t rat_bm25_topk_workspace_bytes(long long N, long long Q, int K);
+int rat_bm25_topk(const int* db, long long N, const int* qry, const double* qry_idf, long long Q, int E, int F, int K,
+                  int unit_scores, int prefer_last, double* values, long long* indices, long long* lens,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

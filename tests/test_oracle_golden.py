@@ -106,3 +106,53 @@ def test_metrics_match_sklearn():
     p = np.round(rng.random(5000), 2)          # many ties
     assert O.auc(y, p) == pytest.approx(roc_auc_score(y, p), abs=1e-12)
     assert O.logloss(y, p) == pytest.approx(log_loss(y, np.clip(p, 1e-7, 1 - 1e-7)), abs=1e-12)
+
+
+# ------------------------------------------------------------------------------------------ BM25 top-K retrieval
+BM25_CASES = ["plain", "chunked", "selfcheck", "exm_small", "exm_only", "sparse", "kkbox_like"]
+
+
+def load_bm25_case(name):
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", f"bm25_{name}.npz"))
+    qbs = int(z["qbs"])
+    return dict(db=z["db"], qry=z["qry"], exm=[int(c) for c in z["exm"]] or None, qbs=None if qbs < 0 else qbs,
+                topK=int(z["topK"]), values=z["values"], indices=z["indices"], lens=z["lens"])
+
+
+def check_bm25_against_reference(c, values, indices, lens):
+    """values / lens bit for bit; indices: the reference's torch.topk orders equal scores arbitrarily, so every index
+    (ours and the reference's) must be a db row that scores exactly the value reported for it, without repeats, and no
+    row with a strictly larger score than the smallest kept one may be missing."""
+    from oracle import bm25_oracle as B
+    assert np.array_equal(values, c["values"]), "values differ from the reference"
+    assert np.array_equal(lens, c["lens"])
+    S = B.all_scores(c["db"], c["qry"], c["exm"], c["qbs"], c["topK"])
+    for who, ind in (("ours", indices), ("reference", c["indices"])):
+        for b in range(len(c["qry"])):
+            n = int(c["lens"][b])
+            row = ind[b]
+            assert (row[:n] >= 0).all() and (row[n:] == -1).all(), who
+            assert len(set(row[:n].tolist())) == n, who
+            assert np.array_equal(S[b, row[:n]], c["values"][b, :n]), who
+            assert (c["values"][b, n:] == 0).all()
+            if n:
+                assert int((S[b] > c["values"][b, n - 1]).sum()) <= n - 1 or n == c["topK"] and \
+                    int((S[b] > c["values"][b, n - 1]).sum()) < n, who
+            if n < c["topK"]:
+                assert int((S[b] > 0).sum()) == n, who
+
+
+@pytest.mark.parametrize("name", BM25_CASES)
+def test_bm25_oracle_matches_reference_fixtures(name):
+    """oracle/bm25_oracle.py against vectors the reference's BM25_topk_retrieval_v4 produced (tests/golden/make_golden_bm25.py):
+    plain / chunked / the reference's own self-check configuration (exact-match columns [0, 4]) / small exact-match groups
+    (unit scores) / exact matching only (last-K truncation) / unseen query values (-1 padding, integer-IDF quirk) / 13 columns."""
+    from oracle import bm25_oracle as B
+    c = load_bm25_case(name)
+    v, i, n = B.bm25_topk(c["db"], c["qry"], c["exm"], c["qbs"], c["topK"])
+    check_bm25_against_reference(c, v, i, n)
+    if name == "selfcheck":     # the reference's own assertion (data_utils.py:1318-1324)
+        for b in range(len(c["qry"])):
+            got = c["db"][i[b]][:, c["exm"]]
+            assert int((got == c["qry"][b][c["exm"]]).all(-1).sum()) >= n[b]

@@ -18,6 +18,25 @@
 
 namespace rat {
 
+// mma.sync / movmatrix WITHOUT `volatile`: they are pure functions of their operands, and the compiler keeps volatile asm
+// statements in program order -- which would pin the HMMAs of two unrolled heads one after the other instead of letting
+// the scheduler interleave the independent chains (HMMA latency ~100 cycles on B200).
+__device__ __forceinline__ void rr_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void rr_mma_hh(uint32_t (&c)[2], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f16.f16.f16.f16 {%0,%1}, {%2,%3,%4,%5}, {%6,%7}, {%0,%1};"
+        : "+r"(c[0]), "+r"(c[1])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t rr_movm(uint32_t a) {
+    uint32_t d;
+    asm("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+    return d;
+}
+
 // One fragment-ordered image entry = uint4 per lane for a PAIR of 8-wide n-tiles (16 "n" rows n0..n0+15) and one 16-wide
 // k-step (columns k0..k0+15) of a matrix elem(n, k):
 //   .x = {e(n0+g,   k0+2t), e(n0+g,   k0+2t+1)}   .y = {e(n0+g,   k0+2t+8), e(n0+g,   k0+2t+9)}
@@ -108,12 +127,12 @@ __device__ __forceinline__ void c_to_a(const float (&c)[2][4], uint32_t (&a)[4])
 template <bool F16P> struct ProjAcc;
 template <> struct ProjAcc<true> {
     uint32_t c[2][2] = {};
-    __device__ __forceinline__ void mma(int nt, const uint32_t (&a)[4], uint32_t b0, uint32_t b1) { mma_hh_16x8x16(c[nt], a, b0, b1); }
+    __device__ __forceinline__ void mma(int nt, const uint32_t (&a)[4], uint32_t b0, uint32_t b1) { rr_mma_hh(c[nt], a, b0, b1); }
     __device__ __forceinline__ void frag(uint32_t (&f)[4]) const { f[0] = c[0][0]; f[1] = c[0][1]; f[2] = c[1][0]; f[3] = c[1][1]; }
 };
 template <> struct ProjAcc<false> {
     float c[2][4] = {};
-    __device__ __forceinline__ void mma(int nt, const uint32_t (&a)[4], uint32_t b0, uint32_t b1) { mma_h_16x8x16(c[nt], a, b0, b1); }
+    __device__ __forceinline__ void mma(int nt, const uint32_t (&a)[4], uint32_t b0, uint32_t b1) { rr_mma(c[nt], a, b0, b1); }
     __device__ __forceinline__ void frag(uint32_t (&f)[4]) const { c_to_a(c, f); }
 };
 

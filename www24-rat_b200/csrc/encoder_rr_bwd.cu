@@ -43,7 +43,7 @@ constexpr int RRB_THREADS = RRB_CWARPS * 32;
 __device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 5, 256;" ::: "memory"); }
 
-template <int KS, int NTO, bool VEC4, bool F16P, bool F16C>
+template <int KS, int NTO, bool VEC4, bool F16P, bool F16C, int UNR>
 __global__ void __launch_bounds__(RRB_THREADS, 1) k_attn_bwd_rr(AttnBwdRRArgs a) {
     extern __shared__ __align__(128) unsigned char rrb_smem[];
     constexpr int Kp = 16 * KS, KC1 = 2 * KS;
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(RRB_THREADS, 1) k_attn_bwd_rr(AttnBwdRRArgs a)
                 const uint4* wk = Wk_i + (size_t)ch * hc * KS * 32 + lane;
                 const uint4* wv = Wv_i + (size_t)ch * hc * KS * 32 + lane;
                 const uint4* wd = Wd_i + (size_t)ch * hc * KS * 32 + lane;
-#pragma unroll 1
+#pragma unroll UNR
                 for (int hl = 0; hl < hc; ++hl) {
                     // the core's outputs (one k-step each) accumulate in fp16: packed accumulators are tile rows as they are;
                     // the projections (three k-steps) do the same when F16P
@@ -349,10 +349,10 @@ __global__ void __launch_bounds__(RRB_THREADS, 1) k_attn_bwd_rr(AttnBwdRRArgs a)
                     const uint32_t v00 = va[0], v10 = va[1], v01 = va[2], v11 = va[3];     // [dd block][token block]
                     // ---- S = q k^T (keys 0..7: rows g of k, keys 8..15: rows g + 8) ; dP = dO v^T   (fp32)
                     float sc[2][4] = {}, dp[2][4] = {};
-                    mma_h_16x8x16(sc[0], qa, ka[0], ka[2]);
-                    mma_h_16x8x16(sc[1], qa, ka[1], ka[3]);
-                    mma_h_16x8x16(dp[0], doa, movm_t(v00), movm_t(v10));
-                    mma_h_16x8x16(dp[1], doa, movm_t(v01), movm_t(v11));
+                    rr_mma(sc[0], qa, ka[0], ka[2]);
+                    rr_mma(sc[1], qa, ka[1], ka[3]);
+                    rr_mma(dp[0], doa, rr_movm(v00), rr_movm(v10));
+                    rr_mma(dp[1], doa, rr_movm(v01), rr_movm(v11));
                     rr_softmax(sc, cl, vlo, vhi);                                             // sc = P
                     float dlo = 0.f, dhi = 0.f;
 #pragma unroll
@@ -369,19 +369,19 @@ __global__ void __launch_bounds__(RRB_THREADS, 1) k_attn_bwd_rr(AttnBwdRRArgs a)
 #pragma unroll
                         for (int e = 0; e < 4; ++e) dp[nt][e] = sc[nt][e] * (dp[nt][e] - ((e < 2) ? dlo : dhi));    // dS
                     c_to_a(dp, sa);
-                    const uint32_t pt[4] = {movm_t(pa[0]), movm_t(pa[2]), movm_t(pa[1]), movm_t(pa[3])};             // P^T
-                    const uint32_t st[4] = {movm_t(sa[0]), movm_t(sa[2]), movm_t(sa[1]), movm_t(sa[3])};             // dS^T
+                    const uint32_t pt[4] = {rr_movm(pa[0]), rr_movm(pa[2]), rr_movm(pa[1]), rr_movm(pa[3])};             // P^T
+                    const uint32_t st[4] = {rr_movm(sa[0]), rr_movm(sa[2]), rr_movm(sa[1]), rr_movm(sa[3])};             // dS^T
                     // ---- O = P v ; dV = P^T dO ; dQ' = dS k ; dK' = dS^T q'   (dq = scale dQ', dk = ln2 dK': folded into the
                     //      dA weight image and the record reduction, so the packed accumulators go to the tile as they are)
                     ProjAcc<F16C> o, dv, dq, dk;
                     o.mma(0, pa, v00, v01);
                     o.mma(1, pa, v10, v11);
-                    dv.mma(0, pt, movm_t(doa[0]), movm_t(doa[1]));
-                    dv.mma(1, pt, movm_t(doa[2]), movm_t(doa[3]));
-                    dq.mma(0, sa, movm_t(ka[0]), movm_t(ka[1]));
-                    dq.mma(1, sa, movm_t(ka[2]), movm_t(ka[3]));
-                    dk.mma(0, st, movm_t(qa[0]), movm_t(qa[1]));
-                    dk.mma(1, st, movm_t(qa[2]), movm_t(qa[3]));
+                    dv.mma(0, pt, rr_movm(doa[0]), rr_movm(doa[1]));
+                    dv.mma(1, pt, rr_movm(doa[2]), rr_movm(doa[3]));
+                    dq.mma(0, sa, rr_movm(ka[0]), rr_movm(ka[1]));
+                    dq.mma(1, sa, rr_movm(ka[2]), rr_movm(ka[3]));
+                    dk.mma(0, st, rr_movm(qa[0]), rr_movm(qa[1]));
+                    dk.mma(1, st, rr_movm(qa[2]), rr_movm(qa[3]));
                     uint32_t of[4], dvf[4], dqf[4], dkf[4];          // {rows g / d 0-7, rows g+8 / d 0-7, rows g / d 8-15, rows g+8 / d 8-15}
                     o.frag(of); dv.frag(dvf); dq.frag(dqf); dk.frag(dkf);
                     // ---- compact fp16 rows of the token tile: dq | dk | dv at columns [part * hc*dh + hl*dh + d], O after them
@@ -482,16 +482,16 @@ __global__ void __launch_bounds__(RRB_THREADS, 1) k_attn_bwd_rr(AttnBwdRRArgs a)
     if (warp == 0) tc5::tmem_dealloc(tmem_base_s, (uint32_t)a.tmem_cols);
 }
 
-template <int KS, int NTO, bool VEC4, bool F16P, bool F16C>
+template <int KS, int NTO, bool VEC4, bool F16P, bool F16C, int UNR>
 static int launch_attn_bwd_rr_v(const AttnBwdRRArgs& a, int grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_attn_bwd_rr<KS, NTO, VEC4, F16P, F16C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(k_attn_bwd_rr<KS, NTO, VEC4, F16P, F16C, UNR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              max_smem_optin() - 2048);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_attn_bwd_rr)");
         attr_set = true;
     }
-    k_attn_bwd_rr<KS, NTO, VEC4, F16P, F16C><<<grid, RRB_THREADS, a.smem_bytes, st>>>(a);
+    k_attn_bwd_rr<KS, NTO, VEC4, F16P, F16C, UNR><<<grid, RRB_THREADS, a.smem_bytes, st>>>(a);
     RAT_CHECK_LAUNCH("k_attn_bwd_rr");
     return RAT_OK;
 }
@@ -499,8 +499,9 @@ template <int KS, int NTO, bool VEC4>
 static int launch_attn_bwd_rr(const AttnBwdRRArgs& a, int grid, cudaStream_t st) {
     static int variant = -1;     // RAT_RR_BWD_VARIANT (tuning aid): 1 = fp16 accumulators for everything but S and dP (see the forward)
     if (variant < 0) { const char* e = getenv("RAT_RR_BWD_VARIANT"); variant = e ? atoi(e) : 0; }
-    if (variant == 1) return launch_attn_bwd_rr_v<KS, NTO, VEC4, true, true>(a, grid, st);
-    return launch_attn_bwd_rr_v<KS, NTO, VEC4, false, false>(a, grid, st);
+    if (variant == 1) return launch_attn_bwd_rr_v<KS, NTO, VEC4, true, true, 1>(a, grid, st);
+    if (variant == 2) return launch_attn_bwd_rr_v<KS, NTO, VEC4, false, false, 2>(a, grid, st);
+    return launch_attn_bwd_rr_v<KS, NTO, VEC4, false, false, 1>(a, grid, st);
 }
 
 static bool attn_bwd_rr_plan(int S, int D, int heads, int dh, AttnBwdRRArgs* a) {

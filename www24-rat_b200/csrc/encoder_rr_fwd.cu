@@ -20,7 +20,7 @@ struct AttnRRArgs {
 // BULK (D % 4 == 0): every warp keeps the token rows of its NEXT task in flight as 1-D bulk asynchronous copies
 // (cp.async.bulk, one per row, completion counted on a per-warp mbarrier) into a private double buffer, so a task starts on
 // rows that are already in shared memory and the residual add re-reads them there instead of from L2.
-template <int KS, int NTO, int WARPS, int CTAS, bool BULK, bool F16P, bool F16C>
+template <int KS, int NTO, int WARPS, int CTAS, bool BULK, bool F16P, bool F16C, int UNR>
 __global__ void __launch_bounds__(WARPS * 32, CTAS) k_attn_fwd_rr(AttnRRArgs a) {
     extern __shared__ __align__(16) uint4 rr_smem[];
     constexpr int NP = (NTO + 1) / 2;                     // n-tile pairs of the out-projection
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_attn_fwd_rr(AttnRRArgs a) 
         const uint4* wk = Wk_i + lane;
         const uint4* wv = Wv_i + lane;
         const uint4* wo = Wo_i + lane;
-#pragma unroll 1
+#pragma unroll UNR
         for (int h = 0; h < H; ++h) {
             // O (one k-step) accumulates in fp16: its packed accumulators ARE the out-projection's operand fragment; the
             // projections (three k-steps) do the same when F16P
@@ -150,8 +150,8 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_attn_fwd_rr(AttnRRArgs a) 
             uint32_t qa[4], ka[4], va[4];                            // 8x8 blocks {lo/0-7, hi/0-7, lo/8-15, hi/8-15}
             q.frag(qa); k.frag(ka); vt.frag(va);
             float sc[2][4] = {};
-            mma_h_16x8x16(sc[0], qa, ka[0], ka[2]);                  // keys 0..7  (rows g of k)
-            mma_h_16x8x16(sc[1], qa, ka[1], ka[3]);                  // keys 8..15 (rows g + 8)
+            rr_mma(sc[0], qa, ka[0], ka[2]);                  // keys 0..7  (rows g of k)
+            rr_mma(sc[1], qa, ka[1], ka[3]);                  // keys 8..15 (rows g + 8)
             rr_softmax(sc, cl, vlo, vhi);
             uint32_t pa[4];
             c_to_a(sc, pa);
@@ -163,8 +163,8 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_attn_fwd_rr(AttnRRArgs a) 
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
                 const uint4 f = wo[p * 32];
-                mma_h_16x8x16(acc[2 * p], oa, f.x, f.y);
-                if (2 * p + 1 < NTO) mma_h_16x8x16(acc[2 * p + 1], oa, f.z, f.w);
+                rr_mma(acc[2 * p], oa, f.x, f.y);
+                if (2 * p + 1 < NTO) rr_mma(acc[2 * p + 1], oa, f.z, f.w);
             }
             wo += NP * 32;
         }
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_attn_fwd_rr(AttnRRArgs a) 
     }
 }
 
-template <int KS, int NTO, int WARPS, int CTAS, bool BULK, bool F16P, bool F16C>
+template <int KS, int NTO, int WARPS, int CTAS, bool BULK, bool F16P, bool F16C, int UNR>
 static int launch_attn_fwd_rr_v(const AttnRRArgs& a, cudaStream_t st) {
     constexpr int NP = (NTO + 1) / 2;
     const size_t stage_bytes = std::max((size_t)(BULK ? WARPS * 2 * 16 * a.D * 4 : 0), (size_t)4 * a.I * a.D * 4);
@@ -205,14 +205,14 @@ static int launch_attn_fwd_rr_v(const AttnRRArgs& a, cudaStream_t st) {
     if (smem > (size_t)max_smem_optin() / CTAS - 2048) return 1;
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
-        cudaError_t e = cudaFuncSetAttribute(k_attn_fwd_rr<KS, NTO, WARPS, CTAS, BULK, F16P, F16C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_attn_fwd_rr<KS, NTO, WARPS, CTAS, BULK, F16P, F16C, UNR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_attn_fwd_rr)");
         attr_smem = smem;
     }
     const long long ntasks = a.g.S <= 8 ? (a.nseq + 1) / 2 : a.nseq;
     const long long nblk = (ntasks + WARPS - 1) / WARPS;
     const int grid = (int)std::min<long long>(nblk, (long long)CTAS * num_sms());
-    k_attn_fwd_rr<KS, NTO, WARPS, CTAS, BULK, F16P, F16C><<<grid, WARPS * 32, smem, st>>>(a);
+    k_attn_fwd_rr<KS, NTO, WARPS, CTAS, BULK, F16P, F16C, UNR><<<grid, WARPS * 32, smem, st>>>(a);
     RAT_CHECK_LAUNCH("k_attn_fwd_rr");
     return RAT_OK;
 }
@@ -224,9 +224,12 @@ static int launch_attn_fwd_rr(const AttnRRArgs& a, cudaStream_t st) {
     if (variant < 0) { const char* e = getenv("RAT_RR_FWD_VARIANT"); variant = e ? atoi(e) : 0; }
     const bool bulk_ok = (a.D % 4) == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0;
     int rc = 1;
-    if (bulk_ok && variant == 0) rc = launch_attn_fwd_rr_v<KS, NTO, 16, 1, true, false, false>(a, st);
-    if (bulk_ok && variant == 1) rc = launch_attn_fwd_rr_v<KS, NTO, 16, 1, true, true, true>(a, st);
-    if (rc == 1) rc = launch_attn_fwd_rr_v<KS, NTO, 16, 1, false, false, false>(a, st);
+    if (bulk_ok && variant == 0) rc = launch_attn_fwd_rr_v<KS, NTO, 16, 1, true, false, false, 1>(a, st);
+    if (bulk_ok && variant == 1) rc = launch_attn_fwd_rr_v<KS, NTO, 16, 1, true, true, true, 1>(a, st);
+    if (bulk_ok && variant == 4) rc = launch_attn_fwd_rr_v<KS, NTO, 16, 1, true, false, false, 2>(a, st);
+    if (bulk_ok && variant == 5) rc = launch_attn_fwd_rr_v<KS, NTO, 12, 1, true, false, false, 2>(a, st);
+    if (bulk_ok && variant == 6) rc = launch_attn_fwd_rr_v<KS, NTO, 8, 1, true, false, false, 4>(a, st);
+    if (rc == 1) rc = launch_attn_fwd_rr_v<KS, NTO, 16, 1, false, false, false, 1>(a, st);
     return rc;
 }
 

@@ -11,8 +11,8 @@ Two producers with the same `len()` / re-iterable contract the training loop nee
 
 Data blocks are read from `.h5` when h5py is importable, else from `.npz` / `.npy` mirrors with the same stem
 (key "data"; retrieval files hold "indices", "values", "lens" like data_generator.py:107-113,213-215).
-BM25 retrieval itself is precomputed offline (pre_retrieval: true is asserted by the reference, :101) and is
-not part of this path.
+BM25 pre-retrieval (pre_retrieval: true is asserted by the reference, :101): the cached retrieval file is read when it
+exists, otherwise it is computed on the GPU (compute_retrieval -> rat_bm25_topk) and saved, like data_generator.py:114-215.
 """
 import logging
 import os
@@ -77,14 +77,77 @@ class Dataset(data.Dataset):
         return len(self.darray)
 
 
-def _load_retrieval(data_path, retrieval_configs):
+def _save_retrieval(path, indices, values, lens):
+    """h5 with the reference's keys (data_generator.py:213-215) when h5py exists, else the npz mirror _load_array reads"""
+    try:
+        import h5py
+    except ImportError:
+        h5py = None
+    if h5py is not None:
+        with h5py.File(path, "a") as hf:
+            for k, v in (("indices", indices), ("values", values), ("lens", lens)):
+                hf.create_dataset(k, data=v)
+    else:
+        np.savez(os.path.splitext(path)[0] + ".npz", indices=indices, values=values, lens=lens)
+
+
+def compute_retrieval(data_array, retrieval_configs, retrieval_pool_fname, db_array=None):
+    """BM25 pre-retrieval of one data block on the GPU: the driver logic of the reference (data_generator.py:115-212 --
+    X-fold self retrieval, label-wise positive / negative pools, external pool) around the device kernel
+    (fuxictr.datasets.data_utils.BM25_topk_retrieval -> rat_bm25_topk).  Returns (indices, values, lens)."""
+    import re
+    from ..datasets.data_utils import BM25_topk_retrieval
+    cfg = retrieval_configs
+    cols = cfg["used_col_indices"]
+
+    def split_by_label(db, labels, qry, remap):
+        """label-wise: K from the positives, K from the negatives (data_generator.py:133-166,182-206)"""
+        outs = []
+        for sel in (np.nonzero(labels)[0], np.nonzero(1 - labels)[0]):
+            r = BM25_topk_retrieval(db_np_data=db[sel], qry_np_data=qry, **cfg)
+            outs.append((remap(sel[r.indices]), r.values, r.lens))       # like the reference, -1 wraps to the last row
+        return (np.concatenate([outs[0][0], outs[1][0]], axis=-1), np.concatenate([outs[0][1], outs[1][1]], axis=-1),
+                np.stack([outs[0][2], outs[1][2]], axis=-1))
+
+    if retrieval_pool_fname == "self":
+        arr = data_array[:, cols].astype(int)
+        labels = data_array[:, -1].astype(int) if cfg["label_wise"] else None
+        fold_num = int(re.match(r"\d+-fold", cfg["split_type"]).group().split("-")[0])
+        fold_size = int(np.ceil(len(arr) / fold_num))
+        ind, val, lens = [], [], []
+        for fi in range(fold_num):
+            lo, hi = fi * fold_size, (fi + 1) * fold_size
+            qry = arr[lo:hi]
+            db = np.concatenate([arr[:lo], arr[hi:]], axis=0)
+            db_idx = np.concatenate([np.arange(lo), np.arange(hi, len(arr))], axis=0)
+            if cfg["label_wise"]:
+                i, v, n = split_by_label(db, np.concatenate([labels[:lo], labels[hi:]]), qry, lambda x: db_idx[x])
+            else:
+                r = BM25_topk_retrieval(db_np_data=db, qry_np_data=qry, **cfg)
+                i, v, n = db_idx[r.indices], r.values, r.lens
+            ind.append(i); val.append(v); lens.append(n)
+        return np.concatenate(ind), np.concatenate(val), np.concatenate(lens)
+    db = db_array[:, cols].astype(int)
+    qry = data_array[:, cols].astype(int)
+    if cfg["label_wise"]:
+        return split_by_label(db, db_array[:, -1].astype(int), qry, lambda x: x)
+    r = BM25_topk_retrieval(db_np_data=db, qry_np_data=qry, **cfg)
+    return r.indices, r.values, r.lens
+
+
+def _load_retrieval(data_path, retrieval_configs, data_array=None, retrieval_pool_fname=None, db_array=None):
+    """the cached retrieval file of the reference (data_generator.py:107-113) or, when it does not exist yet, the BM25
+    pre-retrieval itself on the GPU followed by the same save (data_generator.py:114-215)"""
     root, fname = os.path.split(data_path)
     path = os.path.join(root, "retrieval_{}_".format(retrieval_configs["topK"]) + fname)
-    if not _exists(path):
-        raise FileNotFoundError(
-            "pre-computed retrieval file {} not found: BM25 top-K retrieval is an offline step of the reference "
-            "(BM25_topk_retrieval_v4) and is not re-implemented in the B200 hot path".format(path))
-    return (_load_array(path, "indices"), _load_array(path, "values"), _load_array(path, "lens"))
+    if _exists(path):
+        return (_load_array(path, "indices"), _load_array(path, "values"), _load_array(path, "lens"))
+    if data_array is None or "used_col_indices" not in retrieval_configs:
+        raise FileNotFoundError("pre-computed retrieval file {} not found and no retrieval columns configured".format(path))
+    logging.info("BM25 pre-retrieval on the GPU -> %s", path)
+    ind, val, lens = compute_retrieval(data_array, retrieval_configs, retrieval_pool_fname, db_array)
+    _save_retrieval(path, ind, val, lens)
+    return ind, val, lens
 
 
 def _stats(obj, data_array, batch_size):
@@ -104,7 +167,7 @@ class DataGenerator(data.DataLoader):
         if retrieval_configs is not None:
             assert retrieval_configs["pre_retrieval"], "only the pre-retrieval strategy exists (as in the reference)"
             pool = data_array if retrieval_pool_fname == "self" else _load_array(retrieval_pool_fname)
-            idx, vals, lens = _load_retrieval(data_path, retrieval_configs)
+            idx, vals, lens = _load_retrieval(data_path, retrieval_configs, data_array, retrieval_pool_fname, pool)
             if retrieval_augmented:
                 self.dataset = Dataset(data_array, feature_map, None, pool, idx, vals, lens)
             else:
@@ -184,7 +247,7 @@ class DeviceDataFileGenerator(DeviceDataGenerator):
         assert retrieval_configs is not None and retrieval_augmented, "device generator serves retrieval-augmented data"
         data_array = _load_array(data_path)
         pool = data_array if retrieval_pool_fname == "self" else _load_array(retrieval_pool_fname)
-        idx, _, _ = _load_retrieval(data_path, retrieval_configs)
+        idx, _, _ = _load_retrieval(data_path, retrieval_configs, data_array, retrieval_pool_fname, pool)
         # only the (shuffled) training generator is sharded over the ranks: validation / test generators serve the whole set on
         # every rank, so all ranks compute identical metrics and take identical early-stop / lr-decay decisions
         dp = bool(kwargs.get("data_parallel")) and bool(shuffle)
