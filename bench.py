@@ -274,15 +274,18 @@ def run_ours(a):
     def per_call_ms(name):
         n, ms = prof[name]
         return ms / n
-    # dominant kernel: fused attention backward (2 per RAT block: intra S=N, cross S=T).  It is GEMM-shaped work on
-    # the tensor cores (tcgen05 projections + mma.sync softmax core), so it is reported against the bf16 tensor peak;
-    # the same launch is also shown against the HBM roofline (x + dout read, dx written, base = dout hits L2).
+    # dominant kernel: fused attention backward (2 per RAT block: intra S=N, cross S=T).  GEMM-shaped work on the tensor
+    # cores (mma.sync fragments per warp + tcgen05 weight-gradient / dA products), so it is reported against the measured
+    # dense tensor peak; the same launch is also shown against the HBM roofline (x + dout read, dx written, base = dout
+    # hits L2), which is the roof that bounds it: the arithmetic intensity (165 FLOP/B) is below the ridge.
     attn_bwd_flops = rows_tok * (attn_flops_per_token(D, I, N) + attn_flops_per_token(D, I, T)) / 2 * 2.75
     ab_ms = per_call_ms("rat_attn_bwd")
     ach_tf = attn_bwd_flops / (ab_ms * 1e-3) / 1e12
     ab_bytes = rows_tok * D * 4 * 3
     tc_mode = a.precision == "fp16"
-    roofline = {"kernel": "k_attn_bwd_tc (+k_reduce_attn_tc)" if tc_mode else "k_attn_bwd (+k_reduce_attn)",
+    rr = tc_mode and os.environ.get("RAT_RR", "1") != "0"
+    roofline = {"kernel": ("k_attn_bwd_rr (+k_reduce_attn_tc)" if rr else "k_attn_bwd_tc (+k_reduce_attn_tc)") if tc_mode
+                else "k_attn_bwd (+k_reduce_attn)",
                 "bound": "tensor", "achieved": round(ach_tf, 3),
                 "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": round(ach_tf / pk["tf_sustained"], 5),
                 "traffic": ncu_traffic("attn_bwd", S, B, K) if tc_mode else None,
@@ -290,10 +293,12 @@ def run_ours(a):
                 "flops_per_launch": attn_bwd_flops,
                 "hbm_view": {"bytes_per_launch": ab_bytes, "achieved_gbs": round(ab_bytes / (ab_ms * 1e-3) / 1e9, 1),
                              "frac_of_hbm_peak": round(ab_bytes / (ab_ms * 1e-3) / 1e9 / pk["hbm"], 4)},
-                "note": "algorithmic FLOPs = 2.75x forward (recompute + dgrad + wgrad); issue/latency-bound: every GEMM has "
-                        "K <= 80, N <= 192 and the softmax-backward core between them runs ~450 SASS instructions per "
-                        "(sequence, head) task around 12 mma.sync; see profiles/r01_final_backward_kernels_ncu_full.txt and "
-                        "DESIGN.md section 3"}
+                "note": "average over the step's 8 launches (4 intra S=14, 3 cross S=6 on all tokens, 1 cross on field token 0 "
+                        "only).  Algorithmic FLOPs = 2.75x forward (recompute + dgrad + wgrad).  Every product is a 16x16x(16..48) "
+                        "GEMM: one warp owns a 16-row fragment tile end to end (mma.sync m16n8k16, 288 HMMA per tile at 8.1 "
+                        "cycles each = 22 % of the legacy tensor pipe), weight gradients and dA on tcgen05; the kernel is bound by "
+                        "instruction issue + shared-memory fragment loads + HMMA latency (~100 cycles), see "
+                        "profiles/r02_attn_rr_ncu_full.txt and DESIGN.md section 3"}
     gb = B * gather_bytes_per_sample(K, L, F, D)
     g_step_ms = per_call_ms("rat_gather_fwd_sharded" if sharded else "rat_gather_fwd")
     # A 30 us kernel bracketed by its own event pair also pays ~4 us of event + launch turnaround on the device, so
@@ -495,7 +500,46 @@ def secondary_workloads(a, rank, world, local, dist):
             sweep.append({"K": K, "B_per_gpu": B, "infer_samples_per_s": r["infer_samples_per_s"],
                           "ms_per_batch": r["infer_ms_per_step"]})
     sec["infer_sweep"] = {"shape": a.shape, "n_gpus": world, "precision": a.precision, "grid": sweep}
+    if rank == 0:
+        sec["bm25"] = bm25_workload()
     return sec
+
+
+def bm25_workload(N=1_000_000, Q=8192, C=13, K=5):
+    """BM25 top-K pre-retrieval (the step BEFORE the training path) on one GPU: Q queries against an N-row
+    pool of C categorical columns (kkbox-like id ranges), through the drop-in BM25_topk_retrieval_v4 (host IDF tables + H2D
+    inside the timed region) and the device kernel alone.  Integer compare-scan: the unit is (query, db row) pairs per second."""
+    import rat_native as rn
+    from fuxictr.datasets.data_utils import BM25_topk_retrieval_v4, _dense_ids, _idf_tables, _idf_of_queries
+    g = np.random.default_rng(0)
+    ranges = [40, 6, 3000, 12, 900, 25, 7, 150, 60, 5, 2000, 33, 480][:C]
+    db = np.stack([g.integers(0, r, N) for r in ranges], axis=1)
+    qry = np.stack([g.integers(0, r, Q) for r in ranges], axis=1)
+    t0 = time.perf_counter()
+    res = BM25_topk_retrieval_v4(db, qry, topK=K)
+    torch.cuda.synchronize()
+    t_api = time.perf_counter() - t0
+    dev = torch.device("cuda", torch.cuda.current_device())
+    db_o, q_o = _dense_ids(db, qry)
+    db_d, q_d = torch.from_numpy(db_o).to(dev), torch.from_numpy(q_o).to(dev)
+    w_d = torch.from_numpy(_idf_of_queries(_idf_tables(db), qry)).to(dev)
+    vals = torch.zeros(Q, K, dtype=torch.float64, device=dev); inds = torch.zeros(Q, K, dtype=torch.int64, device=dev)
+    lens = torch.zeros(Q, dtype=torch.int64, device=dev)
+    ws = torch.empty(int(rn.query("rat_bm25_topk_workspace_bytes", N, Q, K)) // 8 + 2, dtype=torch.float64, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms = []
+    for i in range(3):
+        e0.record()
+        rn.call("rat_bm25_topk", db_d, N, q_d, w_d, Q, 0, C, K, 0, 0, vals, inds, lens, ws, ws.numel() * 8, rn.current_stream())
+        e1.record(); torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    k_ms = min(ms)
+    return {"workload": f"BM25 top-{K}: {Q} queries x {N} pool rows x {C} columns", "kernel_ms": round(k_ms, 3),
+            "pairs_per_s": round(Q * N / (k_ms * 1e-3), 1), "column_compares_per_s": round(Q * N * C / (k_ms * 1e-3), 1),
+            "api_seconds_incl_host_idf_and_copies": round(t_api, 3), "queries_per_s_api": round(Q / t_api, 1),
+            "mean_len": float(res.lens.mean()),
+            "bound": "instruction issue (1 compare + 1 select + 1 float64 add per column pair); db rows are staged once per 8 queries "
+                     "in shared memory, so HBM traffic is N*C*4 B per 8 queries"}
 
 
 # ----------------------------------------------------------------------------------------- CPU arms (oracle port)

@@ -97,7 +97,8 @@ def test_attn_bwd_matches_autograd(rn, precision, B, T, N, D, H, dh, mode):
 
 
 @pytest.mark.parametrize("rows,D,M,prenorm", [(120, 10, 40, False), (5000, 40, 80, False), (333, 10, 20, False),
-                                              (777, 20, 40, True), (4097, 40, 80, True)])
+                                              (777, 20, 40, True), (4097, 40, 80, True),
+                                              (40011, 40, 80, False)])     # several tiles per persistent CTA, ragged tail
 def test_ff_bwd_matches_autograd(rn, precision, rows, D, M, prenorm):
     from tests.gpu_util import assert_close, ptol
     g = torch.Generator().manual_seed(rows)

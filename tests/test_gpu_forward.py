@@ -196,7 +196,8 @@ def test_attn_fwd_matches_oracle(rn, precision, B, T, N, D, H, dh, mode):
 
 
 @pytest.mark.parametrize("rows,D,M,prenorm", [(120, 10, 40, False), (5000, 40, 80, False), (333, 10, 20, False),
-                                              (777, 20, 40, True), (4097, 40, 80, True)])
+                                              (777, 20, 40, True), (4097, 40, 80, True),
+                                              (40011, 40, 80, False)])     # several tiles per persistent CTA, ragged tail
 def test_ff_fwd_matches_oracle(rn, precision, rows, D, M, prenorm):
     """x + W2 gelu_erf(W1 [LN]x + b1) + b2 ; rtol 1e-4 atol 1e-5."""
     from tests.gpu_util import assert_close, ptol

@@ -14,7 +14,8 @@ steps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 K = 5
 from rat_native.engine import set_precision
 set_precision(sys.argv[4] if len(sys.argv) > 4 else "fp16")
-fm = shapes.make_feature_map(shape)
+vocab_scale = float(sys.argv[5]) if len(sys.argv) > 5 else 1.0
+fm = shapes.make_feature_map(shape, vocab_scale=vocab_scale)
 params = shapes.model_params(shape, K=K, gpu=0)
 os.makedirs(os.path.join(params["model_root"], fm.dataset_id), exist_ok=True)
 model = models.RAT_m2(fm, **params)

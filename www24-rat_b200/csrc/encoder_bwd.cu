@@ -543,6 +543,10 @@ int attn_bwd_rr_dispatch(const float* x, const float* dout, const float* base, f
                          unsigned long long seed, unsigned int rng_stream, cudaStream_t st);
 size_t attn_bwd_rr_workspace_bytes(int B, int T, int N, int D, int heads, int dh, int mode);
 bool rr_enabled();
+int ff_bwd_rr_dispatch(const float* x, const float* dout, const float* base, float* dx, const float* W1, const float* b1,
+                       const float* W2, float* dW1, float* db1, float* dW2, float* db2, long long rows, int D, int M,
+                       const float* dout_amax, float* dx_amax, float* workspace, size_t workspace_bytes, cudaStream_t st);
+size_t ff_bwd_rr_workspace_bytes(long long rows, int D, int M);
 int ff_bwd_tc_dispatch(const float* x, const float* dout, const float* base, float* dx, const float* ln_w,
                        const float* W1, const float* b1, const float* W2, float* dW1, float* db1, float* dW2, float* db2,
                        long long rows, int D, int M, const float* dout_amax, float* dx_amax, float* workspace,
@@ -651,7 +655,8 @@ extern "C" size_t rat_ff_bwd_workspace_bytes(long long rows, int D, int M) {
     FFPlan p{};
     if (plan_ff_bwd(D, M, &p) != RAT_OK) return 0;
     const long long ntiles = (rows + p.RPT - 1) / p.RPT;
-    return std::max((size_t)bwd_grid(ntiles) * p.psize * sizeof(float), ff_bwd_tc_workspace_bytes(rows, D, M));
+    return std::max({(size_t)bwd_grid(ntiles) * p.psize * sizeof(float), ff_bwd_tc_workspace_bytes(rows, D, M),
+                     ff_bwd_rr_workspace_bytes(rows, D, M)});
 }
 
 template <bool MMA>
@@ -673,6 +678,11 @@ extern "C" int rat_ff_bwd(const float* x, const float* dout, const float* base, 
                           const float* dout_amax, float* dx_amax, float* workspace, size_t workspace_bytes, void* stream) {
     RAT_REQUIRE(rows > 0 && D > 0 && M > 0, "rat_ff_bwd: bad shape");
     RAT_REQUIRE(D <= 128 && pad8(M) <= ENC_THREADS, "rat_ff_bwd: D=%d (<=128) M=%d (<=%d) not supported", D, M, ENC_THREADS);
+    if (precision_mode() == 2 && rr_enabled() && ln_w == nullptr && !getenv("RAT_RR_FF_OFF")) {
+        const int rc3 = ff_bwd_rr_dispatch(x, dout, base, dx, W1, b1, W2, dW1, db1, dW2, db2, rows, D, M, dout_amax, dx_amax, workspace,
+                                           workspace_bytes, (cudaStream_t)stream);
+        if (rc3 <= 0) return rc3;
+    }
     if (precision_mode() == 2) {
         const int rc2 = ff_bwd_tc_dispatch(x, dout, base, dx, ln_w, W1, b1, W2, dW1, db1, dW2, db2, rows, D, M, dout_amax, dx_amax,
                                            workspace, workspace_bytes, (cudaStream_t)stream);

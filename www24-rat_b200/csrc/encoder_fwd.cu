@@ -246,6 +246,9 @@ int attn_fwd_rr_dispatch(const float* x, const float* res, float* out, const flo
                          const float* Wq, const float* Wk, const float* Wv, const float* Wo, const float* bo, int B, int T,
                          int N, int D, int heads, int dh, float scale, float alpha, int mode, cudaStream_t st);
 
+int ff_fwd_rr_dispatch(const float* x, const float* res, float* out, const float* ln_w, const float* ln_b, const float* W1,
+                       const float* b1, const float* W2, const float* b2, long long rows, int D, int M, cudaStream_t st);
+
 // The register-resident attention kernels (encoder_rr_*.cu) are the default of the fp16 mode for sequences <= 16 tokens;
 // RAT_RR=0 in the environment selects the tile-based tcgen05 kernels for every shape (A/B measurements).
 bool rr_enabled() {
@@ -350,6 +353,10 @@ extern "C" int rat_ff_fwd(const float* x, const float* res, float* out, const fl
     FFArgs a{};
     a.x = x; a.res = res; a.out = out; a.ln_w = ln_w; a.ln_b = ln_b; a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2;
     a.rows = rows; a.D = D; a.M = M;
+    if (g_precision == 2 && rr_enabled() && !getenv("RAT_RR_FF_OFF")) {
+        const int rc3 = ff_fwd_rr_dispatch(x, res, out, ln_w, ln_b, W1, b1, W2, b2, rows, D, M, (cudaStream_t)stream);
+        if (rc3 <= 0) return rc3;
+    }
     if (g_precision == 2) {
         const int rc2 = ff_fwd_tc_dispatch(x, res, out, ln_w, ln_b, W1, b1, W2, b2, rows, D, M, (cudaStream_t)stream);
         if (rc2 <= 0) return rc2;

@@ -315,3 +315,14 @@ int ff_bwd_tc_dispatch(const float* x, const float* dout, const float* base, flo
     return RAT_OK;
 }
 
+
+// fixed-order reduction of per-CTA FF gradient records [Mp][Kp] gW1 (column D = gb1) | [Mp][Kp] gW2^T | [Kp] gb2 -- shared with
+// the register-resident backward (encoder_rr_ff.cu)
+int ff_reduce_records(const float* partials, int nparts, int psize, float* dW1, float* db1, float* dW2, float* db2, int D, int M,
+                      int Kp, int Mp, cudaStream_t st) {
+    FFReduceTcArgs r{partials, nparts, psize, dW1, db1, dW2, db2, D, M, Kp, Mp};
+    const int total = 2 * M * D + M + D;
+    k_reduce_ff_tc<<<std::max(1, std::min((total + 31) / 32, 1024)), dim3(32, 8), 0, st>>>(r);
+    RAT_CHECK_LAUNCH("k_reduce_ff_tc");
+    return RAT_OK;
+}
