@@ -2,6 +2,8 @@
 reports a roofline for, keyed by the sha256 of the kernel's source files (bench.py drops an entry whose sources changed).
 
     python tools/ncu_traffic.py <key> <report.ncu-rep> <kernel regex> <shape> <B> <K> <source file> [<source file> ...]
+    NCU_CALLS=<n>: the matching launches belong to n calls of the entry point (e.g. scan + fix-up = one scatter call): the traffic
+    is summed per call instead of averaged per launch.
 e.g. python tools/ncu_traffic.py gather gpurun_out/prof_gather.ncu-rep k_gather_flat kkbox 4096 5 www24-rat_b200/csrc/gather.cu"""
 import csv, hashlib, io, json, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -28,7 +30,12 @@ for f in sources:
     h.update(open(os.path.join(ROOT, f), "rb").read())
 path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
 db = json.load(open(path)) if os.path.exists(path) else {}
-db[key] = {"traffic_bytes": tot / n, "launches_averaged": n, "kernel": rx, "gpu_time_us_under_ncu": dur / n, "shape": shape, "B": B, "K": K,
+calls = int(os.environ.get("NCU_CALLS", "0"))
+if calls:
+    n_div = calls
+else:
+    n_div = n
+db[key] = {"traffic_bytes": tot / n_div, "launches_averaged": n, "kernel": rx, "gpu_time_us_under_ncu": dur / n_div / 1e3 if False else dur / n_div, "shape": shape, "B": B, "K": K,
            "sources": sources, "sha16": h.hexdigest()[:16], "capture": os.path.basename(rep)}
 json.dump(db, open(path, "w"), indent=1, sort_keys=True)
 print(key, db[key])

@@ -1,2 +1,3 @@
-for v in 0 4 5 6; do echo "== fwd variant $v"; RAT_RR_FWD_VARIANT=$v timeout 200 python -m pytest tests -m gpu -x -q -k "attn_fwd" 2>&1 | tail -1; RAT_RR_FWD_VARIANT=$v ONLY_FWD=1 timeout 100 python tools/bench_attn.py kkbox 4096 5 2>&1 | tail -2; done
-for v in 0 2; do echo "== bwd variant $v";  RAT_RR_BWD_VARIANT=$v timeout 200 python -m pytest tests -m gpu -x -q -k "attn_bwd" 2>&1 | tail -1; RAT_RR_BWD_VARIANT=$v timeout 100 python tools/bench_attn.py kkbox 4096 5 2>&1 | grep bwd; done
+timeout 600 python -m pytest tests -m gpu -x -q -k "attn_bwd" 2>&1 | tail -8
+timeout 100 python tools/bench_attn.py kkbox 4096 5 2>&1 | grep bwd
+timeout 100 python tools/bench_attn.py tmall 4096 5 2>&1 | grep bwd
