@@ -424,7 +424,7 @@ def run_ours(a):
 
 
 def small_workload(shape, B, K, precision, rank, world, local, dist, steps=6, warmup=3, sharded=False, vocab_scale=1.0,
-                   pool_rows=262144, legs=("train", "infer")):
+                   pool_rows=262144, legs=("train", "infer"), variant="RAT_m2"):
     """train / inference samples/s of one secondary workload (device-resident inputs, CUDA events, max over ranks)."""
     import rat_native as rn
     from rat_native import shapes
@@ -437,7 +437,7 @@ def small_workload(shape, B, K, precision, rank, world, local, dist, steps=6, wa
     if sharded:
         params["shard_embeddings"] = True
     os.makedirs(os.path.join(params["model_root"], fm.dataset_id), exist_ok=True)
-    model = models.RAT_m2(fm, **params)
+    model = getattr(models, variant)(fm, **params)
     if world > 1:
         eng = model._engine
         dist.broadcast(eng.store.W[:eng.store.emb_off] if sharded else eng.store.W, 0)
@@ -447,7 +447,8 @@ def small_workload(shape, B, K, precision, rank, world, local, dist, steps=6, wa
                               world=world, drop_last=True)
     it = iter(gen)
     batches = [next(it) for _ in range(min(len(gen), steps + warmup))]
-    out = {"shape": shape, "B_per_gpu": B, "K": K, "precision": precision, "n_gpus": world, "params": model.count_parameters()}
+    out = {"model": variant, "shape": shape, "B_per_gpu": B, "K": K, "precision": precision, "n_gpus": world,
+           "params": model.count_parameters()}
     if "train" in legs:
         model.train()
         t = timed(lambda i: model.train_step(batches[i % len(batches)]), steps, warmup, dist)
@@ -500,6 +501,15 @@ def secondary_workloads(a, rank, world, local, dist):
             sweep.append({"K": K, "B_per_gpu": B, "infer_samples_per_s": r["infer_samples_per_s"],
                           "ms_per_batch": r["infer_ms_per_step"]})
     sec["infer_sweep"] = {"shape": a.shape, "n_gpus": world, "precision": a.precision, "grid": sweep}
+    # configs[3]: the other model variants on the headline shape (RAT_m0: one flat 84-token sequence -> tile / mma.sync kernels;
+    # RAT_m1: intra Transformer + cross Transformer on the pooled tokens; RAT_m3: parallel branches, head width 20)
+    sec["variants"] = []
+    for v in ("RAT_m0", "RAT_m1", "RAT_m3"):
+        try:
+            sec["variants"].append(small_workload(a.shape, a.batch, a.topk, a.precision, rank, world, local, dist, steps=4,
+                                                  warmup=2, variant=v))
+        except Exception as exc:            # a secondary line must never take the headline line down
+            sec["variants"].append({"model": v, "error": repr(exc)[:300]})
     if rank == 0:
         sec["bm25"] = bm25_workload()
     return sec

@@ -37,6 +37,16 @@ int rat_device_check(void);
  * relative); 0 = exact fp32 on the SIMT pipe (parity anchor, ~1e-5). */
 int rat_set_precision(int mode);
 int rat_get_precision(void);
+/* Deferred weight-gradient reductions.  rat_attn_bwd / rat_ff_bwd are two launches: the backward kernel (per-CTA gradient
+ * records into `workspace`) and a fixed-order reduction of the records into dW*.  Only the optimizer reads dW*, so with a
+ * reduce stream set the reduction is launched THERE (forked from the call's stream by an event) and the next backward
+ * kernel does not queue behind it; a later call that reuses the same `workspace` first waits for the reduction that still
+ * reads it (alternate two workspaces to get the overlap).  rat_reduce_stream_join makes `stream` wait for every deferred
+ * reduction issued so far -- call it before anything reads the gradients and before a stream capture ends.  NULL = off
+ * (default).  Events only: safe inside CUDA-graph capture.  No reference counterpart (autograd's engine orders its own
+ * accumulation kernels); the contract of rat_attn_bwd / rat_ff_bwd is unchanged after the join. */
+int rat_set_reduce_stream(void* stream);
+int rat_reduce_stream_join(void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * K0: batch assembly
@@ -171,6 +181,36 @@ int rat_bn_act_bwd_apply(const float* dout, const float* out, const float* z, co
                          float* dbeta, int rows, int C, float drop_p, unsigned long long seed,
                          unsigned int rng_stream, float* dz_amax, float param_grad_scale, void* stream);
 int rat_colsum(const float* A, int rows, int C, int lda, float* out, void* stream);
+/* Single-launch forms of the above for single-process training (csrc/mlp_fused.cu: one thread-block cluster of 8 CTAs per
+ * 32-column slab, column partials exchanged through distributed shared memory, rank-order sums => deterministic).
+ * rat_bn_act_fwd_train == rat_bn_sums + rat_bn_finalize(count = rows) + rat_bn_act_fwd: nn.BatchNorm1d in train mode +
+ * ReLU + Dropout of MLP_Layer (layers/deep.py:128-135); mean / rstd are saved for the backward.
+ * rat_bn_act_bwd_fused == rat_bn_act_bwd_sums + rat_bn_act_bwd_apply(count = rows, param_grad_scale = 1) + rat_colsum(dz):
+ * autograd's backward of the same three modules plus the bias gradient of the nn.Linear in front of them (dbias may be
+ * NULL; mean == NULL: no BatchNorm, dz = d relu/dropout).  dz may alias dout.  See below for peer_bufs / rank / world. */
+int rat_bn_act_fwd_train(const float* z, int rows, int C, const float* gamma, const float* beta, float* mean,
+                         float* rstd, float* running_mean, float* running_var, float momentum, float eps, float* out,
+                         float drop_p, unsigned long long seed, unsigned int rng_stream, const void* const* peer_bufs,
+                         int rank, int world, void* stream);
+int rat_bn_act_bwd_fused(const float* dout, const float* out, const float* z, const float* mean, const float* rstd,
+                         const float* gamma, int rows, int C, float* dz, float* dgamma, float* dbeta, float* dbias,
+                         float drop_p, unsigned long long seed, unsigned int rng_stream, float* dz_amax,
+                         const void* const* peer_bufs, int rank, int world, void* stream);
+/* Data-parallel form of the two calls above (world > 1): the statistics are those of the GLOBAL batch (rows * world rows;
+ * every rank passes the same `rows`), i.e. what the single-device reference computes at that batch.  peer_bufs = device
+ * array of `world` pointers to the ranks' symmetric exchange buffers (rat_bn_exchange_workspace_bytes each, zeroed once;
+ * NVLink peer memory); the slab leaders exchange their 2 x 32 double totals inside the launch (one-shot store / flag /
+ * rank-order sum), so no separate all-reduce sits between the statistics and the apply pass.  dgamma / dbeta are written
+ * as 1/world of the global value (the caller's SUM all-reduce of the gradient buffer restores them); dbias is the LOCAL
+ * column sum.  Every rank must enqueue the same sequence of calls.  world == 1: peer_bufs may be NULL. */
+size_t rat_bn_exchange_workspace_bytes(int world);
+/* Every gradient that hangs off dlogit [B] in ONE launch: g_fc_w[d] = sum_b dlogit[b] enc[b*enc_stride + d] and
+ * g_fc_b = sum_b dlogit[b] (self.fc, RAT_m2.py:106,144) and, when h_last != NULL, the final Linear(K -> 1) of the DNN
+ * (layers/deep.py:137): g_final_w[k] = sum_b dlogit[b] h_last[b][k], g_final_b = sum_b dlogit[b],
+ * dh_last[b][k] = dlogit[b] w_final[k].  Replaces 3 rat_sgemm + 2 rat_colsum calls (10 launches). */
+int rat_head_bwd(const float* dlogit, int B, const float* enc, long long enc_stride, int D, float* g_fc_w,
+                 float* g_fc_b, const float* h_last, int K, const float* w_final, float* g_final_w, float* g_final_b,
+                 float* dh_last, void* stream);
 /* logit = fc(enc[b,0,0,:]) + dnn_out[b] + lr_out[b]; y_pred = sigmoid; BCE(mean, log clamp -100) and, when dlogit
  * is non-NULL, dlogit[b] = dBCE/dlogit * inv_count and denc[b,0,0,:] = dlogit[b]*fc_w (denc pre-zeroed by the
  * caller).  Replaces RAT_m2.py:138-150 + BaseModel.add_loss (base_model.py:74-77).  loss_part: double

@@ -304,6 +304,96 @@ def test_bn_act_backward_matches_autograd(rn):
     assert_close("bn dbeta", db, beta.grad, 1e-4, 1e-4)
 
 
+@pytest.mark.parametrize("rows,C,drop", [(4096, 400, 0.0), (1000, 77, 0.0), (2048, 400, 0.2), (37, 32, 0.0)])
+def test_bn_fused_cluster_kernels_match_split_kernels_and_autograd(rn, rows, C, drop):
+    """csrc/mlp_fused.cu: rat_bn_act_fwd_train / rat_bn_act_bwd_fused (one thread-block cluster per 32-column slab, partials
+    through distributed shared memory) against the split kernels they replace (same formulas; only the association of the
+    double column sums differs) and, without dropout, against torch autograd of BatchNorm1d(train) + ReLU incl. the bias
+    gradient of the Linear in front (= colsum(dz)).  Ragged shapes (rows not a multiple of 8 * 16, C not a multiple of 32)."""
+    from tests.gpu_util import assert_close
+    torch.manual_seed(rows + C)
+    d, st = DEV, rn.current_stream()
+    z = (torch.randn(rows, C) * 2 + 0.5)
+    gamma, beta = torch.randn(C), torch.randn(C)
+    dout = torch.randn(rows, C)
+    zd, gd, bd = z.cuda(), gamma.cuda(), beta.cuda()
+    # split path
+    sums = torch.empty(2 * C, dtype=torch.float64, device=d)
+    mean, rstd = torch.empty(C, device=d), torch.empty(C, device=d)
+    rm, rv = torch.zeros(C, device=d), torch.ones(C, device=d)
+    out = torch.empty(rows, C, device=d)
+    rn.call("rat_bn_sums", zd, rows, C, sums, st)
+    rn.call("rat_bn_finalize", sums, float(rows), C, mean, rstd, rm, rv, 0.1, 1e-5, st)
+    rn.call("rat_bn_act_fwd", zd, mean, rstd, gd, bd, out, rows, C, drop, 11, 3, st)
+    dz, dg, db = dout.cuda().clone(), torch.empty(C, device=d), torch.empty(C, device=d)
+    rn.call("rat_bn_act_bwd_sums", dz, out, zd, mean, rstd, rows, C, drop, 11, 3, sums, st)
+    am = torch.zeros(1, device=d)
+    rn.call("rat_bn_act_bwd_apply", dz, out, zd, mean, rstd, gd, sums, float(rows), dz, dg, db, rows, C, drop, 11, 3, am,
+            1.0, st)
+    dbias = torch.empty(C, device=d)
+    rn.call("rat_colsum", dz, rows, C, C, dbias, st)
+    # fused path
+    mean2, rstd2 = torch.empty(C, device=d), torch.empty(C, device=d)
+    rm2, rv2 = torch.zeros(C, device=d), torch.ones(C, device=d)
+    out2 = torch.full((rows, C), float("nan"), device=d)
+    rn.call("rat_bn_act_fwd_train", zd, rows, C, gd, bd, mean2, rstd2, rm2, rv2, 0.1, 1e-5, out2, drop, 11, 3, None, 0, 1, st)
+    assert_close("mean", mean2, mean, 1e-6, 1e-7)
+    assert_close("rstd", rstd2, rstd, 1e-6, 1e-7)
+    assert_close("running_mean", rm2, rm, 1e-6, 1e-7)
+    assert_close("running_var", rv2, rv, 1e-6, 1e-7)
+    assert_close("out", out2, out, 1e-5, 1e-6)
+    assert torch.equal(out2 == 0, out == 0)                         # same ReLU / dropout pattern
+    dz2, dg2, db2, dbias2 = dout.cuda().clone(), torch.empty(C, device=d), torch.empty(C, device=d), torch.empty(C, device=d)
+    am2 = torch.zeros(1, device=d)
+    rn.call("rat_bn_act_bwd_fused", dz2, out, zd, mean, rstd, gd, rows, C, dz2, dg2, db2, dbias2, drop, 11, 3, am2, None, 0, 1, st)
+    assert_close("dz", dz2, dz, 1e-5, 1e-6)
+    assert_close("dgamma", dg2, dg, 1e-5, 1e-5)
+    assert_close("dbeta", db2, db, 1e-5, 1e-5)
+    assert_close("dbias", dbias2, dbias, 1e-4, 2e-4)                # a sum that is ~0 by construction: absolute noise only
+    assert float(am2) == float(dz2.abs().max())
+    # twice the same => bitwise identical (rank-order cluster sums)
+    dz3, dg3, db3, dbias3 = dout.cuda().clone(), torch.empty(C, device=d), torch.empty(C, device=d), torch.empty(C, device=d)
+    rn.call("rat_bn_act_bwd_fused", dz3, out, zd, mean, rstd, gd, rows, C, dz3, dg3, db3, dbias3, drop, 11, 3, None, None, 0, 1, st)
+    assert torch.equal(dz3, dz2) and torch.equal(dg3, dg2) and torch.equal(dbias3, dbias2)
+    # no BatchNorm: dz = d relu, bias gradient = column sums
+    dz4, dbias4 = dout.cuda().clone(), torch.empty(C, device=d)
+    rn.call("rat_bn_act_bwd_fused", dz4, out, None, None, None, None, rows, C, dz4, None, None, dbias4, 0.0, 0, 0, None, None, 0, 1, st)
+    want4 = dout.cuda() * (out > 0)
+    assert torch.equal(dz4, want4)
+    assert_close("dbias (no bn)", dbias4, want4.double().sum(0).float(), 1e-5, 1e-5)
+    if drop == 0.0:
+        zr = z.clone().requires_grad_()
+        gr, br = gamma.clone().requires_grad_(), beta.clone().requires_grad_()
+        o = torch.relu(torch.nn.functional.batch_norm(zr, None, None, gr, br, True, 0.1, 1e-5))
+        o.backward(dout)
+        assert_close("out vs torch", out2, o.detach(), 1e-5, 1e-5)
+        assert_close("dz vs autograd", dz2, zr.grad, 1e-4, 1e-5)
+        assert_close("dgamma vs autograd", dg2, gr.grad, 1e-4, 1e-4)
+        assert_close("dbeta vs autograd", db2, br.grad, 1e-4, 1e-4)
+
+
+@pytest.mark.parametrize("B,D,K,stride", [(4096, 40, 400, 40 * 14 * 6), (513, 20, 0, 20), (100, 40, 33, 40)])
+def test_head_bwd_cluster_kernel(rn, B, D, K, stride):
+    """rat_head_bwd: fc / final-Linear gradients + d h_last from dlogit in one launch vs float64 torch."""
+    from tests.gpu_util import assert_close
+    torch.manual_seed(B + K)
+    d, st = DEV, rn.current_stream()
+    dlogit = (torch.randn(B) * 1e-3).to(d)
+    enc = torch.randn(B, stride, device=d)
+    g_fc_w, g_fc_b = torch.empty(D, device=d), torch.empty(1, device=d)
+    if K:
+        h, w = torch.randn(B, K, device=d).relu(), torch.randn(K, device=d)
+        g_w, g_b, dh = torch.empty(K, device=d), torch.empty(1, device=d), torch.empty(B, K, device=d)
+        rn.call("rat_head_bwd", dlogit, B, enc, stride, D, g_fc_w, g_fc_b, h, K, w, g_w, g_b, dh, st)
+        assert_close("g_final_w", g_w, (dlogit.double() @ h.double()).float(), 1e-5, 1e-7)
+        assert_close("g_final_b", g_b, dlogit.double().sum().float().view(1), 1e-5, 1e-8)
+        assert torch.equal(dh, dlogit[:, None] * w[None, :])
+    else:
+        rn.call("rat_head_bwd", dlogit, B, enc, stride, D, g_fc_w, g_fc_b, None, 0, None, None, None, None, st)
+    assert_close("g_fc_w", g_fc_w, (dlogit.double() @ enc[:, :D].double()).float(), 1e-5, 1e-7)
+    assert_close("g_fc_b", g_fc_b, dlogit.double().sum().float().view(1), 1e-5, 1e-8)
+
+
 # ------------------------------------------------------------------------------------------ K7/K8
 def test_clip_and_adam_match_torch(rn):
     """3 steps of (lambda W + clip + Adam) on a flat buffer vs torch.optim.Adam + clip_grad_norm_."""

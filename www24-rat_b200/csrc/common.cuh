@@ -41,6 +41,14 @@ int max_smem_optin();
 // they are given, so a CUDA graph of the training step replays with a fresh mask every time (the counter is advanced by
 // a kernel INSIDE the graph: rat_rng_step_advance).
 const unsigned int* rng_step_ptr();
+// Deferred record reductions (rat_set_reduce_stream): the k_reduce_* launch that follows a backward kernel only produces
+// weight gradients, which nothing reads before the optimizer, so it need not sit on the critical path between two backward
+// kernels.  reduce_fork returns the stream the reduction has to be launched on (the caller's stream when no reduce stream
+// is set), reduce_forked marks the reduction as the last reader of the record workspace `ws`, and reduce_ws_acquire makes
+// `main` wait for that reader before a kernel overwrites `ws`.  All three are stream-capture safe (events only).
+cudaStream_t reduce_fork(cudaStream_t main, const void* ws);
+void reduce_forked(cudaStream_t launched_on, cudaStream_t main, const void* ws);
+void reduce_ws_acquire(cudaStream_t main, const void* ws);
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline int round_up(int a, int b) { return ceil_div(a, b) * b; }

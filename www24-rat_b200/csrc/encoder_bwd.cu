@@ -602,6 +602,7 @@ extern "C" int rat_attn_bwd_dropout(const float* x, const float* dout, const flo
     RAT_REQUIRE(B > 0 && T > 0 && N > 0 && D > 0 && heads > 0, "rat_attn_bwd: bad shape");
     RAT_REQUIRE(D <= 128, "rat_attn_bwd: D=%d > 128 not supported", D);
     RAT_REQUIRE(out_drop_p >= 0.f && out_drop_p < 1.f, "rat_attn_bwd_dropout: dropout p=%f", out_drop_p);
+    reduce_ws_acquire((cudaStream_t)stream, workspace);     // deferred record reductions (rat_set_reduce_stream)
     if (precision_mode() == 2 && rr_enabled() && !getenv("RAT_RR_BWD_OFF")) {
         const int rc3 = attn_bwd_rr_dispatch(x, dout, base, dx, ln_w, ln_b, Wq, Wk, Wv, Wo, dWq, dWk, dWv, dWo, dbo, dln_w,
                                              dln_b, accumulate_wq, B, T, N, D, heads, dim_head, scale, alpha, mode, dout_amax, dx_amax,
@@ -678,6 +679,7 @@ extern "C" int rat_ff_bwd(const float* x, const float* dout, const float* base, 
                           const float* dout_amax, float* dx_amax, float* workspace, size_t workspace_bytes, void* stream) {
     RAT_REQUIRE(rows > 0 && D > 0 && M > 0, "rat_ff_bwd: bad shape");
     RAT_REQUIRE(D <= 128 && pad8(M) <= ENC_THREADS, "rat_ff_bwd: D=%d (<=128) M=%d (<=%d) not supported", D, M, ENC_THREADS);
+    reduce_ws_acquire((cudaStream_t)stream, workspace);
     if (precision_mode() == 2 && rr_enabled() && ln_w == nullptr && !getenv("RAT_RR_FF_OFF")) {
         const int rc3 = ff_bwd_rr_dispatch(x, dout, base, dx, W1, b1, W2, dW1, db1, dW2, db2, rows, D, M, dout_amax, dx_amax, workspace,
                                            workspace_bytes, (cudaStream_t)stream);
@@ -721,6 +723,7 @@ extern "C" int rat_layernorm_bwd(const float* x, const float* dout, float* dx, c
     const int grid = (int)min((rows + groups - 1) / groups, (long long)num_sms() * 4);
     RAT_REQUIRE(workspace && workspace_bytes >= (size_t)grid * 2 * D * sizeof(float), "rat_layernorm_bwd: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
+    reduce_ws_acquire(st, workspace);
     k_ln_bwd<<<grid, 256, (size_t)groups * 2 * D * sizeof(float), st>>>(x, dout, dx, w, rows, D, lg, workspace);
     RAT_CHECK_LAUNCH("k_ln_bwd");
     ReduceArgs r{};

@@ -560,6 +560,7 @@ int attn_bwd_rr_dispatch(const float* x, const float* dout, const float* base, f
     a.nseq = mode == 0 ? (long long)B * T : (long long)B * N;
     const int grid = attn_bwd_rr_grid(S, a.nseq);
     if (!workspace || workspace_bytes < (size_t)grid * a.psize * sizeof(float)) return 1;
+    reduce_ws_acquire(st, workspace);       // a deferred reduction may still be reading the records of an earlier call
     a.x = x; a.dout = dout; a.base = base; a.dx = dx; a.ln_w = ln_w; a.ln_b = ln_b; a.Wq = Wq; a.Wk = Wk; a.Wv = Wv; a.Wo = Wo;
     a.partials = workspace; a.dout_amax = dout_amax; a.dx_amax = dx_amax;
     a.g.S = S; a.g.mode = mode; a.g.T = T; a.g.N = N;
@@ -583,7 +584,9 @@ int attn_bwd_rr_dispatch(const float* x, const float* dout, const float* base, f
     AttnReduceTcArgs r{workspace, grid, a.psize, dWq, dWk, dWv, dWo, dbo, dln_w, dln_b, accumulate_wq, D, a.I, dh, a.hc,
                        a.nchunks, pad16(D), a.NCc, a.Cc, scale, 0.6931471805599453f};
     const int total = 4 * a.I * D + 3 * D;
-    k_reduce_attn_tc<<<std::max(1, std::min((total + 31) / 32, 1024)), dim3(32, 8), 0, st>>>(r);
+    cudaStream_t rs = reduce_fork(st, workspace);
+    k_reduce_attn_tc<<<std::max(1, std::min((total + 31) / 32, 1024)), dim3(32, 8), 0, rs>>>(r);
     RAT_CHECK_LAUNCH("k_reduce_attn_tc");
+    reduce_forked(rs, st, workspace);
     return RAT_OK;
 }

@@ -523,6 +523,7 @@ int ff_bwd_rr_dispatch(const float* x, const float* dout, const float* base, flo
           reinterpret_cast<uintptr_t>(dx)) & 7) != 0) return 1;
     const int grid = ff_bwd_rr_grid(rows);
     if (!workspace || workspace_bytes < (size_t)grid * a.psize * sizeof(float)) return 1;
+    reduce_ws_acquire(st, workspace);       // a deferred reduction may still be reading the records of an earlier call
     a.x = x; a.dout = dout; a.base = base; a.dx = dx; a.W1 = W1; a.b1 = b1; a.W2 = W2; a.partials = workspace;
     a.dout_amax = dout_amax; a.dx_amax = dx_amax; a.rows = rows;
     const int NTO = (D + 7) / 8, KS2 = pad16(M) / 16;

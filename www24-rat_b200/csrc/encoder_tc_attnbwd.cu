@@ -76,6 +76,7 @@ int attn_bwd_tc_dispatch(const float* x, const float* dout, const float* base, f
     a.nseq = mode == 0 ? (long long)B * T : (long long)B * N;
     const int grid = attn_bwd_tc_grid(a, a.nseq);
     if (!workspace || workspace_bytes < (size_t)grid * a.psize * sizeof(float)) return 1;
+    reduce_ws_acquire(st, workspace);       // a deferred reduction may still be reading the records of an earlier call
     a.x = x; a.dout = dout; a.base = base; a.dx = dx; a.ln_w = ln_w; a.ln_b = ln_b; a.Wq = Wq; a.Wk = Wk; a.Wv = Wv; a.Wo = Wo;
     a.partials = workspace; a.dout_amax = dout_amax; a.dx_amax = dx_amax;
     a.g.S = S; a.g.mode = mode; a.g.T = T; a.g.N = N;
@@ -92,8 +93,10 @@ int attn_bwd_tc_dispatch(const float* x, const float* dout, const float* base, f
     AttnReduceTcArgs r{workspace, grid, a.psize, dWq, dWk, dWv, dWo, dbo, dln_w, dln_b, accumulate_wq, D, a.I, dh, a.hc,
                        a.nchunks, a.Kp, a.NCc, a.Cc, 1.0f, 1.0f};
     const int total = 4 * a.I * D + 3 * D;
-    k_reduce_attn_tc<<<std::max(1, std::min((total + 31) / 32, 1024)), dim3(32, 8), 0, st>>>(r);
+    cudaStream_t rs = reduce_fork(st, workspace);
+    k_reduce_attn_tc<<<std::max(1, std::min((total + 31) / 32, 1024)), dim3(32, 8), 0, rs>>>(r);
     RAT_CHECK_LAUNCH("k_reduce_attn_tc");
+    reduce_forked(rs, st, workspace);
     return RAT_OK;
 }
 

@@ -288,6 +288,7 @@ int ff_bwd_tc_dispatch(const float* x, const float* dout, const float* base, flo
     if (ln_w != nullptr || !ff_bwd_tc_plan(D, M, &a)) return 1;
     const int grid = ff_bwd_tc_grid(rows);
     if (!workspace || workspace_bytes < (size_t)2 * grid * a.psize * sizeof(float)) return 1;
+    reduce_ws_acquire(st, workspace);
     a.x = x; a.dout = dout; a.base = base; a.dx = dx; a.W1 = W1; a.b1 = b1; a.W2 = W2; a.partials = workspace; a.rows = rows;
     a.dout_amax = dout_amax; a.dx_amax = dx_amax;
     const int kch = a.Kp / 16;
@@ -310,8 +311,10 @@ int ff_bwd_tc_dispatch(const float* x, const float* dout, const float* base, flo
     if (rc != RAT_OK) return rc;
     FFReduceTcArgs r{workspace, 2 * grid, a.psize, dW1, db1, dW2, db2, D, M, a.Kp, a.Mp};
     const int total = 2 * M * D + M + D;
-    k_reduce_ff_tc<<<std::max(1, std::min((total + 31) / 32, 1024)), dim3(32, 8), 0, st>>>(r);
+    cudaStream_t rs = reduce_fork(st, workspace);
+    k_reduce_ff_tc<<<std::max(1, std::min((total + 31) / 32, 1024)), dim3(32, 8), 0, rs>>>(r);
     RAT_CHECK_LAUNCH("k_reduce_ff_tc");
+    reduce_forked(rs, st, workspace);
     return RAT_OK;
 }
 
@@ -322,7 +325,9 @@ int ff_reduce_records(const float* partials, int nparts, int psize, float* dW1, 
                       int Kp, int Mp, cudaStream_t st) {
     FFReduceTcArgs r{partials, nparts, psize, dW1, db1, dW2, db2, D, M, Kp, Mp};
     const int total = 2 * M * D + M + D;
-    k_reduce_ff_tc<<<std::max(1, std::min((total + 31) / 32, 1024)), dim3(32, 8), 0, st>>>(r);
+    cudaStream_t rs = reduce_fork(st, partials);
+    k_reduce_ff_tc<<<std::max(1, std::min((total + 31) / 32, 1024)), dim3(32, 8), 0, rs>>>(r);
     RAT_CHECK_LAUNCH("k_reduce_ff_tc");
+    reduce_forked(rs, st, partials);
     return RAT_OK;
 }

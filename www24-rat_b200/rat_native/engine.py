@@ -12,6 +12,7 @@ regulariser, exactly the `"embedding_layer" in name` rule of base_model.py:86.  
 from __future__ import annotations
 
 import math
+import os
 from collections import OrderedDict
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -353,6 +354,7 @@ class RatEngine:
         self._amax_on = False
         self.rank = 0
         self._os_peers = None               # one-shot all-reduce over NVLink peer memory (csrc/collective.cu)
+        self._bnx_peers = None              # in-kernel exchange of the BatchNorm slab totals (csrc/mlp_fused.cu)
         try:
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized():
@@ -377,10 +379,19 @@ class RatEngine:
             dist.barrier()                  # every rank's buffer is zeroed before any peer stores into it
             self._os_buf, self._os_handle = buf, handle
             self._os_peers = torch.tensor([int(p) for p in handle.buffer_ptrs], dtype=torch.int64, device=self.device)
+            n2 = (int(query("rat_bn_exchange_workspace_bytes", self.world)) + 3) // 4
+            buf2 = symm.empty(n2, dtype=torch.int32, device=self.device)
+            buf2.zero_()
+            handle2 = symm.rendezvous(buf2, dist.group.WORLD.group_name)
+            torch.cuda.synchronize()
+            dist.barrier()
+            self._bnx_buf, self._bnx_handle = buf2, handle2
+            self._bnx_peers = torch.tensor([int(p) for p in handle2.buffer_ptrs], dtype=torch.int64, device=self.device)
         except Exception as exc:            # pragma: no cover - depends on the platform
             import logging
             logging.warning("one-shot all-reduce unavailable (%s): using NCCL for the BatchNorm sums", exc)
             self._os_peers = None
+            self._bnx_peers = None
 
     # ------------------------------------------------------------------ workspaces
     def _workspace(self, B: int, T: int, training: bool) -> dict:
@@ -443,6 +454,7 @@ class RatEngine:
             if nb == 0:
                 raise RuntimeError("RAT backward kernels: tile does not fit in shared memory for this shape")
             ws["bwd_ws"] = torch.empty(nb // 4 + 4, **f32)
+            ws["bwd_ws2"] = torch.empty(nb // 4 + 4, **f32)    # second record buffer: deferred reductions (_bwd_ws)
             sb = int(query("rat_emb_scatter_workspace_bytes", B * T * (L + 1), D))
             ws["scatter_ws"] = torch.empty(sb // 4 + 4, dtype=torch.int32, device=dev)
         self._ws[key] = ws
@@ -555,7 +567,7 @@ class RatEngine:
     def _transformer_bwd(self, ws, a, d, prefix, B, T, N):
         s, g = self.spec, self.store.grad_views
         rows = B * T * N
-        bw = ws["bwd_ws"]
+        bw = self._bwd_ws(ws)
         call("rat_layernorm_bwd", a[2 * s.depth], d, d, self.p[prefix + "norm.weight"], g[prefix + "norm.weight"],
              g[prefix + "norm.bias"], rows, s.embedding_dim, bw, bw.numel() * 4, current_stream())
         self._amax_forget(d)                     # written by a kernel that does not publish max|dx|
@@ -578,6 +590,13 @@ class RatEngine:
                 mean, rstd = ws["bn_mean"][li], ws["bn_rstd"][li]
                 gamma, beta = p[f"dnn.dnn.{bn}.weight"], p[f"dnn.dnn.{bn}.bias"]
                 rm, rv = self.buffers[f"dnn.dnn.{bn}.running_mean"], self.buffers[f"dnn.dnn.{bn}.running_var"]
+                if training and self._dnn_fused():     # one cluster kernel: statistics + running stats + apply
+                    call("rat_bn_act_fwd_train", z, B, width, gamma, beta, mean, rstd, rm, rv, 0.1, 1e-5, out,
+                         float(s.net_dropout), s.seed, self._rng_stream(16 + li), self._bnx_peers, self.rank,
+                         self.world, st)
+                    self.buffers[f"dnn.dnn.{bn}.num_batches_tracked"] += 1
+                    h, K = out, width
+                    continue
                 if training:
                     call("rat_bn_sums", z, B, width, ws["bn_sums"][li], st)
                     count = float(B) * self._allreduce_sums(ws["bn_sums"][li])
@@ -591,6 +610,11 @@ class RatEngine:
             h, K = out, width
         call("rat_sgemm", h, p[f"dnn.dnn.{final}.weight"], ws["dnn_out"], p[f"dnn.dnn.{final}.bias"], B, 1, K, K, K, 1,
              0, 0, gw, gw.numel() * 4, st)
+
+    def _dnn_fused(self) -> bool:
+        """single-launch BatchNorm kernels (csrc/mlp_fused.cu); data-parallel: the slab totals are exchanged over NVLink
+        peer memory inside the launch, which needs the symmetric exchange buffer."""
+        return (self.world == 1 or self._bnx_peers is not None) and os.environ.get("RAT_DNN_FUSED", "1") != "0"
 
     def _allreduce_sums(self, t) -> int:
         """data-parallel hook (SyncBN-equivalent): all-reduce raw BN sums; returns the world size."""
@@ -650,9 +674,21 @@ class RatEngine:
                  float(drop), s.seed, self._rng_stream(0), self.err_flag, st)
         if training:                # after the gather is queued: the sort overlaps the RAT-block kernels, not the gather
             self._plan_scatter(ws, B, T)
+        dnn_done = None
+        if len(s.dnn_hidden_units) and self._dnn_on_side_stream():
+            side2, main = self._side_stream(1), torch.cuda.current_stream()
+            ready = torch.cuda.Event()
+            ready.record(main)                          # x_emb is written by the gather
+            side2.wait_event(ready)
+            with torch.cuda.stream(side2):
+                self._dnn_forward(ws, B, training)
+                dnn_done = torch.cuda.Event()
+                dnn_done.record(side2)
         enc = self.encode(ws, B, T, training)
         ws["enc_out"] = enc
-        if len(s.dnn_hidden_units):
+        if dnn_done is not None:
+            torch.cuda.current_stream().wait_event(dnn_done)
+        elif len(s.dnn_hidden_units):
             self._dnn_forward(ws, B, training)
         N = F + 1
         want_loss = with_loss or training
@@ -711,6 +747,29 @@ class RatEngine:
     def _amax_forget(self, t):
         self._amax_of.pop(t.data_ptr(), None)
 
+    def _bwd_ws(self, ws):
+        """record workspace of the next backward kernel.  With deferred reductions (rat_set_reduce_stream) two buffers
+        alternate: the reduction of call i reads one while the kernel of call i+1 writes the other."""
+        self._bwd_flip = not getattr(self, "_bwd_flip", False)
+        return ws["bwd_ws2"] if (self._bwd_flip and self._defer_reduce()) else ws["bwd_ws"]
+
+    def _defer_reduce(self) -> bool:
+        return os.environ.get("RAT_DEFER_REDUCE", "0") == "1"     # measured: no gain (DESIGN.md section 3), off
+
+    def _dnn_on_side_stream(self) -> bool:
+        """run the DNN head (independent of the RAT encoder between the gather and the logit) on its own stream.
+        Needs the single-launch BatchNorm kernels (the split ones share a library-internal scratch buffer)."""
+        return self._dnn_fused() and os.environ.get("RAT_DNN_SIDE", "1") != "0"
+
+    def _side_stream(self, which: int):
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        if which == 0:
+            return self._side
+        if getattr(self, "_side2", None) is None:
+            self._side2 = torch.cuda.Stream(device=self.device)
+        return self._side2
+
     def _attn_bwd(self, ws, x, d_in, base, d_out, pre, mode, B, T, N, alpha=1.0, heads=None, dh=None,
                   wq=None, wk=None, wv=None, names=None, acc_wq=0):
         s, p, g = self.spec, self.p, self.store.grad_views
@@ -723,7 +782,7 @@ class RatEngine:
             gq, gk, gv = gw[:I], gw[I:2 * I], gw[2 * I:]
         else:
             gq, gk, gv = (g[n] for n in names)
-        bw = ws["bwd_ws"]
+        bw = self._bwd_ws(ws)
         call("rat_attn_bwd", x, d_in, base, d_out, p[pre + "norm.weight"], p[pre + "norm.bias"], wq, wk, wv,
              p[pre + "fn.to_out.0.weight"], gq, gk, gv, g[pre + "fn.to_out.0.weight"], g[pre + "fn.to_out.0.bias"],
              g[pre + "norm.weight"], g[pre + "norm.bias"], acc_wq, B, T, N, s.embedding_dim, H, d_h,
@@ -733,7 +792,7 @@ class RatEngine:
     def _ff_bwd(self, ws, x, d_in, base, d_out, pre, rows, ln=None):
         s, p, g = self.spec, self.p, self.store.grad_views
         D, M = s.embedding_dim, s.embedding_dim * s.scale_dim
-        bw = ws["bwd_ws"]
+        bw = self._bwd_ws(ws)
         call("rat_ff_bwd", x, d_in, base, d_out, p[ln + "weight"] if ln else None, p[ln + "bias"] if ln else None,
              p[pre + "net.0.weight"], p[pre + "net.0.bias"], p[pre + "net.3.weight"], g[pre + "net.0.weight"],
              g[pre + "net.0.bias"], g[pre + "net.3.weight"], g[pre + "net.3.bias"], g[ln + "weight"] if ln else None,
@@ -798,18 +857,24 @@ class RatEngine:
         dlogit = ws["dlogit"]
         K = units[-1]
         h_last = ws["h"][-1]
-        # final Linear(K -> 1)
-        call("rat_sgemm", dlogit, h_last, g[f"dnn.dnn.{final}.weight"], None, 1, K, B, 1, K, K, 1, 1, gw, gwb, st)
-        call("rat_colsum", dlogit, B, 1, 1, g[f"dnn.dnn.{final}.bias"], st)
-        call("rat_sgemm", dlogit, p[f"dnn.dnn.{final}.weight"], ws["dh"][-1], None, B, K, 1, 1, K, K, 0, 1, gw, gwb, st)
+        # final Linear(K -> 1): done by rat_head_bwd (backward) together with the fc gradients
         count = float(B * self.world)
+        fused = self._dnn_fused()
         for li in reversed(range(len(units))):
             lin, bn = layers[li]
             u = units[li]
             dh, out, z = ws["dh"][li], ws["h"][li], ws["z"][li]
             drop = float(s.net_dropout)
             am = self._amax_new()       # max|dz| (published by bn_act_bwd_apply): the fp16 GEMMs lift dz by a power of two
-            if bn is not None:
+            if fused:                   # sums + apply + bias gradient in one cluster kernel
+                if bn is not None:
+                    call("rat_bn_act_bwd_fused", dh, out, z, ws["bn_mean"][li], ws["bn_rstd"][li], p[f"dnn.dnn.{bn}.weight"],
+                         B, u, dh, g[f"dnn.dnn.{bn}.weight"], g[f"dnn.dnn.{bn}.bias"], g[f"dnn.dnn.{lin}.bias"], drop,
+                         s.seed, self._rng_stream(16 + li), am, self._bnx_peers, self.rank, self.world, st)
+                else:
+                    call("rat_bn_act_bwd_fused", dh, out, z, None, None, None, B, u, dh, None, None,
+                         g[f"dnn.dnn.{lin}.bias"], drop, s.seed, self._rng_stream(16 + li), am, None, 0, 1, st)
+            elif bn is not None:
                 call("rat_bn_act_bwd_sums", dh, out, z, ws["bn_mean"][li], ws["bn_rstd"][li], B, u, drop, s.seed,
                      self._rng_stream(16 + li), ws["bn_sums"][li], st)
                 self._allreduce_sums(ws["bn_sums"][li])
@@ -824,7 +889,8 @@ class RatEngine:
             d_prev = ws["dh"][li - 1] if li > 0 else ws["dxemb"]
             call("rat_sgemm_scaled", dh, h_prev, g[f"dnn.dnn.{lin}.weight"], None, u, Kin, B, u, Kin, Kin, 1, 1, am,
                  gw, gwb, st)
-            call("rat_colsum", dh, B, u, u, g[f"dnn.dnn.{lin}.bias"], st)
+            if not fused:
+                call("rat_colsum", dh, B, u, u, g[f"dnn.dnn.{lin}.bias"], st)
             call("rat_sgemm_scaled", dh, p[f"dnn.dnn.{lin}.weight"], d_prev, None, B, Kin, u, u, Kin, Kin, 0, 1, am,
                  gw, gwb, st)
 
@@ -839,13 +905,41 @@ class RatEngine:
         slot = self._amax_out(ws["denc"])
         if slot is not None:
             call("rat_absmax", ws["denc"], B, D, ws["enc_stride"], slot, st)
-        # fc
-        call("rat_sgemm", ws["dlogit"], enc, g["fc.weight"], None, 1, D, B, 1, ws["enc_stride"], D, 1, 1, None, 0, st)
-        call("rat_colsum", ws["dlogit"], B, 1, 1, g["fc.bias"], st)
+        # fc + final Linear(K -> 1) of the DNN: every gradient that hangs off dlogit, one launch
         has_dnn = len(s.dnn_hidden_units) > 0
         if has_dnn:
-            self._dnn_backward(ws, B)
-        d = self.encode_backward(ws, B, T)
+            _, final = dnn_layout(s)
+            Kl = s.dnn_hidden_units[-1]
+            call("rat_head_bwd", ws["dlogit"], B, enc, ws["enc_stride"], D, g["fc.weight"], g["fc.bias"], ws["h"][-1], Kl,
+                 self.p[f"dnn.dnn.{final}.weight"], g[f"dnn.dnn.{final}.weight"], g[f"dnn.dnn.{final}.bias"],
+                 ws["dh"][-1], st)
+        else:
+            call("rat_head_bwd", ws["dlogit"], B, enc, ws["enc_stride"], D, g["fc.weight"], g["fc.bias"], None, 0, None,
+                 None, None, None, st)
+        dnn_done = None
+        if has_dnn:
+            if self._dnn_on_side_stream():
+                side2, main = self._side_stream(1), torch.cuda.current_stream()
+                ready = torch.cuda.Event()
+                ready.record(main)
+                side2.wait_event(ready)
+                with torch.cuda.stream(side2):
+                    self._dnn_backward(ws, B)
+                    dnn_done = torch.cuda.Event()
+                    dnn_done.record(side2)
+            else:
+                self._dnn_backward(ws, B)
+        defer = self._defer_reduce()
+        if defer:           # weight-gradient record reductions leave the critical path (include/rat_b200.h)
+            call("rat_set_reduce_stream", self._side_stream(0).cuda_stream)
+        try:
+            d = self.encode_backward(ws, B, T)
+        finally:
+            if defer:
+                call("rat_reduce_stream_join", st)
+                call("rat_set_reduce_stream", None)
+        if dnn_done is not None:
+            torch.cuda.current_stream().wait_event(dnn_done)
         sw = ws["scatter_ws"]
         gs = self.store
         self._net_work = None
