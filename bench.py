@@ -464,6 +464,9 @@ def small_workload(shape, B, K, precision, rank, world, local, dist, steps=6, wa
     model._engine._ws.clear()
     model._engine._graphs.clear()
     del model, gen, batches
+    import gc
+    torch.cuda.synchronize()
+    gc.collect()                # models sit in reference cycles: free their (symmetric-memory) buffers now, not inside a later capture
     torch.cuda.empty_cache()
     set_precision("fp16")
     return out

@@ -21,6 +21,23 @@ import torch
 
 from . import call, current_stream, query, require_device
 
+
+class _no_gc:
+    """No automatic garbage collection while a CUDA graph is being captured: a collected engine of an EARLIER model frees
+    its symmetric-memory buffers (cuMemUnmap / cudaFree), which CUDA forbids during a global-mode capture and which
+    aborts the process from a destructor.  torch.cuda.graph.__enter__ runs gc.collect() itself before the capture starts."""
+
+    def __enter__(self):
+        import gc
+        self._was = gc.isenabled()
+        gc.disable()
+
+    def __exit__(self, *exc):
+        import gc
+        if self._was:
+            gc.enable()
+        return False
+
 EMB = "embedding_layer.embedding_layer.embedding_layer."
 LRP = "lr_layer.embedding_layer.embedding_layer.embedding_layer."
 
@@ -649,7 +666,7 @@ class RatEngine:
                     torch.cuda.synchronize()
                     g = torch.cuda.CUDAGraph()
                     n0 = int(query("rat_launch_count"))
-                    with torch.cuda.graph(g):
+                    with _no_gc(), torch.cuda.graph(g):
                         self._forward_ids_impl(ws, B, T, False, False, None)
                     entry = (g, ws, int(query("rat_launch_count")) - n0)     # the graph keeps its workspace alive
                     self._graphs[key] = entry
@@ -1062,7 +1079,7 @@ class RatEngine:
                         torch.cuda.synchronize()
                         g = torch.cuda.CUDAGraph()
                         n0 = int(query("rat_launch_count"))
-                        with torch.cuda.graph(g):
+                        with _no_gc(), torch.cuda.graph(g):
                             self._train_step_impl(ws, B, T)
                         entry = (g, ws, int(query("rat_launch_count")) - n0)
                     except Exception as exc:             # capture not possible here: stay eager for this key
