@@ -582,6 +582,72 @@ def _full_width_train(rn, shape, B, K, mode="fp32"):
             assert_close_adam(f"param {k}", eng.p[k], w, 2e-4, 1e-4, lr_steps=3.5e-3)
 
 
+def _export_masks(rn, eng, spec, B, T):
+    """0/1 keep-masks of the training step that JUST ran: rat_dropout_bwd regenerates the step's mask function (seed, call-site
+    stream, device-resident step counter, flat element index) on a tensor of ones."""
+    st = rn.current_stream()
+    N, D = spec.num_fields + 1, spec.embedding_dim
+    emb = torch.ones(B, T, N, D, device=DEV)
+    rn.call("rat_dropout_bwd", emb, emb.numel(), float(spec.emb_dropout), eng.spec.seed, 0, st)
+    dnn = []
+    for li, u in enumerate(spec.dnn_hidden_units):
+        m = torch.ones(B, u, device=DEV)
+        if spec.net_dropout > 0:
+            rn.call("rat_dropout_bwd", m, m.numel(), float(spec.net_dropout), eng.spec.seed, 16 + li, st)
+        dnn.append((m != 0).float().cpu())
+    return (emb != 0).float().cpu(), dnn
+
+
+@pytest.mark.parametrize("mode", ["fp32", "fp16"])
+def test_dropout_training_equals_oracle_with_the_same_masks(rn, mode):
+    """tmall configuration (emb_dropout 0.1 on the whole feature block, net_dropout 0.08 after every DNN ReLU): the
+    reference's philox stream cannot be reproduced, but the arithmetic around the masks can be pinned exactly --
+    export the keep-masks each GPU step used and replay the step in the oracle with them: loss, gradient norm and post-Adam
+    weights must agree as tightly as without dropout.  Step 1 runs eagerly, steps 2-3 as CUDA-graph replays (fresh masks
+    from the device-side step counter)."""
+    from rat_native.engine import set_precision
+    from tests.gpu_util import assert_close, assert_close_adam, make_engine, rand_params_nontrivial
+    set_precision(mode)
+    try:
+        f16 = mode != "fp32"
+        B, K = 64, 5
+        spec = O.shape_spec("tmall", vocab_scale=0.002)
+        assert spec.emb_dropout == pytest.approx(0.1) and spec.net_dropout == pytest.approx(0.08)
+        params = rand_params_nontrivial(spec, seed=5)
+        bufs = O.init_buffers(spec)
+        pool = O.synthetic_pool(spec, 2000, seed=3)
+        nbr = O.synthetic_neighbours(B, 2000, K, seed=3)
+        X, y = O.assemble_batch(pool[:B], pool, nbr, np.arange(B))
+        X, y = torch.from_numpy(X), torch.from_numpy(y)
+        eng = make_engine(spec, params, bufs)
+        ws = eng.load_wire(X.cuda(), y.cuda(), training=True)
+        st = O.AdamState()
+        seen = []
+        for step in range(3):
+            eng.train_step_ids(ws, B, K + 1)
+            eng.check_errors()
+            emb_mask, dnn_masks = _export_masks(rn, eng, spec, B, K + 1)
+            keep = float(emb_mask.mean())
+            assert 0.86 < keep < 0.94, keep
+            seen.append(emb_mask)
+            r = O.train_step(params, bufs, spec, st, X, y, emb_mask=emb_mask, dnn_masks=dnn_masks)
+            got_loss = float(ws["loss"][1]) + float(eng.opt_state[5])
+            assert got_loss == pytest.approx(r["loss"], rel=3e-3 if f16 else 2e-4), f"step {step}"
+            assert float(eng.opt_state[0]) == pytest.approx(r["grad_norm"], rel=2e-2 if f16 else 3e-3), f"step {step}"
+        assert not torch.equal(seen[0], seen[1]) and not torch.equal(seen[1], seen[2])      # a fresh mask every step
+        for k, w in params.items():
+            if k.startswith("query_proj"):
+                continue
+            if noise_grad_param(k, spec):
+                assert_close(f"param {k}", eng.p[k], w, 2e-4, 6.5e-3)
+            elif f16:
+                assert_close_adam(f"param {k}", eng.p[k], w, 4e-3, 6e-4, lr_steps=6.5e-3, max_outlier_frac=0.06)
+            else:
+                assert_close_adam(f"param {k}", eng.p[k], w, 2e-4, 1e-4, lr_steps=3.5e-3)
+    finally:
+        set_precision("fp16")
+
+
 @pytest.mark.parametrize("name", CASES_M2 + ["rat_m3_small", "rat_m0_small", "rat_m1_small"])
 def test_two_train_steps_tf32_close_to_reference(rn, name):
     """TF32 mma.sync projections: loss within 2e-3, grad-norm within 1e-2, and every
