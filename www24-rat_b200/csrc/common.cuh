@@ -53,6 +53,31 @@ void reduce_ws_acquire(cudaStream_t main, const void* ws);
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 
+// ---- programmatic dependent launch (PDL) of the RAT-block kernels.  Every register-resident kernel starts with a prologue
+// that does not depend on the previous kernel of the stream (weight images in fragment order, LayerNorm / bias vectors,
+// TMEM allocation, barrier init: 4-9 us per CTA).  Launched with the programmatic-stream-serialization attribute its CTAs
+// may become resident as soon as every CTA of the previous kernel has passed pdl_launch_dependents() (first statement) and an
+// SM has room, i.e. under the previous kernel's tail instead of after its last CTA has drained; pdl_wait() -- before the
+// first read of an activation / gradient-scale slot and before any global write -- blocks until the previous grid has
+// completed and its memory is visible.  Both are no-ops for a kernel launched the ordinary way.  RAT_PDL=0 turns the
+// attribute off.
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <class Kernel, class Args>
+inline cudaError_t launch_pdl(Kernel kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const Args& args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args);
+}
+#endif
+
 #ifdef __CUDACC__
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

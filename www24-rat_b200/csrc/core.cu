@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "../../include/rat_b200.h"
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace rat {
@@ -39,6 +40,10 @@ const unsigned int* rng_step_ptr() {
     return g_rng_step;
 }
 __global__ void k_rng_step(unsigned int* p, unsigned int set, int advance) { *p = advance ? *p + 1u : set; }
+bool pdl_enabled() {
+    static const bool on = !(getenv("RAT_PDL") && getenv("RAT_PDL")[0] == '0');
+    return on;
+}
 int num_sms() { if (!g_sms) query(); return g_sms; }
 int max_smem_optin() { if (!g_smem) query(); return g_smem; }
 

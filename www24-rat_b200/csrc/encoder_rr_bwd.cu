@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(RRB_THREADS, 1) k_attn_bwd_rr(AttnBwdRRArgs a)
     __shared__ unsigned int arrive_cnt;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = lane & 3, g = lane >> 2;
-    const float gs = tc_grad_scale(a.dout_amax), inv_gs = 1.0f / gs;
+    pdl_launch_dependents();
+    float gs = 1.0f, inv_gs = 1.0f;                       // gradient scale: read after pdl_wait (the slot is published by the previous kernel)
     // ---- images (raw weights first, with coalesced loads, into the token-tile region; then fragment order from shared memory)
     {
         float* raw = reinterpret_cast<float*>(Xt);        // Wq | Wk | Wv [3][I][D], Wo [D][I]: 16 I D bytes <= the tile region (plan)
@@ -125,6 +126,9 @@ __global__ void __launch_bounds__(RRB_THREADS, 1) k_attn_bwd_rr(AttnBwdRRArgs a)
     tc5::fence_before_sync();
     __syncthreads();
     tc5::fence_after_sync();
+    pdl_wait();                                           // x / dout / base / the amax slot come from the previous kernels
+    gs = tc_grad_scale(a.dout_amax);
+    inv_gs = 1.0f / gs;
     const uint32_t tmem_W = tmem_base_s;                                   // [nchunks][MB] blocks of Kp columns
     const uint32_t tmem_A = tmem_W + (uint32_t)(a.nchunks * MB * Kp);      // dA, Kp columns
 
@@ -491,7 +495,8 @@ static int launch_attn_bwd_rr_v(const AttnBwdRRArgs& a, int grid, cudaStream_t s
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_attn_bwd_rr)");
         attr_set = true;
     }
-    k_attn_bwd_rr<KS, NTO, VEC4, F16P, F16C, UNR><<<grid, RRB_THREADS, a.smem_bytes, st>>>(a);
+    if (launch_pdl(k_attn_bwd_rr<KS, NTO, VEC4, F16P, F16C, UNR>, dim3(grid), dim3(RRB_THREADS), (size_t)a.smem_bytes, st, a) != cudaSuccess)
+        return cuda_fail(cudaGetLastError(), "k_attn_bwd_rr");
     RAT_CHECK_LAUNCH("k_attn_bwd_rr");
     return RAT_OK;
 }

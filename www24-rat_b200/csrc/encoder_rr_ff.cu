@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_ff_fwd_rr(FFRRArgs a) {
     float* stage = b2_s + NP * 16;                         // BULK: [WARPS][2][16 rows][D]
     __shared__ __align__(8) uint64_t row_bar[WARPS][2];
     const bool prenorm = a.ln_w != nullptr;
+    pdl_launch_dependents();
     for (int i = threadIdx.x; i < KS2 * KS * 32; i += blockDim.x) {
         const int p = i / (KS * 32), ks = (i >> 5) % KS, ln = i & 31;
         W1_i[i] = frag_pair_entry(ln, 16 * p, 16 * ks, [&](int m, int c) { return (m < M && c < D) ? __ldg(a.W1 + (size_t)m * D + c) : 0.f; });
@@ -50,6 +51,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_ff_fwd_rr(FFRRArgs a) {
     if (threadIdx.x < WARPS * 2) tc5::mbar_init(&row_bar[0][0] + threadIdx.x, 1);
     tc5::fence_mbar_init();
     __syncthreads();
+    pdl_wait();                                            // x / res are written by the previous kernel of the stream
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = lane & 3, g = lane >> 2;
     const float invD = 1.0f / (float)D;
     const long long ntasks = (a.rows + 15) >> 4;
@@ -177,7 +179,8 @@ static int launch_ff_fwd_rr_w(const FFRRArgs& a, cudaStream_t st) {
     const long long ntasks = (a.rows + 15) / 16;
     const long long nblk = (ntasks + WARPS - 1) / WARPS;
     const int grid = (int)std::min<long long>(nblk, (long long)CTAS * num_sms());
-    k_ff_fwd_rr<KS, NTO, KS2, WARPS, CTAS, BULK><<<grid, WARPS * 32, smem, st>>>(a);
+    if (launch_pdl(k_ff_fwd_rr<KS, NTO, KS2, WARPS, CTAS, BULK>, dim3(grid), dim3(WARPS * 32), smem, st, a) != cudaSuccess)
+        return cuda_fail(cudaGetLastError(), "k_ff_fwd_rr");
     RAT_CHECK_LAUNCH("k_ff_fwd_rr");
     return RAT_OK;
 }
@@ -240,7 +243,7 @@ __global__ void __launch_bounds__(FFB_WARPS * 32, 1) k_ff_bwd_rr(FFBwdRRArgs a) 
     __shared__ unsigned int arrive_cnt;
     __shared__ float red[FFB_WARPS][Kp];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = lane & 3, g = lane >> 2;
-    const float gs = tc_grad_scale(a.dout_amax), inv_gs = 1.0f / gs;
+    pdl_launch_dependents();
     for (int i = threadIdx.x; i < KS2 * KS * 32; i += blockDim.x) {
         const int p = i / (KS * 32), ks = (i >> 5) % KS, ln = i & 31;
         W1_i[i] = frag_pair_entry(ln, 16 * p, 16 * ks, [&](int m, int c) { return (m < M && c < D) ? __ldg(a.W1 + (size_t)m * D + c) : 0.f; });
@@ -261,6 +264,8 @@ __global__ void __launch_bounds__(FFB_WARPS * 32, 1) k_ff_bwd_rr(FFBwdRRArgs a) 
     tc5::fence_before_sync();
     __syncthreads();
     tc5::fence_after_sync();
+    pdl_wait();                                            // x / dout / base / the amax slot come from the previous kernels
+    const float gs = tc_grad_scale(a.dout_amax), inv_gs = 1.0f / gs;
     const uint32_t tmem_W1 = tmem_base_s, tmem_W2 = tmem_base_s + Kp;      // gW1 [m][c] (c = D: gb1), gW2^T [m][c]
     const uint32_t Xt_s = tc5::smem_u32(Xt), DYt_s = tc5::smem_u32(DYt), Zt_s = tc5::smem_u32(Zt), Ht_s = tc5::smem_u32(Ht);
     const uint32_t idesc_w = tc5::instr_desc(TC_FMT, 128, Kp, 1, 1);
@@ -478,7 +483,8 @@ static int launch_ff_bwd_rr(const FFBwdRRArgs& a, int grid, cudaStream_t st) {
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_ff_bwd_rr)");
         attr_set = true;
     }
-    k_ff_bwd_rr<KS, NTO, KS2><<<grid, FFB_WARPS * 32, a.smem_bytes, st>>>(a);
+    if (launch_pdl(k_ff_bwd_rr<KS, NTO, KS2>, dim3(grid), dim3(FFB_WARPS * 32), (size_t)a.smem_bytes, st, a) != cudaSuccess)
+        return cuda_fail(cudaGetLastError(), "k_ff_bwd_rr");
     RAT_CHECK_LAUNCH("k_ff_bwd_rr");
     return RAT_OK;
 }

@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_attn_fwd_rr(AttnRRArgs a) 
     float* bo_s = lnb_s + KS * 16;                        // [NP * 16]
     float* stage = bo_s + NP * 16;                        // BULK: [WARPS][2][16 rows][D] ; during setup: raw fp32 weights
     __shared__ __align__(8) uint64_t row_bar[WARPS][2];
+    pdl_launch_dependents();
     {
         // raw weights with coalesced loads (one memory latency), then the fragment-order images from shared memory
         float* raw = stage;                               // Wq | Wk | Wv [3][I][D], Wo [D][I]
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_attn_fwd_rr(AttnRRArgs a) 
         tc5::fence_proxy_async();        // the raw-weight region becomes the target of bulk copies
     }
     __syncthreads();
+    pdl_wait();                          // x (and res) are written by the previous kernel of the stream
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = lane & 3, g = lane >> 2;
     const int S = a.g.S;
     const float invD = 1.0f / (float)D;
@@ -212,7 +214,8 @@ static int launch_attn_fwd_rr_v(const AttnRRArgs& a, cudaStream_t st) {
     const long long ntasks = a.g.S <= 8 ? (a.nseq + 1) / 2 : a.nseq;
     const long long nblk = (ntasks + WARPS - 1) / WARPS;
     const int grid = (int)std::min<long long>(nblk, (long long)CTAS * num_sms());
-    k_attn_fwd_rr<KS, NTO, WARPS, CTAS, BULK, F16P, F16C, UNR><<<grid, WARPS * 32, smem, st>>>(a);
+    if (launch_pdl(k_attn_fwd_rr<KS, NTO, WARPS, CTAS, BULK, F16P, F16C, UNR>, dim3(grid), dim3(WARPS * 32), smem, st, a) != cudaSuccess)
+        return cuda_fail(cudaGetLastError(), "k_attn_fwd_rr");
     RAT_CHECK_LAUNCH("k_attn_fwd_rr");
     return RAT_OK;
 }

@@ -523,6 +523,7 @@ struct AttnReduceTcArgs {
     float qmul, kmul;        // multipliers of the dWq / dWk records (the register-resident kernel stores dq / scale, dk / ln2)
 };
 static __global__ void k_reduce_attn_tc(AttnReduceTcArgs a) {
+    pdl_launch_dependents();            // the next backward kernel may run its prologue under this reduction (common.cuh)
     const int D = a.D, I = a.I;
     const int total = 4 * I * D + 3 * D;
     const size_t offO = (size_t)a.nchunks * a.NCc * a.Kp, offS = offO + (size_t)a.nchunks * a.Cc * a.Kp;

@@ -219,6 +219,7 @@ struct FFReduceTcArgs {
     int D, M, Kp, Mp;
 };
 __global__ void k_reduce_ff_tc(FFReduceTcArgs a) {
+    pdl_launch_dependents();            // the next backward kernel may run its prologue under this reduction (common.cuh)
     const int D = a.D, M = a.M, Kp = a.Kp, Mp = a.Mp;
     const int total = 2 * M * D + M + D;
     for (int base = blockIdx.x * 32; base < total; base += gridDim.x * 32) {
