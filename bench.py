@@ -217,7 +217,7 @@ def run_ours(a):
     # host wire-format batches (pinned) for the e2e leg: disjoint rows per step and rank
     rng = np.random.default_rng(1234 + rank)
     host_batches = []
-    for i in range(n_steps_total):
+    for i in range(n_steps_total + 1):            # one more: every timed e2e step stages the NEXT step's batch
         rows = rng.integers(0, a.pool_rows, size=B)
         X, y, v, l = shapes.host_wire_batch(pool, pool, nbr, rows)
         host_batches.append(tuple(torch.from_numpy(t).pin_memory() for t in (X, y, v, l)))
@@ -236,10 +236,24 @@ def run_ours(a):
     clocks = sampler.stop() if sampler else None
     model._engine.check_errors()
 
-    def e2e_train(i):
+    def e2e_train_serial(i):                      # copy, step and loss read strictly one after the other
         loss = model.train_step(host_batches[i])
         return float(loss.item())                 # device -> host read of the step's result
+    t_e2e_serial = timed(e2e_train_serial, a.steps, a.warmup, dist)
+
+    staged = {}
+    def e2e_train(i):
+        # the public training loop (BaseModel.train_one_epoch): batch i+1's pinned host -> device copy is started on the
+        # model's copy stream (stage_batch) before step i is enqueued, so every step still performs exactly one H2D copy
+        # of h2d bytes inside the timed region, overlapped with compute; the loss is read back every step
+        cur = staged.pop(i, None)
+        if cur is None:
+            cur = model.stage_batch(host_batches[i])
+        staged[i + 1] = model.stage_batch(host_batches[i + 1])
+        loss = model.train_step(cur)
+        return float(loss.item())                 # device -> host read of the step's result
     t_e2e = timed(e2e_train, a.steps, a.warmup, dist)
+    staged.clear()
 
     model.eval()
     with torch.no_grad():
@@ -253,7 +267,12 @@ def run_ours(a):
         t_e2e_inf = timed(e2e_inf, a.steps, a.warmup, dist)
 
     # ---- per-kernel timing pass (CUDA events around every C-ABI call; not part of the headline numbers)
+    # Serialised for this pass only: the DNN head normally runs on its own stream NEXT to the RAT encoder and the RAT-block
+    # kernels start their prologue under the previous kernel (programmatic dependent launch); either would make an event
+    # pair measure queueing / overlap instead of the entry point's own kernels.
     model.train()
+    side_env = {k: os.environ.get(k) for k in ("RAT_DNN_SIDE",)}
+    os.environ["RAT_DNN_SIDE"] = "0"
     rn.profile_calls(True)
     nprof = min(5, a.steps)
     for i in range(nprof):
@@ -264,6 +283,11 @@ def run_ours(a):
         torch.cuda.synchronize()
     prof = rn.profile_results()
     rn.profile_calls(False)
+    for k, v in side_env.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
     pk = peaks()
     total_ms = sum(ms for _, ms in prof.values())
     kernels = {k: {"calls_per_step": n // nprof, "ms_per_step": round(ms / nprof, 4), "share": round(ms / total_ms, 4)}
@@ -401,7 +425,11 @@ def run_ours(a):
                    "vocab_scale": a.vocab_scale,
                    "l2": "every step uses a new batch; per-step working set (~660 MB activations) exceeds the 126 MB L2"},
         "e2e": {"value": round(a.steps * gB / t_e2e, 1), "unit": "samples/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": 4, "api": "fuxictr.pytorch.models.RAT_m2.train_step(host f64 wire batch)"},
+                "d2h_bytes_per_step": 4,
+                "api": "fuxictr.pytorch.models.RAT_m2: stage_batch(host f64 wire batch i+1) ; train_step(batch i) ; loss.item() -- "
+                       "the loop of BaseModel.train_one_epoch: one pinned H2D copy per step on the copy stream, under the step",
+                "serial": {"value": round(a.steps * gB / t_e2e_serial, 1), "unit": "samples/s",
+                           "api": "train_step(host f64 wire batch) ; loss.item(): copy, step and read strictly in sequence"}},
         "infer": {"value": round(a.steps * gB / t_inf, 1), "unit": "samples/s",
                   "ms_per_step": round(t_inf / a.steps * 1e3, 4),
                   "e2e": {"value": round(a.steps * gB / t_e2e_inf, 1), "unit": "samples/s", "h2d_bytes_per_step": h2d,
@@ -411,6 +439,10 @@ def run_ours(a):
         "roofline": roofline, "roofline_gather": roofline_gather, "roofline_scatter": roofline_scatter,
         "roofline_adam": roofline_adam,
         "kernels": kernels,
+        "kernels_note": "per-entry-point CUDA-event times of a separate, serialised pass (eager launches, DNN head on the main "
+                        "stream); in the timed steps the whole step is one CUDA graph, the DNN head and the scatter plan run on "
+                        "side streams next to the RAT-block kernels and those start their prologue under the previous kernel "
+                        "(programmatic dependent launch), so the entries add up to more than ms_per_step",
         "reference_derived": {"note": "BASELINE.md derived (not published) reference-GPU numbers, unknown GPU, incl. dataloader",
                               "train_samples_per_s": {"kkbox": 8800, "ml": 52000, "tmall": 3300}[S],
                               "infer_samples_per_s": {"kkbox": 37500, "ml": 110000, "tmall": 22900}[S]},

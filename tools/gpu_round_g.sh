@@ -1,0 +1,14 @@
+#!/bin/bash
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_api.py -x -q -m gpu > gpurun_out/g_pytest_api.log 2>&1
+echo "api suite rc=$?"; tail -3 gpurun_out/g_pytest_api.log
+timeout 900 python bench.py > gpurun_out/g_bench.json 2> gpurun_out/g_bench.err
+echo "bench rc=$?"
+python - <<'PY'
+import json
+d = json.loads(open("gpurun_out/g_bench.json").read().strip().splitlines()[-1])
+print(d["value"], d["ms_per_step"], "e2e", d["e2e"]["value"], "serial", d["e2e"]["serial"]["value"], "infer", d["infer"]["value"], d["infer"]["e2e"]["value"], "launches", d["gpu_launches"])
+for k, v in d["kernels"].items(): print(f"  {k:28s} {v['calls_per_step']:3d} {v['ms_per_step']:.4f}")
+for k in ("roofline", "roofline_gather", "roofline_scatter"): print(k, d[k]["frac"], d[k]["avg_launch_ms"], d[k]["traffic"])
+PY

@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(256) k_gather(GatherArgs a) {
 template <int VW, bool SHARDED, int U>
 __global__ void __launch_bounds__(320, 4) k_gather_flat(GatherArgs a, int NC, int RPB, int RB, int SROWS, int main_blocks,
                                                      FastDiv divT) {
+    pdl_launch_dependents();        // the first attention kernel may stage its weight images under this kernel's tail (common.cuh)
     const int nrows = a.B * a.T;
     if ((int)blockIdx.x >= main_blocks) {
         // ---- LR_Layer (shallow.py:37-38): one warp per target row, lane l owns id column l, sum in field order
@@ -303,6 +304,7 @@ __global__ void k_strided_copy(const float* __restrict__ src, float* __restrict_
 // the last RAT block scattered back into the full [B,T,N,D] block gradient, which it also zero-fills (no separate memset)
 template <int VW>
 __global__ void k_expand_rows(const float* __restrict__ src, float* __restrict__ dst, long long rows, int DV, int group) {
+    pdl_launch_dependents();
     const long long total = rows * group * DV;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long row = i / DV;
