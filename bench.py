@@ -217,7 +217,7 @@ def run_ours(a):
     # host wire-format batches (pinned) for the e2e leg: disjoint rows per step and rank
     rng = np.random.default_rng(1234 + rank)
     host_batches = []
-    for i in range(n_steps_total + 1):            # one more: every timed e2e step stages the NEXT step's batch
+    for i in range(n_steps_total):
         rows = rng.integers(0, a.pool_rows, size=B)
         X, y, v, l = shapes.host_wire_batch(pool, pool, nbr, rows)
         host_batches.append(tuple(torch.from_numpy(t).pin_memory() for t in (X, y, v, l)))
@@ -236,24 +236,10 @@ def run_ours(a):
     clocks = sampler.stop() if sampler else None
     model._engine.check_errors()
 
-    def e2e_train_serial(i):                      # copy, step and loss read strictly one after the other
+    def e2e_train(i):
         loss = model.train_step(host_batches[i])
         return float(loss.item())                 # device -> host read of the step's result
-    t_e2e_serial = timed(e2e_train_serial, a.steps, a.warmup, dist)
-
-    staged = {}
-    def e2e_train(i):
-        # the public training loop (BaseModel.train_one_epoch): batch i+1's pinned host -> device copy is started on the
-        # model's copy stream (stage_batch) before step i is enqueued, so every step still performs exactly one H2D copy
-        # of h2d bytes inside the timed region, overlapped with compute; the loss is read back every step
-        cur = staged.pop(i, None)
-        if cur is None:
-            cur = model.stage_batch(host_batches[i])
-        staged[i + 1] = model.stage_batch(host_batches[i + 1])
-        loss = model.train_step(cur)
-        return float(loss.item())                 # device -> host read of the step's result
     t_e2e = timed(e2e_train, a.steps, a.warmup, dist)
-    staged.clear()
 
     model.eval()
     with torch.no_grad():
@@ -425,11 +411,7 @@ def run_ours(a):
                    "vocab_scale": a.vocab_scale,
                    "l2": "every step uses a new batch; per-step working set (~660 MB activations) exceeds the 126 MB L2"},
         "e2e": {"value": round(a.steps * gB / t_e2e, 1), "unit": "samples/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": 4,
-                "api": "fuxictr.pytorch.models.RAT_m2: stage_batch(host f64 wire batch i+1) ; train_step(batch i) ; loss.item() -- "
-                       "the loop of BaseModel.train_one_epoch: one pinned H2D copy per step on the copy stream, under the step",
-                "serial": {"value": round(a.steps * gB / t_e2e_serial, 1), "unit": "samples/s",
-                           "api": "train_step(host f64 wire batch) ; loss.item(): copy, step and read strictly in sequence"}},
+                "d2h_bytes_per_step": 4, "api": "fuxictr.pytorch.models.RAT_m2.train_step(host f64 wire batch)"},
         "infer": {"value": round(a.steps * gB / t_inf, 1), "unit": "samples/s",
                   "ms_per_step": round(t_inf / a.steps * 1e3, 4),
                   "e2e": {"value": round(a.steps * gB / t_e2e_inf, 1), "unit": "samples/s", "h2d_bytes_per_step": h2d,

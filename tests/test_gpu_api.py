@@ -210,40 +210,3 @@ def test_dropout_training_is_statistically_sane(tmp_path):
     assert np.isfinite(losses).all()
     assert np.mean(losses[-5:]) < np.mean(losses[:5])
 
-
-def test_staged_batches_equal_direct_batches(tmp_path):
-    """BaseModel.stage_batch (host -> device copy of the NEXT batch on the copy stream, the loop of train_one_epoch) must not
-    change anything: two identically initialised models, one fed host batches directly, one fed one-batch-ahead staged
-    batches from pinned memory, produce bit-identical losses, predictions and weights over 6 steps (eager + graph replays)."""
-    from fuxictr.pytorch import models
-    from rat_native import shapes
-    fm = shapes.make_feature_map("kkbox", vocab_scale=0.01, data_dir=str(tmp_path))
-    # dropout off: the keep-masks are a function of the library's device-side step counter, which two models would share
-    params = shapes.model_params("kkbox", K=5, gpu=0, model_root=str(tmp_path / "exps"), emb_dropout=0.0)
-    os.makedirs(os.path.join(params["model_root"], fm.dataset_id), exist_ok=True)
-    pool = shapes.synthetic_array(fm.feature_specs, 3000, seed=5)
-    nbr = shapes.synthetic_neighbours(3000, 3000, 5, seed=5)
-    batches = []
-    for i in range(7):
-        rows = np.arange(i * 128, (i + 1) * 128) % 3000
-        batches.append(tuple(torch.from_numpy(t).pin_memory() for t in shapes.host_wire_batch(pool, pool, nbr, rows)))
-    a = models.RAT_m2(fm, **params)
-    b = models.RAT_m2(fm, **params)
-    b.load_state_dict(a.state_dict())
-    a.train(); b.train()
-    la, lb = [], []
-    nxt = b.stage_batch(batches[0])
-    for i in range(6):
-        la.append(float(a.train_step(batches[i])))
-        cur, nxt = nxt, b.stage_batch(batches[i + 1])
-        lb.append(float(b.train_step(cur)))
-    assert la == lb
-    sa, sb = a.state_dict(), b.state_dict()
-    for k in sa:
-        assert torch.equal(sa[k], sb[k]), k
-    a.eval(); b.eval()
-    with torch.no_grad():
-        pa = a.forward(batches[6])["y_pred"].clone()
-        pb = b.forward(b.stage_batch(batches[6]))["y_pred"].clone()
-    assert torch.equal(pa, pb)
-    assert b.stage_batch(nxt) is nxt                       # idempotent on staged / device batches

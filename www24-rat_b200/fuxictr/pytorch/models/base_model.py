@@ -24,16 +24,7 @@ from rat_native.engine import EngineSpec, FeatureSpec, RatEngine
 from ...metrics import evaluate_metrics
 from ...utils import Monitor
 from ..data_generator import DeviceBatch
-
 from ..torch_utils import get_device, l2_lambda
-
-
-class StagedBatch:
-    """A wire-format batch whose host -> device copy is in flight on the model's copy stream (BaseModel.stage_batch)."""
-    __slots__ = ("X", "y", "ready", "host")
-
-    def __init__(self, X, y, ready, host):
-        self.X, self.y, self.ready, self.host = X, y, ready, host
 
 
 class _FusedAdamHandle(object):
@@ -246,35 +237,8 @@ class BaseModel(nn.Module):
         raise NotImplementedError("task={} is not supported.".format(task))
 
     # ------------------------------------------------------------------ batches
-    def stage_batch(self, inputs):
-        """Start the host -> device copy of a wire-format batch (X [B,1+K,F], y, retrieved_values, retrieved_lens; pinned
-        host tensors copy asynchronously) on a copy stream and return a StagedBatch that train_step / forward accept in
-        place of `inputs`.  Staging batch i+1 before calling train_step on batch i hides the copy (3.5 MB of float64 ids
-        at the kkbox shape) under the step; train_one_epoch does this for host generators.  The reference copies inside
-        train_step (inputs_to_device, base_model.py:125-133) behind a DataLoader with 3 prefetching workers."""
-        if isinstance(inputs, (DeviceBatch, StagedBatch)):
-            return inputs
-        X, y = inputs[0], inputs[1]
-        if getattr(self, "_copy_stream", None) is None:
-            self._copy_stream = torch.cuda.Stream(device=self.device)
-        with torch.cuda.stream(self._copy_stream):
-            Xd = X.to(self.device, dtype=torch.float64, non_blocking=True)
-            yd = y.to(self.device, dtype=torch.float64, non_blocking=True)
-            ready = torch.cuda.Event()
-            ready.record(self._copy_stream)
-        return StagedBatch(Xd, yd, ready, inputs)
-
     def _load_batch(self, inputs, training):
         e = self._engine
-        if isinstance(inputs, StagedBatch):
-            main = torch.cuda.current_stream()
-            main.wait_event(inputs.ready)
-            inputs.X.record_stream(main)                    # allocated on the copy stream, consumed here
-            inputs.y.record_stream(main)
-            assert inputs.X.ndim == 3, "retrieval augmented mode requires input_shape like [Bx(1+K)xF]"
-            self.batch_size = inputs.y.size(0)
-            ws = e.load_wire(inputs.X, inputs.y, training)
-            return ws, inputs.X.shape[0], inputs.X.shape[1]
         if isinstance(inputs, DeviceBatch):
             g = inputs.gen
             B, T = inputs.size, g.K + 1
@@ -392,18 +356,9 @@ class BaseModel(nn.Module):
     def train_one_epoch(self, data_generator, epoch):
         self.train()
         loss_acc = torch.zeros((), device=self.device)      # accumulated on the device: one host read per epoch
-        it = iter(data_generator)
-        nxt = next(it, None)
-        nxt = self.stage_batch(nxt) if nxt is not None else None
-        batch_index = 0
-        while nxt is not None:
-            cur = nxt
-            nxt = next(it, None)
-            if nxt is not None:
-                nxt = self.stage_batch(nxt)                 # the next batch's host -> device copy runs under this step
-            loss_acc += self.train_step(cur)
+        for batch_index, batch_data in enumerate(data_generator):
+            loss_acc += self.train_step(batch_data)
             self.on_batch_end(batch_index)
-            batch_index += 1
             if self._stop_training:
                 break
         self._engine.check_errors()
