@@ -212,13 +212,14 @@ int rat_head_bwd(const float* dlogit, int B, const float* enc, long long enc_str
                  float* g_fc_b, const float* h_last, int K, const float* w_final, float* g_final_w, float* g_final_b,
                  float* dh_last, void* stream);
 /* logit = fc(enc[b,0,0,:]) + dnn_out[b] + lr_out[b]; y_pred = sigmoid; BCE(mean, log clamp -100) and, when dlogit
- * is non-NULL, dlogit[b] = dBCE/dlogit * inv_count and denc[b,0,0,:] = dlogit[b]*fc_w (denc pre-zeroed by the
- * caller).  Replaces RAT_m2.py:138-150 + BaseModel.add_loss (base_model.py:74-77).  loss_part: double
- * [rat_head_blocks(B)] scratch. */
+ * is non-NULL, dlogit[b] = dBCE/dlogit * inv_count and denc[b,0,0,:] = dlogit[b]*fc_w (the other tokens of denc are the
+ * caller's business).  Replaces RAT_m2.py:138-150 + BaseModel.add_loss (base_model.py:74-77).  One warp per sample, D <= 128.
+ * loss_part: double [2 * rat_head_blocks(B)] scratch.  denc_amax (device float, may be NULL): receives max|denc| -- the seed
+ * of the fp16 mode's gradient-scale chain (K5) -- as a plain store (max|dlogit| * max|fc_w|, exact), no caller zeroing. */
 int rat_head_blocks(int B);
 int rat_head(const float* enc, long long enc_stride, const float* fc_w, const float* fc_b, const float* dnn_out,
              const float* lr_out, const float* y_true, int B, int D, float* y_pred, float* dlogit, float* denc,
-             float inv_count, double* loss_part, float* loss_sum, float* loss_mean, void* stream);
+             float inv_count, double* loss_part, float* loss_sum, float* loss_mean, float* denc_amax, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * K5: fused RAT block (backward).  Replace autograd's reverse of RAT_m2.py:155-236 (loss.backward(),

@@ -304,12 +304,13 @@ def test_bn_act_backward_matches_autograd(rn):
     assert_close("bn dbeta", db, beta.grad, 1e-4, 1e-4)
 
 
-@pytest.mark.parametrize("rows,C,drop", [(4096, 400, 0.0), (1000, 77, 0.0), (2048, 400, 0.2), (37, 32, 0.0)])
+@pytest.mark.parametrize("rows,C,drop", [(4096, 400, 0.0), (1000, 77, 0.0), (2048, 400, 0.2), (37, 32, 0.0), (8200, 48, 0.1)])
 def test_bn_fused_cluster_kernels_match_split_kernels_and_autograd(rn, rows, C, drop):
     """csrc/mlp_fused.cu: rat_bn_act_fwd_train / rat_bn_act_bwd_fused (one thread-block cluster per 32-column slab, partials
     through distributed shared memory) against the split kernels they replace (same formulas; only the association of the
     double column sums differs) and, without dropout, against torch autograd of BatchNorm1d(train) + ReLU incl. the bias
-    gradient of the Linear in front (= colsum(dz)).  Ragged shapes (rows not a multiple of 8 * 16, C not a multiple of 32)."""
+    gradient of the Linear in front (= colsum(dz)).  Ragged shapes (rows not a multiple of 8 * 16, C not a multiple of 32);
+    8 / 32 rows per thread held in registers, and the generic two-pass form (more than 4096 rows)."""
     from tests.gpu_util import assert_close
     torch.manual_seed(rows + C)
     d, st = DEV, rn.current_stream()

@@ -367,3 +367,37 @@ def test_eval_forward_full_width_vs_oracle(rn, precision, shape, B, K):
     enc = ws["enc_out"]                 # [B,T,N,D], or [B,T,D] (field token 0 only) from RAT_m2's last block
     assert_close("pooled", enc[:, 0, 0, :] if enc.ndim == 4 else enc[:, 0, :], parts["pooled"], *ptol(3e-4, 3e-5 * float(parts["pooled"].abs().max()), rt=2e-2, at_scale=150.0))
     assert_close("y_pred", y_pred, want[:, 0], *((2e-4, 2e-5) if precision == "fp32" else (0.0, 3e-3)))
+
+
+@pytest.mark.parametrize("B,D,stride", [(4096, 40, 40 * 14 * 6), (300, 10, 10), (7, 128, 130)])
+def test_head_kernel_matches_torch(rn, B, D, stride):
+    """rat_head (one warp per sample): sigmoid(fc(pooled) + dnn + lr), BCE with the -100 log clamp, dlogit, denc and the
+    stored max|denc| (= max|dlogit| * max|fc.weight|, exact) vs float64 torch."""
+    from tests.gpu_util import assert_close
+    torch.manual_seed(B + D)
+    d, st = _dev(), rn.current_stream()
+    enc = torch.randn(B, stride, device=d)
+    w, b = torch.randn(D, device=d) * 0.3, torch.randn(1, device=d)
+    dnn, lr = torch.randn(B, device=d), torch.randn(B, device=d) * 0.1
+    y = (torch.rand(B, device=d) < 0.4).float()
+    y_pred, dlogit = torch.empty(B, device=d), torch.empty(B, device=d)
+    denc = torch.zeros(B, stride, device=d)
+    nb = int(rn.query("rat_head_blocks", B))
+    part = torch.empty(2 * nb, dtype=torch.float64, device=d)
+    loss = torch.empty(2, device=d)
+    amax = torch.full((1,), -1.0, device=d)
+    rn.call("rat_head", enc, stride, w, b, dnn, lr, y, B, D, y_pred, dlogit, denc, 1.0 / B, part, loss[0:1], loss[1:2], amax, st)
+    logit = (enc[:, :D].double() @ w.double()) + b.double() + dnn.double() + lr.double()
+    p = torch.sigmoid(logit)
+    assert_close("y_pred", y_pred, p.float(), 1e-5, 1e-6)
+    bce = -(y.double() * torch.log(p).clamp_min(-100) + (1 - y.double()) * torch.log(1 - p).clamp_min(-100))
+    assert_close("loss sum", loss[0:1], bce.sum().float().view(1), 1e-5, 1e-5)
+    assert_close("loss mean", loss[1:2], bce.mean().float().view(1), 1e-5, 1e-6)
+    assert_close("dlogit", dlogit, ((p - y.double()) / B).float(), 1e-4, 1e-9)
+    assert torch.equal(denc[:, :D], dlogit[:, None] * w[None, :])
+    assert float(denc[:, D:].abs().max()) == 0.0 if stride > D else True
+    assert float(amax) == float(denc.abs().max())
+    # eval form: no labels, no gradient outputs
+    y2 = torch.empty(B, device=d)
+    rn.call("rat_head", enc, stride, w, b, None, None, None, B, D, y2, None, None, 1.0, None, None, None, None, st)
+    assert_close("y_pred (no dnn / lr)", y2, torch.sigmoid(enc[:, :D].double() @ w.double() + b.double()).float(), 1e-5, 1e-6)

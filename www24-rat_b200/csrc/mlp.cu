@@ -268,6 +268,9 @@ __global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ A, int
 
 // ---- head: logit = fc(enc[b,0,0,:]) + dnn_out + lr ; sigmoid ; BCE ; dlogit ---------------------------------
 // F.binary_cross_entropy clamps log() at -100 and its backward divides by max(y(1-y),1e-12); sigmoid' = y(1-y).
+// One WARP per sample (lane = model column, D <= 128): the pooled-token rows are B strided 160-byte reads, which a
+// thread-per-sample kernel (16 blocks at B = 4096) turns into a 14 us latency chain between the forward and the backward.
+// loss_part [2 * gridDim.x] doubles: per-block BCE sums, then per-block max |dlogit| (for max|denc| = max|dlogit| max|fc_w|).
 __global__ void __launch_bounds__(256) k_head(const float* __restrict__ enc, long long enc_stride,
                                               const float* __restrict__ fc_w, const float* __restrict__ fc_b,
                                               const float* __restrict__ dnn_out, const float* __restrict__ lr_out,
@@ -276,46 +279,73 @@ __global__ void __launch_bounds__(256) k_head(const float* __restrict__ enc, lon
                                               float* __restrict__ denc, float inv_count,
                                               double* __restrict__ loss_part) {
     __shared__ double red[8];
+    __shared__ float gred[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) w[q] = lane + 32 * q < D ? fc_w[lane + 32 * q] : 0.f;
+    const float bias = fc_b[0];
     double lsum = 0.0;
-    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < Bn; b += gridDim.x * blockDim.x) {
+    float gmax = 0.f;
+    for (int b = blockIdx.x * 8 + warp; b < Bn; b += gridDim.x * 8) {
         const float* e = enc + (size_t)b * enc_stride;
-        float logit = fc_b[0];
-        for (int d = 0; d < D; ++d) logit = fmaf(e[d], fc_w[d], logit);
+        float s = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (lane + 32 * q < D) s = fmaf(e[lane + 32 * q], w[q], s);
+        float logit = warp_sum(s) + bias;                   // xor butterfly: the same bits in every lane
         if (dnn_out) logit += dnn_out[b];
         if (lr_out) logit += lr_out[b];
         const float y = 1.0f / (1.0f + expf(-logit));
-        y_pred[b] = y;
+        if (lane == 0) y_pred[b] = y;
         if (y_true) {
             const float t = y_true[b];
             const float l1 = fmaxf(logf(y), -100.f), l0 = fmaxf(logf(1.0f - y), -100.f);
-            lsum += -(double)(t * l1 + (1.0f - t) * l0);
+            if (lane == 0) lsum += -(double)(t * l1 + (1.0f - t) * l0);
             if (dlogit) {
                 const float yy = y * (1.0f - y);
                 const float g = (y - t) / fmaxf(yy, 1e-12f) * yy * inv_count;
-                dlogit[b] = g;
+                if (lane == 0) dlogit[b] = g;
+                gmax = fmaxf(gmax, fabsf(g));
                 if (denc) {
                     float* de = denc + (size_t)b * enc_stride;
-                    for (int d = 0; d < D; ++d) de[d] = g * fc_w[d];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (lane + 32 * q < D) de[lane + 32 * q] = g * w[q];
                 }
             }
         }
     }
-    lsum = warp_sum_d(lsum);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lsum;
+    if (lane == 0) { red[warp] = lsum; gred[warp] = gmax; }
     __syncthreads();
     if (threadIdx.x == 0 && loss_part) {
         double s = 0.0;
-        for (int i = 0; i < 8; ++i) s += red[i];
+        float m = 0.f;
+        for (int i = 0; i < 8; ++i) { s += red[i]; m = fmaxf(m, gred[i]); }
         loss_part[blockIdx.x] = s;
+        loss_part[gridDim.x + blockIdx.x] = (double)m;
     }
 }
+// one warp: block partials in a fixed order (lane-strided, then the xor butterfly) => deterministic
 __global__ void k_loss_finalize(const double* __restrict__ part, int n, float inv_count, float* __restrict__ loss_sum,
-                                float* __restrict__ loss_mean) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double s = 0.0;
-        for (int i = 0; i < n; ++i) s += part[i];
+                                float* __restrict__ loss_mean, const float* __restrict__ fc_w, int D,
+                                float* __restrict__ denc_amax) {
+    const int lane = threadIdx.x;
+    double s = 0.0, m = 0.0;
+    for (int i = lane; i < n; i += 32) { s += part[i]; m = fmax(m, part[n + i]); }
+    s = warp_sum_d(s);
+    float wm = 0.f;
+    for (int d = lane; d < D; d += 32) wm = fmaxf(wm, fabsf(fc_w[d]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+    }
+    if (lane == 0) {
         if (loss_sum) loss_sum[0] = (float)s;
         if (loss_mean) loss_mean[0] = (float)(s * (double)inv_count);
+        // denc[b][d] = dlogit[b] * fc_w[d] and float rounding is monotonic: max |denc| == max|dlogit| * max|fc_w| exactly
+        if (denc_amax) denc_amax[0] = (float)m * wm;
     }
 }
 
@@ -542,20 +572,21 @@ extern "C" int rat_colsum(const float* A, int rows, int C, int lda, float* out, 
     return RAT_OK;
 }
 
-extern "C" int rat_head_blocks(int B) { return min(ceil_div(B, 256), 1024); }
+extern "C" int rat_head_blocks(int B) { return min(ceil_div(B, 8), 2 * num_sms()); }
 
 extern "C" int rat_head(const float* enc, long long enc_stride, const float* fc_w, const float* fc_b,
                         const float* dnn_out, const float* lr_out, const float* y_true, int B, int D, float* y_pred,
                         float* dlogit, float* denc, float inv_count, double* loss_part, float* loss_sum,
-                        float* loss_mean, void* stream) {
-    RAT_REQUIRE(B > 0 && D > 0, "rat_head: bad shape");
+                        float* loss_mean, float* denc_amax, void* stream) {
+    RAT_REQUIRE(B > 0 && D > 0 && D <= 128, "rat_head: bad shape B=%d D=%d (D <= 128)", B, D);
+    RAT_REQUIRE(denc_amax == nullptr || (loss_part && denc), "rat_head: denc_amax needs loss_part and denc");
     const int grid = rat_head_blocks(B);
     cudaStream_t st = (cudaStream_t)stream;
     k_head<<<grid, 256, 0, st>>>(enc, enc_stride, fc_w, fc_b, dnn_out, lr_out, y_true, B, D, y_pred, dlogit, denc,
                                  inv_count, loss_part);
     RAT_CHECK_LAUNCH("k_head");
-    if (loss_part && (loss_sum || loss_mean)) {
-        k_loss_finalize<<<1, 32, 0, st>>>(loss_part, grid, 1.0f / (float)B, loss_sum, loss_mean);
+    if (loss_part && (loss_sum || loss_mean || denc_amax)) {
+        k_loss_finalize<<<1, 32, 0, st>>>(loss_part, grid, 1.0f / (float)B, loss_sum, loss_mean, fc_w, D, denc_amax);
         RAT_CHECK_LAUNCH("k_loss_finalize");
     }
     return RAT_OK;

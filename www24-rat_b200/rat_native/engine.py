@@ -366,6 +366,7 @@ class RatEngine:
                                             # only sees direct C-ABI calls)
         self._graphs: Dict[tuple, object] = {}
         self.amax = torch.zeros(256, dtype=torch.float32, device=self.device)
+        self.denc_amax = torch.zeros(1, dtype=torch.float32, device=self.device)     # written by rat_head every training step
         self._amax_next = 0
         self._amax_of = {}
         self._amax_on = False
@@ -426,7 +427,7 @@ class RatEngine:
             x_emb=torch.empty(B, F * D, **f32),
             lr_out=torch.empty(B, **f32) if s.use_wide else None,
             y_pred=torch.empty(B, **f32),
-            loss_part=torch.empty(int(query("rat_head_blocks", B)), dtype=torch.float64, device=dev),
+            loss_part=torch.empty(2 * int(query("rat_head_blocks", B)), dtype=torch.float64, device=dev),
             loss=torch.zeros(2, **f32),
             dnn_out=torch.empty(B, **f32) if len(s.dnn_hidden_units) else None,
         )
@@ -471,7 +472,8 @@ class RatEngine:
             if nb == 0:
                 raise RuntimeError("RAT backward kernels: tile does not fit in shared memory for this shape")
             ws["bwd_ws"] = torch.empty(nb // 4 + 4, **f32)
-            ws["bwd_ws2"] = torch.empty(nb // 4 + 4, **f32)    # second record buffer: deferred reductions (_bwd_ws)
+            if self._defer_reduce():                               # second record buffer: deferred reductions (_bwd_ws)
+                ws["bwd_ws2"] = torch.empty(nb // 4 + 4, **f32)
             sb = int(query("rat_emb_scatter_workspace_bytes", B * T * (L + 1), D))
             ws["scatter_ws"] = torch.empty(sb // 4 + 4, dtype=torch.int32, device=dev)
         self._ws[key] = ws
@@ -713,7 +715,7 @@ class RatEngine:
              ws["y_true"] if want_loss else None, B, D, ws["y_pred"], ws.get("dlogit") if training else None,
              ws.get("denc") if training else None, float(inv_count if inv_count else 1.0 / B),
              ws["loss_part"] if want_loss else None, ws["loss"][0:1] if want_loss else None,
-             ws["loss"][1:2] if want_loss else None, st)
+             ws["loss"][1:2] if want_loss else None, self.denc_amax if training else None, st)
         return ws["y_pred"]
 
     def check_errors(self):
@@ -768,7 +770,8 @@ class RatEngine:
         """record workspace of the next backward kernel.  With deferred reductions (rat_set_reduce_stream) two buffers
         alternate: the reduction of call i reads one while the kernel of call i+1 writes the other."""
         self._bwd_flip = not getattr(self, "_bwd_flip", False)
-        return ws["bwd_ws2"] if (self._bwd_flip and self._defer_reduce()) else ws["bwd_ws"]
+        alt = ws.get("bwd_ws2")
+        return alt if (alt is not None and self._bwd_flip and self._defer_reduce()) else ws["bwd_ws"]
 
     def _defer_reduce(self) -> bool:
         return os.environ.get("RAT_DEFER_REDUCE", "0") == "1"     # measured: no gain (DESIGN.md section 3), off
@@ -919,9 +922,8 @@ class RatEngine:
         self._last_bwd = (ws, B, T)
         self._amax_reset()
         # d(loss)/d(encoder output) is non-zero only in the pooled token [b,0,0,:] (written by rat_head)
-        slot = self._amax_out(ws["denc"])
-        if slot is not None:
-            call("rat_absmax", ws["denc"], B, D, ws["enc_stride"], slot, st)
+        if self._amax_on:               # max|denc| was stored by rat_head itself (max|dlogit| * max|fc.weight|)
+            self._amax_of[ws["denc"].data_ptr()] = self.denc_amax
         # fc + final Linear(K -> 1) of the DNN: every gradient that hangs off dlogit, one launch
         has_dnn = len(s.dnn_hidden_units) > 0
         if has_dnn:
