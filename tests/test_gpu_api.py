@@ -210,3 +210,45 @@ def test_dropout_training_is_statistically_sane(tmp_path):
     assert np.isfinite(losses).all()
     assert np.mean(losses[-5:]) < np.mean(losses[:5])
 
+
+def test_csv_branch_end_to_end(tmp_path):
+    """run_expid.py's csv branch (:53-72) on synthetic kkbox-like csv files: datasets.kkbox.FeatureEncoder -> build_dataset
+    (feature_map.json, train / valid / test / retrieval_pool id blocks) -> h5_generator (BM25 pre-retrieval on the GPU, no cached
+    retrieval files) -> RAT_m2(feature_map) -> fit_generator -> evaluate_generator."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden_encoder as G
+    from fuxictr import datasets
+    from fuxictr.pytorch import models
+    from fuxictr.pytorch.torch_utils import seed_everything
+    from rat_native import shapes
+    case = "kkbox_pool_ratio"
+    module, cols, args = G.write_case_csvs(case, str(tmp_path / "csv"))
+    used = ["msno", "song_id", "city", "isrc", "bd"]
+    params = shapes.model_params("kkbox", K=3, gpu=0, model_root=str(tmp_path / "exps"), data_root=str(tmp_path / "data"),
+                                 data_format="csv", batch_size=64, epochs=1, shuffle=True, num_workers=0,
+                                 dnn_hidden_units=[32, 16], embedding_regularizer=1e-6, version="pytorch",
+                                 feature_cols=cols, label_col=dict(G.LABEL), **args)
+    params["dataset_id"] = case
+    params["retrieval_configs"] = dict(params["retrieval_configs"], used_cols=used, exact_match_cols=[], label_wise=False,
+                                       pre_retrieval=True, enable_clean=False, qry_batch_size=128, db_chunk_size=1000,
+                                       device="cuda:0", topK=3)
+    seed_everything(seed=params["seed"])
+    enc = getattr(datasets, module).FeatureEncoder(**params)
+    assert not os.path.exists(enc.json_file)
+    datasets.build_dataset(enc, **params)
+    data_dir = os.path.join(params["data_root"], case)
+    params["train_data"] = os.path.join(data_dir, "train*.h5")
+    params["valid_data"] = os.path.join(data_dir, "valid*.h5")
+    params["test_data"] = os.path.join(data_dir, "test*.h5")
+    params["retrieval_configs"]["retrieval_pool_data"] = os.path.join(data_dir, "retrieval_pool.h5")
+    feature_map = enc.feature_map
+    assert feature_map.num_fields == 7 and feature_map.input_length == 3 + 3 + feature_map.feature_specs["artist_name"]["max_len"] + 2
+    train_gen, valid_gen = datasets.h5_generator(feature_map, stage="train", **params)
+    test_gen = datasets.h5_generator(feature_map, stage="test", **params)
+    assert train_gen.num_samples == 480 and valid_gen.num_samples == 150 and test_gen.num_samples == 150
+    model = getattr(models, params["model"])(feature_map, **params)
+    model.fit_generator(train_gen, validation_data=valid_gen, **params)
+    res = model.evaluate_generator(test_gen)
+    assert set(res) == {"AUC", "logloss"} and np.isfinite(res["logloss"]) and 0.0 <= res["AUC"] <= 1.0
+    model._engine.check_errors()
