@@ -1,5 +1,6 @@
-// Shared device helpers of the tcgen05 RAT-block kernels (encoder_tc_*.cu): bf16 operand staging in the UMMA canonical
-// layout, ldmatrix / mma.sync bf16 fragments, the register-resident weight-gradient jobs, fast exact-erf GELU.
+// Shared device helpers of the tcgen05 RAT-block kernels (encoder_tc_*.cu): 16-bit operand staging (fp16 by default, bf16 with
+// RAT_TC_FP16=0; "bf16" in older comments below means "the 16-bit operand type") in the UMMA canonical layout, ldmatrix /
+// mma.sync fragments, the register-resident weight-gradient jobs, fast exact-erf GELU.
 #pragma once
 #include "tile.cuh"
 #include "encoder_common.cuh"

@@ -1,12 +1,12 @@
 // K3 (Blackwell path): dense GEMM of the DNN head on the 5th-generation tensor cores.
 //
-//   C[m][n] = sum_k opA(m,k) * opB(k,n) (+ bias[n])       fp32 in / fp32 out, bf16 operands, fp32 accumulate in TMEM
+//   C[m][n] = sum_k opA(m,k) * opB(k,n) (+ bias[n])       fp32 in / fp32 out, fp16 operands (bf16 with RAT_TC_FP16=0), fp32 accumulate in TMEM
 //
 // Replaces the nn.Linear products of MLP_Layer (fuxictr/pytorch/layers/deep.py:126-137) and their autograd reverse:
 //   forward   z  = h W^T + b        opA = h  [B x K]  (K contiguous)   opB = W  [N x K]  (K contiguous)
 //   dgrad     dh = dz W             opA = dz [B x u]  (K contiguous)   opB = W  [u x Kin] (rows = reduction index)
 //   wgrad     dW = dz^T h           opA = dz [B x u]  (rows = reduction index), opB = h [B x Kin] (rows = reduction index)
-// A source tile [rows x cols] is always staged the same way -- converted to bf16 and written chunk-major
+// A source tile [rows x cols] is always staged the same way -- converted to the 16-bit operand type and written chunk-major
 // ([col/8][row][16 B], tc5.cuh) -- and only the UMMA descriptor changes: an operand whose rows are M/N indices is
 // "K-major" (LBO = rows*16, SBO = 128); an operand whose rows are the reduction index is "MN-major" (the same
 // 128-byte core matrices read as [k%8][mn%8]: LBO = 128, SBO = rows*16, major bit set).  No transposed copies.

@@ -463,7 +463,7 @@ extern "C" int rat_sgemm_scaled(const float* A, const float* B, float* C, const 
         RAT_CHECK_LAUNCH("k_outer");
         return RAT_OK;
     }
-    if (precision_mode() == 2) {        // tcgen05 path (bf16 operands, fp32 accumulate); tiny shapes stay on the SIMT kernel
+    if (precision_mode() == 2) {        // tcgen05 path (fp16 operands, fp32 accumulate); tiny shapes stay on the SIMT kernel
         int tc_splits = 1;
         const int rc = gemm_tc_dispatch(A, B, C, bias, M, N, K, lda, ldb, ldc, trans_a, trans_b, a_amax, workspace, workspace_bytes,
                                         &tc_splits, (cudaStream_t)stream);
