@@ -1,8 +1,9 @@
 // K3/K4: DNN head (MLP_Layer fuxictr/pytorch/layers/deep.py:108-141), BatchNorm1d, ReLU, dropout,
 // fc + LR + sigmoid + BCE (RAT_m2.py:144-150, base_model.py:74-77) and their backward.
 //
-// Round-1 implementation: fp32 SIMT shared-memory-tiled GEMM (exact fp32 parity anchor).  The tcgen05/TMEM
-// bf16 variant of the same entry point is planned on top of this (see DESIGN.md "K3").
+// k_sgemm is the fp32 SIMT shared-memory-tiled GEMM (exact fp32 parity anchor and tf32-mode path); in the default fp16
+// tensor-core mode rat_sgemm dispatches to the tcgen05 / TMEM kernel of gemm_tc.cu.  The single-launch BatchNorm /
+// head-gradient cluster kernels live in mlp_fused.cu; the split BatchNorm kernels here remain the eval path and the fallback.
 #include <algorithm>
 #include "common.cuh"
 #include "../../include/rat_b200.h"
