@@ -874,10 +874,7 @@ class RatEngine:
         units = list(s.dnn_hidden_units)
         gw = ws["gemm_ws"]
         gwb = gw.numel() * 4
-        dlogit = ws["dlogit"]
-        K = units[-1]
-        h_last = ws["h"][-1]
-        # final Linear(K -> 1): done by rat_head_bwd (backward) together with the fc gradients
+        # the final Linear(K -> 1) is handled by rat_head_bwd (backward()) together with the fc gradients: dh[-1] is ready
         count = float(B * self.world)
         fused = self._dnn_fused()
         for li in reversed(range(len(units))):
