@@ -71,6 +71,36 @@ def tmall_frame(rng, n):
     })
 
 
+def misc_frame(rng, n):
+    """numeric columns (normalizers, explicit na_value), a vocabulary shared by two id columns, a sequence that shares the
+    vocabulary of a categorical column (which therefore gets the padding row), a non-default splitter"""
+    price = rng.gamma(2.0, 10.0, size=n)
+    price[rng.random(n) < 0.05] = np.nan
+    return pd.DataFrame({
+        "label": rng.integers(0, 2, size=n),
+        "price": price,
+        "score": rng.normal(3.0, 2.0, size=n),
+        "raw": rng.integers(0, 50, size=n).astype(float),
+        "user": _rand_tokens(rng, n, 40),
+        "friend": _rand_tokens(rng, n, 55, p_nan=0.04),
+        "item": _rand_tokens(rng, n, 80, zipf=1.2),
+        "hist": _rand_seq(rng, n, 90, 6, "^", p_empty=0.08),
+        "tags": _rand_seq(rng, n, 12, 3, "^", p_empty=0.0),
+    }).assign(hist=lambda d: d["hist"].str.replace("g", "v"))      # history tokens live in the item vocabulary
+
+
+MISC_COLS = [
+    {"active": True, "dtype": "float", "name": "price", "type": "numeric", "normalizer": "StandardScaler", "na_value": 0},
+    {"active": True, "dtype": "float", "name": "score", "type": "numeric", "normalizer": "MinMaxScaler"},
+    {"active": True, "dtype": "float", "name": "raw", "type": "numeric"},
+    {"active": True, "dtype": "str", "name": "user", "type": "categorical", "embedding_dim": 8},
+    {"active": True, "dtype": "str", "name": "friend", "type": "categorical", "share_embedding": "user", "na_value": "nobody"},
+    {"active": True, "dtype": "str", "name": "item", "type": "categorical", "min_categr_count": 1},
+    {"active": True, "dtype": "str", "name": "hist", "type": "sequence", "share_embedding": "item", "splitter": "^", "max_len": 4,
+     "padding": "pre", "encoder": "MaskedAveragePooling"},
+    {"active": True, "dtype": "str", "name": "tags", "type": "sequence", "splitter": "^"},
+]
+
 KKBOX_COLS = [
     {"active": True, "dtype": "str", "name": ["msno", "song_id", "city"], "type": "categorical"},
     {"active": True, "dtype": "str", "encoder": "MaskedSumPooling", "max_len": 3, "name": "genre_ids", "type": "sequence"},
@@ -95,6 +125,7 @@ CASES = {
                                  retrieval_configs={"split_type": "10-fold", "pool_ratio": 0.2})),
     "kkbox_split_sizes": ("kkbox", kkbox_frame, KKBOX_COLS, (700, 0, 0, 0),
                           dict(min_categr_count=2, valid_size=0.1, test_size=70)),
+    "misc_features": ("kkbox", misc_frame, MISC_COLS, (400, 100, 0, 0), dict(min_categr_count=2)),
     "tmall_pool_file": ("tmall", tmall_frame, TMALL_COLS, (500, 0, 140, 300),
                         dict(min_categr_count=2, retrieval_configs={"split_type": "sequential"})),
 }

@@ -90,6 +90,14 @@ def save_hdf5(data_array, data_path, key="data"):
         np.savez(os.path.splitext(data_path)[0] + ".npz", **{key: data_array})
 
 
+def load_hdf5(data_path, key=None, verbose=True):
+    """one data block back (reference data_utils.py:46-54): `.h5` through h5py, or the `.npz` / `.npy` mirror of the same stem"""
+    from ..pytorch.data_generator import _load_array
+    if verbose:
+        logging.info("Loading data from h5: " + data_path)
+    return _load_array(data_path, key)
+
+
 def split_train_test(train_ddf=None, valid_ddf=None, test_ddf=None, valid_size=0, test_size=0, split_type="sequential"):
     """tail splits of the training frame (reference data_utils.py:1067-1088): the LAST test_size rows become the test set, the
     valid_size rows before them the validation set; sizes < 1 are fractions of the original frame; "random" shuffles the row
@@ -163,3 +171,4 @@ def build_dataset(feature_encoder, train_data=None, valid_data=None, test_data=N
 
 
 from . import kkbox, tmall  # noqa: E402  (run_expid.py: getattr(datasets, <dataset>).FeatureEncoder)
+from .data_utils import BM25_topk_retrieval_v4, BM25_topk_retrieval_v4 as BM25_topk_retrieval  # noqa: E402,F401
